@@ -1,0 +1,154 @@
+/*
+ * splashsurf_b200.h -- C ABI of the B200-native surface-reconstruction hot path.
+ *
+ * Drop-in boundary: this library replaces the body of
+ *     splashsurf_lib::reconstruct_surface_inplace::<i64, f32>()      (splashsurf_lib/src/lib.rs:340-473)
+ * i.e. everything from the particle-AABB filter through
+ *     reconstruction::reconstruct_surface_subdomain_grid()           (splashsurf_lib/src/reconstruction.rs:17-62)
+ * (decomposition -> per-subdomain neighbourhood search + SPH densities -> cubic-spline level-set splat ->
+ * per-subdomain marching cubes -> stitching), executed as CUDA kernels on sm_100a.
+ *
+ * A Rust front-end binds these symbols with `extern "C"` (see INTEGRATION.md for the stub); the Python
+ * harness in splashsurf_b200/ binds them with ctypes.  Plain pointers and sizes only -- no CUDA, torch or
+ * C++ types cross this boundary.  All entry points are thread-compatible: one context must not be used
+ * from two host threads at once (the reference has the same rule for SurfaceReconstruction workspaces,
+ * splashsurf_lib/src/workspace.rs:12-79).
+ */
+#ifndef SPLASHSURF_B200_H
+#define SPLASHSURF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SS_ABI_VERSION 1
+
+/* Error codes.  1..7 mirror ReconstructionError / GridConstructionError
+ * (splashsurf_lib/src/lib.rs:289-314, uniform_grid.rs:147-169); the reference's panics on a non-positive
+ * search radius or degenerate neighbourhood-search domain (neighborhood_search.rs:354-365) map to
+ * SS_ERR_INVALID_PARAMETER. */
+enum {
+    SS_OK = 0,
+    SS_ERR_INVALID_CELL_SIZE = 1,        /* GridConstructionError::InvalidCellSize */
+    SS_ERR_DEGENERATE_AABB = 2,          /* GridConstructionError::DegenerateAabb */
+    SS_ERR_INCONSISTENT_AABB = 3,        /* GridConstructionError::InconsistentAabb */
+    SS_ERR_INDEX_TOO_SMALL = 4,          /* IndexTypeTooSmall*: a dimension exceeds what the device path indexes */
+    SS_ERR_REAL_TOO_SMALL = 5,           /* RealTypeTooSmallDomainSize */
+    SS_ERR_INVALID_PARAMETER = 6,        /* reference: assert!/panic on bad radius, support, subdomain size */
+    SS_ERR_UNSUPPORTED = 7,              /* path not provided by this build (e.g. global hash-map path) */
+    SS_ERR_CUDA = 100,                   /* CUDA runtime failure; see ss_last_error() */
+    SS_ERR_NO_DEVICE = 101,              /* no CUDA device: the product never falls back to a CPU path */
+    SS_ERR_OUT_OF_MEMORY = 102
+};
+
+/* Mirrors splashsurf_lib::Parameters<f32> (lib.rs:158-189) + GridDecompositionParameters (lib.rs:140-145).
+ * All lengths are ABSOLUTE (the CLI / Python front-ends multiply their relative -l/-c values by the
+ * particle radius before this point: splashsurf/src/reconstruct.rs:628-629). */
+typedef struct ss_params_f32 {
+    float particle_radius;
+    float rest_density;
+    float compact_support_radius;
+    float cube_size;
+    float iso_surface_threshold;
+    int32_t has_particle_aabb;           /* Parameters::particle_aabb is Some(..) */
+    float particle_aabb_min[3];
+    float particle_aabb_max[3];
+    int32_t enable_multi_threading;      /* accepted for signature parity; the device path is always parallel */
+    int32_t enable_simd;                 /* 1: arithmetic of the reference's AVX2+FMA grid loop (its x86 default);
+                                            0: arithmetic of its scalar grid loop */
+    int32_t spatial_decomposition;       /* 0: SpatialDecomposition::None, 1: UniformGrid */
+    uint32_t subdomain_num_cubes_per_dim;
+    int32_t auto_disable;                /* GridDecompositionParameters::auto_disable */
+    int32_t global_neighborhood_list;    /* must be 0 in this build (SS_ERR_UNSUPPORTED otherwise) */
+} ss_params_f32;
+
+/* Mirrors UniformCartesianCubeGrid3d<i64, f32> (uniform_grid.rs:132-142). */
+typedef struct ss_grid_f32 {
+    float aabb_min[3];
+    float aabb_max[3];
+    float cell_size;
+    int64_t points_per_dim[3];
+    int64_t cells_per_dim[3];
+} ss_grid_f32;
+
+/* Device-side stage times of the last reconstruction on a context, in milliseconds (CUDA events).
+ * Stage names follow the reference's profiling scopes (README.md:198-231). */
+typedef struct ss_timings {
+    float upload;                /* host -> device copy of the particles (0 when the input was device memory) */
+    float aabb_and_grid;         /* "compute minimum enclosing aabb" + grid setup */
+    float decomposition;         /* "decomposition": classification, membership sort */
+    float density;               /* "compute_global_density_vector": cell lists + SPH densities */
+    float binning;               /* splat bin sort + particle records */
+    float levelset;              /* "density grid loop" over all subdomains */
+    float marching_cubes;        /* "mc triangulation loop": classify, scan, emit */
+    float stitching;             /* "stitching": boundary-vertex weld, compaction, index remap */
+    float total_device;          /* first kernel to last kernel */
+    uint64_t kernel_launches;    /* kernels of this library launched (cub passes included) */
+    uint64_t levelset_launches;  /* launches of the level-set kernel */
+    double levelset_pairs;       /* particle-gridpoint pairs evaluated inside support (work model) */
+} ss_timings;
+
+typedef struct ss_context ss_context;   /* device + stream + reusable device buffers */
+typedef struct ss_surface ss_surface;   /* result, mirrors SurfaceReconstruction<i64, f32> (lib.rs:247-262) */
+
+/* Library / ABI info. */
+int ss_abi_version(void);
+const char *ss_last_error(void);         /* thread-local message for the last non-zero return */
+
+/* Context = the reference's global rayon pool + ReconstructionWorkspace, for one GPU.
+ * device < 0 selects the current CUDA device. */
+int ss_context_create(int device, ss_context **out);
+void ss_context_destroy(ss_context *ctx);
+
+/* reconstruct_surface::<i64, f32>(particle_positions, parameters) (lib.rs:330-337).
+ * `xyz` is N x 3 AoS f32 -- the layout of &[Vector3<f32>] / a C-contiguous numpy (N,3) array -- in HOST or
+ * DEVICE memory (detected).  On success *out owns the result until ss_surface_free(). */
+int ss_reconstruct_surface_f32(ss_context *ctx, const float *xyz, uint64_t n, const ss_params_f32 *params,
+                               ss_surface **out);
+void ss_surface_free(ss_surface *s);
+
+/* grid_for_reconstruction (lib.rs:476-516) alone, for front-ends that need the grid before reconstructing. */
+int ss_grid_for_reconstruction_f32(ss_context *ctx, const float *xyz, uint64_t n, const ss_params_f32 *params,
+                                   ss_grid_f32 *grid_out);
+
+/* ---- result accessors (sizes first, then copies into caller-provided HOST buffers) ---- */
+uint64_t ss_surface_num_vertices(const ss_surface *s);
+uint64_t ss_surface_num_triangles(const ss_surface *s);
+uint64_t ss_surface_num_particles(const ss_surface *s);          /* particles after the AABB filter */
+int ss_surface_used_decomposition(const ss_surface *s);
+int ss_surface_grid(const ss_surface *s, ss_grid_f32 *grid_out);            /* SurfaceReconstruction::grid */
+int ss_surface_subdomain_grid(const ss_surface *s, ss_grid_f32 *grid_out);  /* ::subdomain_grid */
+int ss_surface_copy_vertices(const ss_surface *s, float *dst_xyz);          /* mesh.vertices, nv x 3 */
+int ss_surface_copy_triangles_u32(const ss_surface *s, uint32_t *dst);      /* mesh.triangles, nt x 3 */
+int ss_surface_copy_triangles_u64(const ss_surface *s, uint64_t *dst);      /* same, usize like the reference */
+int ss_surface_copy_particle_densities(const ss_surface *s, float *dst);    /* ::particle_densities */
+int ss_surface_copy_particle_inside_aabb(const ss_surface *s, uint8_t *dst);/* ::particle_inside_aabb (n input) */
+/* Device-resident views (valid until ss_surface_free): vertices nv x 3 f32, triangles nt x 3 u32. */
+const float *ss_surface_device_vertices(const ss_surface *s);
+const uint32_t *ss_surface_device_triangles(const ss_surface *s);
+const float *ss_surface_device_densities(const ss_surface *s);
+
+/* ---- parity taps (used by tests/; cheap, no effect on the hot path unless requested) ---- */
+/* Global MC edge carrying each vertex: (point i, j, k, axis), nv x 4 int64. */
+int ss_surface_copy_vertex_edge_keys(const ss_surface *s, int64_t *dst);
+/* Decomposition: number of non-empty subdomains, their flat indices (ascending), particle counts
+ * (owned + ghost) and the sparse flag (dense_subdomains.rs:1251, :1590). */
+uint64_t ss_surface_num_subdomains(const ss_surface *s);
+int ss_surface_copy_subdomains(const ss_surface *s, int64_t *flat, uint64_t *count, uint8_t *sparse);
+/* Request that the level-set tile ((S+1)^3 f32, i-major) of one subdomain (flat index) is kept by the next
+ * reconstruction on this context; pass -1 to disable. */
+int ss_context_keep_levelset_tile(ss_context *ctx, int64_t flat_subdomain);
+int ss_surface_copy_levelset_tile(const ss_surface *s, float *dst);
+
+/* Timings / launch counts of the reconstruction that produced `s`. */
+int ss_surface_timings(const ss_surface *s, ss_timings *out);
+
+/* Tuning knobs (do not change results): maximum number of subdomain tiles resident at once. */
+int ss_context_set_tile_batch(ss_context *ctx, uint32_t max_tiles);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPLASHSURF_B200_H */

@@ -1,0 +1,312 @@
+"""splashsurf_b200 -- B200-native surface reconstruction behind the splashsurf API.
+
+Host-side mirror of the reference's Python front-end for the hot path
+(``pysplashsurf.reconstruct_surface``, pysplashsurf/src/reconstruction.rs:128-207): same keyword names,
+same RELATIVE ``smoothing_length`` / ``cube_size`` convention (both are multiplied by ``particle_radius``,
+reconstruction.rs:172-176), same result attributes (``mesh.vertices`` (V,3) float32, ``mesh.triangles``
+(T,3) uint64, ``particle_densities``, ``grid``, ``subdomain_grid``, ``particle_inside_aabb``).
+
+All compute happens in ``libsplashsurf_b200.so`` (hand-written sm_100a CUDA behind the C ABI declared in
+``include/splashsurf_b200.h``).  There is no CPU fallback: a missing library or a missing GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import build as _build
+
+__all__ = ["reconstruct_surface", "Context", "SurfaceReconstruction", "TriMesh3d", "UniformGrid", "Aabb3d",
+           "SplashsurfError", "library_path", "load_library"]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class SplashsurfError(RuntimeError):
+    """Raised for every non-zero return of the C ABI (code + the library's message)."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"[ss error {code}] {message}")
+        self.code = code
+        self.message = message
+
+
+class _Params(C.Structure):
+    _fields_ = [
+        ("particle_radius", C.c_float), ("rest_density", C.c_float), ("compact_support_radius", C.c_float),
+        ("cube_size", C.c_float), ("iso_surface_threshold", C.c_float),
+        ("has_particle_aabb", C.c_int32), ("particle_aabb_min", C.c_float * 3), ("particle_aabb_max", C.c_float * 3),
+        ("enable_multi_threading", C.c_int32), ("enable_simd", C.c_int32), ("spatial_decomposition", C.c_int32),
+        ("subdomain_num_cubes_per_dim", C.c_uint32), ("auto_disable", C.c_int32), ("global_neighborhood_list", C.c_int32),
+    ]
+
+
+class _Grid(C.Structure):
+    _fields_ = [("aabb_min", C.c_float * 3), ("aabb_max", C.c_float * 3), ("cell_size", C.c_float),
+                ("points_per_dim", C.c_int64 * 3), ("cells_per_dim", C.c_int64 * 3)]
+
+
+class _Timings(C.Structure):
+    _fields_ = [("upload", C.c_float), ("aabb_and_grid", C.c_float), ("decomposition", C.c_float), ("density", C.c_float),
+                ("binning", C.c_float), ("levelset", C.c_float), ("marching_cubes", C.c_float), ("stitching", C.c_float),
+                ("total_device", C.c_float), ("kernel_launches", C.c_uint64), ("levelset_launches", C.c_uint64),
+                ("levelset_pairs", C.c_double)]
+
+
+_LIB = None
+
+
+def library_path() -> str:
+    return _build.LIB
+
+
+def load_library():
+    """dlopen the in-tree CUDA library; raises if it has not been built (`python -m splashsurf_b200.build`)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: the CUDA extension has not been built "
+                          f"(run `python -m splashsurf_b200.build`); there is no CPU fallback")
+    L = C.CDLL(path)
+    vp, u64, i64 = C.c_void_p, C.c_uint64, C.c_int64
+    L.ss_abi_version.restype = C.c_int
+    L.ss_last_error.restype = C.c_char_p
+    L.ss_context_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.ss_context_destroy.argtypes = [vp]
+    L.ss_context_destroy.restype = None
+    L.ss_reconstruct_surface_f32.argtypes = [vp, vp, u64, C.POINTER(_Params), C.POINTER(vp)]
+    L.ss_surface_free.argtypes = [vp]
+    L.ss_surface_free.restype = None
+    L.ss_grid_for_reconstruction_f32.argtypes = [vp, vp, u64, C.POINTER(_Params), C.POINTER(_Grid)]
+    for name in ("ss_surface_num_vertices", "ss_surface_num_triangles", "ss_surface_num_particles", "ss_surface_num_subdomains"):
+        getattr(L, name).argtypes = [vp]
+        getattr(L, name).restype = u64
+    L.ss_surface_used_decomposition.argtypes = [vp]
+    L.ss_surface_grid.argtypes = [vp, C.POINTER(_Grid)]
+    L.ss_surface_subdomain_grid.argtypes = [vp, C.POINTER(_Grid)]
+    for name in ("ss_surface_copy_vertices", "ss_surface_copy_triangles_u32", "ss_surface_copy_triangles_u64",
+                 "ss_surface_copy_particle_densities", "ss_surface_copy_particle_inside_aabb",
+                 "ss_surface_copy_vertex_edge_keys", "ss_surface_copy_levelset_tile"):
+        getattr(L, name).argtypes = [vp, vp]
+    for name in ("ss_surface_device_vertices", "ss_surface_device_triangles", "ss_surface_device_densities"):
+        getattr(L, name).argtypes = [vp]
+        getattr(L, name).restype = vp
+    L.ss_surface_copy_subdomains.argtypes = [vp, vp, vp, vp]
+    L.ss_context_keep_levelset_tile.argtypes = [vp, i64]
+    L.ss_surface_timings.argtypes = [vp, C.POINTER(_Timings)]
+    L.ss_context_set_tile_batch.argtypes = [vp, C.c_uint32]
+    if L.ss_abi_version() != 1:
+        raise ImportError("libsplashsurf_b200.so ABI version mismatch")
+    _LIB = L
+    return L
+
+
+def _check(L, rc: int):
+    if rc != 0:
+        raise SplashsurfError(rc, (L.ss_last_error() or b"").decode("utf-8", "replace"))
+
+
+# ---------------------------------------------------------------------------- result types ----
+@dataclass
+class Aabb3d:
+    """Mirrors pysplashsurf.Aabb3d (min / max corners)."""
+    min: np.ndarray
+    max: np.ndarray
+
+
+@dataclass
+class UniformGrid:
+    """Mirrors pysplashsurf.UniformGrid / UniformCartesianCubeGrid3d (uniform_grid.rs:132-142)."""
+    aabb: Aabb3d
+    cell_size: float
+    npoints_per_dim: list
+    ncells_per_dim: list
+
+    @staticmethod
+    def _from(g: _Grid) -> "UniformGrid":
+        return UniformGrid(Aabb3d(np.array(g.aabb_min, dtype=np.float32), np.array(g.aabb_max, dtype=np.float32)),
+                           float(g.cell_size), [int(v) for v in g.points_per_dim], [int(v) for v in g.cells_per_dim])
+
+
+@dataclass
+class TriMesh3d:
+    """Mirrors splashsurf_lib::mesh::TriMesh3d (mesh.rs:186-193)."""
+    vertices: np.ndarray   # (V, 3) float32
+    triangles: np.ndarray  # (T, 3) uint64 (usize in the reference)
+
+    @property
+    def nvertices(self) -> int:
+        return len(self.vertices)
+
+    @property
+    def ncells(self) -> int:
+        return len(self.triangles)
+
+
+@dataclass
+class SurfaceReconstruction:
+    """Mirrors splashsurf_lib::SurfaceReconstruction<i64, f32> (lib.rs:247-262)."""
+    mesh: TriMesh3d
+    grid: UniformGrid
+    subdomain_grid: Optional[UniformGrid]
+    particle_densities: Optional[np.ndarray]
+    particle_inside_aabb: Optional[np.ndarray]
+    particle_neighbors: Optional[list] = None
+    # extras of the device path
+    timings: Optional[dict] = None
+    vertex_edge_keys: Optional[np.ndarray] = None
+    subdomains: Optional[dict] = None
+    levelset_tile: Optional[np.ndarray] = None
+
+
+# ---------------------------------------------------------------------------- context ----
+class Context:
+    """One GPU's stream + reusable device buffers (the analogue of the reference's rayon pool + workspace)."""
+
+    def __init__(self, device: int = -1):
+        self._L = load_library()
+        h = C.c_void_p()
+        _check(self._L, self._L.ss_context_create(int(device), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.ss_context_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_tile_batch(self, max_tiles: int):
+        _check(self._L, self._L.ss_context_set_tile_batch(self._h, int(max_tiles)))
+
+    def reconstruct_raw(self, xyz_ptr: int, n: int, params: _Params):
+        """Low-level call: pointer (host or device) to n x 3 f32 -> opaque surface handle."""
+        out = C.c_void_p()
+        _check(self._L, self._L.ss_reconstruct_surface_f32(self._h, C.c_void_p(xyz_ptr), C.c_uint64(n), C.byref(params), C.byref(out)))
+        return out
+
+    def free_surface(self, s):
+        self._L.ss_surface_free(s)
+
+    def timings(self, s) -> dict:
+        t = _Timings()
+        _check(self._L, self._L.ss_surface_timings(s, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in _Timings._fields_}
+
+
+_DEFAULT_CTX: dict = {}
+
+
+def default_context(device: int = -1) -> Context:
+    if device not in _DEFAULT_CTX:
+        _DEFAULT_CTX[device] = Context(device)
+    return _DEFAULT_CTX[device]
+
+
+def make_params(*, particle_radius, rest_density=1000.0, smoothing_length, cube_size, iso_surface_threshold=0.6,
+                aabb_min=None, aabb_max=None, multi_threading=True, simd=True, global_neighborhood_list=False,
+                subdomain_grid=True, subdomain_grid_auto_disable=True, subdomain_num_cubes_per_dim=64) -> _Params:
+    """Front-end parameter mapping of pysplashsurf (reconstruction.rs:160-184): f64 products, then f32."""
+    p = _Params()
+    r = float(particle_radius)
+    p.particle_radius = float(np.float32(r))
+    p.rest_density = float(np.float32(rest_density))
+    p.compact_support_radius = float(np.float32(2.0 * float(smoothing_length) * r))
+    p.cube_size = float(np.float32(float(cube_size) * r))
+    p.iso_surface_threshold = float(np.float32(iso_surface_threshold))
+    has = aabb_min is not None and aabb_max is not None
+    p.has_particle_aabb = int(has)
+    if has:
+        p.particle_aabb_min = (C.c_float * 3)(*[float(np.float32(v)) for v in aabb_min])
+        p.particle_aabb_max = (C.c_float * 3)(*[float(np.float32(v)) for v in aabb_max])
+    p.enable_multi_threading = int(bool(multi_threading))
+    p.enable_simd = int(bool(simd))
+    p.spatial_decomposition = int(bool(subdomain_grid))
+    p.subdomain_num_cubes_per_dim = int(subdomain_num_cubes_per_dim)
+    p.auto_disable = int(bool(subdomain_grid_auto_disable))
+    p.global_neighborhood_list = int(bool(global_neighborhood_list))
+    return p
+
+
+def reconstruct_surface(particles, *, particle_radius: float, rest_density: float = 1000.0, smoothing_length: float,
+                        cube_size: float, iso_surface_threshold: float = 0.6,
+                        aabb_min: Optional[Sequence[float]] = None, aabb_max: Optional[Sequence[float]] = None,
+                        multi_threading: bool = True, simd: bool = True, global_neighborhood_list: bool = False,
+                        subdomain_grid: bool = True, subdomain_grid_auto_disable: bool = True,
+                        subdomain_num_cubes_per_dim: int = 64, context: Optional[Context] = None,
+                        keep_levelset_tile_of: Optional[int] = None, with_debug: bool = False) -> SurfaceReconstruction:
+    """Performs a surface reconstruction from the given particles (no post-processing) on the GPU.
+
+    Same signature and semantics as ``pysplashsurf.reconstruct_surface``; ``particles`` is an (N, 3) float32
+    array (float64 input is not provided by the device path and raises, like an unsupported dtype does in the
+    reference, pysplashsurf/src/reconstruction.rs:204-206).
+    """
+    arr = np.asarray(particles)
+    if arr.dtype != np.float32:
+        raise TypeError("unsupported scalar type: the device path reconstructs float32 particles only")
+    if arr.ndim != 2 or arr.shape[1] != 3:
+        raise ValueError("particles must have shape (N, 3)")
+    arr = np.ascontiguousarray(arr)
+    ctx = context or default_context()
+    L = ctx._L
+    p = make_params(particle_radius=particle_radius, rest_density=rest_density, smoothing_length=smoothing_length,
+                    cube_size=cube_size, iso_surface_threshold=iso_surface_threshold, aabb_min=aabb_min, aabb_max=aabb_max,
+                    multi_threading=multi_threading, simd=simd, global_neighborhood_list=global_neighborhood_list,
+                    subdomain_grid=subdomain_grid, subdomain_grid_auto_disable=subdomain_grid_auto_disable,
+                    subdomain_num_cubes_per_dim=subdomain_num_cubes_per_dim)
+    _check(L, L.ss_context_keep_levelset_tile(ctx._h, -1 if keep_levelset_tile_of is None else int(keep_levelset_tile_of)))
+    s = ctx.reconstruct_raw(arr.ctypes.data, len(arr), p)
+    try:
+        return _collect(ctx, s, len(arr), p, with_debug or keep_levelset_tile_of is not None, keep_levelset_tile_of is not None)
+    finally:
+        ctx.free_surface(s)
+
+
+def _collect(ctx: Context, s, n_in: int, p: _Params, debug: bool, tile: bool) -> SurfaceReconstruction:
+    L = ctx._L
+    nv, nt, n = L.ss_surface_num_vertices(s), L.ss_surface_num_triangles(s), L.ss_surface_num_particles(s)
+    verts = np.empty((nv, 3), dtype=np.float32)
+    tris = np.empty((nt, 3), dtype=np.uint64)
+    dens = np.empty(n, dtype=np.float32)
+    _check(L, L.ss_surface_copy_vertices(s, verts.ctypes.data))
+    _check(L, L.ss_surface_copy_triangles_u64(s, tris.ctypes.data))
+    _check(L, L.ss_surface_copy_particle_densities(s, dens.ctypes.data))
+    g = _Grid()
+    _check(L, L.ss_surface_grid(s, C.byref(g)))
+    sub = None
+    if L.ss_surface_used_decomposition(s):
+        sg = _Grid()
+        _check(L, L.ss_surface_subdomain_grid(s, C.byref(sg)))
+        sub = UniformGrid._from(sg)
+    inside = None
+    if p.has_particle_aabb:
+        inside = np.empty(n_in, dtype=np.uint8)
+        if n_in:
+            _check(L, L.ss_surface_copy_particle_inside_aabb(s, inside.ctypes.data))
+        inside = inside.astype(bool)
+    res = SurfaceReconstruction(mesh=TriMesh3d(verts, tris), grid=UniformGrid._from(g), subdomain_grid=sub,
+                                particle_densities=dens, particle_inside_aabb=inside, timings=ctx.timings(s))
+    if debug:
+        keys = np.empty((nv, 4), dtype=np.int64)
+        _check(L, L.ss_surface_copy_vertex_edge_keys(s, keys.ctypes.data))
+        res.vertex_edge_keys = keys
+        ns = L.ss_surface_num_subdomains(s)
+        flat, cnt, sp = np.empty(ns, np.int64), np.empty(ns, np.uint64), np.empty(ns, np.uint8)
+        _check(L, L.ss_surface_copy_subdomains(s, flat.ctypes.data, cnt.ctypes.data, sp.ctypes.data))
+        res.subdomains = {"flat": flat, "count": cnt, "sparse": sp.astype(bool)}
+    if tile:
+        S = int(p.subdomain_num_cubes_per_dim)
+        t = np.empty((S + 1,) * 3, dtype=np.float32)
+        _check(L, L.ss_surface_copy_levelset_tile(s, t.ctypes.data))
+        res.levelset_tile = t
+    return res

@@ -1,0 +1,663 @@
+// ss_kernels.cuh -- device kernels of the B200 reconstruct path (included once by ss_pipeline.cu).
+//
+// Pipeline (one GPU):
+//   k_aabb                      particle bounding box                         (aabb.rs:28-52)
+//   k_classify_count/fill       owner + ghost subdomain memberships           (dense_subdomains.rs:1810-1905)
+//   [cub radix sort]            -> per-subdomain ascending particle lists     (dense_subdomains.rs:476-488)
+//   k_ns_keys + [sort] + k_density   per-subdomain cell lists, SPH densities  (neighborhood_search.rs:345-438,
+//                                                                              density_map.rs:150-186)
+//   k_bin_keys + [sort] + k_records  splat bins (8^3-point bricks) + particle records
+//   k_levelset                  ordered cubic-spline gather per grid point    (dense_subdomains.rs:784-1213)
+//   k_mc_count + [scan] + k_mc_emit  marching cubes per subdomain tile        (dense_subdomains.rs:1470-1568)
+//   k_weld_* / k_compact_*      boundary-vertex de-duplication ("stitching")  (dense_subdomains.rs:1603-1749)
+#pragma once
+#include "ss_common.cuh"
+#include "mc_lut.inc"
+
+__constant__ signed char c_tri_table[256][16];
+__constant__ unsigned char c_num_tris[256];
+// local edge -> (origin corner offset, axis), uniform_grid.rs:822-871
+__constant__ signed char c_edge_org[12][3] = { {0,0,0},{1,0,0},{0,1,0},{0,0,0},{0,0,1},{1,0,1},{0,1,1},{0,0,1},{0,0,0},{1,0,0},{1,1,0},{0,1,0} };
+__constant__ signed char c_edge_axis[12] = { 0, 1, 0, 1, 0, 1, 0, 1, 2, 2, 2, 2 };
+
+// ------------------------------------------------------------------ AABB ----
+__device__ __forceinline__ int ss_f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__host__ __device__ inline float ss_ord2f(int i) {
+    int j = i >= 0 ? i : i ^ 0x7fffffff;
+#ifdef __CUDA_ARCH__
+    return __int_as_float(j);
+#else
+    float f; memcpy(&f, &j, 4); return f;
+#endif
+}
+
+__global__ void k_aabb(const float *__restrict__ xyz, uint64_t n, int *__restrict__ out /* min3, max3 ordered ints */) {
+    int mn[3] = { INT_MAX, INT_MAX, INT_MAX }, mx[3] = { INT_MIN, INT_MIN, INT_MIN };
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { int v = ss_f2ord(xyz[3 * i + d]); mn[d] = min(mn[d], v); mx[d] = max(mx[d], v); }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[d] = min(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+            mx[d] = max(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { atomicMin(&out[d], mn[d]); atomicMax(&out[3 + d], mx[d]); }
+    }
+}
+
+// particle AABB filter (lib.rs:369-406): half-open contains_point
+__global__ void k_filter_flags(const float *__restrict__ xyz, uint64_t n, float3 mn, float3 mx,
+                               uint8_t *__restrict__ flag, uint32_t *__restrict__ flag32) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+    int in = (x >= mn.x && y >= mn.y && z >= mn.z) && (x < mx.x && y < mx.y && z < mx.z);
+    flag[i] = (uint8_t)in; flag32[i] = (uint32_t)in;
+}
+__global__ void k_filter_scatter(const float *__restrict__ xyz, uint64_t n, const uint8_t *__restrict__ flag,
+                                 const uint32_t *__restrict__ off, float *__restrict__ out) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n || !flag[i]) return;
+    uint32_t o = off[i];
+    out[3 * (uint64_t)o] = xyz[3 * i]; out[3 * (uint64_t)o + 1] = xyz[3 * i + 1]; out[3 * (uint64_t)o + 2] = xyz[3 * i + 2];
+}
+
+// ------------------------------------------------------------------ decomposition ----
+// Visits every subdomain the particle belongs to (owner + ghosts), dense_subdomains.rs:1810-1905.
+template <typename F>
+__device__ __forceinline__ int ss_classify(const SsDev &P, float px, float py, float pz, F &&emit) {
+    float p[3] = { px, py, pz };
+    int ijk[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        ijk[d] = ss_cell_of(p[d], P.gmin[d], P.sub_size);
+        if (ijk[d] < 0 || ijk[d] >= P.nsd[d]) return 0;
+    }
+    float minc[3], maxc[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { minc[d] = ss_coord(P.gmin[d], ijk[d], P.sub_size); maxc[d] = ss_coord(P.gmin[d], ijk[d] + 1, P.sub_size); }
+    const int r = P.srad;
+    int cnt = 0;
+    for (int i = -r; i <= r; ++i) for (int j = -r; j <= r; ++j) for (int k = -r; k <= r; ++k) {
+        int st[3] = { i, j, k };
+        bool ok = true;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            int s = st[d];
+            float off = (float)(abs(s) - 1);
+            if (s > 0) ok = ok && (__fsub_rn(__fadd_rn(maxc[d], __fmul_rn(off, P.sub_size)), p[d]) < P.margin);
+            else if (s < 0) ok = ok && (__fsub_rn(p[d], __fsub_rn(minc[d], __fmul_rn(off, P.sub_size))) < P.margin);
+        }
+        if (!ok) continue;
+        int t0 = ijk[0] + i, t1 = ijk[1] + j, t2 = ijk[2] + k;
+        if (t0 < 0 || t1 < 0 || t2 < 0 || t0 >= P.nsd[0] || t1 >= P.nsd[1] || t2 >= P.nsd[2]) continue;
+        emit(cnt, (t0 * P.nsd[1] + t1) * P.nsd[2] + t2);
+        ++cnt;
+    }
+    return cnt;
+}
+
+__global__ void k_classify_count(SsDev P, const float *__restrict__ xyz, uint32_t n, uint32_t *__restrict__ cnt) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    cnt[i] = (uint32_t)ss_classify(P, xyz[3 * (uint64_t)i], xyz[3 * (uint64_t)i + 1], xyz[3 * (uint64_t)i + 2], [](int, int) {});
+}
+__global__ void k_classify_fill(SsDev P, const float *__restrict__ xyz, uint32_t n, const uint32_t *__restrict__ off,
+                                uint32_t *__restrict__ sub_flat, uint32_t *__restrict__ pidx) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t o = off[i];
+    ss_classify(P, xyz[3 * (uint64_t)i], xyz[3 * (uint64_t)i + 1], xyz[3 * (uint64_t)i + 2],
+                [&](int m, int flat) { sub_flat[o + m] = (uint32_t)flat; pidx[o + m] = i; });
+}
+
+// membership index -> compressed subdomain id: segment heads flagged, then scanned
+__global__ void k_seg_flags(const uint32_t *__restrict__ keys, uint32_t m, uint32_t *__restrict__ flag) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= m) return;
+    flag[e] = (e == 0 || keys[e] != keys[e - 1]) ? 1u : 0u;
+}
+// after inclusive scan of flags: cid[e] = scan[e]-1; records each segment's flat id and start
+__global__ void k_seg_finish(const uint32_t *__restrict__ keys, uint32_t m, const uint32_t *__restrict__ incl,
+                             uint32_t *__restrict__ cid, uint32_t *__restrict__ sub_flat, uint32_t *__restrict__ sub_off) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= m) return;
+    uint32_t id = incl[e] - 1;
+    cid[e] = id;
+    if (e == 0 || keys[e] != keys[e - 1]) { sub_flat[id] = keys[e]; sub_off[id] = e; }
+    if (e == m - 1) sub_off[id + 1] = m;
+}
+
+struct SsSubGeom { float smin[3], smax[3]; int ijk[3]; };
+__device__ __forceinline__ SsSubGeom ss_sub_geom(const SsDev &P, uint32_t flat) {
+    SsSubGeom g;
+    int f = (int)flat;
+    g.ijk[0] = f / (P.nsd[1] * P.nsd[2]);
+    g.ijk[1] = (f - g.ijk[0] * P.nsd[1] * P.nsd[2]) / P.nsd[2];
+    g.ijk[2] = f - g.ijk[0] * P.nsd[1] * P.nsd[2] - g.ijk[1] * P.nsd[2];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { g.smin[d] = ss_coord(P.gmin[d], g.ijk[d], P.sub_size); g.smax[d] = ss_coord(P.gmin[d], g.ijk[d] + 1, P.sub_size); }
+    return g;
+}
+
+// neighbourhood-search grid of one subdomain: from_aabb(subdomain aabb grown by 1.5*margin, h)
+// (dense_subdomains.rs:560-565, uniform_grid.rs:175-201)
+struct SsNsGrid { float amin[3]; int nc[3]; };
+__device__ __forceinline__ SsNsGrid ss_ns_grid(const SsDev &P, const SsSubGeom &g) {
+    SsNsGrid ns;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        float mmin = __fsub_rn(g.smin[d], P.grow), mmax = __fadd_rn(g.smax[d], P.grow);
+        ns.amin[d] = __fmul_rn(floorf(__fdiv_rn(mmin, P.h)), P.h);
+        float ext = __fsub_rn(mmax, ns.amin[d]);
+        int n = (int)ceilf(__fdiv_rn(ext, P.h));
+        ns.nc[d] = n > 1 ? n : 1;
+    }
+    return ns;
+}
+
+// ------------------------------------------------------------------ density ----
+// key = cid * ns_stride + NS cell (x-major flat, padded to nsD per dim)
+__global__ void k_ns_keys(SsDev P, const float *__restrict__ xyz, uint32_t m, const uint32_t *__restrict__ cid,
+                          const uint32_t *__restrict__ sub_flat, const uint32_t *__restrict__ pidx,
+                          uint32_t *__restrict__ key, int *__restrict__ err) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= m) return;
+    uint32_t s = cid[e], p = pidx[e];
+    SsSubGeom g = ss_sub_geom(P, sub_flat[s]);
+    SsNsGrid ns = ss_ns_grid(P, g);
+    int c[3];
+    bool bad = false;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        c[d] = ss_cell_of(xyz[3 * (uint64_t)p + d], ns.amin[d], P.h);
+        if (c[d] < 0 || c[d] >= ns.nc[d] || ns.nc[d] > P.nsD) { bad = true; c[d] = 0; }
+    }
+    if (bad) atomicExch(err, 1);   // reference: unwrap() panic "particle outside NS grid"
+    key[e] = s * (uint32_t)P.ns_stride + (uint32_t)((c[0] * P.nsD + c[1]) * P.nsD + c[2]);
+}
+
+// Dense (start, end) tables over a sorted key array: start[key] = first entry of the run (table pre-filled with
+// 0xffffffff = empty), end[key] = one past its last entry.  Keys >= nkeys (dropped entries) are ignored.
+__global__ void k_mark_starts(const uint32_t *__restrict__ key, uint32_t m, uint32_t *__restrict__ start, uint32_t nkeys) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= m) return;
+    uint32_t k = key[e];
+    if (k >= nkeys) return;
+    if (e == 0 || k != key[e - 1]) start[k] = e;
+}
+__global__ void k_run_counts(const uint32_t *__restrict__ key, uint32_t m, uint32_t *__restrict__ end, uint32_t nkeys) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= m) return;
+    uint32_t k = key[e];
+    if (k >= nkeys) return;
+    if (e == m - 1 || k != key[e + 1]) end[k] = e + 1;
+}
+
+__global__ void k_gather_pos(const float *__restrict__ xyz, const uint32_t *__restrict__ pidx, uint32_t m,
+                             float4 *__restrict__ out) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= m) return;
+    uint32_t p = pidx[e];
+    out[e] = make_float4(xyz[3 * (uint64_t)p], xyz[3 * (uint64_t)p + 1], xyz[3 * (uint64_t)p + 2], __uint_as_float(p));
+}
+
+// One thread per (subdomain, particle) membership in NS-sorted order.  Particles contained in the
+// subdomain's AABB get rho = m * (W(0) + sum_j W(|xj - xi|)) with neighbours visited in the reference's
+// order: 26 adjacent cells in x-major (-1,0,1)^3 order, then the own cell; ascending particle index
+// inside a cell (neighborhood_search.rs:396-433, density_map.rs:169-185).
+__global__ void __launch_bounds__(128)
+k_density(SsDev P, uint32_t m, const uint32_t *__restrict__ key, const float4 *__restrict__ spos,
+          const uint32_t *__restrict__ sub_flat, const uint32_t *__restrict__ cstart, const uint32_t *__restrict__ cend,
+          float *__restrict__ rho) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= m) return;
+    uint32_t k = key[e];
+    uint32_t s = k / (uint32_t)P.ns_stride, cell = k - s * (uint32_t)P.ns_stride;
+    float4 pi = spos[e];
+    SsSubGeom g = ss_sub_geom(P, sub_flat[s]);
+    bool inside = (pi.x >= g.smin[0] && pi.y >= g.smin[1] && pi.z >= g.smin[2]) &&
+                  (pi.x < g.smax[0] && pi.y < g.smax[1] && pi.z < g.smax[2]);       // aabb.rs:220-222
+    if (!inside) return;
+    SsNsGrid ns = ss_ns_grid(P, g);
+    int c0 = (int)cell / (P.nsD * P.nsD), c1 = ((int)cell / P.nsD) % P.nsD, c2 = (int)cell % P.nsD;
+    float acc = ss_kernel_scalar(P, 0.0f);
+    const uint32_t base = s * (uint32_t)P.ns_stride;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int sx = -1; sx <= 1; ++sx) for (int sy = -1; sy <= 1; ++sy) for (int sz = -1; sz <= 1; ++sz) {
+            bool self = (sx == 0 && sy == 0 && sz == 0);
+            if ((pass == 0) == self) continue;
+            int q0 = c0 + sx, q1 = c1 + sy, q2 = c2 + sz;
+            if (q0 < 0 || q1 < 0 || q2 < 0 || q0 >= ns.nc[0] || q1 >= ns.nc[1] || q2 >= ns.nc[2]) continue;
+            uint32_t kk = base + (uint32_t)((q0 * P.nsD + q1) * P.nsD + q2);
+            uint32_t a = cstart[kk];
+            if (a == 0xffffffffu) continue;
+            uint32_t b = cend[kk];
+            for (uint32_t t = a; t < b; ++t) {
+                if (t == e) continue;
+                float4 pj = spos[t];
+                float dx = __fsub_rn(pj.x, pi.x), dy = __fsub_rn(pj.y, pi.y), dz = __fsub_rn(pj.z, pi.z);
+                float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                if (d2 < P.h2) acc = __fadd_rn(acc, ss_kernel_scalar(P, __fsqrt_rn(d2)));
+            }
+        }
+    }
+    rho[__float_as_uint(pi.w)] = __fmul_rn(acc, P.rest_mass);
+}
+
+// ------------------------------------------------------------------ splat binning ----
+// Bins are 8x8x8-point bricks of the subdomain tile, extended by nlo/nhi halo bins.  Binning is only a
+// conservative cull: a particle farther than h from every tile point is dropped (key 0xffffffff).
+__global__ void k_bin_keys(SsDev P, const float *__restrict__ xyz, uint32_t m, const uint32_t *__restrict__ cid,
+                           const uint32_t *__restrict__ sub_flat, const uint32_t *__restrict__ pidx,
+                           uint32_t *__restrict__ key) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= m) return;
+    uint32_t s = cid[e], p = pidx[e];
+    SsSubGeom g = ss_sub_geom(P, sub_flat[s]);
+    int b[3];
+    bool drop = false;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        float u = (xyz[3 * (uint64_t)p + d] - g.smin[d]) * P.inv_c;        // local coordinate in cells
+        if (u < -P.rr_cells || u > (float)P.S + P.rr_cells) drop = true;
+        int bb = (int)floorf(u * 0.125f) + P.nlo;
+        bb = max(0, min(P.nbin - 1, bb));
+        b[d] = bb;
+    }
+    key[e] = drop ? 0xffffffffu : s * (uint32_t)P.nbin_sub + (uint32_t)((b[0] * P.nbin + b[1]) * P.nbin + b[2]);
+}
+
+// particle record in bin-sorted order: (x, y, z, V = m / rho) + k_split of the AVX remainder lanes
+__global__ void k_records(SsDev P, const float *__restrict__ xyz, const float *__restrict__ rho, uint32_t m,
+                          const uint32_t *__restrict__ key, const uint32_t *__restrict__ pidx,
+                          const uint32_t *__restrict__ sub_flat, float4 *__restrict__ rec, int *__restrict__ ksplit) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= m) return;
+    uint32_t k = key[e];
+    if (k == 0xffffffffu) return;
+    uint32_t s = k / (uint32_t)P.nbin_sub, p = pidx[e];
+    float x = xyz[3 * (uint64_t)p], y = xyz[3 * (uint64_t)p + 1], z = xyz[3 * (uint64_t)p + 2];
+    float v = __fdiv_rn(P.rest_mass, rho[p]);                              // dense_subdomains.rs:1044
+    rec[e] = make_float4(x, y, z, v);
+    SsSubGeom g = ss_sub_geom(P, sub_flat[s]);
+    // particle_influence_aabb along z (dense_subdomains.rs:660-693) and the 8-lane remainder (:1050-1051)
+    int ck = ss_cell_of(z, g.smin[2], P.c);
+    int lo = min(max(ck - P.R, 0), P.np);
+    int up = max(min(ck + P.R + 2, P.np), 0);
+    int rem = up > lo ? (up - lo) % 8 : 0;
+    ksplit[e] = up - rem;
+}
+
+// ------------------------------------------------------------------ level set ----
+#define SS_LS_THREADS 512
+#define SS_LS_CAP 1024          // candidates staged per pass
+
+struct SsLsArgs {
+    const uint32_t *bin_start;   // [nsub * nbin_sub] run start or 0xffffffff
+    const uint32_t *bin_end;     // [nsub * nbin_sub] run end
+    const float4 *rec;           // bin-sorted records
+    const int *ksplit;
+    const uint32_t *pidx;        // bin-sorted particle indices
+    const uint32_t *sub_flat;    // compressed -> flat
+    const uint8_t *sub_sparse;   // compressed -> sparse flag
+    const uint32_t *batch_subs;  // compressed ids in this batch
+    float *tiles;                // [batch][np^3]
+    unsigned long long *pairs;   // work counter (in-support evaluations), optional
+};
+
+// Sorts the staged candidate keys ((pidx << 10) | slot) ascending: bitonic network in shared memory.
+__device__ __forceinline__ void ss_bitonic(unsigned long long *keys, int n /* power of two */) {
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < n; t += blockDim.x) {
+                int ixj = t ^ j;
+                if (ixj > t) {
+                    unsigned long long a = keys[t], b = keys[ixj];
+                    bool up = ((t & k) == 0);
+                    if ((a > b) == up) { keys[t] = b; keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// One CTA = one 8x8x8-point brick of one subdomain tile; one warp = a 2x4x4 point box; one lane = one point.
+// Per point, phi = ordered fold over the subdomain's particles in ascending global index of
+//     dense : phi = fma(W_avx(r), V, phi)  (or phi + W*V for the 8-lane remainder)   dense_subdomains.rs:1106-1128
+//     sparse: phi = phi + V * W_scalar(r)                                            dense_subdomains.rs:1184-1194
+// restricted to particles with d^2 < h^2 (dense) / d^2 < 1.01 h^2 (scalar).  Candidates come from the
+// brick's neighbouring bins, are sorted by global index in shared memory, and each warp walks only the
+// candidates within h of its own point box.
+__global__ void __launch_bounds__(SS_LS_THREADS)
+k_levelset(SsDev P, SsLsArgs A) {
+    __shared__ float4 s_rec[SS_LS_CAP];
+    __shared__ int s_ks[SS_LS_CAP];
+    __shared__ unsigned long long s_key[SS_LS_CAP];
+    __shared__ uint32_t s_rng[2][128];          // candidate runs (start, end)
+    __shared__ uint32_t s_pre[129];
+    __shared__ uint32_t s_mask[SS_LS_THREADS / 32][SS_LS_CAP / 32];
+    __shared__ int s_nrun;
+
+    const int nb = P.nb;
+    int brick = blockIdx.x;
+    const int bz = brick % nb; brick /= nb;
+    const int by = brick % nb; brick /= nb;
+    const int bx = brick % nb; brick /= nb;
+    const uint32_t s = A.batch_subs[brick];
+    const int tile_idx = brick;
+    const bool sparse = A.sub_sparse[s] || !P.simd;
+    const SsSubGeom g = ss_sub_geom(P, A.sub_flat[s]);
+
+    // ---- candidate runs: bins [bx-nlo, bx+nhi] x [by-..] with contiguous z ranges
+    const int nx = P.nlo + P.nhi + 1;
+    if (threadIdx.x < nx * nx) {
+        int ix = threadIdx.x / nx, iy = threadIdx.x % nx;
+        // bin index of brick b is b + nlo; neighbours b-nlo..b+nhi -> bin indices b .. b+nlo+nhi
+        int X = bx + ix, Y = by + iy, Z0 = bz, Z1 = bz + P.nlo + P.nhi;
+        uint32_t a = 0xffffffffu, b = 0;
+        uint32_t base = s * (uint32_t)P.nbin_sub + (uint32_t)((X * P.nbin + Y) * P.nbin);
+        for (int Z = Z0; Z <= Z1; ++Z) {
+            uint32_t st = A.bin_start[base + Z];
+            if (st != 0xffffffffu) { if (a == 0xffffffffu) a = st; b = A.bin_end[base + Z]; }
+        }
+        s_rng[0][threadIdx.x] = a; s_rng[1][threadIdx.x] = (a == 0xffffffffu) ? 0 : b - a;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int r = 0; r < nx * nx; ++r) { s_pre[r] = acc; acc += s_rng[1][r]; }
+        s_pre[nx * nx] = acc; s_nrun = nx * nx;
+    }
+    __syncthreads();
+    const uint32_t C = s_pre[nx * nx];
+    if (C == 0) return;                          // tile is pre-zeroed
+
+    // ---- this lane's grid point
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wi = warp >> 2, wj = (warp >> 1) & 1, wk = warp & 1;
+    const int li = lane >> 4, lj = (lane >> 2) & 3, lk = lane & 3;
+    const int i = bx * 8 + wi * 2 + li, j = by * 8 + wj * 4 + lj, k = bz * 8 + wk * 4 + lk;
+    const bool valid = (i < P.np) && (j < P.np) && (k < P.np);
+    const int gi = g.ijk[0] * P.S + i, gj = g.ijk[1] * P.S + j, gk = g.ijk[2] * P.S + k;
+    // grid point coordinates from GLOBAL indices: x, y = mul then add, z fused in the AVX path
+    // (dense_subdomains.rs:1068, :1101-1102); scalar path: point_coordinates (uniform_grid.rs:418-425)
+    const float gx = __fadd_rn(__fmul_rn((float)gi, P.c), P.gmin[0]);
+    const float gy = __fadd_rn(__fmul_rn((float)gj, P.c), P.gmin[1]);
+    const float gz = sparse ? __fadd_rn(P.gmin[2], __fmul_rn((float)gk, P.c)) : __fmaf_rn((float)gk, P.c, P.gmin[2]);
+    // warp box (for culling only): corner points of the 2x4x4 box, clipped to the tile
+    const int i0 = bx * 8 + wi * 2, j0 = by * 8 + wj * 4, k0 = bz * 8 + wk * 4;
+    const bool warp_valid = (i0 < P.np) && (j0 < P.np) && (k0 < P.np);
+    const int i1 = min(i0 + 1, P.np - 1), j1 = min(j0 + 3, P.np - 1), k1 = min(k0 + 3, P.np - 1);
+    const float bxl = P.gmin[0] + (float)(g.ijk[0] * P.S + i0) * P.c, bxh = P.gmin[0] + (float)(g.ijk[0] * P.S + i1) * P.c;
+    const float byl = P.gmin[1] + (float)(g.ijk[1] * P.S + j0) * P.c, byh = P.gmin[1] + (float)(g.ijk[1] * P.S + j1) * P.c;
+    const float bzl = P.gmin[2] + (float)(g.ijk[2] * P.S + k0) * P.c, bzh = P.gmin[2] + (float)(g.ijk[2] * P.S + k1) * P.c;
+    const float cull2 = (sparse ? P.h2m : P.h2) * 1.0001f;
+
+    float phi = 0.0f;
+    unsigned long long npairs = 0;
+
+    if (C <= SS_LS_CAP) {
+        // ---- stage + sort candidates by global particle index
+        int npow = 32; while (npow < (int)C) npow <<= 1;
+        for (int t = threadIdx.x; t < npow; t += blockDim.x) {
+            if (t < (int)C) {
+                int r = 0; while (s_pre[r + 1] <= (uint32_t)t) ++r;
+                uint32_t src = s_rng[0][r] + ((uint32_t)t - s_pre[r]);
+                s_key[t] = ((unsigned long long)A.pidx[src] << 32) | src;
+            } else s_key[t] = ~0ull;
+        }
+        __syncthreads();
+        ss_bitonic(s_key, npow);
+        for (int t = threadIdx.x; t < (int)C; t += blockDim.x) {
+            uint32_t src = (uint32_t)(s_key[t] & 0xffffffffu);
+            s_rec[t] = A.rec[src]; s_ks[t] = A.ksplit[src];
+        }
+        __syncthreads();
+        if (!warp_valid) return;
+        // ---- per-warp cull: candidates within h of the warp's point box
+        const int nwords = ((int)C + 31) >> 5;
+        for (int w = 0; w < nwords; ++w) {
+            int c = w * 32 + lane;
+            bool keep = false;
+            if (c < (int)C) {
+                float4 r = s_rec[c];
+                float dx = fmaxf(fmaxf(bxl - r.x, r.x - bxh), 0.0f);
+                float dy = fmaxf(fmaxf(byl - r.y, r.y - byh), 0.0f);
+                float dz = fmaxf(fmaxf(bzl - r.z, r.z - bzh), 0.0f);
+                keep = (dx * dx + dy * dy + dz * dz) < cull2;
+            }
+            uint32_t mword = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) s_mask[warp][w] = mword;
+        }
+        __syncwarp();
+        // ---- ordered accumulation
+        for (int w = 0; w < nwords; ++w) {
+            uint32_t mword = s_mask[warp][w];
+            while (mword) {
+                int c = w * 32 + __ffs(mword) - 1;
+                mword &= mword - 1;
+                float4 r = s_rec[c];
+                float dx = __fsub_rn(r.x, gx), dy = __fsub_rn(r.y, gy), dz = __fsub_rn(r.z, gz);
+                if (!sparse) {
+                    float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+                    if (d2 < P.h2) {
+                        float wgt = ss_kernel_avx(P, __fsqrt_rn(d2));
+                        phi = (k < s_ks[c]) ? __fmaf_rn(wgt, r.w, phi) : __fadd_rn(phi, __fmul_rn(wgt, r.w));
+                        ++npairs;
+                    }
+                } else {
+                    float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                    if (d2 < P.h2m) {
+                        float wgt = ss_kernel_scalar(P, __fsqrt_rn(d2));
+                        phi = __fadd_rn(phi, __fmul_rn(r.w, wgt));
+                        ++npairs;
+                    }
+                }
+            }
+        }
+    } else {
+        // ---- oversized brick (pathological clustering): every lane walks all candidates in ascending
+        // particle index by repeated selection of the next-larger index.  O(C^2) but exact.
+        if (!warp_valid) return;
+        long long last = -1;
+        for (uint32_t done = 0; done < C; ++done) {
+            // find the smallest pidx > last among all runs (runs are ascending inside each bin, but a run
+            // spans several bins; scan everything)
+            unsigned long long best = ~0ull;
+            for (int r = 0; r < s_nrun; ++r) {
+                uint32_t a = s_rng[0][r], len = s_rng[1][r];
+                for (uint32_t t = lane; t < len; t += 32) {
+                    uint32_t pi = A.pidx[a + t];
+                    if ((long long)pi > last) { unsigned long long kk = ((unsigned long long)pi << 32) | (a + t); if (kk < best) best = kk; }
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1) { unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o); if (other < best) best = other; }
+            if (best == ~0ull) break;
+            last = (long long)(best >> 32);
+            uint32_t src = (uint32_t)(best & 0xffffffffu);
+            float4 r = A.rec[src];
+            int ks = A.ksplit[src];
+            float dx = __fsub_rn(r.x, gx), dy = __fsub_rn(r.y, gy), dz = __fsub_rn(r.z, gz);
+            if (!sparse) {
+                float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+                if (d2 < P.h2) {
+                    float wgt = ss_kernel_avx(P, __fsqrt_rn(d2));
+                    phi = (k < ks) ? __fmaf_rn(wgt, r.w, phi) : __fadd_rn(phi, __fmul_rn(wgt, r.w));
+                }
+            } else {
+                float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                if (d2 < P.h2m) phi = __fadd_rn(phi, __fmul_rn(r.w, ss_kernel_scalar(P, __fsqrt_rn(d2))));
+            }
+        }
+    }
+    if (valid) A.tiles[(size_t)tile_idx * P.np * P.np * P.np + ((size_t)i * P.np + j) * P.np + k] = phi;
+    if (A.pairs) {
+        for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(0xffffffffu, npairs, o);
+        if (lane == 0 && npairs) atomicAdd(A.pairs, npairs);
+    }
+}
+
+// ------------------------------------------------------------------ marching cubes ----
+// Per tile point: which of its +x/+y/+z edges carry a vertex (endpoints on different sides of the
+// threshold, `value > threshold` == inside, dense_subdomains.rs:1482) and how many triangles its cell emits.
+__global__ void k_mc_count(SsDev P, const float *__restrict__ tiles, uint32_t npts_total,
+                           uint32_t *__restrict__ vcnt, uint32_t *__restrict__ tcnt, uint8_t *__restrict__ vmask) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= npts_total) return;
+    const int np = P.np, np3 = np * np * np;
+    uint32_t tile = t / (uint32_t)np3; int l = (int)(t - tile * (uint32_t)np3);
+    int i = l / (np * np), j = (l / np) % np, k = l % np;
+    const float *phi = tiles + (size_t)tile * np3;
+    float thr = P.thr;
+    bool in0 = phi[l] > thr;
+    uint32_t mask = 0;
+    if (i + 1 < np && ((phi[l + np * np] > thr) != in0)) mask |= 1u;
+    if (j + 1 < np && ((phi[l + np] > thr) != in0)) mask |= 2u;
+    if (k + 1 < np && ((phi[l + 1] > thr) != in0)) mask |= 4u;
+    vmask[t] = (uint8_t)mask;
+    vcnt[t] = __popc(mask);
+    uint32_t nt = 0;
+    if (i < P.S && j < P.S && k < P.S) {
+        int idx = (in0 ? 1 : 0);
+        idx |= (phi[l + np * np] > thr) ? 2 : 0;              // corner 1 (1,0,0)
+        idx |= (phi[l + np * np + np] > thr) ? 4 : 0;         // corner 2 (1,1,0)
+        idx |= (phi[l + np] > thr) ? 8 : 0;                   // corner 3 (0,1,0)
+        idx |= (phi[l + 1] > thr) ? 16 : 0;                   // corner 4 (0,0,1)
+        idx |= (phi[l + np * np + 1] > thr) ? 32 : 0;         // corner 5 (1,0,1)
+        idx |= (phi[l + np * np + np + 1] > thr) ? 64 : 0;    // corner 6 (1,1,1)
+        idx |= (phi[l + np + 1] > thr) ? 128 : 0;             // corner 7 (0,1,1)
+        nt = c_num_tris[idx];
+    }
+    tcnt[t] = nt;
+}
+
+struct SsMcOut {
+    float *verts;                 // [*][3]
+    uint32_t *tris;               // [*][3]
+    unsigned long long *vkeys;    // per provisional vertex: global edge key
+    unsigned long long *bkeys;    // boundary list: key
+    uint32_t *bids;               // boundary list: provisional vertex id
+    uint32_t *bcount;             // boundary list length (atomic)
+    uint32_t vbase, tbase;        // offsets of this batch in the global arrays
+    uint32_t bcap;
+};
+
+__global__ void k_mc_emit(SsDev P, const float *__restrict__ tiles, uint32_t npts_total,
+                          const uint32_t *__restrict__ voff, const uint32_t *__restrict__ toff,
+                          const uint8_t *__restrict__ vmask, const uint32_t *__restrict__ batch_subs,
+                          const uint32_t *__restrict__ sub_flat, SsMcOut O) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= npts_total) return;
+    const int np = P.np, np3 = np * np * np;
+    uint32_t tile = t / (uint32_t)np3; int l = (int)(t - tile * (uint32_t)np3);
+    int i = l / (np * np), j = (l / np) % np, k = l % np;
+    const float *phi = tiles + (size_t)tile * np3;
+    const float thr = P.thr;
+    const SsSubGeom g = ss_sub_geom(P, sub_flat[batch_subs[tile]]);
+    const uint32_t mask = vmask[t];
+    // ---- vertices on the edges owned by this point (dense_subdomains.rs:1498-1538)
+    if (mask) {
+        uint32_t vid = O.vbase + voff[t];
+        const float a = phi[l];
+        const int o[3] = { i, j, k };
+        float oc[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) oc[d] = ss_coord(g.smin[d], o[d], P.c);
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) {
+            if (!(mask & (1u << ax))) continue;
+            const int stride = ax == 0 ? np * np : (ax == 1 ? np : 1);
+            const float b = phi[l + stride];
+            const float alpha = __fdiv_rn(__fsub_rn(thr, a), __fsub_rn(b, a));
+            const float one_m = __fsub_rn(1.0f, alpha);
+            float pos[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                float tc = (d == ax) ? ss_coord(g.smin[d], o[d] + 1, P.c) : oc[d];
+                pos[d] = __fadd_rn(__fmul_rn(oc[d], one_m), __fmul_rn(tc, alpha));
+            }
+            O.verts[3 * (size_t)vid] = pos[0]; O.verts[3 * (size_t)vid + 1] = pos[1]; O.verts[3 * (size_t)vid + 2] = pos[2];
+            unsigned long long key = ss_edge_key(g.ijk[0] * P.S + i, g.ijk[1] * P.S + j, g.ijk[2] * P.S + k, ax);
+            O.vkeys[vid] = key;
+            // boundary edge: an orthogonal coordinate on a tile face (uniform_grid.rs:332-338)
+            bool boundary = false;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) if (d != ax && (o[d] == 0 || o[d] == P.S)) boundary = true;
+            if (boundary) {
+                uint32_t slot = atomicAdd(O.bcount, 1u);
+                if (slot < O.bcap) { O.bkeys[slot] = key; O.bids[slot] = vid; }
+            }
+            ++vid;
+        }
+    }
+    // ---- triangles of the cell whose origin is this point (dense_subdomains.rs:1470-1552)
+    if (i < P.S && j < P.S && k < P.S) {
+        int idx = (phi[l] > thr) ? 1 : 0;
+        idx |= (phi[l + np * np] > thr) ? 2 : 0;
+        idx |= (phi[l + np * np + np] > thr) ? 4 : 0;
+        idx |= (phi[l + np] > thr) ? 8 : 0;
+        idx |= (phi[l + 1] > thr) ? 16 : 0;
+        idx |= (phi[l + np * np + 1] > thr) ? 32 : 0;
+        idx |= (phi[l + np * np + np + 1] > thr) ? 64 : 0;
+        idx |= (phi[l + np + 1] > thr) ? 128 : 0;
+        const int nt = c_num_tris[idx];
+        uint32_t tid = O.tbase + toff[t];
+        for (int q = 0; q < nt; ++q) {
+#pragma unroll
+            for (int mth = 0; mth < 3; ++mth) {
+                const int le = c_tri_table[idx][3 * q + (2 - mth)];          // reversed triplet, lut.rs:338-342
+                const int ax = c_edge_axis[le];
+                const int lo = l + c_edge_org[le][0] * np * np + c_edge_org[le][1] * np + c_edge_org[le][2];
+                const uint32_t to = tile * (uint32_t)np3 + (uint32_t)lo;
+                const uint32_t below = vmask[to] & ((1u << ax) - 1u);
+                O.tris[3 * (size_t)tid + mth] = O.vbase + voff[to] + __popc(below);
+            }
+            ++tid;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ stitching (weld) ----
+// Sorted boundary list (key, provisional id): duplicates of a key map to the smallest id of the run.
+__global__ void k_weld_runs(const unsigned long long *__restrict__ bkeys, const uint32_t *__restrict__ bids, uint32_t nb,
+                            uint32_t *__restrict__ remap, uint32_t *__restrict__ keep) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nb) return;
+    if (e > 0 && bkeys[e] == bkeys[e - 1]) return;          // run heads only
+    uint32_t best = bids[e];
+    uint32_t f = e + 1;
+    while (f < nb && bkeys[f] == bkeys[e]) { best = min(best, bids[f]); ++f; }
+    for (uint32_t q = e; q < f; ++q) { uint32_t id = bids[q]; remap[id] = best; if (id != best) keep[id] = 0; }
+}
+__global__ void k_iota_keep(uint32_t n, uint32_t *__restrict__ remap, uint32_t *__restrict__ keep) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    remap[e] = e; keep[e] = 1;
+}
+__global__ void k_compact_verts(uint32_t n, const uint32_t *__restrict__ keep, const uint32_t *__restrict__ newid,
+                                const float *__restrict__ vin, const unsigned long long *__restrict__ kin,
+                                float *__restrict__ vout, unsigned long long *__restrict__ kout) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n || !keep[e]) return;
+    uint32_t o = newid[e];
+    vout[3 * (size_t)o] = vin[3 * (size_t)e]; vout[3 * (size_t)o + 1] = vin[3 * (size_t)e + 1]; vout[3 * (size_t)o + 2] = vin[3 * (size_t)e + 2];
+    kout[o] = kin[e];
+}
+__global__ void k_remap_tris(uint64_t n3, const uint32_t *__restrict__ remap, const uint32_t *__restrict__ newid,
+                             uint32_t *__restrict__ tris) {
+    uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (e >= n3) return;
+    tris[e] = newid[remap[tris[e]]];
+}
+__global__ void k_tris_to_u64(uint64_t n3, const uint32_t *__restrict__ in, unsigned long long *__restrict__ out) {
+    uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (e >= n3) return;
+    out[e] = in[e];
+}

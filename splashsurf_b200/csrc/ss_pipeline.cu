@@ -1,0 +1,717 @@
+// ss_pipeline.cu -- host orchestration + C ABI of the B200 reconstruct path (see include/splashsurf_b200.h).
+//
+// Host-side mirror of splashsurf_lib::reconstruct_surface_inplace (lib.rs:340-473) and
+// reconstruction::reconstruct_surface_subdomain_grid (reconstruction.rs:17-62): parameter validation, grid
+// derivation in exact f32 (lib.rs:476-516, dense_subdomains.rs:89-244), then the device pipeline.  There is
+// no CPU fallback: without a CUDA device every entry point fails with SS_ERR_NO_DEVICE.
+#include "../../include/splashsurf_b200.h"
+#include "ss_kernels.cuh"
+
+#include <cub/cub.cuh>
+#include <cfloat>
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+// ------------------------------------------------------------------ errors ----
+static thread_local std::string g_last_error;
+static int ss_fail(int code, const std::string &msg) { g_last_error = msg; return code; }
+
+struct SsCudaError { cudaError_t e; const char *what; const char *file; int line; };
+#define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) throw SsCudaError{ _e, #call, __FILE__, __LINE__ }; } while (0)
+
+// ------------------------------------------------------------------ device buffers ----
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+    template <typename T> T *as() const { return (T *)p; }
+    void ensure(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; throw SsCudaError{ e, "cudaMalloc", __FILE__, __LINE__ }; }
+        cap = want;
+    }
+    // grow while preserving contents
+    void grow_keep(size_t bytes, size_t used, cudaStream_t st) {
+        if (bytes <= cap) return;
+        size_t want = std::max(bytes + bytes / 4, cap * 2) + 256;
+        void *q = nullptr;
+        cudaError_t e = cudaMalloc(&q, want);
+        if (e != cudaSuccess) throw SsCudaError{ e, "cudaMalloc", __FILE__, __LINE__ };
+        if (p && used) CK(cudaMemcpyAsync(q, p, used, cudaMemcpyDeviceToDevice, st));
+        if (p) { CK(cudaStreamSynchronize(st)); cudaFree(p); }
+        p = q; cap = want;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct HostGrid { float mn[3], mx[3]; float cell; int64_t np[3], nc[3]; };
+
+struct ss_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[12];
+    uint32_t max_tiles = 0;          // 0 = auto
+    int64_t keep_tile_flat = -1;
+    // reusable scratch
+    DevBuf xyz, xyz_f, filt_flag, filt_flag32, filt_off, aabb, cnt, off, key_a, key_b, val_a, val_b, cid, cub_tmp,
+        sub_flat, sub_off, sub_sparse, flags, scan, spos, rho, tab_a, tab_b, rec, ksplit, batch_subs, tiles, vcnt,
+        tcnt, vmask, bkeys_a, bkeys_b, bids_a, bids_b, bcount, remap, keep, newid, err, pairs;
+    uint64_t launches = 0;
+};
+
+struct ss_surface {
+    int device = 0;
+    uint64_t n_in = 0, n = 0, nv = 0, nt = 0, nsub = 0;
+    int used_decomposition = 0;
+    HostGrid grid{}, subgrid{};
+    int S = 0;
+    DevBuf verts, tris, vkeys, rho;
+    std::vector<uint8_t> inside_aabb;
+    std::vector<int64_t> sub_flat; std::vector<uint64_t> sub_count; std::vector<uint8_t> sub_sparse;
+    std::vector<float> tile;
+    ss_timings tm{};
+};
+
+// ------------------------------------------------------------------ host grid math (exact f32) ----
+// All expressions are single roundings in the order the reference evaluates them; `volatile` stores stop the
+// host compiler from keeping excess precision or contracting (the TU is also built with -ffp-contract=off).
+static inline float fmulr(float a, float b) { volatile float r = a * b; return r; }
+static inline float faddr(float a, float b) { volatile float r = a + b; return r; }
+static inline float fsubr(float a, float b) { volatile float r = a - b; return r; }
+static inline float fdivr(float a, float b) { volatile float r = a / b; return r; }
+
+static int grid_new(HostGrid &g, const float mn[3], const int64_t nc[3], float cell) {       // uniform_grid.rs:204-232
+    for (int d = 0; d < 3; ++d) {
+        g.mn[d] = mn[d]; g.nc[d] = nc[d]; g.np[d] = nc[d] + 1;
+        g.mx[d] = faddr(mn[d], fmulr(cell, (float)nc[d]));
+        if (!std::isfinite(g.mx[d])) return SS_ERR_REAL_TOO_SMALL;
+    }
+    g.cell = cell;
+    return SS_OK;
+}
+static int grid_from_aabb(HostGrid &g, const float mn[3], const float mx[3], float cell) {   // uniform_grid.rs:175-201
+    if (!(cell > 0.0f)) return SS_ERR_INVALID_CELL_SIZE;
+    if (mn[0] == mx[0] && mn[1] == mx[1] && mn[2] == mx[2]) return SS_ERR_DEGENERATE_AABB;
+    for (int d = 0; d < 3; ++d) if (!(mn[d] <= mx[d])) return SS_ERR_INCONSISTENT_AABB;
+    float amin[3]; int64_t nc[3];
+    for (int d = 0; d < 3; ++d) {
+        amin[d] = fmulr(floorf(fdivr(mn[d], cell)), cell);
+        float ncr = ceilf(fdivr(fsubr(mx[d], amin[d]), cell));
+        if (!(ncr < 9.0e18f)) return SS_ERR_INDEX_TOO_SMALL;
+        int64_t n = (int64_t)ncr;
+        nc[d] = n > 1 ? n : 1;
+    }
+    return grid_new(g, amin, nc, cell);
+}
+static void grid_to_abi(const HostGrid &g, ss_grid_f32 *o) {
+    for (int d = 0; d < 3; ++d) { o->aabb_min[d] = g.mn[d]; o->aabb_max[d] = g.mx[d]; o->points_per_dim[d] = g.np[d]; o->cells_per_dim[d] = g.nc[d]; }
+    o->cell_size = g.cell;
+}
+
+static int validate_params(const ss_params_f32 *p) {
+    if (!p) return ss_fail(SS_ERR_INVALID_PARAMETER, "params is NULL");
+    if (!(p->cube_size > 0.0f)) return ss_fail(SS_ERR_INVALID_CELL_SIZE, "invalid cell size supplied, cell size has to be larger than zero");
+    if (!(p->compact_support_radius > 0.0f)) return ss_fail(SS_ERR_INVALID_PARAMETER, "compact support radius has to be positive (search radius for neighborhood search has to be positive)");
+    if (!(p->particle_radius > 0.0f)) return ss_fail(SS_ERR_INVALID_PARAMETER, "particle radius has to be positive");
+    if (p->global_neighborhood_list) return ss_fail(SS_ERR_UNSUPPORTED, "global_neighborhood_list is not provided by the device path");
+    if (p->spatial_decomposition == 1 && p->subdomain_num_cubes_per_dim < 1) return ss_fail(SS_ERR_INVALID_PARAMETER, "subdomain_num_cubes_per_dim has to be >= 1");
+    return SS_OK;
+}
+
+// ------------------------------------------------------------------ small launch helpers ----
+static inline unsigned nblk(uint64_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
+#define LAUNCH(ctx, kern, grid, block, ...) do { kern<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__); (ctx)->launches++; } while (0)
+
+static void cub_sort_pairs(ss_context *c, const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout,
+                           uint32_t n, int end_bit) {
+    size_t tmp = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, kin, kout, vin, vout, (int)n, 0, end_bit, c->stream));
+    c->cub_tmp.ensure(tmp);
+    CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, kin, kout, vin, vout, (int)n, 0, end_bit, c->stream));
+    c->launches += 1 + (uint64_t)((end_bit + 7) / 8) * 2;   // upsweep/onesweep histogram + per-digit passes (approx.)
+}
+static void cub_excl_scan(ss_context *c, const uint32_t *in, uint32_t *out, uint32_t n) {
+    size_t tmp = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, (int)n, c->stream));
+    c->cub_tmp.ensure(tmp);
+    CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, in, out, (int)n, c->stream));
+    c->launches += 2;
+}
+static void cub_incl_scan(ss_context *c, const uint32_t *in, uint32_t *out, uint32_t n) {
+    size_t tmp = 0;
+    CK(cub::DeviceScan::InclusiveSum(nullptr, tmp, in, out, (int)n, c->stream));
+    c->cub_tmp.ensure(tmp);
+    CK(cub::DeviceScan::InclusiveSum(c->cub_tmp.p, tmp, in, out, (int)n, c->stream));
+    c->launches += 2;
+}
+static int bits_for(uint64_t maxval) { int b = 1; while (b < 64 && (maxval >> b)) ++b; return b; }
+
+// ------------------------------------------------------------------ context ----
+extern "C" int ss_abi_version(void) { return SS_ABI_VERSION; }
+extern "C" const char *ss_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int ss_context_create(int device, ss_context **out) {
+    if (!out) return ss_fail(SS_ERR_INVALID_PARAMETER, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return ss_fail(SS_ERR_NO_DEVICE, std::string("no CUDA device available (") + cudaGetErrorString(e) + "); this library has no CPU path");
+    try {
+        if (device < 0) CK(cudaGetDevice(&device));
+        if (device >= ndev) return ss_fail(SS_ERR_INVALID_PARAMETER, "device index out of range");
+        CK(cudaSetDevice(device));
+        ss_context *c = new ss_context();
+        c->device = device;
+        CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
+        CK(cudaMemcpyToSymbol(c_tri_table, SS_MC_TRI_TABLE, sizeof(SS_MC_TRI_TABLE)));
+        CK(cudaMemcpyToSymbol(c_num_tris, SS_MC_NUM_TRIS, sizeof(SS_MC_NUM_TRIS)));
+        *out = c;
+        return SS_OK;
+    } catch (const SsCudaError &err) {
+        return ss_fail(SS_ERR_CUDA, std::string(err.what) + ": " + cudaGetErrorString(err.e));
+    }
+}
+
+extern "C" void ss_context_destroy(ss_context *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf *bufs[] = { &c->xyz, &c->xyz_f, &c->filt_flag, &c->filt_flag32, &c->filt_off, &c->aabb, &c->cnt, &c->off, &c->key_a, &c->key_b,
+                       &c->val_a, &c->val_b, &c->cid, &c->cub_tmp, &c->sub_flat, &c->sub_off, &c->sub_sparse, &c->flags, &c->scan,
+                       &c->spos, &c->rho, &c->tab_a, &c->tab_b, &c->rec, &c->ksplit, &c->batch_subs, &c->tiles, &c->vcnt, &c->tcnt,
+                       &c->vmask, &c->bkeys_a, &c->bkeys_b, &c->bids_a, &c->bids_b, &c->bcount, &c->remap, &c->keep, &c->newid,
+                       &c->err, &c->pairs };
+    for (DevBuf *b : bufs) b->release();
+    for (auto &ev : c->ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int ss_context_keep_levelset_tile(ss_context *c, int64_t flat) { if (!c) return SS_ERR_INVALID_PARAMETER; c->keep_tile_flat = flat; return SS_OK; }
+extern "C" int ss_context_set_tile_batch(ss_context *c, uint32_t m) { if (!c) return SS_ERR_INVALID_PARAMETER; c->max_tiles = m; return SS_OK; }
+
+// ------------------------------------------------------------------ stage: input, filter, AABB, grid ----
+struct Prepared {
+    const float *d_xyz = nullptr;   // filtered particles on device
+    uint64_t n = 0;
+    HostGrid grid{};
+    float upload_ms = 0.f;
+};
+
+static int prepare_particles(ss_context *c, const float *xyz, uint64_t n_in, const ss_params_f32 *p, Prepared &P,
+                             std::vector<uint8_t> *inside_out) {
+    if (n_in > 0xfffffff0ull) return ss_fail(SS_ERR_INDEX_TOO_SMALL, "more than 2^32 particles are not supported by one device");
+    const float *d_in = nullptr;
+    cudaPointerAttributes attr{};
+    bool on_device = false;
+    if (xyz && n_in) {
+        cudaError_t e = cudaPointerGetAttributes(&attr, xyz);
+        if (e == cudaSuccess && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged)) on_device = true;
+        else cudaGetLastError();
+    }
+    CK(cudaEventRecord(c->ev[0], c->stream));
+    if (on_device) d_in = xyz;
+    else if (n_in) {
+        c->xyz.ensure(n_in * 12);
+        CK(cudaMemcpyAsync(c->xyz.p, xyz, n_in * 12, cudaMemcpyHostToDevice, c->stream));
+        d_in = c->xyz.as<float>();
+    }
+    CK(cudaEventRecord(c->ev[1], c->stream));
+    P.d_xyz = d_in; P.n = n_in;
+    // particle AABB filter, lib.rs:369-406
+    if (p->has_particle_aabb && n_in) {
+        c->filt_flag.ensure(n_in); c->filt_flag32.ensure(n_in * 4); c->filt_off.ensure(n_in * 4 + 4);
+        float3 mn = make_float3(p->particle_aabb_min[0], p->particle_aabb_min[1], p->particle_aabb_min[2]);
+        float3 mx = make_float3(p->particle_aabb_max[0], p->particle_aabb_max[1], p->particle_aabb_max[2]);
+        LAUNCH(c, k_filter_flags, nblk(n_in, 256), 256, d_in, n_in, mn, mx, c->filt_flag.as<uint8_t>(), c->filt_flag32.as<uint32_t>());
+        cub_excl_scan(c, c->filt_flag32.as<uint32_t>(), c->filt_off.as<uint32_t>(), (uint32_t)n_in);
+        uint32_t last_off = 0, last_flag = 0;
+        CK(cudaMemcpyAsync(&last_off, c->filt_off.as<uint32_t>() + (n_in - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(&last_flag, c->filt_flag32.as<uint32_t>() + (n_in - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        uint64_t nf = (uint64_t)last_off + last_flag;
+        c->xyz_f.ensure(std::max<uint64_t>(nf, 1) * 12);
+        LAUNCH(c, k_filter_scatter, nblk(n_in, 256), 256, d_in, n_in, c->filt_flag.as<uint8_t>(), c->filt_off.as<uint32_t>(), c->xyz_f.as<float>());
+        P.d_xyz = c->xyz_f.as<float>(); P.n = nf;
+        if (inside_out) {
+            inside_out->resize(n_in);
+            CK(cudaMemcpyAsync(inside_out->data(), c->filt_flag.p, n_in, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+        }
+    } else if (p->has_particle_aabb && inside_out) inside_out->clear();
+
+    // grid_for_reconstruction, lib.rs:476-516
+    float mn[3], mx[3];
+    if (p->has_particle_aabb) {
+        for (int d = 0; d < 3; ++d) { mn[d] = p->particle_aabb_min[d]; mx[d] = p->particle_aabb_max[d]; }
+    } else {
+        if (P.n == 0) { for (int d = 0; d < 3; ++d) mn[d] = mx[d] = 0.0f; }   // Aabb3d::zeros(), aabb.rs:29-30
+        else {
+            c->aabb.ensure(6 * sizeof(int));
+            int init[6] = { INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN };
+            CK(cudaMemcpyAsync(c->aabb.p, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+            unsigned blocks = std::min<uint64_t>(nblk(P.n, 256), 148 * 16);
+            LAUNCH(c, k_aabb, blocks, 256, P.d_xyz, P.n, c->aabb.as<int>());
+            int res[6];
+            CK(cudaMemcpyAsync(res, c->aabb.p, sizeof(res), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            for (int d = 0; d < 3; ++d) { mn[d] = ss_ord2f(res[d]); mx[d] = ss_ord2f(res[3 + d]); }
+        }
+        for (int d = 0; d < 3; ++d) { mn[d] = fsubr(mn[d], p->particle_radius); mx[d] = faddr(mx[d], p->particle_radius); }
+    }
+    // compute_kernel_evaluation_radius, density_map.rs:551-580
+    float half_cells = ceilf(fdivr(p->compact_support_radius, p->cube_size));
+    float margin = fmulr(fmulr(p->cube_size, half_cells), faddr(1.0f, sqrtf(FLT_EPSILON)));
+    for (int d = 0; d < 3; ++d) { mn[d] = fsubr(mn[d], margin); mx[d] = faddr(mx[d], margin); }
+    int rc = grid_from_aabb(P.grid, mn, mx, p->cube_size);
+    if (rc != SS_OK) return ss_fail(rc, rc == SS_ERR_DEGENERATE_AABB ? "degenerate AABB supplied, every dimension of the AABB has to have non-zero extents"
+                                        : rc == SS_ERR_INCONSISTENT_AABB ? "inconsistent AABB supplied" : "grid construction failed");
+    return SS_OK;
+}
+
+extern "C" int ss_grid_for_reconstruction_f32(ss_context *c, const float *xyz, uint64_t n, const ss_params_f32 *p, ss_grid_f32 *out) {
+    if (!c || !out) return ss_fail(SS_ERR_INVALID_PARAMETER, "NULL argument");
+    int rc = validate_params(p);
+    if (rc) return rc;
+    try {
+        CK(cudaSetDevice(c->device));
+        Prepared P;
+        rc = prepare_particles(c, xyz, n, p, P, nullptr);
+        if (rc) return rc;
+        grid_to_abi(P.grid, out);
+        return SS_OK;
+    } catch (const SsCudaError &err) {
+        return ss_fail(err.e == cudaErrorMemoryAllocation ? SS_ERR_OUT_OF_MEMORY : SS_ERR_CUDA,
+                       std::string(err.what) + ": " + cudaGetErrorString(err.e));
+    }
+}
+
+// ------------------------------------------------------------------ the subdomain-grid pipeline ----
+static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params_f32 *p, ss_surface *out) {
+    const uint64_t n = PP.n;
+    const float *d_xyz = PP.d_xyz;
+    cudaStream_t st = c->stream;
+
+    // ---- initialize_parameters, dense_subdomains.rs:89-244
+    const int64_t S = (int64_t)p->subdomain_num_cubes_per_dim;
+    const float h = p->compact_support_radius, cs = p->cube_size;
+    const float r2 = faddr(p->particle_radius, p->particle_radius);
+    const float rest_mass = fmulr(fmulr(fmulr(r2, r2), r2), p->rest_density);
+    const float margin = fmulr(fmulr(ceilf(fdivr(h, cs)), cs), 1.01f);
+    int64_t nsd[3], ncg[3];
+    for (int d = 0; d < 3; ++d) { nsd[d] = (PP.grid.nc[d] + S - 1) / S; ncg[d] = nsd[d] * S; }
+    HostGrid gg, sg;
+    int rc = grid_new(gg, PP.grid.mn, ncg, cs);
+    if (rc) return ss_fail(rc, "global marching cubes grid construction failed");
+    const float sub_size = fmulr(cs, (float)S);
+    rc = grid_new(sg, gg.mn, nsd, sub_size);
+    if (rc) return ss_fail(rc, "subdomain grid construction failed");
+    out->grid = gg; out->subgrid = sg; out->S = (int)S;
+
+    for (int d = 0; d < 3; ++d) {
+        if (gg.np[d] >= (1 << 20)) return ss_fail(SS_ERR_INDEX_TOO_SMALL, "more than 2^20 grid points per dimension are not supported by the device path");
+    }
+    if ((double)nsd[0] * (double)nsd[1] * (double)nsd[2] >= 2147483647.0) return ss_fail(SS_ERR_INDEX_TOO_SMALL, "too many subdomain slots");
+    if (S > 1024) return ss_fail(SS_ERR_INDEX_TOO_SMALL, "subdomain_num_cubes_per_dim > 1024 is not supported");
+
+    SsDev D{};
+    for (int d = 0; d < 3; ++d) { D.gmin[d] = gg.mn[d]; D.nsd[d] = (int)nsd[d]; }
+    D.c = cs; D.h = h; D.h2 = fmulr(h, h); D.h2m = fmulr(D.h2, 1.01f); D.thr = p->iso_surface_threshold;
+    D.rest_mass = rest_mass; D.sub_size = sub_size; D.margin = margin; D.grow = fmulr(margin, 1.5f);
+    D.S = (int)S; D.np = (int)S + 1;
+    D.R = (int)ceilf(fdivr(h, cs));
+    D.srad = (int)ceilf(fdivr(margin, sub_size));
+    if (D.srad > 8) return ss_fail(SS_ERR_INVALID_PARAMETER, "ghost margin spans more than 8 subdomains; increase subdomain_num_cubes_per_dim");
+    {   // kernel.rs:327-336 (AVX) and :61-66 (scalar)
+        D.a_hinv = fdivr(1.0f, h);
+        float rrr = fmulr(fmulr(h, h), h);
+        D.a_sigma = fdivr(8.0f, fmulr(SS_PI_F, rrr));
+        D.a_s2 = fmulr(2.0f, D.a_sigma); D.a_s6 = fmulr(6.0f, D.a_sigma); D.a_s12 = fmulr(12.0f, D.a_sigma);
+        D.s_sigma = fdivr(8.0f, rrr);
+        D.s_c_inner = fdivr(3.0f, fmulr(2.0f, SS_PI_F));
+        D.s_c_outer = fdivr(1.0f, fmulr(4.0f, SS_PI_F));
+        D.s_two_thirds = fdivr(2.0f, 3.0f);
+    }
+    D.nsD = (int)ceil(((double)S * cs + 3.0 * (double)margin) / (double)h) + 3;
+    D.ns_stride = D.nsD * D.nsD * D.nsD;
+    D.nb = (D.np + 7) / 8;
+    const double Rr = (double)h / (double)cs;
+    D.nlo = (int)ceil(Rr / 8.0);
+    D.nhi = (int)ceil((7.0 + Rr) / 8.0) - 1;
+    if (D.nlo < 1) D.nlo = 1;
+    if (D.nhi < 1) D.nhi = 1;
+    D.nbin = D.nb + D.nlo + D.nhi; D.nbin_sub = D.nbin * D.nbin * D.nbin;
+    D.inv_c = (float)(1.0 / (double)cs);
+    D.rr_cells = (float)(Rr * 1.001 + 0.01);
+    D.simd = p->enable_simd ? 1 : 0;
+    if ((D.nlo + D.nhi + 1) * (D.nlo + D.nhi + 1) > 128) return ss_fail(SS_ERR_INVALID_PARAMETER, "compact support spans too many cells (h / cube_size > ~40)");
+
+    CK(cudaEventRecord(c->ev[2], st));
+    out->nv = out->nt = 0; out->nsub = 0;
+    out->rho.ensure(std::max<uint64_t>(n, 1) * 4);
+    float *d_rho = out->rho.as<float>();
+    CK(cudaMemsetAsync(d_rho, 0, std::max<uint64_t>(n, 1) * 4, st));
+    if (n == 0) { for (int e = 3; e <= 9; ++e) CK(cudaEventRecord(c->ev[e], st)); CK(cudaStreamSynchronize(st)); return SS_OK; }
+
+    // ---- decomposition: memberships (owner + ghosts), stable sort by subdomain
+    c->cnt.ensure(n * 4); c->off.ensure(n * 4 + 4);
+    LAUNCH(c, k_classify_count, nblk(n, 256), 256, D, d_xyz, (uint32_t)n, c->cnt.as<uint32_t>());
+    cub_excl_scan(c, c->cnt.as<uint32_t>(), c->off.as<uint32_t>(), (uint32_t)n);
+    uint32_t lo = 0, lc = 0;
+    CK(cudaMemcpyAsync(&lo, c->off.as<uint32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&lc, c->cnt.as<uint32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const uint64_t M64 = (uint64_t)lo + lc;
+    if (M64 >= 0xfffffff0ull) return ss_fail(SS_ERR_INDEX_TOO_SMALL, "more than 2^32 subdomain memberships");
+    const uint32_t M = (uint32_t)M64;
+    if (M == 0) { for (int e = 3; e <= 9; ++e) CK(cudaEventRecord(c->ev[e], st)); CK(cudaStreamSynchronize(st)); return SS_OK; }
+    c->key_a.ensure((size_t)M * 4); c->key_b.ensure((size_t)M * 4); c->val_a.ensure((size_t)M * 4); c->val_b.ensure((size_t)M * 4);
+    LAUNCH(c, k_classify_fill, nblk(n, 256), 256, D, d_xyz, (uint32_t)n, c->off.as<uint32_t>(), c->key_a.as<uint32_t>(), c->val_a.as<uint32_t>());
+    const uint64_t nslots = (uint64_t)nsd[0] * nsd[1] * nsd[2];
+    cub_sort_pairs(c, c->key_a.as<uint32_t>(), c->key_b.as<uint32_t>(), c->val_a.as<uint32_t>(), c->val_b.as<uint32_t>(), M, bits_for(nslots));
+    // key_b = flat subdomain per membership (sorted), val_b = particle index (ascending inside a subdomain)
+    c->flags.ensure((size_t)M * 4); c->scan.ensure((size_t)M * 4); c->cid.ensure((size_t)M * 4);
+    LAUNCH(c, k_seg_flags, nblk(M, 256), 256, c->key_b.as<uint32_t>(), M, c->flags.as<uint32_t>());
+    cub_incl_scan(c, c->flags.as<uint32_t>(), c->scan.as<uint32_t>(), M);
+    uint32_t nsub = 0;
+    CK(cudaMemcpyAsync(&nsub, c->scan.as<uint32_t>() + (M - 1), 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    c->sub_flat.ensure((size_t)nsub * 4); c->sub_off.ensure((size_t)(nsub + 1) * 4); c->sub_sparse.ensure(nsub);
+    LAUNCH(c, k_seg_finish, nblk(M, 256), 256, c->key_b.as<uint32_t>(), M, c->scan.as<uint32_t>(), c->cid.as<uint32_t>(),
+           c->sub_flat.as<uint32_t>(), c->sub_off.as<uint32_t>());
+    std::vector<uint32_t> h_flat(nsub), h_off(nsub + 1);
+    CK(cudaMemcpyAsync(h_flat.data(), c->sub_flat.p, (size_t)nsub * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_off.data(), c->sub_off.p, (size_t)(nsub + 1) * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    // sparse classification, dense_subdomains.rs:1242-1251, :1590
+    uint64_t maxp = 0;
+    for (uint32_t s = 0; s < nsub; ++s) maxp = std::max<uint64_t>(maxp, h_off[s + 1] - h_off[s]);
+    const uint64_t sparse_limit = std::max<uint64_t>(maxp / 20, 100);
+    out->nsub = nsub; out->sub_flat.resize(nsub); out->sub_count.resize(nsub); out->sub_sparse.resize(nsub);
+    for (uint32_t s = 0; s < nsub; ++s) {
+        out->sub_flat[s] = h_flat[s]; out->sub_count[s] = h_off[s + 1] - h_off[s];
+        out->sub_sparse[s] = (out->sub_count[s] <= sparse_limit) ? 1 : 0;
+    }
+    CK(cudaMemcpyAsync(c->sub_sparse.p, out->sub_sparse.data(), nsub, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(c->ev[3], st));
+
+    // ---- densities: per-subdomain cell lists on the h-lattice, ordered neighbour sums
+    if ((uint64_t)nsub * (uint64_t)D.ns_stride >= 0xffffffffull || (uint64_t)nsub * (uint64_t)D.nbin_sub >= 0xffffffffull)
+        return ss_fail(SS_ERR_INDEX_TOO_SMALL, "too many non-empty subdomains for 32-bit cell keys");
+    c->err.ensure(4);
+    CK(cudaMemsetAsync(c->err.p, 0, 4, st));
+    // membership arrays: cid (compressed subdomain), val_b (particle); keys -> key_a, sorted -> key_b? key_b is in use
+    // (flat ids are no longer needed after cid): reuse key_b as sort output, val_a as sorted payload.
+    LAUNCH(c, k_ns_keys, nblk(M, 256), 256, D, d_xyz, M, c->cid.as<uint32_t>(), c->sub_flat.as<uint32_t>(), c->val_b.as<uint32_t>(),
+           c->key_a.as<uint32_t>(), c->err.as<int>());
+    const uint64_t ns_keys = (uint64_t)nsub * D.ns_stride;
+    cub_sort_pairs(c, c->key_a.as<uint32_t>(), c->key_b.as<uint32_t>(), c->val_b.as<uint32_t>(), c->val_a.as<uint32_t>(), M, bits_for(ns_keys));
+    c->tab_a.ensure(ns_keys * 4); c->tab_b.ensure(ns_keys * 4);
+    CK(cudaMemsetAsync(c->tab_a.p, 0xff, ns_keys * 4, st));
+    LAUNCH(c, k_mark_starts, nblk(M, 256), 256, c->key_b.as<uint32_t>(), M, c->tab_a.as<uint32_t>(), (uint32_t)ns_keys);
+    LAUNCH(c, k_run_counts, nblk(M, 256), 256, c->key_b.as<uint32_t>(), M, c->tab_b.as<uint32_t>(), (uint32_t)ns_keys);
+    c->spos.ensure((size_t)M * 16);
+    LAUNCH(c, k_gather_pos, nblk(M, 256), 256, d_xyz, c->val_a.as<uint32_t>(), M, c->spos.as<float4>());
+    LAUNCH(c, k_density, nblk(M, 128), 128, D, M, c->key_b.as<uint32_t>(), c->spos.as<float4>(), c->sub_flat.as<uint32_t>(),
+           c->tab_a.as<uint32_t>(), c->tab_b.as<uint32_t>(), d_rho);
+    CK(cudaEventRecord(c->ev[4], st));
+
+    // ---- splat binning: (subdomain, 8^3-point brick) bins + particle records
+    // val_b still holds the membership particle indices in subdomain order (stable input for the bin sort)
+    LAUNCH(c, k_bin_keys, nblk(M, 256), 256, D, d_xyz, M, c->cid.as<uint32_t>(), c->sub_flat.as<uint32_t>(), c->val_b.as<uint32_t>(),
+           c->key_a.as<uint32_t>());
+    cub_sort_pairs(c, c->key_a.as<uint32_t>(), c->key_b.as<uint32_t>(), c->val_b.as<uint32_t>(), c->val_a.as<uint32_t>(), M, 32);
+    const uint64_t bin_keys = (uint64_t)nsub * D.nbin_sub;
+    c->tab_a.ensure(bin_keys * 4); c->tab_b.ensure(bin_keys * 4);
+    CK(cudaMemsetAsync(c->tab_a.p, 0xff, bin_keys * 4, st));
+    LAUNCH(c, k_mark_starts, nblk(M, 256), 256, c->key_b.as<uint32_t>(), M, c->tab_a.as<uint32_t>(), (uint32_t)bin_keys);
+    LAUNCH(c, k_run_counts, nblk(M, 256), 256, c->key_b.as<uint32_t>(), M, c->tab_b.as<uint32_t>(), (uint32_t)bin_keys);
+    c->rec.ensure((size_t)M * 16); c->ksplit.ensure((size_t)M * 4);
+    LAUNCH(c, k_records, nblk(M, 256), 256, D, d_xyz, d_rho, M, c->key_b.as<uint32_t>(), c->val_a.as<uint32_t>(),
+           c->sub_flat.as<uint32_t>(), c->rec.as<float4>(), c->ksplit.as<int>());
+    int h_err = 0;
+    CK(cudaMemcpyAsync(&h_err, c->err.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(c->ev[5], st));
+    CK(cudaStreamSynchronize(st));
+    if (h_err) return ss_fail(SS_ERR_INVALID_PARAMETER, "particle outside of its subdomain's neighbourhood-search grid (reference: panic)");
+
+    // ---- level set + marching cubes over batches of subdomain tiles
+    const size_t np3 = (size_t)D.np * D.np * D.np;
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const size_t per_tile = np3 * (4 + 4 + 4 + 1) + 64;
+    size_t max_tiles = c->max_tiles ? c->max_tiles : std::max<size_t>(1, std::min<size_t>((free_b / 3) / per_tile, 4096));
+    max_tiles = std::min<size_t>(max_tiles, std::max<size_t>(1, (size_t)0x7fffffff / np3 / 2));
+    max_tiles = std::min<size_t>(max_tiles, nsub);
+    c->tiles.ensure(max_tiles * np3 * 4); c->vcnt.ensure(max_tiles * np3 * 4 + 4); c->tcnt.ensure(max_tiles * np3 * 4 + 4);
+    c->vmask.ensure(max_tiles * np3); c->batch_subs.ensure(max_tiles * 4);
+    c->bcount.ensure(4); c->pairs.ensure(8);
+    CK(cudaMemsetAsync(c->bcount.p, 0, 4, st));
+    CK(cudaMemsetAsync(c->pairs.p, 0, 8, st));
+    std::vector<uint32_t> h_batch(max_tiles);
+    uint64_t vtotal = 0, ttotal = 0;
+    size_t bcap = 1 << 16;
+    c->bkeys_a.ensure(bcap * 8); c->bids_a.ensure(bcap * 4);
+    size_t vcap = 1 << 16, tcap = 1 << 17;
+    out->verts.ensure(vcap * 12); out->vkeys.ensure(vcap * 8); out->tris.ensure(tcap * 12);
+    float ls_ms = 0.f, mc_ms = 0.f;
+    uint64_t ls_launches = 0;
+    out->tile.clear();
+    for (uint32_t s0 = 0; s0 < nsub; s0 += (uint32_t)max_tiles) {
+        const uint32_t nbatch = std::min<uint32_t>((uint32_t)max_tiles, nsub - s0);
+        for (uint32_t q = 0; q < nbatch; ++q) h_batch[q] = s0 + q;
+        CK(cudaMemcpyAsync(c->batch_subs.p, h_batch.data(), (size_t)nbatch * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(c->ev[10], st));
+        CK(cudaMemsetAsync(c->tiles.p, 0, (size_t)nbatch * np3 * 4, st));
+        SsLsArgs A{};
+        A.bin_start = c->tab_a.as<uint32_t>(); A.bin_end = c->tab_b.as<uint32_t>(); A.rec = c->rec.as<float4>();
+        A.ksplit = c->ksplit.as<int>(); A.pidx = c->val_a.as<uint32_t>(); A.sub_flat = c->sub_flat.as<uint32_t>();
+        A.sub_sparse = c->sub_sparse.as<uint8_t>(); A.batch_subs = c->batch_subs.as<uint32_t>(); A.tiles = c->tiles.as<float>();
+        A.pairs = c->pairs.as<unsigned long long>();
+        const unsigned nbricks = (unsigned)(D.nb * D.nb * D.nb);
+        LAUNCH(c, k_levelset, nbatch * nbricks, SS_LS_THREADS, D, A);
+        ++ls_launches;
+        CK(cudaEventRecord(c->ev[11], st));
+        // optional parity tap
+        if (c->keep_tile_flat >= 0) {
+            for (uint32_t q = 0; q < nbatch; ++q) if ((int64_t)h_flat[s0 + q] == c->keep_tile_flat) {
+                out->tile.resize(np3);
+                CK(cudaMemcpyAsync(out->tile.data(), c->tiles.as<float>() + (size_t)q * np3, np3 * 4, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+            }
+        }
+        // marching cubes: count, scan, emit
+        const uint32_t npts = (uint32_t)(nbatch * np3);
+        LAUNCH(c, k_mc_count, nblk(npts, 256), 256, D, c->tiles.as<float>(), npts, c->vcnt.as<uint32_t>(), c->tcnt.as<uint32_t>(), c->vmask.as<uint8_t>());
+        uint32_t lastv[2] = { 0, 0 }, lastt[2] = { 0, 0 };
+        CK(cudaMemcpyAsync(&lastv[1], c->vcnt.as<uint32_t>() + (npts - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&lastt[1], c->tcnt.as<uint32_t>() + (npts - 1), 4, cudaMemcpyDeviceToHost, st));
+        cub_excl_scan(c, c->vcnt.as<uint32_t>(), c->vcnt.as<uint32_t>(), npts);
+        cub_excl_scan(c, c->tcnt.as<uint32_t>(), c->tcnt.as<uint32_t>(), npts);
+        CK(cudaMemcpyAsync(&lastv[0], c->vcnt.as<uint32_t>() + (npts - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&lastt[0], c->tcnt.as<uint32_t>() + (npts - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const uint64_t bv = (uint64_t)lastv[0] + lastv[1], bt = (uint64_t)lastt[0] + lastt[1];
+        if (vtotal + bv >= 0xfffffff0ull || (ttotal + bt) * 3 >= 0xffffffffffull) return ss_fail(SS_ERR_INDEX_TOO_SMALL, "mesh too large for 32-bit vertex ids");
+        if (bv || bt) {
+            out->verts.grow_keep((vtotal + bv) * 12, vtotal * 12, st);
+            out->vkeys.grow_keep((vtotal + bv) * 8, vtotal * 8, st);
+            out->tris.grow_keep((ttotal + bt) * 12, ttotal * 12, st);
+            // boundary list can hold at most every vertex of the batch
+            uint32_t bc = 0;
+            CK(cudaMemcpyAsync(&bc, c->bcount.p, 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            c->bkeys_a.grow_keep(((size_t)bc + bv) * 8, (size_t)bc * 8, st);
+            c->bids_a.grow_keep(((size_t)bc + bv) * 4, (size_t)bc * 4, st);
+            SsMcOut O{};
+            O.verts = out->verts.as<float>(); O.tris = out->tris.as<uint32_t>(); O.vkeys = out->vkeys.as<unsigned long long>();
+            O.bkeys = c->bkeys_a.as<unsigned long long>(); O.bids = c->bids_a.as<uint32_t>(); O.bcount = c->bcount.as<uint32_t>();
+            O.vbase = (uint32_t)vtotal; O.tbase = (uint32_t)ttotal; O.bcap = (uint32_t)std::min<size_t>((size_t)bc + bv, 0xffffffffu);
+            LAUNCH(c, k_mc_emit, nblk(npts, 256), 256, D, c->tiles.as<float>(), npts, c->vcnt.as<uint32_t>(), c->tcnt.as<uint32_t>(),
+                   c->vmask.as<uint8_t>(), c->batch_subs.as<uint32_t>(), c->sub_flat.as<uint32_t>(), O);
+            vtotal += bv; ttotal += bt;
+        }
+        CK(cudaEventRecord(c->ev[6], st));
+        CK(cudaEventSynchronize(c->ev[6]));
+        float a = 0.f, b = 0.f;
+        CK(cudaEventElapsedTime(&a, c->ev[10], c->ev[11]));
+        CK(cudaEventElapsedTime(&b, c->ev[11], c->ev[6]));
+        ls_ms += a; mc_ms += b;
+    }
+    CK(cudaEventRecord(c->ev[7], st));
+
+    // ---- stitching: weld duplicated boundary vertices, compact, remap triangle indices
+    uint32_t bc = 0;
+    CK(cudaMemcpyAsync(&bc, c->bcount.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    uint64_t nv_final = vtotal;
+    if (vtotal && bc) {
+        c->bkeys_b.ensure((size_t)bc * 8); c->bids_b.ensure((size_t)bc * 4);
+        size_t tmp = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->bkeys_a.as<unsigned long long>(), c->bkeys_b.as<unsigned long long>(),
+                                           c->bids_a.as<uint32_t>(), c->bids_b.as<uint32_t>(), (int)bc, 0, 64, st));
+        c->cub_tmp.ensure(tmp);
+        CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, c->bkeys_a.as<unsigned long long>(), c->bkeys_b.as<unsigned long long>(),
+                                           c->bids_a.as<uint32_t>(), c->bids_b.as<uint32_t>(), (int)bc, 0, 64, st));
+        c->launches += 17;
+        c->remap.ensure(vtotal * 4); c->keep.ensure(vtotal * 4); c->newid.ensure(vtotal * 4 + 4);
+        LAUNCH(c, k_iota_keep, nblk(vtotal, 256), 256, (uint32_t)vtotal, c->remap.as<uint32_t>(), c->keep.as<uint32_t>());
+        LAUNCH(c, k_weld_runs, nblk(bc, 256), 256, c->bkeys_b.as<unsigned long long>(), c->bids_b.as<uint32_t>(), bc,
+               c->remap.as<uint32_t>(), c->keep.as<uint32_t>());
+        cub_excl_scan(c, c->keep.as<uint32_t>(), c->newid.as<uint32_t>(), (uint32_t)vtotal);
+        uint32_t lk = 0, ln = 0;
+        CK(cudaMemcpyAsync(&lk, c->keep.as<uint32_t>() + (vtotal - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&ln, c->newid.as<uint32_t>() + (vtotal - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        nv_final = (uint64_t)lk + ln;
+        // compact into fresh buffers (swap)
+        DevBuf nverts, nkeys;
+        nverts.ensure(std::max<uint64_t>(nv_final, 1) * 12); nkeys.ensure(std::max<uint64_t>(nv_final, 1) * 8);
+        LAUNCH(c, k_compact_verts, nblk(vtotal, 256), 256, (uint32_t)vtotal, c->keep.as<uint32_t>(), c->newid.as<uint32_t>(),
+               out->verts.as<float>(), out->vkeys.as<unsigned long long>(), nverts.as<float>(), nkeys.as<unsigned long long>());
+        LAUNCH(c, k_remap_tris, nblk(ttotal * 3, 256), 256, ttotal * 3, c->remap.as<uint32_t>(), c->newid.as<uint32_t>(), out->tris.as<uint32_t>());
+        CK(cudaStreamSynchronize(st));
+        out->verts.release(); out->vkeys.release();
+        out->verts = nverts; out->vkeys = nkeys;
+    }
+    out->nv = nv_final; out->nt = ttotal;
+    CK(cudaEventRecord(c->ev[8], st));
+    CK(cudaEventRecord(c->ev[9], st));
+    CK(cudaStreamSynchronize(st));
+
+    // ---- timings
+    ss_timings &T = out->tm;
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); T.decomposition = ms;
+    CK(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4])); T.density = ms;
+    CK(cudaEventElapsedTime(&ms, c->ev[4], c->ev[5])); T.binning = ms;
+    T.levelset = ls_ms; T.marching_cubes = mc_ms;
+    CK(cudaEventElapsedTime(&ms, c->ev[7], c->ev[8])); T.stitching = ms;
+    T.levelset_launches = ls_launches;
+    unsigned long long h_pairs = 0;
+    CK(cudaMemcpy(&h_pairs, c->pairs.p, 8, cudaMemcpyDeviceToHost));
+    T.levelset_pairs = (double)h_pairs;
+    return SS_OK;
+}
+
+// ------------------------------------------------------------------ public entry ----
+extern "C" int ss_reconstruct_surface_f32(ss_context *c, const float *xyz, uint64_t n_in, const ss_params_f32 *p, ss_surface **out) {
+    if (!c || !out) return ss_fail(SS_ERR_INVALID_PARAMETER, "NULL argument");
+    *out = nullptr;
+    int rc = validate_params(p);
+    if (rc) return rc;
+    if (n_in && !xyz) return ss_fail(SS_ERR_INVALID_PARAMETER, "xyz is NULL");
+    ss_surface *s = nullptr;
+    try {
+        CK(cudaSetDevice(c->device));
+        s = new ss_surface();
+        s->device = c->device; s->n_in = n_in;
+        c->launches = 0;
+        Prepared P;
+        rc = prepare_particles(c, xyz, n_in, p, P, &s->inside_aabb);
+        if (rc) { ss_surface_free(s); return rc; }
+        s->n = P.n; s->grid = P.grid;
+        // decomposition decision, lib.rs:421-464
+        int use_dec = 0;
+        if (p->spatial_decomposition == 1) {
+            if (p->auto_disable) {
+                int64_t mc = std::max(P.grid.nc[0], std::max(P.grid.nc[1], P.grid.nc[2]));
+                uint32_t with_margin = (uint32_t)(1.2 * (double)p->subdomain_num_cubes_per_dim);
+                use_dec = (uint64_t)mc > (uint64_t)with_margin;
+            } else use_dec = 1;
+        }
+        s->used_decomposition = use_dec;
+        if (!use_dec) {
+            ss_surface_free(s);
+            return ss_fail(SS_ERR_UNSUPPORTED, "global (non-decomposed) reconstruction path is not provided by this build; "
+                                               "use spatial_decomposition=1 with auto_disable=0");
+        }
+        rc = run_subdomain_grid(c, P, p, s);
+        if (rc) { ss_surface_free(s); return rc; }
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); s->tm.upload = ms;
+        CK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); s->tm.aabb_and_grid = ms;
+        CK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[9])); s->tm.total_device = ms;
+        s->tm.kernel_launches = c->launches;
+        *out = s;
+        return SS_OK;
+    } catch (const SsCudaError &err) {
+        if (s) ss_surface_free(s);
+        cudaGetLastError();
+        char buf[512];
+        snprintf(buf, sizeof(buf), "%s failed at %s:%d: %s", err.what, err.file, err.line, cudaGetErrorString(err.e));
+        return ss_fail(err.e == cudaErrorMemoryAllocation ? SS_ERR_OUT_OF_MEMORY : SS_ERR_CUDA, buf);
+    } catch (const std::bad_alloc &) {
+        if (s) ss_surface_free(s);
+        return ss_fail(SS_ERR_OUT_OF_MEMORY, "host allocation failed");
+    }
+}
+
+extern "C" void ss_surface_free(ss_surface *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    s->verts.release(); s->tris.release(); s->vkeys.release(); s->rho.release();
+    delete s;
+}
+
+// ------------------------------------------------------------------ accessors ----
+extern "C" uint64_t ss_surface_num_vertices(const ss_surface *s) { return s ? s->nv : 0; }
+extern "C" uint64_t ss_surface_num_triangles(const ss_surface *s) { return s ? s->nt : 0; }
+extern "C" uint64_t ss_surface_num_particles(const ss_surface *s) { return s ? s->n : 0; }
+extern "C" uint64_t ss_surface_num_subdomains(const ss_surface *s) { return s ? s->nsub : 0; }
+extern "C" int ss_surface_used_decomposition(const ss_surface *s) { return s ? s->used_decomposition : 0; }
+extern "C" int ss_surface_grid(const ss_surface *s, ss_grid_f32 *o) { if (!s || !o) return SS_ERR_INVALID_PARAMETER; grid_to_abi(s->grid, o); return SS_OK; }
+extern "C" int ss_surface_subdomain_grid(const ss_surface *s, ss_grid_f32 *o) {
+    if (!s || !o) return SS_ERR_INVALID_PARAMETER;
+    if (!s->used_decomposition) return ss_fail(SS_ERR_INVALID_PARAMETER, "no subdomain grid: decomposition was not used");
+    grid_to_abi(s->subgrid, o); return SS_OK;
+}
+static int copy_out(const ss_surface *s, void *dst, const void *src, size_t bytes) {
+    if (!s || (!dst && bytes)) return ss_fail(SS_ERR_INVALID_PARAMETER, "NULL argument");
+    if (!bytes) return SS_OK;
+    cudaSetDevice(s->device);
+    cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return ss_fail(SS_ERR_CUDA, cudaGetErrorString(e));
+    return SS_OK;
+}
+extern "C" int ss_surface_copy_vertices(const ss_surface *s, float *dst) { return copy_out(s, dst, s ? s->verts.p : nullptr, s ? s->nv * 12 : 0); }
+extern "C" int ss_surface_copy_triangles_u32(const ss_surface *s, uint32_t *dst) { return copy_out(s, dst, s ? s->tris.p : nullptr, s ? s->nt * 12 : 0); }
+extern "C" int ss_surface_copy_triangles_u64(const ss_surface *s, uint64_t *dst) {
+    if (!s || (!dst && s->nt)) return ss_fail(SS_ERR_INVALID_PARAMETER, "NULL argument");
+    if (!s->nt) return SS_OK;
+    cudaSetDevice(s->device);
+    void *tmp = nullptr;
+    if (cudaMalloc(&tmp, s->nt * 24) != cudaSuccess) return ss_fail(SS_ERR_OUT_OF_MEMORY, "cudaMalloc failed");
+    k_tris_to_u64<<<nblk(s->nt * 3, 256), 256>>>(s->nt * 3, s->tris.as<uint32_t>(), (unsigned long long *)tmp);
+    cudaError_t e = cudaMemcpy(dst, tmp, s->nt * 24, cudaMemcpyDeviceToHost);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return ss_fail(SS_ERR_CUDA, cudaGetErrorString(e));
+    return SS_OK;
+}
+extern "C" int ss_surface_copy_particle_densities(const ss_surface *s, float *dst) { return copy_out(s, dst, s ? s->rho.p : nullptr, s ? s->n * 4 : 0); }
+extern "C" int ss_surface_copy_particle_inside_aabb(const ss_surface *s, uint8_t *dst) {
+    if (!s || !dst) return SS_ERR_INVALID_PARAMETER;
+    if (s->inside_aabb.empty()) return ss_fail(SS_ERR_INVALID_PARAMETER, "no particle AABB was specified");
+    memcpy(dst, s->inside_aabb.data(), s->inside_aabb.size());
+    return SS_OK;
+}
+extern "C" const float *ss_surface_device_vertices(const ss_surface *s) { return s ? s->verts.as<float>() : nullptr; }
+extern "C" const uint32_t *ss_surface_device_triangles(const ss_surface *s) { return s ? s->tris.as<uint32_t>() : nullptr; }
+extern "C" const float *ss_surface_device_densities(const ss_surface *s) { return s ? s->rho.as<float>() : nullptr; }
+
+extern "C" int ss_surface_copy_vertex_edge_keys(const ss_surface *s, int64_t *dst) {
+    if (!s || (!dst && s->nv)) return SS_ERR_INVALID_PARAMETER;
+    std::vector<unsigned long long> k(s->nv);
+    int rc = copy_out(s, k.data(), s->vkeys.p, s->nv * 8);
+    if (rc) return rc;
+    for (uint64_t v = 0; v < s->nv; ++v) {
+        dst[4 * v] = (int64_t)((k[v] >> 42) & 0xfffff); dst[4 * v + 1] = (int64_t)((k[v] >> 22) & 0xfffff);
+        dst[4 * v + 2] = (int64_t)((k[v] >> 2) & 0xfffff); dst[4 * v + 3] = (int64_t)(k[v] & 3);
+    }
+    return SS_OK;
+}
+extern "C" int ss_surface_copy_subdomains(const ss_surface *s, int64_t *flat, uint64_t *count, uint8_t *sparse) {
+    if (!s) return SS_ERR_INVALID_PARAMETER;
+    for (uint64_t q = 0; q < s->nsub; ++q) {
+        if (flat) flat[q] = s->sub_flat[q];
+        if (count) count[q] = s->sub_count[q];
+        if (sparse) sparse[q] = s->sub_sparse[q];
+    }
+    return SS_OK;
+}
+extern "C" int ss_surface_copy_levelset_tile(const ss_surface *s, float *dst) {
+    if (!s || !dst) return SS_ERR_INVALID_PARAMETER;
+    if (s->tile.empty()) return ss_fail(SS_ERR_INVALID_PARAMETER, "no level-set tile was kept (ss_context_keep_levelset_tile)");
+    memcpy(dst, s->tile.data(), s->tile.size() * 4);
+    return SS_OK;
+}
+extern "C" int ss_surface_timings(const ss_surface *s, ss_timings *o) { if (!s || !o) return SS_ERR_INVALID_PARAMETER; *o = s->tm; return SS_OK; }
