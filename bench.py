@@ -1,0 +1,268 @@
+#!/usr/bin/env python3
+"""bench.py -- Mparticles/s of the reconstruct hot path (BASELINE.json metric) on N B200s of one node.
+
+A step = one full `reconstruct_surface` pass (decomposition -> densities -> level-set splat -> marching cubes ->
+stitching) over one synthetic particle cloud.  Workload at N=1: BASELINE configs[3], the 50 M-particle dam break the
+metric is quoted on (it fits one B200).  `value` is timed with the particles already resident in HBM (CUDA events on
+the library's stream around every step); `e2e` runs the same call through the C ABI with HOST buffers -- pinned input
+copied host->device and the mesh copied device->host inside the timed region.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--particles M] [--impl reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RECON_KW = dict(particle_radius=0.01, smoothing_length=2.0, cube_size=0.5, iso_surface_threshold=0.6)
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # 148 SMs x 128 FMA lanes x 2 flop x max SM clock (nominal)
+
+
+def measured_peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_cloud(n_target):
+    from splashsurf_b200 import synthetic as syn
+    if n_target >= 50_000_000:
+        return syn.dam_break_50m(), "synthetic dam-break 50 M (column 340x370x340 + sheet 1063x20x340, r=0.01, seed 3)"
+    return syn.dam_break_scaled(n_target, 0.01, 3), f"synthetic dam-break scaled to ~{n_target} particles (cfg-4 proportions, r=0.01, seed 3)"
+
+
+def time_reference(p, repeats):
+    """The reference's own CPU implementation (pysplashsurf 0.14.0 wheel, rayon + AVX2) on all host cores."""
+    import oracle
+    ps = oracle.reference()
+    best = None
+    for _ in range(repeats):
+        t = time.perf_counter()
+        r = ps.reconstruct_surface(p, particle_radius=RECON_KW["particle_radius"], smoothing_length=RECON_KW["smoothing_length"],
+                                   cube_size=RECON_KW["cube_size"], iso_surface_threshold=RECON_KW["iso_surface_threshold"],
+                                   multi_threading=True, simd=True, subdomain_grid=True, subdomain_num_cubes_per_dim=64)
+        dt = time.perf_counter() - t
+        best = dt if best is None else min(best, dt)
+        nv, nt = len(r.mesh.vertices), len(r.mesh.triangles)
+        del r
+    return best, nv, nt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import oracle
+    n_sample = args.ref_particles
+    p, desc = make_cloud(n_sample)
+    if not oracle.reference_available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (reference wheel) not present on this box"}))
+        return 0
+    for _ in range(min(args.warmup, 1)):
+        time_reference(p, 1)
+    times = []
+    for _ in range(args.steps):
+        dt, nv, nt = time_reference(p, 1)
+        times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    val = len(p) / (ms * 1e-3) / 1e6
+    line = {"impl": "reference", "metric": "Mparticles/s end-to-end reconstruct", "value": val, "unit": "Mparticles/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": "cfg-4 dam break (bounded sample): " + desc, "particles": int(len(p)),
+                                                            "r": 0.01, "cube_size": "0.5r", "smoothing_length": "2.0r", "subdomain_cubes": 64},
+            "cpu_baseline": {"value": val, "unit": "Mparticles/s", "cores": os.cpu_count(), "kind": "reference",
+                             "sample": f"{len(p)} particles of the same dam break, pysplashsurf 0.14.0 wheel (portable manylinux build, runtime AVX2), all host threads"},
+            "e2e": {"value": val, "unit": "Mparticles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+            "mesh": {"vertices": nv, "triangles": nt}}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--particles", type=int, default=50_000_400, help="target particle count of the dam break (default: cfg-4)")
+    ap.add_argument("--ref-particles", type=int, default=2_000_000, help="bounded sample for the CPU reference")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the reconstruct path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import splashsurf_b200 as ss
+    from splashsurf_b200 import distributed as ssd
+    ctx = ss.Context(local_rank)
+    params = ss.make_params(**RECON_KW)
+
+    # ---- workload (identical on every rank; each rank keeps its slab when world > 1)
+    p_all, desc = make_cloud(args.particles)
+    n_total = len(p_all)
+    runner = ssd.Runner(ctx, params, world, rank, local_rank)
+    p_local = runner.take_local(p_all)
+    del p_all
+    host_in = torch.from_numpy(p_local).pin_memory()
+    dev_in = host_in.cuda(non_blocking=False)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident steps
+    for _ in range(args.warmup):
+        res = runner.step(dev_in.data_ptr(), len(p_local), copy_out=False)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    dev_ms, ls_ms, launches, pairs, ls_launches = 0.0, 0.0, 0, 0.0, 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = runner.step(dev_in.data_ptr(), len(p_local), copy_out=False)
+        dev_ms += res["device_ms"]; ls_ms += res["timings"]["levelset"]; launches += res["launches"]
+        pairs += res["timings"]["levelset_pairs"]; ls_launches += res["timings"]["levelset_launches"]
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    clocks = sampler.stop()
+    stats = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    dev_ms_max, wall_ms_max = stats.tolist()
+    ms_per_step = dev_ms_max / args.steps
+    value = n_total / (ms_per_step * 1e-3) / 1e6
+    nv, nt = res["nv"], res["nt"]
+    stage = {k: round(v, 3) for k, v in res["timings"].items() if isinstance(v, float)}
+
+    # ---- end to end through the C ABI with host buffers (pinned input, mesh copied back)
+    for _ in range(min(args.warmup, 2)):
+        runner.step(host_in.data_ptr(), len(p_local), copy_out=True)
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(args.steps):
+        r2 = runner.step(host_in.data_ptr(), len(p_local), copy_out=True)
+        d2h = r2["d2h_bytes"]
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - t0)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = t.item() / args.steps
+    e2e_val = n_total / (e2e_ms * 1e-3) / 1e6
+
+    if rank == 0:
+        peak, peak_src = measured_peak_hbm()
+        n_sub = res["nsub"]
+        np3 = 65 ** 3
+        # algorithmic bytes of the level-set kernel per step: particle records (16 B pos+V, 4 B k_split, 4 B index) of every
+        # membership once + one f32 tile write per subdomain (16 g N + 4 P N)
+        ls_bytes = res["memberships"] * 24.0 + n_sub * np3 * 4.0
+        ls_s = (ls_ms / args.steps) * 1e-3
+        ach = ls_bytes / ls_s / 1e9 if ls_s > 0 else 0.0
+        flops = (pairs / args.steps) * 30.0
+        roof = {"bound": "hbm", "kernel": "k_levelset", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "peak_source": peak_src, "launches_per_step": ls_launches / args.steps, "ms_per_step": ls_ms / args.steps,
+                "algorithmic_bytes_per_step": ls_bytes,
+                "note": "the ordered level-set gather is FP32-issue bound, not HBM bound (SURVEY.md 8d): see fp32",
+                "fp32": {"achieved_tflops": flops / ls_s / 1e12 if ls_s > 0 else 0.0, "peak_tflops": FP32_PEAK_TFLOPS,
+                         "frac": (flops / ls_s / 1e12) / FP32_PEAK_TFLOPS if ls_s > 0 else 0.0,
+                         "model": "in-support particle-gridpoint pairs x 30 flop", "pairs_per_step": pairs / args.steps}}
+        line = {"metric": "Mparticles/s end-to-end reconstruct", "value": value, "unit": "Mparticles/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": ("cfg-4: " if n_total >= 50_000_000 else "cfg-4 (scaled): ") + desc, "particles": int(n_total), "r": 0.01,
+                           "cube_size": "0.5r", "smoothing_length": "2.0r", "iso": 0.6, "subdomain_cubes": 64,
+                           "parallelism": f"subdomain slabs x{world}" if world > 1 else "single GPU",
+                           "l2": "inputs (600 MB) and tiles (GBs) exceed the 126 MB L2; no flush needed"},
+                "mesh": {"vertices": int(nv), "triangles": int(nt), "subdomains": int(n_sub)},
+                "wall_ms_per_step": wall_ms_max / args.steps, "stage_ms_last_step": stage,
+                "e2e": {"value": e2e_val, "unit": "Mparticles/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(len(p_local) * 12 * world),
+                        "d2h_bytes_per_step": int(d2h)},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                import oracle
+                if oracle.reference_available():
+                    ps, _ = make_cloud(args.ref_particles)
+                    dt, _, _ = time_reference(ps, 2)
+                    line["cpu_baseline"] = {"value": len(ps) / dt / 1e6, "unit": "Mparticles/s", "cores": os.cpu_count(), "kind": "reference",
+                                            "sample": f"{len(ps)}-particle dam break (same generator), best of 2, pysplashsurf 0.14.0 wheel on all host threads"}
+                else:
+                    line["cpu_baseline"] = {"value": None, "unit": "Mparticles/s", "cores": os.cpu_count(), "kind": "reference", "sample": "oracle/_ref missing"}
+            except Exception as e:   # the baseline must never take the bench line down
+                line["cpu_baseline"] = {"value": None, "unit": "Mparticles/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -113,6 +113,15 @@ void ss_surface_free(ss_surface *s);
 int ss_grid_for_reconstruction_f32(ss_context *ctx, const float *xyz, uint64_t n, const ss_params_f32 *params,
                                    ss_grid_f32 *grid_out);
 
+/* Stage-level entry: density_grid_loop_auto / density_grid_loop_scalar (dense_subdomains.rs:715-847, both `pub`
+ * and driven by the reference's own bench fixture, benches/benches/bench_grid_loop.rs:203-262).  Evaluates the
+ * (S+1)^3 level-set tile (i-major, f32) of ONE subdomain from an explicit particle list -- accumulated in list
+ * order -- and explicit particle densities.  mode 0: arithmetic of the AVX2+FMA loop, 1: scalar loop.
+ * xyz / rho / tile_out may be host or device pointers. */
+int ss_levelset_tile_f32(ss_context *ctx, const float *xyz, const float *rho, uint64_t n, const float global_min[3],
+                         float cube_size, const int64_t subdomain_ijk[3], uint32_t subdomain_cubes,
+                         float compact_support_radius, float particle_rest_mass, int mode, float *tile_out);
+
 /* ---- result accessors (sizes first, then copies into caller-provided HOST buffers) ---- */
 uint64_t ss_surface_num_vertices(const ss_surface *s);
 uint64_t ss_surface_num_triangles(const ss_surface *s);

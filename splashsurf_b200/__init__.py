@@ -20,7 +20,7 @@ import numpy as np
 
 from . import build as _build
 
-__all__ = ["reconstruct_surface", "Context", "SurfaceReconstruction", "TriMesh3d", "UniformGrid", "Aabb3d",
+__all__ = ["reconstruct_surface", "density_grid_loop", "Context", "SurfaceReconstruction", "TriMesh3d", "UniformGrid", "Aabb3d",
            "SplashsurfError", "library_path", "load_library"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -101,6 +101,7 @@ def load_library():
     L.ss_context_keep_levelset_tile.argtypes = [vp, i64]
     L.ss_surface_timings.argtypes = [vp, C.POINTER(_Timings)]
     L.ss_context_set_tile_batch.argtypes = [vp, C.c_uint32]
+    L.ss_levelset_tile_f32.argtypes = [vp, vp, vp, u64, vp, C.c_float, vp, C.c_uint32, C.c_float, C.c_float, C.c_int, vp]
     if L.ss_abi_version() != 1:
         raise ImportError("libsplashsurf_b200.so ABI version mismatch")
     _LIB = L
@@ -310,3 +311,26 @@ def _collect(ctx: Context, s, n_in: int, p: _Params, debug: bool, tile: bool) ->
         _check(L, L.ss_surface_copy_levelset_tile(s, t.ctypes.data))
         res.levelset_tile = t
     return res
+
+
+def density_grid_loop(subdomain_particles, subdomain_particle_densities, *, global_min, cube_size, subdomain_ijk,
+                      subdomain_cubes: int, compact_support_radius: float, particle_rest_mass: float, simd: bool = True,
+                      context: Optional[Context] = None) -> np.ndarray:
+    """Level-set tile of one subdomain: the device counterpart of ``density_grid_loop_auto`` (simd=True) /
+    ``density_grid_loop_scalar`` (simd=False), splashsurf_lib/src/dense_subdomains.rs:715-847.
+    Returns the (S+1, S+1, S+1) float32 tile."""
+    ctx = context or default_context()
+    L = ctx._L
+    xyz = np.ascontiguousarray(subdomain_particles, dtype=np.float32).reshape(-1, 3)
+    rho = np.ascontiguousarray(subdomain_particle_densities, dtype=np.float32)
+    if len(rho) != len(xyz):
+        raise ValueError("one density per particle is required")
+    gmin = np.ascontiguousarray(global_min, dtype=np.float32)
+    sijk = np.ascontiguousarray(subdomain_ijk, dtype=np.int64)
+    S = int(subdomain_cubes)
+    out = np.empty((S + 1,) * 3, dtype=np.float32)
+    _check(L, L.ss_levelset_tile_f32(ctx._h, xyz.ctypes.data, rho.ctypes.data, len(xyz), gmin.ctypes.data,
+                                     C.c_float(float(np.float32(cube_size))), sijk.ctypes.data, S,
+                                     C.c_float(float(np.float32(compact_support_radius))),
+                                     C.c_float(float(np.float32(particle_rest_mass))), 0 if simd else 1, out.ctypes.data))
+    return out

@@ -33,10 +33,11 @@ struct SsDev {
     // neighbourhood-search grid bound and level-set binning
     int nsD, ns_stride;   // max NS cells per dim per subdomain, nsD^3
     int nb;               // bricks per dim = ceil(np / 8)
-    int nlo, nhi;         // candidate bins below / above a brick
-    int nbin, nbin_sub;   // bins per dim (nb+nlo+nhi), nbin^3
+    int be;               // bin edge in cells (multiple of 8; 8 unless h/c is large)
+    int nlo;              // bin index offset = ceil(R / be): local coordinate u lands in bin floor(u/be)+nlo
+    int nbin, nbin_sub;   // bins per dim, nbin^3
     float inv_c;          // 1/c (binning only; not parity relevant)
-    float rr_cells;       // h/c + slack (binning only)
+    float rr_cells;       // R + slack: particles farther than this from the tile are dropped (binning only)
     int simd;             // 1: AVX-path arithmetic for dense subdomains
 };
 
@@ -48,6 +49,8 @@ __host__ __device__ inline float ss_coord(float mn, int64_t i, float cell) {
     volatile float t = (float)i * cell; return mn + t;
 #endif
 }
+
+__host__ __device__ inline int ss_floor_div(int a, int b) { int q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
 
 __device__ __forceinline__ int ss_cell_of(float x, float mn, float cell) {
     return (int)floorf(__fdiv_rn(__fsub_rn(x, mn), cell));      // uniform_grid.rs:444-451

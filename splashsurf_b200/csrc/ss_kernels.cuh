@@ -251,8 +251,8 @@ k_density(SsDev P, uint32_t m, const uint32_t *__restrict__ key, const float4 *_
 }
 
 // ------------------------------------------------------------------ splat binning ----
-// Bins are 8x8x8-point bricks of the subdomain tile, extended by nlo/nhi halo bins.  Binning is only a
-// conservative cull: a particle farther than h from every tile point is dropped (key 0xffffffff).
+// Bins are cubes of `be` cells (8 = one 8x8x8-point brick, unless h/c is large) of the subdomain tile plus a halo.
+// Binning is only a conservative cull: a particle farther than h from every tile point is dropped (key 0xffffffff).
 __global__ void k_bin_keys(SsDev P, const float *__restrict__ xyz, uint32_t m, const uint32_t *__restrict__ cid,
                            const uint32_t *__restrict__ sub_flat, const uint32_t *__restrict__ pidx,
                            uint32_t *__restrict__ key) {
@@ -266,7 +266,7 @@ __global__ void k_bin_keys(SsDev P, const float *__restrict__ xyz, uint32_t m, c
     for (int d = 0; d < 3; ++d) {
         float u = (xyz[3 * (uint64_t)p + d] - g.smin[d]) * P.inv_c;        // local coordinate in cells
         if (u < -P.rr_cells || u > (float)P.S + P.rr_cells) drop = true;
-        int bb = (int)floorf(u * 0.125f) + P.nlo;
+        int bb = (int)floorf(u / (float)P.be) + P.nlo;
         bb = max(0, min(P.nbin - 1, bb));
         b[d] = bb;
     }
@@ -355,15 +355,17 @@ k_levelset(SsDev P, SsLsArgs A) {
     const bool sparse = A.sub_sparse[s] || !P.simd;
     const SsSubGeom g = ss_sub_geom(P, A.sub_flat[s]);
 
-    // ---- candidate runs: bins [bx-nlo, bx+nhi] x [by-..] with contiguous z ranges
-    const int nx = P.nlo + P.nhi + 1;
-    if (threadIdx.x < nx * nx) {
-        int ix = threadIdx.x / nx, iy = threadIdx.x % nx;
-        // bin index of brick b is b + nlo; neighbours b-nlo..b+nhi -> bin indices b .. b+nlo+nhi
-        int X = bx + ix, Y = by + iy, Z0 = bz, Z1 = bz + P.nlo + P.nhi;
+    // ---- candidate runs: bins overlapping [8b - R, 8b + 7 + R) per axis; z-ranges are contiguous in key order
+    const int xl = max(ss_floor_div(8 * bx - P.R, P.be) + P.nlo, 0), xh = min(ss_floor_div(8 * bx + 6 + P.R, P.be) + P.nlo, P.nbin - 1);
+    const int yl = max(ss_floor_div(8 * by - P.R, P.be) + P.nlo, 0), yh = min(ss_floor_div(8 * by + 6 + P.R, P.be) + P.nlo, P.nbin - 1);
+    const int zl = max(ss_floor_div(8 * bz - P.R, P.be) + P.nlo, 0), zh = min(ss_floor_div(8 * bz + 6 + P.R, P.be) + P.nlo, P.nbin - 1);
+    const int nxr = xh - xl + 1, nyr = yh - yl + 1;
+    const int nruns = nxr * nyr;                 // host guarantees <= 128
+    if ((int)threadIdx.x < nruns) {
+        int X = xl + (int)threadIdx.x / nyr, Y = yl + (int)threadIdx.x % nyr;
         uint32_t a = 0xffffffffu, b = 0;
         uint32_t base = s * (uint32_t)P.nbin_sub + (uint32_t)((X * P.nbin + Y) * P.nbin);
-        for (int Z = Z0; Z <= Z1; ++Z) {
+        for (int Z = zl; Z <= zh; ++Z) {
             uint32_t st = A.bin_start[base + Z];
             if (st != 0xffffffffu) { if (a == 0xffffffffu) a = st; b = A.bin_end[base + Z]; }
         }
@@ -372,11 +374,11 @@ k_levelset(SsDev P, SsLsArgs A) {
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t acc = 0;
-        for (int r = 0; r < nx * nx; ++r) { s_pre[r] = acc; acc += s_rng[1][r]; }
-        s_pre[nx * nx] = acc; s_nrun = nx * nx;
+        for (int r = 0; r < nruns; ++r) { s_pre[r] = acc; acc += s_rng[1][r]; }
+        s_pre[nruns] = acc; s_nrun = nruns;
     }
     __syncthreads();
-    const uint32_t C = s_pre[nx * nx];
+    const uint32_t C = s_pre[nruns];
     if (C == 0) return;                          // tile is pre-zeroed
 
     // ---- this lane's grid point

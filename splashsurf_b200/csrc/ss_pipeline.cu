@@ -295,6 +295,28 @@ extern "C" int ss_grid_for_reconstruction_f32(ss_context *c, const float *xyz, u
     }
 }
 
+// kernel.rs:327-336 (AVX-path constants) and :61-66 (scalar normalisation), evaluated in f32 like the reference
+static void fill_kernel_consts(SsDev &D, float h) {
+    D.a_hinv = fdivr(1.0f, h);
+    float rrr = fmulr(fmulr(h, h), h);
+    D.a_sigma = fdivr(8.0f, fmulr(SS_PI_F, rrr));
+    D.a_s2 = fmulr(2.0f, D.a_sigma); D.a_s6 = fmulr(6.0f, D.a_sigma); D.a_s12 = fmulr(12.0f, D.a_sigma);
+    D.s_sigma = fdivr(8.0f, rrr);
+    D.s_c_inner = fdivr(3.0f, fmulr(2.0f, SS_PI_F));
+    D.s_c_outer = fdivr(1.0f, fmulr(4.0f, SS_PI_F));
+    D.s_two_thirds = fdivr(2.0f, 3.0f);
+}
+// splat bins: cubes of `be` cells; a brick (8 points) gathers the bins overlapping [8b - R, 8b + 7 + R)
+static void fill_bins(SsDev &D, float cs) {
+    D.nb = (D.np + 7) / 8;
+    D.be = 8 * std::max(1, (7 + 2 * D.R + 39) / 40);
+    D.nlo = (D.R + D.be - 1) / D.be;
+    D.nbin = ss_floor_div(D.S + D.R, D.be) + D.nlo + 1;
+    D.nbin_sub = D.nbin * D.nbin * D.nbin;
+    D.inv_c = (float)(1.0 / (double)cs);
+    D.rr_cells = (float)D.R + 0.01f;
+}
+
 // ------------------------------------------------------------------ the subdomain-grid pipeline ----
 static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params_f32 *p, ss_surface *out) {
     const uint64_t n = PP.n;
@@ -331,29 +353,15 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     D.R = (int)ceilf(fdivr(h, cs));
     D.srad = (int)ceilf(fdivr(margin, sub_size));
     if (D.srad > 8) return ss_fail(SS_ERR_INVALID_PARAMETER, "ghost margin spans more than 8 subdomains; increase subdomain_num_cubes_per_dim");
-    {   // kernel.rs:327-336 (AVX) and :61-66 (scalar)
-        D.a_hinv = fdivr(1.0f, h);
-        float rrr = fmulr(fmulr(h, h), h);
-        D.a_sigma = fdivr(8.0f, fmulr(SS_PI_F, rrr));
-        D.a_s2 = fmulr(2.0f, D.a_sigma); D.a_s6 = fmulr(6.0f, D.a_sigma); D.a_s12 = fmulr(12.0f, D.a_sigma);
-        D.s_sigma = fdivr(8.0f, rrr);
-        D.s_c_inner = fdivr(3.0f, fmulr(2.0f, SS_PI_F));
-        D.s_c_outer = fdivr(1.0f, fmulr(4.0f, SS_PI_F));
-        D.s_two_thirds = fdivr(2.0f, 3.0f);
-    }
+    fill_kernel_consts(D, h);
     D.nsD = (int)ceil(((double)S * cs + 3.0 * (double)margin) / (double)h) + 3;
     D.ns_stride = D.nsD * D.nsD * D.nsD;
-    D.nb = (D.np + 7) / 8;
-    const double Rr = (double)h / (double)cs;
-    D.nlo = (int)ceil(Rr / 8.0);
-    D.nhi = (int)ceil((7.0 + Rr) / 8.0) - 1;
-    if (D.nlo < 1) D.nlo = 1;
-    if (D.nhi < 1) D.nhi = 1;
-    D.nbin = D.nb + D.nlo + D.nhi; D.nbin_sub = D.nbin * D.nbin * D.nbin;
-    D.inv_c = (float)(1.0 / (double)cs);
-    D.rr_cells = (float)(Rr * 1.001 + 0.01);
+    fill_bins(D, cs);
     D.simd = p->enable_simd ? 1 : 0;
-    if ((D.nlo + D.nhi + 1) * (D.nlo + D.nhi + 1) > 128) return ss_fail(SS_ERR_INVALID_PARAMETER, "compact support spans too many cells (h / cube_size > ~40)");
+    {
+        int per_axis = ss_floor_div(6 + D.R, D.be) - ss_floor_div(-D.R, D.be) + 2;
+        if (per_axis * per_axis > 128) return ss_fail(SS_ERR_INVALID_PARAMETER, "internal: too many candidate bin runs per brick");
+    }
 
     CK(cudaEventRecord(c->ev[2], st));
     out->nv = out->nt = 0; out->nsub = 0;
@@ -470,8 +478,8 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
         const uint32_t nbatch = std::min<uint32_t>((uint32_t)max_tiles, nsub - s0);
         for (uint32_t q = 0; q < nbatch; ++q) h_batch[q] = s0 + q;
         CK(cudaMemcpyAsync(c->batch_subs.p, h_batch.data(), (size_t)nbatch * 4, cudaMemcpyHostToDevice, st));
-        CK(cudaEventRecord(c->ev[10], st));
         CK(cudaMemsetAsync(c->tiles.p, 0, (size_t)nbatch * np3 * 4, st));
+        CK(cudaEventRecord(c->ev[10], st));
         SsLsArgs A{};
         A.bin_start = c->tab_a.as<uint32_t>(); A.bin_end = c->tab_b.as<uint32_t>(); A.rec = c->rec.as<float4>();
         A.ksplit = c->ksplit.as<int>(); A.pidx = c->val_a.as<uint32_t>(); A.sub_flat = c->sub_flat.as<uint32_t>();
@@ -581,6 +589,75 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     CK(cudaMemcpy(&h_pairs, c->pairs.p, 8, cudaMemcpyDeviceToHost));
     T.levelset_pairs = (double)h_pairs;
     return SS_OK;
+}
+
+// ------------------------------------------------------------------ stage-level entry: one level-set tile ----
+// density_grid_loop_auto / density_grid_loop_scalar (dense_subdomains.rs:715-847, both `pub`): the level-set tile of
+// ONE subdomain from an explicit particle list (in list order == ascending index) and explicit densities.
+__global__ void k_iota2(uint32_t n, uint32_t *__restrict__ a, uint32_t *__restrict__ zero) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    a[e] = e; zero[e] = 0;
+}
+extern "C" int ss_levelset_tile_f32(ss_context *c, const float *xyz, const float *rho, uint64_t n, const float global_min[3],
+                                    float cube_size, const int64_t subdomain_ijk[3], uint32_t S, float h, float rest_mass,
+                                    int mode, float *tile_out) {
+    if (!c || !tile_out || !global_min || !subdomain_ijk || (n && (!xyz || !rho))) return ss_fail(SS_ERR_INVALID_PARAMETER, "NULL argument");
+    if (!(cube_size > 0.0f) || !(h > 0.0f) || S < 1 || S > 1024) return ss_fail(SS_ERR_INVALID_PARAMETER, "bad tile parameters");
+    if (n >= 0x7fffffffull) return ss_fail(SS_ERR_INDEX_TOO_SMALL, "too many particles");
+    for (int d = 0; d < 3; ++d) if (subdomain_ijk[d] < 0 || subdomain_ijk[d] > 1000) return ss_fail(SS_ERR_INVALID_PARAMETER, "subdomain_ijk out of range");
+    try {
+        CK(cudaSetDevice(c->device));
+        cudaStream_t st = c->stream;
+        SsDev D{};
+        for (int d = 0; d < 3; ++d) { D.gmin[d] = global_min[d]; D.nsd[d] = (int)subdomain_ijk[d] + 1; }
+        D.c = cube_size; D.h = h; D.h2 = fmulr(h, h); D.h2m = fmulr(D.h2, 1.01f); D.rest_mass = rest_mass;
+        D.sub_size = fmulr(cube_size, (float)S); D.S = (int)S; D.np = (int)S + 1;
+        D.R = (int)ceilf(fdivr(h, cube_size));
+        fill_kernel_consts(D, h);
+        fill_bins(D, cube_size);
+        D.simd = mode == 0 ? 1 : 0;
+        const size_t np3 = (size_t)D.np * D.np * D.np;
+        c->tiles.ensure(np3 * 4);
+        CK(cudaMemsetAsync(c->tiles.p, 0, np3 * 4, st));
+        if (n) {
+            const uint32_t M = (uint32_t)n;
+            const uint32_t flat = (uint32_t)((subdomain_ijk[0] * D.nsd[1] + subdomain_ijk[1]) * D.nsd[2] + subdomain_ijk[2]);
+            c->xyz.ensure(n * 12); c->rho.ensure(n * 4);
+            CK(cudaMemcpyAsync(c->xyz.p, xyz, n * 12, cudaMemcpyDefault, st));
+            CK(cudaMemcpyAsync(c->rho.p, rho, n * 4, cudaMemcpyDefault, st));
+            c->key_a.ensure((size_t)M * 4); c->key_b.ensure((size_t)M * 4); c->val_a.ensure((size_t)M * 4); c->val_b.ensure((size_t)M * 4);
+            c->cid.ensure((size_t)M * 4); c->sub_flat.ensure(4); c->sub_sparse.ensure(1); c->batch_subs.ensure(4);
+            LAUNCH(c, k_iota2, nblk(M, 256), 256, M, c->val_b.as<uint32_t>(), c->cid.as<uint32_t>());
+            uint32_t zero = 0; uint8_t z8 = 0;
+            CK(cudaMemcpyAsync(c->sub_flat.p, &flat, 4, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(c->sub_sparse.p, &z8, 1, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(c->batch_subs.p, &zero, 4, cudaMemcpyHostToDevice, st));
+            LAUNCH(c, k_bin_keys, nblk(M, 256), 256, D, c->xyz.as<float>(), M, c->cid.as<uint32_t>(), c->sub_flat.as<uint32_t>(),
+                   c->val_b.as<uint32_t>(), c->key_a.as<uint32_t>());
+            cub_sort_pairs(c, c->key_a.as<uint32_t>(), c->key_b.as<uint32_t>(), c->val_b.as<uint32_t>(), c->val_a.as<uint32_t>(), M, 32);
+            const uint64_t bin_keys = (uint64_t)D.nbin_sub;
+            c->tab_a.ensure(bin_keys * 4); c->tab_b.ensure(bin_keys * 4);
+            CK(cudaMemsetAsync(c->tab_a.p, 0xff, bin_keys * 4, st));
+            LAUNCH(c, k_mark_starts, nblk(M, 256), 256, c->key_b.as<uint32_t>(), M, c->tab_a.as<uint32_t>(), (uint32_t)bin_keys);
+            LAUNCH(c, k_run_counts, nblk(M, 256), 256, c->key_b.as<uint32_t>(), M, c->tab_b.as<uint32_t>(), (uint32_t)bin_keys);
+            c->rec.ensure((size_t)M * 16); c->ksplit.ensure((size_t)M * 4);
+            LAUNCH(c, k_records, nblk(M, 256), 256, D, c->xyz.as<float>(), c->rho.as<float>(), M, c->key_b.as<uint32_t>(), c->val_a.as<uint32_t>(),
+                   c->sub_flat.as<uint32_t>(), c->rec.as<float4>(), c->ksplit.as<int>());
+            SsLsArgs A{};
+            A.bin_start = c->tab_a.as<uint32_t>(); A.bin_end = c->tab_b.as<uint32_t>(); A.rec = c->rec.as<float4>();
+            A.ksplit = c->ksplit.as<int>(); A.pidx = c->val_a.as<uint32_t>(); A.sub_flat = c->sub_flat.as<uint32_t>();
+            A.sub_sparse = c->sub_sparse.as<uint8_t>(); A.batch_subs = c->batch_subs.as<uint32_t>(); A.tiles = c->tiles.as<float>();
+            A.pairs = nullptr;
+            LAUNCH(c, k_levelset, (unsigned)(D.nb * D.nb * D.nb), SS_LS_THREADS, D, A);
+        }
+        CK(cudaMemcpyAsync(tile_out, c->tiles.p, np3 * 4, cudaMemcpyDefault, st));
+        CK(cudaStreamSynchronize(st));
+        return SS_OK;
+    } catch (const SsCudaError &err) {
+        cudaGetLastError();
+        return ss_fail(err.e == cudaErrorMemoryAllocation ? SS_ERR_OUT_OF_MEMORY : SS_ERR_CUDA, std::string(err.what) + ": " + cudaGetErrorString(err.e));
+    }
 }
 
 // ------------------------------------------------------------------ public entry ----

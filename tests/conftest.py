@@ -1,0 +1,43 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `pytest -m gpu`)")
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+    d = {k: z[k] for k in z.files}
+    if "kwargs" in d:
+        d["kwargs"] = json.loads(str(d["kwargs"]))
+    return d
+
+
+@pytest.fixture(scope="session")
+def oracle_mod():
+    import oracle
+    oracle.build()
+    return oracle
+
+
+@pytest.fixture(scope="session")
+def ss():
+    """The product package with its CUDA library built and loaded (no compute without a GPU)."""
+    import splashsurf_b200
+    from splashsurf_b200 import build
+    build.build()
+    splashsurf_b200.load_library()
+    return splashsurf_b200
+
+
+MESH_CASES = ["cfg1_ref", "cube16_ref", "cube16_scalar_ref", "splash_small_ref", "splash_aabb_ref"]

@@ -1,0 +1,61 @@
+"""CPU tests of the drop-in boundary: the C-ABI library builds, loads, exports every symbol the header declares,
+and refuses to run without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "splashsurf_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(ss_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol(ss):
+    L = ss.load_library()
+    names = declared_symbols()
+    assert "ss_reconstruct_surface_f32" in names and "ss_levelset_tile_f32" in names and len(names) >= 25
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/splashsurf_b200.h but not exported"
+    assert L.ss_abi_version() == 1
+
+
+def test_params_struct_layout_matches_header(ss):
+    # 5 floats, i32, 2x3 floats, 3 x i32, u32, 2 x i32  = 68 bytes, no padding
+    assert C.sizeof(ss._Params) == 4 * (5 + 1 + 6 + 3 + 1 + 2)
+    assert C.sizeof(ss._Grid) == 4 * 7 + 4 + 8 * 6     # 7 floats (+4 pad) + 6 int64
+
+
+def test_no_cpu_fallback_without_gpu(ss):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(ss.SplashsurfError) as e:
+        ss.Context()
+    assert e.value.code == 101          # SS_ERR_NO_DEVICE
+    with pytest.raises(ss.SplashsurfError):
+        ss.reconstruct_surface(np.zeros((4, 3), np.float32), particle_radius=0.025, smoothing_length=2.0, cube_size=0.5)
+
+
+def test_front_end_parameter_mapping(ss):
+    """pysplashsurf multiplies smoothing_length and cube_size by the particle radius in f64, then casts to f32
+    (pysplashsurf/src/reconstruction.rs:172-176)."""
+    p = ss.make_params(particle_radius=0.025, smoothing_length=2.2, cube_size=1.1)
+    assert p.compact_support_radius == float(np.float32(2.0 * 2.2 * 0.025))
+    assert p.cube_size == float(np.float32(1.1 * 0.025))
+    assert p.spatial_decomposition == 1 and p.auto_disable == 1 and p.subdomain_num_cubes_per_dim == 64
+    with pytest.raises(TypeError):
+        ss.reconstruct_surface(np.zeros((4, 3), np.float64), particle_radius=0.025, smoothing_length=2.0, cube_size=0.5)
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "splashsurf_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
