@@ -87,7 +87,8 @@ typedef struct ss_timings {
     float total_device;          /* first kernel to last kernel */
     uint64_t kernel_launches;    /* kernels of this library launched (cub passes included) */
     uint64_t levelset_launches;  /* launches of the level-set kernel */
-    double levelset_pairs;       /* particle-gridpoint pairs evaluated inside support (work model) */
+    uint64_t levelset_fixup_points; /* certified points re-evaluated exactly because they touch the surface */
+    double levelset_pairs;       /* in-support particle-gridpoint evaluations (only with ss_context_set_count_pairs) */
 } ss_timings;
 
 typedef struct ss_context ss_context;   /* device + stream + reusable device buffers */
@@ -154,8 +155,15 @@ int ss_surface_copy_levelset_tile(const ss_surface *s, float *dst);
 /* Timings / launch counts of the reconstruction that produced `s`. */
 int ss_surface_timings(const ss_surface *s, ss_timings *out);
 
-/* Tuning knobs (do not change results): maximum number of subdomain tiles resident at once. */
+/* Tuning knobs (do not change results).
+ * - maximum number of subdomain tiles resident at once;
+ * - level-set evaluation: by default grid points that are provably inside the fluid (a partial sum of the
+ *   non-negative kernel terms already exceeds the threshold) are only classified, and every point on a
+ *   surface-crossing edge is evaluated exactly; `exact_everywhere` evaluates every point exactly like the reference;
+ * - count_pairs: count in-support kernel evaluations into ss_timings.levelset_pairs (instrumented kernel). */
 int ss_context_set_tile_batch(ss_context *ctx, uint32_t max_tiles);
+int ss_context_set_levelset_exact_everywhere(ss_context *ctx, int on);
+int ss_context_set_count_pairs(ss_context *ctx, int on);
 
 #ifdef __cplusplus
 }

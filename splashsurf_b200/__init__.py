@@ -54,7 +54,7 @@ class _Timings(C.Structure):
     _fields_ = [("upload", C.c_float), ("aabb_and_grid", C.c_float), ("decomposition", C.c_float), ("density", C.c_float),
                 ("binning", C.c_float), ("levelset", C.c_float), ("marching_cubes", C.c_float), ("stitching", C.c_float),
                 ("total_device", C.c_float), ("kernel_launches", C.c_uint64), ("levelset_launches", C.c_uint64),
-                ("levelset_pairs", C.c_double)]
+                ("levelset_fixup_points", C.c_uint64), ("levelset_pairs", C.c_double)]
 
 
 _LIB = None
@@ -101,6 +101,8 @@ def load_library():
     L.ss_context_keep_levelset_tile.argtypes = [vp, i64]
     L.ss_surface_timings.argtypes = [vp, C.POINTER(_Timings)]
     L.ss_context_set_tile_batch.argtypes = [vp, C.c_uint32]
+    L.ss_context_set_levelset_exact_everywhere.argtypes = [vp, C.c_int]
+    L.ss_context_set_count_pairs.argtypes = [vp, C.c_int]
     L.ss_levelset_tile_f32.argtypes = [vp, vp, vp, u64, vp, C.c_float, vp, C.c_uint32, C.c_float, C.c_float, C.c_int, vp]
     if L.ss_abi_version() != 1:
         raise ImportError("libsplashsurf_b200.so ABI version mismatch")
@@ -189,6 +191,13 @@ class Context:
 
     def set_tile_batch(self, max_tiles: int):
         _check(self._L, self._L.ss_context_set_tile_batch(self._h, int(max_tiles)))
+
+    def set_levelset_exact_everywhere(self, on: bool):
+        """Evaluate every level-set grid point exactly (default: interior points are only classified)."""
+        _check(self._L, self._L.ss_context_set_levelset_exact_everywhere(self._h, int(bool(on))))
+
+    def set_count_pairs(self, on: bool):
+        _check(self._L, self._L.ss_context_set_count_pairs(self._h, int(bool(on))))
 
     def reconstruct_raw(self, xyz_ptr: int, n: int, params: _Params):
         """Low-level call: pointer (host or device) to n x 3 f32 -> opaque surface handle."""

@@ -23,6 +23,7 @@ struct SsDev {
     float margin;         // ghost particle margin
     float grow;           // margin * 1.5f (neighbourhood-search domain growth)
     int S, np;            // cubes per subdomain, points per subdomain (S+1)
+    uint32_t np_magic;    // floor(2^32 / np) + 1: l / np == umulhi(l, np_magic) for l < np^2
     int nsd[3];           // subdomains per dimension
     int R;                // cube_radius = ceil(h/c)
     int srad;             // subdomain radius for ghost classification

@@ -296,98 +296,160 @@ __global__ void k_records(SsDev P, const float *__restrict__ xyz, const float *_
 
 // ------------------------------------------------------------------ level set ----
 #define SS_LS_THREADS 512
-#define SS_LS_CAP 1024          // candidates staged per pass
+#define SS_LS_WARPS (SS_LS_THREADS / 32)
+#define SS_LS_CAP 512            // candidates staged per brick; larger bricks take the slow exact path
+#define SS_MARKER 3.0e38f        // "certified inside, exact value not computed" (always > threshold)
+
+enum { SS_LS_EXACT_ALL = 0, SS_LS_CERTIFY = 1, SS_LS_FIX = 2 };
+
+// per-tile constants of a batch, filled on the host (exact f32)
+struct SsTile {
+    int gbase[3];        // global point index of the tile's point (0,0,0): subdomain_ijk * S
+    uint32_t s;          // compressed subdomain id
+    uint32_t sparse;     // scalar-arithmetic subdomain (dense_subdomains.rs:1251, :1590) or simd disabled
+    float smin[3];       // subdomain aabb.min (marching cubes vertex coordinates)
+};
 
 struct SsLsArgs {
     const uint32_t *bin_start;   // [nsub * nbin_sub] run start or 0xffffffff
     const uint32_t *bin_end;     // [nsub * nbin_sub] run end
-    const float4 *rec;           // bin-sorted records
+    const float4 *rec;           // bin-sorted records (x, y, z, V)
     const int *ksplit;
     const uint32_t *pidx;        // bin-sorted particle indices
     const uint32_t *sub_flat;    // compressed -> flat
     const uint8_t *sub_sparse;   // compressed -> sparse flag
-    const uint32_t *batch_subs;  // compressed ids in this batch
+    const SsTile *tile_tab;      // [batch] per-tile constants (host-filled)
+    const int2 *brick_rng;       // [nb] candidate bin range (lo, hi) of brick b along one axis
+    const uint32_t *fix_bricks;  // SS_LS_FIX: list of flagged bricks (global brick index)
     float *tiles;                // [batch][np^3]
-    unsigned long long *pairs;   // work counter (in-support evaluations), optional
+    uint8_t *wflag;              // [batch][nb^3][16] warp boxes that need exact values (SS_LS_FIX)
+    unsigned long long *pairs;   // work counter (in-support evaluations), only with COUNT
+    int mode;
 };
 
-// Sorts the staged candidate keys ((pidx << 10) | slot) ascending: bitonic network in shared memory.
+// Sorts the staged candidate keys ((pidx << 32) | slot) ascending: bitonic network in shared memory.
 __device__ __forceinline__ void ss_bitonic(unsigned long long *keys, int n /* power of two */) {
     for (int k = 2; k <= n; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < n; t += blockDim.x) {
-                int ixj = t ^ j;
-                if (ixj > t) {
-                    unsigned long long a = keys[t], b = keys[ixj];
-                    bool up = ((t & k) == 0);
-                    if ((a > b) == up) { keys[t] = b; keys[ixj] = a; }
-                }
+            for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+                int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));      // index with bit j clear
+                int hi = lo | j;
+                unsigned long long a = keys[lo], b = keys[hi];
+                bool up = ((lo & k) == 0);
+                if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
             }
             __syncthreads();
         }
     }
 }
 
+// One exact accumulation step (the reference's arithmetic) of candidate `r` (x, y, z, V) into phi.
+template <bool SPARSE, bool UNIFORM_FMA>
+__device__ __forceinline__ void ss_accumulate(const SsDev &P, const float4 r, const int ks, const int k,
+                                              const float gx, const float gy, const float gz, float &phi, unsigned &hits) {
+    const float dx = __fsub_rn(r.x, gx), dy = __fsub_rn(r.y, gy), dz = __fsub_rn(r.z, gz);
+    if (!SPARSE) {
+        // dense_subdomains.rs:1071-1090 + :1110-1127
+        const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+        if (d2 < P.h2) {
+            const float wgt = ss_kernel_avx(P, __fsqrt_rn(d2));
+            if (UNIFORM_FMA) phi = __fmaf_rn(wgt, r.w, phi);
+            else phi = (k < ks) ? __fmaf_rn(wgt, r.w, phi) : __fadd_rn(phi, __fmul_rn(wgt, r.w));
+            ++hits;
+        }
+    } else {
+        // dense_subdomains.rs:828-842 / :1181-1194
+        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        if (d2 < P.h2m) {
+            phi = __fadd_rn(phi, __fmul_rn(r.w, ss_kernel_scalar(P, __fsqrt_rn(d2))));
+            ++hits;
+        }
+    }
+}
+
 // One CTA = one 8x8x8-point brick of one subdomain tile; one warp = a 2x4x4 point box; one lane = one point.
-// Per point, phi = ordered fold over the subdomain's particles in ascending global index of
+//
+// Exact value of a point: phi = ordered fold over the subdomain's particles in ascending global index of
 //     dense : phi = fma(W_avx(r), V, phi)  (or phi + W*V for the 8-lane remainder)   dense_subdomains.rs:1106-1128
 //     sparse: phi = phi + V * W_scalar(r)                                            dense_subdomains.rs:1184-1194
-// restricted to particles with d^2 < h^2 (dense) / d^2 < 1.01 h^2 (scalar).  Candidates come from the
-// brick's neighbouring bins, are sorted by global index in shared memory, and each warp walks only the
-// candidates within h of its own point box.
-__global__ void __launch_bounds__(SS_LS_THREADS)
+// restricted to particles with d^2 < h^2 (dense) / d^2 < 1.01 h^2 (scalar).  Candidates come from the brick's
+// neighbouring bins; each warp walks only the candidates within h of its own point box, in ascending index.
+//
+// Certification (SS_LS_CERTIFY): every term is >= 0, so the reference's value is >= any partial sum of its terms
+// (up to ~1e-6 relative rounding).  A warp first sums -- with fast arithmetic, in any order -- the candidates
+// within 0.55 h of its box; if every lane already exceeds threshold * (1 + 1e-4) all 32 points are provably inside
+// and only SS_MARKER is stored.  Otherwise the warp evaluates all its points exactly.  k_fixup_flags then finds
+// marker points that touch an outside point (a surface-crossing edge needs both exact endpoints) and a second
+// launch (SS_LS_FIX) evaluates those warp boxes exactly.
+template <bool COUNT>
+__global__ void __launch_bounds__(SS_LS_THREADS, 3)
 k_levelset(SsDev P, SsLsArgs A) {
     __shared__ float4 s_rec[SS_LS_CAP];
     __shared__ int s_ks[SS_LS_CAP];
     __shared__ unsigned long long s_key[SS_LS_CAP];
-    __shared__ uint32_t s_rng[2][128];          // candidate runs (start, end)
+    __shared__ unsigned short s_list[SS_LS_WARPS][SS_LS_CAP];
+    __shared__ uint32_t s_rng[2][128];          // candidate runs (start, length)
     __shared__ uint32_t s_pre[129];
-    __shared__ uint32_t s_mask[SS_LS_THREADS / 32][SS_LS_CAP / 32];
-    __shared__ int s_nrun;
 
     const int nb = P.nb;
-    int brick = blockIdx.x;
-    const int bz = brick % nb; brick /= nb;
-    const int by = brick % nb; brick /= nb;
-    const int bx = brick % nb; brick /= nb;
-    const uint32_t s = A.batch_subs[brick];
-    const int tile_idx = brick;
-    const bool sparse = A.sub_sparse[s] || !P.simd;
-    const SsSubGeom g = ss_sub_geom(P, A.sub_flat[s]);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mode = A.mode;
+    int bx, by, bz, tile_idx;
+    uint32_t brick_lin;
+    if (mode == SS_LS_FIX) {
+        brick_lin = A.fix_bricks[blockIdx.x];
+        uint32_t q = brick_lin;
+        bz = (int)(q % (uint32_t)nb); q /= (uint32_t)nb;
+        by = (int)(q % (uint32_t)nb); q /= (uint32_t)nb;
+        bx = (int)(q % (uint32_t)nb); tile_idx = (int)(q / (uint32_t)nb);
+    } else {
+        bx = blockIdx.x; by = blockIdx.y;
+        tile_idx = (int)(blockIdx.z / (unsigned)nb); bz = (int)(blockIdx.z - (unsigned)tile_idx * (unsigned)nb);
+        brick_lin = (((uint32_t)tile_idx * nb + bx) * nb + by) * nb + bz;
+    }
+    const bool my_flag = (mode != SS_LS_FIX) || (A.wflag[(size_t)brick_lin * SS_LS_WARPS + warp] != 0);
+
+    const SsTile T = A.tile_tab[tile_idx];
+    const uint32_t s = T.s;
+    const bool sparse = T.sparse != 0;
 
     // ---- candidate runs: bins overlapping [8b - R, 8b + 7 + R) per axis; z-ranges are contiguous in key order
-    const int xl = max(ss_floor_div(8 * bx - P.R, P.be) + P.nlo, 0), xh = min(ss_floor_div(8 * bx + 6 + P.R, P.be) + P.nlo, P.nbin - 1);
-    const int yl = max(ss_floor_div(8 * by - P.R, P.be) + P.nlo, 0), yh = min(ss_floor_div(8 * by + 6 + P.R, P.be) + P.nlo, P.nbin - 1);
-    const int zl = max(ss_floor_div(8 * bz - P.R, P.be) + P.nlo, 0), zh = min(ss_floor_div(8 * bz + 6 + P.R, P.be) + P.nlo, P.nbin - 1);
-    const int nxr = xh - xl + 1, nyr = yh - yl + 1;
-    const int nruns = nxr * nyr;                 // host guarantees <= 128
+    const int2 rx = A.brick_rng[bx], ry = A.brick_rng[by], rz = A.brick_rng[bz];
+    const int nyr = ry.y - ry.x + 1;
+    const int nruns = (rx.y - rx.x + 1) * nyr;   // host guarantees <= 128
     if ((int)threadIdx.x < nruns) {
-        int X = xl + (int)threadIdx.x / nyr, Y = yl + (int)threadIdx.x % nyr;
+        int X = rx.x + (int)threadIdx.x / nyr, Y = ry.x + (int)threadIdx.x % nyr;
         uint32_t a = 0xffffffffu, b = 0;
         uint32_t base = s * (uint32_t)P.nbin_sub + (uint32_t)((X * P.nbin + Y) * P.nbin);
-        for (int Z = zl; Z <= zh; ++Z) {
+        for (int Z = rz.x; Z <= rz.y; ++Z) {
             uint32_t st = A.bin_start[base + Z];
             if (st != 0xffffffffu) { if (a == 0xffffffffu) a = st; b = A.bin_end[base + Z]; }
         }
         s_rng[0][threadIdx.x] = a; s_rng[1][threadIdx.x] = (a == 0xffffffffu) ? 0 : b - a;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t acc = 0;
-        for (int r = 0; r < nruns; ++r) { s_pre[r] = acc; acc += s_rng[1][r]; }
-        s_pre[nruns] = acc; s_nrun = nruns;
+    if (warp == 0) {
+        // exclusive prefix of the run lengths (<= 128 runs: 4 per lane)
+        uint32_t v[4], tot = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { int r = lane * 4 + q; v[q] = r < nruns ? s_rng[1][r] : 0; tot += v[q]; }
+        uint32_t incl = tot;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
+        uint32_t run = incl - tot;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { int r = lane * 4 + q; if (r < nruns) s_pre[r] = run; run += v[q]; }
+        if (lane == 31) s_pre[128] = incl;
     }
     __syncthreads();
-    const uint32_t C = s_pre[nruns];
-    if (C == 0) return;                          // tile is pre-zeroed
+    const uint32_t C = s_pre[128];
+    if (C == 0) return;                          // tile is pre-zeroed: phi = 0 exactly
 
     // ---- this lane's grid point
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wi = warp >> 2, wj = (warp >> 1) & 1, wk = warp & 1;
     const int li = lane >> 4, lj = (lane >> 2) & 3, lk = lane & 3;
     const int i = bx * 8 + wi * 2 + li, j = by * 8 + wj * 4 + lj, k = bz * 8 + wk * 4 + lk;
     const bool valid = (i < P.np) && (j < P.np) && (k < P.np);
-    const int gi = g.ijk[0] * P.S + i, gj = g.ijk[1] * P.S + j, gk = g.ijk[2] * P.S + k;
+    const int gi = T.gbase[0] + i, gj = T.gbase[1] + j, gk = T.gbase[2] + k;
     // grid point coordinates from GLOBAL indices: x, y = mul then add, z fused in the AVX path
     // (dense_subdomains.rs:1068, :1101-1102); scalar path: point_coordinates (uniform_grid.rs:418-425)
     const float gx = __fadd_rn(__fmul_rn((float)gi, P.c), P.gmin[0]);
@@ -397,83 +459,23 @@ k_levelset(SsDev P, SsLsArgs A) {
     const int i0 = bx * 8 + wi * 2, j0 = by * 8 + wj * 4, k0 = bz * 8 + wk * 4;
     const bool warp_valid = (i0 < P.np) && (j0 < P.np) && (k0 < P.np);
     const int i1 = min(i0 + 1, P.np - 1), j1 = min(j0 + 3, P.np - 1), k1 = min(k0 + 3, P.np - 1);
-    const float bxl = P.gmin[0] + (float)(g.ijk[0] * P.S + i0) * P.c, bxh = P.gmin[0] + (float)(g.ijk[0] * P.S + i1) * P.c;
-    const float byl = P.gmin[1] + (float)(g.ijk[1] * P.S + j0) * P.c, byh = P.gmin[1] + (float)(g.ijk[1] * P.S + j1) * P.c;
-    const float bzl = P.gmin[2] + (float)(g.ijk[2] * P.S + k0) * P.c, bzh = P.gmin[2] + (float)(g.ijk[2] * P.S + k1) * P.c;
+    const float bxl = fmaf((float)(T.gbase[0] + i0), P.c, P.gmin[0]), bxh = fmaf((float)(T.gbase[0] + i1), P.c, P.gmin[0]);
+    const float byl = fmaf((float)(T.gbase[1] + j0), P.c, P.gmin[1]), byh = fmaf((float)(T.gbase[1] + j1), P.c, P.gmin[1]);
+    const float bzl = fmaf((float)(T.gbase[2] + k0), P.c, P.gmin[2]), bzh = fmaf((float)(T.gbase[2] + k1), P.c, P.gmin[2]);
     const float cull2 = (sparse ? P.h2m : P.h2) * 1.0001f;
+    const size_t out_idx = (size_t)tile_idx * P.np * P.np * P.np + ((size_t)i * P.np + j) * P.np + k;
 
     float phi = 0.0f;
-    unsigned long long npairs = 0;
+    unsigned hits = 0;
 
-    if (C <= SS_LS_CAP) {
-        // ---- stage + sort candidates by global particle index
-        int npow = 32; while (npow < (int)C) npow <<= 1;
-        for (int t = threadIdx.x; t < npow; t += blockDim.x) {
-            if (t < (int)C) {
-                int r = 0; while (s_pre[r + 1] <= (uint32_t)t) ++r;
-                uint32_t src = s_rng[0][r] + ((uint32_t)t - s_pre[r]);
-                s_key[t] = ((unsigned long long)A.pidx[src] << 32) | src;
-            } else s_key[t] = ~0ull;
-        }
-        __syncthreads();
-        ss_bitonic(s_key, npow);
-        for (int t = threadIdx.x; t < (int)C; t += blockDim.x) {
-            uint32_t src = (uint32_t)(s_key[t] & 0xffffffffu);
-            s_rec[t] = A.rec[src]; s_ks[t] = A.ksplit[src];
-        }
-        __syncthreads();
-        if (!warp_valid) return;
-        // ---- per-warp cull: candidates within h of the warp's point box
-        const int nwords = ((int)C + 31) >> 5;
-        for (int w = 0; w < nwords; ++w) {
-            int c = w * 32 + lane;
-            bool keep = false;
-            if (c < (int)C) {
-                float4 r = s_rec[c];
-                float dx = fmaxf(fmaxf(bxl - r.x, r.x - bxh), 0.0f);
-                float dy = fmaxf(fmaxf(byl - r.y, r.y - byh), 0.0f);
-                float dz = fmaxf(fmaxf(bzl - r.z, r.z - bzh), 0.0f);
-                keep = (dx * dx + dy * dy + dz * dz) < cull2;
-            }
-            uint32_t mword = __ballot_sync(0xffffffffu, keep);
-            if (lane == 0) s_mask[warp][w] = mword;
-        }
-        __syncwarp();
-        // ---- ordered accumulation
-        for (int w = 0; w < nwords; ++w) {
-            uint32_t mword = s_mask[warp][w];
-            while (mword) {
-                int c = w * 32 + __ffs(mword) - 1;
-                mword &= mword - 1;
-                float4 r = s_rec[c];
-                float dx = __fsub_rn(r.x, gx), dy = __fsub_rn(r.y, gy), dz = __fsub_rn(r.z, gz);
-                if (!sparse) {
-                    float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
-                    if (d2 < P.h2) {
-                        float wgt = ss_kernel_avx(P, __fsqrt_rn(d2));
-                        phi = (k < s_ks[c]) ? __fmaf_rn(wgt, r.w, phi) : __fadd_rn(phi, __fmul_rn(wgt, r.w));
-                        ++npairs;
-                    }
-                } else {
-                    float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                    if (d2 < P.h2m) {
-                        float wgt = ss_kernel_scalar(P, __fsqrt_rn(d2));
-                        phi = __fadd_rn(phi, __fmul_rn(r.w, wgt));
-                        ++npairs;
-                    }
-                }
-            }
-        }
-    } else {
-        // ---- oversized brick (pathological clustering): every lane walks all candidates in ascending
-        // particle index by repeated selection of the next-larger index.  O(C^2) but exact.
-        if (!warp_valid) return;
+    if (C > SS_LS_CAP) {
+        // ---- oversized brick (pathological clustering): every warp walks all candidates in ascending particle
+        // index by repeated selection of the next-larger index.  O(C^2) but exact; no certification.
+        if (!warp_valid || !my_flag) return;
         long long last = -1;
         for (uint32_t done = 0; done < C; ++done) {
-            // find the smallest pidx > last among all runs (runs are ascending inside each bin, but a run
-            // spans several bins; scan everything)
             unsigned long long best = ~0ull;
-            for (int r = 0; r < s_nrun; ++r) {
+            for (int r = 0; r < nruns; ++r) {
                 uint32_t a = s_rng[0][r], len = s_rng[1][r];
                 for (uint32_t t = lane; t < len; t += 32) {
                     uint32_t pi = A.pidx[a + t];
@@ -486,58 +488,229 @@ k_levelset(SsDev P, SsLsArgs A) {
             uint32_t src = (uint32_t)(best & 0xffffffffu);
             float4 r = A.rec[src];
             int ks = A.ksplit[src];
-            float dx = __fsub_rn(r.x, gx), dy = __fsub_rn(r.y, gy), dz = __fsub_rn(r.z, gz);
-            if (!sparse) {
-                float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
-                if (d2 < P.h2) {
-                    float wgt = ss_kernel_avx(P, __fsqrt_rn(d2));
-                    phi = (k < ks) ? __fmaf_rn(wgt, r.w, phi) : __fadd_rn(phi, __fmul_rn(wgt, r.w));
-                }
-            } else {
-                float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                if (d2 < P.h2m) phi = __fadd_rn(phi, __fmul_rn(r.w, ss_kernel_scalar(P, __fsqrt_rn(d2))));
-            }
+            if (sparse) ss_accumulate<true, false>(P, r, ks, k, gx, gy, gz, phi, hits);
+            else ss_accumulate<false, false>(P, r, ks, k, gx, gy, gz, phi, hits);
+        }
+        if (valid) A.tiles[out_idx] = phi;
+        return;
+    }
+
+    // ---- stage candidates (bin order) in shared memory: one warp per run
+    for (int r = warp; r < nruns; r += SS_LS_WARPS) {
+        const uint32_t a = s_rng[0][r], len = s_rng[1][r], dst = s_pre[r];
+        for (uint32_t t = lane; t < len; t += 32) {
+            const uint32_t src = a + t;
+            s_rec[dst + t] = A.rec[src]; s_ks[dst + t] = A.ksplit[src];
+            s_key[dst + t] = ((unsigned long long)A.pidx[src] << 32) | (dst + t);
         }
     }
-    if (valid) A.tiles[(size_t)tile_idx * P.np * P.np * P.np + ((size_t)i * P.np + j) * P.np + k] = phi;
-    if (A.pairs) {
-        for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(0xffffffffu, npairs, o);
-        if (lane == 0 && npairs) atomicAdd(A.pairs, npairs);
+    __syncthreads();
+
+    // ---- certification: fast partial sum over the candidates within 0.55 h of the warp box
+    bool need_exact = warp_valid && my_flag;
+    if (mode == SS_LS_CERTIFY && warp_valid) {
+        const float near2 = 0.3025f * P.h2;          // (0.55 h)^2
+        const float cert = P.thr + fabsf(P.thr) * 1.0e-4f + 1.0e-30f;
+        float sum = 0.0f;
+        const int nwords = ((int)C + 31) >> 5;
+        for (int w = 0; w < nwords; ++w) {
+            const int c = w * 32 + lane;
+            bool keep = false;
+            if (c < (int)C) {
+                const float4 r = s_rec[c];
+                const float dx = fmaxf(fmaxf(bxl - r.x, r.x - bxh), 0.0f);
+                const float dy = fmaxf(fmaxf(byl - r.y, r.y - byh), 0.0f);
+                const float dz = fmaxf(fmaxf(bzl - r.z, r.z - bzh), 0.0f);
+                keep = (dx * dx + dy * dy + dz * dz) < near2;
+            }
+            uint32_t mword = __ballot_sync(0xffffffffu, keep);
+            while (mword) {
+                const int cc = w * 32 + __ffs(mword) - 1;
+                mword &= mword - 1;
+                const float4 r = s_rec[cc];
+                const float dx = r.x - gx, dy = r.y - gy, dz = r.z - gz;
+                const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                // cubic spline in v = max(1 - r/h, 0) (zero beyond h); any rounding is fine here: 1e-4 safety margin
+                const float q = d2 * rsqrtf(fmaxf(d2, 1.0e-30f)) * P.a_hinv;
+                const float v = fmaxf(1.0f - q, 0.0f);
+                const float v2 = v * v;
+                const float inner = fmaf(v, fmaf(v, fmaf(v, -6.0f, 12.0f), -6.0f), 1.0f);
+                const float wgt = (q <= 0.5f) ? inner : 2.0f * v2 * v;
+                sum = fmaf(wgt, r.w, sum);
+            }
+        }
+        sum *= P.a_sigma;
+        // lanes outside the tile (clipped boxes) do not need a value
+        const bool ok = !valid || (sum > cert);
+        need_exact = !__all_sync(0xffffffffu, ok);
+    }
+    const int block_need = __syncthreads_or(need_exact ? 1 : 0);
+    if (!block_need) {
+        if (mode == SS_LS_CERTIFY && valid) A.tiles[out_idx] = SS_MARKER;
+        return;
+    }
+
+    // ---- exact path: order the candidates by global particle index
+    int npow = 32; while (npow < (int)C) npow <<= 1;
+    for (int t = (int)C + threadIdx.x; t < npow; t += blockDim.x) s_key[t] = ~0ull;
+    __syncthreads();
+    ss_bitonic(s_key, npow);
+    if (!warp_valid) return;
+    if (!need_exact) {
+        if (mode == SS_LS_CERTIFY && valid) A.tiles[out_idx] = SS_MARKER;
+        return;
+    }
+    // ---- per-warp compacted list (sorted order) of the candidates within h of the warp's point box
+    int nlist = 0;
+    bool all_fma = true;                                   // no lane of this warp in any candidate's remainder lanes
+    {
+        const int nwords = ((int)C + 31) >> 5;
+        for (int w = 0; w < nwords; ++w) {
+            const int rnk = w * 32 + lane;
+            bool keep = false;
+            int slot = 0;
+            if (rnk < (int)C) {
+                slot = (int)(s_key[rnk] & 0xffffu);
+                const float4 r = s_rec[slot];
+                const float dx = fmaxf(fmaxf(bxl - r.x, r.x - bxh), 0.0f);
+                const float dy = fmaxf(fmaxf(byl - r.y, r.y - byh), 0.0f);
+                const float dz = fmaxf(fmaxf(bzl - r.z, r.z - bzh), 0.0f);
+                keep = (dx * dx + dy * dy + dz * dz) < cull2;
+                if (keep && s_ks[slot] <= k1) all_fma = false;
+            }
+            const uint32_t mword = __ballot_sync(0xffffffffu, keep);
+            if (keep) s_list[warp][nlist + __popc(mword & ((1u << lane) - 1u))] = (unsigned short)slot;
+            nlist += __popc(mword);
+        }
+        all_fma = __all_sync(0xffffffffu, all_fma);
+        __syncwarp();
+    }
+    // ---- ordered accumulation
+    if (sparse) {
+        for (int n = 0; n < nlist; ++n) {
+            const int slot = s_list[warp][n];
+            ss_accumulate<true, false>(P, s_rec[slot], 0, k, gx, gy, gz, phi, hits);
+        }
+    } else if (all_fma) {
+        for (int n = 0; n < nlist; ++n) {
+            const int slot = s_list[warp][n];
+            ss_accumulate<false, true>(P, s_rec[slot], 0, k, gx, gy, gz, phi, hits);
+        }
+    } else {
+        for (int n = 0; n < nlist; ++n) {
+            const int slot = s_list[warp][n];
+            ss_accumulate<false, false>(P, s_rec[slot], s_ks[slot], k, gx, gy, gz, phi, hits);
+        }
+    }
+    if (valid) A.tiles[out_idx] = phi;
+    if (COUNT && A.pairs) {
+        unsigned long long np_ = hits;
+        for (int o = 16; o > 0; o >>= 1) np_ += __shfl_xor_sync(0xffffffffu, np_, o);
+        if (lane == 0 && np_) atomicAdd(A.pairs, np_);
     }
 }
 
-// ------------------------------------------------------------------ marching cubes ----
-// Per tile point: which of its +x/+y/+z edges carry a vertex (endpoints on different sides of the
-// threshold, `value > threshold` == inside, dense_subdomains.rs:1482) and how many triangles its cell emits.
-__global__ void k_mc_count(SsDev P, const float *__restrict__ tiles, uint32_t npts_total,
-                           uint32_t *__restrict__ vcnt, uint32_t *__restrict__ tcnt, uint8_t *__restrict__ vmask) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= npts_total) return;
-    const int np = P.np, np3 = np * np * np;
-    uint32_t tile = t / (uint32_t)np3; int l = (int)(t - tile * (uint32_t)np3);
-    int i = l / (np * np), j = (l / np) % np, k = l % np;
-    const float *phi = tiles + (size_t)tile * np3;
-    float thr = P.thr;
-    bool in0 = phi[l] > thr;
-    uint32_t mask = 0;
-    if (i + 1 < np && ((phi[l + np * np] > thr) != in0)) mask |= 1u;
-    if (j + 1 < np && ((phi[l + np] > thr) != in0)) mask |= 2u;
-    if (k + 1 < np && ((phi[l + 1] > thr) != in0)) mask |= 4u;
-    vmask[t] = (uint8_t)mask;
-    vcnt[t] = __popc(mask);
-    uint32_t nt = 0;
-    if (i < P.S && j < P.S && k < P.S) {
-        int idx = (in0 ? 1 : 0);
-        idx |= (phi[l + np * np] > thr) ? 2 : 0;              // corner 1 (1,0,0)
-        idx |= (phi[l + np * np + np] > thr) ? 4 : 0;         // corner 2 (1,1,0)
-        idx |= (phi[l + np] > thr) ? 8 : 0;                   // corner 3 (0,1,0)
-        idx |= (phi[l + 1] > thr) ? 16 : 0;                   // corner 4 (0,0,1)
-        idx |= (phi[l + np * np + 1] > thr) ? 32 : 0;         // corner 5 (1,0,1)
-        idx |= (phi[l + np * np + np + 1] > thr) ? 64 : 0;    // corner 6 (1,1,1)
-        idx |= (phi[l + np + 1] > thr) ? 128 : 0;             // corner 7 (0,1,1)
-        nt = c_num_tris[idx];
+// ------------------------------------------------------------------ tile-plane indexing ----
+// The tile passes below use grid = (nbatch * np, ceil(np^2 / 256)), block = 256: blockIdx.x -> (tile, i),
+// blockIdx.y * 256 + threadIdx.x -> flattened (j, k).  One multiply-high replaces the division by np.
+#define SS_TP_THREADS 256
+__device__ __forceinline__ bool ss_plane_index(const SsDev &P, int &tile, int &i, int &j, int &k, int &l) {
+    tile = (int)(blockIdx.x / (unsigned)P.np); i = (int)(blockIdx.x - (unsigned)tile * (unsigned)P.np);
+    const uint32_t l2 = blockIdx.y * SS_TP_THREADS + threadIdx.x;
+    j = (int)__umulhi(l2, P.np_magic); k = (int)l2 - j * P.np;
+    l = i * P.np * P.np + (int)l2;
+    return l2 < (uint32_t)(P.np * P.np);
+}
+// block-wide exclusive scan of a small per-thread count; returns the thread's prefix, total in `total`
+__device__ __forceinline__ uint32_t ss_block_excl_scan(uint32_t v, uint32_t &total) {
+    __shared__ uint32_t s_w[SS_TP_THREADS / 32 + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+    for (int o = 1; o < 32; o <<= 1) { uint32_t n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < SS_TP_THREADS / 32 ? s_w[lane] : 0, wi = w;
+        for (int o = 1; o < SS_TP_THREADS / 32; o <<= 1) { uint32_t n = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += n; }
+        if (lane < SS_TP_THREADS / 32) s_w[lane] = wi - w;
+        if (lane == SS_TP_THREADS / 32 - 1) s_w[SS_TP_THREADS / 32] = wi;
     }
-    tcnt[t] = nt;
+    __syncthreads();
+    total = s_w[SS_TP_THREADS / 32];
+    return s_w[warp] + incl - v;
+}
+
+// Marker points (certified inside, value unknown) that touch an outside point along a grid edge carry a
+// surface-crossing edge, so they need their exact value: flag their warp box and list their brick for the
+// SS_LS_FIX launch.
+__global__ void __launch_bounds__(SS_TP_THREADS)
+k_fixup_flags(SsDev P, const float *__restrict__ tiles, uint8_t *__restrict__ wflag, uint32_t *__restrict__ brick_seen,
+              uint32_t *__restrict__ fix_bricks, uint32_t *__restrict__ nfix /* [0]: bricks, [1]: points */) {
+    int tile, i, j, k, l;
+    if (!ss_plane_index(P, tile, i, j, k, l)) return;
+    const int np = P.np;
+    const float *phi = tiles + (size_t)tile * np * np * np;
+    if (phi[l] != SS_MARKER) return;
+    const float thr = P.thr;
+    bool hit = false;
+    if (i > 0) hit |= !(phi[l - np * np] > thr);
+    if (i + 1 < np) hit |= !(phi[l + np * np] > thr);
+    if (j > 0) hit |= !(phi[l - np] > thr);
+    if (j + 1 < np) hit |= !(phi[l + np] > thr);
+    if (k > 0) hit |= !(phi[l - 1] > thr);
+    if (k + 1 < np) hit |= !(phi[l + 1] > thr);
+    if (!hit) return;
+    const int nb = P.nb;
+    const int warp = (((i & 7) >> 1) << 2) | (((j & 7) >> 2) << 1) | ((k & 7) >> 2);
+    const uint32_t brick = (((uint32_t)tile * nb + (i >> 3)) * nb + (j >> 3)) * nb + (k >> 3);
+    wflag[(size_t)brick * SS_LS_WARPS + warp] = 1;
+    if (atomicExch(&brick_seen[brick], 1u) == 0u) fix_bricks[atomicAdd(&nfix[0], 1u)] = brick;
+    atomicAdd(&nfix[1], 1u);
+}
+
+// ------------------------------------------------------------------ marching cubes ----
+__device__ __forceinline__ int ss_case_index(const float *__restrict__ phi, int l, int np, float thr) {
+    int idx = (phi[l] > thr) ? 1 : 0;                      // corner 0 (0,0,0)   uniform_grid.rs:822-831
+    idx |= (phi[l + np * np] > thr) ? 2 : 0;               // corner 1 (1,0,0)
+    idx |= (phi[l + np * np + np] > thr) ? 4 : 0;          // corner 2 (1,1,0)
+    idx |= (phi[l + np] > thr) ? 8 : 0;                    // corner 3 (0,1,0)
+    idx |= (phi[l + 1] > thr) ? 16 : 0;                    // corner 4 (0,0,1)
+    idx |= (phi[l + np * np + 1] > thr) ? 32 : 0;          // corner 5 (1,0,1)
+    idx |= (phi[l + np * np + np + 1] > thr) ? 64 : 0;     // corner 6 (1,1,1)
+    idx |= (phi[l + np + 1] > thr) ? 128 : 0;              // corner 7 (0,1,1)
+    return idx;
+}
+
+// Pass 1: per tile point, which of its +x/+y/+z edges carry a vertex (endpoints on different sides of the
+// threshold; `value > threshold` == inside, dense_subdomains.rs:1482) and how many triangles its cell emits;
+// per block of 256 points the totals.
+__global__ void __launch_bounds__(SS_TP_THREADS)
+k_mc_count(SsDev P, const float *__restrict__ tiles, uint8_t *__restrict__ vmask, uint32_t *__restrict__ vblk, uint32_t *__restrict__ tblk) {
+    int tile, i, j, k, l;
+    const bool ok = ss_plane_index(P, tile, i, j, k, l);
+    const int np = P.np;
+    uint32_t mask = 0, nt = 0;
+    if (ok) {
+        const float *phi = tiles + (size_t)tile * np * np * np;
+        const float thr = P.thr;
+        const bool in0 = phi[l] > thr;
+        if (i + 1 < np && ((phi[l + np * np] > thr) != in0)) mask |= 1u;
+        if (j + 1 < np && ((phi[l + np] > thr) != in0)) mask |= 2u;
+        if (k + 1 < np && ((phi[l + 1] > thr) != in0)) mask |= 4u;
+        vmask[(size_t)tile * np * np * np + l] = (uint8_t)mask;
+        if (i < P.S && j < P.S && k < P.S) nt = c_num_tris[ss_case_index(phi, l, np, thr)];
+    }
+    uint32_t packed = (nt << 16) | __popc(mask);            // <= 256*5 and 256*3: no overflow between halves
+    for (int o = 16; o > 0; o >>= 1) packed += __shfl_xor_sync(0xffffffffu, packed, o);
+    __shared__ uint32_t s_part[SS_TP_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = packed;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int w = 0; w < SS_TP_THREADS / 32; ++w) tot += s_part[w];
+        const uint32_t b = blockIdx.x * gridDim.y + blockIdx.y;
+        vblk[b] = tot & 0xffffu; tblk[b] = tot >> 16;
+    }
 }
 
 struct SsMcOut {
@@ -551,78 +724,86 @@ struct SsMcOut {
     uint32_t bcap;
 };
 
-__global__ void k_mc_emit(SsDev P, const float *__restrict__ tiles, uint32_t npts_total,
-                          const uint32_t *__restrict__ voff, const uint32_t *__restrict__ toff,
-                          const uint8_t *__restrict__ vmask, const uint32_t *__restrict__ batch_subs,
-                          const uint32_t *__restrict__ sub_flat, SsMcOut O) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= npts_total) return;
-    const int np = P.np, np3 = np * np * np;
-    uint32_t tile = t / (uint32_t)np3; int l = (int)(t - tile * (uint32_t)np3);
-    int i = l / (np * np), j = (l / np) % np, k = l % np;
-    const float *phi = tiles + (size_t)tile * np3;
+// Pass 2: vertices on the edges owned by each point (dense_subdomains.rs:1498-1538); records the id of each
+// point's first vertex in voff.
+__global__ void __launch_bounds__(SS_TP_THREADS)
+k_mc_verts(SsDev P, const float *__restrict__ tiles, const uint8_t *__restrict__ vmask, const uint32_t *__restrict__ vblk_off,
+           const uint32_t *__restrict__ vblk, uint32_t *__restrict__ voff, const SsTile *__restrict__ tile_tab, SsMcOut O) {
+    const uint32_t b = blockIdx.x * gridDim.y + blockIdx.y;
+    if (vblk[b] == 0) return;
+    int tile, i, j, k, l;
+    const bool ok = ss_plane_index(P, tile, i, j, k, l);
+    const int np = P.np;
+    const size_t pt = (size_t)tile * np * np * np + l;
+    const uint32_t mask = ok ? vmask[pt] : 0u;
+    uint32_t total;
+    const uint32_t pre = ss_block_excl_scan(__popc(mask), total);
+    if (!mask) return;
+    uint32_t vid = O.vbase + vblk_off[b] + pre;
+    voff[pt] = vid;
+    const float *phi = tiles + (size_t)tile * np * np * np;
+    const SsTile T = tile_tab[tile];
     const float thr = P.thr;
-    const SsSubGeom g = ss_sub_geom(P, sub_flat[batch_subs[tile]]);
-    const uint32_t mask = vmask[t];
-    // ---- vertices on the edges owned by this point (dense_subdomains.rs:1498-1538)
-    if (mask) {
-        uint32_t vid = O.vbase + voff[t];
-        const float a = phi[l];
-        const int o[3] = { i, j, k };
-        float oc[3];
+    const float a = phi[l];
+    const int o[3] = { i, j, k };
+    float oc[3];
 #pragma unroll
-        for (int d = 0; d < 3; ++d) oc[d] = ss_coord(g.smin[d], o[d], P.c);
+    for (int d = 0; d < 3; ++d) oc[d] = ss_coord(T.smin[d], o[d], P.c);
 #pragma unroll
-        for (int ax = 0; ax < 3; ++ax) {
-            if (!(mask & (1u << ax))) continue;
-            const int stride = ax == 0 ? np * np : (ax == 1 ? np : 1);
-            const float b = phi[l + stride];
-            const float alpha = __fdiv_rn(__fsub_rn(thr, a), __fsub_rn(b, a));
-            const float one_m = __fsub_rn(1.0f, alpha);
-            float pos[3];
+    for (int ax = 0; ax < 3; ++ax) {
+        if (!(mask & (1u << ax))) continue;
+        const int stride = ax == 0 ? np * np : (ax == 1 ? np : 1);
+        const float bval = phi[l + stride];
+        const float alpha = __fdiv_rn(__fsub_rn(thr, a), __fsub_rn(bval, a));      // dense_subdomains.rs:1516-1519
+        const float one_m = __fsub_rn(1.0f, alpha);
+        float pos[3];
 #pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                float tc = (d == ax) ? ss_coord(g.smin[d], o[d] + 1, P.c) : oc[d];
-                pos[d] = __fadd_rn(__fmul_rn(oc[d], one_m), __fmul_rn(tc, alpha));
-            }
-            O.verts[3 * (size_t)vid] = pos[0]; O.verts[3 * (size_t)vid + 1] = pos[1]; O.verts[3 * (size_t)vid + 2] = pos[2];
-            unsigned long long key = ss_edge_key(g.ijk[0] * P.S + i, g.ijk[1] * P.S + j, g.ijk[2] * P.S + k, ax);
-            O.vkeys[vid] = key;
-            // boundary edge: an orthogonal coordinate on a tile face (uniform_grid.rs:332-338)
-            bool boundary = false;
-#pragma unroll
-            for (int d = 0; d < 3; ++d) if (d != ax && (o[d] == 0 || o[d] == P.S)) boundary = true;
-            if (boundary) {
-                uint32_t slot = atomicAdd(O.bcount, 1u);
-                if (slot < O.bcap) { O.bkeys[slot] = key; O.bids[slot] = vid; }
-            }
-            ++vid;
+        for (int d = 0; d < 3; ++d) {
+            const float tc = (d == ax) ? ss_coord(T.smin[d], o[d] + 1, P.c) : oc[d];
+            pos[d] = __fadd_rn(__fmul_rn(oc[d], one_m), __fmul_rn(tc, alpha));
         }
+        O.verts[3 * (size_t)vid] = pos[0]; O.verts[3 * (size_t)vid + 1] = pos[1]; O.verts[3 * (size_t)vid + 2] = pos[2];
+        const unsigned long long key = ss_edge_key(T.gbase[0] + i, T.gbase[1] + j, T.gbase[2] + k, ax);
+        O.vkeys[vid] = key;
+        // boundary edge: an orthogonal coordinate on a tile face (uniform_grid.rs:332-338)
+        bool boundary = false;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) if (d != ax && (o[d] == 0 || o[d] == P.S)) boundary = true;
+        if (boundary) {
+            const uint32_t slot = atomicAdd(O.bcount, 1u);
+            if (slot < O.bcap) { O.bkeys[slot] = key; O.bids[slot] = vid; }
+        }
+        ++vid;
     }
-    // ---- triangles of the cell whose origin is this point (dense_subdomains.rs:1470-1552)
-    if (i < P.S && j < P.S && k < P.S) {
-        int idx = (phi[l] > thr) ? 1 : 0;
-        idx |= (phi[l + np * np] > thr) ? 2 : 0;
-        idx |= (phi[l + np * np + np] > thr) ? 4 : 0;
-        idx |= (phi[l + np] > thr) ? 8 : 0;
-        idx |= (phi[l + 1] > thr) ? 16 : 0;
-        idx |= (phi[l + np * np + 1] > thr) ? 32 : 0;
-        idx |= (phi[l + np * np + np + 1] > thr) ? 64 : 0;
-        idx |= (phi[l + np + 1] > thr) ? 128 : 0;
-        const int nt = c_num_tris[idx];
-        uint32_t tid = O.tbase + toff[t];
-        for (int q = 0; q < nt; ++q) {
+}
+
+// Pass 3: triangles of the cell whose origin is each point (dense_subdomains.rs:1470-1552)
+__global__ void __launch_bounds__(SS_TP_THREADS)
+k_mc_tris(SsDev P, const float *__restrict__ tiles, const uint8_t *__restrict__ vmask, const uint32_t *__restrict__ tblk_off,
+          const uint32_t *__restrict__ tblk, const uint32_t *__restrict__ voff, SsMcOut O) {
+    const uint32_t b = blockIdx.x * gridDim.y + blockIdx.y;
+    if (tblk[b] == 0) return;
+    int tile, i, j, k, l;
+    const bool ok = ss_plane_index(P, tile, i, j, k, l);
+    const int np = P.np;
+    const float *phi = tiles + (size_t)tile * np * np * np;
+    int idx = 0, nt = 0;
+    if (ok && i < P.S && j < P.S && k < P.S) { idx = ss_case_index(phi, l, np, P.thr); nt = c_num_tris[idx]; }
+    uint32_t total;
+    const uint32_t pre = ss_block_excl_scan((uint32_t)nt, total);
+    if (!nt) return;
+    uint32_t tid = O.tbase + tblk_off[b] + pre;
+    const size_t tbase_pt = (size_t)tile * np * np * np;
+    for (int q = 0; q < nt; ++q) {
 #pragma unroll
-            for (int mth = 0; mth < 3; ++mth) {
-                const int le = c_tri_table[idx][3 * q + (2 - mth)];          // reversed triplet, lut.rs:338-342
-                const int ax = c_edge_axis[le];
-                const int lo = l + c_edge_org[le][0] * np * np + c_edge_org[le][1] * np + c_edge_org[le][2];
-                const uint32_t to = tile * (uint32_t)np3 + (uint32_t)lo;
-                const uint32_t below = vmask[to] & ((1u << ax) - 1u);
-                O.tris[3 * (size_t)tid + mth] = O.vbase + voff[to] + __popc(below);
-            }
-            ++tid;
+        for (int mth = 0; mth < 3; ++mth) {
+            const int le = c_tri_table[idx][3 * q + (2 - mth)];              // reversed triplet, lut.rs:338-342
+            const int ax = c_edge_axis[le];
+            const int lo = l + c_edge_org[le][0] * np * np + c_edge_org[le][1] * np + c_edge_org[le][2];
+            const uint32_t below = vmask[tbase_pt + lo] & ((1u << ax) - 1u);
+            O.tris[3 * (size_t)tid + mth] = voff[tbase_pt + lo] + __popc(below);
         }
+        ++tid;
     }
 }
 

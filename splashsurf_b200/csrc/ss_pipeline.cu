@@ -59,10 +59,12 @@ struct ss_context {
     cudaEvent_t ev[12];
     uint32_t max_tiles = 0;          // 0 = auto
     int64_t keep_tile_flat = -1;
+    int ls_exact_all = 0;            // 1: evaluate every grid point exactly (no certification)
+    int count_pairs = 0;             // 1: count in-support evaluations (work model; slower)
     // reusable scratch
     DevBuf xyz, xyz_f, filt_flag, filt_flag32, filt_off, aabb, cnt, off, key_a, key_b, val_a, val_b, cid, cub_tmp,
         sub_flat, sub_off, sub_sparse, flags, scan, spos, rho, tab_a, tab_b, rec, ksplit, batch_subs, tiles, vcnt,
-        tcnt, vmask, bkeys_a, bkeys_b, bids_a, bids_b, bcount, remap, keep, newid, err, pairs;
+        tcnt, vmask, voff, vblk_off, tblk_off, tile_tab, brick_rng, wflag, brick_seen, fix_list, nflag, bkeys_a, bkeys_b, bids_a, bids_b, bcount, remap, keep, newid, err, pairs;
     uint64_t launches = 0;
 };
 
@@ -188,7 +190,7 @@ extern "C" void ss_context_destroy(ss_context *c) {
     DevBuf *bufs[] = { &c->xyz, &c->xyz_f, &c->filt_flag, &c->filt_flag32, &c->filt_off, &c->aabb, &c->cnt, &c->off, &c->key_a, &c->key_b,
                        &c->val_a, &c->val_b, &c->cid, &c->cub_tmp, &c->sub_flat, &c->sub_off, &c->sub_sparse, &c->flags, &c->scan,
                        &c->spos, &c->rho, &c->tab_a, &c->tab_b, &c->rec, &c->ksplit, &c->batch_subs, &c->tiles, &c->vcnt, &c->tcnt,
-                       &c->vmask, &c->bkeys_a, &c->bkeys_b, &c->bids_a, &c->bids_b, &c->bcount, &c->remap, &c->keep, &c->newid,
+                       &c->vmask, &c->voff, &c->vblk_off, &c->tblk_off, &c->tile_tab, &c->brick_rng, &c->wflag, &c->brick_seen, &c->fix_list, &c->nflag, &c->bkeys_a, &c->bkeys_b, &c->bids_a, &c->bids_b, &c->bcount, &c->remap, &c->keep, &c->newid,
                        &c->err, &c->pairs };
     for (DevBuf *b : bufs) b->release();
     for (auto &ev : c->ev) cudaEventDestroy(ev);
@@ -198,6 +200,8 @@ extern "C" void ss_context_destroy(ss_context *c) {
 
 extern "C" int ss_context_keep_levelset_tile(ss_context *c, int64_t flat) { if (!c) return SS_ERR_INVALID_PARAMETER; c->keep_tile_flat = flat; return SS_OK; }
 extern "C" int ss_context_set_tile_batch(ss_context *c, uint32_t m) { if (!c) return SS_ERR_INVALID_PARAMETER; c->max_tiles = m; return SS_OK; }
+extern "C" int ss_context_set_levelset_exact_everywhere(ss_context *c, int on) { if (!c) return SS_ERR_INVALID_PARAMETER; c->ls_exact_all = on ? 1 : 0; return SS_OK; }
+extern "C" int ss_context_set_count_pairs(ss_context *c, int on) { if (!c) return SS_ERR_INVALID_PARAMETER; c->count_pairs = on ? 1 : 0; return SS_OK; }
 
 // ------------------------------------------------------------------ stage: input, filter, AABB, grid ----
 struct Prepared {
@@ -349,7 +353,7 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     for (int d = 0; d < 3; ++d) { D.gmin[d] = gg.mn[d]; D.nsd[d] = (int)nsd[d]; }
     D.c = cs; D.h = h; D.h2 = fmulr(h, h); D.h2m = fmulr(D.h2, 1.01f); D.thr = p->iso_surface_threshold;
     D.rest_mass = rest_mass; D.sub_size = sub_size; D.margin = margin; D.grow = fmulr(margin, 1.5f);
-    D.S = (int)S; D.np = (int)S + 1;
+    D.S = (int)S; D.np = (int)S + 1; D.np_magic = (uint32_t)(4294967296ull / (uint64_t)D.np) + 1u;
     D.R = (int)ceilf(fdivr(h, cs));
     D.srad = (int)ceilf(fdivr(margin, sub_size));
     if (D.srad > 8) return ss_fail(SS_ERR_INVALID_PARAMETER, "ghost margin spans more than 8 subdomains; increase subdomain_num_cubes_per_dim");
@@ -456,38 +460,84 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     const size_t np3 = (size_t)D.np * D.np * D.np;
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
-    const size_t per_tile = np3 * (4 + 4 + 4 + 1) + 64;
+    const unsigned nbricks = (unsigned)(D.nb * D.nb * D.nb);
+    const unsigned planes_y = (unsigned)((D.np * D.np + SS_TP_THREADS - 1) / SS_TP_THREADS);
+    const size_t per_tile = np3 * (4 + 4 + 1) + (size_t)nbricks * (SS_LS_WARPS + 8) + (size_t)D.np * planes_y * 16 + 256;
     size_t max_tiles = c->max_tiles ? c->max_tiles : std::max<size_t>(1, std::min<size_t>((free_b / 3) / per_tile, 4096));
     max_tiles = std::min<size_t>(max_tiles, std::max<size_t>(1, (size_t)0x7fffffff / np3 / 2));
+    max_tiles = std::min<size_t>(max_tiles, std::max<size_t>(1, (size_t)65535 / D.nb));       // gridDim.z = nb * tiles
     max_tiles = std::min<size_t>(max_tiles, nsub);
-    c->tiles.ensure(max_tiles * np3 * 4); c->vcnt.ensure(max_tiles * np3 * 4 + 4); c->tcnt.ensure(max_tiles * np3 * 4 + 4);
-    c->vmask.ensure(max_tiles * np3); c->batch_subs.ensure(max_tiles * 4);
+    const size_t nblk_max = max_tiles * D.np * planes_y;
+    c->tiles.ensure(max_tiles * np3 * 4); c->voff.ensure(max_tiles * np3 * 4); c->vmask.ensure(max_tiles * np3);
+    c->vcnt.ensure(nblk_max * 4 + 4); c->tcnt.ensure(nblk_max * 4 + 4); c->vblk_off.ensure(nblk_max * 4 + 4); c->tblk_off.ensure(nblk_max * 4 + 4);
+    c->tile_tab.ensure(max_tiles * sizeof(SsTile)); c->brick_rng.ensure((size_t)D.nb * sizeof(int2));
     c->bcount.ensure(4); c->pairs.ensure(8);
     CK(cudaMemsetAsync(c->bcount.p, 0, 4, st));
     CK(cudaMemsetAsync(c->pairs.p, 0, 8, st));
-    std::vector<uint32_t> h_batch(max_tiles);
+    {   // candidate bin range of brick b along one axis: bins overlapping [8b - R, 8b + 7 + R)
+        std::vector<int2> h_rng(D.nb);
+        for (int bb = 0; bb < D.nb; ++bb) {
+            h_rng[bb].x = std::max(ss_floor_div(8 * bb - D.R, D.be) + D.nlo, 0);
+            h_rng[bb].y = std::min(ss_floor_div(8 * bb + 6 + D.R, D.be) + D.nlo, D.nbin - 1);
+        }
+        CK(cudaMemcpyAsync(c->brick_rng.p, h_rng.data(), (size_t)D.nb * sizeof(int2), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    std::vector<SsTile> h_tiles(max_tiles);
     uint64_t vtotal = 0, ttotal = 0;
     size_t bcap = 1 << 16;
     c->bkeys_a.ensure(bcap * 8); c->bids_a.ensure(bcap * 4);
     size_t vcap = 1 << 16, tcap = 1 << 17;
     out->verts.ensure(vcap * 12); out->vkeys.ensure(vcap * 8); out->tris.ensure(tcap * 12);
     float ls_ms = 0.f, mc_ms = 0.f;
-    uint64_t ls_launches = 0;
+    uint64_t ls_launches = 0, fix_points = 0;
     out->tile.clear();
+    const bool exact_all = c->ls_exact_all || c->keep_tile_flat >= 0;
     for (uint32_t s0 = 0; s0 < nsub; s0 += (uint32_t)max_tiles) {
         const uint32_t nbatch = std::min<uint32_t>((uint32_t)max_tiles, nsub - s0);
-        for (uint32_t q = 0; q < nbatch; ++q) h_batch[q] = s0 + q;
-        CK(cudaMemcpyAsync(c->batch_subs.p, h_batch.data(), (size_t)nbatch * 4, cudaMemcpyHostToDevice, st));
+        for (uint32_t q = 0; q < nbatch; ++q) {
+            SsTile &T = h_tiles[q];
+            const int64_t f = h_flat[s0 + q];
+            int64_t ijk[3];
+            ijk[0] = f / (nsd[1] * nsd[2]); ijk[1] = (f - ijk[0] * nsd[1] * nsd[2]) / nsd[2]; ijk[2] = f - ijk[0] * nsd[1] * nsd[2] - ijk[1] * nsd[2];
+            for (int d = 0; d < 3; ++d) { T.gbase[d] = (int)(ijk[d] * S); T.smin[d] = faddr(gg.mn[d], fmulr((float)ijk[d], sub_size)); }
+            T.s = s0 + q; T.sparse = (out->sub_sparse[s0 + q] || !D.simd) ? 1u : 0u;
+        }
+        CK(cudaMemcpyAsync(c->tile_tab.p, h_tiles.data(), (size_t)nbatch * sizeof(SsTile), cudaMemcpyHostToDevice, st));
         CK(cudaMemsetAsync(c->tiles.p, 0, (size_t)nbatch * np3 * 4, st));
         CK(cudaEventRecord(c->ev[10], st));
         SsLsArgs A{};
         A.bin_start = c->tab_a.as<uint32_t>(); A.bin_end = c->tab_b.as<uint32_t>(); A.rec = c->rec.as<float4>();
-        A.ksplit = c->ksplit.as<int>(); A.pidx = c->val_a.as<uint32_t>(); A.sub_flat = c->sub_flat.as<uint32_t>();
-        A.sub_sparse = c->sub_sparse.as<uint8_t>(); A.batch_subs = c->batch_subs.as<uint32_t>(); A.tiles = c->tiles.as<float>();
-        A.pairs = c->pairs.as<unsigned long long>();
-        const unsigned nbricks = (unsigned)(D.nb * D.nb * D.nb);
-        LAUNCH(c, k_levelset, nbatch * nbricks, SS_LS_THREADS, D, A);
+        A.ksplit = c->ksplit.as<int>(); A.pidx = c->val_a.as<uint32_t>();
+        A.tile_tab = c->tile_tab.as<SsTile>(); A.brick_rng = c->brick_rng.as<int2>(); A.tiles = c->tiles.as<float>();
+        A.pairs = c->count_pairs ? c->pairs.as<unsigned long long>() : nullptr;
+        A.mode = exact_all ? SS_LS_EXACT_ALL : SS_LS_CERTIFY;
+        A.wflag = nullptr; A.fix_bricks = nullptr;
+        const dim3 ls_grid((unsigned)D.nb, (unsigned)D.nb, (unsigned)D.nb * nbatch);
+        if (c->count_pairs) LAUNCH(c, k_levelset<true>, ls_grid, SS_LS_THREADS, D, A);
+        else LAUNCH(c, k_levelset<false>, ls_grid, SS_LS_THREADS, D, A);
         ++ls_launches;
+        const dim3 tp_grid((unsigned)(nbatch * D.np), planes_y);
+        if (!exact_all) {
+            // exact values for certified points that turn out to lie on a surface-crossing edge
+            const size_t nbr = (size_t)nbatch * nbricks;
+            c->wflag.ensure(nbr * SS_LS_WARPS); c->brick_seen.ensure(nbr * 4); c->fix_list.ensure(nbr * 4); c->nflag.ensure(8);
+            CK(cudaMemsetAsync(c->wflag.p, 0, nbr * SS_LS_WARPS, st));
+            CK(cudaMemsetAsync(c->brick_seen.p, 0, nbr * 4, st));
+            CK(cudaMemsetAsync(c->nflag.p, 0, 8, st));
+            LAUNCH(c, k_fixup_flags, tp_grid, SS_TP_THREADS, D, c->tiles.as<float>(), c->wflag.as<uint8_t>(), c->brick_seen.as<uint32_t>(),
+                   c->fix_list.as<uint32_t>(), c->nflag.as<uint32_t>());
+            uint32_t nfl[2] = { 0, 0 };
+            CK(cudaMemcpyAsync(nfl, c->nflag.p, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (nfl[0]) {
+                A.mode = SS_LS_FIX; A.wflag = c->wflag.as<uint8_t>(); A.fix_bricks = c->fix_list.as<uint32_t>();
+                if (c->count_pairs) LAUNCH(c, k_levelset<true>, nfl[0], SS_LS_THREADS, D, A);
+                else LAUNCH(c, k_levelset<false>, nfl[0], SS_LS_THREADS, D, A);
+                ++ls_launches;
+                fix_points += nfl[1];
+            }
+        }
         CK(cudaEventRecord(c->ev[11], st));
         // optional parity tap
         if (c->keep_tile_flat >= 0) {
@@ -497,16 +547,18 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
                 CK(cudaStreamSynchronize(st));
             }
         }
-        // marching cubes: count, scan, emit
-        const uint32_t npts = (uint32_t)(nbatch * np3);
-        LAUNCH(c, k_mc_count, nblk(npts, 256), 256, D, c->tiles.as<float>(), npts, c->vcnt.as<uint32_t>(), c->tcnt.as<uint32_t>(), c->vmask.as<uint8_t>());
+        // marching cubes: count per block, scan the block totals, emit vertices, emit triangles
+        const uint32_t nblocks = nbatch * (uint32_t)D.np * planes_y;
+        LAUNCH(c, k_mc_count, tp_grid, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->vcnt.as<uint32_t>(), c->tcnt.as<uint32_t>());
+        cub_excl_scan(c, c->vcnt.as<uint32_t>(), c->vblk_off.as<uint32_t>(), nblocks);
+        cub_excl_scan(c, c->tcnt.as<uint32_t>(), c->tblk_off.as<uint32_t>(), nblocks);
         uint32_t lastv[2] = { 0, 0 }, lastt[2] = { 0, 0 };
-        CK(cudaMemcpyAsync(&lastv[1], c->vcnt.as<uint32_t>() + (npts - 1), 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(&lastt[1], c->tcnt.as<uint32_t>() + (npts - 1), 4, cudaMemcpyDeviceToHost, st));
-        cub_excl_scan(c, c->vcnt.as<uint32_t>(), c->vcnt.as<uint32_t>(), npts);
-        cub_excl_scan(c, c->tcnt.as<uint32_t>(), c->tcnt.as<uint32_t>(), npts);
-        CK(cudaMemcpyAsync(&lastv[0], c->vcnt.as<uint32_t>() + (npts - 1), 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(&lastt[0], c->tcnt.as<uint32_t>() + (npts - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&lastv[1], c->vcnt.as<uint32_t>() + (nblocks - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&lastt[1], c->tcnt.as<uint32_t>() + (nblocks - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&lastv[0], c->vblk_off.as<uint32_t>() + (nblocks - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&lastt[0], c->tblk_off.as<uint32_t>() + (nblocks - 1), 4, cudaMemcpyDeviceToHost, st));
+        uint32_t bc = 0;
+        CK(cudaMemcpyAsync(&bc, c->bcount.p, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         const uint64_t bv = (uint64_t)lastv[0] + lastv[1], bt = (uint64_t)lastt[0] + lastt[1];
         if (vtotal + bv >= 0xfffffff0ull || (ttotal + bt) * 3 >= 0xffffffffffull) return ss_fail(SS_ERR_INDEX_TOO_SMALL, "mesh too large for 32-bit vertex ids");
@@ -515,17 +567,16 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
             out->vkeys.grow_keep((vtotal + bv) * 8, vtotal * 8, st);
             out->tris.grow_keep((ttotal + bt) * 12, ttotal * 12, st);
             // boundary list can hold at most every vertex of the batch
-            uint32_t bc = 0;
-            CK(cudaMemcpyAsync(&bc, c->bcount.p, 4, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
             c->bkeys_a.grow_keep(((size_t)bc + bv) * 8, (size_t)bc * 8, st);
             c->bids_a.grow_keep(((size_t)bc + bv) * 4, (size_t)bc * 4, st);
             SsMcOut O{};
             O.verts = out->verts.as<float>(); O.tris = out->tris.as<uint32_t>(); O.vkeys = out->vkeys.as<unsigned long long>();
             O.bkeys = c->bkeys_a.as<unsigned long long>(); O.bids = c->bids_a.as<uint32_t>(); O.bcount = c->bcount.as<uint32_t>();
             O.vbase = (uint32_t)vtotal; O.tbase = (uint32_t)ttotal; O.bcap = (uint32_t)std::min<size_t>((size_t)bc + bv, 0xffffffffu);
-            LAUNCH(c, k_mc_emit, nblk(npts, 256), 256, D, c->tiles.as<float>(), npts, c->vcnt.as<uint32_t>(), c->tcnt.as<uint32_t>(),
-                   c->vmask.as<uint8_t>(), c->batch_subs.as<uint32_t>(), c->sub_flat.as<uint32_t>(), O);
+            LAUNCH(c, k_mc_verts, tp_grid, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->vblk_off.as<uint32_t>(),
+                   c->vcnt.as<uint32_t>(), c->voff.as<uint32_t>(), c->tile_tab.as<SsTile>(), O);
+            LAUNCH(c, k_mc_tris, tp_grid, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->tblk_off.as<uint32_t>(),
+                   c->tcnt.as<uint32_t>(), c->voff.as<uint32_t>(), O);
             vtotal += bv; ttotal += bt;
         }
         CK(cudaEventRecord(c->ev[6], st));
@@ -584,7 +635,7 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     CK(cudaEventElapsedTime(&ms, c->ev[4], c->ev[5])); T.binning = ms;
     T.levelset = ls_ms; T.marching_cubes = mc_ms;
     CK(cudaEventElapsedTime(&ms, c->ev[7], c->ev[8])); T.stitching = ms;
-    T.levelset_launches = ls_launches;
+    T.levelset_launches = ls_launches; T.levelset_fixup_points = fix_points;
     unsigned long long h_pairs = 0;
     CK(cudaMemcpy(&h_pairs, c->pairs.p, 8, cudaMemcpyDeviceToHost));
     T.levelset_pairs = (double)h_pairs;
@@ -612,7 +663,7 @@ extern "C" int ss_levelset_tile_f32(ss_context *c, const float *xyz, const float
         SsDev D{};
         for (int d = 0; d < 3; ++d) { D.gmin[d] = global_min[d]; D.nsd[d] = (int)subdomain_ijk[d] + 1; }
         D.c = cube_size; D.h = h; D.h2 = fmulr(h, h); D.h2m = fmulr(D.h2, 1.01f); D.rest_mass = rest_mass;
-        D.sub_size = fmulr(cube_size, (float)S); D.S = (int)S; D.np = (int)S + 1;
+        D.sub_size = fmulr(cube_size, (float)S); D.S = (int)S; D.np = (int)S + 1; D.np_magic = (uint32_t)(4294967296ull / (uint64_t)D.np) + 1u;
         D.R = (int)ceilf(fdivr(h, cube_size));
         fill_kernel_consts(D, h);
         fill_bins(D, cube_size);
@@ -644,12 +695,24 @@ extern "C" int ss_levelset_tile_f32(ss_context *c, const float *xyz, const float
             c->rec.ensure((size_t)M * 16); c->ksplit.ensure((size_t)M * 4);
             LAUNCH(c, k_records, nblk(M, 256), 256, D, c->xyz.as<float>(), c->rho.as<float>(), M, c->key_b.as<uint32_t>(), c->val_a.as<uint32_t>(),
                    c->sub_flat.as<uint32_t>(), c->rec.as<float4>(), c->ksplit.as<int>());
+            SsTile T{};
+            for (int d = 0; d < 3; ++d) { T.gbase[d] = (int)(subdomain_ijk[d] * (int64_t)S); T.smin[d] = faddr(global_min[d], fmulr((float)subdomain_ijk[d], D.sub_size)); }
+            T.s = 0; T.sparse = D.simd ? 0u : 1u;
+            std::vector<int2> h_rng(D.nb);
+            for (int bb = 0; bb < D.nb; ++bb) {
+                h_rng[bb].x = std::max(ss_floor_div(8 * bb - D.R, D.be) + D.nlo, 0);
+                h_rng[bb].y = std::min(ss_floor_div(8 * bb + 6 + D.R, D.be) + D.nlo, D.nbin - 1);
+            }
+            c->tile_tab.ensure(sizeof(SsTile)); c->brick_rng.ensure((size_t)D.nb * sizeof(int2));
+            CK(cudaMemcpyAsync(c->tile_tab.p, &T, sizeof(SsTile), cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(c->brick_rng.p, h_rng.data(), (size_t)D.nb * sizeof(int2), cudaMemcpyHostToDevice, st));
             SsLsArgs A{};
             A.bin_start = c->tab_a.as<uint32_t>(); A.bin_end = c->tab_b.as<uint32_t>(); A.rec = c->rec.as<float4>();
-            A.ksplit = c->ksplit.as<int>(); A.pidx = c->val_a.as<uint32_t>(); A.sub_flat = c->sub_flat.as<uint32_t>();
-            A.sub_sparse = c->sub_sparse.as<uint8_t>(); A.batch_subs = c->batch_subs.as<uint32_t>(); A.tiles = c->tiles.as<float>();
-            A.pairs = nullptr;
-            LAUNCH(c, k_levelset, (unsigned)(D.nb * D.nb * D.nb), SS_LS_THREADS, D, A);
+            A.ksplit = c->ksplit.as<int>(); A.pidx = c->val_a.as<uint32_t>();
+            A.tile_tab = c->tile_tab.as<SsTile>(); A.brick_rng = c->brick_rng.as<int2>(); A.tiles = c->tiles.as<float>();
+            A.pairs = nullptr; A.wflag = nullptr; A.fix_bricks = nullptr; A.mode = SS_LS_EXACT_ALL;
+            LAUNCH(c, k_levelset<false>, dim3((unsigned)D.nb, (unsigned)D.nb, (unsigned)D.nb), SS_LS_THREADS, D, A);
+            CK(cudaStreamSynchronize(st));
         }
         CK(cudaMemcpyAsync(tile_out, c->tiles.p, np3 * 4, cudaMemcpyDefault, st));
         CK(cudaStreamSynchronize(st));

@@ -51,12 +51,16 @@ def test_cuda_bit_exact_vs_oracle(ss, oracle_mod, name, gen, kw):
     from splashsurf_b200 import synthetic as syn
     p = gen(syn)
     o = oracle_mod.reconstruct(p, **kw)
-    g = ss.reconstruct_surface(p, with_debug=True, **kw)
-    assert np.array_equal(g.subdomains["flat"], o["subdomain_flat"]) and np.array_equal(g.subdomains["count"], o["subdomain_count"])
-    assert np.array_equal(g.subdomains["sparse"], o["subdomain_sparse"])
-    assert np.array_equal(g.particle_densities, o["particle_densities"])
-    m = _parity(oracle_mod, g, o, kw.get("subdomain_num_cubes_per_dim", 64))
-    assert m["keys_equal"] and m["triangles_equal"] and m["n_not_bitexact"] == 0, m
+    for exact_everywhere in (False, True):          # default: interior points only classified; both must be bit-exact
+        ctx = ss.Context()
+        ctx.set_levelset_exact_everywhere(exact_everywhere)
+        g = ss.reconstruct_surface(p, with_debug=True, context=ctx, **kw)
+        ctx.close()
+        assert np.array_equal(g.subdomains["flat"], o["subdomain_flat"]) and np.array_equal(g.subdomains["count"], o["subdomain_count"])
+        assert np.array_equal(g.subdomains["sparse"], o["subdomain_sparse"])
+        assert np.array_equal(g.particle_densities, o["particle_densities"])
+        m = _parity(oracle_mod, g, o, kw.get("subdomain_num_cubes_per_dim", 64))
+        assert m["keys_equal"] and m["triangles_equal"] and m["n_not_bitexact"] == 0, (exact_everywhere, m)
 
 
 def test_cuda_aabb_filter(ss, oracle_mod):
