@@ -178,14 +178,14 @@ def main():
 
     # ---- device-resident steps
     for _ in range(args.warmup):
-        res = runner.step(dev_in.data_ptr(), len(p_local), copy_out=False)
+        res = runner.step(dev_in, copy_out=False)
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
     dev_ms, ls_ms, launches, pairs, ls_launches = 0.0, 0.0, 0, 0.0, 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res = runner.step(dev_in.data_ptr(), len(p_local), copy_out=False)
+        res = runner.step(dev_in, copy_out=False)
         dev_ms += res["device_ms"]; ls_ms += res["timings"]["levelset"]; launches += res["launches"]
         pairs += res["timings"]["levelset_pairs"]; ls_launches += res["timings"]["levelset_launches"]
     barrier()
@@ -197,23 +197,36 @@ def main():
     dev_ms_max, wall_ms_max = stats.tolist()
     ms_per_step = dev_ms_max / args.steps
     value = n_total / (ms_per_step * 1e-3) / 1e6
-    nv, nt = res["nv"], res["nt"]
+    agg = torch.tensor([res["nv"], res["nt"], res["nsub_owned"], res["memberships"], ls_ms, pairs, float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        agg_max = agg.clone()
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+        dist.all_reduce(agg_max, op=dist.ReduceOp.MAX)
+        ls_ms = float(agg_max[4])            # slowest rank's level-set time
+    nv, nt, nsub_total, memberships_total = int(agg[0]), int(agg[1]), int(agg[2]), float(agg[3])
+    launches = int(agg[6])
     # one instrumented step (outside the timed region) for the work model of the level-set kernel
     ctx.set_count_pairs(True)
-    pairs = runner.step(dev_in.data_ptr(), len(p_local), copy_out=False)["timings"]["levelset_pairs"] * args.steps
+    pairs_t = torch.tensor([runner.step(dev_in, copy_out=False)["timings"]["levelset_pairs"] * args.steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(pairs_t, op=dist.ReduceOp.SUM)
+    pairs = float(pairs_t.item())
     ctx.set_count_pairs(False)
     fixups = res["timings"].get("levelset_fixup_points", 0)
     stage = {k: round(v, 3) for k, v in res["timings"].items() if isinstance(v, float)}
 
     # ---- end to end through the C ABI with host buffers (pinned input, mesh copied back)
     for _ in range(min(args.warmup, 2)):
-        runner.step(host_in.data_ptr(), len(p_local), copy_out=True)
+        runner.step(host_in, copy_out=True)
     barrier()
     t0 = time.perf_counter()
     d2h = 0
+    nv_g = nt_g = None
     for _ in range(args.steps):
-        r2 = runner.step(host_in.data_ptr(), len(p_local), copy_out=True)
+        r2 = runner.step(host_in, copy_out=True)
         d2h = r2["d2h_bytes"]
+        if r2.get("nv_global") is not None:
+            nv_g, nt_g = r2["nv_global"], r2["nt_global"]
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t0)
     t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
@@ -224,11 +237,11 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
-        n_sub = res["nsub"]
+        n_sub = nsub_total
         np3 = 65 ** 3
         # algorithmic bytes of the level-set kernel per step: particle records (16 B pos+V, 4 B k_split, 4 B index) of every
         # membership once + one f32 tile write per subdomain (16 g N + 4 P N)
-        ls_bytes = res["memberships"] * 24.0 + n_sub * np3 * 4.0
+        ls_bytes = memberships_total * 24.0 + n_sub * np3 * 4.0
         ls_s = (ls_ms / args.steps) * 1e-3
         ach = ls_bytes / ls_s / 1e9 if ls_s > 0 else 0.0
         flops = (pairs / args.steps) * 30.0
@@ -247,7 +260,7 @@ def main():
                            "cube_size": "0.5r", "smoothing_length": "2.0r", "iso": 0.6, "subdomain_cubes": 64,
                            "parallelism": f"subdomain slabs x{world}" if world > 1 else "single GPU",
                            "l2": "inputs (600 MB) and tiles (GBs) exceed the 126 MB L2; no flush needed"},
-                "mesh": {"vertices": int(nv), "triangles": int(nt), "subdomains": int(n_sub)},
+                "mesh": {"vertices": int(nv_g if nv_g is not None else nv), "triangles": int(nt_g if nt_g is not None else nt), "subdomains": int(n_sub)},
                 "wall_ms_per_step": wall_ms_max / args.steps, "stage_ms_last_step": stage,
                 "e2e": {"value": e2e_val, "unit": "Mparticles/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(len(p_local) * 12 * world),
                         "d2h_bytes_per_step": int(d2h)},

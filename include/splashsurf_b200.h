@@ -114,6 +114,28 @@ void ss_surface_free(ss_surface *s);
 int ss_grid_for_reconstruction_f32(ss_context *ctx, const float *xyz, uint64_t n, const ss_params_f32 *params,
                                    ss_grid_f32 *grid_out);
 
+/* ---- multi-GPU (one process per GPU; see splashsurf_b200/distributed.py and DESIGN.md row e) ----
+ * The reference parallelises over subdomains (dense_subdomains.rs:521-526, :1581-1598); across GPUs each rank
+ * owns a slab of the subdomain grid: subdomains whose index along `axis` lies in [own_lo, own_hi).  `grid` is the
+ * grid of ALL particles (ss_grid_for_reconstruction_f32 of the reduced bounding box); `xyz` are the rank's particles
+ * in ASCENDING GLOBAL INDEX order: every particle that is a member (owner or ghost) of a subdomain in
+ * [own_lo - halo, own_hi + halo).  Subdomains of the halo layers are processed for particle densities only, so that
+ * ghost particles get the same density the owning rank computes.  `global_max_particles` is the maximum particle
+ * count of any subdomain over all ranks (sparse-subdomain rule, dense_subdomains.rs:1242-1251); with
+ * stop_after_decomposition != 0 only the decomposition runs and ss_surface_max_subdomain_particles() reports the
+ * local maximum to be max-reduced across ranks. */
+int ss_reconstruct_partition_f32(ss_context *ctx, const float *xyz, uint64_t n, const ss_params_f32 *params,
+                                 const ss_grid_f32 *grid, int axis, int64_t own_lo, int64_t own_hi, int64_t halo,
+                                 uint64_t global_max_particles, int stop_after_decomposition, ss_surface **out);
+uint64_t ss_surface_max_subdomain_particles(const ss_surface *s);
+const unsigned long long *ss_surface_device_vertex_keys(const ss_surface *s);   /* nv u64 MC edge keys, device memory */
+int ss_surface_copy_subdomain_owned(const ss_surface *s, uint8_t *dst);          /* 1: owned, 0: density-only halo */
+/* Welds vertices with equal MC edge key in a concatenation of per-rank meshes (all pointers DEVICE memory; `cand`
+ * lists the vertex ids that may be duplicated, i.e. vertices on the faces between slabs).  Compacts verts / keys in
+ * place, renumbers tris, returns the vertex count in *nv_out ("stitching" across GPUs). */
+int ss_weld_meshes(ss_context *ctx, float *verts, unsigned long long *keys, uint64_t nv, uint32_t *tris, uint64_t nt,
+                   const uint32_t *cand, uint64_t n_cand, uint64_t *nv_out);
+
 /* Stage-level entry: density_grid_loop_auto / density_grid_loop_scalar (dense_subdomains.rs:715-847, both `pub`
  * and driven by the reference's own bench fixture, benches/benches/bench_grid_loop.rs:203-262).  Evaluates the
  * (S+1)^3 level-set tile (i-major, f32) of ONE subdomain from an explicit particle list -- accumulated in list

@@ -104,6 +104,13 @@ def load_library():
     L.ss_context_set_levelset_exact_everywhere.argtypes = [vp, C.c_int]
     L.ss_context_set_count_pairs.argtypes = [vp, C.c_int]
     L.ss_levelset_tile_f32.argtypes = [vp, vp, vp, u64, vp, C.c_float, vp, C.c_uint32, C.c_float, C.c_float, C.c_int, vp]
+    L.ss_reconstruct_partition_f32.argtypes = [vp, vp, u64, C.POINTER(_Params), C.POINTER(_Grid), C.c_int, i64, i64, i64, u64, C.c_int, C.POINTER(vp)]
+    L.ss_surface_max_subdomain_particles.argtypes = [vp]
+    L.ss_surface_max_subdomain_particles.restype = u64
+    L.ss_surface_device_vertex_keys.argtypes = [vp]
+    L.ss_surface_device_vertex_keys.restype = vp
+    L.ss_surface_copy_subdomain_owned.argtypes = [vp, vp]
+    L.ss_weld_meshes.argtypes = [vp, vp, vp, u64, vp, u64, vp, u64, C.POINTER(u64)]
     if L.ss_abi_version() != 1:
         raise ImportError("libsplashsurf_b200.so ABI version mismatch")
     _LIB = L

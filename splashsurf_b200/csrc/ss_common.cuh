@@ -40,6 +40,8 @@ struct SsDev {
     float inv_c;          // 1/c (binning only; not parity relevant)
     float rr_cells;       // R + slack: particles farther than this from the tile are dropped (binning only)
     int simd;             // 1: AVX-path arithmetic for dense subdomains
+    // multi-GPU partition: memberships are kept only for subdomains with keep_lo <= ijk[part_axis] < keep_hi
+    int part_axis, keep_lo, keep_hi;
 };
 
 // ------------------------------------------------------------------ exact helpers ----

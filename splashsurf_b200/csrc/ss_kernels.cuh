@@ -96,6 +96,10 @@ __device__ __forceinline__ int ss_classify(const SsDev &P, float px, float py, f
         if (!ok) continue;
         int t0 = ijk[0] + i, t1 = ijk[1] + j, t2 = ijk[2] + k;
         if (t0 < 0 || t1 < 0 || t2 < 0 || t0 >= P.nsd[0] || t1 >= P.nsd[1] || t2 >= P.nsd[2]) continue;
+        {   // partitioned run: this rank keeps only its slab (+ density halo) of subdomains
+            const int ta = P.part_axis == 0 ? t0 : (P.part_axis == 1 ? t1 : t2);
+            if (ta < P.keep_lo || ta >= P.keep_hi) continue;
+        }
         emit(cnt, (t0 * P.nsd[1] + t1) * P.nsd[2] + t2);
         ++cnt;
     }
@@ -255,10 +259,11 @@ k_density(SsDev P, uint32_t m, const uint32_t *__restrict__ key, const float4 *_
 // Binning is only a conservative cull: a particle farther than h from every tile point is dropped (key 0xffffffff).
 __global__ void k_bin_keys(SsDev P, const float *__restrict__ xyz, uint32_t m, const uint32_t *__restrict__ cid,
                            const uint32_t *__restrict__ sub_flat, const uint32_t *__restrict__ pidx,
-                           uint32_t *__restrict__ key) {
+                           const uint8_t *__restrict__ sub_owned, uint32_t *__restrict__ key) {
     uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= m) return;
     uint32_t s = cid[e], p = pidx[e];
+    if (sub_owned && !sub_owned[s]) { key[e] = 0xffffffffu; return; }   // density-only halo subdomain
     SsSubGeom g = ss_sub_geom(P, sub_flat[s]);
     int b[3];
     bool drop = false;
@@ -818,6 +823,11 @@ __global__ void k_weld_runs(const unsigned long long *__restrict__ bkeys, const 
     uint32_t f = e + 1;
     while (f < nb && bkeys[f] == bkeys[e]) { best = min(best, bids[f]); ++f; }
     for (uint32_t q = e; q < f; ++q) { uint32_t id = bids[q]; remap[id] = best; if (id != best) keep[id] = 0; }
+}
+__global__ void k_gather_keys(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ ids, uint32_t n,
+                              unsigned long long *__restrict__ out) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) out[e] = keys[ids[e]];
 }
 __global__ void k_iota_keep(uint32_t n, uint32_t *__restrict__ remap, uint32_t *__restrict__ keep) {
     uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;

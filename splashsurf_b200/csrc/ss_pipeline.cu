@@ -63,7 +63,7 @@ struct ss_context {
     int count_pairs = 0;             // 1: count in-support evaluations (work model; slower)
     // reusable scratch
     DevBuf xyz, xyz_f, filt_flag, filt_flag32, filt_off, aabb, cnt, off, key_a, key_b, val_a, val_b, cid, cub_tmp,
-        sub_flat, sub_off, sub_sparse, flags, scan, spos, rho, tab_a, tab_b, rec, ksplit, batch_subs, tiles, vcnt,
+        sub_flat, sub_off, sub_sparse, sub_owned, flags, scan, spos, rho, tab_a, tab_b, rec, ksplit, batch_subs, tiles, vcnt,
         tcnt, vmask, voff, vblk_off, tblk_off, tile_tab, brick_rng, wflag, brick_seen, fix_list, nflag, bkeys_a, bkeys_b, bids_a, bids_b, bcount, remap, keep, newid, err, pairs;
     uint64_t launches = 0;
 };
@@ -76,7 +76,8 @@ struct ss_surface {
     int S = 0;
     DevBuf verts, tris, vkeys, rho;
     std::vector<uint8_t> inside_aabb;
-    std::vector<int64_t> sub_flat; std::vector<uint64_t> sub_count; std::vector<uint8_t> sub_sparse;
+    std::vector<int64_t> sub_flat; std::vector<uint64_t> sub_count; std::vector<uint8_t> sub_sparse, sub_owned;
+    uint64_t max_particles = 0;
     std::vector<float> tile;
     ss_timings tm{};
 };
@@ -188,7 +189,7 @@ extern "C" void ss_context_destroy(ss_context *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = { &c->xyz, &c->xyz_f, &c->filt_flag, &c->filt_flag32, &c->filt_off, &c->aabb, &c->cnt, &c->off, &c->key_a, &c->key_b,
-                       &c->val_a, &c->val_b, &c->cid, &c->cub_tmp, &c->sub_flat, &c->sub_off, &c->sub_sparse, &c->flags, &c->scan,
+                       &c->val_a, &c->val_b, &c->cid, &c->cub_tmp, &c->sub_flat, &c->sub_off, &c->sub_sparse, &c->sub_owned, &c->flags, &c->scan,
                        &c->spos, &c->rho, &c->tab_a, &c->tab_b, &c->rec, &c->ksplit, &c->batch_subs, &c->tiles, &c->vcnt, &c->tcnt,
                        &c->vmask, &c->voff, &c->vblk_off, &c->tblk_off, &c->tile_tab, &c->brick_rng, &c->wflag, &c->brick_seen, &c->fix_list, &c->nflag, &c->bkeys_a, &c->bkeys_b, &c->bids_a, &c->bids_b, &c->bcount, &c->remap, &c->keep, &c->newid,
                        &c->err, &c->pairs };
@@ -212,7 +213,7 @@ struct Prepared {
 };
 
 static int prepare_particles(ss_context *c, const float *xyz, uint64_t n_in, const ss_params_f32 *p, Prepared &P,
-                             std::vector<uint8_t> *inside_out) {
+                             std::vector<uint8_t> *inside_out, const ss_grid_f32 *given_grid = nullptr) {
     if (n_in > 0xfffffff0ull) return ss_fail(SS_ERR_INDEX_TOO_SMALL, "more than 2^32 particles are not supported by one device");
     const float *d_in = nullptr;
     cudaPointerAttributes attr{};
@@ -253,6 +254,11 @@ static int prepare_particles(ss_context *c, const float *xyz, uint64_t n_in, con
         }
     } else if (p->has_particle_aabb && inside_out) inside_out->clear();
 
+    if (given_grid) {   // partitioned run: the grid of ALL particles was computed by the caller
+        for (int d = 0; d < 3; ++d) { P.grid.mn[d] = given_grid->aabb_min[d]; P.grid.mx[d] = given_grid->aabb_max[d]; P.grid.np[d] = given_grid->points_per_dim[d]; P.grid.nc[d] = given_grid->cells_per_dim[d]; }
+        P.grid.cell = given_grid->cell_size;
+        return SS_OK;
+    }
     // grid_for_reconstruction, lib.rs:476-516
     float mn[3], mx[3];
     if (p->has_particle_aabb) {
@@ -322,7 +328,16 @@ static void fill_bins(SsDev &D, float cs) {
 }
 
 // ------------------------------------------------------------------ the subdomain-grid pipeline ----
-static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params_f32 *p, ss_surface *out) {
+struct Partition {
+    int enabled = 0;
+    int axis = 0;
+    int64_t own_lo = 0, own_hi = 0;     // owned subdomain index range along `axis`
+    int64_t halo = 0;                   // extra subdomain layers kept for densities only
+    uint64_t global_max_particles = 0;  // max particles per subdomain over ALL ranks (0: use the local maximum)
+    int stop_after_decomposition = 0;   // only report the local maximum (out->max_particles)
+};
+
+static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params_f32 *p, ss_surface *out, const Partition &part = Partition()) {
     const uint64_t n = PP.n;
     const float *d_xyz = PP.d_xyz;
     cudaStream_t st = c->stream;
@@ -362,6 +377,10 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     D.ns_stride = D.nsD * D.nsD * D.nsD;
     fill_bins(D, cs);
     D.simd = p->enable_simd ? 1 : 0;
+    D.part_axis = part.enabled ? part.axis : 0;
+    D.keep_lo = part.enabled ? (int)std::max<int64_t>(part.own_lo - part.halo, 0) : 0;
+    D.keep_hi = part.enabled ? (int)std::min<int64_t>(part.own_hi + part.halo, nsd[D.part_axis]) : (int)nsd[0];
+    if (!part.enabled) { D.part_axis = 0; D.keep_lo = 0; D.keep_hi = (int)nsd[0]; }
     {
         int per_axis = ss_floor_div(6 + D.R, D.be) - ss_floor_div(-D.R, D.be) + 2;
         if (per_axis * per_axis > 128) return ss_fail(SS_ERR_INVALID_PARAMETER, "internal: too many candidate bin runs per brick");
@@ -407,12 +426,28 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     // sparse classification, dense_subdomains.rs:1242-1251, :1590
     uint64_t maxp = 0;
     for (uint32_t s = 0; s < nsub; ++s) maxp = std::max<uint64_t>(maxp, h_off[s + 1] - h_off[s]);
+    out->max_particles = maxp;
+    if (part.enabled && part.global_max_particles) maxp = std::max<uint64_t>(maxp, part.global_max_particles);
     const uint64_t sparse_limit = std::max<uint64_t>(maxp / 20, 100);
     out->nsub = nsub; out->sub_flat.resize(nsub); out->sub_count.resize(nsub); out->sub_sparse.resize(nsub);
+    std::vector<uint8_t> h_owned(nsub, 1);
+    std::vector<uint32_t> owned_list;
+    owned_list.reserve(nsub);
     for (uint32_t s = 0; s < nsub; ++s) {
         out->sub_flat[s] = h_flat[s]; out->sub_count[s] = h_off[s + 1] - h_off[s];
         out->sub_sparse[s] = (out->sub_count[s] <= sparse_limit) ? 1 : 0;
+        if (part.enabled) {
+            const int64_t f = h_flat[s];
+            int64_t ijk[3];
+            ijk[0] = f / (nsd[1] * nsd[2]); ijk[1] = (f - ijk[0] * nsd[1] * nsd[2]) / nsd[2]; ijk[2] = f - ijk[0] * nsd[1] * nsd[2] - ijk[1] * nsd[2];
+            h_owned[s] = (ijk[part.axis] >= part.own_lo && ijk[part.axis] < part.own_hi) ? 1 : 0;
+        }
+        if (h_owned[s]) owned_list.push_back(s);
     }
+    out->sub_owned = h_owned;
+    if (part.enabled && part.stop_after_decomposition) { for (int e = 3; e <= 9; ++e) CK(cudaEventRecord(c->ev[e], st)); CK(cudaStreamSynchronize(st)); return SS_OK; }
+    c->sub_owned.ensure(nsub);
+    CK(cudaMemcpyAsync(c->sub_owned.p, h_owned.data(), nsub, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(c->sub_sparse.p, out->sub_sparse.data(), nsub, cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(c->ev[3], st));
 
@@ -440,7 +475,7 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     // ---- splat binning: (subdomain, 8^3-point brick) bins + particle records
     // val_b still holds the membership particle indices in subdomain order (stable input for the bin sort)
     LAUNCH(c, k_bin_keys, nblk(M, 256), 256, D, d_xyz, M, c->cid.as<uint32_t>(), c->sub_flat.as<uint32_t>(), c->val_b.as<uint32_t>(),
-           c->key_a.as<uint32_t>());
+           part.enabled ? c->sub_owned.as<uint8_t>() : nullptr, c->key_a.as<uint32_t>());
     cub_sort_pairs(c, c->key_a.as<uint32_t>(), c->key_b.as<uint32_t>(), c->val_b.as<uint32_t>(), c->val_a.as<uint32_t>(), M, 32);
     const uint64_t bin_keys = (uint64_t)nsub * D.nbin_sub;
     c->tab_a.ensure(bin_keys * 4); c->tab_b.ensure(bin_keys * 4);
@@ -466,7 +501,8 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     size_t max_tiles = c->max_tiles ? c->max_tiles : std::max<size_t>(1, std::min<size_t>((free_b / 3) / per_tile, 4096));
     max_tiles = std::min<size_t>(max_tiles, std::max<size_t>(1, (size_t)0x7fffffff / np3 / 2));
     max_tiles = std::min<size_t>(max_tiles, std::max<size_t>(1, (size_t)65535 / D.nb));       // gridDim.z = nb * tiles
-    max_tiles = std::min<size_t>(max_tiles, nsub);
+    const uint32_t nown = (uint32_t)owned_list.size();
+    max_tiles = std::min<size_t>(max_tiles, std::max<uint32_t>(nown, 1));
     const size_t nblk_max = max_tiles * D.np * planes_y;
     c->tiles.ensure(max_tiles * np3 * 4); c->voff.ensure(max_tiles * np3 * 4); c->vmask.ensure(max_tiles * np3);
     c->vcnt.ensure(nblk_max * 4 + 4); c->tcnt.ensure(nblk_max * 4 + 4); c->vblk_off.ensure(nblk_max * 4 + 4); c->tblk_off.ensure(nblk_max * 4 + 4);
@@ -493,15 +529,16 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     uint64_t ls_launches = 0, fix_points = 0;
     out->tile.clear();
     const bool exact_all = c->ls_exact_all || c->keep_tile_flat >= 0;
-    for (uint32_t s0 = 0; s0 < nsub; s0 += (uint32_t)max_tiles) {
-        const uint32_t nbatch = std::min<uint32_t>((uint32_t)max_tiles, nsub - s0);
+    for (uint32_t s0 = 0; s0 < nown; s0 += (uint32_t)max_tiles) {
+        const uint32_t nbatch = std::min<uint32_t>((uint32_t)max_tiles, nown - s0);
         for (uint32_t q = 0; q < nbatch; ++q) {
             SsTile &T = h_tiles[q];
-            const int64_t f = h_flat[s0 + q];
+            const uint32_t sid = owned_list[s0 + q];
+            const int64_t f = h_flat[sid];
             int64_t ijk[3];
             ijk[0] = f / (nsd[1] * nsd[2]); ijk[1] = (f - ijk[0] * nsd[1] * nsd[2]) / nsd[2]; ijk[2] = f - ijk[0] * nsd[1] * nsd[2] - ijk[1] * nsd[2];
             for (int d = 0; d < 3; ++d) { T.gbase[d] = (int)(ijk[d] * S); T.smin[d] = faddr(gg.mn[d], fmulr((float)ijk[d], sub_size)); }
-            T.s = s0 + q; T.sparse = (out->sub_sparse[s0 + q] || !D.simd) ? 1u : 0u;
+            T.s = sid; T.sparse = (out->sub_sparse[sid] || !D.simd) ? 1u : 0u;
         }
         CK(cudaMemcpyAsync(c->tile_tab.p, h_tiles.data(), (size_t)nbatch * sizeof(SsTile), cudaMemcpyHostToDevice, st));
         CK(cudaMemsetAsync(c->tiles.p, 0, (size_t)nbatch * np3 * 4, st));
@@ -541,7 +578,7 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
         CK(cudaEventRecord(c->ev[11], st));
         // optional parity tap
         if (c->keep_tile_flat >= 0) {
-            for (uint32_t q = 0; q < nbatch; ++q) if ((int64_t)h_flat[s0 + q] == c->keep_tile_flat) {
+            for (uint32_t q = 0; q < nbatch; ++q) if ((int64_t)h_flat[owned_list[s0 + q]] == c->keep_tile_flat) {
                 out->tile.resize(np3);
                 CK(cudaMemcpyAsync(out->tile.data(), c->tiles.as<float>() + (size_t)q * np3, np3 * 4, cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
@@ -685,7 +722,7 @@ extern "C" int ss_levelset_tile_f32(ss_context *c, const float *xyz, const float
             CK(cudaMemcpyAsync(c->sub_sparse.p, &z8, 1, cudaMemcpyHostToDevice, st));
             CK(cudaMemcpyAsync(c->batch_subs.p, &zero, 4, cudaMemcpyHostToDevice, st));
             LAUNCH(c, k_bin_keys, nblk(M, 256), 256, D, c->xyz.as<float>(), M, c->cid.as<uint32_t>(), c->sub_flat.as<uint32_t>(),
-                   c->val_b.as<uint32_t>(), c->key_a.as<uint32_t>());
+                   c->val_b.as<uint32_t>(), (const uint8_t *)nullptr, c->key_a.as<uint32_t>());
             cub_sort_pairs(c, c->key_a.as<uint32_t>(), c->key_b.as<uint32_t>(), c->val_b.as<uint32_t>(), c->val_a.as<uint32_t>(), M, 32);
             const uint64_t bin_keys = (uint64_t)D.nbin_sub;
             c->tab_a.ensure(bin_keys * 4); c->tab_b.ensure(bin_keys * 4);
@@ -721,6 +758,108 @@ extern "C" int ss_levelset_tile_f32(ss_context *c, const float *xyz, const float
         cudaGetLastError();
         return ss_fail(err.e == cudaErrorMemoryAllocation ? SS_ERR_OUT_OF_MEMORY : SS_ERR_CUDA, std::string(err.what) + ": " + cudaGetErrorString(err.e));
     }
+}
+
+// ------------------------------------------------------------------ multi-GPU: one rank's slab of subdomains ----
+extern "C" int ss_reconstruct_partition_f32(ss_context *c, const float *xyz, uint64_t n_in, const ss_params_f32 *p, const ss_grid_f32 *grid,
+                                            int axis, int64_t own_lo, int64_t own_hi, int64_t halo, uint64_t global_max_particles,
+                                            int stop_after_decomposition, ss_surface **out) {
+    if (!c || !out || !grid) return ss_fail(SS_ERR_INVALID_PARAMETER, "NULL argument");
+    *out = nullptr;
+    int rc = validate_params(p);
+    if (rc) return rc;
+    if (p->has_particle_aabb) return ss_fail(SS_ERR_UNSUPPORTED, "filter particles before partitioning (particle_aabb is applied by the caller)");
+    if (p->spatial_decomposition != 1) return ss_fail(SS_ERR_INVALID_PARAMETER, "partitioned reconstruction requires the subdomain grid");
+    if (axis < 0 || axis > 2 || own_lo < 0 || own_hi < own_lo || halo < 0) return ss_fail(SS_ERR_INVALID_PARAMETER, "bad partition");
+    if (n_in && !xyz) return ss_fail(SS_ERR_INVALID_PARAMETER, "xyz is NULL");
+    ss_surface *s = nullptr;
+    try {
+        CK(cudaSetDevice(c->device));
+        s = new ss_surface();
+        s->device = c->device; s->n_in = n_in;
+        c->launches = 0;
+        Prepared P;
+        rc = prepare_particles(c, xyz, n_in, p, P, nullptr, grid);
+        if (rc) { ss_surface_free(s); return rc; }
+        s->n = P.n; s->grid = P.grid; s->used_decomposition = 1;
+        Partition part;
+        part.enabled = 1; part.axis = axis; part.own_lo = own_lo; part.own_hi = own_hi; part.halo = halo;
+        part.global_max_particles = global_max_particles; part.stop_after_decomposition = stop_after_decomposition;
+        rc = run_subdomain_grid(c, P, p, s, part);
+        if (rc) { ss_surface_free(s); return rc; }
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); s->tm.upload = ms;
+        CK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); s->tm.aabb_and_grid = ms;
+        CK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[9])); s->tm.total_device = ms;
+        s->tm.kernel_launches = c->launches;
+        *out = s;
+        return SS_OK;
+    } catch (const SsCudaError &err) {
+        if (s) ss_surface_free(s);
+        cudaGetLastError();
+        char buf[512];
+        snprintf(buf, sizeof(buf), "%s failed at %s:%d: %s", err.what, err.file, err.line, cudaGetErrorString(err.e));
+        return ss_fail(err.e == cudaErrorMemoryAllocation ? SS_ERR_OUT_OF_MEMORY : SS_ERR_CUDA, buf);
+    } catch (const std::bad_alloc &) {
+        if (s) ss_surface_free(s);
+        return ss_fail(SS_ERR_OUT_OF_MEMORY, "host allocation failed");
+    }
+}
+extern "C" uint64_t ss_surface_max_subdomain_particles(const ss_surface *s) { return s ? s->max_particles : 0; }
+
+// Welds vertices that carry the same MC edge key (duplicates on faces between ranks' slabs) in a concatenation of
+// per-rank meshes.  All pointers are DEVICE memory: verts nv x 3 f32, keys nv u64 (as produced per vertex by
+// ss_surface_device_vertex_keys), tris nt x 3 u32 (already offset to the concatenated numbering).  `cand` lists the
+// n_cand vertex ids that may have duplicates.  Compacts verts/keys in place, rewrites tris, returns the new count.
+extern "C" int ss_weld_meshes(ss_context *c, float *verts, unsigned long long *keys, uint64_t nv, uint32_t *tris, uint64_t nt,
+                              const uint32_t *cand, uint64_t n_cand, uint64_t *nv_out) {
+    if (!c || !nv_out) return ss_fail(SS_ERR_INVALID_PARAMETER, "NULL argument");
+    *nv_out = nv;
+    if (!nv || !n_cand) return SS_OK;
+    if (nv >= 0xfffffff0ull || n_cand >= 0x7fffffffull) return ss_fail(SS_ERR_INDEX_TOO_SMALL, "mesh too large");
+    try {
+        CK(cudaSetDevice(c->device));
+        cudaStream_t st = c->stream;
+        const uint32_t bc = (uint32_t)n_cand;
+        c->bkeys_a.ensure((size_t)bc * 8); c->bkeys_b.ensure((size_t)bc * 8); c->bids_b.ensure((size_t)bc * 4);
+        LAUNCH(c, k_gather_keys, nblk(bc, 256), 256, keys, cand, bc, c->bkeys_a.as<unsigned long long>());
+        size_t tmp = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->bkeys_a.as<unsigned long long>(), c->bkeys_b.as<unsigned long long>(),
+                                           cand, c->bids_b.as<uint32_t>(), (int)bc, 0, 64, st));
+        c->cub_tmp.ensure(tmp);
+        CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, c->bkeys_a.as<unsigned long long>(), c->bkeys_b.as<unsigned long long>(),
+                                           cand, c->bids_b.as<uint32_t>(), (int)bc, 0, 64, st));
+        c->remap.ensure(nv * 4); c->keep.ensure(nv * 4); c->newid.ensure(nv * 4 + 4);
+        LAUNCH(c, k_iota_keep, nblk(nv, 256), 256, (uint32_t)nv, c->remap.as<uint32_t>(), c->keep.as<uint32_t>());
+        LAUNCH(c, k_weld_runs, nblk(bc, 256), 256, c->bkeys_b.as<unsigned long long>(), c->bids_b.as<uint32_t>(), bc,
+               c->remap.as<uint32_t>(), c->keep.as<uint32_t>());
+        cub_excl_scan(c, c->keep.as<uint32_t>(), c->newid.as<uint32_t>(), (uint32_t)nv);
+        uint32_t lk = 0, ln = 0;
+        CK(cudaMemcpyAsync(&lk, c->keep.as<uint32_t>() + (nv - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&ln, c->newid.as<uint32_t>() + (nv - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const uint64_t nv_final = (uint64_t)lk + ln;
+        DevBuf nverts, nkeys;
+        nverts.ensure(nv_final * 12 + 16); nkeys.ensure(nv_final * 8 + 16);
+        LAUNCH(c, k_compact_verts, nblk(nv, 256), 256, (uint32_t)nv, c->keep.as<uint32_t>(), c->newid.as<uint32_t>(), verts, keys,
+               nverts.as<float>(), nkeys.as<unsigned long long>());
+        if (nt) LAUNCH(c, k_remap_tris, nblk(nt * 3, 256), 256, nt * 3, c->remap.as<uint32_t>(), c->newid.as<uint32_t>(), tris);
+        CK(cudaMemcpyAsync(verts, nverts.p, nv_final * 12, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(keys, nkeys.p, nv_final * 8, cudaMemcpyDeviceToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        nverts.release(); nkeys.release();
+        *nv_out = nv_final;
+        return SS_OK;
+    } catch (const SsCudaError &err) {
+        cudaGetLastError();
+        return ss_fail(err.e == cudaErrorMemoryAllocation ? SS_ERR_OUT_OF_MEMORY : SS_ERR_CUDA, std::string(err.what) + ": " + cudaGetErrorString(err.e));
+    }
+}
+extern "C" const unsigned long long *ss_surface_device_vertex_keys(const ss_surface *s) { return s ? s->vkeys.as<unsigned long long>() : nullptr; }
+extern "C" int ss_surface_copy_subdomain_owned(const ss_surface *s, uint8_t *dst) {
+    if (!s || !dst) return SS_ERR_INVALID_PARAMETER;
+    for (uint64_t q = 0; q < s->nsub; ++q) dst[q] = s->sub_owned.empty() ? 1 : s->sub_owned[q];
+    return SS_OK;
 }
 
 // ------------------------------------------------------------------ public entry ----

@@ -184,3 +184,16 @@ def test_cuda_dam_break_properties(ss):
     g2 = ss.reconstruct_surface(p, context=ctx, **kw)
     assert np.array_equal(g.mesh.vertices, g2.mesh.vertices) and np.array_equal(g.mesh.triangles, g2.mesh.triangles)
     ctx.close()
+
+
+def test_cuda_multi_gpu_parity():
+    """Two ranks (one per GPU, NCCL): slab partition + halo exchange + mesh gather/weld == oracle, bit for bit."""
+    import subprocess, sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29544", os.path.join(root, "tools", "mgpu_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
