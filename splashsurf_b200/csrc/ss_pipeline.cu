@@ -66,9 +66,19 @@ struct ss_context {
         sub_flat, sub_off, sub_sparse, sub_owned, flags, scan, spos, rho, tab_a, tab_b, rec, ksplit, batch_subs, tiles, vcnt,
         tcnt, vmask, voff, vblk_off, tblk_off, tile_tab, brick_rng, wflag, brick_seen, fix_list, nflag, bkeys_a, bkeys_b, bids_a, bids_b, bcount, remap, keep, newid, err, pairs;
     uint64_t launches = 0;
+    // result buffers handed to surfaces and returned by ss_surface_free (avoids cudaMalloc/cudaFree per frame,
+    // the analogue of the reference's ReconstructionWorkspace, workspace.rs:12-79)
+    DevBuf o_verts, o_tris, o_vkeys, o_rho, o_verts2, o_vkeys2;
+    uint64_t hint_nv = 0, hint_nt = 0, hint_bc = 0;
 };
 
+#include <mutex>
+#include <set>
+static std::mutex g_ctx_mutex;
+static std::set<ss_context *> g_live_contexts;
+
 struct ss_surface {
+    ss_context *owner = nullptr;
     int device = 0;
     uint64_t n_in = 0, n = 0, nv = 0, nt = 0, nsub = 0;
     int used_decomposition = 0;
@@ -177,6 +187,7 @@ extern "C" int ss_context_create(int device, ss_context **out) {
         for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
         CK(cudaMemcpyToSymbol(c_tri_table, SS_MC_TRI_TABLE, sizeof(SS_MC_TRI_TABLE)));
         CK(cudaMemcpyToSymbol(c_num_tris, SS_MC_NUM_TRIS, sizeof(SS_MC_NUM_TRIS)));
+        { std::lock_guard<std::mutex> lk(g_ctx_mutex); g_live_contexts.insert(c); }
         *out = c;
         return SS_OK;
     } catch (const SsCudaError &err) {
@@ -186,13 +197,14 @@ extern "C" int ss_context_create(int device, ss_context **out) {
 
 extern "C" void ss_context_destroy(ss_context *c) {
     if (!c) return;
+    { std::lock_guard<std::mutex> lk(g_ctx_mutex); g_live_contexts.erase(c); }
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = { &c->xyz, &c->xyz_f, &c->filt_flag, &c->filt_flag32, &c->filt_off, &c->aabb, &c->cnt, &c->off, &c->key_a, &c->key_b,
                        &c->val_a, &c->val_b, &c->cid, &c->cub_tmp, &c->sub_flat, &c->sub_off, &c->sub_sparse, &c->sub_owned, &c->flags, &c->scan,
                        &c->spos, &c->rho, &c->tab_a, &c->tab_b, &c->rec, &c->ksplit, &c->batch_subs, &c->tiles, &c->vcnt, &c->tcnt,
                        &c->vmask, &c->voff, &c->vblk_off, &c->tblk_off, &c->tile_tab, &c->brick_rng, &c->wflag, &c->brick_seen, &c->fix_list, &c->nflag, &c->bkeys_a, &c->bkeys_b, &c->bids_a, &c->bids_b, &c->bcount, &c->remap, &c->keep, &c->newid,
-                       &c->err, &c->pairs };
+                       &c->err, &c->pairs, &c->o_verts, &c->o_tris, &c->o_vkeys, &c->o_rho, &c->o_verts2, &c->o_vkeys2 };
     for (DevBuf *b : bufs) b->release();
     for (auto &ev : c->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->stream);
@@ -388,6 +400,9 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
 
     CK(cudaEventRecord(c->ev[2], st));
     out->nv = out->nt = 0; out->nsub = 0;
+    out->owner = c;
+    out->rho = c->o_rho; c->o_rho = DevBuf(); out->verts = c->o_verts; c->o_verts = DevBuf();
+    out->tris = c->o_tris; c->o_tris = DevBuf(); out->vkeys = c->o_vkeys; c->o_vkeys = DevBuf();
     out->rho.ensure(std::max<uint64_t>(n, 1) * 4);
     float *d_rho = out->rho.as<float>();
     CK(cudaMemsetAsync(d_rho, 0, std::max<uint64_t>(n, 1) * 4, st));
@@ -521,9 +536,9 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     }
     std::vector<SsTile> h_tiles(max_tiles);
     uint64_t vtotal = 0, ttotal = 0;
-    size_t bcap = 1 << 16;
+    size_t bcap = std::max<size_t>(1 << 16, c->hint_bc + c->hint_bc / 8);
     c->bkeys_a.ensure(bcap * 8); c->bids_a.ensure(bcap * 4);
-    size_t vcap = 1 << 16, tcap = 1 << 17;
+    size_t vcap = std::max<size_t>(1 << 16, c->hint_nv + c->hint_nv / 8), tcap = std::max<size_t>(1 << 17, c->hint_nt + c->hint_nt / 8);
     out->verts.ensure(vcap * 12); out->vkeys.ensure(vcap * 8); out->tris.ensure(tcap * 12);
     float ls_ms = 0.f, mc_ms = 0.f;
     uint64_t ls_launches = 0, fix_points = 0;
@@ -650,16 +665,18 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
         CK(cudaStreamSynchronize(st));
         nv_final = (uint64_t)lk + ln;
         // compact into fresh buffers (swap)
-        DevBuf nverts, nkeys;
-        nverts.ensure(std::max<uint64_t>(nv_final, 1) * 12); nkeys.ensure(std::max<uint64_t>(nv_final, 1) * 8);
+        DevBuf nverts = c->o_verts2, nkeys = c->o_vkeys2;
+        c->o_verts2 = DevBuf(); c->o_vkeys2 = DevBuf();
+        nverts.ensure(std::max<uint64_t>(vtotal, 1) * 12); nkeys.ensure(std::max<uint64_t>(vtotal, 1) * 8);
         LAUNCH(c, k_compact_verts, nblk(vtotal, 256), 256, (uint32_t)vtotal, c->keep.as<uint32_t>(), c->newid.as<uint32_t>(),
                out->verts.as<float>(), out->vkeys.as<unsigned long long>(), nverts.as<float>(), nkeys.as<unsigned long long>());
         LAUNCH(c, k_remap_tris, nblk(ttotal * 3, 256), 256, ttotal * 3, c->remap.as<uint32_t>(), c->newid.as<uint32_t>(), out->tris.as<uint32_t>());
         CK(cudaStreamSynchronize(st));
-        out->verts.release(); out->vkeys.release();
+        c->o_verts2 = out->verts; c->o_vkeys2 = out->vkeys;     // keep the pre-weld buffers for the next frame
         out->verts = nverts; out->vkeys = nkeys;
     }
     out->nv = nv_final; out->nt = ttotal;
+    c->hint_nv = vtotal; c->hint_nt = ttotal; c->hint_bc = bc;
     CK(cudaEventRecord(c->ev[8], st));
     CK(cudaEventRecord(c->ev[9], st));
     CK(cudaStreamSynchronize(st));
@@ -915,9 +932,22 @@ extern "C" int ss_reconstruct_surface_f32(ss_context *c, const float *xyz, uint6
     }
 }
 
+static void give_back(DevBuf &slot, DevBuf &buf) {
+    if (!buf.p) return;
+    if (!slot.p) { slot = buf; buf.p = nullptr; buf.cap = 0; }
+    else if (slot.cap < buf.cap) { cudaFree(slot.p); slot = buf; buf.p = nullptr; buf.cap = 0; }
+    else buf.release();
+}
 extern "C" void ss_surface_free(ss_surface *s) {
     if (!s) return;
     cudaSetDevice(s->device);
+    {
+        std::lock_guard<std::mutex> lk(g_ctx_mutex);
+        if (s->owner && g_live_contexts.count(s->owner)) {
+            ss_context *c = s->owner;
+            give_back(c->o_verts, s->verts); give_back(c->o_tris, s->tris); give_back(c->o_vkeys, s->vkeys); give_back(c->o_rho, s->rho);
+        }
+    }
     s->verts.release(); s->tris.release(); s->vkeys.release(); s->rho.release();
     delete s;
 }
