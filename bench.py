@@ -144,6 +144,10 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    # stdout hygiene: NCCL / library chatter must not precede the JSON line -> fd 1 points at stderr until the end
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -191,6 +195,7 @@ def main():
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)
     clocks = sampler.stop()
+    sys.stderr.write(f"[rank {rank}] device ms/step {dev_ms / args.steps:.2f}, level-set {ls_ms / args.steps:.2f}, particles processed {res.get('recv_particles', len(p_local))}\n")
     stats = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
@@ -277,7 +282,9 @@ def main():
                     line["cpu_baseline"] = {"value": None, "unit": "Mparticles/s", "cores": os.cpu_count(), "kind": "reference", "sample": "oracle/_ref missing"}
             except Exception as e:   # the baseline must never take the bench line down
                 line["cpu_baseline"] = {"value": None, "unit": "Mparticles/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -37,7 +37,8 @@ enum {
     SS_ERR_INDEX_TOO_SMALL = 4,          /* IndexTypeTooSmall*: a dimension exceeds what the device path indexes */
     SS_ERR_REAL_TOO_SMALL = 5,           /* RealTypeTooSmallDomainSize */
     SS_ERR_INVALID_PARAMETER = 6,        /* reference: assert!/panic on bad radius, support, subdomain size */
-    SS_ERR_UNSUPPORTED = 7,              /* path not provided by this build (e.g. global hash-map path) */
+    SS_ERR_UNSUPPORTED = 7,              /* feature not provided by this build (global_neighborhood_list) */
+    SS_ERR_INVALID_DOMAIN = 8,           /* DensityMapError::InvalidDomain (density_map.rs:48-61) */
     SS_ERR_CUDA = 100,                   /* CUDA runtime failure; see ss_last_error() */
     SS_ERR_NO_DEVICE = 101,              /* no CUDA device: the product never falls back to a CPU path */
     SS_ERR_OUT_OF_MEMORY = 102

@@ -97,9 +97,10 @@ def absolute_params(particle_radius, smoothing_length, cube_size):
 
 def reconstruct(particles, *, particle_radius, smoothing_length, cube_size, rest_density=1000.0,
                 iso_surface_threshold=0.6, aabb_min=None, aabb_max=None, simd=True, subdomain_grid=True,
-                subdomain_grid_auto_disable=True, subdomain_num_cubes_per_dim=64, tile_of_subdomain=None,
+                subdomain_grid_auto_disable=True, subdomain_num_cubes_per_dim=64, multi_threading=True, tile_of_subdomain=None,
                 want_neighbor_counts=False, num_threads=None):
-    """C-oracle counterpart of pysplashsurf.reconstruct_surface (same RELATIVE smoothing_length / cube_size)."""
+    """C-oracle counterpart of pysplashsurf.reconstruct_surface (same RELATIVE smoothing_length / cube_size).
+    `multi_threading` is accepted and ignored: the global path is restated with its sequential (deterministic) semantics."""
     L = lib()
     if num_threads is not None:
         L.so_set_num_threads(int(num_threads))
@@ -127,7 +128,7 @@ def reconstruct(particles, *, particle_radius, smoothing_length, cube_size, rest
         if rc != 0:
             return d
         n = res.n_filtered
-        d["subdomain_grid"] = _grid_dict(res.subdomain_grid)
+        d["subdomain_grid"] = _grid_dict(res.subdomain_grid) if res.used_decomposition else None
         d["particle_densities"] = np.ctypeslib.as_array(res.densities, (n,)).copy() if n else np.zeros(0, np.float32)
         d["particle_inside_aabb"] = (np.ctypeslib.as_array(res.inside_aabb, (len(xyz),)).astype(bool).copy()
                                      if p.has_particle_aabb else None)

@@ -37,7 +37,7 @@ typedef struct {
     int32_t has_particle_aabb;
     float aabb_min[3], aabb_max[3];
     int32_t enable_simd;      /* 1: AVX2-FMA grid loop semantics, 0: scalar grid loop */
-    int32_t decomposition;    /* 1: UniformGrid, 0: None (global path; not restated here) */
+    int32_t decomposition;    /* 1: UniformGrid, 0: None (global path, sequential semantics) */
     uint32_t subdomain_num_cubes_per_dim;
     int32_t auto_disable;
 } so_params;
@@ -559,6 +559,167 @@ static void stitch(so_result *res, so_patch *patches, uint64_t npatch) {
     free(l2g); free(ext);
 }
 
+
+/* ------------------------------------------------- global (non-decomposed) path ---- */
+/* reconstruction.rs:65-194 with enable_multi_threading = false (the deterministic variant; the multi-threaded
+ * variant sums thread-local maps in scheduling order and is not bit-reproducible):
+ *   neighborhood_search_spatial_hashing (neighborhood_search.rs:148-230) over from_aabb(grid.aabb, h),
+ *   sequential_compute_particle_densities (density_map.rs:130-186),
+ *   sequential_generate_sparse_density_map (density_map.rs:370-412, support loop :677-736),
+ *   construct_mc_input + triangulate (marching_cubes/narrow_band_extraction.rs:51-219, triangulation.rs:23-57). */
+static int reconstruct_global(so_result *res, const float *xyz, uint64_t n, const so_params *p, const so_grid *g) {
+    const float h = p->compact_support_radius, c = p->cube_size, thr = p->iso_surface_threshold;
+    float r2 = p->particle_radius + p->particle_radius;
+    const float rest_mass = (r2 * r2 * r2) * p->rest_density;
+    res->densities = (float *)calloc(n ? n : 1, sizeof(float));
+    /* ---- densities on one neighbourhood-search grid over the whole domain */
+    if (n) {
+        so_grid ns;
+        if (grid_from_aabb(&ns, g->aabb_min, g->aabb_max, h) != 0) return 6;
+        int64_t ncell = ns.nc[0] * ns.nc[1] * ns.nc[2];
+        uint64_t *cstart = (uint64_t *)calloc((size_t)ncell + 1, sizeof(uint64_t));
+        int64_t *cell_of = (int64_t *)malloc(sizeof(int64_t) * n);
+        for (uint64_t a = 0; a < n; ++a) {
+            int64_t cc[3];
+            for (int d = 0; d < 3; ++d) { cc[d] = grid_cell_of(&ns, d, xyz[3 * a + d]); if (cc[d] < 0 || cc[d] >= ns.nc[d]) { free(cstart); free(cell_of); return 6; } }
+            cell_of[a] = cc[0] * ns.nc[1] * ns.nc[2] + cc[1] * ns.nc[2] + cc[2];
+            cstart[cell_of[a] + 1]++;
+        }
+        for (int64_t q = 0; q < ncell; ++q) cstart[q + 1] += cstart[q];
+        uint64_t *order = (uint64_t *)malloc(sizeof(uint64_t) * n);
+        uint64_t *cur = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(ncell ? ncell : 1));
+        memcpy(cur, cstart, sizeof(uint64_t) * (size_t)ncell);
+        for (uint64_t a = 0; a < n; ++a) order[cur[cell_of[a]]++] = a;
+        free(cur);
+        k_scalar kern = k_scalar_new(h);
+        float h2 = h * h;
+        for (uint64_t a = 0; a < n; ++a) {
+            const float *pi = xyz + 3 * a;
+            int64_t cc[3];
+            for (int d = 0; d < 3; ++d) cc[d] = grid_cell_of(&ns, d, pi[d]);
+            float rho = k_scalar_eval(&kern, 0.0f);
+            for (int pass = 0; pass < 2; ++pass)
+            for (int sx = -1; sx <= 1; ++sx) for (int sy = -1; sy <= 1; ++sy) for (int sz = -1; sz <= 1; ++sz) {
+                int self = (sx == 0 && sy == 0 && sz == 0);
+                if ((pass == 0) == self) continue;
+                int64_t q[3] = { cc[0] + sx, cc[1] + sy, cc[2] + sz };
+                if (q[0] < 0 || q[1] < 0 || q[2] < 0 || q[0] >= ns.nc[0] || q[1] >= ns.nc[1] || q[2] >= ns.nc[2]) continue;
+                int64_t fc = q[0] * ns.nc[1] * ns.nc[2] + q[1] * ns.nc[2] + q[2];
+                for (uint64_t t = cstart[fc]; t < cstart[fc + 1]; ++t) {
+                    uint64_t b = order[t];
+                    if (b == a) continue;
+                    const float *pj = xyz + 3 * b;
+                    float dx = pj[0] - pi[0], dy = pj[1] - pi[1], dz = pj[2] - pi[2];
+                    float d2 = dx * dx + dy * dy + dz * dz;
+                    if (d2 < h2) rho += k_scalar_eval(&kern, sqrtf(d2));
+                }
+            }
+            res->densities[a] = rho * rest_mass;
+        }
+        free(order); free(cell_of); free(cstart);
+    }
+    /* ---- density map on the dense point array (missing == 0) */
+    float half_real = f_ceil(h / c);
+    int64_t half = (int64_t)half_real, supported = 2 * half + 2;
+    float rev = c * half_real * (1.0f + sqrtf(FLT_EPSILON));
+    float rev2 = rev * rev;
+    float amin[3], amax[3];
+    for (int d = 0; d < 3; ++d) { amin[d] = g->aabb_min[d] - (-rev); amax[d] = g->aabb_max[d] + (-rev); }
+    if ((amin[0] == amax[0] && amin[1] == amax[1] && amin[2] == amax[2]) || !(amin[0] <= amax[0] && amin[1] <= amax[1] && amin[2] <= amax[2])) return 8;
+    const int64_t np0 = g->np[0], np1 = g->np[1], np2 = g->np[2];
+    size_t npts = (size_t)(np0 * np1 * np2);
+    float *phi = (float *)calloc(npts, sizeof(float));
+    k_scalar kern = k_scalar_new(h);
+    for (uint64_t a = 0; a < n; ++a) {
+        const float *pp = xyz + 3 * a;
+        int in = 1;
+        for (int d = 0; d < 3; ++d) if (!(pp[d] >= amin[d] && pp[d] < amax[d])) in = 0;
+        if (!in) continue;
+        float vol = rest_mass / res->densities[a];
+        int64_t imin[3]; float mp[3];
+        for (int d = 0; d < 3; ++d) { imin[d] = grid_cell_of(g, d, pp[d]) - half; mp[d] = grid_coord(g, d, imin[d]); }
+        float dx = mp[0] - pp[0] - c;
+        for (int64_t i = imin[0]; i != imin[0] + supported; ++i) {
+            dx += c; float dxdx = dx * dx;
+            float dy = mp[1] - pp[1] - c;
+            for (int64_t j = imin[1]; j != imin[1] + supported; ++j) {
+                dy += c; float dydy = dy * dy;
+                float dz = mp[2] - pp[2] - c;
+                for (int64_t k = imin[2]; k != imin[2] + supported; ++k) {
+                    dz += c; float dzdz = dz * dz;
+                    float rr = dxdx + dydy + dzdz;
+                    if (rr < rev2) phi[(i * np1 + j) * np2 + k] += vol * k_scalar_eval(&kern, sqrtf(rr));
+                }
+            }
+        }
+    }
+    /* ---- marching cubes input: vertices on edges from a point >= thr to a neighbour < thr */
+    so_patch pt; memset(&pt, 0, sizeof(pt));
+    int64_t *edge_vertex = (int64_t *)malloc(sizeof(int64_t) * 3 * npts);
+    uint8_t *marked = (uint8_t *)calloc(npts, 1);      /* corner flagged Above by the edge loop */
+    for (size_t e = 0; e < 3 * npts; ++e) edge_vertex[e] = -1;
+    static const int NB[6][3] = { {1,0,0},{-1,0,0},{0,1,0},{0,-1,0},{0,0,1},{0,0,-1} };
+    for (int64_t i = 0; i < np0; ++i) for (int64_t j = 0; j < np1; ++j) for (int64_t k = 0; k < np2; ++k) {
+        float vp = phi[(i * np1 + j) * np2 + k];
+        if (vp < thr) continue;
+        for (int q = 0; q < 6; ++q) {
+            int64_t ni = i + NB[q][0], nj = j + NB[q][1], nk = k + NB[q][2];
+            if (ni < 0 || nj < 0 || nk < 0 || ni >= np0 || nj >= np1 || nk >= np2) continue;
+            float vn = phi[(ni * np1 + nj) * np2 + nk];
+            if (!(vn < thr)) continue;
+            float alpha = (thr - vp) / (vn - vp);
+            float one_m = 1.0f - alpha;
+            float pc[3] = { grid_coord(g, 0, i), grid_coord(g, 1, j), grid_coord(g, 2, k) };
+            float nc_[3] = { grid_coord(g, 0, ni), grid_coord(g, 1, nj), grid_coord(g, 2, nk) };
+            float x[3];
+            for (int d = 0; d < 3; ++d) x[d] = pc[d] * one_m + nc_[d] * alpha;
+            int ax = q / 2;
+            int64_t o[3] = { i < ni ? i : ni, j < nj ? j : nj, k < nk ? k : nk };
+            int64_t key[4] = { o[0], o[1], o[2], ax };
+            edge_vertex[((o[0] * np1 + o[1]) * np2 + o[2]) * 3 + ax] = (int64_t)pt.nv;
+            patch_push_v(&pt, x, key, 1);
+            marked[(i * np1 + j) * np2 + k] = 1;
+        }
+    }
+    /* ---- triangulate every cell that touches a crossing edge */
+    int rc = 0;
+    for (int64_t i = 0; i + 1 < np0 && !rc; ++i) for (int64_t j = 0; j + 1 < np1 && !rc; ++j) for (int64_t k = 0; k + 1 < np2 && !rc; ++k) {
+        int any_edge = 0;
+        for (int le = 0; le < 12 && !any_edge; ++le) {
+            int oc = EDGE_CORNER[le], ax = EDGE_AXIS[le];
+            int64_t o[3] = { i + CORNER[oc][0], j + CORNER[oc][1], k + CORNER[oc][2] };
+            if (edge_vertex[((o[0] * np1 + o[1]) * np2 + o[2]) * 3 + ax] >= 0) any_edge = 1;
+        }
+        if (!any_edge) continue;
+        int idx = 0;
+        for (int v = 0; v < 8; ++v) {
+            size_t l = (size_t)(((i + CORNER[v][0]) * np1 + (j + CORNER[v][1])) * np2 + (k + CORNER[v][2]));
+            /* narrow_band_extraction.rs:124-126 (Above set by the edge loop) and :179-184 (value > threshold) */
+            if (marked[l] || phi[l] > thr) idx |= (1 << v);
+        }
+        const int8_t *row = SS_MC_TRI_TABLE[idx];
+        for (int t = 0; t < 5 && row[3 * t] >= 0; ++t) {
+            uint64_t tri[3];
+            for (int m = 0; m < 3; ++m) {
+                int le = row[3 * t + (2 - m)];
+                int oc = EDGE_CORNER[le], ax = EDGE_AXIS[le];
+                int64_t o[3] = { i + CORNER[oc][0], j + CORNER[oc][1], k + CORNER[oc][2] };
+                int64_t vid = edge_vertex[((o[0] * np1 + o[1]) * np2 + o[2]) * 3 + ax];
+                if (vid < 0) { rc = 9; break; }       /* reference: "Missing iso surface vertex" error */
+                tri[m] = (uint64_t)vid;
+            }
+            if (rc) break;
+            patch_push_t(&pt, tri);
+        }
+    }
+    res->nv = pt.nv; res->nt = pt.nt;
+    res->vertices = pt.v ? pt.v : (float *)malloc(4);
+    res->vertex_keys = pt.vkey ? pt.vkey : (int64_t *)malloc(8);
+    res->triangles = pt.t ? pt.t : (uint64_t *)malloc(8);
+    free(pt.vinterior); free(edge_vertex); free(marked); free(phi);
+    return rc;
+}
+
 /* ------------------------------------------------------ thread helper ---- */
 /* The reference parallelises over subdomains with rayon (dense_subdomains.rs:521-526, :1581-1598);
  * here: a pthread pool pulling subdomain indices from an atomic counter. */
@@ -670,7 +831,7 @@ int so_reconstruct(const float *xyz_in, uint64_t n_in, const so_params *p, so_re
         } else use_dec = 1;
     }
     res->used_decomposition = use_dec;
-    if (!use_dec) { free(filtered); return 100; /* global path not restated in this oracle */ }
+    if (!use_dec) { int rcg = reconstruct_global(res, xyz, n, p, &g0); free(filtered); return rcg; }
 
     /* dense_subdomains.rs:89-244 initialize_parameters */
     int64_t S = (int64_t)p->subdomain_num_cubes_per_dim;

@@ -40,6 +40,13 @@ struct SsDev {
     float inv_c;          // 1/c (binning only; not parity relevant)
     float rr_cells;       // R + slack: particles farther than this from the tile are dropped (binning only)
     int simd;             // 1: AVX-path arithmetic for dense subdomains
+    // global (non-decomposed) path, reconstruction.rs:65-194: one neighbourhood-search grid over the whole domain,
+    // incremental stencil distances, narrow-band marching cubes; tiles are only an implementation detail there
+    int gmode;
+    float g_ns_amin[3]; int g_ns_nc[3];        // from_aabb(grid.aabb, h)
+    float g_allow_min[3], g_allow_max[3];      // grid.aabb shrunk by the kernel evaluation radius (density_map.rs:606-610)
+    float rev2;                                // kernel_evaluation_radius^2
+    int sup;                                   // supported points per axis = 2R + 2
     // multi-GPU partition: memberships are kept only for subdomains with keep_lo <= ijk[part_axis] < keep_hi
     int part_axis, keep_lo, keep_hi;
 };

@@ -254,6 +254,55 @@ k_density(SsDev P, uint32_t m, const uint32_t *__restrict__ key, const float4 *_
     rho[__float_as_uint(pi.w)] = __fmul_rn(acc, P.rest_mass);
 }
 
+
+// ---- global path: one neighbourhood-search grid over the whole domain (neighborhood_search.rs:148-230) ----
+__global__ void k_ns_keys_global(SsDev P, const float *__restrict__ xyz, uint32_t n, uint32_t *__restrict__ key, uint32_t *__restrict__ idx,
+                                 int *__restrict__ err) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    int c[3];
+    bool bad = false;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        c[d] = ss_cell_of(xyz[3 * (uint64_t)p + d], P.g_ns_amin[d], P.h);
+        if (c[d] < 0 || c[d] >= P.g_ns_nc[d]) { bad = true; c[d] = 0; }
+    }
+    if (bad) atomicExch(err, 1);
+    key[p] = (uint32_t)((c[0] * P.g_ns_nc[1] + c[1]) * P.g_ns_nc[2] + c[2]);
+    idx[p] = p;
+}
+__global__ void __launch_bounds__(128)
+k_density_global(SsDev P, uint32_t n, const uint32_t *__restrict__ key, const float4 *__restrict__ spos,
+                 const uint32_t *__restrict__ cstart, const uint32_t *__restrict__ cend, float *__restrict__ rho) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int cell = (int)key[e];
+    const int n1 = P.g_ns_nc[1], n2 = P.g_ns_nc[2];
+    const int c0 = cell / (n1 * n2), c1 = (cell / n2) % n1, c2 = cell % n2;
+    const float4 pi = spos[e];
+    float acc = ss_kernel_scalar(P, 0.0f);
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int sx = -1; sx <= 1; ++sx) for (int sy = -1; sy <= 1; ++sy) for (int sz = -1; sz <= 1; ++sz) {
+            bool self = (sx == 0 && sy == 0 && sz == 0);
+            if ((pass == 0) == self) continue;
+            int q0 = c0 + sx, q1 = c1 + sy, q2 = c2 + sz;
+            if (q0 < 0 || q1 < 0 || q2 < 0 || q0 >= P.g_ns_nc[0] || q1 >= n1 || q2 >= n2) continue;
+            uint32_t kk = (uint32_t)((q0 * n1 + q1) * n2 + q2);
+            uint32_t a = cstart[kk];
+            if (a == 0xffffffffu) continue;
+            uint32_t b = cend[kk];
+            for (uint32_t t = a; t < b; ++t) {
+                if (t == e) continue;
+                float4 pj = spos[t];
+                float dx = __fsub_rn(pj.x, pi.x), dy = __fsub_rn(pj.y, pi.y), dz = __fsub_rn(pj.z, pi.z);
+                float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                if (d2 < P.h2) acc = __fadd_rn(acc, ss_kernel_scalar(P, __fsqrt_rn(d2)));
+            }
+        }
+    }
+    rho[__float_as_uint(pi.w)] = __fmul_rn(acc, P.rest_mass);
+}
+
 // ------------------------------------------------------------------ splat binning ----
 // Bins are cubes of `be` cells (8 = one 8x8x8-point brick, unless h/c is large) of the subdomain tile plus a halo.
 // Binning is only a conservative cull: a particle farther than h from every tile point is dropped (key 0xffffffff).
@@ -372,6 +421,40 @@ __device__ __forceinline__ void ss_accumulate(const SsDev &P, const float4 r, co
     }
 }
 
+
+// Global path (density_map.rs:677-736): the delta of stencil point n along an axis is built by n+1 sequential additions
+// of the cell size to (min_supported_point - particle - cell_size); accepted when r^2 < kernel_evaluation_radius^2.
+__device__ __forceinline__ void ss_accumulate_global(const SsDev &P, const float4 r, const int *imin, const float *dx0,
+                                                     const int gi, const int gj, const int gk, float &phi, unsigned &hits) {
+    const int nx = gi - imin[0], ny = gj - imin[1], nz = gk - imin[2];
+    if ((unsigned)nx >= (unsigned)P.sup || (unsigned)ny >= (unsigned)P.sup || (unsigned)nz >= (unsigned)P.sup) return;
+    float dx = dx0[0], dy = dx0[1], dz = dx0[2];
+    for (int t = 0; t <= nx; ++t) dx = __fadd_rn(dx, P.c);
+    for (int t = 0; t <= ny; ++t) dy = __fadd_rn(dy, P.c);
+    for (int t = 0; t <= nz; ++t) dz = __fadd_rn(dz, P.c);
+    const float rr = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    if (rr < P.rev2) {
+        phi = __fadd_rn(phi, __fmul_rn(r.w, ss_kernel_scalar(P, __fsqrt_rn(rr))));
+        ++hits;
+    }
+}
+
+// per candidate: allowed-domain test, first stencil point, start deltas (density_map.rs:645-697)
+__device__ __forceinline__ bool ss_global_candidate(const SsDev &P, const float4 r, int *imin, float *dx0) {
+    const float p[3] = { r.x, r.y, r.z };
+    bool allowed = true;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) allowed = allowed && (p[d] >= P.g_allow_min[d]) && (p[d] < P.g_allow_max[d]);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const int cell = ss_cell_of(p[d], P.gmin[d], P.c);
+        imin[d] = allowed ? cell - P.R : (1 << 30);          // never in range when the particle is skipped
+        const float mp = ss_coord(P.gmin[d], cell - P.R, P.c);
+        dx0[d] = __fsub_rn(__fsub_rn(mp, p[d]), P.c);
+    }
+    return allowed;
+}
+
 // One CTA = one 8x8x8-point brick of one subdomain tile; one warp = a 2x4x4 point box; one lane = one point.
 //
 // Exact value of a point: phi = ordered fold over the subdomain's particles in ascending global index of
@@ -386,7 +469,7 @@ __device__ __forceinline__ void ss_accumulate(const SsDev &P, const float4 r, co
 // and only SS_MARKER is stored.  Otherwise the warp evaluates all its points exactly.  k_fixup_flags then finds
 // marker points that touch an outside point (a surface-crossing edge needs both exact endpoints) and a second
 // launch (SS_LS_FIX) evaluates those warp boxes exactly.
-template <bool COUNT>
+template <bool COUNT, bool GLOBAL>
 __global__ void __launch_bounds__(SS_LS_THREADS, 3)
 k_levelset(SsDev P, SsLsArgs A) {
     __shared__ float4 s_rec[SS_LS_CAP];
@@ -395,6 +478,9 @@ k_levelset(SsDev P, SsLsArgs A) {
     __shared__ unsigned short s_list[SS_LS_WARPS][SS_LS_CAP];
     __shared__ uint32_t s_rng[2][128];          // candidate runs (start, length)
     __shared__ uint32_t s_pre[129];
+    // global path only: per candidate the first stencil point index and the start value of the incremental deltas
+    __shared__ int s_imin[GLOBAL ? SS_LS_CAP : 1][3];
+    __shared__ float s_dx0[GLOBAL ? SS_LS_CAP : 1][3];
 
     const int nb = P.nb;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -416,7 +502,7 @@ k_levelset(SsDev P, SsLsArgs A) {
 
     const SsTile T = A.tile_tab[tile_idx];
     const uint32_t s = T.s;
-    const bool sparse = T.sparse != 0;
+    const bool sparse = GLOBAL || T.sparse != 0;
 
     // ---- candidate runs: bins overlapping [8b - R, 8b + 7 + R) per axis; z-ranges are contiguous in key order
     const int2 rx = A.brick_rng[bx], ry = A.brick_rng[by], rz = A.brick_rng[bz];
@@ -467,7 +553,7 @@ k_levelset(SsDev P, SsLsArgs A) {
     const float bxl = fmaf((float)(T.gbase[0] + i0), P.c, P.gmin[0]), bxh = fmaf((float)(T.gbase[0] + i1), P.c, P.gmin[0]);
     const float byl = fmaf((float)(T.gbase[1] + j0), P.c, P.gmin[1]), byh = fmaf((float)(T.gbase[1] + j1), P.c, P.gmin[1]);
     const float bzl = fmaf((float)(T.gbase[2] + k0), P.c, P.gmin[2]), bzh = fmaf((float)(T.gbase[2] + k1), P.c, P.gmin[2]);
-    const float cull2 = (sparse ? P.h2m : P.h2) * 1.0001f;
+    const float cull2 = (GLOBAL ? P.rev2 : (sparse ? P.h2m : P.h2)) * 1.0001f;
     const size_t out_idx = (size_t)tile_idx * P.np * P.np * P.np + ((size_t)i * P.np + j) * P.np + k;
 
     float phi = 0.0f;
@@ -493,7 +579,8 @@ k_levelset(SsDev P, SsLsArgs A) {
             uint32_t src = (uint32_t)(best & 0xffffffffu);
             float4 r = A.rec[src];
             int ks = A.ksplit[src];
-            if (sparse) ss_accumulate<true, false>(P, r, ks, k, gx, gy, gz, phi, hits);
+            if (GLOBAL) { int im[3]; float d0[3]; ss_global_candidate(P, r, im, d0); ss_accumulate_global(P, r, im, d0, gi, gj, gk, phi, hits); }
+            else if (sparse) ss_accumulate<true, false>(P, r, ks, k, gx, gy, gz, phi, hits);
             else ss_accumulate<false, false>(P, r, ks, k, gx, gy, gz, phi, hits);
         }
         if (valid) A.tiles[out_idx] = phi;
@@ -505,7 +592,9 @@ k_levelset(SsDev P, SsLsArgs A) {
         const uint32_t a = s_rng[0][r], len = s_rng[1][r], dst = s_pre[r];
         for (uint32_t t = lane; t < len; t += 32) {
             const uint32_t src = a + t;
-            s_rec[dst + t] = A.rec[src]; s_ks[dst + t] = A.ksplit[src];
+            float4 rc = A.rec[src];
+            if (GLOBAL && !ss_global_candidate(P, rc, s_imin[dst + t], s_dx0[dst + t])) rc.w = 0.0f;   // skipped particle: no volume
+            s_rec[dst + t] = rc; s_ks[dst + t] = A.ksplit[src];
             s_key[dst + t] = ((unsigned long long)A.pidx[src] << 32) | (dst + t);
         }
     }
@@ -591,7 +680,12 @@ k_levelset(SsDev P, SsLsArgs A) {
         __syncwarp();
     }
     // ---- ordered accumulation
-    if (sparse) {
+    if (GLOBAL) {
+        for (int n = 0; n < nlist; ++n) {
+            const int slot = s_list[warp][n];
+            ss_accumulate_global(P, s_rec[slot], s_imin[slot], s_dx0[slot], gi, gj, gk, phi, hits);
+        }
+    } else if (sparse) {
         for (int n = 0; n < nlist; ++n) {
             const int slot = s_list[warp][n];
             ss_accumulate<true, false>(P, s_rec[slot], 0, k, gx, gy, gz, phi, hits);
@@ -674,21 +768,46 @@ k_fixup_flags(SsDev P, const float *__restrict__ tiles, uint8_t *__restrict__ wf
 }
 
 // ------------------------------------------------------------------ marching cubes ----
-__device__ __forceinline__ int ss_case_index(const float *__restrict__ phi, int l, int np, float thr) {
-    int idx = (phi[l] > thr) ? 1 : 0;                      // corner 0 (0,0,0)   uniform_grid.rs:822-831
-    idx |= (phi[l + np * np] > thr) ? 2 : 0;               // corner 1 (1,0,0)
-    idx |= (phi[l + np * np + np] > thr) ? 4 : 0;          // corner 2 (1,1,0)
-    idx |= (phi[l + np] > thr) ? 8 : 0;                    // corner 3 (0,1,0)
-    idx |= (phi[l + 1] > thr) ? 16 : 0;                    // corner 4 (0,0,1)
-    idx |= (phi[l + np * np + 1] > thr) ? 32 : 0;          // corner 5 (1,0,1)
-    idx |= (phi[l + np * np + np + 1] > thr) ? 64 : 0;     // corner 6 (1,1,1)
-    idx |= (phi[l + np + 1] > thr) ? 128 : 0;              // corner 7 (0,1,1)
+// "Above" flag of a grid point.  Subdomain path: value > threshold (dense_subdomains.rs:1482).  Global path: a point with
+// value >= threshold that has a neighbour below it is marked Above by the edge loop, every other point by value > threshold
+// (narrow_band_extraction.rs:79-126, :179-184) -- the two differ only for value == threshold (neighbours inside the tile).
+template <bool GLOBAL>
+__device__ __forceinline__ bool ss_above(const float *__restrict__ phi, int l, int i, int j, int k, int np, float thr) {
+    const float v = phi[l];
+    if (v > thr) return true;
+    if (!GLOBAL || v != thr) return false;
+    bool below = false;
+    if (i > 0) below |= phi[l - np * np] < thr;
+    if (i + 1 < np) below |= phi[l + np * np] < thr;
+    if (j > 0) below |= phi[l - np] < thr;
+    if (j + 1 < np) below |= phi[l + np] < thr;
+    if (k > 0) below |= phi[l - 1] < thr;
+    if (k + 1 < np) below |= phi[l + 1] < thr;
+    return below;
+}
+template <bool GLOBAL>
+__device__ __forceinline__ int ss_case_index(const float *__restrict__ phi, int l, int i, int j, int k, int np, float thr) {
+    int idx = ss_above<GLOBAL>(phi, l, i, j, k, np, thr) ? 1 : 0;                                   // corner 0 (0,0,0)
+    idx |= ss_above<GLOBAL>(phi, l + np * np, i + 1, j, k, np, thr) ? 2 : 0;                        // corner 1 (1,0,0)
+    idx |= ss_above<GLOBAL>(phi, l + np * np + np, i + 1, j + 1, k, np, thr) ? 4 : 0;               // corner 2 (1,1,0)
+    idx |= ss_above<GLOBAL>(phi, l + np, i, j + 1, k, np, thr) ? 8 : 0;                             // corner 3 (0,1,0)
+    idx |= ss_above<GLOBAL>(phi, l + 1, i, j, k + 1, np, thr) ? 16 : 0;                             // corner 4 (0,0,1)
+    idx |= ss_above<GLOBAL>(phi, l + np * np + 1, i + 1, j, k + 1, np, thr) ? 32 : 0;               // corner 5 (1,0,1)
+    idx |= ss_above<GLOBAL>(phi, l + np * np + np + 1, i + 1, j + 1, k + 1, np, thr) ? 64 : 0;      // corner 6 (1,1,1)
+    idx |= ss_above<GLOBAL>(phi, l + np + 1, i, j + 1, k + 1, np, thr) ? 128 : 0;                   // corner 7 (0,1,1)
     return idx;
+}
+// does the edge between two grid values carry a vertex?
+template <bool GLOBAL>
+__device__ __forceinline__ bool ss_crossing(float a, float b, float thr) {
+    return GLOBAL ? ((a >= thr) != (b >= thr))           // one end >= threshold, the other < (narrow_band_extraction.rs:79-102)
+                  : ((a > thr) != (b > thr));            // endpoints on different sides (dense_subdomains.rs:1482)
 }
 
 // Pass 1: per tile point, which of its +x/+y/+z edges carry a vertex (endpoints on different sides of the
 // threshold; `value > threshold` == inside, dense_subdomains.rs:1482) and how many triangles its cell emits;
 // per block of 256 points the totals.
+template <bool GLOBAL>
 __global__ void __launch_bounds__(SS_TP_THREADS)
 k_mc_count(SsDev P, const float *__restrict__ tiles, uint8_t *__restrict__ vmask, uint32_t *__restrict__ vblk, uint32_t *__restrict__ tblk) {
     int tile, i, j, k, l;
@@ -698,12 +817,12 @@ k_mc_count(SsDev P, const float *__restrict__ tiles, uint8_t *__restrict__ vmask
     if (ok) {
         const float *phi = tiles + (size_t)tile * np * np * np;
         const float thr = P.thr;
-        const bool in0 = phi[l] > thr;
-        if (i + 1 < np && ((phi[l + np * np] > thr) != in0)) mask |= 1u;
-        if (j + 1 < np && ((phi[l + np] > thr) != in0)) mask |= 2u;
-        if (k + 1 < np && ((phi[l + 1] > thr) != in0)) mask |= 4u;
+        const float v0 = phi[l];
+        if (i + 1 < np && ss_crossing<GLOBAL>(v0, phi[l + np * np], thr)) mask |= 1u;
+        if (j + 1 < np && ss_crossing<GLOBAL>(v0, phi[l + np], thr)) mask |= 2u;
+        if (k + 1 < np && ss_crossing<GLOBAL>(v0, phi[l + 1], thr)) mask |= 4u;
         vmask[(size_t)tile * np * np * np + l] = (uint8_t)mask;
-        if (i < P.S && j < P.S && k < P.S) nt = c_num_tris[ss_case_index(phi, l, np, thr)];
+        if (i < P.S && j < P.S && k < P.S) nt = c_num_tris[ss_case_index<GLOBAL>(phi, l, i, j, k, np, thr)];
     }
     uint32_t packed = (nt << 16) | __popc(mask);            // <= 256*5 and 256*3: no overflow between halves
     for (int o = 16; o > 0; o >>= 1) packed += __shfl_xor_sync(0xffffffffu, packed, o);
@@ -731,6 +850,7 @@ struct SsMcOut {
 
 // Pass 2: vertices on the edges owned by each point (dense_subdomains.rs:1498-1538); records the id of each
 // point's first vertex in voff.
+template <bool GLOBAL>
 __global__ void __launch_bounds__(SS_TP_THREADS)
 k_mc_verts(SsDev P, const float *__restrict__ tiles, const uint8_t *__restrict__ vmask, const uint32_t *__restrict__ vblk_off,
            const uint32_t *__restrict__ vblk, uint32_t *__restrict__ voff, const SsTile *__restrict__ tile_tab, SsMcOut O) {
@@ -759,13 +879,29 @@ k_mc_verts(SsDev P, const float *__restrict__ tiles, const uint8_t *__restrict__
         if (!(mask & (1u << ax))) continue;
         const int stride = ax == 0 ? np * np : (ax == 1 ? np : 1);
         const float bval = phi[l + stride];
-        const float alpha = __fdiv_rn(__fsub_rn(thr, a), __fsub_rn(bval, a));      // dense_subdomains.rs:1516-1519
-        const float one_m = __fsub_rn(1.0f, alpha);
         float pos[3];
+        if (!GLOBAL) {
+            const float alpha = __fdiv_rn(__fsub_rn(thr, a), __fsub_rn(bval, a));      // dense_subdomains.rs:1516-1519
+            const float one_m = __fsub_rn(1.0f, alpha);
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            const float tc = (d == ax) ? ss_coord(T.smin[d], o[d] + 1, P.c) : oc[d];
-            pos[d] = __fadd_rn(__fmul_rn(oc[d], one_m), __fmul_rn(tc, alpha));
+            for (int d = 0; d < 3; ++d) {
+                const float tc = (d == ax) ? ss_coord(T.smin[d], o[d] + 1, P.c) : oc[d];
+                pos[d] = __fadd_rn(__fmul_rn(oc[d], one_m), __fmul_rn(tc, alpha));
+            }
+        } else {
+            // narrow_band_extraction.rs:104-109: interpolate from the point >= threshold towards its neighbour below,
+            // coordinates from the global grid
+            const bool from_o = a >= thr;
+            const float vp = from_o ? a : bval, vn = from_o ? bval : a;
+            const float alpha = __fdiv_rn(__fsub_rn(thr, vp), __fsub_rn(vn, vp));
+            const float one_m = __fsub_rn(1.0f, alpha);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const float c0 = ss_coord(P.gmin[d], T.gbase[d] + o[d], P.c);
+                const float c1 = (d == ax) ? ss_coord(P.gmin[d], T.gbase[d] + o[d] + 1, P.c) : c0;
+                const float pc = from_o ? c0 : c1, nc = from_o ? c1 : c0;
+                pos[d] = __fadd_rn(__fmul_rn(pc, one_m), __fmul_rn(nc, alpha));
+            }
         }
         O.verts[3 * (size_t)vid] = pos[0]; O.verts[3 * (size_t)vid + 1] = pos[1]; O.verts[3 * (size_t)vid + 2] = pos[2];
         const unsigned long long key = ss_edge_key(T.gbase[0] + i, T.gbase[1] + j, T.gbase[2] + k, ax);
@@ -783,6 +919,7 @@ k_mc_verts(SsDev P, const float *__restrict__ tiles, const uint8_t *__restrict__
 }
 
 // Pass 3: triangles of the cell whose origin is each point (dense_subdomains.rs:1470-1552)
+template <bool GLOBAL>
 __global__ void __launch_bounds__(SS_TP_THREADS)
 k_mc_tris(SsDev P, const float *__restrict__ tiles, const uint8_t *__restrict__ vmask, const uint32_t *__restrict__ tblk_off,
           const uint32_t *__restrict__ tblk, const uint32_t *__restrict__ voff, SsMcOut O) {
@@ -793,7 +930,7 @@ k_mc_tris(SsDev P, const float *__restrict__ tiles, const uint8_t *__restrict__ 
     const int np = P.np;
     const float *phi = tiles + (size_t)tile * np * np * np;
     int idx = 0, nt = 0;
-    if (ok && i < P.S && j < P.S && k < P.S) { idx = ss_case_index(phi, l, np, P.thr); nt = c_num_tris[idx]; }
+    if (ok && i < P.S && j < P.S && k < P.S) { idx = ss_case_index<GLOBAL>(phi, l, i, j, k, np, P.thr); nt = c_num_tris[idx]; }
     uint32_t total;
     const uint32_t pre = ss_block_excl_scan((uint32_t)nt, total);
     if (!nt) return;

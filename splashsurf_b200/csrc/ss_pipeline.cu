@@ -63,7 +63,7 @@ struct ss_context {
     int count_pairs = 0;             // 1: count in-support evaluations (work model; slower)
     // reusable scratch
     DevBuf xyz, xyz_f, filt_flag, filt_flag32, filt_off, aabb, cnt, off, key_a, key_b, val_a, val_b, cid, cub_tmp,
-        sub_flat, sub_off, sub_sparse, sub_owned, flags, scan, spos, rho, tab_a, tab_b, rec, ksplit, batch_subs, tiles, vcnt,
+        sub_flat, sub_off, sub_sparse, sub_owned, gkey_a, gkey_b, gval_a, gval_b, flags, scan, spos, rho, tab_a, tab_b, rec, ksplit, batch_subs, tiles, vcnt,
         tcnt, vmask, voff, vblk_off, tblk_off, tile_tab, brick_rng, wflag, brick_seen, fix_list, nflag, bkeys_a, bkeys_b, bids_a, bids_b, bcount, remap, keep, newid, err, pairs;
     uint64_t launches = 0;
     // result buffers handed to surfaces and returned by ss_surface_free (avoids cudaMalloc/cudaFree per frame,
@@ -201,7 +201,7 @@ extern "C" void ss_context_destroy(ss_context *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = { &c->xyz, &c->xyz_f, &c->filt_flag, &c->filt_flag32, &c->filt_off, &c->aabb, &c->cnt, &c->off, &c->key_a, &c->key_b,
-                       &c->val_a, &c->val_b, &c->cid, &c->cub_tmp, &c->sub_flat, &c->sub_off, &c->sub_sparse, &c->sub_owned, &c->flags, &c->scan,
+                       &c->val_a, &c->val_b, &c->cid, &c->cub_tmp, &c->sub_flat, &c->sub_off, &c->sub_sparse, &c->sub_owned, &c->gkey_a, &c->gkey_b, &c->gval_a, &c->gval_b, &c->flags, &c->scan,
                        &c->spos, &c->rho, &c->tab_a, &c->tab_b, &c->rec, &c->ksplit, &c->batch_subs, &c->tiles, &c->vcnt, &c->tcnt,
                        &c->vmask, &c->voff, &c->vblk_off, &c->tblk_off, &c->tile_tab, &c->brick_rng, &c->wflag, &c->brick_seen, &c->fix_list, &c->nflag, &c->bkeys_a, &c->bkeys_b, &c->bids_a, &c->bids_b, &c->bcount, &c->remap, &c->keep, &c->newid,
                        &c->err, &c->pairs, &c->o_verts, &c->o_tris, &c->o_vkeys, &c->o_rho, &c->o_verts2, &c->o_vkeys2 };
@@ -317,6 +317,19 @@ extern "C" int ss_grid_for_reconstruction_f32(ss_context *c, const float *xyz, u
     }
 }
 
+
+// ------------------------------------------------------------------ templated launch helpers ----
+static void launch_levelset(ss_context *c, dim3 grid, const SsDev &D, const SsLsArgs &A, bool count, bool global) {
+    if (global) {
+        if (count) k_levelset<true, true><<<grid, SS_LS_THREADS, 0, c->stream>>>(D, A);
+        else k_levelset<false, true><<<grid, SS_LS_THREADS, 0, c->stream>>>(D, A);
+    } else {
+        if (count) k_levelset<true, false><<<grid, SS_LS_THREADS, 0, c->stream>>>(D, A);
+        else k_levelset<false, false><<<grid, SS_LS_THREADS, 0, c->stream>>>(D, A);
+    }
+    c->launches++;
+}
+
 // kernel.rs:327-336 (AVX-path constants) and :61-66 (scalar normalisation), evaluated in f32 like the reference
 static void fill_kernel_consts(SsDev &D, float h) {
     D.a_hinv = fdivr(1.0f, h);
@@ -349,17 +362,20 @@ struct Partition {
     int stop_after_decomposition = 0;   // only report the local maximum (out->max_particles)
 };
 
-static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params_f32 *p, ss_surface *out, const Partition &part = Partition()) {
+static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params_f32 *p, ss_surface *out, const Partition &part = Partition(),
+                              bool global_mode = false) {
     const uint64_t n = PP.n;
     const float *d_xyz = PP.d_xyz;
     cudaStream_t st = c->stream;
 
     // ---- initialize_parameters, dense_subdomains.rs:89-244
-    const int64_t S = (int64_t)p->subdomain_num_cubes_per_dim;
+    // global path (reconstruction.rs:65-194): tiles of 64 cells are an implementation detail, the arithmetic is global
+    const int64_t S = global_mode ? 64 : (int64_t)p->subdomain_num_cubes_per_dim;
     const float h = p->compact_support_radius, cs = p->cube_size;
     const float r2 = faddr(p->particle_radius, p->particle_radius);
     const float rest_mass = fmulr(fmulr(fmulr(r2, r2), r2), p->rest_density);
-    const float margin = fmulr(fmulr(ceilf(fdivr(h, cs)), cs), 1.01f);
+    const float margin = global_mode ? fmulr(cs, ceilf(fdivr(h, cs)) + 2.0f)      // stencil reach (R + 1 cells) + slack
+                                     : fmulr(fmulr(ceilf(fdivr(h, cs)), cs), 1.01f);
     int64_t nsd[3], ncg[3];
     for (int d = 0; d < 3; ++d) { nsd[d] = (PP.grid.nc[d] + S - 1) / S; ncg[d] = nsd[d] * S; }
     HostGrid gg, sg;
@@ -368,7 +384,7 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     const float sub_size = fmulr(cs, (float)S);
     rc = grid_new(sg, gg.mn, nsd, sub_size);
     if (rc) return ss_fail(rc, "subdomain grid construction failed");
-    out->grid = gg; out->subgrid = sg; out->S = (int)S;
+    out->grid = global_mode ? PP.grid : gg; out->subgrid = sg; out->S = (int)S;
 
     for (int d = 0; d < 3; ++d) {
         if (gg.np[d] >= (1 << 20)) return ss_fail(SS_ERR_INDEX_TOO_SMALL, "more than 2^20 grid points per dimension are not supported by the device path");
@@ -389,6 +405,23 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     D.ns_stride = D.nsD * D.nsD * D.nsD;
     fill_bins(D, cs);
     D.simd = p->enable_simd ? 1 : 0;
+    D.gmode = global_mode ? 1 : 0;
+    uint64_t g_ns_cells = 0;
+    if (global_mode) {
+        HostGrid ns;
+        int rcn = grid_from_aabb(ns, PP.grid.mn, PP.grid.mx, h);                       // neighborhood_search.rs:172-173
+        if (rcn) return ss_fail(SS_ERR_INVALID_PARAMETER, "failed to construct grid for neighborhood search");
+        for (int d = 0; d < 3; ++d) { D.g_ns_amin[d] = ns.mn[d]; D.g_ns_nc[d] = (int)ns.nc[d]; }
+        g_ns_cells = (uint64_t)ns.nc[0] * ns.nc[1] * ns.nc[2];
+        if (g_ns_cells >= (1ull << 28)) return ss_fail(SS_ERR_INDEX_TOO_SMALL, "domain too large for the global (non-decomposed) path");
+        const float half_real = ceilf(fdivr(h, cs));
+        const float rev = fmulr(fmulr(cs, half_real), faddr(1.0f, sqrtf(FLT_EPSILON)));   // density_map.rs:575-576
+        D.rev2 = fmulr(rev, rev); D.sup = 2 * D.R + 2;
+        for (int d = 0; d < 3; ++d) { D.g_allow_min[d] = fsubr(PP.grid.mn[d], -rev); D.g_allow_max[d] = faddr(PP.grid.mx[d], -rev); }
+        bool degen = D.g_allow_min[0] == D.g_allow_max[0] && D.g_allow_min[1] == D.g_allow_max[1] && D.g_allow_min[2] == D.g_allow_max[2];
+        bool cons = D.g_allow_min[0] <= D.g_allow_max[0] && D.g_allow_min[1] <= D.g_allow_max[1] && D.g_allow_min[2] <= D.g_allow_max[2];
+        if (degen || !cons) return ss_fail(SS_ERR_INVALID_DOMAIN, "the allowed domain of particles is inconsistent/degenerate (DensityMapError::InvalidDomain)");
+    }
     D.part_axis = part.enabled ? part.axis : 0;
     D.keep_lo = part.enabled ? (int)std::max<int64_t>(part.own_lo - part.halo, 0) : 0;
     D.keep_hi = part.enabled ? (int)std::min<int64_t>(part.own_hi + part.halo, nsd[D.part_axis]) : (int)nsd[0];
@@ -450,7 +483,7 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     owned_list.reserve(nsub);
     for (uint32_t s = 0; s < nsub; ++s) {
         out->sub_flat[s] = h_flat[s]; out->sub_count[s] = h_off[s + 1] - h_off[s];
-        out->sub_sparse[s] = (out->sub_count[s] <= sparse_limit) ? 1 : 0;
+        out->sub_sparse[s] = (!global_mode && out->sub_count[s] <= sparse_limit) ? 1 : 0;
         if (part.enabled) {
             const int64_t f = h_flat[s];
             int64_t ijk[3];
@@ -473,6 +506,7 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     CK(cudaMemsetAsync(c->err.p, 0, 4, st));
     // membership arrays: cid (compressed subdomain), val_b (particle); keys -> key_a, sorted -> key_b? key_b is in use
     // (flat ids are no longer needed after cid): reuse key_b as sort output, val_a as sorted payload.
+    if (!global_mode) {
     LAUNCH(c, k_ns_keys, nblk(M, 256), 256, D, d_xyz, M, c->cid.as<uint32_t>(), c->sub_flat.as<uint32_t>(), c->val_b.as<uint32_t>(),
            c->key_a.as<uint32_t>(), c->err.as<int>());
     const uint64_t ns_keys = (uint64_t)nsub * D.ns_stride;
@@ -485,6 +519,21 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     LAUNCH(c, k_gather_pos, nblk(M, 256), 256, d_xyz, c->val_a.as<uint32_t>(), M, c->spos.as<float4>());
     LAUNCH(c, k_density, nblk(M, 128), 128, D, M, c->key_b.as<uint32_t>(), c->spos.as<float4>(), c->sub_flat.as<uint32_t>(),
            c->tab_a.as<uint32_t>(), c->tab_b.as<uint32_t>(), d_rho);
+    } else {
+        // one cell list over the whole domain; particles (not memberships) are the entries
+        const uint32_t n32 = (uint32_t)n;
+        c->gkey_a.ensure((size_t)n32 * 4); c->gkey_b.ensure((size_t)n32 * 4); c->gval_a.ensure((size_t)n32 * 4); c->gval_b.ensure((size_t)n32 * 4);
+        LAUNCH(c, k_ns_keys_global, nblk(n32, 256), 256, D, d_xyz, n32, c->gkey_a.as<uint32_t>(), c->gval_a.as<uint32_t>(), c->err.as<int>());
+        cub_sort_pairs(c, c->gkey_a.as<uint32_t>(), c->gkey_b.as<uint32_t>(), c->gval_a.as<uint32_t>(), c->gval_b.as<uint32_t>(), n32, bits_for(g_ns_cells));
+        c->tab_a.ensure(g_ns_cells * 4); c->tab_b.ensure(g_ns_cells * 4);
+        CK(cudaMemsetAsync(c->tab_a.p, 0xff, g_ns_cells * 4, st));
+        LAUNCH(c, k_mark_starts, nblk(n32, 256), 256, c->gkey_b.as<uint32_t>(), n32, c->tab_a.as<uint32_t>(), (uint32_t)g_ns_cells);
+        LAUNCH(c, k_run_counts, nblk(n32, 256), 256, c->gkey_b.as<uint32_t>(), n32, c->tab_b.as<uint32_t>(), (uint32_t)g_ns_cells);
+        c->spos.ensure((size_t)n32 * 16);
+        LAUNCH(c, k_gather_pos, nblk(n32, 256), 256, d_xyz, c->gval_b.as<uint32_t>(), n32, c->spos.as<float4>());
+        LAUNCH(c, k_density_global, nblk(n32, 128), 128, D, n32, c->gkey_b.as<uint32_t>(), c->spos.as<float4>(), c->tab_a.as<uint32_t>(),
+               c->tab_b.as<uint32_t>(), d_rho);
+    }
     CK(cudaEventRecord(c->ev[4], st));
 
     // ---- splat binning: (subdomain, 8^3-point brick) bins + particle records
@@ -566,8 +615,7 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
         A.mode = exact_all ? SS_LS_EXACT_ALL : SS_LS_CERTIFY;
         A.wflag = nullptr; A.fix_bricks = nullptr;
         const dim3 ls_grid((unsigned)D.nb, (unsigned)D.nb, (unsigned)D.nb * nbatch);
-        if (c->count_pairs) LAUNCH(c, k_levelset<true>, ls_grid, SS_LS_THREADS, D, A);
-        else LAUNCH(c, k_levelset<false>, ls_grid, SS_LS_THREADS, D, A);
+        launch_levelset(c, ls_grid, D, A, c->count_pairs != 0, global_mode);
         ++ls_launches;
         const dim3 tp_grid((unsigned)(nbatch * D.np), planes_y);
         if (!exact_all) {
@@ -584,8 +632,7 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
             CK(cudaStreamSynchronize(st));
             if (nfl[0]) {
                 A.mode = SS_LS_FIX; A.wflag = c->wflag.as<uint8_t>(); A.fix_bricks = c->fix_list.as<uint32_t>();
-                if (c->count_pairs) LAUNCH(c, k_levelset<true>, nfl[0], SS_LS_THREADS, D, A);
-                else LAUNCH(c, k_levelset<false>, nfl[0], SS_LS_THREADS, D, A);
+                launch_levelset(c, dim3(nfl[0]), D, A, c->count_pairs != 0, global_mode);
                 ++ls_launches;
                 fix_points += nfl[1];
             }
@@ -601,7 +648,8 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
         }
         // marching cubes: count per block, scan the block totals, emit vertices, emit triangles
         const uint32_t nblocks = nbatch * (uint32_t)D.np * planes_y;
-        LAUNCH(c, k_mc_count, tp_grid, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->vcnt.as<uint32_t>(), c->tcnt.as<uint32_t>());
+        if (global_mode) LAUNCH(c, k_mc_count<true>, tp_grid, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->vcnt.as<uint32_t>(), c->tcnt.as<uint32_t>());
+        else LAUNCH(c, k_mc_count<false>, tp_grid, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->vcnt.as<uint32_t>(), c->tcnt.as<uint32_t>());
         cub_excl_scan(c, c->vcnt.as<uint32_t>(), c->vblk_off.as<uint32_t>(), nblocks);
         cub_excl_scan(c, c->tcnt.as<uint32_t>(), c->tblk_off.as<uint32_t>(), nblocks);
         uint32_t lastv[2] = { 0, 0 }, lastt[2] = { 0, 0 };
@@ -625,10 +673,17 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
             O.verts = out->verts.as<float>(); O.tris = out->tris.as<uint32_t>(); O.vkeys = out->vkeys.as<unsigned long long>();
             O.bkeys = c->bkeys_a.as<unsigned long long>(); O.bids = c->bids_a.as<uint32_t>(); O.bcount = c->bcount.as<uint32_t>();
             O.vbase = (uint32_t)vtotal; O.tbase = (uint32_t)ttotal; O.bcap = (uint32_t)std::min<size_t>((size_t)bc + bv, 0xffffffffu);
-            LAUNCH(c, k_mc_verts, tp_grid, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->vblk_off.as<uint32_t>(),
-                   c->vcnt.as<uint32_t>(), c->voff.as<uint32_t>(), c->tile_tab.as<SsTile>(), O);
-            LAUNCH(c, k_mc_tris, tp_grid, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->tblk_off.as<uint32_t>(),
-                   c->tcnt.as<uint32_t>(), c->voff.as<uint32_t>(), O);
+            if (global_mode) {
+                LAUNCH(c, k_mc_verts<true>, tp_grid, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->vblk_off.as<uint32_t>(),
+                       c->vcnt.as<uint32_t>(), c->voff.as<uint32_t>(), c->tile_tab.as<SsTile>(), O);
+                LAUNCH(c, k_mc_tris<true>, tp_grid, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->tblk_off.as<uint32_t>(),
+                       c->tcnt.as<uint32_t>(), c->voff.as<uint32_t>(), O);
+            } else {
+                LAUNCH(c, k_mc_verts<false>, tp_grid, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->vblk_off.as<uint32_t>(),
+                       c->vcnt.as<uint32_t>(), c->voff.as<uint32_t>(), c->tile_tab.as<SsTile>(), O);
+                LAUNCH(c, k_mc_tris<false>, tp_grid, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->tblk_off.as<uint32_t>(),
+                       c->tcnt.as<uint32_t>(), c->voff.as<uint32_t>(), O);
+            }
             vtotal += bv; ttotal += bt;
         }
         CK(cudaEventRecord(c->ev[6], st));
@@ -765,7 +820,7 @@ extern "C" int ss_levelset_tile_f32(ss_context *c, const float *xyz, const float
             A.ksplit = c->ksplit.as<int>(); A.pidx = c->val_a.as<uint32_t>();
             A.tile_tab = c->tile_tab.as<SsTile>(); A.brick_rng = c->brick_rng.as<int2>(); A.tiles = c->tiles.as<float>();
             A.pairs = nullptr; A.wflag = nullptr; A.fix_bricks = nullptr; A.mode = SS_LS_EXACT_ALL;
-            LAUNCH(c, k_levelset<false>, dim3((unsigned)D.nb, (unsigned)D.nb, (unsigned)D.nb), SS_LS_THREADS, D, A);
+            launch_levelset(c, dim3((unsigned)D.nb, (unsigned)D.nb, (unsigned)D.nb), D, A, false, false);
             CK(cudaStreamSynchronize(st));
         }
         CK(cudaMemcpyAsync(tile_out, c->tiles.p, np3 * 4, cudaMemcpyDefault, st));
@@ -906,12 +961,7 @@ extern "C" int ss_reconstruct_surface_f32(ss_context *c, const float *xyz, uint6
             } else use_dec = 1;
         }
         s->used_decomposition = use_dec;
-        if (!use_dec) {
-            ss_surface_free(s);
-            return ss_fail(SS_ERR_UNSUPPORTED, "global (non-decomposed) reconstruction path is not provided by this build; "
-                                               "use spatial_decomposition=1 with auto_disable=0");
-        }
-        rc = run_subdomain_grid(c, P, p, s);
+        rc = run_subdomain_grid(c, P, p, s, Partition(), /*global_mode=*/!use_dec);
         if (rc) { ss_surface_free(s); return rc; }
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); s->tm.upload = ms;

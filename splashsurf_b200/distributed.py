@@ -21,6 +21,10 @@ import torch
 import torch.distributed as dist
 
 
+# fixed cost of one occupied subdomain tile in the slab balance, in "particle equivalents" (measured: a 64^3-cell tile of
+# bulk fluid holds 4096 particles; a nearly empty tile still costs about as much level-set + marching-cubes time)
+TILE_COST_PARTICLES = 4096.0
+
 # ---------------------------------------------------------------------------- partition plan (pure host logic) ----
 @dataclass
 class SlabPlan:
@@ -198,7 +202,17 @@ class Runner:
         layer = owner_layer(xd[:, ax], float(grid.aabb_min[ax]), sub_size)
         hist = torch.bincount(layer.clamp(0, plan0.nsub_axis - 1), minlength=plan0.nsub_axis).to(torch.float64)
         dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=self.group)
-        plan = make_plan(list(grid.cells_per_dim), S, p.cube_size, p.compact_support_radius, hist.cpu().numpy(), world, axis=ax)
+        # work model per layer: particles + a fixed cost per occupied subdomain tile (every tile pays for its 729 bricks and
+        # 65^3 grid points even when it only holds a thin sheet of fluid)
+        nsd = [(int(nc) + S - 1) // S for nc in grid.cells_per_dim]
+        o = [owner_layer(xd[:, d], float(grid.aabb_min[d]), sub_size).clamp(0, nsd[d] - 1) for d in range(3)]
+        occ = torch.zeros(nsd[0] * nsd[1] * nsd[2], dtype=torch.int32, device=self.device)
+        occ[(o[0] * nsd[1] + o[1]) * nsd[2] + o[2]] = 1
+        dist.all_reduce(occ, op=dist.ReduceOp.MAX, group=self.group)
+        other = tuple(d for d in range(3) if d != ax)
+        tiles = occ.view(nsd[0], nsd[1], nsd[2]).sum(dim=other).to(torch.float64)
+        work = hist + TILE_COST_PARTICLES * tiles
+        plan = make_plan(list(grid.cells_per_dim), S, p.cube_size, p.compact_support_radius, work.cpu().numpy(), world, axis=ax)
         self.last_plan = plan
         # 3. halo exchange (variable all-to-all over NCCL); keeps ascending global particle order
         recv, counts = exchange_particles(xd, layer, plan, world, self.group)

@@ -40,4 +40,5 @@ def ss():
     return splashsurf_b200
 
 
-MESH_CASES = ["cfg1_ref", "cube16_ref", "cube16_scalar_ref", "splash_small_ref", "splash_aabb_ref"]
+MESH_CASES = ["cfg1_ref", "cube16_ref", "cube16_scalar_ref", "splash_small_ref", "splash_aabb_ref", "global_cube_ref",
+              "global_autodisable_ref"]

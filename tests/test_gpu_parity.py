@@ -42,6 +42,9 @@ SEEDED = [
     ("splash_l22", lambda syn: syn.splash((22, 22, 22), 6, 0.025, 106), dict(particle_radius=0.025, smoothing_length=2.2, cube_size=1.1, subdomain_num_cubes_per_dim=24)),
     ("splash_c025", lambda syn: syn.splash((10, 10, 10), 3, 0.025, 107), dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.25)),
     ("dam_small", lambda syn: syn.dam_break_scaled(120_000, 0.01, 108), dict(particle_radius=0.01, smoothing_length=2.0, cube_size=0.5)),
+    ("global_nodec", lambda syn: syn.splash((14, 14, 14), 4, 0.025, 112), dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.75, subdomain_grid=False)),
+    ("global_auto", lambda syn: syn.jittered_cube(8, 0.025, 113), dict(particle_radius=0.025, smoothing_length=2.0, cube_size=1.0)),
+    ("global_big", lambda syn: syn.jittered_cube(30, 0.025, 114), dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.5, subdomain_grid=False)),
     ("thr03", lambda syn: syn.jittered_cube(20, 0.025, 109), dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.5, iso_surface_threshold=0.3, rest_density=850.0)),
 ]
 
@@ -56,8 +59,11 @@ def test_cuda_bit_exact_vs_oracle(ss, oracle_mod, name, gen, kw):
         ctx.set_levelset_exact_everywhere(exact_everywhere)
         g = ss.reconstruct_surface(p, with_debug=True, context=ctx, **kw)
         ctx.close()
-        assert np.array_equal(g.subdomains["flat"], o["subdomain_flat"]) and np.array_equal(g.subdomains["count"], o["subdomain_count"])
-        assert np.array_equal(g.subdomains["sparse"], o["subdomain_sparse"])
+        if o["used_decomposition"]:
+            assert np.array_equal(g.subdomains["flat"], o["subdomain_flat"]) and np.array_equal(g.subdomains["count"], o["subdomain_count"])
+            assert np.array_equal(g.subdomains["sparse"], o["subdomain_sparse"])
+        else:
+            assert g.subdomain_grid is None and g.grid.ncells_per_dim == o["grid"]["ncells"].tolist()
         assert np.array_equal(g.particle_densities, o["particle_densities"])
         m = _parity(oracle_mod, g, o, kw.get("subdomain_num_cubes_per_dim", 64))
         assert m["keys_equal"] and m["triangles_equal"] and m["n_not_bitexact"] == 0, (exact_everywhere, m)

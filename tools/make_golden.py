@@ -42,6 +42,11 @@ def main():
     ref_case("splash_small_ref", syn.splash((20, 20, 20), 5, 0.025, 23), particle_radius=0.025, smoothing_length=2.0, cube_size=0.6)
     ref_case("splash_aabb_ref", syn.splash((20, 20, 20), 5, 0.025, 24), particle_radius=0.025, smoothing_length=2.0, cube_size=0.6,
              aabb_min=[-0.05, -0.05, -0.05], aabb_max=[0.7, 1.8, 0.7], subdomain_num_cubes_per_dim=32)
+    # global (non-decomposed) path, sequential (deterministic) variant of the reference
+    ref_case("global_cube_ref", syn.jittered_cube(12, 0.025, 41), particle_radius=0.025, smoothing_length=2.0, cube_size=0.5,
+             subdomain_grid=False, multi_threading=False)
+    ref_case("global_autodisable_ref", syn.splash((9, 9, 9), 2, 0.025, 44), particle_radius=0.025, smoothing_length=2.0, cube_size=0.9,
+             multi_threading=False)
     # single-particle cases of the reference's own tests (tests/integration_tests/test_subdomains.rs:80-105,
     # test_simple.rs:99-126): counts only
     singles = {}
