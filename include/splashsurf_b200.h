@@ -188,6 +188,14 @@ int ss_context_set_tile_batch(ss_context *ctx, uint32_t max_tiles);
 int ss_context_set_levelset_exact_everywhere(ss_context *ctx, int on);
 int ss_context_set_count_pairs(ss_context *ctx, int on);
 
+/* ---- SPH normals at the mesh vertices: SphInterpolator::interpolate_normals (sph_interpolation.rs:82-133) as used by the
+ * pipeline's `--sph-normals` (splashsurf/src/reconstruct.rs:1126-1129, :1287-1294): particle volume = (4/3 pi r^3 rho0) /
+ * rho_j, cubic-spline gradient, normalised.  Enable on the context before reconstructing; the unit normals (nv x 3 f32)
+ * are then part of the result.  Parity with the reference is to rounding (its summation follows R-tree order). */
+int ss_context_set_compute_sph_normals(ss_context *ctx, int on);
+int ss_surface_copy_normals(const ss_surface *s, float *dst_xyz);
+const float *ss_surface_device_normals(const ss_surface *s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,6 +77,7 @@ def lib():
         L.so_kernel_scalar.argtypes = [C.c_float, C.c_float]
         L.so_kernel_avx.restype = C.c_float
         L.so_kernel_avx.argtypes = [C.c_float, C.c_float]
+        L.so_sph_normals.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_float, C.c_float, C.c_void_p, C.c_uint64, C.c_void_p]
         L.so_num_threads.restype = C.c_int
         L.so_set_num_threads.argtypes = [C.c_int]
         _LIB = L
@@ -160,6 +161,25 @@ def levelset_tile(xyz, rho, *, global_min, cube_size, subdomain_ijk, subdomain_c
                        C.c_float(float(cube_size)), sijk.ctypes.data, S, smin.ctypes.data, C.c_float(float(h)),
                        C.c_float(float(rest_mass)), int(mode))
     return phi
+
+
+def sph_rest_mass(particle_radius, rest_density=1000.0):
+    """Sphere rest mass used by the pipeline's SPH interpolator (splashsurf/src/reconstruct.rs:1126-1129), f32."""
+    r = np.float32(particle_radius)
+    vol = np.float32(np.float32(4.0) * np.float32(np.pi / 3.0)) * np.float32(r * r * r)
+    return np.float32(vol * np.float32(rest_density))
+
+
+def sph_normals(particles, densities, points, *, compact_support_radius, particle_rest_mass):
+    """SphInterpolator.interpolate_normals restated (summation order differs from the reference's R-tree order)."""
+    L = lib()
+    xyz = np.ascontiguousarray(particles, dtype=np.float32).reshape(-1, 3)
+    rho = np.ascontiguousarray(densities, dtype=np.float32)
+    pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)
+    out = np.empty_like(pts)
+    L.so_sph_normals(xyz.ctypes.data, rho.ctypes.data, len(xyz), C.c_float(float(np.float32(compact_support_radius))),
+                     C.c_float(float(np.float32(particle_rest_mass))), pts.ctypes.data, len(pts), out.ctypes.data)
+    return out
 
 
 def num_threads() -> int:

@@ -894,6 +894,62 @@ void so_levelset_tile(float *phi, const float *xyz, const float *rho, uint64_t n
     free(mem);
 }
 
+/* SPH normals at arbitrary points: sph_interpolation.rs:82-133 (+ kernel.rs:109-141 gradient norm).  The reference visits
+ * neighbours in R-tree traversal order, which is not restated; the summation order here is cell order, so parity with the
+ * reference binary is to rounding (tests use 2e-5 absolute on the unit vectors). */
+static inline float k_scalar_dq(float q) {
+    if (q < 1.0f) return (3.0f / (4.0f * SO_PI_F)) * (-4.0f * q + 3.0f * q * q);
+    else if (q < 2.0f) { float x = 2.0f - q; return -(3.0f / (4.0f * SO_PI_F)) * x * x; }
+    return 0.0f;
+}
+void so_sph_normals(const float *xyz, const float *rho, uint64_t n, float h, float rest_mass, const float *pts, uint64_t npts, float *out) {
+    if (!npts) return;
+    float mn[3] = { 1e30f, 1e30f, 1e30f }, mx[3] = { -1e30f, -1e30f, -1e30f };
+    for (uint64_t a = 0; a < n; ++a) for (int d = 0; d < 3; ++d) { float v = xyz[3 * a + d]; if (v < mn[d]) mn[d] = v; if (v > mx[d]) mx[d] = v; }
+    int64_t nc[3];
+    for (int d = 0; d < 3; ++d) { nc[d] = n ? (int64_t)((mx[d] - mn[d]) / h) + 1 : 1; }
+    int64_t ncell = nc[0] * nc[1] * nc[2];
+    uint64_t *cstart = (uint64_t *)calloc((size_t)ncell + 1, sizeof(uint64_t));
+    int64_t *cell_of = (int64_t *)malloc(sizeof(int64_t) * (n ? n : 1));
+    for (uint64_t a = 0; a < n; ++a) {
+        int64_t c[3];
+        for (int d = 0; d < 3; ++d) { c[d] = (int64_t)((xyz[3 * a + d] - mn[d]) / h); if (c[d] >= nc[d]) c[d] = nc[d] - 1; if (c[d] < 0) c[d] = 0; }
+        cell_of[a] = (c[0] * nc[1] + c[1]) * nc[2] + c[2]; cstart[cell_of[a] + 1]++;
+    }
+    for (int64_t q = 0; q < ncell; ++q) cstart[q + 1] += cstart[q];
+    uint64_t *order = (uint64_t *)malloc(sizeof(uint64_t) * (n ? n : 1));
+    uint64_t *cur = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)ncell);
+    memcpy(cur, cstart, sizeof(uint64_t) * (size_t)ncell);
+    for (uint64_t a = 0; a < n; ++a) order[cur[cell_of[a]]++] = a;
+    free(cur);
+    k_scalar kern = k_scalar_new(h);
+    float h2 = h * h, dqdr = (1.0f + 1.0f) / h;
+    for (uint64_t v = 0; v < npts; ++v) {
+        const float *x = pts + 3 * v;
+        float g[3] = { 0.0f, 0.0f, 0.0f };
+        int64_t c[3];
+        for (int d = 0; d < 3; ++d) c[d] = (int64_t)floorf((x[d] - mn[d]) / h);
+        for (int64_t i = c[0] - 1; i <= c[0] + 1; ++i) for (int64_t j = c[1] - 1; j <= c[1] + 1; ++j) for (int64_t k = c[2] - 1; k <= c[2] + 1; ++k) {
+            if (i < 0 || j < 0 || k < 0 || i >= nc[0] || j >= nc[1] || k >= nc[2]) continue;
+            int64_t fc = (i * nc[1] + j) * nc[2] + k;
+            for (uint64_t t = cstart[fc]; t < cstart[fc + 1]; ++t) {
+                uint64_t b = order[t];
+                float dx = xyz[3 * b] - x[0], dy = xyz[3 * b + 1] - x[1], dz = xyz[3 * b + 2] - x[2];
+                float d2 = dx * dx + dy * dy + dz * dz;
+                if (!(d2 <= h2)) continue;
+                float r = sqrtf(d2);
+                float q = (r + r) / kern.h;
+                float gn = kern.sigma * k_scalar_dq(q) * dqdr;
+                float vol = rest_mass / rho[b];
+                g[0] += (dx / r) * gn * vol; g[1] += (dy / r) * gn * vol; g[2] += (dz / r) * gn * vol;
+            }
+        }
+        float nrm = sqrtf(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+        out[3 * v] = g[0] / nrm; out[3 * v + 1] = g[1] / nrm; out[3 * v + 2] = g[2] / nrm;
+    }
+    free(order); free(cell_of); free(cstart);
+}
+
 /* scalar + AVX-lane kernels exposed for the kernel unit tests (kernel.rs:143-180, :381-481) */
 float so_kernel_scalar(float h, float r) { k_scalar k = k_scalar_new(h); return k_scalar_eval(&k, r); }
 float so_kernel_avx(float h, float r) { k_avx k = k_avx_new(h); return k_avx_eval(&k, r); }

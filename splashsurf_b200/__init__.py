@@ -20,7 +20,7 @@ import numpy as np
 
 from . import build as _build
 
-__all__ = ["reconstruct_surface", "density_grid_loop", "Context", "SurfaceReconstruction", "TriMesh3d", "UniformGrid", "Aabb3d",
+__all__ = ["reconstruct_surface", "reconstruction_pipeline", "MeshWithData", "density_grid_loop", "Context", "SurfaceReconstruction", "TriMesh3d", "UniformGrid", "Aabb3d",
            "SplashsurfError", "library_path", "load_library"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -103,6 +103,10 @@ def load_library():
     L.ss_context_set_tile_batch.argtypes = [vp, C.c_uint32]
     L.ss_context_set_levelset_exact_everywhere.argtypes = [vp, C.c_int]
     L.ss_context_set_count_pairs.argtypes = [vp, C.c_int]
+    L.ss_context_set_compute_sph_normals.argtypes = [vp, C.c_int]
+    L.ss_surface_copy_normals.argtypes = [vp, vp]
+    L.ss_surface_device_normals.argtypes = [vp]
+    L.ss_surface_device_normals.restype = vp
     L.ss_levelset_tile_f32.argtypes = [vp, vp, vp, u64, vp, C.c_float, vp, C.c_uint32, C.c_float, C.c_float, C.c_int, vp]
     L.ss_reconstruct_partition_f32.argtypes = [vp, vp, u64, C.POINTER(_Params), C.POINTER(_Grid), C.c_int, i64, i64, i64, u64, C.c_int, C.POINTER(vp)]
     L.ss_surface_max_subdomain_particles.argtypes = [vp]
@@ -173,6 +177,7 @@ class SurfaceReconstruction:
     vertex_edge_keys: Optional[np.ndarray] = None
     subdomains: Optional[dict] = None
     levelset_tile: Optional[np.ndarray] = None
+    normals: Optional[np.ndarray] = None       # (V, 3) unit SPH normals when requested
 
 
 # ---------------------------------------------------------------------------- context ----
@@ -261,7 +266,7 @@ def reconstruct_surface(particles, *, particle_radius: float, rest_density: floa
                         multi_threading: bool = True, simd: bool = True, global_neighborhood_list: bool = False,
                         subdomain_grid: bool = True, subdomain_grid_auto_disable: bool = True,
                         subdomain_num_cubes_per_dim: int = 64, context: Optional[Context] = None,
-                        keep_levelset_tile_of: Optional[int] = None, with_debug: bool = False) -> SurfaceReconstruction:
+                        keep_levelset_tile_of: Optional[int] = None, with_debug: bool = False, sph_normals: bool = False) -> SurfaceReconstruction:
     """Performs a surface reconstruction from the given particles (no post-processing) on the GPU.
 
     Same signature and semantics as ``pysplashsurf.reconstruct_surface``; ``particles`` is an (N, 3) float32
@@ -282,10 +287,18 @@ def reconstruct_surface(particles, *, particle_radius: float, rest_density: floa
                     subdomain_grid=subdomain_grid, subdomain_grid_auto_disable=subdomain_grid_auto_disable,
                     subdomain_num_cubes_per_dim=subdomain_num_cubes_per_dim)
     _check(L, L.ss_context_keep_levelset_tile(ctx._h, -1 if keep_levelset_tile_of is None else int(keep_levelset_tile_of)))
+    _check(L, L.ss_context_set_compute_sph_normals(ctx._h, int(bool(sph_normals))))
     s = ctx.reconstruct_raw(arr.ctypes.data, len(arr), p)
     try:
-        return _collect(ctx, s, len(arr), p, with_debug or keep_levelset_tile_of is not None, keep_levelset_tile_of is not None)
+        res = _collect(ctx, s, len(arr), p, with_debug or keep_levelset_tile_of is not None, keep_levelset_tile_of is not None)
+        if sph_normals:
+            nrm = np.empty((res.mesh.nvertices, 3), dtype=np.float32)
+            if len(nrm):
+                _check(L, L.ss_surface_copy_normals(s, nrm.ctypes.data))
+            res.normals = nrm
+        return res
     finally:
+        _check(L, L.ss_context_set_compute_sph_normals(ctx._h, 0))
         ctx.free_surface(s)
 
 
@@ -350,3 +363,42 @@ def density_grid_loop(subdomain_particles, subdomain_particle_densities, *, glob
                                      C.c_float(float(np.float32(compact_support_radius))),
                                      C.c_float(float(np.float32(particle_rest_mass))), 0 if simd else 1, out.ctypes.data))
     return out
+
+
+@dataclass
+class MeshWithData:
+    """Mirrors pysplashsurf.MeshWithData for the attributes this package can produce."""
+    mesh: TriMesh3d
+    point_attributes: dict
+    cell_attributes: dict
+
+    @property
+    def nvertices(self) -> int:
+        return self.mesh.nvertices
+
+    @property
+    def ncells(self) -> int:
+        return self.mesh.ncells
+
+
+def reconstruction_pipeline(particles, *, attributes_to_interpolate=None, particle_radius: float, rest_density: float = 1000.0,
+                            smoothing_length: float, cube_size: float, iso_surface_threshold: float = 0.6, aabb_min=None, aabb_max=None,
+                            multi_threading: bool = True, simd: bool = True, subdomain_grid: bool = True,
+                            subdomain_grid_auto_disable: bool = True, subdomain_num_cubes_per_dim: int = 64,
+                            compute_normals: bool = False, sph_normals: bool = False, context: Optional[Context] = None, **post):
+    """The hot-path subset of ``pysplashsurf.reconstruction_pipeline`` (pysplashsurf/src/pipeline.rs:109-200): surface
+    reconstruction plus SPH normals (``compute_normals=True, sph_normals=True``).  Every other post-processing switch of the
+    reference pipeline (cleanup, decimation, smoothing, quads, attribute interpolation, area-weighted normals) is outside the
+    device path and raises NotImplementedError when enabled."""
+    enabled = [k for k, v in post.items() if v not in (False, None, 0) and k not in ("mesh_smoothing_weights", "mesh_smoothing_weights_normalization",
+                                                                                       "quad_max_edge_diag_ratio", "quad_max_normal_angle",
+                                                                                       "quad_max_interior_angle", "mesh_aabb_clamp_vertices", "max_iter")]
+    if enabled or attributes_to_interpolate or (compute_normals and not sph_normals):
+        raise NotImplementedError(f"post-processing not provided by the device path: {enabled or 'attributes / mesh normals'}")
+    rec = reconstruct_surface(particles, particle_radius=particle_radius, rest_density=rest_density, smoothing_length=smoothing_length,
+                              cube_size=cube_size, iso_surface_threshold=iso_surface_threshold, aabb_min=aabb_min, aabb_max=aabb_max,
+                              multi_threading=multi_threading, simd=simd, subdomain_grid=subdomain_grid,
+                              subdomain_grid_auto_disable=subdomain_grid_auto_disable, subdomain_num_cubes_per_dim=subdomain_num_cubes_per_dim,
+                              context=context, sph_normals=bool(compute_normals and sph_normals))
+    attrs = {"normals": rec.normals} if rec.normals is not None else {}
+    return MeshWithData(rec.mesh, attrs, {}), rec

@@ -949,6 +949,81 @@ k_mc_tris(SsDev P, const float *__restrict__ tiles, const uint8_t *__restrict__ 
     }
 }
 
+
+// ------------------------------------------------------------------ SPH normals at the mesh vertices ----
+// SphInterpolator::interpolate_normals (sph_interpolation.rs:82-133): n_i = normalize(sum_j V_j (x_j - x_i)/r * |grad W|(r))
+// over particles with |x_j - x_i|^2 <= h^2, V_j = m_sphere / rho_j.  One thread per vertex; candidates are the bins of the
+// tile the vertex lies in (every particle within h of a tile point is a member of that tile's subdomain).  The reference
+// sums in R-tree traversal order; here: bin order (parity to rounding, not bit-exact).
+struct SsNrmArgs {
+    const float *verts; const unsigned long long *vkeys; uint32_t nv;
+    const uint32_t *sub_flat; const uint8_t *sub_owned; uint32_t nsub;
+    const uint32_t *bin_start, *bin_end; const float4 *rec; const uint32_t *pidx; const float *rho;
+    const int2 *brick_rng; float sphere_mass; float *normals;
+};
+__device__ __forceinline__ float ss_kernel_dq(const SsDev &P, float q) {          // kernel.rs:83-94, constant 3/(4 pi)
+    const float k = __fdiv_rn(3.0f, __fmul_rn(4.0f, SS_PI_F));
+    if (q < 1.0f) return __fmul_rn(k, __fadd_rn(__fmul_rn(-4.0f, q), __fmul_rn(__fmul_rn(3.0f, q), q)));
+    else if (q < 2.0f) { const float x = __fsub_rn(2.0f, q); return __fmul_rn(__fmul_rn(-k, x), x); }
+    return 0.0f;
+}
+__global__ void __launch_bounds__(128)
+k_sph_normals(SsDev P, SsNrmArgs A) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= A.nv) return;
+    const unsigned long long key = A.vkeys[v];
+    const int g[3] = { (int)((key >> 42) & 0xfffff), (int)((key >> 22) & 0xfffff), (int)((key >> 2) & 0xfffff) };
+    const float xi = A.verts[3 * (size_t)v], yi = A.verts[3 * (size_t)v + 1], zi = A.verts[3 * (size_t)v + 2];
+    // find an active tile that contains the vertex' grid edge
+    int t[3], found = -1;
+    for (int combo = 0; combo < 8 && found < 0; ++combo) {
+        bool ok = true;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            int td = min(g[d] / P.S, P.nsd[d] - 1);
+            if (combo & (1 << d)) { if (g[d] % P.S == 0 && td > 0) td -= 1; else ok = false; }
+            t[d] = td;
+        }
+        if (!ok) continue;
+        const uint32_t flat = (uint32_t)((t[0] * P.nsd[1] + t[1]) * P.nsd[2] + t[2]);
+        uint32_t lo = 0, hi = A.nsub;
+        while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (A.sub_flat[mid] < flat) lo = mid + 1; else hi = mid; }
+        if (lo < A.nsub && A.sub_flat[lo] == flat && (!A.sub_owned || A.sub_owned[lo])) found = (int)lo;
+    }
+    float gx = 0.0f, gy = 0.0f, gz = 0.0f;
+    if (found >= 0) {
+        const float dqdr = __fdiv_rn(2.0f, P.h);
+        int2 rng[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { const int lp = g[d] - t[d] * P.S; rng[d] = A.brick_rng[min(lp >> 3, P.nb - 1)]; }
+        const uint32_t base = (uint32_t)found * (uint32_t)P.nbin_sub;
+        for (int X = rng[0].x; X <= rng[0].y; ++X) for (int Y = rng[1].x; Y <= rng[1].y; ++Y) {
+            uint32_t a = 0xffffffffu, b = 0;
+            const uint32_t row = base + (uint32_t)((X * P.nbin + Y) * P.nbin);
+            for (int Z = rng[2].x; Z <= rng[2].y; ++Z) {
+                const uint32_t st = A.bin_start[row + Z];
+                if (st != 0xffffffffu) { if (a == 0xffffffffu) a = st; b = A.bin_end[row + Z]; }
+            }
+            if (a == 0xffffffffu) continue;
+            for (uint32_t e = a; e < b; ++e) {
+                const float4 r = A.rec[e];
+                const float dx = __fsub_rn(r.x, xi), dy = __fsub_rn(r.y, yi), dz = __fsub_rn(r.z, zi);
+                const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                if (!(d2 <= P.h2)) continue;
+                const float rr = __fsqrt_rn(d2);
+                const float q = __fdiv_rn(__fadd_rn(rr, rr), P.h);
+                const float gn = __fmul_rn(__fmul_rn(P.s_sigma, ss_kernel_dq(P, q)), dqdr);
+                const float vol = __fdiv_rn(A.sphere_mass, A.rho[A.pidx[e]]);
+                gx = __fadd_rn(gx, __fmul_rn(__fmul_rn(__fdiv_rn(dx, rr), gn), vol));
+                gy = __fadd_rn(gy, __fmul_rn(__fmul_rn(__fdiv_rn(dy, rr), gn), vol));
+                gz = __fadd_rn(gz, __fmul_rn(__fmul_rn(__fdiv_rn(dz, rr), gn), vol));
+            }
+        }
+    }
+    const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz)));
+    A.normals[3 * (size_t)v] = __fdiv_rn(gx, nrm); A.normals[3 * (size_t)v + 1] = __fdiv_rn(gy, nrm); A.normals[3 * (size_t)v + 2] = __fdiv_rn(gz, nrm);
+}
+
 // ------------------------------------------------------------------ stitching (weld) ----
 // Sorted boundary list (key, provisional id): duplicates of a key map to the smallest id of the run.
 __global__ void k_weld_runs(const unsigned long long *__restrict__ bkeys, const uint32_t *__restrict__ bids, uint32_t nb,

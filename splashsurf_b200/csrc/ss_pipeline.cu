@@ -61,6 +61,7 @@ struct ss_context {
     int64_t keep_tile_flat = -1;
     int ls_exact_all = 0;            // 1: evaluate every grid point exactly (no certification)
     int count_pairs = 0;             // 1: count in-support evaluations (work model; slower)
+    int sph_normals = 0;             // 1: SPH normals at the mesh vertices (sph_interpolation.rs:82-133)
     // reusable scratch
     DevBuf xyz, xyz_f, filt_flag, filt_flag32, filt_off, aabb, cnt, off, key_a, key_b, val_a, val_b, cid, cub_tmp,
         sub_flat, sub_off, sub_sparse, sub_owned, gkey_a, gkey_b, gval_a, gval_b, flags, scan, spos, rho, tab_a, tab_b, rec, ksplit, batch_subs, tiles, vcnt,
@@ -68,7 +69,7 @@ struct ss_context {
     uint64_t launches = 0;
     // result buffers handed to surfaces and returned by ss_surface_free (avoids cudaMalloc/cudaFree per frame,
     // the analogue of the reference's ReconstructionWorkspace, workspace.rs:12-79)
-    DevBuf o_verts, o_tris, o_vkeys, o_rho, o_verts2, o_vkeys2;
+    DevBuf o_verts, o_tris, o_vkeys, o_rho, o_verts2, o_vkeys2, o_normals;
     uint64_t hint_nv = 0, hint_nt = 0, hint_bc = 0;
 };
 
@@ -84,7 +85,8 @@ struct ss_surface {
     int used_decomposition = 0;
     HostGrid grid{}, subgrid{};
     int S = 0;
-    DevBuf verts, tris, vkeys, rho;
+    DevBuf verts, tris, vkeys, rho, normals;
+    int has_normals = 0;
     std::vector<uint8_t> inside_aabb;
     std::vector<int64_t> sub_flat; std::vector<uint64_t> sub_count; std::vector<uint8_t> sub_sparse, sub_owned;
     uint64_t max_particles = 0;
@@ -204,7 +206,7 @@ extern "C" void ss_context_destroy(ss_context *c) {
                        &c->val_a, &c->val_b, &c->cid, &c->cub_tmp, &c->sub_flat, &c->sub_off, &c->sub_sparse, &c->sub_owned, &c->gkey_a, &c->gkey_b, &c->gval_a, &c->gval_b, &c->flags, &c->scan,
                        &c->spos, &c->rho, &c->tab_a, &c->tab_b, &c->rec, &c->ksplit, &c->batch_subs, &c->tiles, &c->vcnt, &c->tcnt,
                        &c->vmask, &c->voff, &c->vblk_off, &c->tblk_off, &c->tile_tab, &c->brick_rng, &c->wflag, &c->brick_seen, &c->fix_list, &c->nflag, &c->bkeys_a, &c->bkeys_b, &c->bids_a, &c->bids_b, &c->bcount, &c->remap, &c->keep, &c->newid,
-                       &c->err, &c->pairs, &c->o_verts, &c->o_tris, &c->o_vkeys, &c->o_rho, &c->o_verts2, &c->o_vkeys2 };
+                       &c->err, &c->pairs, &c->o_verts, &c->o_tris, &c->o_vkeys, &c->o_rho, &c->o_verts2, &c->o_vkeys2, &c->o_normals };
     for (DevBuf *b : bufs) b->release();
     for (auto &ev : c->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->stream);
@@ -214,6 +216,15 @@ extern "C" void ss_context_destroy(ss_context *c) {
 extern "C" int ss_context_keep_levelset_tile(ss_context *c, int64_t flat) { if (!c) return SS_ERR_INVALID_PARAMETER; c->keep_tile_flat = flat; return SS_OK; }
 extern "C" int ss_context_set_tile_batch(ss_context *c, uint32_t m) { if (!c) return SS_ERR_INVALID_PARAMETER; c->max_tiles = m; return SS_OK; }
 extern "C" int ss_context_set_levelset_exact_everywhere(ss_context *c, int on) { if (!c) return SS_ERR_INVALID_PARAMETER; c->ls_exact_all = on ? 1 : 0; return SS_OK; }
+extern "C" int ss_context_set_compute_sph_normals(ss_context *c, int on) { if (!c) return SS_ERR_INVALID_PARAMETER; c->sph_normals = on ? 1 : 0; return SS_OK; }
+extern "C" int ss_surface_copy_normals(const ss_surface *s, float *dst) {
+    if (!s || !dst) return SS_ERR_INVALID_PARAMETER;
+    if (!s->has_normals) return ss_fail(SS_ERR_INVALID_PARAMETER, "normals were not computed (ss_context_set_compute_sph_normals)");
+    cudaSetDevice(s->device);
+    cudaError_t e = cudaMemcpy(dst, s->normals.p, s->nv * 12, cudaMemcpyDeviceToHost);
+    return e == cudaSuccess ? SS_OK : ss_fail(SS_ERR_CUDA, cudaGetErrorString(e));
+}
+extern "C" const float *ss_surface_device_normals(const ss_surface *s) { return (s && s->has_normals) ? s->normals.as<float>() : nullptr; }
 extern "C" int ss_context_set_count_pairs(ss_context *c, int on) { if (!c) return SS_ERR_INVALID_PARAMETER; c->count_pairs = on ? 1 : 0; return SS_OK; }
 
 // ------------------------------------------------------------------ stage: input, filter, AABB, grid ----
@@ -732,6 +743,23 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     }
     out->nv = nv_final; out->nt = ttotal;
     c->hint_nv = vtotal; c->hint_nt = ttotal; c->hint_bc = bc;
+    if (c->sph_normals && nv_final) {
+        // SPH normals at the vertices (pipeline post-processing step, splashsurf/src/reconstruct.rs:1287-1294); sphere rest mass
+        // 4/3 pi r^3 rho0 as in reconstruct.rs:1126-1129
+        out->normals = c->o_normals; c->o_normals = DevBuf();
+        out->normals.ensure(nv_final * 12);
+        SsNrmArgs NA{};
+        NA.verts = out->verts.as<float>(); NA.vkeys = out->vkeys.as<unsigned long long>(); NA.nv = (uint32_t)nv_final;
+        NA.sub_flat = c->sub_flat.as<uint32_t>(); NA.sub_owned = part.enabled ? c->sub_owned.as<uint8_t>() : nullptr; NA.nsub = nsub;
+        NA.bin_start = c->tab_a.as<uint32_t>(); NA.bin_end = c->tab_b.as<uint32_t>(); NA.rec = c->rec.as<float4>(); NA.pidx = c->val_a.as<uint32_t>();
+        NA.rho = d_rho; NA.brick_rng = c->brick_rng.as<int2>();
+        const float r3 = fmulr(fmulr(p->particle_radius, p->particle_radius), p->particle_radius);
+        const float frac_pi_3 = 1.04719755119659774615f;
+        NA.sphere_mass = fmulr(fmulr(fmulr(4.0f, frac_pi_3), r3), p->rest_density);
+        NA.normals = out->normals.as<float>();
+        LAUNCH(c, k_sph_normals, nblk(nv_final, 128), 128, D, NA);
+        out->has_normals = 1;
+    }
     CK(cudaEventRecord(c->ev[8], st));
     CK(cudaEventRecord(c->ev[9], st));
     CK(cudaStreamSynchronize(st));
@@ -996,9 +1024,10 @@ extern "C" void ss_surface_free(ss_surface *s) {
         if (s->owner && g_live_contexts.count(s->owner)) {
             ss_context *c = s->owner;
             give_back(c->o_verts, s->verts); give_back(c->o_tris, s->tris); give_back(c->o_vkeys, s->vkeys); give_back(c->o_rho, s->rho);
+            give_back(c->o_normals, s->normals);
         }
     }
-    s->verts.release(); s->tris.release(); s->vkeys.release(); s->rho.release();
+    s->verts.release(); s->tris.release(); s->vkeys.release(); s->rho.release(); s->normals.release();
     delete s;
 }
 

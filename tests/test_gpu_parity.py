@@ -203,3 +203,19 @@ def test_cuda_multi_gpu_parity():
            "--master-port", "29544", os.path.join(root, "tools", "mgpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
+
+
+def test_cuda_sph_normals(ss, oracle_mod):
+    """SphInterpolator::interpolate_normals at the mesh vertices (sph_interpolation.rs:82-133): unit vectors within 2e-5 of the
+    oracle (summation order differs: R-tree order in the reference, bin order here), for the subdomain and the global path."""
+    from splashsurf_b200 import synthetic as syn
+    for p, kw in ((syn.splash((20, 20, 20), 5, 0.025, 120), dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.5)),
+                  (syn.jittered_cube(10, 0.025, 121), dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.75, subdomain_grid=False))):
+        mesh, rec = ss.reconstruction_pipeline(p, compute_normals=True, sph_normals=True, **kw)
+        n = mesh.point_attributes["normals"]
+        _, h, _ = oracle_mod.absolute_params(kw["particle_radius"], kw["smoothing_length"], kw["cube_size"])
+        ref = oracle_mod.sph_normals(p, rec.particle_densities, mesh.mesh.vertices, compact_support_radius=h,
+                                     particle_rest_mass=oracle_mod.sph_rest_mass(kw["particle_radius"]))
+        assert n.shape == ref.shape and not np.isnan(n).any()
+        assert np.abs(np.linalg.norm(n, axis=1) - 1.0).max() < 1e-5
+        assert np.abs(n - ref).max() <= 2e-5, np.abs(n - ref).max()

@@ -109,3 +109,11 @@ def test_oracle_vs_reference_binary_live(oracle_mod):
     keys = oracle_mod.resolve_keys(rv, o["grid"]["aabb_min"], o["grid"]["cell_size"], o["vertex_keys"], rt, o["triangles"])
     m = oracle_mod.mesh_parity(rv, rt, keys, o["vertices"], o["triangles"], o["vertex_keys"], 64)
     assert m["keys_equal"] and m["triangles_equal"] and m["n_interior_not_bitexact"] == 0, m
+
+
+def test_oracle_sph_normals_fixture(oracle_mod):
+    """SPH normals of the reference pipeline (fixture from the reference binary) vs the restatement: 2e-5 absolute on unit
+    vectors (the reference sums in R-tree traversal order, the restatement in cell order)."""
+    g = load_golden("sph_normals_ref")
+    n = oracle_mod.sph_normals(g["particles"], g["densities"], g["vertices"], compact_support_radius=g["h"], particle_rest_mass=g["rest_mass"])
+    assert np.abs(n - g["normals"]).max() <= 2e-5

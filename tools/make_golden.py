@@ -62,6 +62,12 @@ def main():
     singles["simple"] = {"nv": len(r.mesh.vertices), "nt": len(r.mesh.triangles)}
     json.dump(singles, open(os.path.join(GOLD, "single_particle.json"), "w"), indent=1)
     print(singles)
+    # SPH normals (SphInterpolator::interpolate_normals through the reference pipeline)
+    pn = syn.splash((12, 12, 12), 3, 0.025, 45)
+    m, r = ps.reconstruction_pipeline(pn, particle_radius=0.025, smoothing_length=2.0, cube_size=0.6, compute_normals=True, sph_normals=True)
+    np.savez_compressed(os.path.join(GOLD, "sph_normals_ref.npz"), particles=pn, densities=np.asarray(r.particle_densities),
+                        vertices=np.asarray(m.mesh.vertices), normals=np.asarray(m.point_attributes["normals"]),
+                        h=np.float32(2.0 * 2.0 * 0.025), rest_mass=oracle.sph_rest_mass(0.025))
     # the reference's hot-loop fixture (benches/benches/bench_grid_loop.rs:203-262): inputs only, repacked
     d = json.load(open("/root/reference/data/density_grid_loop_subdomain_33.json"))
     np.savez_compressed(
