@@ -54,7 +54,8 @@ class _Timings(C.Structure):
     _fields_ = [("upload", C.c_float), ("aabb_and_grid", C.c_float), ("decomposition", C.c_float), ("density", C.c_float),
                 ("binning", C.c_float), ("levelset", C.c_float), ("marching_cubes", C.c_float), ("stitching", C.c_float),
                 ("total_device", C.c_float), ("kernel_launches", C.c_uint64), ("levelset_launches", C.c_uint64),
-                ("levelset_fixup_points", C.c_uint64), ("levelset_pairs", C.c_double)]
+                ("levelset_fixup_points", C.c_uint64), ("levelset_pairs", C.c_double),
+                ("bricks_total", C.c_uint64), ("bricks_mc", C.c_uint64), ("bricks_fixscan", C.c_uint64)]
 
 
 _LIB = None

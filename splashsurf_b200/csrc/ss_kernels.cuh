@@ -377,6 +377,7 @@ struct SsLsArgs {
     const uint32_t *fix_bricks;  // SS_LS_FIX: list of flagged bricks (global brick index)
     float *tiles;                // [batch][np^3]
     uint8_t *wflag;              // [batch][nb^3][16] warp boxes that need exact values (SS_LS_FIX)
+    uint8_t *bstate;             // [batch][nb^3] 0: untouched (all zero), 1: every point certified inside, 2: has exact values
     unsigned long long *pairs;   // work counter (in-support evaluations), only with COUNT
     int mode;
 };
@@ -584,6 +585,7 @@ k_levelset(SsDev P, SsLsArgs A) {
             else ss_accumulate<false, false>(P, r, ks, k, gx, gy, gz, phi, hits);
         }
         if (valid) A.tiles[out_idx] = phi;
+        if (threadIdx.x == 0 && mode != SS_LS_FIX && A.bstate) A.bstate[brick_lin] = 2;
         return;
     }
 
@@ -603,42 +605,49 @@ k_levelset(SsDev P, SsLsArgs A) {
     // ---- certification: fast partial sum over the candidates within 0.55 h of the warp box
     bool need_exact = warp_valid && my_flag;
     if (mode == SS_LS_CERTIFY && warp_valid) {
-        const float near2 = 0.3025f * P.h2;          // (0.55 h)^2
         const float cert = P.thr + fabsf(P.thr) * 1.0e-4f + 1.0e-30f;
         float sum = 0.0f;
         const int nwords = ((int)C + 31) >> 5;
-        for (int w = 0; w < nwords; ++w) {
-            const int c = w * 32 + lane;
-            bool keep = false;
-            if (c < (int)C) {
-                const float4 r = s_rec[c];
-                const float dx = fmaxf(fmaxf(bxl - r.x, r.x - bxh), 0.0f);
-                const float dy = fmaxf(fmaxf(byl - r.y, r.y - byh), 0.0f);
-                const float dz = fmaxf(fmaxf(bzl - r.z, r.z - bzh), 0.0f);
-                keep = (dx * dx + dy * dy + dz * dz) < near2;
+        // ring 0: candidates within 0.55 h of the warp box (73 % of the kernel weight in bulk fluid); only if some lane
+        // is still short, ring 1: 0.55 h .. 0.8 h (98 %)
+        float r_lo2 = -1.0f, r_hi2 = 0.3025f * P.h2;
+        for (int ring = 0; ring < 2; ++ring) {
+            for (int w = 0; w < nwords; ++w) {
+                const int c = w * 32 + lane;
+                bool keep = false;
+                if (c < (int)C) {
+                    const float4 r = s_rec[c];
+                    const float dx = fmaxf(fmaxf(bxl - r.x, r.x - bxh), 0.0f);
+                    const float dy = fmaxf(fmaxf(byl - r.y, r.y - byh), 0.0f);
+                    const float dz = fmaxf(fmaxf(bzl - r.z, r.z - bzh), 0.0f);
+                    const float db2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                    keep = (db2 < r_hi2) && !(db2 < r_lo2);
+                }
+                uint32_t mword = __ballot_sync(0xffffffffu, keep);
+                while (mword) {
+                    const int cc = w * 32 + __ffs(mword) - 1;
+                    mword &= mword - 1;
+                    const float4 r = s_rec[cc];
+                    const float dx = r.x - gx, dy = r.y - gy, dz = r.z - gz;
+                    const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                    // cubic spline in v = max(1 - r/h, 0) (zero beyond h); any rounding is fine here: 1e-4 safety margin
+                    const float q = d2 * rsqrtf(fmaxf(d2, 1.0e-30f)) * P.a_hinv;
+                    const float v = fmaxf(1.0f - q, 0.0f);
+                    const float v2 = v * v;
+                    const float inner = fmaf(v, fmaf(v, fmaf(v, -6.0f, 12.0f), -6.0f), 1.0f);
+                    const float wgt = (q <= 0.5f) ? inner : 2.0f * v2 * v;
+                    sum = fmaf(wgt, r.w, sum);
+                }
             }
-            uint32_t mword = __ballot_sync(0xffffffffu, keep);
-            while (mword) {
-                const int cc = w * 32 + __ffs(mword) - 1;
-                mword &= mword - 1;
-                const float4 r = s_rec[cc];
-                const float dx = r.x - gx, dy = r.y - gy, dz = r.z - gz;
-                const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-                // cubic spline in v = max(1 - r/h, 0) (zero beyond h); any rounding is fine here: 1e-4 safety margin
-                const float q = d2 * rsqrtf(fmaxf(d2, 1.0e-30f)) * P.a_hinv;
-                const float v = fmaxf(1.0f - q, 0.0f);
-                const float v2 = v * v;
-                const float inner = fmaf(v, fmaf(v, fmaf(v, -6.0f, 12.0f), -6.0f), 1.0f);
-                const float wgt = (q <= 0.5f) ? inner : 2.0f * v2 * v;
-                sum = fmaf(wgt, r.w, sum);
-            }
+            // lanes outside the tile (clipped boxes) do not need a value
+            const bool ok = !valid || (sum * P.a_sigma > cert);
+            need_exact = !__all_sync(0xffffffffu, ok);
+            if (!need_exact) break;
+            r_lo2 = r_hi2; r_hi2 = 0.64f * P.h2;
         }
-        sum *= P.a_sigma;
-        // lanes outside the tile (clipped boxes) do not need a value
-        const bool ok = !valid || (sum > cert);
-        need_exact = !__all_sync(0xffffffffu, ok);
     }
     const int block_need = __syncthreads_or(need_exact ? 1 : 0);
+    if (threadIdx.x == 0 && mode != SS_LS_FIX && A.bstate) A.bstate[brick_lin] = block_need ? 2 : 1;
     if (!block_need) {
         if (mode == SS_LS_CERTIFY && valid) A.tiles[out_idx] = SS_MARKER;
         return;
@@ -709,16 +718,64 @@ k_levelset(SsDev P, SsLsArgs A) {
     }
 }
 
-// ------------------------------------------------------------------ tile-plane indexing ----
-// The tile passes below use grid = (nbatch * np, ceil(np^2 / 256)), block = 256: blockIdx.x -> (tile, i),
-// blockIdx.y * 256 + threadIdx.x -> flattened (j, k).  One multiply-high replaces the division by np.
-#define SS_TP_THREADS 256
-__device__ __forceinline__ bool ss_plane_index(const SsDev &P, int &tile, int &i, int &j, int &k, int &l) {
-    tile = (int)(blockIdx.x / (unsigned)P.np); i = (int)(blockIdx.x - (unsigned)tile * (unsigned)P.np);
-    const uint32_t l2 = blockIdx.y * SS_TP_THREADS + threadIdx.x;
-    j = (int)__umulhi(l2, P.np_magic); k = (int)l2 - j * P.np;
-    l = i * P.np * P.np + (int)l2;
-    return l2 < (uint32_t)(P.np * P.np);
+// ------------------------------------------------------------------ brick-indexed tile passes ----
+// The passes below use the level-set grid (one CTA of 512 threads per 8x8x8-point brick, one thread per point) and the
+// per-brick state the level-set kernel records, so that bricks in the bulk (all certified) or in the void (all zero) cost
+// one state lookup instead of a sweep over their 512 grid points.
+#define SS_TP_THREADS 512
+struct SsBrick { int tile, bx, by, bz; uint32_t lin; };
+__device__ __forceinline__ int ss_state_at(const SsDev &P, const uint8_t *__restrict__ bstate, const SsBrick &B, int dx, int dy, int dz) {
+    const int x = B.bx + dx, y = B.by + dy, z = B.bz + dz;
+    if (x < 0 || y < 0 || z < 0 || x >= P.nb || y >= P.nb || z >= P.nb) return -1;       // outside the tile: no constraint
+    return bstate[(((size_t)B.tile * P.nb + x) * P.nb + y) * P.nb + z];
+}
+__device__ __forceinline__ SsBrick ss_brick_from_lin(const SsDev &P, uint32_t lin) {
+    SsBrick B;
+    B.lin = lin;
+    uint32_t q = lin;
+    B.bz = (int)(q % (uint32_t)P.nb); q /= (uint32_t)P.nb;
+    B.by = (int)(q % (uint32_t)P.nb); q /= (uint32_t)P.nb;
+    B.bx = (int)(q % (uint32_t)P.nb); B.tile = (int)(q / (uint32_t)P.nb);
+    return B;
+}
+// the passes run over compacted lists of bricks: blockIdx.x -> list entry
+__device__ __forceinline__ SsBrick ss_brick_of_block(const SsDev &P, const uint32_t *__restrict__ list) {
+    return ss_brick_from_lin(P, list[blockIdx.x]);
+}
+
+// Classifies every brick of the batch from the states the level-set kernel recorded:
+//   flag_mc : the brick can hold a surface-crossing edge or a triangle (not all 8 bricks its cells reach are uniformly
+//             certified-inside or uniformly untouched)
+//   flag_fix: the brick holds markers that may touch an outside point (it has exact values itself, or a face neighbour is
+//             not fully certified)
+__global__ void k_brick_classify(SsDev P, const uint8_t *__restrict__ bstate, uint32_t nbricks, uint32_t *__restrict__ flag_mc,
+                                 uint32_t *__restrict__ flag_fix) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbricks) return;
+    const SsBrick B = ss_brick_from_lin(P, b);
+    const int st = bstate[b];
+    bool uniform = (st == 0 || st == 1);
+    if (uniform) {
+#pragma unroll
+        for (int q = 1; q < 8; ++q) { const int s2 = ss_state_at(P, bstate, B, q & 1, (q >> 1) & 1, (q >> 2) & 1); if (s2 != st && s2 != -1) uniform = false; }
+    }
+    flag_mc[b] = uniform ? 0u : 1u;
+    bool fix = (st == 2);
+    if (st == 1) {
+        const int nbr[6][3] = { {1,0,0},{-1,0,0},{0,1,0},{0,-1,0},{0,0,1},{0,0,-1} };
+#pragma unroll
+        for (int q = 0; q < 6; ++q) { const int s2 = ss_state_at(P, bstate, B, nbr[q][0], nbr[q][1], nbr[q][2]); if (s2 != 1 && s2 != -1) fix = true; }
+    }
+    flag_fix[b] = fix ? 1u : 0u;
+}
+__global__ void k_compact_list(const uint32_t *__restrict__ flag, const uint32_t *__restrict__ off, uint32_t n, uint32_t *__restrict__ list) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < n && flag[b]) list[off[b]] = b;
+}
+__device__ __forceinline__ bool ss_brick_point(const SsDev &P, const SsBrick &B, int &i, int &j, int &k, int &l) {
+    i = B.bx * 8 + (threadIdx.x >> 6); j = B.by * 8 + ((threadIdx.x >> 3) & 7); k = B.bz * 8 + (threadIdx.x & 7);
+    l = (i * P.np + j) * P.np + k;
+    return i < P.np && j < P.np && k < P.np;
 }
 // block-wide exclusive scan of a small per-thread count; returns the thread's prefix, total in `total`
 __device__ __forceinline__ uint32_t ss_block_excl_scan(uint32_t v, uint32_t &total) {
@@ -741,14 +798,15 @@ __device__ __forceinline__ uint32_t ss_block_excl_scan(uint32_t v, uint32_t &tot
 
 // Marker points (certified inside, value unknown) that touch an outside point along a grid edge carry a
 // surface-crossing edge, so they need their exact value: flag their warp box and list their brick for the
-// SS_LS_FIX launch.
+// SS_LS_FIX launch.  Only bricks that hold markers and are not surrounded by all-marker bricks are swept.
 __global__ void __launch_bounds__(SS_TP_THREADS)
-k_fixup_flags(SsDev P, const float *__restrict__ tiles, uint8_t *__restrict__ wflag, uint32_t *__restrict__ brick_seen,
-              uint32_t *__restrict__ fix_bricks, uint32_t *__restrict__ nfix /* [0]: bricks, [1]: points */) {
-    int tile, i, j, k, l;
-    if (!ss_plane_index(P, tile, i, j, k, l)) return;
+k_fixup_flags(SsDev P, const float *__restrict__ tiles, const uint32_t *__restrict__ list, uint8_t *__restrict__ wflag,
+              uint32_t *__restrict__ brick_seen, uint32_t *__restrict__ fix_bricks, uint32_t *__restrict__ nfix /* [0]: bricks, [1]: points */) {
+    const SsBrick B = ss_brick_of_block(P, list);
+    int i, j, k, l;
+    if (!ss_brick_point(P, B, i, j, k, l)) return;
     const int np = P.np;
-    const float *phi = tiles + (size_t)tile * np * np * np;
+    const float *phi = tiles + (size_t)B.tile * np * np * np;
     if (phi[l] != SS_MARKER) return;
     const float thr = P.thr;
     bool hit = false;
@@ -759,11 +817,9 @@ k_fixup_flags(SsDev P, const float *__restrict__ tiles, uint8_t *__restrict__ wf
     if (k > 0) hit |= !(phi[l - 1] > thr);
     if (k + 1 < np) hit |= !(phi[l + 1] > thr);
     if (!hit) return;
-    const int nb = P.nb;
     const int warp = (((i & 7) >> 1) << 2) | (((j & 7) >> 2) << 1) | ((k & 7) >> 2);
-    const uint32_t brick = (((uint32_t)tile * nb + (i >> 3)) * nb + (j >> 3)) * nb + (k >> 3);
-    wflag[(size_t)brick * SS_LS_WARPS + warp] = 1;
-    if (atomicExch(&brick_seen[brick], 1u) == 0u) fix_bricks[atomicAdd(&nfix[0], 1u)] = brick;
+    wflag[(size_t)B.lin * SS_LS_WARPS + warp] = 1;
+    if (atomicExch(&brick_seen[B.lin], 1u) == 0u) fix_bricks[atomicAdd(&nfix[0], 1u)] = B.lin;
     atomicAdd(&nfix[1], 1u);
 }
 
@@ -804,27 +860,28 @@ __device__ __forceinline__ bool ss_crossing(float a, float b, float thr) {
                   : ((a > thr) != (b > thr));            // endpoints on different sides (dense_subdomains.rs:1482)
 }
 
-// Pass 1: per tile point, which of its +x/+y/+z edges carry a vertex (endpoints on different sides of the
-// threshold; `value > threshold` == inside, dense_subdomains.rs:1482) and how many triangles its cell emits;
-// per block of 256 points the totals.
+// Pass 1 (over the bricks k_brick_classify listed): per tile point, which of its +x/+y/+z edges carry a vertex and how many
+// triangles its cell emits; per brick the totals.  Unlisted bricks keep their pre-zeroed masks.
 template <bool GLOBAL>
 __global__ void __launch_bounds__(SS_TP_THREADS)
-k_mc_count(SsDev P, const float *__restrict__ tiles, uint8_t *__restrict__ vmask, uint32_t *__restrict__ vblk, uint32_t *__restrict__ tblk) {
-    int tile, i, j, k, l;
-    const bool ok = ss_plane_index(P, tile, i, j, k, l);
+k_mc_count(SsDev P, const float *__restrict__ tiles, const uint32_t *__restrict__ list, uint8_t *__restrict__ vmask,
+           uint32_t *__restrict__ vblk, uint32_t *__restrict__ tblk) {
+    const SsBrick B = ss_brick_of_block(P, list);
+    int i, j, k, l;
+    const bool ok = ss_brick_point(P, B, i, j, k, l);
     const int np = P.np;
     uint32_t mask = 0, nt = 0;
     if (ok) {
-        const float *phi = tiles + (size_t)tile * np * np * np;
+        const float *phi = tiles + (size_t)B.tile * np * np * np;
         const float thr = P.thr;
         const float v0 = phi[l];
         if (i + 1 < np && ss_crossing<GLOBAL>(v0, phi[l + np * np], thr)) mask |= 1u;
         if (j + 1 < np && ss_crossing<GLOBAL>(v0, phi[l + np], thr)) mask |= 2u;
         if (k + 1 < np && ss_crossing<GLOBAL>(v0, phi[l + 1], thr)) mask |= 4u;
-        vmask[(size_t)tile * np * np * np + l] = (uint8_t)mask;
+        if (mask) vmask[(size_t)B.tile * np * np * np + l] = (uint8_t)mask;
         if (i < P.S && j < P.S && k < P.S) nt = c_num_tris[ss_case_index<GLOBAL>(phi, l, i, j, k, np, thr)];
     }
-    uint32_t packed = (nt << 16) | __popc(mask);            // <= 256*5 and 256*3: no overflow between halves
+    uint32_t packed = (nt << 16) | __popc(mask);            // <= 512*5 and 512*3: no overflow between halves
     for (int o = 16; o > 0; o >>= 1) packed += __shfl_xor_sync(0xffffffffu, packed, o);
     __shared__ uint32_t s_part[SS_TP_THREADS / 32];
     if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = packed;
@@ -832,8 +889,7 @@ k_mc_count(SsDev P, const float *__restrict__ tiles, uint8_t *__restrict__ vmask
     if (threadIdx.x == 0) {
         uint32_t tot = 0;
         for (int w = 0; w < SS_TP_THREADS / 32; ++w) tot += s_part[w];
-        const uint32_t b = blockIdx.x * gridDim.y + blockIdx.y;
-        vblk[b] = tot & 0xffffu; tblk[b] = tot >> 16;
+        vblk[blockIdx.x] = tot & 0xffffu; tblk[blockIdx.x] = tot >> 16;
     }
 }
 
@@ -853,18 +909,20 @@ struct SsMcOut {
 template <bool GLOBAL>
 __global__ void __launch_bounds__(SS_TP_THREADS)
 k_mc_verts(SsDev P, const float *__restrict__ tiles, const uint8_t *__restrict__ vmask, const uint32_t *__restrict__ vblk_off,
-           const uint32_t *__restrict__ vblk, uint32_t *__restrict__ voff, const SsTile *__restrict__ tile_tab, SsMcOut O) {
-    const uint32_t b = blockIdx.x * gridDim.y + blockIdx.y;
-    if (vblk[b] == 0) return;
-    int tile, i, j, k, l;
-    const bool ok = ss_plane_index(P, tile, i, j, k, l);
+           const uint32_t *__restrict__ vblk, uint32_t *__restrict__ voff, const SsTile *__restrict__ tile_tab, const uint32_t *__restrict__ list,
+           SsMcOut O) {
+    if (vblk[blockIdx.x] == 0) return;
+    const SsBrick B = ss_brick_of_block(P, list);
+    int i, j, k, l;
+    const bool ok = ss_brick_point(P, B, i, j, k, l);
+    const int tile = B.tile;
     const int np = P.np;
     const size_t pt = (size_t)tile * np * np * np + l;
     const uint32_t mask = ok ? vmask[pt] : 0u;
     uint32_t total;
     const uint32_t pre = ss_block_excl_scan(__popc(mask), total);
     if (!mask) return;
-    uint32_t vid = O.vbase + vblk_off[b] + pre;
+    uint32_t vid = O.vbase + vblk_off[blockIdx.x] + pre;
     voff[pt] = vid;
     const float *phi = tiles + (size_t)tile * np * np * np;
     const SsTile T = tile_tab[tile];
@@ -922,11 +980,12 @@ k_mc_verts(SsDev P, const float *__restrict__ tiles, const uint8_t *__restrict__
 template <bool GLOBAL>
 __global__ void __launch_bounds__(SS_TP_THREADS)
 k_mc_tris(SsDev P, const float *__restrict__ tiles, const uint8_t *__restrict__ vmask, const uint32_t *__restrict__ tblk_off,
-          const uint32_t *__restrict__ tblk, const uint32_t *__restrict__ voff, SsMcOut O) {
-    const uint32_t b = blockIdx.x * gridDim.y + blockIdx.y;
-    if (tblk[b] == 0) return;
-    int tile, i, j, k, l;
-    const bool ok = ss_plane_index(P, tile, i, j, k, l);
+          const uint32_t *__restrict__ tblk, const uint32_t *__restrict__ voff, const uint32_t *__restrict__ list, SsMcOut O) {
+    if (tblk[blockIdx.x] == 0) return;
+    const SsBrick B = ss_brick_of_block(P, list);
+    int i, j, k, l;
+    const bool ok = ss_brick_point(P, B, i, j, k, l);
+    const int tile = B.tile;
     const int np = P.np;
     const float *phi = tiles + (size_t)tile * np * np * np;
     int idx = 0, nt = 0;
@@ -934,7 +993,7 @@ k_mc_tris(SsDev P, const float *__restrict__ tiles, const uint8_t *__restrict__ 
     uint32_t total;
     const uint32_t pre = ss_block_excl_scan((uint32_t)nt, total);
     if (!nt) return;
-    uint32_t tid = O.tbase + tblk_off[b] + pre;
+    uint32_t tid = O.tbase + tblk_off[blockIdx.x] + pre;
     const size_t tbase_pt = (size_t)tile * np * np * np;
     for (int q = 0; q < nt; ++q) {
 #pragma unroll
@@ -948,7 +1007,6 @@ k_mc_tris(SsDev P, const float *__restrict__ tiles, const uint8_t *__restrict__ 
         ++tid;
     }
 }
-
 
 // ------------------------------------------------------------------ SPH normals at the mesh vertices ----
 // SphInterpolator::interpolate_normals (sph_interpolation.rs:82-133): n_i = normalize(sum_j V_j (x_j - x_i)/r * |grad W|(r))

@@ -65,7 +65,7 @@ struct ss_context {
     // reusable scratch
     DevBuf xyz, xyz_f, filt_flag, filt_flag32, filt_off, aabb, cnt, off, key_a, key_b, val_a, val_b, cid, cub_tmp,
         sub_flat, sub_off, sub_sparse, sub_owned, gkey_a, gkey_b, gval_a, gval_b, flags, scan, spos, rho, tab_a, tab_b, rec, ksplit, batch_subs, tiles, vcnt,
-        tcnt, vmask, voff, vblk_off, tblk_off, tile_tab, brick_rng, wflag, brick_seen, fix_list, nflag, bkeys_a, bkeys_b, bids_a, bids_b, bcount, remap, keep, newid, err, pairs;
+        tcnt, vmask, voff, vblk_off, tblk_off, tile_tab, brick_rng, bstate, flag_mc, flag_fix, off_mc, off_fix, list_mc, list_fix, wflag, brick_seen, fix_list, nflag, bkeys_a, bkeys_b, bids_a, bids_b, bcount, remap, keep, newid, err, pairs;
     uint64_t launches = 0;
     // result buffers handed to surfaces and returned by ss_surface_free (avoids cudaMalloc/cudaFree per frame,
     // the analogue of the reference's ReconstructionWorkspace, workspace.rs:12-79)
@@ -205,7 +205,7 @@ extern "C" void ss_context_destroy(ss_context *c) {
     DevBuf *bufs[] = { &c->xyz, &c->xyz_f, &c->filt_flag, &c->filt_flag32, &c->filt_off, &c->aabb, &c->cnt, &c->off, &c->key_a, &c->key_b,
                        &c->val_a, &c->val_b, &c->cid, &c->cub_tmp, &c->sub_flat, &c->sub_off, &c->sub_sparse, &c->sub_owned, &c->gkey_a, &c->gkey_b, &c->gval_a, &c->gval_b, &c->flags, &c->scan,
                        &c->spos, &c->rho, &c->tab_a, &c->tab_b, &c->rec, &c->ksplit, &c->batch_subs, &c->tiles, &c->vcnt, &c->tcnt,
-                       &c->vmask, &c->voff, &c->vblk_off, &c->tblk_off, &c->tile_tab, &c->brick_rng, &c->wflag, &c->brick_seen, &c->fix_list, &c->nflag, &c->bkeys_a, &c->bkeys_b, &c->bids_a, &c->bids_b, &c->bcount, &c->remap, &c->keep, &c->newid,
+                       &c->vmask, &c->voff, &c->vblk_off, &c->tblk_off, &c->tile_tab, &c->brick_rng, &c->bstate, &c->flag_mc, &c->flag_fix, &c->off_mc, &c->off_fix, &c->list_mc, &c->list_fix, &c->wflag, &c->brick_seen, &c->fix_list, &c->nflag, &c->bkeys_a, &c->bkeys_b, &c->bids_a, &c->bids_b, &c->bcount, &c->remap, &c->keep, &c->newid,
                        &c->err, &c->pairs, &c->o_verts, &c->o_tris, &c->o_vkeys, &c->o_rho, &c->o_verts2, &c->o_vkeys2, &c->o_normals };
     for (DevBuf *b : bufs) b->release();
     for (auto &ev : c->ev) cudaEventDestroy(ev);
@@ -571,17 +571,16 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     const unsigned nbricks = (unsigned)(D.nb * D.nb * D.nb);
-    const unsigned planes_y = (unsigned)((D.np * D.np + SS_TP_THREADS - 1) / SS_TP_THREADS);
-    const size_t per_tile = np3 * (4 + 4 + 1) + (size_t)nbricks * (SS_LS_WARPS + 8) + (size_t)D.np * planes_y * 16 + 256;
+    const size_t per_tile = np3 * (4 + 4 + 1) + (size_t)nbricks * (SS_LS_WARPS + 8 + 1 + 16) + 256;
     size_t max_tiles = c->max_tiles ? c->max_tiles : std::max<size_t>(1, std::min<size_t>((free_b / 3) / per_tile, 4096));
     max_tiles = std::min<size_t>(max_tiles, std::max<size_t>(1, (size_t)0x7fffffff / np3 / 2));
     max_tiles = std::min<size_t>(max_tiles, std::max<size_t>(1, (size_t)65535 / D.nb));       // gridDim.z = nb * tiles
     const uint32_t nown = (uint32_t)owned_list.size();
     max_tiles = std::min<size_t>(max_tiles, std::max<uint32_t>(nown, 1));
-    const size_t nblk_max = max_tiles * D.np * planes_y;
+    const size_t nblk_max = max_tiles * nbricks;
     c->tiles.ensure(max_tiles * np3 * 4); c->voff.ensure(max_tiles * np3 * 4); c->vmask.ensure(max_tiles * np3);
     c->vcnt.ensure(nblk_max * 4 + 4); c->tcnt.ensure(nblk_max * 4 + 4); c->vblk_off.ensure(nblk_max * 4 + 4); c->tblk_off.ensure(nblk_max * 4 + 4);
-    c->tile_tab.ensure(max_tiles * sizeof(SsTile)); c->brick_rng.ensure((size_t)D.nb * sizeof(int2));
+    c->tile_tab.ensure(max_tiles * sizeof(SsTile)); c->brick_rng.ensure((size_t)D.nb * sizeof(int2)); c->bstate.ensure(nblk_max);
     c->bcount.ensure(4); c->pairs.ensure(8);
     CK(cudaMemsetAsync(c->bcount.p, 0, 4, st));
     CK(cudaMemsetAsync(c->pairs.p, 0, 8, st));
@@ -617,6 +616,8 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
         }
         CK(cudaMemcpyAsync(c->tile_tab.p, h_tiles.data(), (size_t)nbatch * sizeof(SsTile), cudaMemcpyHostToDevice, st));
         CK(cudaMemsetAsync(c->tiles.p, 0, (size_t)nbatch * np3 * 4, st));
+        CK(cudaMemsetAsync(c->bstate.p, 0, (size_t)nbatch * nbricks, st));
+        CK(cudaMemsetAsync(c->vmask.p, 0, (size_t)nbatch * np3, st));
         CK(cudaEventRecord(c->ev[10], st));
         SsLsArgs A{};
         A.bin_start = c->tab_a.as<uint32_t>(); A.bin_end = c->tab_b.as<uint32_t>(); A.rec = c->rec.as<float4>();
@@ -624,20 +625,36 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
         A.tile_tab = c->tile_tab.as<SsTile>(); A.brick_rng = c->brick_rng.as<int2>(); A.tiles = c->tiles.as<float>();
         A.pairs = c->count_pairs ? c->pairs.as<unsigned long long>() : nullptr;
         A.mode = exact_all ? SS_LS_EXACT_ALL : SS_LS_CERTIFY;
-        A.wflag = nullptr; A.fix_bricks = nullptr;
+        A.wflag = nullptr; A.fix_bricks = nullptr; A.bstate = c->bstate.as<uint8_t>();
         const dim3 ls_grid((unsigned)D.nb, (unsigned)D.nb, (unsigned)D.nb * nbatch);
         launch_levelset(c, ls_grid, D, A, c->count_pairs != 0, global_mode);
         ++ls_launches;
-        const dim3 tp_grid((unsigned)(nbatch * D.np), planes_y);
-        if (!exact_all) {
+        // bricks that can carry surface (for marching cubes) / markers next to outside points (for the fix-up sweep)
+        const uint32_t nbr_b = nbatch * nbricks;
+        c->flag_mc.ensure((size_t)nbr_b * 4); c->flag_fix.ensure((size_t)nbr_b * 4); c->off_mc.ensure((size_t)nbr_b * 4 + 4); c->off_fix.ensure((size_t)nbr_b * 4 + 4);
+        c->list_mc.ensure((size_t)nbr_b * 4); c->list_fix.ensure((size_t)nbr_b * 4);
+        LAUNCH(c, k_brick_classify, nblk(nbr_b, 256), 256, D, c->bstate.as<uint8_t>(), nbr_b, c->flag_mc.as<uint32_t>(), c->flag_fix.as<uint32_t>());
+        cub_excl_scan(c, c->flag_mc.as<uint32_t>(), c->off_mc.as<uint32_t>(), nbr_b);
+        cub_excl_scan(c, c->flag_fix.as<uint32_t>(), c->off_fix.as<uint32_t>(), nbr_b);
+        LAUNCH(c, k_compact_list, nblk(nbr_b, 256), 256, c->flag_mc.as<uint32_t>(), c->off_mc.as<uint32_t>(), nbr_b, c->list_mc.as<uint32_t>());
+        LAUNCH(c, k_compact_list, nblk(nbr_b, 256), 256, c->flag_fix.as<uint32_t>(), c->off_fix.as<uint32_t>(), nbr_b, c->list_fix.as<uint32_t>());
+        uint32_t lc[4] = { 0, 0, 0, 0 };
+        CK(cudaMemcpyAsync(&lc[0], c->off_mc.as<uint32_t>() + (nbr_b - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&lc[1], c->flag_mc.as<uint32_t>() + (nbr_b - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&lc[2], c->off_fix.as<uint32_t>() + (nbr_b - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&lc[3], c->flag_fix.as<uint32_t>() + (nbr_b - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const uint32_t n_mc = lc[0] + lc[1], n_fixscan = lc[2] + lc[3];
+        out->tm.bricks_total += nbr_b; out->tm.bricks_mc += n_mc; out->tm.bricks_fixscan += n_fixscan;
+        if (!exact_all && n_fixscan) {
             // exact values for certified points that turn out to lie on a surface-crossing edge
             const size_t nbr = (size_t)nbatch * nbricks;
             c->wflag.ensure(nbr * SS_LS_WARPS); c->brick_seen.ensure(nbr * 4); c->fix_list.ensure(nbr * 4); c->nflag.ensure(8);
             CK(cudaMemsetAsync(c->wflag.p, 0, nbr * SS_LS_WARPS, st));
             CK(cudaMemsetAsync(c->brick_seen.p, 0, nbr * 4, st));
             CK(cudaMemsetAsync(c->nflag.p, 0, 8, st));
-            LAUNCH(c, k_fixup_flags, tp_grid, SS_TP_THREADS, D, c->tiles.as<float>(), c->wflag.as<uint8_t>(), c->brick_seen.as<uint32_t>(),
-                   c->fix_list.as<uint32_t>(), c->nflag.as<uint32_t>());
+            LAUNCH(c, k_fixup_flags, n_fixscan, SS_TP_THREADS, D, c->tiles.as<float>(), c->list_fix.as<uint32_t>(), c->wflag.as<uint8_t>(),
+                   c->brick_seen.as<uint32_t>(), c->fix_list.as<uint32_t>(), c->nflag.as<uint32_t>());
             uint32_t nfl[2] = { 0, 0 };
             CK(cudaMemcpyAsync(nfl, c->nflag.p, 8, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
@@ -657,21 +674,26 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
                 CK(cudaStreamSynchronize(st));
             }
         }
-        // marching cubes: count per block, scan the block totals, emit vertices, emit triangles
-        const uint32_t nblocks = nbatch * (uint32_t)D.np * planes_y;
-        if (global_mode) LAUNCH(c, k_mc_count<true>, tp_grid, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->vcnt.as<uint32_t>(), c->tcnt.as<uint32_t>());
-        else LAUNCH(c, k_mc_count<false>, tp_grid, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->vcnt.as<uint32_t>(), c->tcnt.as<uint32_t>());
-        cub_excl_scan(c, c->vcnt.as<uint32_t>(), c->vblk_off.as<uint32_t>(), nblocks);
-        cub_excl_scan(c, c->tcnt.as<uint32_t>(), c->tblk_off.as<uint32_t>(), nblocks);
-        uint32_t lastv[2] = { 0, 0 }, lastt[2] = { 0, 0 };
-        CK(cudaMemcpyAsync(&lastv[1], c->vcnt.as<uint32_t>() + (nblocks - 1), 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(&lastt[1], c->tcnt.as<uint32_t>() + (nblocks - 1), 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(&lastv[0], c->vblk_off.as<uint32_t>() + (nblocks - 1), 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(&lastt[0], c->tblk_off.as<uint32_t>() + (nblocks - 1), 4, cudaMemcpyDeviceToHost, st));
+        // marching cubes over the listed bricks: count, scan the brick totals, emit vertices, emit triangles
+        uint64_t bv = 0, bt = 0;
+        if (n_mc) {
+            if (global_mode) LAUNCH(c, k_mc_count<true>, n_mc, SS_TP_THREADS, D, c->tiles.as<float>(), c->list_mc.as<uint32_t>(), c->vmask.as<uint8_t>(), c->vcnt.as<uint32_t>(), c->tcnt.as<uint32_t>());
+            else LAUNCH(c, k_mc_count<false>, n_mc, SS_TP_THREADS, D, c->tiles.as<float>(), c->list_mc.as<uint32_t>(), c->vmask.as<uint8_t>(), c->vcnt.as<uint32_t>(), c->tcnt.as<uint32_t>());
+            cub_excl_scan(c, c->vcnt.as<uint32_t>(), c->vblk_off.as<uint32_t>(), n_mc);
+            cub_excl_scan(c, c->tcnt.as<uint32_t>(), c->tblk_off.as<uint32_t>(), n_mc);
+        }
         uint32_t bc = 0;
         CK(cudaMemcpyAsync(&bc, c->bcount.p, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        const uint64_t bv = (uint64_t)lastv[0] + lastv[1], bt = (uint64_t)lastt[0] + lastt[1];
+        if (n_mc) {
+            uint32_t lv[2] = { 0, 0 }, lt[2] = { 0, 0 };
+            CK(cudaMemcpyAsync(&lv[1], c->vcnt.as<uint32_t>() + (n_mc - 1), 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(&lt[1], c->tcnt.as<uint32_t>() + (n_mc - 1), 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(&lv[0], c->vblk_off.as<uint32_t>() + (n_mc - 1), 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(&lt[0], c->tblk_off.as<uint32_t>() + (n_mc - 1), 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            bv = (uint64_t)lv[0] + lv[1]; bt = (uint64_t)lt[0] + lt[1];
+        }
         if (vtotal + bv >= 0xfffffff0ull || (ttotal + bt) * 3 >= 0xffffffffffull) return ss_fail(SS_ERR_INDEX_TOO_SMALL, "mesh too large for 32-bit vertex ids");
         if (bv || bt) {
             out->verts.grow_keep((vtotal + bv) * 12, vtotal * 12, st);
@@ -685,15 +707,15 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
             O.bkeys = c->bkeys_a.as<unsigned long long>(); O.bids = c->bids_a.as<uint32_t>(); O.bcount = c->bcount.as<uint32_t>();
             O.vbase = (uint32_t)vtotal; O.tbase = (uint32_t)ttotal; O.bcap = (uint32_t)std::min<size_t>((size_t)bc + bv, 0xffffffffu);
             if (global_mode) {
-                LAUNCH(c, k_mc_verts<true>, tp_grid, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->vblk_off.as<uint32_t>(),
-                       c->vcnt.as<uint32_t>(), c->voff.as<uint32_t>(), c->tile_tab.as<SsTile>(), O);
-                LAUNCH(c, k_mc_tris<true>, tp_grid, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->tblk_off.as<uint32_t>(),
-                       c->tcnt.as<uint32_t>(), c->voff.as<uint32_t>(), O);
+                LAUNCH(c, k_mc_verts<true>, n_mc, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->vblk_off.as<uint32_t>(),
+                       c->vcnt.as<uint32_t>(), c->voff.as<uint32_t>(), c->tile_tab.as<SsTile>(), c->list_mc.as<uint32_t>(), O);
+                LAUNCH(c, k_mc_tris<true>, n_mc, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->tblk_off.as<uint32_t>(),
+                       c->tcnt.as<uint32_t>(), c->voff.as<uint32_t>(), c->list_mc.as<uint32_t>(), O);
             } else {
-                LAUNCH(c, k_mc_verts<false>, tp_grid, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->vblk_off.as<uint32_t>(),
-                       c->vcnt.as<uint32_t>(), c->voff.as<uint32_t>(), c->tile_tab.as<SsTile>(), O);
-                LAUNCH(c, k_mc_tris<false>, tp_grid, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->tblk_off.as<uint32_t>(),
-                       c->tcnt.as<uint32_t>(), c->voff.as<uint32_t>(), O);
+                LAUNCH(c, k_mc_verts<false>, n_mc, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->vblk_off.as<uint32_t>(),
+                       c->vcnt.as<uint32_t>(), c->voff.as<uint32_t>(), c->tile_tab.as<SsTile>(), c->list_mc.as<uint32_t>(), O);
+                LAUNCH(c, k_mc_tris<false>, n_mc, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->tblk_off.as<uint32_t>(),
+                       c->tcnt.as<uint32_t>(), c->voff.as<uint32_t>(), c->list_mc.as<uint32_t>(), O);
             }
             vtotal += bv; ttotal += bt;
         }
@@ -847,7 +869,7 @@ extern "C" int ss_levelset_tile_f32(ss_context *c, const float *xyz, const float
             A.bin_start = c->tab_a.as<uint32_t>(); A.bin_end = c->tab_b.as<uint32_t>(); A.rec = c->rec.as<float4>();
             A.ksplit = c->ksplit.as<int>(); A.pidx = c->val_a.as<uint32_t>();
             A.tile_tab = c->tile_tab.as<SsTile>(); A.brick_rng = c->brick_rng.as<int2>(); A.tiles = c->tiles.as<float>();
-            A.pairs = nullptr; A.wflag = nullptr; A.fix_bricks = nullptr; A.mode = SS_LS_EXACT_ALL;
+            A.pairs = nullptr; A.wflag = nullptr; A.fix_bricks = nullptr; A.bstate = nullptr; A.mode = SS_LS_EXACT_ALL;
             launch_levelset(c, dim3((unsigned)D.nb, (unsigned)D.nb, (unsigned)D.nb), D, A, false, false);
             CK(cudaStreamSynchronize(st));
         }
