@@ -187,10 +187,11 @@ def main():
     barrier()
     sampler.start()
     dev_ms, ls_ms, launches, pairs, ls_launches = 0.0, 0.0, 0, 0.0, 0
+    step_ms = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
         res = runner.step(dev_in, copy_out=False)
-        dev_ms += res["device_ms"]; ls_ms += res["timings"]["levelset"]; launches += res["launches"]
+        dev_ms += res["device_ms"]; ls_ms += res["timings"]["levelset"]; launches += res["launches"]; step_ms.append(round(res["device_ms"], 2))
         pairs += res["timings"]["levelset_pairs"]; ls_launches += res["timings"]["levelset_launches"]
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)
@@ -266,7 +267,7 @@ def main():
                            "parallelism": f"subdomain slabs x{world}" if world > 1 else "single GPU",
                            "l2": "inputs (600 MB) and tiles (GBs) exceed the 126 MB L2; no flush needed"},
                 "mesh": {"vertices": int(nv_g if nv_g is not None else nv), "triangles": int(nt_g if nt_g is not None else nt), "subdomains": int(n_sub)},
-                "wall_ms_per_step": wall_ms_max / args.steps, "stage_ms_last_step": stage,
+                "wall_ms_per_step": wall_ms_max / args.steps, "step_ms_rank0": step_ms, "stage_ms_last_step": stage,
                 "e2e": {"value": e2e_val, "unit": "Mparticles/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(len(p_local) * 12 * world),
                         "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}

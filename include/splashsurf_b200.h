@@ -91,6 +91,7 @@ typedef struct ss_timings {
     uint64_t levelset_fixup_points; /* certified points re-evaluated exactly because they touch the surface */
     double levelset_pairs;       /* in-support particle-gridpoint evaluations (only with ss_context_set_count_pairs) */
     uint64_t bricks_total;       /* 8^3-point bricks of all processed tiles */
+    uint64_t bricks_levelset;    /* non-empty bricks evaluated by the level-set kernel (CTAs launched) */
     uint64_t bricks_mc;          /* bricks swept by marching cubes (can hold surface) */
     uint64_t bricks_fixscan;     /* bricks swept for certified points next to outside points */
 } ss_timings;

@@ -55,7 +55,7 @@ class _Timings(C.Structure):
                 ("binning", C.c_float), ("levelset", C.c_float), ("marching_cubes", C.c_float), ("stitching", C.c_float),
                 ("total_device", C.c_float), ("kernel_launches", C.c_uint64), ("levelset_launches", C.c_uint64),
                 ("levelset_fixup_points", C.c_uint64), ("levelset_pairs", C.c_double),
-                ("bricks_total", C.c_uint64), ("bricks_mc", C.c_uint64), ("bricks_fixscan", C.c_uint64)]
+                ("bricks_total", C.c_uint64), ("bricks_levelset", C.c_uint64), ("bricks_mc", C.c_uint64), ("bricks_fixscan", C.c_uint64)]
 
 
 _LIB = None

@@ -34,6 +34,7 @@ struct SsDev {
     // neighbourhood-search grid bound and level-set binning
     int nsD, ns_stride;   // max NS cells per dim per subdomain, nsD^3
     int nb;               // bricks per dim = ceil(np / 8)
+    int ext_bricks;       // 1: np == 8 (nb - 1) + 1 -> the np-1 planes are evaluated by the last full brick's CTA
     int be;               // bin edge in cells (multiple of 8; 8 unless h/c is large)
     int nlo;              // bin index offset = ceil(R / be): local coordinate u lands in bin floor(u/be)+nlo
     int nbin, nbin_sub;   // bins per dim, nbin^3

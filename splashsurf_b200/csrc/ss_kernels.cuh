@@ -375,6 +375,7 @@ struct SsLsArgs {
     const SsTile *tile_tab;      // [batch] per-tile constants (host-filled)
     const int2 *brick_rng;       // [nb] candidate bin range (lo, hi) of brick b along one axis
     const uint32_t *fix_bricks;  // SS_LS_FIX: list of flagged bricks (global brick index)
+    const uint32_t *work_list;   // other modes: list of non-empty bricks to evaluate
     float *tiles;                // [batch][np^3]
     uint8_t *wflag;              // [batch][nb^3][16] warp boxes that need exact values (SS_LS_FIX)
     uint8_t *bstate;             // [batch][nb^3] 0: untouched (all zero), 1: every point certified inside, 2: has exact values
@@ -456,6 +457,144 @@ __device__ __forceinline__ bool ss_global_candidate(const SsDev &P, const float4
     return allowed;
 }
 
+// A warp's set of grid points: origin + power-of-two dimensions (dx * dy * dz <= 32), clipped to the tile.
+struct SsWarpBox { int i0, j0, k0, dx, dy, dz; };
+
+// Everything a lane needs about its grid point and its warp's box.
+struct SsLanePoint {
+    int i, j, k, gi, gj, gk, k1;
+    bool valid, warp_valid;
+    float gx, gy, gz;                 // point coordinates (reference arithmetic)
+    float bxl, bxh, byl, byh, bzl, bzh;   // warp box in world coordinates (culling only)
+    size_t out_idx;
+};
+__device__ __forceinline__ SsLanePoint ss_lane_point(const SsDev &P, const SsTile &T, const SsWarpBox &W, int tile_idx, int lane, bool sparse) {
+    SsLanePoint L;
+    const int lk = lane & (W.dz - 1), lj = (lane / W.dz) & (W.dy - 1), li = lane / (W.dz * W.dy);
+    L.i = W.i0 + li; L.j = W.j0 + lj; L.k = W.k0 + lk;
+    L.valid = (li < W.dx) && (L.i < P.np) && (L.j < P.np) && (L.k < P.np);
+    L.warp_valid = (W.i0 < P.np) && (W.j0 < P.np) && (W.k0 < P.np);
+    L.gi = T.gbase[0] + L.i; L.gj = T.gbase[1] + L.j; L.gk = T.gbase[2] + L.k;
+    // grid point coordinates from GLOBAL indices: x, y = mul then add, z fused in the AVX path
+    // (dense_subdomains.rs:1068, :1101-1102); scalar path: point_coordinates (uniform_grid.rs:418-425)
+    L.gx = __fadd_rn(__fmul_rn((float)L.gi, P.c), P.gmin[0]);
+    L.gy = __fadd_rn(__fmul_rn((float)L.gj, P.c), P.gmin[1]);
+    L.gz = sparse ? __fadd_rn(P.gmin[2], __fmul_rn((float)L.gk, P.c)) : __fmaf_rn((float)L.gk, P.c, P.gmin[2]);
+    const int i1 = min(W.i0 + W.dx - 1, P.np - 1), j1 = min(W.j0 + W.dy - 1, P.np - 1), k1 = min(W.k0 + W.dz - 1, P.np - 1);
+    L.k1 = k1;
+    L.bxl = fmaf((float)(T.gbase[0] + W.i0), P.c, P.gmin[0]); L.bxh = fmaf((float)(T.gbase[0] + i1), P.c, P.gmin[0]);
+    L.byl = fmaf((float)(T.gbase[1] + W.j0), P.c, P.gmin[1]); L.byh = fmaf((float)(T.gbase[1] + j1), P.c, P.gmin[1]);
+    L.bzl = fmaf((float)(T.gbase[2] + W.k0), P.c, P.gmin[2]); L.bzh = fmaf((float)(T.gbase[2] + k1), P.c, P.gmin[2]);
+    L.out_idx = (size_t)tile_idx * P.np * P.np * P.np + ((size_t)L.i * P.np + L.j) * P.np + L.k;
+    return L;
+}
+__device__ __forceinline__ float ss_box_dist2(const SsLanePoint &L, const float4 r) {
+    const float dx = fmaxf(fmaxf(L.bxl - r.x, r.x - L.bxh), 0.0f);
+    const float dy = fmaxf(fmaxf(L.byl - r.y, r.y - L.byh), 0.0f);
+    const float dz = fmaxf(fmaxf(L.bzl - r.z, r.z - L.bzh), 0.0f);
+    return fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+}
+
+// Certification of one warp box: true when every valid lane is provably inside (see k_levelset).
+__device__ __forceinline__ bool ss_certify_box(const SsDev &P, const SsLanePoint &L, const float4 *s_rec, int C, int lane) {
+    const float cert = P.thr + fabsf(P.thr) * 1.0e-4f + 1.0e-30f;
+    float sum = 0.0f;
+    const int nwords = (C + 31) >> 5;
+    // ring 0: candidates within 0.55 h of the warp box (73 % of the kernel weight in bulk fluid); only if some lane
+    // is still short, ring 1: 0.55 h .. 0.8 h (98 %)
+    float r_lo2 = -1.0f, r_hi2 = 0.3025f * P.h2;
+    for (int ring = 0; ring < 2; ++ring) {
+        for (int w = 0; w < nwords; ++w) {
+            const int c = w * 32 + lane;
+            bool keep = false;
+            if (c < C) { const float db2 = ss_box_dist2(L, s_rec[c]); keep = (db2 < r_hi2) && !(db2 < r_lo2); }
+            uint32_t mword = __ballot_sync(0xffffffffu, keep);
+            while (mword) {
+                const int cc = w * 32 + __ffs(mword) - 1;
+                mword &= mword - 1;
+                const float4 r = s_rec[cc];
+                const float dx = r.x - L.gx, dy = r.y - L.gy, dz = r.z - L.gz;
+                const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                // cubic spline in v = max(1 - r/h, 0) (zero beyond h); any rounding is fine here: 1e-4 safety margin
+                const float q = d2 * rsqrtf(fmaxf(d2, 1.0e-30f)) * P.a_hinv;
+                const float v = fmaxf(1.0f - q, 0.0f);
+                const float v2 = v * v;
+                const float inner = fmaf(v, fmaf(v, fmaf(v, -6.0f, 12.0f), -6.0f), 1.0f);
+                const float wgt = (q <= 0.5f) ? inner : 2.0f * v2 * v;
+                sum = fmaf(wgt, r.w, sum);
+            }
+        }
+        // lanes outside the tile (clipped boxes) do not need a value
+        const bool ok = !L.valid || (sum * P.a_sigma > cert);
+        if (__all_sync(0xffffffffu, ok)) return true;
+        r_lo2 = r_hi2; r_hi2 = 0.64f * P.h2;
+    }
+    return false;
+}
+
+// Exact, ordered evaluation of one warp box from the sorted candidate keys; returns the lane's value.
+template <bool GLOBAL>
+__device__ __forceinline__ float ss_exact_box(const SsDev &P, const SsLanePoint &L, bool sparse, const float4 *s_rec, const int *s_ks,
+                                              const unsigned long long *s_key, unsigned short *my_list, const int (*s_imin)[3],
+                                              const float (*s_dx0)[3], int C, int lane, unsigned &hits) {
+    const float cull2 = (GLOBAL ? P.rev2 : (sparse ? P.h2m : P.h2)) * 1.0001f;
+    // per-warp compacted list (sorted order) of the candidates within h of the warp's point box
+    int nlist = 0;
+    bool all_fma = true;                                   // no lane of this warp in any candidate's remainder lanes
+    const int nwords = (C + 31) >> 5;
+    for (int w = 0; w < nwords; ++w) {
+        const int rnk = w * 32 + lane;
+        bool keep = false;
+        int slot = 0;
+        if (rnk < C) {
+            slot = (int)(s_key[rnk] & 0xffffu);
+            keep = ss_box_dist2(L, s_rec[slot]) < cull2;
+            if (keep && s_ks[slot] <= L.k1) all_fma = false;
+        }
+        const uint32_t mword = __ballot_sync(0xffffffffu, keep);
+        if (keep) my_list[nlist + __popc(mword & ((1u << lane) - 1u))] = (unsigned short)slot;
+        nlist += __popc(mword);
+    }
+    all_fma = __all_sync(0xffffffffu, all_fma);
+    __syncwarp();
+    float phi = 0.0f;
+    if (GLOBAL) {
+        for (int n = 0; n < nlist; ++n) {
+            const int slot = my_list[n];
+            ss_accumulate_global(P, s_rec[slot], s_imin[slot], s_dx0[slot], L.gi, L.gj, L.gk, phi, hits);
+        }
+    } else if (sparse) {
+        for (int n = 0; n < nlist; ++n) ss_accumulate<true, false>(P, s_rec[my_list[n]], 0, L.k, L.gx, L.gy, L.gz, phi, hits);
+    } else if (all_fma) {
+        for (int n = 0; n < nlist; ++n) ss_accumulate<false, true>(P, s_rec[my_list[n]], 0, L.k, L.gx, L.gy, L.gz, phi, hits);
+    } else {
+        for (int n = 0; n < nlist; ++n) { const int slot = my_list[n]; ss_accumulate<false, false>(P, s_rec[slot], s_ks[slot], L.k, L.gx, L.gy, L.gz, phi, hits); }
+    }
+    __syncwarp();
+    return phi;
+}
+
+// Extension tasks: when the tile has 8 * (nb - 1) + 1 points per axis, the single point planes at index np - 1 are
+// evaluated by the CTA of the last full brick (it already staged their candidates) instead of by 217 nearly idle
+// CTAs per tile.  Task t of a brick with (ex, ey, ez) "last brick along x / y / z" flags:
+//   0,1: x-face halves   2,3: y-face halves   4,5: z-face halves   6: xy-edge   7: xz-edge   8: yz-edge   9: corner
+__device__ __forceinline__ bool ss_ext_task(int t, int bx, int by, int bz, bool ex, bool ey, bool ez, SsWarpBox &W, int &vbx, int &vby, int &vbz) {
+    const int i0 = bx * 8, j0 = by * 8, k0 = bz * 8, iL = i0 + 8, jL = j0 + 8, kL = k0 + 8;
+    vbx = bx; vby = by; vbz = bz;
+    switch (t) {
+        case 0: case 1: if (!ex) return false; W = SsWarpBox{ iL, j0 + 4 * t, k0, 1, 4, 8 }; vbx = bx + 1; return true;
+        case 2: case 3: if (!ey) return false; W = SsWarpBox{ i0 + 4 * (t - 2), jL, k0, 4, 1, 8 }; vby = by + 1; return true;
+        case 4: case 5: if (!ez) return false; W = SsWarpBox{ i0 + 4 * (t - 4), j0, kL, 4, 8, 1 }; vbz = bz + 1; return true;
+        case 6: if (!(ex && ey)) return false; W = SsWarpBox{ iL, jL, k0, 1, 1, 8 }; vbx = bx + 1; vby = by + 1; return true;
+        case 7: if (!(ex && ez)) return false; W = SsWarpBox{ iL, j0, kL, 1, 8, 1 }; vbx = bx + 1; vbz = bz + 1; return true;
+        case 8: if (!(ey && ez)) return false; W = SsWarpBox{ i0, jL, kL, 8, 1, 1 }; vby = by + 1; vbz = bz + 1; return true;
+        case 9: if (!(ex && ey && ez)) return false; W = SsWarpBox{ iL, jL, kL, 1, 1, 1 }; vbx = bx + 1; vby = by + 1; vbz = bz + 1; return true;
+    }
+    return false;
+}
+// virtual (index nb - 1) bricks covered by extension tasks: 0:x 1:y 2:z 3:xy 4:xz 5:yz 6:xyz  <- tasks
+__device__ __forceinline__ int ss_ext_group(int t) { return t < 6 ? (t >> 1) : t - 3; }
+
 // One CTA = one 8x8x8-point brick of one subdomain tile; one warp = a 2x4x4 point box; one lane = one point.
 //
 // Exact value of a point: phi = ordered fold over the subdomain's particles in ascending global index of
@@ -466,10 +605,14 @@ __device__ __forceinline__ bool ss_global_candidate(const SsDev &P, const float4
 //
 // Certification (SS_LS_CERTIFY): every term is >= 0, so the reference's value is >= any partial sum of its terms
 // (up to ~1e-6 relative rounding).  A warp first sums -- with fast arithmetic, in any order -- the candidates
-// within 0.55 h of its box; if every lane already exceeds threshold * (1 + 1e-4) all 32 points are provably inside
+// near its box; if every lane already exceeds threshold * (1 + 1e-4) all its points are provably inside
 // and only SS_MARKER is stored.  Otherwise the warp evaluates all its points exactly.  k_fixup_flags then finds
 // marker points that touch an outside point (a surface-crossing edge needs both exact endpoints) and a second
 // launch (SS_LS_FIX) evaluates those warp boxes exactly.
+//
+// Launch: SS_LS_CERTIFY / SS_LS_EXACT_ALL run over a work list of non-empty bricks (k_brick_worklist); with
+// P.ext_bricks the list only holds bricks 0 .. nb-2 per axis and the last one also evaluates the np-1 planes
+// (extension tasks).  SS_LS_FIX runs over the flagged bricks (any index, no extension).
 template <bool COUNT, bool GLOBAL>
 __global__ void __launch_bounds__(SS_LS_THREADS, 3)
 k_levelset(SsDev P, SsLsArgs A) {
@@ -479,6 +622,7 @@ k_levelset(SsDev P, SsLsArgs A) {
     __shared__ unsigned short s_list[SS_LS_WARPS][SS_LS_CAP];
     __shared__ uint32_t s_rng[2][128];          // candidate runs (start, length)
     __shared__ uint32_t s_pre[129];
+    __shared__ int s_ext_need[8];               // per virtual brick group: some extension warp needs exact values
     // global path only: per candidate the first stencil point index and the start value of the incremental deltas
     __shared__ int s_imin[GLOBAL ? SS_LS_CAP : 1][3];
     __shared__ float s_dx0[GLOBAL ? SS_LS_CAP : 1][3];
@@ -486,27 +630,28 @@ k_levelset(SsDev P, SsLsArgs A) {
     const int nb = P.nb;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mode = A.mode;
+    const uint32_t brick_lin = (mode == SS_LS_FIX) ? A.fix_bricks[blockIdx.x] : A.work_list[blockIdx.x];
     int bx, by, bz, tile_idx;
-    uint32_t brick_lin;
-    if (mode == SS_LS_FIX) {
-        brick_lin = A.fix_bricks[blockIdx.x];
+    {
         uint32_t q = brick_lin;
         bz = (int)(q % (uint32_t)nb); q /= (uint32_t)nb;
         by = (int)(q % (uint32_t)nb); q /= (uint32_t)nb;
         bx = (int)(q % (uint32_t)nb); tile_idx = (int)(q / (uint32_t)nb);
-    } else {
-        bx = blockIdx.x; by = blockIdx.y;
-        tile_idx = (int)(blockIdx.z / (unsigned)nb); bz = (int)(blockIdx.z - (unsigned)tile_idx * (unsigned)nb);
-        brick_lin = (((uint32_t)tile_idx * nb + bx) * nb + by) * nb + bz;
     }
+    const bool ext = P.ext_bricks && mode != SS_LS_FIX;
+    const bool ex = ext && bx == nb - 2, ey = ext && by == nb - 2, ez = ext && bz == nb - 2;
     const bool my_flag = (mode != SS_LS_FIX) || (A.wflag[(size_t)brick_lin * SS_LS_WARPS + warp] != 0);
+    if (threadIdx.x < 8) s_ext_need[threadIdx.x] = 0;
 
     const SsTile T = A.tile_tab[tile_idx];
     const uint32_t s = T.s;
     const bool sparse = GLOBAL || T.sparse != 0;
 
-    // ---- candidate runs: bins overlapping [8b - R, 8b + 7 + R) per axis; z-ranges are contiguous in key order
-    const int2 rx = A.brick_rng[bx], ry = A.brick_rng[by], rz = A.brick_rng[bz];
+    // ---- candidate runs: bins overlapping [8b - R, 8b + 7 + R) per axis (+ the extension plane); z contiguous in key order
+    int2 rx = A.brick_rng[bx], ry = A.brick_rng[by], rz = A.brick_rng[bz];
+    if (ex) rx.y = A.brick_rng[bx + 1].y;
+    if (ey) ry.y = A.brick_rng[by + 1].y;
+    if (ez) rz.y = A.brick_rng[bz + 1].y;
     const int nyr = ry.y - ry.x + 1;
     const int nruns = (rx.y - rx.x + 1) * nyr;   // host guarantees <= 128
     if ((int)threadIdx.x < nruns) {
@@ -533,59 +678,49 @@ k_levelset(SsDev P, SsLsArgs A) {
         if (lane == 31) s_pre[128] = incl;
     }
     __syncthreads();
-    const uint32_t C = s_pre[128];
-    if (C == 0) return;                          // tile is pre-zeroed: phi = 0 exactly
+    const int C = (int)s_pre[128];
+    if (C == 0) return;                          // tile is pre-zeroed: phi = 0 exactly (bstate stays 0)
 
-    // ---- this lane's grid point
-    const int wi = warp >> 2, wj = (warp >> 1) & 1, wk = warp & 1;
-    const int li = lane >> 4, lj = (lane >> 2) & 3, lk = lane & 3;
-    const int i = bx * 8 + wi * 2 + li, j = by * 8 + wj * 4 + lj, k = bz * 8 + wk * 4 + lk;
-    const bool valid = (i < P.np) && (j < P.np) && (k < P.np);
-    const int gi = T.gbase[0] + i, gj = T.gbase[1] + j, gk = T.gbase[2] + k;
-    // grid point coordinates from GLOBAL indices: x, y = mul then add, z fused in the AVX path
-    // (dense_subdomains.rs:1068, :1101-1102); scalar path: point_coordinates (uniform_grid.rs:418-425)
-    const float gx = __fadd_rn(__fmul_rn((float)gi, P.c), P.gmin[0]);
-    const float gy = __fadd_rn(__fmul_rn((float)gj, P.c), P.gmin[1]);
-    const float gz = sparse ? __fadd_rn(P.gmin[2], __fmul_rn((float)gk, P.c)) : __fmaf_rn((float)gk, P.c, P.gmin[2]);
-    // warp box (for culling only): corner points of the 2x4x4 box, clipped to the tile
-    const int i0 = bx * 8 + wi * 2, j0 = by * 8 + wj * 4, k0 = bz * 8 + wk * 4;
-    const bool warp_valid = (i0 < P.np) && (j0 < P.np) && (k0 < P.np);
-    const int i1 = min(i0 + 1, P.np - 1), j1 = min(j0 + 3, P.np - 1), k1 = min(k0 + 3, P.np - 1);
-    const float bxl = fmaf((float)(T.gbase[0] + i0), P.c, P.gmin[0]), bxh = fmaf((float)(T.gbase[0] + i1), P.c, P.gmin[0]);
-    const float byl = fmaf((float)(T.gbase[1] + j0), P.c, P.gmin[1]), byh = fmaf((float)(T.gbase[1] + j1), P.c, P.gmin[1]);
-    const float bzl = fmaf((float)(T.gbase[2] + k0), P.c, P.gmin[2]), bzh = fmaf((float)(T.gbase[2] + k1), P.c, P.gmin[2]);
-    const float cull2 = (GLOBAL ? P.rev2 : (sparse ? P.h2m : P.h2)) * 1.0001f;
-    const size_t out_idx = (size_t)tile_idx * P.np * P.np * P.np + ((size_t)i * P.np + j) * P.np + k;
-
-    float phi = 0.0f;
+    const SsWarpBox Wm = { bx * 8 + (warp >> 2) * 2, by * 8 + ((warp >> 1) & 1) * 4, bz * 8 + (warp & 1) * 4, 2, 4, 4 };
+    SsWarpBox We = Wm;
+    int vbx = bx, vby = by, vbz = bz;
+    const bool has_ext = (ex || ey || ez) && warp < 10 && ss_ext_task(warp, bx, by, bz, ex, ey, ez, We, vbx, vby, vbz);
     unsigned hits = 0;
 
     if (C > SS_LS_CAP) {
         // ---- oversized brick (pathological clustering): every warp walks all candidates in ascending particle
         // index by repeated selection of the next-larger index.  O(C^2) but exact; no certification.
-        if (!warp_valid || !my_flag) return;
-        long long last = -1;
-        for (uint32_t done = 0; done < C; ++done) {
-            unsigned long long best = ~0ull;
-            for (int r = 0; r < nruns; ++r) {
-                uint32_t a = s_rng[0][r], len = s_rng[1][r];
-                for (uint32_t t = lane; t < len; t += 32) {
-                    uint32_t pi = A.pidx[a + t];
-                    if ((long long)pi > last) { unsigned long long kk = ((unsigned long long)pi << 32) | (a + t); if (kk < best) best = kk; }
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 1 && !has_ext) break;
+            const SsLanePoint L = ss_lane_point(P, T, pass ? We : Wm, tile_idx, lane, sparse);
+            if (!L.warp_valid || (pass == 0 && !my_flag)) continue;
+            float phi = 0.0f;
+            long long last = -1;
+            for (int done = 0; done < C; ++done) {
+                unsigned long long best = ~0ull;
+                for (int r = 0; r < nruns; ++r) {
+                    uint32_t a = s_rng[0][r], len = s_rng[1][r];
+                    for (uint32_t t = lane; t < len; t += 32) {
+                        uint32_t pi = A.pidx[a + t];
+                        if ((long long)pi > last) { unsigned long long kk = ((unsigned long long)pi << 32) | (a + t); if (kk < best) best = kk; }
+                    }
                 }
+                for (int o = 16; o > 0; o >>= 1) { unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o); if (other < best) best = other; }
+                if (best == ~0ull) break;
+                last = (long long)(best >> 32);
+                uint32_t src = (uint32_t)(best & 0xffffffffu);
+                float4 r = A.rec[src];
+                int ks = A.ksplit[src];
+                if (GLOBAL) { int im[3]; float d0[3]; if (ss_global_candidate(P, r, im, d0)) ss_accumulate_global(P, r, im, d0, L.gi, L.gj, L.gk, phi, hits); }
+                else if (sparse) ss_accumulate<true, false>(P, r, ks, L.k, L.gx, L.gy, L.gz, phi, hits);
+                else ss_accumulate<false, false>(P, r, ks, L.k, L.gx, L.gy, L.gz, phi, hits);
             }
-            for (int o = 16; o > 0; o >>= 1) { unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o); if (other < best) best = other; }
-            if (best == ~0ull) break;
-            last = (long long)(best >> 32);
-            uint32_t src = (uint32_t)(best & 0xffffffffu);
-            float4 r = A.rec[src];
-            int ks = A.ksplit[src];
-            if (GLOBAL) { int im[3]; float d0[3]; ss_global_candidate(P, r, im, d0); ss_accumulate_global(P, r, im, d0, gi, gj, gk, phi, hits); }
-            else if (sparse) ss_accumulate<true, false>(P, r, ks, k, gx, gy, gz, phi, hits);
-            else ss_accumulate<false, false>(P, r, ks, k, gx, gy, gz, phi, hits);
+            if (L.valid) A.tiles[L.out_idx] = phi;
         }
-        if (valid) A.tiles[out_idx] = phi;
-        if (threadIdx.x == 0 && mode != SS_LS_FIX && A.bstate) A.bstate[brick_lin] = 2;
+        if (mode != SS_LS_FIX && A.bstate) {
+            if (threadIdx.x == 0) A.bstate[brick_lin] = 2;
+            if (has_ext && lane == 0) A.bstate[(((size_t)tile_idx * nb + vbx) * nb + vby) * nb + vbz] = 2;
+        }
         return;
     }
 
@@ -602,120 +737,81 @@ k_levelset(SsDev P, SsLsArgs A) {
     }
     __syncthreads();
 
-    // ---- certification: fast partial sum over the candidates within 0.55 h of the warp box
-    bool need_exact = warp_valid && my_flag;
-    if (mode == SS_LS_CERTIFY && warp_valid) {
-        const float cert = P.thr + fabsf(P.thr) * 1.0e-4f + 1.0e-30f;
-        float sum = 0.0f;
-        const int nwords = ((int)C + 31) >> 5;
-        // ring 0: candidates within 0.55 h of the warp box (73 % of the kernel weight in bulk fluid); only if some lane
-        // is still short, ring 1: 0.55 h .. 0.8 h (98 %)
-        float r_lo2 = -1.0f, r_hi2 = 0.3025f * P.h2;
-        for (int ring = 0; ring < 2; ++ring) {
-            for (int w = 0; w < nwords; ++w) {
-                const int c = w * 32 + lane;
-                bool keep = false;
-                if (c < (int)C) {
-                    const float4 r = s_rec[c];
-                    const float dx = fmaxf(fmaxf(bxl - r.x, r.x - bxh), 0.0f);
-                    const float dy = fmaxf(fmaxf(byl - r.y, r.y - byh), 0.0f);
-                    const float dz = fmaxf(fmaxf(bzl - r.z, r.z - bzh), 0.0f);
-                    const float db2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-                    keep = (db2 < r_hi2) && !(db2 < r_lo2);
-                }
-                uint32_t mword = __ballot_sync(0xffffffffu, keep);
-                while (mword) {
-                    const int cc = w * 32 + __ffs(mword) - 1;
-                    mword &= mword - 1;
-                    const float4 r = s_rec[cc];
-                    const float dx = r.x - gx, dy = r.y - gy, dz = r.z - gz;
-                    const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-                    // cubic spline in v = max(1 - r/h, 0) (zero beyond h); any rounding is fine here: 1e-4 safety margin
-                    const float q = d2 * rsqrtf(fmaxf(d2, 1.0e-30f)) * P.a_hinv;
-                    const float v = fmaxf(1.0f - q, 0.0f);
-                    const float v2 = v * v;
-                    const float inner = fmaf(v, fmaf(v, fmaf(v, -6.0f, 12.0f), -6.0f), 1.0f);
-                    const float wgt = (q <= 0.5f) ? inner : 2.0f * v2 * v;
-                    sum = fmaf(wgt, r.w, sum);
-                }
-            }
-            // lanes outside the tile (clipped boxes) do not need a value
-            const bool ok = !valid || (sum * P.a_sigma > cert);
-            need_exact = !__all_sync(0xffffffffu, ok);
-            if (!need_exact) break;
-            r_lo2 = r_hi2; r_hi2 = 0.64f * P.h2;
-        }
+    // ---- certification of the warp's main box and (if any) its extension box
+    bool need_main, need_ext = false;
+    {
+        const SsLanePoint L = ss_lane_point(P, T, Wm, tile_idx, lane, sparse);
+        need_main = L.warp_valid && my_flag;
+        if (mode == SS_LS_CERTIFY && L.warp_valid) need_main = !ss_certify_box(P, L, s_rec, C, lane);
     }
-    const int block_need = __syncthreads_or(need_exact ? 1 : 0);
-    if (threadIdx.x == 0 && mode != SS_LS_FIX && A.bstate) A.bstate[brick_lin] = block_need ? 2 : 1;
+    if (has_ext) {
+        const SsLanePoint L = ss_lane_point(P, T, We, tile_idx, lane, sparse);
+        need_ext = L.warp_valid;
+        if (mode == SS_LS_CERTIFY && L.warp_valid) need_ext = !ss_certify_box(P, L, s_rec, C, lane);
+        if (need_ext && lane == 0) s_ext_need[ss_ext_group(warp)] = 1;
+    }
+    const int main_need = __syncthreads_or(need_main ? 1 : 0);
+    const int any_ext_need = s_ext_need[0] | s_ext_need[1] | s_ext_need[2] | s_ext_need[3] | s_ext_need[4] | s_ext_need[5] | s_ext_need[6];
+    if (mode != SS_LS_FIX && A.bstate) {
+        if (threadIdx.x == 0) A.bstate[brick_lin] = main_need ? 2 : 1;
+        if (has_ext && lane == 0) A.bstate[(((size_t)tile_idx * nb + vbx) * nb + vby) * nb + vbz] = s_ext_need[ss_ext_group(warp)] ? 2 : 1;
+    }
+    const bool block_need = main_need || any_ext_need;
     if (!block_need) {
-        if (mode == SS_LS_CERTIFY && valid) A.tiles[out_idx] = SS_MARKER;
+        if (mode == SS_LS_CERTIFY) {
+            const SsLanePoint L = ss_lane_point(P, T, Wm, tile_idx, lane, sparse);
+            if (L.valid) A.tiles[L.out_idx] = SS_MARKER;
+            if (has_ext) { const SsLanePoint Le = ss_lane_point(P, T, We, tile_idx, lane, sparse); if (Le.valid) A.tiles[Le.out_idx] = SS_MARKER; }
+        }
         return;
     }
 
     // ---- exact path: order the candidates by global particle index
-    int npow = 32; while (npow < (int)C) npow <<= 1;
-    for (int t = (int)C + threadIdx.x; t < npow; t += blockDim.x) s_key[t] = ~0ull;
+    int npow = 32; while (npow < C) npow <<= 1;
+    for (int t = C + threadIdx.x; t < npow; t += blockDim.x) s_key[t] = ~0ull;
     __syncthreads();
     ss_bitonic(s_key, npow);
-    if (!warp_valid) return;
-    if (!need_exact) {
-        if (mode == SS_LS_CERTIFY && valid) A.tiles[out_idx] = SS_MARKER;
-        return;
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1 && !has_ext) break;
+        const SsLanePoint L = ss_lane_point(P, T, pass ? We : Wm, tile_idx, lane, sparse);
+        if (!L.warp_valid) continue;
+        const bool need = pass ? need_ext : need_main;
+        if (!need) { if (mode == SS_LS_CERTIFY && L.valid) A.tiles[L.out_idx] = SS_MARKER; continue; }
+        const float phi = ss_exact_box<GLOBAL>(P, L, sparse, s_rec, s_ks, s_key, s_list[warp], s_imin, s_dx0, C, lane, hits);
+        if (L.valid) A.tiles[L.out_idx] = phi;
     }
-    // ---- per-warp compacted list (sorted order) of the candidates within h of the warp's point box
-    int nlist = 0;
-    bool all_fma = true;                                   // no lane of this warp in any candidate's remainder lanes
-    {
-        const int nwords = ((int)C + 31) >> 5;
-        for (int w = 0; w < nwords; ++w) {
-            const int rnk = w * 32 + lane;
-            bool keep = false;
-            int slot = 0;
-            if (rnk < (int)C) {
-                slot = (int)(s_key[rnk] & 0xffffu);
-                const float4 r = s_rec[slot];
-                const float dx = fmaxf(fmaxf(bxl - r.x, r.x - bxh), 0.0f);
-                const float dy = fmaxf(fmaxf(byl - r.y, r.y - byh), 0.0f);
-                const float dz = fmaxf(fmaxf(bzl - r.z, r.z - bzh), 0.0f);
-                keep = (dx * dx + dy * dy + dz * dz) < cull2;
-                if (keep && s_ks[slot] <= k1) all_fma = false;
-            }
-            const uint32_t mword = __ballot_sync(0xffffffffu, keep);
-            if (keep) s_list[warp][nlist + __popc(mword & ((1u << lane) - 1u))] = (unsigned short)slot;
-            nlist += __popc(mword);
-        }
-        all_fma = __all_sync(0xffffffffu, all_fma);
-        __syncwarp();
-    }
-    // ---- ordered accumulation
-    if (GLOBAL) {
-        for (int n = 0; n < nlist; ++n) {
-            const int slot = s_list[warp][n];
-            ss_accumulate_global(P, s_rec[slot], s_imin[slot], s_dx0[slot], gi, gj, gk, phi, hits);
-        }
-    } else if (sparse) {
-        for (int n = 0; n < nlist; ++n) {
-            const int slot = s_list[warp][n];
-            ss_accumulate<true, false>(P, s_rec[slot], 0, k, gx, gy, gz, phi, hits);
-        }
-    } else if (all_fma) {
-        for (int n = 0; n < nlist; ++n) {
-            const int slot = s_list[warp][n];
-            ss_accumulate<false, true>(P, s_rec[slot], 0, k, gx, gy, gz, phi, hits);
-        }
-    } else {
-        for (int n = 0; n < nlist; ++n) {
-            const int slot = s_list[warp][n];
-            ss_accumulate<false, false>(P, s_rec[slot], s_ks[slot], k, gx, gy, gz, phi, hits);
-        }
-    }
-    if (valid) A.tiles[out_idx] = phi;
     if (COUNT && A.pairs) {
         unsigned long long np_ = hits;
         for (int o = 16; o > 0; o >>= 1) np_ += __shfl_xor_sync(0xffffffffu, np_, o);
         if (lane == 0 && np_) atomicAdd(A.pairs, np_);
     }
+}
+
+// Work list of the level-set launch: one thread per brick; listed when any of its candidate bins holds particles
+// (with extension bricks: bricks 0 .. nb-2 per axis, the last one looking one bin range further).
+__global__ void k_brick_worklist(SsDev P, const SsTile *__restrict__ tile_tab, const int2 *__restrict__ brick_rng,
+                                 const uint32_t *__restrict__ bin_start, uint32_t ntiles, uint32_t *__restrict__ flag) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t nb = (uint32_t)P.nb;
+    if (b >= ntiles * nb * nb * nb) return;
+    uint32_t q = b;
+    const int bz = (int)(q % nb); q /= nb;
+    const int by = (int)(q % nb); q /= nb;
+    const int bx = (int)(q % nb); const uint32_t tile = q / nb;
+    if (P.ext_bricks && (bx == (int)nb - 1 || by == (int)nb - 1 || bz == (int)nb - 1)) { flag[b] = 0; return; }
+    int2 rx = brick_rng[bx], ry = brick_rng[by], rz = brick_rng[bz];
+    if (P.ext_bricks) {
+        if (bx == (int)nb - 2) rx.y = brick_rng[bx + 1].y;
+        if (by == (int)nb - 2) ry.y = brick_rng[by + 1].y;
+        if (bz == (int)nb - 2) rz.y = brick_rng[bz + 1].y;
+    }
+    const uint32_t s = tile_tab[tile].s;
+    bool any = false;
+    for (int X = rx.x; X <= rx.y && !any; ++X) for (int Y = ry.x; Y <= ry.y && !any; ++Y) {
+        const uint32_t base = s * (uint32_t)P.nbin_sub + (uint32_t)((X * P.nbin + Y) * P.nbin);
+        for (int Z = rz.x; Z <= rz.y; ++Z) if (bin_start[base + Z] != 0xffffffffu) { any = true; break; }
+    }
+    flag[b] = any ? 1u : 0u;
 }
 
 // ------------------------------------------------------------------ brick-indexed tile passes ----

@@ -65,7 +65,7 @@ struct ss_context {
     // reusable scratch
     DevBuf xyz, xyz_f, filt_flag, filt_flag32, filt_off, aabb, cnt, off, key_a, key_b, val_a, val_b, cid, cub_tmp,
         sub_flat, sub_off, sub_sparse, sub_owned, gkey_a, gkey_b, gval_a, gval_b, flags, scan, spos, rho, tab_a, tab_b, rec, ksplit, batch_subs, tiles, vcnt,
-        tcnt, vmask, voff, vblk_off, tblk_off, tile_tab, brick_rng, bstate, flag_mc, flag_fix, off_mc, off_fix, list_mc, list_fix, wflag, brick_seen, fix_list, nflag, bkeys_a, bkeys_b, bids_a, bids_b, bcount, remap, keep, newid, err, pairs;
+        tcnt, vmask, voff, vblk_off, tblk_off, tile_tab, brick_rng, bstate, flag_ls, off_ls, list_ls, flag_mc, flag_fix, off_mc, off_fix, list_mc, list_fix, wflag, brick_seen, fix_list, nflag, bkeys_a, bkeys_b, bids_a, bids_b, bcount, remap, keep, newid, err, pairs;
     uint64_t launches = 0;
     // result buffers handed to surfaces and returned by ss_surface_free (avoids cudaMalloc/cudaFree per frame,
     // the analogue of the reference's ReconstructionWorkspace, workspace.rs:12-79)
@@ -205,7 +205,7 @@ extern "C" void ss_context_destroy(ss_context *c) {
     DevBuf *bufs[] = { &c->xyz, &c->xyz_f, &c->filt_flag, &c->filt_flag32, &c->filt_off, &c->aabb, &c->cnt, &c->off, &c->key_a, &c->key_b,
                        &c->val_a, &c->val_b, &c->cid, &c->cub_tmp, &c->sub_flat, &c->sub_off, &c->sub_sparse, &c->sub_owned, &c->gkey_a, &c->gkey_b, &c->gval_a, &c->gval_b, &c->flags, &c->scan,
                        &c->spos, &c->rho, &c->tab_a, &c->tab_b, &c->rec, &c->ksplit, &c->batch_subs, &c->tiles, &c->vcnt, &c->tcnt,
-                       &c->vmask, &c->voff, &c->vblk_off, &c->tblk_off, &c->tile_tab, &c->brick_rng, &c->bstate, &c->flag_mc, &c->flag_fix, &c->off_mc, &c->off_fix, &c->list_mc, &c->list_fix, &c->wflag, &c->brick_seen, &c->fix_list, &c->nflag, &c->bkeys_a, &c->bkeys_b, &c->bids_a, &c->bids_b, &c->bcount, &c->remap, &c->keep, &c->newid,
+                       &c->vmask, &c->voff, &c->vblk_off, &c->tblk_off, &c->tile_tab, &c->brick_rng, &c->bstate, &c->flag_ls, &c->off_ls, &c->list_ls, &c->flag_mc, &c->flag_fix, &c->off_mc, &c->off_fix, &c->list_mc, &c->list_fix, &c->wflag, &c->brick_seen, &c->fix_list, &c->nflag, &c->bkeys_a, &c->bkeys_b, &c->bids_a, &c->bids_b, &c->bcount, &c->remap, &c->keep, &c->newid,
                        &c->err, &c->pairs, &c->o_verts, &c->o_tris, &c->o_vkeys, &c->o_rho, &c->o_verts2, &c->o_vkeys2, &c->o_normals };
     for (DevBuf *b : bufs) b->release();
     for (auto &ev : c->ev) cudaEventDestroy(ev);
@@ -341,6 +341,20 @@ static void launch_levelset(ss_context *c, dim3 grid, const SsDev &D, const SsLs
     c->launches++;
 }
 
+// Work list of non-empty bricks for the level-set launch (k_brick_worklist + scan + compaction); returns its length.
+static uint32_t build_worklist(ss_context *c, const SsDev &D, uint32_t ntiles) {
+    const uint32_t nbr = ntiles * (uint32_t)(D.nb * D.nb * D.nb);
+    c->flag_ls.ensure((size_t)nbr * 4); c->off_ls.ensure((size_t)nbr * 4 + 4); c->list_ls.ensure((size_t)nbr * 4);
+    LAUNCH(c, k_brick_worklist, nblk(nbr, 256), 256, D, c->tile_tab.as<SsTile>(), c->brick_rng.as<int2>(), c->tab_a.as<uint32_t>(), ntiles, c->flag_ls.as<uint32_t>());
+    cub_excl_scan(c, c->flag_ls.as<uint32_t>(), c->off_ls.as<uint32_t>(), nbr);
+    LAUNCH(c, k_compact_list, nblk(nbr, 256), 256, c->flag_ls.as<uint32_t>(), c->off_ls.as<uint32_t>(), nbr, c->list_ls.as<uint32_t>());
+    uint32_t lc[2] = { 0, 0 };
+    CK(cudaMemcpyAsync(&lc[0], c->off_ls.as<uint32_t>() + (nbr - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&lc[1], c->flag_ls.as<uint32_t>() + (nbr - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return lc[0] + lc[1];
+}
+
 // kernel.rs:327-336 (AVX-path constants) and :61-66 (scalar normalisation), evaluated in f32 like the reference
 static void fill_kernel_consts(SsDev &D, float h) {
     D.a_hinv = fdivr(1.0f, h);
@@ -355,6 +369,7 @@ static void fill_kernel_consts(SsDev &D, float h) {
 // splat bins: cubes of `be` cells; a brick (8 points) gathers the bins overlapping [8b - R, 8b + 7 + R)
 static void fill_bins(SsDev &D, float cs) {
     D.nb = (D.np + 7) / 8;
+    D.ext_bricks = (D.nb >= 2 && D.np == 8 * (D.nb - 1) + 1) ? 1 : 0;
     D.be = 8 * std::max(1, (7 + 2 * D.R + 39) / 40);
     D.nlo = (D.R + D.be - 1) / D.be;
     D.nbin = ss_floor_div(D.S + D.R, D.be) + D.nlo + 1;
@@ -626,9 +641,10 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
         A.pairs = c->count_pairs ? c->pairs.as<unsigned long long>() : nullptr;
         A.mode = exact_all ? SS_LS_EXACT_ALL : SS_LS_CERTIFY;
         A.wflag = nullptr; A.fix_bricks = nullptr; A.bstate = c->bstate.as<uint8_t>();
-        const dim3 ls_grid((unsigned)D.nb, (unsigned)D.nb, (unsigned)D.nb * nbatch);
-        launch_levelset(c, ls_grid, D, A, c->count_pairs != 0, global_mode);
-        ++ls_launches;
+        const uint32_t n_work = build_worklist(c, D, nbatch);
+        A.work_list = c->list_ls.as<uint32_t>();
+        if (n_work) { launch_levelset(c, dim3(n_work), D, A, c->count_pairs != 0, global_mode); ++ls_launches; }
+        out->tm.bricks_levelset += n_work;
         // bricks that can carry surface (for marching cubes) / markers next to outside points (for the fix-up sweep)
         const uint32_t nbr_b = nbatch * nbricks;
         c->flag_mc.ensure((size_t)nbr_b * 4); c->flag_fix.ensure((size_t)nbr_b * 4); c->off_mc.ensure((size_t)nbr_b * 4 + 4); c->off_fix.ensure((size_t)nbr_b * 4 + 4);
@@ -870,7 +886,9 @@ extern "C" int ss_levelset_tile_f32(ss_context *c, const float *xyz, const float
             A.ksplit = c->ksplit.as<int>(); A.pidx = c->val_a.as<uint32_t>();
             A.tile_tab = c->tile_tab.as<SsTile>(); A.brick_rng = c->brick_rng.as<int2>(); A.tiles = c->tiles.as<float>();
             A.pairs = nullptr; A.wflag = nullptr; A.fix_bricks = nullptr; A.bstate = nullptr; A.mode = SS_LS_EXACT_ALL;
-            launch_levelset(c, dim3((unsigned)D.nb, (unsigned)D.nb, (unsigned)D.nb), D, A, false, false);
+            const uint32_t n_work = build_worklist(c, D, 1);
+            A.work_list = c->list_ls.as<uint32_t>();
+            if (n_work) launch_levelset(c, dim3(n_work), D, A, false, false);
             CK(cudaStreamSynchronize(st));
         }
         CK(cudaMemcpyAsync(tile_out, c->tiles.p, np3 * 4, cudaMemcpyDefault, st));
