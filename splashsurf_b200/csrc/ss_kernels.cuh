@@ -211,6 +211,7 @@ __global__ void k_gather_pos(const float *__restrict__ xyz, const uint32_t *__re
     out[e] = make_float4(xyz[3 * (uint64_t)p], xyz[3 * (uint64_t)p + 1], xyz[3 * (uint64_t)p + 2], __uint_as_float(p));
 }
 
+#define SS_NS_LIST 96
 // One thread per (subdomain, particle) membership in NS-sorted order.  Particles contained in the
 // subdomain's AABB get rho = m * (W(0) + sum_j W(|xj - xi|)) with neighbours visited in the reference's
 // order: 26 adjacent cells in x-major (-1,0,1)^3 order, then the own cell; ascending particle index
@@ -230,6 +231,11 @@ k_density(SsDev P, uint32_t m, const uint32_t *__restrict__ key, const float4 *_
     if (!inside) return;
     SsNsGrid ns = ss_ns_grid(P, g);
     int c0 = (int)cell / (P.nsD * P.nsD), c1 = ((int)cell / P.nsD) % P.nsD, c2 = (int)cell % P.nsD;
+    // Phase 1 collects the squared distances of the neighbours (d^2 < h^2) in visiting order, phase 2 evaluates the kernel
+    // over that list: the expensive evaluation is then not executed for every candidate of the warp (only ~15 % of the
+    // candidates of the 27 cells are neighbours), and the summation order is unchanged.
+    float d2list[SS_NS_LIST];
+    int nl = 0;
     float acc = ss_kernel_scalar(P, 0.0f);
     const uint32_t base = s * (uint32_t)P.ns_stride;
     for (int pass = 0; pass < 2; ++pass) {
@@ -247,10 +253,17 @@ k_density(SsDev P, uint32_t m, const uint32_t *__restrict__ key, const float4 *_
                 float4 pj = spos[t];
                 float dx = __fsub_rn(pj.x, pi.x), dy = __fsub_rn(pj.y, pi.y), dz = __fsub_rn(pj.z, pi.z);
                 float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                if (d2 < P.h2) acc = __fadd_rn(acc, ss_kernel_scalar(P, __fsqrt_rn(d2)));
+                if (d2 < P.h2) {
+                    if (nl == SS_NS_LIST) {          // list full (very dense cluster): drain it, order is preserved
+                        for (int n = 0; n < SS_NS_LIST; ++n) acc = __fadd_rn(acc, ss_kernel_scalar(P, __fsqrt_rn(d2list[n])));
+                        nl = 0;
+                    }
+                    d2list[nl++] = d2;
+                }
             }
         }
     }
+    for (int n = 0; n < nl; ++n) acc = __fadd_rn(acc, ss_kernel_scalar(P, __fsqrt_rn(d2list[n])));
     rho[__float_as_uint(pi.w)] = __fmul_rn(acc, P.rest_mass);
 }
 
