@@ -509,37 +509,44 @@ __device__ __forceinline__ float ss_box_dist2(const SsLanePoint &L, const float4
 }
 
 // Certification of one warp box: true when every valid lane is provably inside (see k_levelset).
-__device__ __forceinline__ bool ss_certify_box(const SsDev &P, const SsLanePoint &L, const float4 *s_rec, int C, int lane) {
-    const float cert = P.thr + fabsf(P.thr) * 1.0e-4f + 1.0e-30f;
+//
+// Lower bound of the kernel shape f(q) = W(q h) / sigma as a cubic in s = q^2 (so no square root is needed):
+//     g(s) = max(0, G0 + G1 s + G2 s^2 + G3 s^3) <= f(sqrt(s))   for all s >= 0
+// (tools/fit_kernel_bound.py: linear program over a fine grid; g captures 94 % of the kernel's volume integral, zero at
+// q = 0.755).  G0 carries an extra -1e-5 safety offset; the comparison keeps a 1e-4 relative margin on top.
+#define SS_G0 0.98199678f
+#define SS_G1 -4.74153665f
+#define SS_G2 8.78317336f
+#define SS_G3 -6.1170936f
+__device__ __forceinline__ bool ss_certify_box(const SsDev &P, const SsLanePoint &L, const float4 *s_rec, int C, int lane, int w0) {
+    const float cert = (P.thr + fabsf(P.thr) * 1.0e-4f + 1.0e-30f) / P.a_sigma;     // compare the un-normalised sum
+    const float inv_h2 = P.a_hinv * P.a_hinv;
     float sum = 0.0f;
     const int nwords = (C + 31) >> 5;
-    // ring 0: candidates within 0.55 h of the warp box (73 % of the kernel weight in bulk fluid); only if some lane
-    // is still short, ring 1: 0.55 h .. 0.8 h (98 %)
+    // ring 0: candidates within 0.55 h of the warp box; only if some lane is still short, ring 1: 0.55 h .. 0.8 h.
+    // Words are visited starting at the brick's own bin (closest particles first) and the warp stops as soon as every lane
+    // has enough.
     float r_lo2 = -1.0f, r_hi2 = 0.3025f * P.h2;
     for (int ring = 0; ring < 2; ++ring) {
-        for (int w = 0; w < nwords; ++w) {
+        for (int wi = 0; wi < nwords; ++wi) {
+            int w = wi + w0; if (w >= nwords) w -= nwords;
             const int c = w * 32 + lane;
             bool keep = false;
             if (c < C) { const float db2 = ss_box_dist2(L, s_rec[c]); keep = (db2 < r_hi2) && !(db2 < r_lo2); }
             uint32_t mword = __ballot_sync(0xffffffffu, keep);
+            if (!mword) continue;
             while (mword) {
                 const int cc = w * 32 + __ffs(mword) - 1;
                 mword &= mword - 1;
                 const float4 r = s_rec[cc];
                 const float dx = r.x - L.gx, dy = r.y - L.gy, dz = r.z - L.gz;
-                const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-                // cubic spline in v = max(1 - r/h, 0) (zero beyond h); any rounding is fine here: 1e-4 safety margin
-                const float q = d2 * rsqrtf(fmaxf(d2, 1.0e-30f)) * P.a_hinv;
-                const float v = fmaxf(1.0f - q, 0.0f);
-                const float v2 = v * v;
-                const float inner = fmaf(v, fmaf(v, fmaf(v, -6.0f, 12.0f), -6.0f), 1.0f);
-                const float wgt = (q <= 0.5f) ? inner : 2.0f * v2 * v;
-                sum = fmaf(wgt, r.w, sum);
+                const float sq = fmaf(dx, dx, fmaf(dy, dy, dz * dz)) * inv_h2;
+                const float g = fmaf(sq, fmaf(sq, fmaf(sq, SS_G3, SS_G2), SS_G1), SS_G0);
+                sum = fmaf(fmaxf(g, 0.0f), r.w, sum);
             }
+            // lanes outside the tile (clipped boxes) do not need a value
+            if (__all_sync(0xffffffffu, !L.valid || (sum > cert))) return true;
         }
-        // lanes outside the tile (clipped boxes) do not need a value
-        const bool ok = !L.valid || (sum * P.a_sigma > cert);
-        if (__all_sync(0xffffffffu, ok)) return true;
         r_lo2 = r_hi2; r_hi2 = 0.64f * P.h2;
     }
     return false;
@@ -751,16 +758,23 @@ k_levelset(SsDev P, SsLsArgs A) {
     __syncthreads();
 
     // ---- certification of the warp's main box and (if any) its extension box
+    // start the candidate sweep at the run that holds the brick's own bin
+    int w0;
+    {
+        const int ox = min(max(ss_floor_div(8 * bx, P.be) + P.nlo - rx.x, 0), rx.y - rx.x), oy = min(max(ss_floor_div(8 * by, P.be) + P.nlo - ry.x, 0), nyr - 1);
+        w0 = (int)(s_pre[ox * nyr + oy] >> 5);
+        if (w0 >= ((C + 31) >> 5)) w0 = 0;
+    }
     bool need_main, need_ext = false;
     {
         const SsLanePoint L = ss_lane_point(P, T, Wm, tile_idx, lane, sparse);
         need_main = L.warp_valid && my_flag;
-        if (mode == SS_LS_CERTIFY && L.warp_valid) need_main = !ss_certify_box(P, L, s_rec, C, lane);
+        if (mode == SS_LS_CERTIFY && L.warp_valid) need_main = !ss_certify_box(P, L, s_rec, C, lane, w0);
     }
     if (has_ext) {
         const SsLanePoint L = ss_lane_point(P, T, We, tile_idx, lane, sparse);
         need_ext = L.warp_valid;
-        if (mode == SS_LS_CERTIFY && L.warp_valid) need_ext = !ss_certify_box(P, L, s_rec, C, lane);
+        if (mode == SS_LS_CERTIFY && L.warp_valid) need_ext = !ss_certify_box(P, L, s_rec, C, lane, w0);
         if (need_ext && lane == 0) s_ext_need[ss_ext_group(warp)] = 1;
     }
     const int main_need = __syncthreads_or(need_main ? 1 : 0);
