@@ -132,6 +132,11 @@ int ss_grid_for_reconstruction_f32(ss_context *ctx, const float *xyz, uint64_t n
 int ss_reconstruct_partition_f32(ss_context *ctx, const float *xyz, uint64_t n, const ss_params_f32 *params,
                                  const ss_grid_f32 *grid, int axis, int64_t own_lo, int64_t own_hi, int64_t halo,
                                  uint64_t global_max_particles, int stop_after_decomposition, ss_surface **out);
+/* Same, in ONE call: after the decomposition the library calls `max_reduce(local_max, user)`, which must return the maximum
+ * over all ranks (e.g. an NCCL all-reduce issued by the caller), and continues with it. */
+int ss_reconstruct_partition_cb_f32(ss_context *ctx, const float *xyz, uint64_t n, const ss_params_f32 *params,
+                                    const ss_grid_f32 *grid, int axis, int64_t own_lo, int64_t own_hi, int64_t halo,
+                                    uint64_t (*max_reduce)(uint64_t local_max, void *user), void *user, ss_surface **out);
 uint64_t ss_surface_max_subdomain_particles(const ss_surface *s);
 const unsigned long long *ss_surface_device_vertex_keys(const ss_surface *s);   /* nv u64 MC edge keys, device memory */
 int ss_surface_copy_subdomain_owned(const ss_surface *s, uint8_t *dst);          /* 1: owned, 0: density-only halo */

@@ -386,6 +386,8 @@ struct Partition {
     int64_t halo = 0;                   // extra subdomain layers kept for densities only
     uint64_t global_max_particles = 0;  // max particles per subdomain over ALL ranks (0: use the local maximum)
     int stop_after_decomposition = 0;   // only report the local maximum (out->max_particles)
+    uint64_t (*max_reduce)(uint64_t local_max, void *user) = nullptr;   // all-reduce(MAX) of the local maximum across ranks
+    void *max_reduce_user = nullptr;
 };
 
 static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params_f32 *p, ss_surface *out, const Partition &part = Partition(),
@@ -501,6 +503,7 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     uint64_t maxp = 0;
     for (uint32_t s = 0; s < nsub; ++s) maxp = std::max<uint64_t>(maxp, h_off[s + 1] - h_off[s]);
     out->max_particles = maxp;
+    if (part.enabled && part.max_reduce) maxp = std::max<uint64_t>(maxp, part.max_reduce(maxp, part.max_reduce_user));
     if (part.enabled && part.global_max_particles) maxp = std::max<uint64_t>(maxp, part.global_max_particles);
     const uint64_t sparse_limit = std::max<uint64_t>(maxp / 20, 100);
     out->nsub = nsub; out->sub_flat.resize(nsub); out->sub_count.resize(nsub); out->sub_sparse.resize(nsub);
@@ -901,9 +904,22 @@ extern "C" int ss_levelset_tile_f32(ss_context *c, const float *xyz, const float
 }
 
 // ------------------------------------------------------------------ multi-GPU: one rank's slab of subdomains ----
+static int reconstruct_partition_impl(ss_context *c, const float *xyz, uint64_t n_in, const ss_params_f32 *p, const ss_grid_f32 *grid,
+                                      int axis, int64_t own_lo, int64_t own_hi, int64_t halo, uint64_t global_max_particles,
+                                      int stop_after_decomposition, uint64_t (*max_reduce)(uint64_t, void *), void *user, ss_surface **out);
 extern "C" int ss_reconstruct_partition_f32(ss_context *c, const float *xyz, uint64_t n_in, const ss_params_f32 *p, const ss_grid_f32 *grid,
                                             int axis, int64_t own_lo, int64_t own_hi, int64_t halo, uint64_t global_max_particles,
                                             int stop_after_decomposition, ss_surface **out) {
+    return reconstruct_partition_impl(c, xyz, n_in, p, grid, axis, own_lo, own_hi, halo, global_max_particles, stop_after_decomposition, nullptr, nullptr, out);
+}
+extern "C" int ss_reconstruct_partition_cb_f32(ss_context *c, const float *xyz, uint64_t n_in, const ss_params_f32 *p, const ss_grid_f32 *grid,
+                                               int axis, int64_t own_lo, int64_t own_hi, int64_t halo,
+                                               uint64_t (*max_reduce)(uint64_t local_max, void *user), void *user, ss_surface **out) {
+    return reconstruct_partition_impl(c, xyz, n_in, p, grid, axis, own_lo, own_hi, halo, 0, 0, max_reduce, user, out);
+}
+static int reconstruct_partition_impl(ss_context *c, const float *xyz, uint64_t n_in, const ss_params_f32 *p, const ss_grid_f32 *grid,
+                                      int axis, int64_t own_lo, int64_t own_hi, int64_t halo, uint64_t global_max_particles,
+                                      int stop_after_decomposition, uint64_t (*max_reduce)(uint64_t, void *), void *user, ss_surface **out) {
     if (!c || !out || !grid) return ss_fail(SS_ERR_INVALID_PARAMETER, "NULL argument");
     *out = nullptr;
     int rc = validate_params(p);
@@ -925,6 +941,7 @@ extern "C" int ss_reconstruct_partition_f32(ss_context *c, const float *xyz, uin
         Partition part;
         part.enabled = 1; part.axis = axis; part.own_lo = own_lo; part.own_hi = own_hi; part.halo = halo;
         part.global_max_particles = global_max_particles; part.stop_after_decomposition = stop_after_decomposition;
+        part.max_reduce = max_reduce; part.max_reduce_user = user;
         rc = run_subdomain_grid(c, P, p, s, part);
         if (rc) { ss_surface_free(s); return rc; }
         float ms = 0.f;

@@ -85,13 +85,12 @@ def owner_layer(x_axis: torch.Tensor, gmin: float, sub_size: float) -> torch.Ten
 
 def exchange_particles(x_local: torch.Tensor, layer: torch.Tensor, plan: SlabPlan, world: int, group=None):
     """Variable all-to-all: returns (particles for this rank in ascending global order, counts received per source)."""
-    sel, counts = [], []
-    for r in range(world):
-        lo, hi = plan.recv_range(r)
-        m = (layer >= lo) & (layer < hi)
-        sel.append(x_local[m])
-        counts.append(int(m.sum().item()))
-    send = torch.cat(sel, dim=0).contiguous() if sel else x_local[:0]
+    los = torch.tensor([plan.recv_range(r)[0] for r in range(world)], dtype=torch.int64, device=x_local.device)
+    his = torch.tensor([plan.recv_range(r)[1] for r in range(world)], dtype=torch.int64, device=x_local.device)
+    masks = (layer[None, :] >= los[:, None]) & (layer[None, :] < his[:, None])          # (world, n)
+    idx = torch.nonzero(masks)                                                           # row-major: by rank, then ascending index
+    send = x_local[idx[:, 1]].contiguous()
+    counts = [int(v) for v in masks.sum(dim=1).tolist()]
     cnt_in = torch.tensor(counts, dtype=torch.int64, device=x_local.device)
     cnt_out = torch.empty(world, dtype=torch.int64, device=x_local.device)
     dist.all_to_all_single(cnt_out, cnt_in, group=group)
@@ -103,6 +102,9 @@ def exchange_particles(x_local: torch.Tensor, layer: torch.Tensor, plan: SlabPla
 
 
 # ---------------------------------------------------------------------------- device helpers ----
+_MAXCB = C.CFUNCTYPE(C.c_uint64, C.c_uint64, C.c_void_p)
+
+
 class _CudaView:
     """Zero-copy torch view of device memory owned by the C library (via __cuda_array_interface__)."""
 
@@ -218,21 +220,20 @@ class Runner:
         recv, counts = exchange_particles(xd, layer, plan, world, self.group)
         t_ev[1].record()
         own_lo, own_hi = plan.own(rank)
-        # 4. local maximum subdomain population -> global (sparse rule, dense_subdomains.rs:1242-1251)
+        # 4./5. this rank's slab; the library calls back for the global maximum subdomain population (sparse rule,
+        # dense_subdomains.rs:1242-1251) right after its decomposition
         torch.cuda.synchronize()
+
+        def _max_cb(local_max, _user):
+            t = torch.tensor([int(local_max)], dtype=torch.int64, device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            return int(t.item())
+
+        cb = _MAXCB(_max_cb)
+        pre_launches = 0
         s = C.c_void_p()
-        rc = L.ss_reconstruct_partition_f32(self.ctx._h, C.c_void_p(recv.data_ptr()), C.c_uint64(recv.shape[0]), C.byref(p),
-                                            C.byref(grid), ax, own_lo, own_hi, plan.halo, C.c_uint64(0), 1, C.byref(s))
-        if rc:
-            raise RuntimeError((L.ss_last_error() or b"").decode())
-        gmax = torch.tensor([L.ss_surface_max_subdomain_particles(s)], dtype=torch.int64, device=self.device)
-        pre_launches = int(self.ctx.timings(s)["kernel_launches"])
-        self.ctx.free_surface(s)
-        dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=self.group)
-        # 5. this rank's slab
-        s = C.c_void_p()
-        rc = L.ss_reconstruct_partition_f32(self.ctx._h, C.c_void_p(recv.data_ptr()), C.c_uint64(recv.shape[0]), C.byref(p),
-                                            C.byref(grid), ax, own_lo, own_hi, plan.halo, C.c_uint64(int(gmax.item())), 0, C.byref(s))
+        rc = L.ss_reconstruct_partition_cb_f32(self.ctx._h, C.c_void_p(recv.data_ptr()), C.c_uint64(recv.shape[0]), C.byref(p),
+                                               C.byref(grid), ax, own_lo, own_hi, plan.halo, C.cast(cb, C.c_void_p), None, C.byref(s))
         if rc:
             raise RuntimeError((L.ss_last_error() or b"").decode())
         try:
