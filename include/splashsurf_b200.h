@@ -62,7 +62,7 @@ typedef struct ss_params_f32 {
     int32_t spatial_decomposition;       /* 0: SpatialDecomposition::None, 1: UniformGrid */
     uint32_t subdomain_num_cubes_per_dim;
     int32_t auto_disable;                /* GridDecompositionParameters::auto_disable */
-    int32_t global_neighborhood_list;    /* must be 0 in this build (SS_ERR_UNSUPPORTED otherwise) */
+    int32_t global_neighborhood_list;    /* Parameters::global_neighborhood_list: also return the per-particle neighbour lists */
 } ss_params_f32;
 
 /* Mirrors UniformCartesianCubeGrid3d<i64, f32> (uniform_grid.rs:132-142). */
@@ -167,6 +167,10 @@ int ss_surface_copy_triangles_u32(const ss_surface *s, uint32_t *dst);      /* m
 int ss_surface_copy_triangles_u64(const ss_surface *s, uint64_t *dst);      /* same, usize like the reference */
 int ss_surface_copy_particle_densities(const ss_surface *s, float *dst);    /* ::particle_densities */
 int ss_surface_copy_particle_inside_aabb(const ss_surface *s, uint8_t *dst);/* ::particle_inside_aabb (n input) */
+/* SurfaceReconstruction::particle_neighbors (only with global_neighborhood_list): CSR -- offsets has num_particles + 1
+ * entries, indices holds global particle indices in the reference's visiting order (neighborhood_search.rs:396-433). */
+uint64_t ss_surface_num_neighbors(const ss_surface *s);
+int ss_surface_copy_neighbor_lists(const ss_surface *s, uint64_t *offsets, uint32_t *indices);
 /* Device-resident views (valid until ss_surface_free): vertices nv x 3 f32, triangles nt x 3 u32. */
 const float *ss_surface_device_vertices(const ss_surface *s);
 const uint32_t *ss_surface_device_triangles(const ss_surface *s);

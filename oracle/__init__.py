@@ -69,7 +69,7 @@ def lib():
         L = C.CDLL(so)
         L.so_reconstruct.restype = C.c_int
         L.so_reconstruct.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(_Params), C.POINTER(C.POINTER(_Result)),
-                                     C.c_int64, C.c_void_p, C.c_void_p]
+                                     C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.so_free.argtypes = [C.POINTER(_Result)]
         L.so_levelset_tile.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_float,
                                        C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_float, C.c_int]
@@ -99,7 +99,7 @@ def absolute_params(particle_radius, smoothing_length, cube_size):
 def reconstruct(particles, *, particle_radius, smoothing_length, cube_size, rest_density=1000.0,
                 iso_surface_threshold=0.6, aabb_min=None, aabb_max=None, simd=True, subdomain_grid=True,
                 subdomain_grid_auto_disable=True, subdomain_num_cubes_per_dim=64, multi_threading=True, tile_of_subdomain=None,
-                want_neighbor_counts=False, num_threads=None):
+                want_neighbor_counts=False, want_neighbors=False, num_threads=None):
     """C-oracle counterpart of pysplashsurf.reconstruct_surface (same RELATIVE smoothing_length / cube_size).
     `multi_threading` is accepted and ignored: the global path is restated with its sequential (deterministic) semantics."""
     L = lib()
@@ -118,11 +118,20 @@ def reconstruct(particles, *, particle_radius, smoothing_length, cube_size, rest
     p.subdomain_num_cubes_per_dim, p.auto_disable = int(subdomain_num_cubes_per_dim), int(subdomain_grid_auto_disable)
     S = int(subdomain_num_cubes_per_dim)
     tile = np.zeros((S + 1,) * 3, dtype=np.float32) if tile_of_subdomain is not None else None
-    ncnt = np.zeros(len(xyz), dtype=np.int64) if want_neighbor_counts else None
+    ncnt = np.zeros(len(xyz), dtype=np.int64) if (want_neighbor_counts or want_neighbors) else None
     out = C.POINTER(_Result)()
     rc = L.so_reconstruct(xyz.ctypes.data, len(xyz), C.byref(p), C.byref(out),
                           -1 if tile_of_subdomain is None else int(tile_of_subdomain),
-                          None if tile is None else tile.ctypes.data, None if ncnt is None else ncnt.ctypes.data)
+                          None if tile is None else tile.ctypes.data, None if ncnt is None else ncnt.ctypes.data, None, None)
+    nbr = None
+    if want_neighbors and rc == 0 and not p.has_particle_aabb:
+        # second pass: fill the CSR lists with the offsets from the counts of the first pass
+        L.so_free(out)
+        off = np.concatenate([[0], np.cumsum(ncnt)]).astype(np.int64)
+        idx = np.zeros(max(int(off[-1]), 1), dtype=np.int64)
+        out = C.POINTER(_Result)()
+        rc = L.so_reconstruct(xyz.ctypes.data, len(xyz), C.byref(p), C.byref(out), -1, None, ncnt.ctypes.data, off.ctypes.data, idx.ctypes.data)
+        nbr = (off, idx[:int(off[-1])])
     try:
         res = out.contents
         d = {"rc": rc, "grid": _grid_dict(res.grid), "used_decomposition": bool(res.used_decomposition)}
@@ -141,7 +150,7 @@ def reconstruct(particles, *, particle_radius, smoothing_length, cube_size, rest
         d["subdomain_count"] = np.ctypeslib.as_array(res.subdomain_count, (ns,)).copy() if ns else np.zeros(0, np.uint64)
         d["subdomain_sparse"] = np.ctypeslib.as_array(res.subdomain_sparse, (ns,)).astype(bool).copy() if ns else np.zeros(0, bool)
         d["max_particles"], d["sparse_limit"] = int(res.max_particles), int(res.sparse_limit)
-        d["tile"], d["neighbor_counts"] = tile, ncnt
+        d["tile"], d["neighbor_counts"], d["neighbors"] = tile, ncnt, nbr
         return d
     finally:
         L.so_free(out)

@@ -277,7 +277,7 @@ static void unflatten_sub(const so_grid *sg, int64_t flat, int64_t ijk[3]) {
 /* dense_subdomains.rs:496-646 + neighborhood_search.rs:345-438 + density_map.rs:150-186 */
 static void subdomain_densities(const float *xyz, const so_grid *sg, const int64_t sijk[3],
                                 const uint64_t *mem, uint64_t nm, float h, float margin, float rest_mass,
-                                float *global_rho, int64_t *neighbor_counts) {
+                                float *global_rho, int64_t *neighbor_counts, const int64_t *nbr_off, int64_t *nbr_out) {
     float smin[3], smax[3], mmin[3], mmax[3];
     float grow = margin * 1.5f;
     for (int d = 0; d < 3; ++d) {
@@ -333,7 +333,7 @@ static void subdomain_densities(const float *xyz, const so_grid *sg, const int64
                 const float *pj = xyz + 3 * mem[b];
                 float dx = pj[0] - pi[0], dy = pj[1] - pi[1], dz = pj[2] - pi[2];
                 float d2 = dx * dx + dy * dy + dz * dz;
-                if (d2 < h2) { rho += k_scalar_eval(&kern, sqrtf(d2)); ++nn; }
+                if (d2 < h2) { rho += k_scalar_eval(&kern, sqrtf(d2)); if (nbr_out) nbr_out[nbr_off[mem[a]] + nn] = (int64_t)mem[b]; ++nn; }
             }
         }
         rho *= rest_mass;
@@ -567,7 +567,8 @@ static void stitch(so_result *res, so_patch *patches, uint64_t npatch) {
  *   sequential_compute_particle_densities (density_map.rs:130-186),
  *   sequential_generate_sparse_density_map (density_map.rs:370-412, support loop :677-736),
  *   construct_mc_input + triangulate (marching_cubes/narrow_band_extraction.rs:51-219, triangulation.rs:23-57). */
-static int reconstruct_global(so_result *res, const float *xyz, uint64_t n, const so_params *p, const so_grid *g) {
+static int reconstruct_global(so_result *res, const float *xyz, uint64_t n, const so_params *p, const so_grid *g,
+                              int64_t *neighbor_counts, const int64_t *nbr_off, int64_t *nbr_out) {
     const float h = p->compact_support_radius, c = p->cube_size, thr = p->iso_surface_threshold;
     float r2 = p->particle_radius + p->particle_radius;
     const float rest_mass = (r2 * r2 * r2) * p->rest_density;
@@ -598,6 +599,7 @@ static int reconstruct_global(so_result *res, const float *xyz, uint64_t n, cons
             int64_t cc[3];
             for (int d = 0; d < 3; ++d) cc[d] = grid_cell_of(&ns, d, pi[d]);
             float rho = k_scalar_eval(&kern, 0.0f);
+            int64_t nn = 0;
             for (int pass = 0; pass < 2; ++pass)
             for (int sx = -1; sx <= 1; ++sx) for (int sy = -1; sy <= 1; ++sy) for (int sz = -1; sz <= 1; ++sz) {
                 int self = (sx == 0 && sy == 0 && sz == 0);
@@ -611,10 +613,11 @@ static int reconstruct_global(so_result *res, const float *xyz, uint64_t n, cons
                     const float *pj = xyz + 3 * b;
                     float dx = pj[0] - pi[0], dy = pj[1] - pi[1], dz = pj[2] - pi[2];
                     float d2 = dx * dx + dy * dy + dz * dz;
-                    if (d2 < h2) rho += k_scalar_eval(&kern, sqrtf(d2));
+                    if (d2 < h2) { rho += k_scalar_eval(&kern, sqrtf(d2)); if (nbr_out) nbr_out[nbr_off[a] + nn] = (int64_t)b; ++nn; }
                 }
             }
             res->densities[a] = rho * rest_mass;
+            if (neighbor_counts) neighbor_counts[a] = nn;
         }
         free(order); free(cell_of); free(cstart);
     }
@@ -757,6 +760,7 @@ typedef struct {
     const float *xyz; const so_grid *sg, *gg; const so_decomp *dc; so_result *res; const so_params *p;
     float h, c, thr, margin, rest_mass; int64_t S; uint64_t sparse_limit;
     int64_t *neighbor_counts; int64_t tile_sub_flat; float *tile_out; so_patch *patches;
+    const int64_t *nbr_off; int64_t *nbr_out;
 } so_job;
 
 static void density_task(int64_t s, void *ctx, void **tls) {
@@ -765,7 +769,7 @@ static void density_task(int64_t s, void *ctx, void **tls) {
     int64_t sijk[3]; unflatten_sub(jb->sg, jb->dc->flat[s], sijk);
     subdomain_densities(jb->xyz, jb->sg, sijk, jb->dc->members + jb->dc->offset[s],
                         jb->dc->offset[s + 1] - jb->dc->offset[s], jb->h, jb->margin, jb->rest_mass,
-                        jb->res->densities, jb->neighbor_counts);
+                        jb->res->densities, jb->neighbor_counts, jb->nbr_off, jb->nbr_out);
 }
 
 static void recon_task(int64_t s, void *ctx, void **tls) {
@@ -799,7 +803,7 @@ void so_free(so_result *r) {
 /* Optional debug taps: if tile_sub_flat >= 0, the level-set tile of that subdomain is copied to tile_out
  * ((S+1)^3 floats). */
 int so_reconstruct(const float *xyz_in, uint64_t n_in, const so_params *p, so_result **out,
-                   int64_t tile_sub_flat, float *tile_out, int64_t *neighbor_counts) {
+                   int64_t tile_sub_flat, float *tile_out, int64_t *neighbor_counts, const int64_t *nbr_off, int64_t *nbr_out) {
     so_result *res = (so_result *)calloc(1, sizeof(so_result));
     *out = res;
     /* lib.rs:369-406 particle AABB filter (half-open contains_point) */
@@ -831,7 +835,7 @@ int so_reconstruct(const float *xyz_in, uint64_t n_in, const so_params *p, so_re
         } else use_dec = 1;
     }
     res->used_decomposition = use_dec;
-    if (!use_dec) { int rcg = reconstruct_global(res, xyz, n, p, &g0); free(filtered); return rcg; }
+    if (!use_dec) { int rcg = reconstruct_global(res, xyz, n, p, &g0, neighbor_counts, nbr_off, nbr_out); free(filtered); return rcg; }
 
     /* dense_subdomains.rs:89-244 initialize_parameters */
     int64_t S = (int64_t)p->subdomain_num_cubes_per_dim;
@@ -867,7 +871,7 @@ int so_reconstruct(const float *xyz_in, uint64_t n_in, const so_params *p, so_re
     job.xyz = xyz; job.sg = &sg; job.gg = &gg; job.dc = &dc; job.res = res; job.p = p;
     job.h = h; job.c = c; job.thr = thr; job.margin = margin; job.rest_mass = rest_mass; job.S = S;
     job.sparse_limit = sparse_limit; job.neighbor_counts = neighbor_counts;
-    job.tile_sub_flat = tile_sub_flat; job.tile_out = tile_out;
+    job.tile_sub_flat = tile_sub_flat; job.tile_out = tile_out; job.nbr_off = nbr_off; job.nbr_out = nbr_out;
     parallel_for((int64_t)dc.nsub, density_task, &job);
 
     so_patch *patches = (so_patch *)calloc(dc.nsub ? dc.nsub : 1, sizeof(so_patch));

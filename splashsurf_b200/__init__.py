@@ -99,6 +99,9 @@ def load_library():
         getattr(L, name).argtypes = [vp]
         getattr(L, name).restype = vp
     L.ss_surface_copy_subdomains.argtypes = [vp, vp, vp, vp]
+    L.ss_surface_num_neighbors.argtypes = [vp]
+    L.ss_surface_num_neighbors.restype = u64
+    L.ss_surface_copy_neighbor_lists.argtypes = [vp, vp, vp]
     L.ss_context_keep_levelset_tile.argtypes = [vp, i64]
     L.ss_surface_timings.argtypes = [vp, C.POINTER(_Timings)]
     L.ss_context_set_tile_batch.argtypes = [vp, C.c_uint32]
@@ -163,6 +166,22 @@ class TriMesh3d:
     @property
     def ncells(self) -> int:
         return len(self.triangles)
+
+
+class NeighborhoodLists:
+    """Mirrors pysplashsurf.NeighborhoodLists on top of CSR arrays (offsets, indices)."""
+
+    def __init__(self, offsets: np.ndarray, indices: np.ndarray):
+        self.offsets, self.indices = offsets, indices
+
+    def __len__(self) -> int:
+        return len(self.offsets) - 1
+
+    def __getitem__(self, idx: int) -> list:
+        return self.indices[int(self.offsets[idx]):int(self.offsets[idx + 1])].tolist()
+
+    def get_neighborhood_lists(self) -> list:
+        return [self[i] for i in range(len(self))]
 
 
 @dataclass
@@ -328,6 +347,11 @@ def _collect(ctx: Context, s, n_in: int, p: _Params, debug: bool, tile: bool) ->
         inside = inside.astype(bool)
     res = SurfaceReconstruction(mesh=TriMesh3d(verts, tris), grid=UniformGrid._from(g), subdomain_grid=sub,
                                 particle_densities=dens, particle_inside_aabb=inside, timings=ctx.timings(s))
+    if p.global_neighborhood_list:
+        off = np.empty(n + 1, dtype=np.uint64)
+        idx = np.empty(L.ss_surface_num_neighbors(s), dtype=np.uint32)
+        _check(L, L.ss_surface_copy_neighbor_lists(s, off.ctypes.data, idx.ctypes.data if len(idx) else None))
+        res.particle_neighbors = NeighborhoodLists(off, idx)
     if debug:
         keys = np.empty((nv, 4), dtype=np.int64)
         _check(L, L.ss_surface_copy_vertex_edge_keys(s, keys.ctypes.data))

@@ -216,10 +216,15 @@ __global__ void k_gather_pos(const float *__restrict__ xyz, const uint32_t *__re
 // subdomain's AABB get rho = m * (W(0) + sum_j W(|xj - xi|)) with neighbours visited in the reference's
 // order: 26 adjacent cells in x-major (-1,0,1)^3 order, then the own cell; ascending particle index
 // inside a cell (neighborhood_search.rs:396-433, density_map.rs:169-185).
+// FILL = false: densities (+ optional neighbour counts); FILL = true: writes the neighbour indices (global particle ids, in
+// the reference's order) into the CSR array prepared from those counts (Parameters::global_neighborhood_list,
+// dense_subdomains.rs:617-639).
+template <bool FILL>
 __global__ void __launch_bounds__(128)
 k_density(SsDev P, uint32_t m, const uint32_t *__restrict__ key, const float4 *__restrict__ spos,
           const uint32_t *__restrict__ sub_flat, const uint32_t *__restrict__ cstart, const uint32_t *__restrict__ cend,
-          float *__restrict__ rho) {
+          float *__restrict__ rho, unsigned long long *__restrict__ nbr_count, const unsigned long long *__restrict__ nbr_off,
+          uint32_t *__restrict__ nbr_idx) {
     uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= m) return;
     uint32_t k = key[e];
@@ -234,8 +239,10 @@ k_density(SsDev P, uint32_t m, const uint32_t *__restrict__ key, const float4 *_
     // Phase 1 collects the squared distances of the neighbours (d^2 < h^2) in visiting order, phase 2 evaluates the kernel
     // over that list: the expensive evaluation is then not executed for every candidate of the warp (only ~15 % of the
     // candidates of the 27 cells are neighbours), and the summation order is unchanged.
-    float d2list[SS_NS_LIST];
+    float d2list[FILL ? 1 : SS_NS_LIST];
     int nl = 0;
+    unsigned long long ncount = 0;
+    const unsigned long long fill_base = FILL ? nbr_off[__float_as_uint(pi.w)] : 0ull;
     float acc = ss_kernel_scalar(P, 0.0f);
     const uint32_t base = s * (uint32_t)P.ns_stride;
     for (int pass = 0; pass < 2; ++pass) {
@@ -254,6 +261,8 @@ k_density(SsDev P, uint32_t m, const uint32_t *__restrict__ key, const float4 *_
                 float dx = __fsub_rn(pj.x, pi.x), dy = __fsub_rn(pj.y, pi.y), dz = __fsub_rn(pj.z, pi.z);
                 float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
                 if (d2 < P.h2) {
+                    if (FILL) { nbr_idx[fill_base + ncount] = __float_as_uint(pj.w); ++ncount; continue; }
+                    ++ncount;
                     if (nl == SS_NS_LIST) {          // list full (very dense cluster): drain it, order is preserved
                         for (int n = 0; n < SS_NS_LIST; ++n) acc = __fadd_rn(acc, ss_kernel_scalar(P, __fsqrt_rn(d2list[n])));
                         nl = 0;
@@ -263,7 +272,9 @@ k_density(SsDev P, uint32_t m, const uint32_t *__restrict__ key, const float4 *_
             }
         }
     }
+    if (FILL) return;
     for (int n = 0; n < nl; ++n) acc = __fadd_rn(acc, ss_kernel_scalar(P, __fsqrt_rn(d2list[n])));
+    if (nbr_count) nbr_count[__float_as_uint(pi.w)] = ncount;
     rho[__float_as_uint(pi.w)] = __fmul_rn(acc, P.rest_mass);
 }
 
@@ -284,9 +295,11 @@ __global__ void k_ns_keys_global(SsDev P, const float *__restrict__ xyz, uint32_
     key[p] = (uint32_t)((c[0] * P.g_ns_nc[1] + c[1]) * P.g_ns_nc[2] + c[2]);
     idx[p] = p;
 }
+template <bool FILL>
 __global__ void __launch_bounds__(128)
 k_density_global(SsDev P, uint32_t n, const uint32_t *__restrict__ key, const float4 *__restrict__ spos,
-                 const uint32_t *__restrict__ cstart, const uint32_t *__restrict__ cend, float *__restrict__ rho) {
+                 const uint32_t *__restrict__ cstart, const uint32_t *__restrict__ cend, float *__restrict__ rho,
+                 unsigned long long *__restrict__ nbr_count, const unsigned long long *__restrict__ nbr_off, uint32_t *__restrict__ nbr_idx) {
     uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     const int cell = (int)key[e];
@@ -294,6 +307,8 @@ k_density_global(SsDev P, uint32_t n, const uint32_t *__restrict__ key, const fl
     const int c0 = cell / (n1 * n2), c1 = (cell / n2) % n1, c2 = cell % n2;
     const float4 pi = spos[e];
     float acc = ss_kernel_scalar(P, 0.0f);
+    unsigned long long ncount = 0;
+    const unsigned long long fill_base = FILL ? nbr_off[__float_as_uint(pi.w)] : 0ull;
     for (int pass = 0; pass < 2; ++pass) {
         for (int sx = -1; sx <= 1; ++sx) for (int sy = -1; sy <= 1; ++sy) for (int sz = -1; sz <= 1; ++sz) {
             bool self = (sx == 0 && sy == 0 && sz == 0);
@@ -309,11 +324,17 @@ k_density_global(SsDev P, uint32_t n, const uint32_t *__restrict__ key, const fl
                 float4 pj = spos[t];
                 float dx = __fsub_rn(pj.x, pi.x), dy = __fsub_rn(pj.y, pi.y), dz = __fsub_rn(pj.z, pi.z);
                 float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                if (d2 < P.h2) acc = __fadd_rn(acc, ss_kernel_scalar(P, __fsqrt_rn(d2)));
+                if (d2 < P.h2) {
+                    if (FILL) nbr_idx[fill_base + ncount] = __float_as_uint(pj.w);
+                    else acc = __fadd_rn(acc, ss_kernel_scalar(P, __fsqrt_rn(d2)));
+                    ++ncount;
+                }
             }
         }
     }
+    if (FILL) return;
     rho[__float_as_uint(pi.w)] = __fmul_rn(acc, P.rest_mass);
+    if (nbr_count) nbr_count[__float_as_uint(pi.w)] = ncount;
 }
 
 // ------------------------------------------------------------------ splat binning ----

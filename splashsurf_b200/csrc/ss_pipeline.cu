@@ -85,8 +85,9 @@ struct ss_surface {
     int used_decomposition = 0;
     HostGrid grid{}, subgrid{};
     int S = 0;
-    DevBuf verts, tris, vkeys, rho, normals;
-    int has_normals = 0;
+    DevBuf verts, tris, vkeys, rho, normals, nbr_off, nbr_idx;
+    int has_normals = 0, has_neighbors = 0;
+    uint64_t n_neighbors = 0;
     std::vector<uint8_t> inside_aabb;
     std::vector<int64_t> sub_flat; std::vector<uint64_t> sub_count; std::vector<uint8_t> sub_sparse, sub_owned;
     uint64_t max_particles = 0;
@@ -135,7 +136,6 @@ static int validate_params(const ss_params_f32 *p) {
     if (!(p->cube_size > 0.0f)) return ss_fail(SS_ERR_INVALID_CELL_SIZE, "invalid cell size supplied, cell size has to be larger than zero");
     if (!(p->compact_support_radius > 0.0f)) return ss_fail(SS_ERR_INVALID_PARAMETER, "compact support radius has to be positive (search radius for neighborhood search has to be positive)");
     if (!(p->particle_radius > 0.0f)) return ss_fail(SS_ERR_INVALID_PARAMETER, "particle radius has to be positive");
-    if (p->global_neighborhood_list) return ss_fail(SS_ERR_UNSUPPORTED, "global_neighborhood_list is not provided by the device path");
     if (p->spatial_decomposition == 1 && p->subdomain_num_cubes_per_dim < 1) return ss_fail(SS_ERR_INVALID_PARAMETER, "subdomain_num_cubes_per_dim has to be >= 1");
     return SS_OK;
 }
@@ -341,6 +341,19 @@ static void launch_levelset(ss_context *c, dim3 grid, const SsDev &D, const SsLs
     c->launches++;
 }
 
+// in-place exclusive scan of the per-particle neighbour counts (n + 1 entries, last = 0) -> CSR offsets; returns the total
+static uint64_t scan_neighbor_counts(ss_context *c, unsigned long long *cnt, uint64_t n) {
+    size_t tmp = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, cnt, cnt, (int)(n + 1), c->stream));
+    c->cub_tmp.ensure(tmp);
+    CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, cnt, cnt, (int)(n + 1), c->stream));
+    c->launches += 2;
+    unsigned long long total = 0;
+    CK(cudaMemcpyAsync(&total, cnt + n, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return total;
+}
+
 // Work list of non-empty bricks for the level-set launch (k_brick_worklist + scan + compaction); returns its length.
 static uint32_t build_worklist(ss_context *c, const SsDev &D, uint32_t ntiles) {
     const uint32_t nbr = ntiles * (uint32_t)(D.nb * D.nb * D.nb);
@@ -459,6 +472,7 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
         if (per_axis * per_axis > 128) return ss_fail(SS_ERR_INVALID_PARAMETER, "internal: too many candidate bin runs per brick");
     }
 
+    const bool want_nbrs = p->global_neighborhood_list != 0 && !part.enabled;
     CK(cudaEventRecord(c->ev[2], st));
     out->nv = out->nt = 0; out->nsub = 0;
     out->owner = c;
@@ -546,8 +560,17 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     LAUNCH(c, k_run_counts, nblk(M, 256), 256, c->key_b.as<uint32_t>(), M, c->tab_b.as<uint32_t>(), (uint32_t)ns_keys);
     c->spos.ensure((size_t)M * 16);
     LAUNCH(c, k_gather_pos, nblk(M, 256), 256, d_xyz, c->val_a.as<uint32_t>(), M, c->spos.as<float4>());
-    LAUNCH(c, k_density, nblk(M, 128), 128, D, M, c->key_b.as<uint32_t>(), c->spos.as<float4>(), c->sub_flat.as<uint32_t>(),
-           c->tab_a.as<uint32_t>(), c->tab_b.as<uint32_t>(), d_rho);
+    unsigned long long *d_ncnt = nullptr;
+    if (want_nbrs) { out->nbr_off.ensure((n + 1) * 8); d_ncnt = out->nbr_off.as<unsigned long long>(); CK(cudaMemsetAsync(d_ncnt, 0, (n + 1) * 8, st)); }
+    LAUNCH(c, k_density<false>, nblk(M, 128), 128, D, M, c->key_b.as<uint32_t>(), c->spos.as<float4>(), c->sub_flat.as<uint32_t>(),
+           c->tab_a.as<uint32_t>(), c->tab_b.as<uint32_t>(), d_rho, d_ncnt, (const unsigned long long *)nullptr, (uint32_t *)nullptr);
+    if (want_nbrs) {
+        const uint64_t total = scan_neighbor_counts(c, d_ncnt, n);
+        out->nbr_idx.ensure(std::max<uint64_t>(total, 1) * 4);
+        LAUNCH(c, k_density<true>, nblk(M, 128), 128, D, M, c->key_b.as<uint32_t>(), c->spos.as<float4>(), c->sub_flat.as<uint32_t>(),
+               c->tab_a.as<uint32_t>(), c->tab_b.as<uint32_t>(), d_rho, (unsigned long long *)nullptr, (const unsigned long long *)d_ncnt, out->nbr_idx.as<uint32_t>());
+        out->has_neighbors = 1; out->n_neighbors = total;
+    }
     } else {
         // one cell list over the whole domain; particles (not memberships) are the entries
         const uint32_t n32 = (uint32_t)n;
@@ -560,8 +583,17 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
         LAUNCH(c, k_run_counts, nblk(n32, 256), 256, c->gkey_b.as<uint32_t>(), n32, c->tab_b.as<uint32_t>(), (uint32_t)g_ns_cells);
         c->spos.ensure((size_t)n32 * 16);
         LAUNCH(c, k_gather_pos, nblk(n32, 256), 256, d_xyz, c->gval_b.as<uint32_t>(), n32, c->spos.as<float4>());
-        LAUNCH(c, k_density_global, nblk(n32, 128), 128, D, n32, c->gkey_b.as<uint32_t>(), c->spos.as<float4>(), c->tab_a.as<uint32_t>(),
-               c->tab_b.as<uint32_t>(), d_rho);
+        unsigned long long *d_ncnt = nullptr;
+        if (want_nbrs) { out->nbr_off.ensure((n + 1) * 8); d_ncnt = out->nbr_off.as<unsigned long long>(); CK(cudaMemsetAsync(d_ncnt, 0, (n + 1) * 8, st)); }
+        LAUNCH(c, k_density_global<false>, nblk(n32, 128), 128, D, n32, c->gkey_b.as<uint32_t>(), c->spos.as<float4>(), c->tab_a.as<uint32_t>(),
+               c->tab_b.as<uint32_t>(), d_rho, d_ncnt, (const unsigned long long *)nullptr, (uint32_t *)nullptr);
+        if (want_nbrs) {
+            const uint64_t total = scan_neighbor_counts(c, d_ncnt, n);
+            out->nbr_idx.ensure(std::max<uint64_t>(total, 1) * 4);
+            LAUNCH(c, k_density_global<true>, nblk(n32, 128), 128, D, n32, c->gkey_b.as<uint32_t>(), c->spos.as<float4>(), c->tab_a.as<uint32_t>(),
+                   c->tab_b.as<uint32_t>(), d_rho, (unsigned long long *)nullptr, (const unsigned long long *)d_ncnt, out->nbr_idx.as<uint32_t>());
+            out->has_neighbors = 1; out->n_neighbors = total;
+        }
     }
     CK(cudaEventRecord(c->ev[4], st));
 
@@ -590,9 +622,10 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     CK(cudaMemGetInfo(&free_b, &total_b));
     const unsigned nbricks = (unsigned)(D.nb * D.nb * D.nb);
     const size_t per_tile = np3 * (4 + 4 + 1) + (size_t)nbricks * (SS_LS_WARPS + 8 + 1 + 16) + 256;
-    size_t max_tiles = c->max_tiles ? c->max_tiles : std::max<size_t>(1, std::min<size_t>((free_b / 3) / per_tile, 4096));
-    max_tiles = std::min<size_t>(max_tiles, std::max<size_t>(1, (size_t)0x7fffffff / np3 / 2));
-    max_tiles = std::min<size_t>(max_tiles, std::max<size_t>(1, (size_t)65535 / D.nb));       // gridDim.z = nb * tiles
+    // as many tiles per batch as fit a third of the free memory (fewer host synchronisations per frame); the brick index
+    // tile * nb^3 + ... must stay below 2^31
+    size_t max_tiles = c->max_tiles ? c->max_tiles : std::max<size_t>(1, (free_b / 3) / per_tile);
+    max_tiles = std::min<size_t>(max_tiles, std::max<size_t>(1, (size_t)0x7fffffff / nbricks / 2));
     const uint32_t nown = (uint32_t)owned_list.size();
     max_tiles = std::min<size_t>(max_tiles, std::max<uint32_t>(nown, 1));
     const size_t nblk_max = max_tiles * nbricks;
@@ -1084,7 +1117,7 @@ extern "C" void ss_surface_free(ss_surface *s) {
             give_back(c->o_normals, s->normals);
         }
     }
-    s->verts.release(); s->tris.release(); s->vkeys.release(); s->rho.release(); s->normals.release();
+    s->verts.release(); s->tris.release(); s->vkeys.release(); s->rho.release(); s->normals.release(); s->nbr_off.release(); s->nbr_idx.release();
     delete s;
 }
 
@@ -1158,5 +1191,14 @@ extern "C" int ss_surface_copy_levelset_tile(const ss_surface *s, float *dst) {
     if (s->tile.empty()) return ss_fail(SS_ERR_INVALID_PARAMETER, "no level-set tile was kept (ss_context_keep_levelset_tile)");
     memcpy(dst, s->tile.data(), s->tile.size() * 4);
     return SS_OK;
+}
+extern "C" uint64_t ss_surface_num_neighbors(const ss_surface *s) { return (s && s->has_neighbors) ? s->n_neighbors : 0; }
+extern "C" int ss_surface_copy_neighbor_lists(const ss_surface *s, uint64_t *offsets, uint32_t *indices) {
+    if (!s) return SS_ERR_INVALID_PARAMETER;
+    if (!s->has_neighbors) return ss_fail(SS_ERR_INVALID_PARAMETER, "neighbor lists were not requested (Parameters::global_neighborhood_list)");
+    int rc = SS_OK;
+    if (offsets) rc = copy_out(s, offsets, s->nbr_off.p, (s->n + 1) * 8);
+    if (!rc && indices) rc = copy_out(s, indices, s->nbr_idx.p, s->n_neighbors * 4);
+    return rc;
 }
 extern "C" int ss_surface_timings(const ss_surface *s, ss_timings *o) { if (!s || !o) return SS_ERR_INVALID_PARAMETER; *o = s->tm; return SS_OK; }

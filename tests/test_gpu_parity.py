@@ -219,3 +219,20 @@ def test_cuda_sph_normals(ss, oracle_mod):
         assert n.shape == ref.shape and not np.isnan(n).any()
         assert np.abs(np.linalg.norm(n, axis=1) - 1.0).max() < 1e-5
         assert np.abs(n - ref).max() <= 2e-5, np.abs(n - ref).max()
+
+
+def test_cuda_global_neighborhood_list(ss, oracle_mod):
+    """Parameters::global_neighborhood_list: per-particle neighbour lists in the reference's visiting order
+    (dense_subdomains.rs:617-639 / neighborhood_search.rs:396-433), subdomain and global path."""
+    from splashsurf_b200 import synthetic as syn
+    p = syn.splash((16, 16, 16), 4, 0.025, 130)
+    for kw in (dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.5),
+               dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.75, subdomain_grid=False)):
+        g = ss.reconstruct_surface(p, global_neighborhood_list=True, **kw)
+        o = oracle_mod.reconstruct(p, want_neighbors=True, **kw)
+        off, idx = o["neighbors"]
+        assert len(g.particle_neighbors) == len(p)
+        assert np.array_equal(g.particle_neighbors.offsets.astype(np.int64), off)
+        assert np.array_equal(g.particle_neighbors.indices.astype(np.int64), idx)
+        assert g.particle_neighbors[7] == idx[off[7]:off[8]].tolist()
+        assert np.array_equal(g.particle_densities, o["particle_densities"])

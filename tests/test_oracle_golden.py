@@ -117,3 +117,11 @@ def test_oracle_sph_normals_fixture(oracle_mod):
     g = load_golden("sph_normals_ref")
     n = oracle_mod.sph_normals(g["particles"], g["densities"], g["vertices"], compact_support_radius=g["h"], particle_rest_mass=g["rest_mass"])
     assert np.abs(n - g["normals"]).max() <= 2e-5
+
+
+def test_oracle_neighbor_lists_fixture(oracle_mod):
+    """Neighbour lists of the reference binary (global_neighborhood_list=True) vs the restatement: identical lists, in order."""
+    g = load_golden("neighbors_ref")
+    o = oracle_mod.reconstruct(g["particles"], particle_radius=0.025, smoothing_length=2.0, cube_size=0.5, want_neighbors=True)
+    off, idx = o["neighbors"]
+    assert np.array_equal(off, g["offsets"]) and np.array_equal(idx, g["indices"])

@@ -68,6 +68,13 @@ def main():
     np.savez_compressed(os.path.join(GOLD, "sph_normals_ref.npz"), particles=pn, densities=np.asarray(r.particle_densities),
                         vertices=np.asarray(m.mesh.vertices), normals=np.asarray(m.point_attributes["normals"]),
                         h=np.float32(2.0 * 2.0 * 0.025), rest_mass=oracle.sph_rest_mass(0.025))
+    # per-particle neighbour lists (Parameters::global_neighborhood_list)
+    pq = syn.splash((10, 10, 10), 2, 0.025, 46)
+    rq = ps.reconstruct_surface(pq, particle_radius=0.025, smoothing_length=2.0, cube_size=0.5, global_neighborhood_list=True)
+    lists = rq.particle_neighbors.get_neighborhood_lists()
+    np.savez_compressed(os.path.join(GOLD, "neighbors_ref.npz"), particles=pq,
+                        offsets=np.concatenate([[0], np.cumsum([len(l) for l in lists])]).astype(np.int64),
+                        indices=np.concatenate([np.asarray(l, dtype=np.int64) for l in lists]))
     # the reference's hot-loop fixture (benches/benches/bench_grid_loop.rs:203-262): inputs only, repacked
     d = json.load(open("/root/reference/data/density_grid_loop_subdomain_33.json"))
     np.savez_compressed(
