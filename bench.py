@@ -158,7 +158,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the reconstruct path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # a mismatched collective must fail fast instead of burning the default 10-minute NCCL timeout
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=240))
 
     import splashsurf_b200 as ss
     from splashsurf_b200 import distributed as ssd
@@ -251,7 +253,15 @@ def main():
         ls_s = (ls_ms / args.steps) * 1e-3
         ach = ls_bytes / ls_s / 1e9 if ls_s > 0 else 0.0
         flops = (pairs / args.steps) * 30.0
-        roof = {"bound": "hbm", "kernel": "k_levelset", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        traffic, traffic_note = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "levelset_traffic.json")))
+            traffic = tj["dram_bytes"] / tj["particles_exact"] * n_total / max(ls_launches / args.steps, 1.0)
+            traffic_note = "per launch; scaled by particle count from " + tj["source"]
+        except Exception:
+            pass
+        roof = {"bound": "hbm", "kernel": "k_levelset", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "traffic_note": traffic_note,
                 "peak_source": peak_src, "launches_per_step": ls_launches / args.steps, "ms_per_step": ls_ms / args.steps,
                 "algorithmic_bytes_per_step": ls_bytes,
                 "note": "the ordered level-set gather is FP32-issue bound, not HBM bound (SURVEY.md 8d): see fp32",

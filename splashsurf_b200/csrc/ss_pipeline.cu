@@ -481,7 +481,14 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     out->rho.ensure(std::max<uint64_t>(n, 1) * 4);
     float *d_rho = out->rho.as<float>();
     CK(cudaMemsetAsync(d_rho, 0, std::max<uint64_t>(n, 1) * 4, st));
-    if (n == 0) { for (int e = 3; e <= 9; ++e) CK(cudaEventRecord(c->ev[e], st)); CK(cudaStreamSynchronize(st)); return SS_OK; }
+    // NOTE (multi-GPU): the max-reduce callback is a collective -- every rank must call it exactly once per
+    // reconstruction, also ranks that received no particles or own no subdomain.
+    if (n == 0) {
+        for (int e = 3; e <= 9; ++e) CK(cudaEventRecord(c->ev[e], st));
+        CK(cudaStreamSynchronize(st));
+        if (part.enabled && part.max_reduce) part.max_reduce(0, part.max_reduce_user);
+        return SS_OK;
+    }
 
     // ---- decomposition: memberships (owner + ghosts), stable sort by subdomain
     c->cnt.ensure(n * 4); c->off.ensure(n * 4 + 4);
@@ -494,7 +501,12 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     const uint64_t M64 = (uint64_t)lo + lc;
     if (M64 >= 0xfffffff0ull) return ss_fail(SS_ERR_INDEX_TOO_SMALL, "more than 2^32 subdomain memberships");
     const uint32_t M = (uint32_t)M64;
-    if (M == 0) { for (int e = 3; e <= 9; ++e) CK(cudaEventRecord(c->ev[e], st)); CK(cudaStreamSynchronize(st)); return SS_OK; }
+    if (M == 0) {
+        for (int e = 3; e <= 9; ++e) CK(cudaEventRecord(c->ev[e], st));
+        CK(cudaStreamSynchronize(st));
+        if (part.enabled && part.max_reduce) part.max_reduce(0, part.max_reduce_user);
+        return SS_OK;
+    }
     c->key_a.ensure((size_t)M * 4); c->key_b.ensure((size_t)M * 4); c->val_a.ensure((size_t)M * 4); c->val_b.ensure((size_t)M * 4);
     LAUNCH(c, k_classify_fill, nblk(n, 256), 256, D, d_xyz, (uint32_t)n, c->off.as<uint32_t>(), c->key_a.as<uint32_t>(), c->val_a.as<uint32_t>());
     const uint64_t nslots = (uint64_t)nsd[0] * nsd[1] * nsd[2];

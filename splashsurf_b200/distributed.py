@@ -77,6 +77,28 @@ def make_plan(grid_ncells, subdomain_cubes: int, cube_size: float, compact_suppo
     return SlabPlan(ax, nsd[ax], balanced_cuts(hist, world), srad, srad)
 
 
+def plan_partition(x: torch.Tensor, grid_min, grid_ncells, S: int, cube_size: float, compact_support: float, world: int, group=None):
+    """Collective: every rank passes its local particles (any device) and gets the same SlabPlan plus its particles' owner
+    layers.  Work model per layer of subdomains: particles + a fixed cost per occupied subdomain tile (every tile pays for
+    its bricks and 65^3 grid points even when it only holds a thin sheet of fluid)."""
+    plan0 = make_plan(grid_ncells, S, cube_size, compact_support, None, world)
+    ax = plan0.axis
+    sub_size = float(np.float32(np.float32(cube_size) * np.float32(S)))
+    nsd = [(int(nc) + S - 1) // S for nc in grid_ncells]
+    o = [owner_layer(x[:, d], float(grid_min[d]), sub_size).clamp(0, nsd[d] - 1) for d in range(3)]
+    layer = owner_layer(x[:, ax], float(grid_min[ax]), sub_size)
+    hist = torch.bincount(o[ax], minlength=nsd[ax]).to(torch.float64)
+    dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+    occ = torch.zeros(nsd[0] * nsd[1] * nsd[2], dtype=torch.int32, device=x.device)
+    occ[(o[0] * nsd[1] + o[1]) * nsd[2] + o[2]] = 1
+    dist.all_reduce(occ, op=dist.ReduceOp.MAX, group=group)
+    other = tuple(d for d in range(3) if d != ax)
+    tiles = occ.view(nsd[0], nsd[1], nsd[2]).sum(dim=other).to(torch.float64)
+    work = hist + TILE_COST_PARTICLES * tiles
+    plan = make_plan(grid_ncells, S, cube_size, compact_support, work.cpu().numpy(), world, axis=ax)
+    return plan, layer
+
+
 def owner_layer(x_axis: torch.Tensor, gmin: float, sub_size: float) -> torch.Tensor:
     """Subdomain layer index of each particle along the partition axis (float64 on purpose: only used to route
     particles conservatively, +-1 slack is added by SlabPlan.recv_range)."""
@@ -102,9 +124,6 @@ def exchange_particles(x_local: torch.Tensor, layer: torch.Tensor, plan: SlabPla
 
 
 # ---------------------------------------------------------------------------- device helpers ----
-_MAXCB = C.CFUNCTYPE(C.c_uint64, C.c_uint64, C.c_void_p)
-
-
 class _CudaView:
     """Zero-copy torch view of device memory owned by the C library (via __cuda_array_interface__)."""
 
@@ -196,44 +215,31 @@ class Runner:
         rc = L.ss_grid_for_reconstruction_f32(self.ctx._h, C.c_void_p(corners.ctypes.data), C.c_uint64(2), C.byref(p), C.byref(grid))
         if rc:
             raise RuntimeError((L.ss_last_error() or b"").decode())
-        # 2. slab plan balanced by the histogram of owner layers
-        S = int(p.subdomain_num_cubes_per_dim)
-        plan0 = make_plan(list(grid.cells_per_dim), S, p.cube_size, p.compact_support_radius, None, world)
-        ax = plan0.axis
-        sub_size = float(np.float32(np.float32(p.cube_size) * np.float32(S)))
-        layer = owner_layer(xd[:, ax], float(grid.aabb_min[ax]), sub_size)
-        hist = torch.bincount(layer.clamp(0, plan0.nsub_axis - 1), minlength=plan0.nsub_axis).to(torch.float64)
-        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=self.group)
-        # work model per layer: particles + a fixed cost per occupied subdomain tile (every tile pays for its 729 bricks and
-        # 65^3 grid points even when it only holds a thin sheet of fluid)
-        nsd = [(int(nc) + S - 1) // S for nc in grid.cells_per_dim]
-        o = [owner_layer(xd[:, d], float(grid.aabb_min[d]), sub_size).clamp(0, nsd[d] - 1) for d in range(3)]
-        occ = torch.zeros(nsd[0] * nsd[1] * nsd[2], dtype=torch.int32, device=self.device)
-        occ[(o[0] * nsd[1] + o[1]) * nsd[2] + o[2]] = 1
-        dist.all_reduce(occ, op=dist.ReduceOp.MAX, group=self.group)
-        other = tuple(d for d in range(3) if d != ax)
-        tiles = occ.view(nsd[0], nsd[1], nsd[2]).sum(dim=other).to(torch.float64)
-        work = hist + TILE_COST_PARTICLES * tiles
-        plan = make_plan(list(grid.cells_per_dim), S, p.cube_size, p.compact_support_radius, work.cpu().numpy(), world, axis=ax)
+        # 2. slab plan balanced by a work model (particles + occupied tiles per layer)
+        plan, layer = plan_partition(xd, [float(v) for v in grid.aabb_min], [int(v) for v in grid.cells_per_dim], int(p.subdomain_num_cubes_per_dim),
+                                     float(p.cube_size), float(p.compact_support_radius), world, self.group)
+        ax = plan.axis
         self.last_plan = plan
         # 3. halo exchange (variable all-to-all over NCCL); keeps ascending global particle order
         recv, counts = exchange_particles(xd, layer, plan, world, self.group)
         t_ev[1].record()
         own_lo, own_hi = plan.own(rank)
-        # 4./5. this rank's slab; the library calls back for the global maximum subdomain population (sparse rule,
-        # dense_subdomains.rs:1242-1251) right after its decomposition
+        # 4. local maximum subdomain population -> global maximum (sparse rule, dense_subdomains.rs:1242-1251).  Every rank
+        #    makes the same two library calls and the same all-reduce, also ranks that received no particles.
         torch.cuda.synchronize()
-
-        def _max_cb(local_max, _user):
-            t = torch.tensor([int(local_max)], dtype=torch.int64, device=self.device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
-            return int(t.item())
-
-        cb = _MAXCB(_max_cb)
-        pre_launches = 0
         s = C.c_void_p()
-        rc = L.ss_reconstruct_partition_cb_f32(self.ctx._h, C.c_void_p(recv.data_ptr()), C.c_uint64(recv.shape[0]), C.byref(p),
-                                               C.byref(grid), ax, own_lo, own_hi, plan.halo, C.cast(cb, C.c_void_p), None, C.byref(s))
+        rc = L.ss_reconstruct_partition_f32(self.ctx._h, C.c_void_p(recv.data_ptr()), C.c_uint64(recv.shape[0]), C.byref(p),
+                                            C.byref(grid), ax, own_lo, own_hi, plan.halo, C.c_uint64(0), 1, C.byref(s))
+        if rc:
+            raise RuntimeError((L.ss_last_error() or b"").decode())
+        gmax = torch.tensor([L.ss_surface_max_subdomain_particles(s)], dtype=torch.int64, device=self.device)
+        pre_launches = int(self.ctx.timings(s)["kernel_launches"])
+        self.ctx.free_surface(s)
+        dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=self.group)
+        # 5. this rank's slab
+        s = C.c_void_p()
+        rc = L.ss_reconstruct_partition_f32(self.ctx._h, C.c_void_p(recv.data_ptr()), C.c_uint64(recv.shape[0]), C.byref(p),
+                                            C.byref(grid), ax, own_lo, own_hi, plan.halo, C.c_uint64(int(gmax.item())), 0, C.byref(s))
         if rc:
             raise RuntimeError((L.ss_last_error() or b"").decode())
         try:

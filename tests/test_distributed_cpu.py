@@ -28,20 +28,20 @@ gid = torch.arange(lo, hi, dtype=torch.float32)                            # car
 import oracle
 g = oracle.reconstruct(p_all, particle_radius=r, smoothing_length=2.0, cube_size=0.5)
 gmin, ncells = g["subdomain_grid"]["aabb_min"], g["grid"]["ncells"]
-plan0 = ssd.make_plan(ncells, S, c, h, None, world)
-ax = plan0.axis
-sub_size = float(np.float32(np.float32(c) * np.float32(S)))
-layer = ssd.owner_layer(x[:, ax], float(gmin[ax]), sub_size)
-hist = torch.bincount(layer.clamp(0, plan0.nsub_axis - 1), minlength=plan0.nsub_axis).to(torch.float64)
-dist.all_reduce(hist)
-plan = ssd.make_plan(ncells, S, c, h, hist.numpy(), world, axis=ax)
+plan, layer = ssd.plan_partition(x, [float(v) for v in gmin], [int(v) for v in ncells], S, c, h, world)
+ax = plan.axis
+hist = torch.tensor([float(n)])
 recv, counts = ssd.exchange_particles(x, layer, plan, world)
 # same exchange on the ids to learn which global particles arrived, in which order
 ids3 = torch.stack([gid, gid, gid], dim=1)
 recv_ids, _ = ssd.exchange_particles(ids3, layer, plan, world)
 ids = recv_ids[:, 0].to(torch.int64).numpy()
+# an empty rank (no particles at all) must go through the same collectives without hanging
+empty = x[:0]
+plan_e, layer_e = ssd.plan_partition(x if rank == 0 else empty, [float(v) for v in gmin], [int(v) for v in ncells], S, c, h, world)
+recv_e, _ = ssd.exchange_particles(x if rank == 0 else empty, layer if rank == 0 else layer_e, plan_e, world)
 res = {"rank": rank, "axis": ax, "cuts": plan.cuts, "srad": plan.srad, "ids": ids.tolist(), "n": n,
-       "match": bool(np.array_equal(recv.numpy(), p_all[ids])), "hist_total": float(hist.sum())}
+       "match": bool(np.array_equal(recv.numpy(), p_all[ids])), "hist_total": float(hist.sum()), "empty_case_recv": int(recv_e.shape[0])}
 json.dump(res, open(os.path.join(os.environ["SS_OUT"], f"rank{rank}.json"), "w"))
 dist.destroy_process_group()
 '''

@@ -13,7 +13,8 @@ from splashsurf_b200 import distributed as ssd, synthetic as syn
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import datetime
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=120))
     ok = True
     cases = [
         ("splash", syn.splash((60, 20, 20), 8, 0.025, 31), dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.5)),

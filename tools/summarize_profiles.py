@@ -77,12 +77,15 @@ if __name__ == "__main__":
     g = os.path.join(ROOT, "gpurun_out")
     jobs = [("prof_levelset_r1a.ncu-rep", "r1a_levelset_exact_everywhere_ncu.txt", "round 1, first version: every grid point evaluated exactly (2 M-particle dam break)"),
             ("prof_levelset_r1b.ncu-rep", "r1b_levelset_certify_ncu.txt", "round 1: certification pass added (4 M particles); launch 0 = certify, launch 1 = fix-up"),
-            ("prof_levelset_r1c.ncu-rep", "r1c_levelset_certify_opt_ncu.txt", "round 1: prologue/staging/FMA-certification optimised (4 M particles)")]
+            ("prof_levelset_r1c.ncu-rep", "r1c_levelset_certify_opt_ncu.txt", "round 1: prologue/staging/FMA-certification optimised (4 M particles)"),
+            ("prof_levelset_r1d.ncu-rep", "r1d_levelset_worklist_ext_ncu.txt", "round 1: work list of non-empty bricks + extension bricks + two-ring certification (4 M particles; before the cubic lower bound)")]
     for rep, name, note in jobs:
         if os.path.exists(os.path.join(g, rep)):
             summarize_rep(os.path.join(g, rep), name, note)
     for c, name, note in [("launches_r1a.csv", "r1a_launch_list.txt", "2 M particles, exact-everywhere version"),
-                          ("launches_r1b.csv", "r1b_launch_list.txt", "10 M particles, certification version")]:
+                          ("launches_r1b.csv", "r1b_launch_list.txt", "10 M particles, certification version"),
+                          ("launches_r1c.csv", "r1c_launch_list_50M.txt", "`python bench.py --steps 1 --warmup 0` (50 M particles), plane-indexed MC passes"),
+                          ("launches_r1d.csv", "r1d_launch_list_50M.txt", "`python bench.py --steps 1 --warmup 0` (50 M particles), brick-list MC passes, before two-ring certification / work list / extension bricks")]:
         if os.path.exists(os.path.join(g, c)):
             summarize_launches(os.path.join(g, c), name, note)
     print(os.listdir(OUT))
