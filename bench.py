@@ -22,6 +22,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+METRIC = "Mparticles/s end-to-end reconstruct (50M pts, cell=0.5r) at 1/2/4/8 GPU vs CPU ref"     # BASELINE.json
 RECON_KW = dict(particle_radius=0.01, smoothing_length=2.0, cube_size=0.5, iso_surface_threshold=0.6)
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # 148 SMs x 128 FMA lanes x 2 flop x max SM clock (nominal)
 
@@ -120,7 +121,7 @@ def run_reference(args):
         times.append(dt)
     ms = 1e3 * float(np.mean(times))
     val = len(p) / (ms * 1e-3) / 1e6
-    line = {"impl": "reference", "metric": "Mparticles/s end-to-end reconstruct", "value": val, "unit": "Mparticles/s", "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mparticles/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": {"workload": "cfg-4 dam break (bounded sample): " + desc, "particles": int(len(p)),
                                                             "r": 0.01, "cube_size": "0.5r", "smoothing_length": "2.0r", "subdomain_cubes": 64},
@@ -269,7 +270,7 @@ def main():
                          "frac": (flops / ls_s / 1e12) / FP32_PEAK_TFLOPS if ls_s > 0 else 0.0,
                          "model": "exactly evaluated in-support particle-gridpoint pairs x 30 flop", "pairs_per_step": pairs / args.steps,
                          "fixup_points_per_step": int(fixups)}}
-        line = {"metric": "Mparticles/s end-to-end reconstruct", "value": value, "unit": "Mparticles/s", "n_gpus": world, "steps": args.steps,
+        line = {"metric": METRIC, "value": value, "unit": "Mparticles/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": ("cfg-4: " if n_total >= 50_000_000 else "cfg-4 (scaled): ") + desc, "particles": int(n_total), "r": 0.01,

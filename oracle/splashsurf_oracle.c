@@ -75,6 +75,9 @@ typedef struct {
  * tools/derive_mc_lut.py from black-box probing of the reference binary (see
  * tests/golden/mc_lut_cases.json).  Raw (un-reversed) edge triplets. */
 #include "../splashsurf_b200/csrc/mc_lut.inc"
+static signed char SS_MC_TRI_TABLE[256][16];
+static int g_lut_ready = 0;
+static void lut_init(void) { if (!g_lut_ready) { ss_mc_unpack(SS_MC_TRI_TABLE); g_lut_ready = 1; } }
 
 /* ------------------------------------------------------------- helpers ---- */
 static inline float f_floor(float x) { return floorf(x); }
@@ -465,7 +468,7 @@ static void subdomain_mc(so_patch *pt, const float *phi, const float smin[3], co
             if (val > thr) idx |= (1 << v);
         }
         if (idx == 0) continue;
-        const int8_t *row = SS_MC_TRI_TABLE[idx];
+        const signed char *row = SS_MC_TRI_TABLE[idx];
         for (int t = 0; t < 5 && row[3 * t] >= 0; ++t) {
             uint64_t tri[3];
             for (int m = 0; m < 3; ++m) {
@@ -700,7 +703,7 @@ static int reconstruct_global(so_result *res, const float *xyz, uint64_t n, cons
             /* narrow_band_extraction.rs:124-126 (Above set by the edge loop) and :179-184 (value > threshold) */
             if (marked[l] || phi[l] > thr) idx |= (1 << v);
         }
-        const int8_t *row = SS_MC_TRI_TABLE[idx];
+        const signed char *row = SS_MC_TRI_TABLE[idx];
         for (int t = 0; t < 5 && row[3 * t] >= 0; ++t) {
             uint64_t tri[3];
             for (int m = 0; m < 3; ++m) {
@@ -806,6 +809,7 @@ int so_reconstruct(const float *xyz_in, uint64_t n_in, const so_params *p, so_re
                    int64_t tile_sub_flat, float *tile_out, int64_t *neighbor_counts, const int64_t *nbr_off, int64_t *nbr_out) {
     so_result *res = (so_result *)calloc(1, sizeof(so_result));
     *out = res;
+    lut_init();
     /* lib.rs:369-406 particle AABB filter (half-open contains_point) */
     const float *xyz = xyz_in; float *filtered = NULL; uint64_t n = n_in;
     if (p->has_particle_aabb) {

@@ -187,7 +187,11 @@ extern "C" int ss_context_create(int device, ss_context **out) {
         c->device = device;
         CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
-        CK(cudaMemcpyToSymbol(c_tri_table, SS_MC_TRI_TABLE, sizeof(SS_MC_TRI_TABLE)));
+        {
+            signed char table[256][16];
+            ss_mc_unpack(table);
+            CK(cudaMemcpyToSymbol(c_tri_table, table, sizeof(table)));
+        }
         CK(cudaMemcpyToSymbol(c_num_tris, SS_MC_NUM_TRIS, sizeof(SS_MC_NUM_TRIS)));
         { std::lock_guard<std::mutex> lk(g_ctx_mutex); g_live_contexts.insert(c); }
         *out = c;

@@ -53,11 +53,13 @@ def test_mc_lut_known_answers():
     assert cases[0b00010100] == [[10, 2, 1], [7, 4, 8]]
     assert cases[0] == [] and cases[255] == []
     inc = open(os.path.join(os.path.dirname(GOLDEN), "..", "splashsurf_b200", "csrc", "mc_lut.inc")).read()
-    rows = [r for r in inc.split("SS_MC_TRI_TABLE[256][16] = {")[1].split("};")[0].strip().split("\n")]
-    for idx, (row, tl) in enumerate(zip(rows, cases)):
-        vals = [int(v) for v in row.strip().strip("{},").split(",")]
+    import re
+    words = [int(w, 16) for w in re.findall(r"0x([0-9a-f]{16})ull", inc)]
+    assert len(words) == 256
+    for idx, (word, tl) in enumerate(zip(words, cases)):
+        vals = [(word >> (4 * k)) & 0xF for k in range(16)]
         raw = [e for t in tl for e in (t[2], t[1], t[0])]
-        assert vals[:len(raw)] == raw and all(v == -1 for v in vals[len(raw):]), idx
+        assert vals[:len(raw)] == raw and all(v == 0xF for v in vals[len(raw):]), idx
     # complementary cases use the same edge sets
     for idx in range(256):
         a = sorted({e for t in cases[idx] for e in t}); b = sorted({e for t in cases[255 - idx] for e in t})
