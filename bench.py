@@ -79,8 +79,23 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_cloud(n_target):
+WORKLOADS = {
+    "cfg4": None,    # default: dam break (50 M, or scaled with --particles)
+    "cfg2": ("synthetic jittered cube 100^3 = 1 M particles (r=0.025, seed 1234)", dict(particle_radius=0.025)),
+    "cfg3": ("synthetic dam-break 10 M (column 200x230x200 + sheet 400x10x200, r=0.01, seed 2)", dict()),
+    "cfg5": ("synthetic splash 200 M (body 540x583x540 + droplets, r=0.005, seed 4), cube 0.45 r",
+             dict(particle_radius=0.005, cube_size=0.45)),
+}
+
+
+def make_cloud(n_target, workload="cfg4"):
     from splashsurf_b200 import synthetic as syn
+    if workload == "cfg2":
+        return syn.jittered_cube(100, 0.025, 1234), WORKLOADS["cfg2"][0]
+    if workload == "cfg3":
+        return syn.dam_break_10m(), WORKLOADS["cfg3"][0]
+    if workload == "cfg5":
+        return syn.splash_200m(), WORKLOADS["cfg5"][0]
     if n_target >= 50_000_000:
         return syn.dam_break_50m(), "synthetic dam-break 50 M (column 340x370x340 + sheet 1063x20x340, r=0.01, seed 3)"
     return syn.dam_break_scaled(n_target, 0.01, 3), f"synthetic dam-break scaled to ~{n_target} particles (cfg-4 proportions, r=0.01, seed 3)"
@@ -141,6 +156,7 @@ def main():
     ap.add_argument("--particles", type=int, default=50_000_400, help="target particle count of the dam break (default: cfg-4)")
     ap.add_argument("--ref-particles", type=int, default=2_000_000, help="bounded sample for the CPU reference")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS), help="BASELINE config (default cfg4 = the metric's 50 M dam break)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -166,10 +182,13 @@ def main():
     import splashsurf_b200 as ss
     from splashsurf_b200 import distributed as ssd
     ctx = ss.Context(local_rank)
-    params = ss.make_params(**RECON_KW)
+    kw = dict(RECON_KW)
+    if WORKLOADS.get(args.workload):
+        kw.update(WORKLOADS[args.workload][1])
+    params = ss.make_params(**kw)
 
     # ---- workload (identical on every rank; each rank keeps its slab when world > 1)
-    p_all, desc = make_cloud(args.particles)
+    p_all, desc = make_cloud(args.particles, args.workload)
     n_total = len(p_all)
     runner = ssd.Runner(ctx, params, world, rank, local_rank)
     p_local = runner.take_local(p_all)
@@ -273,8 +292,9 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "Mparticles/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": ("cfg-4: " if n_total >= 50_000_000 else "cfg-4 (scaled): ") + desc, "particles": int(n_total), "r": 0.01,
-                           "cube_size": "0.5r", "smoothing_length": "2.0r", "iso": 0.6, "subdomain_cubes": 64,
+                "config": {"workload": (args.workload + ": " if args.workload != "cfg4" else ("cfg-4: " if n_total >= 50_000_000 else "cfg-4 (scaled): ")) + desc,
+                           "particles": int(n_total), "r": kw["particle_radius"],
+                           "cube_size": f"{kw['cube_size']}r", "smoothing_length": "2.0r", "iso": 0.6, "subdomain_cubes": 64,
                            "parallelism": f"subdomain slabs x{world}" if world > 1 else "single GPU",
                            "l2": "inputs (600 MB) and tiles (GBs) exceed the 126 MB L2; no flush needed"},
                 "mesh": {"vertices": int(nv_g if nv_g is not None else nv), "triangles": int(nt_g if nt_g is not None else nt), "subdomains": int(n_sub)},

@@ -73,6 +73,30 @@ def splash(n_body=(60, 65, 60), n_droplets: int = 12, r: float = 0.005, seed: in
     return _jitter(np.concatenate(parts, axis=0), d, rng)
 
 
+def splash_200m(scale: float = 1.0, seed: int = 4) -> np.ndarray:
+    """cfg-5: dam-break body 540x583x540 (r = 0.005) plus lattice-ball droplets of radius U[10, 40] d at random centres above
+    it, added until N = 200 M (~340 droplets).  `scale` < 1 shrinks every lattice count (for tests / smaller boxes)."""
+    r = 0.005
+    d = 2.0 * r
+    rng = np.random.default_rng(seed)
+    nb = tuple(max(4, int(round(v * scale))) for v in (540, 583, 540))
+    parts = [_lattice(*nb, d)]
+    n = len(parts[0])
+    target = int(200_000_000 * scale ** 3)
+    top = nb[1] * d
+    while n < target:
+        rad = rng.uniform(10.0, 40.0) * scale * d
+        ctr = np.array([rng.uniform(0, nb[0] * d), top + rad + rng.uniform(2.0, 60.0) * scale * d, rng.uniform(0, nb[2] * d)])
+        m = int(np.ceil(rad / d))
+        ball = _lattice(2 * m + 1, 2 * m + 1, 2 * m + 1, d, origin=tuple(ctr - m * d))
+        ball = ball[np.linalg.norm(ball - ctr[None].astype(np.float32), axis=1) <= rad]
+        if n + len(ball) > target:
+            ball = ball[: max(target - n, 0)]
+        parts.append(ball)
+        n += len(ball)
+    return _jitter(np.concatenate(parts, axis=0), d, rng)
+
+
 def load_vtk_points(path: str) -> np.ndarray:
     """Legacy-VTK BINARY (big-endian float) POINTS reader, enough for data/*_particles.vtk fixtures."""
     b = open(path, "rb").read()

@@ -59,3 +59,21 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+
+
+def test_ctypes_signatures_match_header_arity(ss):
+    """Every binding in splashsurf_b200/__init__.py that declares argtypes has as many arguments as the C declaration."""
+    hdr = open(os.path.join(ROOT, "include", "splashsurf_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    L = ss.load_library()
+    checked = 0
+    for m in re.finditer(r"\b(ss_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", hdr, flags=re.S):
+        name, args = m.group(1), m.group(2).strip()
+        # drop nested parentheses of function-pointer parameters before counting commas
+        flat = re.sub(r"\([^()]*\)", "", args)
+        n = 0 if flat in ("", "void") else flat.count(",") + 1
+        fn = getattr(L, name)
+        if fn.argtypes is not None:
+            assert len(fn.argtypes) == n, (name, len(fn.argtypes), n)
+            checked += 1
+    assert checked >= 25
