@@ -7,8 +7,9 @@
 //   k_ns_keys + [sort] + k_density   per-subdomain cell lists, SPH densities  (neighborhood_search.rs:345-438,
 //                                                                              density_map.rs:150-186)
 //   k_bin_keys + [sort] + k_records  splat bins (8^3-point bricks) + particle records
-//   k_levelset                  ordered cubic-spline gather per grid point    (dense_subdomains.rs:784-1213)
-//   k_mc_count + [scan] + k_mc_emit  marching cubes per subdomain tile        (dense_subdomains.rs:1470-1568)
+//   k_brick_worklist + k_levelset    ordered cubic-spline gather per grid point; certify pass, then
+//   k_brick_classify + k_fixup_flags + k_levelset(FIX)  exact values next to the surface (dense_subdomains.rs:784-1213)
+//   k_mc_count + [scan] + k_mc_verts + k_mc_tris  marching cubes over listed bricks (dense_subdomains.rs:1470-1568)
 //   k_weld_* / k_compact_*      boundary-vertex de-duplication ("stitching")  (dense_subdomains.rs:1603-1749)
 #pragma once
 #include "ss_common.cuh"
