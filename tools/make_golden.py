@@ -86,5 +86,36 @@ def main():
         squared_support_with_margin=np.float32(d["squared_support_with_margin"]))
 
 
+def postprocess_case():
+    """Post-processing steps of the reference pipeline (reconstruct.rs:1094-1391): raw mesh in the wheel's own order plus
+    every per-vertex output, so that oracle/postprocess.py can be pinned without canonicalising anything."""
+    pp_particles = ((10, 10, 10), 2, 0.025, 61)
+    x = syn.splash(*pp_particles)
+    vel = np.random.default_rng(62).normal(size=x.shape).astype(np.float32)
+    temp = (x[:, 1] * np.float32(3.0) + np.float32(1.0)).astype(np.float32)
+    kw = dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.75, iso_surface_threshold=0.6)
+    post = dict(mesh_smoothing_weights=True, mesh_smoothing_weights_normalization=13.0, mesh_smoothing_iters=5,
+                compute_normals=True, sph_normals=True, normals_smoothing_iters=3)
+    m, rec = ps.reconstruction_pipeline(x, attributes_to_interpolate={"vel": vel, "temp": temp}, **kw, **post, output_raw_mesh=True,
+                                        output_mesh_smoothing_weights=True, output_raw_normals=True)
+    m2, rec2 = ps.reconstruction_pipeline(x, **kw, mesh_smoothing_weights=False, mesh_smoothing_iters=2, compute_normals=True,
+                                          sph_normals=False, output_raw_mesh=True)
+    a = m.point_attributes
+    path = os.path.join(GOLD, "postprocess_ref.npz")
+    np.savez_compressed(
+        path, splash_args=json.dumps(pp_particles), kwargs=json.dumps(kw), post=json.dumps(post),
+        densities=np.asarray(rec.particle_densities), raw_vertices=np.asarray(rec.mesh.vertices),
+        triangles=np.asarray(rec.mesh.triangles).astype(np.uint32), vertices=np.asarray(m.mesh.vertices),
+        wnn=np.asarray(a["wnn"]), sw=np.asarray(a["sw"]), normals=np.asarray(a["normals"]), raw_normals=np.asarray(a["raw_normals"]),
+        vel=np.asarray(a["vel"]), temp=np.asarray(a["temp"]),
+        b_raw_vertices=np.asarray(rec2.mesh.vertices), b_triangles=np.asarray(rec2.mesh.triangles).astype(np.uint32),
+        b_vertices=np.asarray(m2.mesh.vertices), b_normals=np.asarray(m2.point_attributes["normals"]))
+    print("postprocess_ref", len(x), "particles ->", len(rec.mesh.vertices), "verts", os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
-    main()
+    if "--only-postprocess" in sys.argv:
+        postprocess_case()
+    else:
+        main()
+        postprocess_case()
