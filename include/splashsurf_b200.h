@@ -209,6 +209,41 @@ int ss_context_set_compute_sph_normals(ss_context *ctx, int on);
 int ss_surface_copy_normals(const ss_surface *s, float *dst_xyz);
 const float *ss_surface_device_normals(const ss_surface *s);
 
+/* ---- Mesh post-processing on the device (the steps of splashsurf/src/reconstruct.rs:1094-1391 that follow the
+ * reconstruction).  They operate in place on the surface's device mesh; copy results out with the accessors above.
+ * The entries marked [bins] query the particles through the splat bins of the reconstruction that produced the surface and
+ * must therefore be called before the next reconstruction on the same context (SS_ERR_INVALID_PARAMETER otherwise); they
+ * are not available on partitioned (multi-GPU) surfaces (SS_ERR_UNSUPPORTED).  Sums run in a different order than the
+ * reference's R-tree / hash order: results agree to f32 round-off, not bit for bit.
+ * Reference order of the steps: weights -> vertex smoothing -> normals -> normal smoothing -> attribute interpolation. */
+
+/* [bins] SphInterpolator::interpolate_scalar_quantity / interpolate_vector_quantity (sph_interpolation.rs:141-258) at the mesh
+ * vertices, interpolator as in reconstruct.rs:1094-1149 (sphere rest mass 4/3 pi r^3 rho0, the reconstruction's densities).
+ * values: [num_particles * dim] of the FILTERED particles, dim = 1 or 3; out: [num_vertices * dim]; host or device pointers. */
+int ss_surface_interpolate_quantity_f32(ss_surface *s, const float *values, uint32_t dim, int first_order_correction, float *out);
+
+/* [bins] Smoothing weights (reconstruct.rs:1159-1258): distance-weighted neighbour count per particle, SPH-interpolated to the
+ * vertices ("wnn"), min(max(n, 0) / normalization, 1) through the smooth-step 6x^5 - 15x^4 + 10x^3 ("sw").  The weights stay
+ * on the device for ss_surface_laplacian_smoothing_f32; wnn_out / weights_out ([num_vertices]) may be NULL. */
+int ss_surface_compute_smoothing_weights_f32(ss_surface *s, float normalization, float *wnn_out, float *weights_out);
+
+/* splashsurf_lib::postprocessing::par_laplacian_smoothing_inplace (postprocessing.rs:17-53), including its buffer swap (the
+ * blended vertex is the one of two iterations ago).  weights: [num_vertices] or NULL = the weights computed by
+ * ss_surface_compute_smoothing_weights_f32 on this surface, 1 if it was not called. */
+int ss_surface_laplacian_smoothing_f32(ss_surface *s, uint32_t iterations, float beta, const float *weights);
+
+/* Vertex normals at the current (possibly smoothed) vertices, readable with ss_surface_copy_normals:
+ * sph != 0: [bins] SphInterpolator::interpolate_normals (sph_interpolation.rs:82-133);
+ * sph == 0: TriMesh3d::par_vertex_normals, area-weighted triangle normals (mesh.rs:799-906). */
+int ss_surface_compute_normals_f32(ss_surface *s, int sph);
+
+/* par_laplacian_smoothing_normals_inplace (postprocessing.rs:56-97) on the surface's normals. */
+int ss_surface_smooth_normals_f32(ss_surface *s, uint32_t iterations);
+
+/* TriMesh3d::vertex_vertex_connectivity (mesh.rs:290-306) as CSR, neighbours ascending: offsets [num_vertices + 1],
+ * indices [*n_indices]; pass indices = NULL to query *n_indices first. */
+int ss_surface_vertex_connectivity(ss_surface *s, uint64_t *offsets, uint32_t *indices, uint64_t *n_indices);
+
 #ifdef __cplusplus
 }
 #endif

@@ -120,6 +120,12 @@ def load_library():
     L.ss_surface_device_vertex_keys.restype = vp
     L.ss_surface_copy_subdomain_owned.argtypes = [vp, vp]
     L.ss_weld_meshes.argtypes = [vp, vp, vp, u64, vp, u64, vp, u64, C.POINTER(u64)]
+    L.ss_surface_interpolate_quantity_f32.argtypes = [vp, vp, C.c_uint32, C.c_int, vp]
+    L.ss_surface_compute_smoothing_weights_f32.argtypes = [vp, C.c_float, vp, vp]
+    L.ss_surface_laplacian_smoothing_f32.argtypes = [vp, C.c_uint32, C.c_float, vp]
+    L.ss_surface_compute_normals_f32.argtypes = [vp, C.c_int]
+    L.ss_surface_smooth_normals_f32.argtypes = [vp, C.c_uint32]
+    L.ss_surface_vertex_connectivity.argtypes = [vp, vp, vp, C.POINTER(u64)]
     if L.ss_abi_version() != 1:
         raise ImportError("libsplashsurf_b200.so ABI version mismatch")
     _LIB = L
@@ -411,20 +417,85 @@ def reconstruction_pipeline(particles, *, attributes_to_interpolate=None, partic
                             smoothing_length: float, cube_size: float, iso_surface_threshold: float = 0.6, aabb_min=None, aabb_max=None,
                             multi_threading: bool = True, simd: bool = True, subdomain_grid: bool = True,
                             subdomain_grid_auto_disable: bool = True, subdomain_num_cubes_per_dim: int = 64,
-                            compute_normals: bool = False, sph_normals: bool = False, context: Optional[Context] = None, **post):
-    """The hot-path subset of ``pysplashsurf.reconstruction_pipeline`` (pysplashsurf/src/pipeline.rs:109-200): surface
-    reconstruction plus SPH normals (``compute_normals=True, sph_normals=True``).  Every other post-processing switch of the
-    reference pipeline (cleanup, decimation, smoothing, quads, attribute interpolation, area-weighted normals) is outside the
-    device path and raises NotImplementedError when enabled."""
-    enabled = [k for k, v in post.items() if v not in (False, None, 0) and k not in ("mesh_smoothing_weights", "mesh_smoothing_weights_normalization",
-                                                                                       "quad_max_edge_diag_ratio", "quad_max_normal_angle",
-                                                                                       "quad_max_interior_angle", "mesh_aabb_clamp_vertices", "max_iter")]
-    if enabled or attributes_to_interpolate or (compute_normals and not sph_normals):
-        raise NotImplementedError(f"post-processing not provided by the device path: {enabled or 'attributes / mesh normals'}")
-    rec = reconstruct_surface(particles, particle_radius=particle_radius, rest_density=rest_density, smoothing_length=smoothing_length,
-                              cube_size=cube_size, iso_surface_threshold=iso_surface_threshold, aabb_min=aabb_min, aabb_max=aabb_max,
-                              multi_threading=multi_threading, simd=simd, subdomain_grid=subdomain_grid,
-                              subdomain_grid_auto_disable=subdomain_grid_auto_disable, subdomain_num_cubes_per_dim=subdomain_num_cubes_per_dim,
-                              context=context, sph_normals=bool(compute_normals and sph_normals))
-    attrs = {"normals": rec.normals} if rec.normals is not None else {}
-    return MeshWithData(rec.mesh, attrs, {}), rec
+                            compute_normals: bool = False, sph_normals: bool = False, normals_smoothing_iters: Optional[int] = None,
+                            mesh_smoothing_iters: Optional[int] = None, mesh_smoothing_weights: bool = True,
+                            mesh_smoothing_weights_normalization: float = 13.0, output_mesh_smoothing_weights: bool = False,
+                            output_raw_normals: bool = False, output_raw_mesh: bool = False, context: Optional[Context] = None,
+                            with_debug: bool = False, **post):
+    """``pysplashsurf.reconstruction_pipeline`` (pysplashsurf/src/pipeline.rs:109-200) on the GPU: surface reconstruction plus
+    the post-processing steps of splashsurf/src/reconstruct.rs:1094-1391 that run on the device -- smoothing weights, weighted
+    Laplacian smoothing, SPH or area-weighted normals (at the smoothed vertices), normal smoothing and SPH interpolation of
+    float32 particle attributes.  Returns ``(MeshWithData, SurfaceReconstruction)``; the reconstruction holds the raw mesh.
+
+    The remaining switches of the reference pipeline (mesh cleanup, barnacle decimation, quad conversion, mesh AABB clamping,
+    mesh checks) are sequential half-edge / CPU steps outside the device path and raise NotImplementedError when enabled."""
+    passive = ("mesh_cleanup_snap_dist", "keep_vertices", "quad_max_edge_diag_ratio", "quad_max_normal_angle", "quad_max_interior_angle",
+               "mesh_aabb_clamp_vertices")
+    enabled = [k for k, v in post.items() if v not in (False, None, 0) and k not in passive]
+    if enabled:
+        raise NotImplementedError(f"post-processing not provided by the device path: {enabled}")
+    arr = np.asarray(particles)
+    if arr.dtype != np.float32:
+        raise TypeError("unsupported scalar type: the device path reconstructs float32 particles only")
+    if arr.ndim != 2 or arr.shape[1] != 3:
+        raise ValueError("particles must have shape (N, 3)")
+    arr = np.ascontiguousarray(arr)
+    attributes = {}
+    for name, a in (attributes_to_interpolate or {}).items():
+        a = np.asarray(a)
+        if a.dtype != np.float32 or not (a.ndim == 1 or (a.ndim == 2 and a.shape[1] == 3)) or len(a) != len(arr):
+            raise NotImplementedError(f"attribute {name!r}: only float32 arrays of shape (N,) or (N, 3) are interpolated")
+        attributes[name] = np.ascontiguousarray(a)
+    ctx = context or default_context()
+    L = ctx._L
+    p = make_params(particle_radius=particle_radius, rest_density=rest_density, smoothing_length=smoothing_length, cube_size=cube_size,
+                    iso_surface_threshold=iso_surface_threshold, aabb_min=aabb_min, aabb_max=aabb_max, multi_threading=multi_threading,
+                    simd=simd, subdomain_grid=subdomain_grid, subdomain_grid_auto_disable=subdomain_grid_auto_disable,
+                    subdomain_num_cubes_per_dim=subdomain_num_cubes_per_dim)
+    _check(L, L.ss_context_keep_levelset_tile(ctx._h, -1))
+    _check(L, L.ss_context_set_compute_sph_normals(ctx._h, 0))
+    s = ctx.reconstruct_raw(arr.ctypes.data, len(arr), p)
+    try:
+        rec = _collect(ctx, s, len(arr), p, with_debug, False)                  # raw mesh, densities, grids
+        nv = rec.mesh.nvertices
+        point = {}
+        weights_used = bool(mesh_smoothing_weights)
+        if weights_used:                                                        # reconstruct.rs:1159-1258 (at the raw vertices)
+            wnn, sw = np.empty(nv, np.float32), np.empty(nv, np.float32)
+            _check(L, L.ss_surface_compute_smoothing_weights_f32(s, C.c_float(float(np.float32(mesh_smoothing_weights_normalization))),
+                                                                 wnn.ctypes.data if nv else None, sw.ctypes.data if nv else None))
+            if output_mesh_smoothing_weights:
+                point["wnn"], point["sw"] = wnn, sw
+        if mesh_smoothing_iters is not None:                                    # reconstruct.rs:1261-1279, beta = 1
+            _check(L, L.ss_surface_laplacian_smoothing_f32(s, int(mesh_smoothing_iters), C.c_float(1.0), None))
+        verts = rec.mesh.vertices
+        if mesh_smoothing_iters:
+            verts = np.empty((nv, 3), np.float32)
+            _check(L, L.ss_surface_copy_vertices(s, verts.ctypes.data))
+        if compute_normals:                                                     # reconstruct.rs:1282-1342
+            _check(L, L.ss_surface_compute_normals_f32(s, int(bool(sph_normals))))
+            raw = np.empty((nv, 3), np.float32)
+            if nv:
+                _check(L, L.ss_surface_copy_normals(s, raw.ctypes.data))
+            if normals_smoothing_iters is not None:
+                _check(L, L.ss_surface_smooth_normals_f32(s, int(normals_smoothing_iters)))
+                sm = np.empty((nv, 3), np.float32)
+                if nv:
+                    _check(L, L.ss_surface_copy_normals(s, sm.ctypes.data))
+                point["normals"] = sm
+                if output_raw_normals:
+                    point["raw_normals"] = raw
+            else:
+                point["normals"] = raw
+        inside = rec.particle_inside_aabb
+        for name, a in attributes.items():                                      # reconstruct.rs:1345-1391 (filtered_quantity)
+            vals = np.ascontiguousarray(a[inside]) if inside is not None else a
+            dim = 1 if vals.ndim == 1 else 3
+            out = np.empty(nv if dim == 1 else (nv, 3), np.float32)
+            _check(L, L.ss_surface_interpolate_quantity_f32(s, vals.ctypes.data if len(vals) else None, dim, 1, out.ctypes.data if nv else None))
+            point[name] = out
+        rec.normals = point.get("normals")
+        mesh = TriMesh3d(verts, rec.mesh.triangles)
+        return MeshWithData(mesh, point, {}), rec
+    finally:
+        ctx.free_surface(s)

@@ -53,6 +53,17 @@ struct DevBuf {
 
 struct HostGrid { float mn[3], mx[3]; float cell; int64_t np[3], nc[3]; };
 
+// State of the most recent reconstruction that the post-processing entries (ss_post.cuh) need, and their scratch.
+struct PostScratch {
+    int valid = 0;                   // the splat bins in the context scratch belong to frame `ss_context::frame`
+    int partitioned = 0;
+    SsDev D{};
+    uint32_t nsub = 0, M = 0;
+    float sphere_mass = 0.f;         // 4/3 pi r^3 rho0 (reconstruct.rs:1126-1129)
+    DevBuf keys_a, keys_b, flag, scan, vals, out, tmpv;
+    void release_all() { for (DevBuf *b : { &keys_a, &keys_b, &flag, &scan, &vals, &out, &tmpv }) b->release(); }
+};
+
 struct ss_context {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -71,6 +82,8 @@ struct ss_context {
     // the analogue of the reference's ReconstructionWorkspace, workspace.rs:12-79)
     DevBuf o_verts, o_tris, o_vkeys, o_rho, o_verts2, o_vkeys2, o_normals;
     uint64_t hint_nv = 0, hint_nt = 0, hint_bc = 0;
+    uint64_t frame = 0;              // serial of the last call that rewrote the scratch
+    PostScratch post;
 };
 
 #include <mutex>
@@ -86,7 +99,9 @@ struct ss_surface {
     HostGrid grid{}, subgrid{};
     int S = 0;
     DevBuf verts, tris, vkeys, rho, normals, nbr_off, nbr_idx;
-    int has_normals = 0, has_neighbors = 0;
+    DevBuf weights, adj_row, adj_idx, inc_row, inc_idx;      // post-processing: smoothing weights, vertex->vertex / vertex->triangle CSR
+    int has_normals = 0, has_neighbors = 0, has_weights = 0, has_adj = 0, has_inc = 0;
+    uint64_t frame = 0;              // ss_context::frame of the reconstruction that produced this surface
     uint64_t n_neighbors = 0;
     std::vector<uint8_t> inside_aabb;
     std::vector<int64_t> sub_flat; std::vector<uint64_t> sub_count; std::vector<uint8_t> sub_sparse, sub_owned;
@@ -212,6 +227,7 @@ extern "C" void ss_context_destroy(ss_context *c) {
                        &c->vmask, &c->voff, &c->vblk_off, &c->tblk_off, &c->tile_tab, &c->brick_rng, &c->bstate, &c->flag_ls, &c->off_ls, &c->list_ls, &c->flag_mc, &c->flag_fix, &c->off_mc, &c->off_fix, &c->list_mc, &c->list_fix, &c->wflag, &c->brick_seen, &c->fix_list, &c->nflag, &c->bkeys_a, &c->bkeys_b, &c->bids_a, &c->bids_b, &c->bcount, &c->remap, &c->keep, &c->newid,
                        &c->err, &c->pairs, &c->o_verts, &c->o_tris, &c->o_vkeys, &c->o_rho, &c->o_verts2, &c->o_vkeys2, &c->o_normals };
     for (DevBuf *b : bufs) b->release();
+    c->post.release_all();
     for (auto &ev : c->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -480,6 +496,7 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     CK(cudaEventRecord(c->ev[2], st));
     out->nv = out->nt = 0; out->nsub = 0;
     out->owner = c;
+    c->post.valid = 0; out->frame = ++c->frame;
     out->rho = c->o_rho; c->o_rho = DevBuf(); out->verts = c->o_verts; c->o_verts = DevBuf();
     out->tris = c->o_tris; c->o_tris = DevBuf(); out->vkeys = c->o_vkeys; c->o_vkeys = DevBuf();
     out->rho.ensure(std::max<uint64_t>(n, 1) * 4);
@@ -833,6 +850,13 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     }
     out->nv = nv_final; out->nt = ttotal;
     c->hint_nv = vtotal; c->hint_nt = ttotal; c->hint_bc = bc;
+    {
+        // the splat bins stay in the scratch until the next call on this context: ss_post.cuh queries them
+        const float r3p = fmulr(fmulr(p->particle_radius, p->particle_radius), p->particle_radius);
+        c->post.D = D; c->post.nsub = nsub; c->post.M = M; c->post.partitioned = part.enabled;
+        c->post.sphere_mass = fmulr(fmulr(fmulr(4.0f, 1.04719755119659774615f), r3p), p->rest_density);
+        c->post.valid = 1;
+    }
     if (c->sph_normals && nv_final) {
         // SPH normals at the vertices (pipeline post-processing step, splashsurf/src/reconstruct.rs:1287-1294); sphere rest mass
         // 4/3 pi r^3 rho0 as in reconstruct.rs:1126-1129
@@ -887,6 +911,7 @@ extern "C" int ss_levelset_tile_f32(ss_context *c, const float *xyz, const float
     try {
         CK(cudaSetDevice(c->device));
         cudaStream_t st = c->stream;
+        c->post.valid = 0; ++c->frame;                       // this entry rewrites the bins in the scratch
         SsDev D{};
         for (int d = 0; d < 3; ++d) { D.gmin[d] = global_min[d]; D.nsd[d] = (int)subdomain_ijk[d] + 1; }
         D.c = cube_size; D.h = h; D.h2 = fmulr(h, h); D.h2m = fmulr(D.h2, 1.01f); D.rest_mass = rest_mass;
@@ -1134,6 +1159,7 @@ extern "C" void ss_surface_free(ss_surface *s) {
         }
     }
     s->verts.release(); s->tris.release(); s->vkeys.release(); s->rho.release(); s->normals.release(); s->nbr_off.release(); s->nbr_idx.release();
+    s->weights.release(); s->adj_row.release(); s->adj_idx.release(); s->inc_row.release(); s->inc_idx.release();
     delete s;
 }
 
@@ -1218,3 +1244,5 @@ extern "C" int ss_surface_copy_neighbor_lists(const ss_surface *s, uint64_t *off
     return rc;
 }
 extern "C" int ss_surface_timings(const ss_surface *s, ss_timings *o) { if (!s || !o) return SS_ERR_INVALID_PARAMETER; *o = s->tm; return SS_OK; }
+
+#include "ss_post.cuh"

@@ -1,0 +1,154 @@
+"""GPU tests of the device post-processing entries through the C ABI / the pipeline mirror, against
+oracle/postprocess.py (pinned against the reference pipeline, tests/test_oracle_postprocess.py).  The kernels themselves are
+also stepped on the CPU by tests/test_post_emulation.py.  Tolerance: 2e-5 relative (f32 sums in a different order)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+REL = 2e-5
+
+
+def _key_order(keys):
+    k = np.asarray(keys).reshape(len(keys), -1)
+    return np.lexsort(tuple(k[:, c] for c in range(k.shape[1] - 1, -1, -1)))
+
+
+def compare_point_fields(fields_a, keys_a, fields_b, keys_b, tol=REL):
+    """Compares per-vertex arrays of two meshes with the same vertex set in different orders (matched by MC edge key)."""
+    oa, ob = _key_order(keys_a), _key_order(keys_b)
+    assert np.array_equal(np.asarray(keys_a)[oa], np.asarray(keys_b)[ob])
+    worst = {}
+    for name in fields_b:
+        a = np.asarray(fields_a[name], dtype=np.float64)[oa]
+        b = np.asarray(fields_b[name], dtype=np.float64)[ob]
+        assert a.shape == b.shape, name
+        assert not np.isnan(a).any() and not np.isnan(b).any(), name
+        err = float(np.abs(a - b).max()) / max(float(np.abs(b).max()), 1.0)
+        worst[name] = err
+        assert err <= tol, (name, err)
+    return worst
+
+
+def test_compare_helper_matches_permuted_copy():
+    """CPU self-test of the matching helper used by the GPU tests below."""
+    rng = np.random.default_rng(0)
+    keys = rng.permutation(40 * 4).reshape(40, 4).astype(np.int64)
+    f = {"a": rng.normal(size=40).astype(np.float32), "v": rng.normal(size=(40, 3)).astype(np.float32)}
+    perm = rng.permutation(40)
+    compare_point_fields({k: v[perm] for k, v in f.items()}, keys[perm], f, keys)
+    bad = {k: v[perm].copy() for k, v in f.items()}
+    bad["a"][3] += 1.0
+    with pytest.raises(AssertionError):
+        compare_point_fields(bad, keys[perm], f, keys)
+
+
+def _oracle_pipeline(oracle_mod, x, kw, post, attributes=None):
+    from oracle import postprocess as pp
+    o = oracle_mod.reconstruct(x, **kw)
+    assert o["rc"] == 0
+    inside = o.get("particle_inside_aabb")
+    xf = x[inside] if inside is not None else x
+    attrs = {k: (v[inside] if inside is not None else v) for k, v in (attributes or {}).items()}
+    _, h, _ = oracle_mod.absolute_params(kw["particle_radius"], kw["smoothing_length"], kw["cube_size"])
+    out = pp.pipeline(xf, o["particle_densities"], o["vertices"], o["triangles"], particle_radius=kw["particle_radius"], rest_density=1000.0,
+                      compact_support_radius=float(h), attributes=attrs, sph_normals_fn=oracle_mod.sph_normals, **post)
+    return o, out
+
+
+CASES = [
+    ("weights_smoothing_sphnormals", dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.75, subdomain_num_cubes_per_dim=32,
+                                          subdomain_grid_auto_disable=False),
+     dict(mesh_smoothing_weights=True, mesh_smoothing_weights_normalization=13.0, mesh_smoothing_iters=5, compute_normals=True,
+          sph_normals=True, normals_smoothing_iters=3)),
+    ("unweighted_even_iterations_area_normals", dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.6),
+     dict(mesh_smoothing_weights=False, mesh_smoothing_iters=4, compute_normals=True, sph_normals=False, normals_smoothing_iters=None)),
+    ("weights_only_no_smoothing", dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.9),
+     dict(mesh_smoothing_weights=True, mesh_smoothing_weights_normalization=9.0, mesh_smoothing_iters=None, compute_normals=True,
+          sph_normals=True, normals_smoothing_iters=None)),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,kw,post", CASES, ids=[c[0] for c in CASES])
+def test_pipeline_postprocessing_matches_oracle(ss, oracle_mod, name, kw, post):
+    from splashsurf_b200 import synthetic
+    x = synthetic.splash((14, 12, 13), 4, 0.025, 201)
+    rng = np.random.default_rng(202)
+    attributes = {"vel": rng.normal(size=x.shape).astype(np.float32), "temp": (x[:, 1] * 3 + 1).astype(np.float32)}
+    o, ref = _oracle_pipeline(oracle_mod, x, kw, post, attributes)
+    m, rec = ss.reconstruction_pipeline(x, attributes_to_interpolate=attributes, **kw, **post, output_mesh_smoothing_weights=True,
+                                        output_raw_normals=True, with_debug=True)
+    got = dict(m.point_attributes)
+    got["vertices"] = m.mesh.vertices
+    want = {k: v for k, v in ref.items() if k in got}
+    assert set(want) >= {"vertices", "vel", "temp", "normals"}
+    compare_point_fields(got, rec.vertex_edge_keys, want, o["vertex_keys"], 5e-5 if post.get("sph_normals") else REL)
+    # the raw mesh stays available in the reconstruction object and the smoothing really moved the vertices
+    assert np.array_equal(rec.mesh.triangles, m.mesh.triangles)
+    if post.get("mesh_smoothing_iters"):
+        assert np.abs(rec.mesh.vertices - m.mesh.vertices).max() > 1e-4
+    else:
+        assert np.array_equal(rec.mesh.vertices, m.mesh.vertices)
+
+
+@pytest.mark.gpu
+def test_pipeline_with_particle_aabb_filters_attributes(ss, oracle_mod):
+    from splashsurf_b200 import synthetic
+    x = synthetic.splash((16, 12, 12), 3, 0.025, 211)
+    kw = dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.75, aabb_min=[-0.05, -0.05, -0.05], aabb_max=[0.55, 1.5, 0.7])
+    post = dict(mesh_smoothing_weights=True, mesh_smoothing_iters=2, compute_normals=False)
+    attributes = {"temp": (x[:, 0] - x[:, 2]).astype(np.float32)}
+    o, ref = _oracle_pipeline(oracle_mod, x, kw, post, attributes)
+    assert o.get("particle_inside_aabb") is not None and not o["particle_inside_aabb"].all()
+    m, rec = ss.reconstruction_pipeline(x, attributes_to_interpolate=attributes, **kw, **post, with_debug=True)
+    compare_point_fields({"vertices": m.mesh.vertices, "temp": m.point_attributes["temp"]}, rec.vertex_edge_keys,
+                         {"vertices": ref["vertices"], "temp": ref["temp"]}, o["vertex_keys"])
+
+
+@pytest.mark.gpu
+def test_c_abi_smoothing_with_explicit_weights_and_connectivity(ss, oracle_mod):
+    """ss_surface_laplacian_smoothing_f32 with caller weights / beta, ss_surface_vertex_connectivity, and the stale-surface error."""
+    from oracle import postprocess as pp
+    from splashsurf_b200 import synthetic
+    x = synthetic.splash((12, 12, 12), 2, 0.025, 221)
+    kw = dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.75)
+    ctx = ss.Context()
+    L = ctx._L
+    p = ss.make_params(**kw)
+    s = ctx.reconstruct_raw(x.ctypes.data, len(x), p)
+    try:
+        nv, nt = L.ss_surface_num_vertices(s), L.ss_surface_num_triangles(s)
+        v0 = np.empty((nv, 3), np.float32); t = np.empty((nt, 3), np.uint64)
+        assert L.ss_surface_copy_vertices(s, v0.ctypes.data) == 0 and L.ss_surface_copy_triangles_u64(s, t.ctypes.data) == 0
+        # connectivity: same sets as the reference's, ascending per vertex
+        n_idx = C.c_uint64()
+        off = np.empty(nv + 1, np.uint64)
+        assert L.ss_surface_vertex_connectivity(s, off.ctypes.data, None, C.byref(n_idx)) == 0
+        idx = np.empty(n_idx.value, np.uint32)
+        assert L.ss_surface_vertex_connectivity(s, off.ctypes.data, idx.ctypes.data, C.byref(n_idx)) == 0
+        roff, radj = pp.vertex_vertex_connectivity(t, nv)
+        assert np.array_equal(off.astype(np.int64), roff)
+        for i in range(0, nv, 11):
+            assert np.array_equal(idx[int(off[i]):int(off[i + 1])], np.sort(radj[roff[i]:roff[i + 1]]))
+        # smoothing with explicit weights, beta = 0.8, odd and even iteration counts applied one after the other
+        w = np.random.default_rng(3).uniform(0, 1, nv).astype(np.float32)
+        want = v0
+        for iters in (3, 2):
+            assert L.ss_surface_laplacian_smoothing_f32(s, iters, C.c_float(0.8), w.ctypes.data) == 0
+            want = pp.laplacian_smoothing(want, roff, radj, iters, 0.8, w)
+            got = np.empty((nv, 3), np.float32)
+            assert L.ss_surface_copy_vertices(s, got.ctypes.data) == 0
+            assert np.abs(got.astype(np.float64) - want).max() <= REL
+        # a second reconstruction on the context retires the first surface's particle bins
+        s2 = ctx.reconstruct_raw(x.ctypes.data, len(x), p)
+        try:
+            assert L.ss_surface_compute_smoothing_weights_f32(s, C.c_float(13.0), None, None) == 6      # SS_ERR_INVALID_PARAMETER
+            assert b"bins" in L.ss_last_error()
+            assert L.ss_surface_compute_smoothing_weights_f32(s2, C.c_float(13.0), None, None) == 0
+            assert L.ss_surface_compute_normals_f32(s, 0) == 0                                          # mesh-only steps still work
+        finally:
+            ctx.free_surface(s2)
+    finally:
+        ctx.free_surface(s)
+        ctx.close()
