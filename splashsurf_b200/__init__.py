@@ -74,7 +74,12 @@ def load_library():
     if not os.path.exists(path):
         raise ImportError(f"{path} is missing: the CUDA extension has not been built "
                           f"(run `python -m splashsurf_b200.build`); there is no CPU fallback")
-    L = C.CDLL(path)
+    _LIB = _bind(C.CDLL(path))
+    return _LIB
+
+
+def _bind(L):
+    """Declares the C-ABI prototypes (include/splashsurf_b200.h) on a loaded library handle."""
     vp, u64, i64 = C.c_void_p, C.c_uint64, C.c_int64
     L.ss_abi_version.restype = C.c_int
     L.ss_last_error.restype = C.c_char_p
@@ -128,7 +133,6 @@ def load_library():
     L.ss_surface_vertex_connectivity.argtypes = [vp, vp, vp, C.POINTER(u64)]
     if L.ss_abi_version() != 1:
         raise ImportError("libsplashsurf_b200.so ABI version mismatch")
-    _LIB = L
     return L
 
 

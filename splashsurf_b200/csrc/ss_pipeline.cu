@@ -7,7 +7,9 @@
 #include "../../include/splashsurf_b200.h"
 #include "ss_kernels.cuh"
 
+#ifndef SS_HOST_EMUL               // (tests/emul/cuda_emul.h compiles this file with g++ to step the kernels on the CPU)
 #include <cub/cub.cuh>
+#endif
 #include <cfloat>
 #include <climits>
 #include <cstdio>
@@ -157,7 +159,10 @@ static int validate_params(const ss_params_f32 *p) {
 
 // ------------------------------------------------------------------ small launch helpers ----
 static inline unsigned nblk(uint64_t n, unsigned t) { return (unsigned)((n + t - 1) / t); }
-#define LAUNCH(ctx, kern, grid, block, ...) do { kern<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__); (ctx)->launches++; } while (0)
+#ifndef SS_LAUNCH
+#define SS_LAUNCH(kern, grid, block, stream, ...) kern<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#endif
+#define LAUNCH(ctx, kern, grid, block, ...) do { SS_LAUNCH(kern, grid, block, (ctx)->stream, __VA_ARGS__); (ctx)->launches++; } while (0)
 
 static void cub_sort_pairs(ss_context *c, const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout,
                            uint32_t n, int end_bit) {
@@ -351,14 +356,9 @@ extern "C" int ss_grid_for_reconstruction_f32(ss_context *c, const float *xyz, u
 
 // ------------------------------------------------------------------ templated launch helpers ----
 static void launch_levelset(ss_context *c, dim3 grid, const SsDev &D, const SsLsArgs &A, bool count, bool global) {
-    if (global) {
-        if (count) k_levelset<true, true><<<grid, SS_LS_THREADS, 0, c->stream>>>(D, A);
-        else k_levelset<false, true><<<grid, SS_LS_THREADS, 0, c->stream>>>(D, A);
-    } else {
-        if (count) k_levelset<true, false><<<grid, SS_LS_THREADS, 0, c->stream>>>(D, A);
-        else k_levelset<false, false><<<grid, SS_LS_THREADS, 0, c->stream>>>(D, A);
-    }
-    c->launches++;
+    void (*kern)(SsDev, SsLsArgs) = global ? (count ? k_levelset<true, true> : k_levelset<false, true>)
+                                           : (count ? k_levelset<true, false> : k_levelset<false, false>);
+    LAUNCH(c, kern, grid, SS_LS_THREADS, D, A);
 }
 
 // in-place exclusive scan of the per-particle neighbour counts (n + 1 entries, last = 0) -> CSR offsets; returns the total
@@ -1191,7 +1191,7 @@ extern "C" int ss_surface_copy_triangles_u64(const ss_surface *s, uint64_t *dst)
     cudaSetDevice(s->device);
     void *tmp = nullptr;
     if (cudaMalloc(&tmp, s->nt * 24) != cudaSuccess) return ss_fail(SS_ERR_OUT_OF_MEMORY, "cudaMalloc failed");
-    k_tris_to_u64<<<nblk(s->nt * 3, 256), 256>>>(s->nt * 3, s->tris.as<uint32_t>(), (unsigned long long *)tmp);
+    SS_LAUNCH(k_tris_to_u64, nblk(s->nt * 3, 256), 256, (cudaStream_t)0, s->nt * 3, s->tris.as<uint32_t>(), (unsigned long long *)tmp);
     cudaError_t e = cudaMemcpy(dst, tmp, s->nt * 24, cudaMemcpyDeviceToHost);
     cudaFree(tmp);
     if (e != cudaSuccess) return ss_fail(SS_ERR_CUDA, cudaGetErrorString(e));

@@ -1,0 +1,171 @@
+"""CPU execution of the CUDA sources (tests/emul/cuda_emul.h): the whole device pipeline -- host orchestration in
+ss_pipeline.cu and every kernel in ss_kernels.cuh / ss_post.cuh -- compiled with g++ and run thread by thread (CUDA threads
+as fibers, warp / block collectives resolved by a scheduler), then checked against the pinned oracle exactly like the GPU
+tests do.  This is how kernel logic is verified in the build container, which has no GPU; it is NOT a product path:
+the emulated library lives under tests/, is injected only by the fixture below, and is never timed.
+
+What it proves: the statements of the kernels compute the reference's results (bit-exact) for small inputs, for every
+code path the GPU tests cover.  What it cannot prove: anything about performance, memory-model races between warps of a
+block beyond barrier placement, or sm_100a code generation -- `pytest -m gpu` on the B200 remains the gate."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+EMUL_DIR = os.path.join(ROOT, "tests", "emul")
+CSRC = os.path.join(ROOT, "splashsurf_b200", "csrc")
+
+
+def build_emulated_library() -> str:
+    so = os.path.join(EMUL_DIR, "libsplashsurf_emul.so")
+    deps = [os.path.join(EMUL_DIR, "cuda_emul.h")] + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + \
+        [os.path.join(ROOT, "include", "splashsurf_b200.h")]
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    if not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-g", "-ffp-contract=off", "-fno-fast-math", "-w", "-x", "c++", "-DSS_HOST_EMUL",
+                               "-I" + cuda_inc, "-include", os.path.join(EMUL_DIR, "cuda_emul.h"), "-shared", "-fPIC", "-pthread",
+                               "-o", so, os.path.join(CSRC, "ss_pipeline.cu")])
+    return so
+
+
+@pytest.fixture(scope="module")
+def emu():
+    """splashsurf_b200 bound to the emulated library for the duration of this module."""
+    import splashsurf_b200 as ss
+    so = build_emulated_library()
+    saved_lib, saved_ctx = ss._LIB, dict(ss._DEFAULT_CTX)
+    ss._DEFAULT_CTX.clear()
+    ss._LIB = ss._bind(C.CDLL(so))
+    try:
+        yield ss
+    finally:
+        for ctx in ss._DEFAULT_CTX.values():
+            ctx.close()
+        ss._DEFAULT_CTX.clear()
+        ss._DEFAULT_CTX.update(saved_ctx)
+        ss._LIB = saved_lib
+
+
+def _parity(oracle_mod, g, o, S=64):
+    return oracle_mod.mesh_parity(g.mesh.vertices, g.mesh.triangles, g.vertex_edge_keys, o["vertices"], o["triangles"], o["vertex_keys"], S)
+
+
+def _check_bit_exact(emu, oracle_mod, p, kw, exact_everywhere=False, tile_batch=None):
+    ctx = emu.Context()
+    try:
+        ctx.set_levelset_exact_everywhere(exact_everywhere)
+        if tile_batch:
+            ctx.set_tile_batch(tile_batch)
+        g = emu.reconstruct_surface(p, with_debug=True, context=ctx, **kw)
+    finally:
+        ctx.close()
+    o = oracle_mod.reconstruct(p, **kw)
+    if o["used_decomposition"]:
+        assert np.array_equal(g.subdomains["flat"], o["subdomain_flat"]) and np.array_equal(g.subdomains["count"], o["subdomain_count"])
+        assert np.array_equal(g.subdomains["sparse"], o["subdomain_sparse"])
+    assert np.array_equal(g.particle_densities, o["particle_densities"])
+    m = _parity(oracle_mod, g, o, kw.get("subdomain_num_cubes_per_dim", 64))
+    assert m["keys_equal"] and m["triangles_equal"] and m["n_not_bitexact"] == 0, m
+    return g, o
+
+
+@pytest.mark.parametrize("case", ["cfg1_ref", "global_cube_ref", "global_autodisable_ref"])
+def test_emulated_matches_reference_fixture(emu, oracle_mod, case):
+    """Same assertions as tests/test_gpu_parity.py::test_cuda_matches_reference_fixture (outputs of the reference binary)."""
+    gold = load_golden(case)
+    g = emu.reconstruct_surface(gold["particles"], with_debug=True, **gold["kwargs"])
+    assert np.array_equal(g.grid.aabb.min, gold["grid_min"]) and g.grid.ncells_per_dim == gold["grid_ncells"].tolist()
+    assert np.array_equal(g.particle_densities, gold["densities"])
+    m = oracle_mod.mesh_parity(g.mesh.vertices, g.mesh.triangles, g.vertex_edge_keys, gold["vertices"], gold["triangles"], gold["keys"],
+                               gold["kwargs"].get("subdomain_num_cubes_per_dim", 64))
+    assert m["keys_equal"] and m["triangles_equal"], m
+    assert m["n_interior_not_bitexact"] == 0 and m["max_abs"] <= 2e-6, m
+
+
+def _splash(*a):
+    from splashsurf_b200 import synthetic as syn
+    return syn.splash(*a)
+
+
+def _cube(*a):
+    from splashsurf_b200 import synthetic as syn
+    return syn.jittered_cube(*a)
+
+
+BASE = dict(particle_radius=0.025, smoothing_length=2.0)
+SEEDED = [
+    ("certify_default", lambda: _cube(12, 0.025, 301), dict(BASE, cube_size=0.5), {}),
+    ("exact_everywhere", lambda: _cube(11, 0.025, 302), dict(BASE, cube_size=0.5), dict(exact_everywhere=True)),
+    ("scalar_arithmetic", lambda: _splash((10, 10, 10), 2, 0.025, 303), dict(BASE, cube_size=0.6, simd=False), {}),
+    ("S20_partial_last_brick", lambda: _splash((10, 10, 10), 2, 0.025, 304),
+     dict(BASE, cube_size=0.6, subdomain_num_cubes_per_dim=20, subdomain_grid_auto_disable=False), {}),
+    ("S50_partial_last_brick", lambda: _splash((10, 10, 10), 2, 0.025, 305),
+     dict(BASE, cube_size=0.6, subdomain_num_cubes_per_dim=50, subdomain_grid_auto_disable=False), {}),
+    ("S16_tile_batches_of_2", lambda: _splash((9, 9, 9), 2, 0.025, 306),
+     dict(BASE, cube_size=0.75, subdomain_num_cubes_per_dim=16, subdomain_grid_auto_disable=False), dict(tile_batch=2)),
+    ("l22_c11_S24", lambda: _splash((9, 9, 9), 2, 0.025, 307), dict(particle_radius=0.025, smoothing_length=2.2, cube_size=1.1,
+                                                                   subdomain_num_cubes_per_dim=24), {}),
+    ("fine_c025", lambda: _splash((6, 6, 6), 1, 0.025, 308), dict(BASE, cube_size=0.25), {}),
+    ("global_no_decomposition", lambda: _splash((9, 9, 9), 2, 0.025, 309), dict(BASE, cube_size=0.75, subdomain_grid=False), {}),
+    ("threshold_03_density_850", lambda: _cube(10, 0.025, 310), dict(BASE, cube_size=0.5, iso_surface_threshold=0.3, rest_density=850.0), {}),
+]
+
+
+@pytest.mark.parametrize("name,gen,kw,opts", SEEDED, ids=[s[0] for s in SEEDED])
+def test_emulated_bit_exact_vs_oracle(emu, oracle_mod, name, gen, kw, opts):
+    _check_bit_exact(emu, oracle_mod, gen(), kw, **opts)
+
+
+def test_emulated_aabb_filter_and_edge_cases(emu, oracle_mod):
+    p = _splash((10, 10, 10), 2, 0.025, 320)
+    kw = dict(BASE, cube_size=0.6, aabb_min=[-0.05, -0.05, -0.05], aabb_max=[0.4, 1.2, 0.45])
+    g, o = _check_bit_exact(emu, oracle_mod, p, kw)
+    assert np.array_equal(g.particle_inside_aabb, o["particle_inside_aabb"]) and not g.particle_inside_aabb.all()
+    kw = dict(BASE, cube_size=0.5, subdomain_grid_auto_disable=False)
+    g = emu.reconstruct_surface(np.zeros((0, 3), np.float32), **kw)                      # empty input
+    assert g.mesh.nvertices == 0 and g.mesh.ncells == 0 and g.grid.ncells_per_dim == [64, 64, 64]
+    g, _ = _check_bit_exact(emu, oracle_mod, np.array([[0, 0, 0], [3, 3, 3]], np.float32), kw)   # two far-apart particles
+    assert g.mesh.nvertices == 252
+    # > 512 candidates around one brick: the oversized-candidate path of the level-set kernel
+    _check_bit_exact(emu, oracle_mod, np.random.default_rng(1).normal(0, 0.004, (600, 3)).astype(np.float32), kw)
+    with pytest.raises(emu.SplashsurfError) as e:
+        emu.reconstruct_surface(np.zeros((4, 3), np.float32), particle_radius=0.025, smoothing_length=2.0, cube_size=0.0)
+    assert e.value.code == 1
+
+
+def test_emulated_neighbor_lists_normals_and_tile_tap(emu, oracle_mod):
+    p = _splash((9, 9, 9), 2, 0.025, 330)
+    kw = dict(BASE, cube_size=0.6)
+    o = oracle_mod.reconstruct(p, want_neighbors=True, **kw)
+    g = emu.reconstruct_surface(p, global_neighborhood_list=True, **kw)
+    off, idx = o["neighbors"]
+    assert np.array_equal(g.particle_neighbors.offsets.astype(np.int64), off)
+    assert np.array_equal(g.particle_neighbors.indices.astype(np.int64), idx)
+    g = emu.reconstruct_surface(p, sph_normals=True, **kw)
+    ref = oracle_mod.sph_normals(p, g.particle_densities, g.mesh.vertices, compact_support_radius=0.1,
+                                 particle_rest_mass=float(oracle_mod.sph_rest_mass(0.025)))
+    assert np.abs(g.normals - ref).max() <= 2e-5
+    # the reference's hot-loop fixture (benches/benches/bench_grid_loop.rs:203-262) through ss_levelset_tile_f32
+    gl = load_golden("grid_loop_subdomain_33")
+    common = dict(global_min=gl["global_min"], cube_size=gl["cell_size"], subdomain_ijk=gl["subdomain_ijk"], subdomain_cubes=64)
+    for simd in (True, False):
+        t = emu.density_grid_loop(gl["particles"], gl["densities"], compact_support_radius=gl["h"], particle_rest_mass=gl["rest_mass"], simd=simd, **common)
+        ref = oracle_mod.levelset_tile(gl["particles"], gl["densities"], subdomain_min=gl["subdomain_min"], h=gl["h"], rest_mass=gl["rest_mass"],
+                                       mode=0 if simd else 1, **common)
+        assert np.array_equal(t, ref)
+
+
+# ------------------------------------------------------------------ post-processing through the same entry points ----
+def test_emulated_postprocessing_pipeline(emu, oracle_mod):
+    """The GPU post-processing tests (tests/test_zz_gpu_postprocess.py) executed against the emulated library."""
+    import test_zz_gpu_postprocess as T
+    for name, kw, post in T.CASES:
+        T.test_pipeline_postprocessing_matches_oracle(emu, oracle_mod, name, kw, post)
+    T.test_pipeline_with_particle_aabb_filters_attributes(emu, oracle_mod)
+    T.test_c_abi_smoothing_with_explicit_weights_and_connectivity(emu, oracle_mod)

@@ -236,16 +236,3 @@ def test_cuda_global_neighborhood_list(ss, oracle_mod):
         assert np.array_equal(g.particle_neighbors.indices.astype(np.int64), idx)
         assert g.particle_neighbors[7] == idx[off[7]:off[8]].tolist()
         assert np.array_equal(g.particle_densities, o["particle_densities"])
-
-
-@pytest.mark.parametrize("S", [20, 50])
-def test_cuda_subdomain_size_not_multiple_of_8(ss, oracle_mod, S):
-    """Tiles whose point count is not 8k+1 take the level-set path without extension bricks (partial last brick)."""
-    from splashsurf_b200 import synthetic as syn
-    p = syn.splash((18, 18, 18), 4, 0.025, 140 + S)
-    kw = dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.6, subdomain_num_cubes_per_dim=S, subdomain_grid_auto_disable=False)
-    o = oracle_mod.reconstruct(p, **kw)
-    g = ss.reconstruct_surface(p, with_debug=True, **kw)
-    assert np.array_equal(g.particle_densities, o["particle_densities"])
-    m = _parity(oracle_mod, g, o, S)
-    assert m["keys_equal"] and m["triangles_equal"] and m["n_not_bitexact"] == 0, m

@@ -83,6 +83,13 @@ def test_pipeline_postprocessing_matches_oracle(ss, oracle_mod, name, kw, post):
     got["vertices"] = m.mesh.vertices
     want = {k: v for k, v in ref.items() if k in got}
     assert set(want) >= {"vertices", "vel", "temp", "normals"}
+    if post.get("compute_normals") and not post.get("sph_normals") and post.get("mesh_smoothing_iters"):
+        # Area-weighted normals of a smoothed mesh amplify the 1-ulp differences of the smoothed vertices by
+        # 1 / (edge length) on sliver triangles, so they are checked on the device's own vertices instead.
+        from oracle import postprocess as pp
+        want.pop("normals")
+        mine = pp.vertex_normals(m.mesh.vertices, m.mesh.triangles)
+        assert np.abs(got["normals"].astype(np.float64) - mine).max() <= REL
     compare_point_fields(got, rec.vertex_edge_keys, want, o["vertex_keys"], 5e-5 if post.get("sph_normals") else REL)
     # the raw mesh stays available in the reconstruction object and the smoothing really moved the vertices
     assert np.array_equal(rec.mesh.triangles, m.mesh.triangles)
