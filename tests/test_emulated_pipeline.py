@@ -169,3 +169,109 @@ def test_emulated_postprocessing_pipeline(emu, oracle_mod):
         T.test_pipeline_postprocessing_matches_oracle(emu, oracle_mod, name, kw, post)
     T.test_pipeline_with_particle_aabb_filters_attributes(emu, oracle_mod)
     T.test_c_abi_smoothing_with_explicit_weights_and_connectivity(emu, oracle_mod)
+
+
+# ------------------------------------------------------------------ slab partition (multi-GPU entries), ranks run one after another ----
+def _virtual_ranks(emu, oracle_mod, x, kw, world, use_callback, force_cuts=None):
+    """Runs the per-rank library calls of splashsurf_b200.distributed.Runner._step_multi for `world` slabs in this process
+    (the exchange is replaced by selecting each rank's receive set directly) and welds the per-rank meshes like rank 0 does."""
+    from splashsurf_b200 import _Grid
+    from splashsurf_b200.distributed import make_plan
+    ctx = emu.Context()
+    L = ctx._L
+    p = emu.make_params(**kw)
+    corners = np.stack([x.min(axis=0), x.max(axis=0)]).astype(np.float32)
+    grid = _Grid()
+    assert L.ss_grid_for_reconstruction_f32(ctx._h, corners.ctypes.data, 2, C.byref(p), C.byref(grid)) == 0
+    S = int(p.subdomain_num_cubes_per_dim)
+    ncells = [int(v) for v in grid.cells_per_dim]
+    plan0 = make_plan(ncells, S, float(p.cube_size), float(p.compact_support_radius), None, world)
+    ax = plan0.axis
+    sub = float(np.float32(np.float32(p.cube_size) * np.float32(S)))
+    layer = np.floor((x[:, ax].astype(np.float64) - float(grid.aabb_min[ax])) / sub).astype(np.int64)
+    hist = np.bincount(np.clip(layer, 0, plan0.nsub_axis - 1), minlength=plan0.nsub_axis)
+    plan = make_plan(ncells, S, float(p.cube_size), float(p.compact_support_radius), hist, world)
+    if force_cuts is not None:
+        plan.cuts = list(force_cuts)
+    recv = []
+    for r in range(world):
+        lo, hi = plan.recv_range(r)
+        recv.append(np.ascontiguousarray(x[(layer >= lo) & (layer < hi)]))          # ascending global order
+    # local maxima -> global maximum (the all-reduce MAX of the runner)
+    local_max = []
+    for r in range(world):
+        s = C.c_void_p()
+        lo, hi = plan.own(r)
+        assert L.ss_reconstruct_partition_f32(ctx._h, recv[r].ctypes.data if len(recv[r]) else None, len(recv[r]), C.byref(p), C.byref(grid),
+                                              ax, lo, hi, plan.halo, 0, 1, C.byref(s)) == 0, L.ss_last_error()
+        local_max.append(L.ss_surface_max_subdomain_particles(s))
+        ctx.free_surface(s)
+    gmax = max(local_max)
+    calls = []
+    CB = C.CFUNCTYPE(C.c_uint64, C.c_uint64, C.c_void_p)
+
+    def reduce_cb(local, user):
+        calls.append(int(local))
+        return gmax
+    cb = CB(reduce_cb)
+    vs, ks, ts, off = [], [], [], 0
+    for r in range(world):
+        s = C.c_void_p()
+        lo, hi = plan.own(r)
+        xp = recv[r].ctypes.data if len(recv[r]) else None
+        if use_callback:
+            rc = L.ss_reconstruct_partition_cb_f32(ctx._h, xp, len(recv[r]), C.byref(p), C.byref(grid), ax, lo, hi, plan.halo, cb, None, C.byref(s))
+        else:
+            rc = L.ss_reconstruct_partition_f32(ctx._h, xp, len(recv[r]), C.byref(p), C.byref(grid), ax, lo, hi, plan.halo, gmax, 0, C.byref(s))
+        assert rc == 0, L.ss_last_error()
+        nv, nt = L.ss_surface_num_vertices(s), L.ss_surface_num_triangles(s)
+        v = np.empty((nv, 3), np.float32); t = np.empty((nt, 3), np.uint32)
+        assert L.ss_surface_copy_vertices(s, v.ctypes.data) == 0 and L.ss_surface_copy_triangles_u32(s, t.ctypes.data) == 0
+        kp = L.ss_surface_device_vertex_keys(s)
+        k = np.frombuffer(C.string_at(kp, nv * 8), dtype=np.uint64).copy() if nv else np.empty(0, np.uint64)
+        vs.append(v); ks.append(k); ts.append(t + np.uint32(off)); off += nv
+        ctx.free_surface(s)
+    if use_callback:
+        assert len(calls) == world and sorted(calls) == sorted(int(m) for m in local_max)     # called once per rank, also by empty ranks
+    V, K, T = np.ascontiguousarray(np.concatenate(vs)), np.ascontiguousarray(np.concatenate(ks)), np.ascontiguousarray(np.concatenate(ts))
+    shift = (42, 22, 2)[ax]
+    coord = (K >> np.uint64(shift)) & np.uint64(0xFFFFF)
+    cand = np.nonzero(((K & np.uint64(3)) != ax) & np.isin(coord, [c * S for c in plan.cuts[1:-1]]))[0].astype(np.uint32)
+    nv_out = C.c_uint64(len(V))
+    assert L.ss_weld_meshes(ctx._h, V.ctypes.data, K.ctypes.data, len(V), T.ctypes.data, len(T), cand.ctypes.data if len(cand) else None,
+                            len(cand), C.byref(nv_out)) == 0
+    ctx.close()
+    nvg = int(nv_out.value)
+    K = K[:nvg]
+    keys4 = np.stack([(K >> np.uint64(42)) & np.uint64(0xFFFFF), (K >> np.uint64(22)) & np.uint64(0xFFFFF), (K >> np.uint64(2)) & np.uint64(0xFFFFF),
+                      K & np.uint64(3)], axis=1).astype(np.int64)
+    return V[:nvg], T.astype(np.uint64), keys4, plan, [len(a) for a in recv]
+
+
+@pytest.mark.parametrize("use_callback", [False, True], ids=["two_call", "callback"])
+def test_emulated_slab_partition_matches_single_device(emu, oracle_mod, use_callback):
+    from splashsurf_b200 import synthetic as syn
+    x = syn.dam_break((10, 6, 6), (14, 2, 6), 0.025, 401)                 # long along x: several subdomain layers
+    kw = dict(BASE, cube_size=0.75, subdomain_num_cubes_per_dim=16, subdomain_grid_auto_disable=False)
+    o = oracle_mod.reconstruct(x, **kw)
+    for world, cuts in ((2, None), (3, None)):
+        v, t, keys, plan, nrecv = _virtual_ranks(emu, oracle_mod, x, kw, world, use_callback, cuts)
+        assert plan.nsub_axis >= 3 and all(plan.cuts[r] < plan.cuts[r + 1] for r in range(world)), plan
+        m = oracle_mod.mesh_parity(v, t, keys, o["vertices"], o["triangles"], o["vertex_keys"], 16)
+        assert m["keys_equal"] and m["triangles_equal"] and m["n_not_bitexact"] == 0, (world, m)
+
+
+def test_emulated_slab_partition_with_idle_rank(emu, oracle_mod):
+    """A rank that owns no subdomain layer and receives no particle still makes every library call (and its max-reduce
+    callback), the situation that dead-locked the 8-rank run of round 1."""
+    from splashsurf_b200 import synthetic as syn
+    x = syn.dam_break((10, 6, 6), (14, 2, 6), 0.025, 402)
+    kw = dict(BASE, cube_size=0.75, subdomain_num_cubes_per_dim=16, subdomain_grid_auto_disable=False)
+    o = oracle_mod.reconstruct(x, **kw)
+    nlayers = (int(o["grid"]["ncells"][0]) + 15) // 16
+    cuts = [0, nlayers // 2, nlayers // 2, nlayers]                      # rank 1 owns nothing
+    for use_callback in (False, True):
+        v, t, keys, plan, nrecv = _virtual_ranks(emu, oracle_mod, x, kw, 3, use_callback, cuts)
+        assert nrecv[1] == 0
+        m = oracle_mod.mesh_parity(v, t, keys, o["vertices"], o["triangles"], o["vertex_keys"], 16)
+        assert m["keys_equal"] and m["triangles_equal"] and m["n_not_bitexact"] == 0, m
