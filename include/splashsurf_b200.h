@@ -199,6 +199,9 @@ int ss_surface_timings(const ss_surface *s, ss_timings *out);
  * - count_pairs: count in-support kernel evaluations into ss_timings.levelset_pairs (instrumented kernel). */
 int ss_context_set_tile_batch(ss_context *ctx, uint32_t max_tiles);
 int ss_context_set_levelset_exact_everywhere(ss_context *ctx, int on);
+/* Level-set launch structure: 0 (default) = fused certification + exact pass per brick (k_levelset); 1 = certification in its
+ * own barrier-light kernel followed by an exact pass over the boxes it could not certify (ss_certify.cuh).  Same results. */
+int ss_context_set_levelset_variant(ss_context *ctx, int variant);
 int ss_context_set_count_pairs(ss_context *ctx, int on);
 
 /* ---- SPH normals at the mesh vertices: SphInterpolator::interpolate_normals (sph_interpolation.rs:82-133) as used by the

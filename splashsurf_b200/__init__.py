@@ -111,6 +111,7 @@ def _bind(L):
     L.ss_surface_timings.argtypes = [vp, C.POINTER(_Timings)]
     L.ss_context_set_tile_batch.argtypes = [vp, C.c_uint32]
     L.ss_context_set_levelset_exact_everywhere.argtypes = [vp, C.c_int]
+    L.ss_context_set_levelset_variant.argtypes = [vp, C.c_int]
     L.ss_context_set_count_pairs.argtypes = [vp, C.c_int]
     L.ss_context_set_compute_sph_normals.argtypes = [vp, C.c_int]
     L.ss_surface_copy_normals.argtypes = [vp, vp]
@@ -238,6 +239,10 @@ class Context:
     def set_levelset_exact_everywhere(self, on: bool):
         """Evaluate every level-set grid point exactly (default: interior points are only classified)."""
         _check(self._L, self._L.ss_context_set_levelset_exact_everywhere(self._h, int(bool(on))))
+
+    def set_levelset_variant(self, variant: int):
+        """0: fused certify + exact level-set kernel (default); 1: separate certification kernel (same results)."""
+        _check(self._L, self._L.ss_context_set_levelset_variant(self._h, int(variant)))
 
     def set_count_pairs(self, on: bool):
         _check(self._L, self._L.ss_context_set_count_pairs(self._h, int(bool(on))))

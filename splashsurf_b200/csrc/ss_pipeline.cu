@@ -6,6 +6,7 @@
 // no CPU fallback: without a CUDA device every entry point fails with SS_ERR_NO_DEVICE.
 #include "../../include/splashsurf_b200.h"
 #include "ss_kernels.cuh"
+#include "ss_certify.cuh"
 
 #ifndef SS_HOST_EMUL               // (tests/emul/cuda_emul.h compiles this file with g++ to step the kernels on the CPU)
 #include <cub/cub.cuh>
@@ -73,12 +74,13 @@ struct ss_context {
     uint32_t max_tiles = 0;          // 0 = auto
     int64_t keep_tile_flat = -1;
     int ls_exact_all = 0;            // 1: evaluate every grid point exactly (no certification)
+    int ls_variant = 0;              // 1: certification in its own barrier-light kernel (ss_certify.cuh)
     int count_pairs = 0;             // 1: count in-support evaluations (work model; slower)
     int sph_normals = 0;             // 1: SPH normals at the mesh vertices (sph_interpolation.rs:82-133)
     // reusable scratch
     DevBuf xyz, xyz_f, filt_flag, filt_flag32, filt_off, aabb, cnt, off, key_a, key_b, val_a, val_b, cid, cub_tmp,
         sub_flat, sub_off, sub_sparse, sub_owned, gkey_a, gkey_b, gval_a, gval_b, flags, scan, spos, rho, tab_a, tab_b, rec, ksplit, batch_subs, tiles, vcnt,
-        tcnt, vmask, voff, vblk_off, tblk_off, tile_tab, brick_rng, bstate, flag_ls, off_ls, list_ls, flag_mc, flag_fix, off_mc, off_fix, list_mc, list_fix, wflag, brick_seen, fix_list, nflag, bkeys_a, bkeys_b, bids_a, bids_b, bcount, remap, keep, newid, err, pairs;
+        tcnt, vmask, voff, vblk_off, tblk_off, tile_tab, brick_rng, bstate, flag_ls, off_ls, list_ls, flag_mc, flag_fix, off_mc, off_fix, list_mc, list_fix, wflag, wstate, desc_ls, brick_seen, fix_list, nflag, bkeys_a, bkeys_b, bids_a, bids_b, bcount, remap, keep, newid, err, pairs;
     uint64_t launches = 0;
     // result buffers handed to surfaces and returned by ss_surface_free (avoids cudaMalloc/cudaFree per frame,
     // the analogue of the reference's ReconstructionWorkspace, workspace.rs:12-79)
@@ -229,7 +231,7 @@ extern "C" void ss_context_destroy(ss_context *c) {
     DevBuf *bufs[] = { &c->xyz, &c->xyz_f, &c->filt_flag, &c->filt_flag32, &c->filt_off, &c->aabb, &c->cnt, &c->off, &c->key_a, &c->key_b,
                        &c->val_a, &c->val_b, &c->cid, &c->cub_tmp, &c->sub_flat, &c->sub_off, &c->sub_sparse, &c->sub_owned, &c->gkey_a, &c->gkey_b, &c->gval_a, &c->gval_b, &c->flags, &c->scan,
                        &c->spos, &c->rho, &c->tab_a, &c->tab_b, &c->rec, &c->ksplit, &c->batch_subs, &c->tiles, &c->vcnt, &c->tcnt,
-                       &c->vmask, &c->voff, &c->vblk_off, &c->tblk_off, &c->tile_tab, &c->brick_rng, &c->bstate, &c->flag_ls, &c->off_ls, &c->list_ls, &c->flag_mc, &c->flag_fix, &c->off_mc, &c->off_fix, &c->list_mc, &c->list_fix, &c->wflag, &c->brick_seen, &c->fix_list, &c->nflag, &c->bkeys_a, &c->bkeys_b, &c->bids_a, &c->bids_b, &c->bcount, &c->remap, &c->keep, &c->newid,
+                       &c->vmask, &c->voff, &c->vblk_off, &c->tblk_off, &c->tile_tab, &c->brick_rng, &c->bstate, &c->flag_ls, &c->off_ls, &c->list_ls, &c->flag_mc, &c->flag_fix, &c->off_mc, &c->off_fix, &c->list_mc, &c->list_fix, &c->wflag, &c->wstate, &c->desc_ls, &c->brick_seen, &c->fix_list, &c->nflag, &c->bkeys_a, &c->bkeys_b, &c->bids_a, &c->bids_b, &c->bcount, &c->remap, &c->keep, &c->newid,
                        &c->err, &c->pairs, &c->o_verts, &c->o_tris, &c->o_vkeys, &c->o_rho, &c->o_verts2, &c->o_vkeys2, &c->o_normals };
     for (DevBuf *b : bufs) b->release();
     c->post.release_all();
@@ -241,6 +243,10 @@ extern "C" void ss_context_destroy(ss_context *c) {
 extern "C" int ss_context_keep_levelset_tile(ss_context *c, int64_t flat) { if (!c) return SS_ERR_INVALID_PARAMETER; c->keep_tile_flat = flat; return SS_OK; }
 extern "C" int ss_context_set_tile_batch(ss_context *c, uint32_t m) { if (!c) return SS_ERR_INVALID_PARAMETER; c->max_tiles = m; return SS_OK; }
 extern "C" int ss_context_set_levelset_exact_everywhere(ss_context *c, int on) { if (!c) return SS_ERR_INVALID_PARAMETER; c->ls_exact_all = on ? 1 : 0; return SS_OK; }
+extern "C" int ss_context_set_levelset_variant(ss_context *c, int v) {
+    if (!c || v < 0 || v > 1) return ss_fail(SS_ERR_INVALID_PARAMETER, "level-set variant must be 0 or 1");
+    c->ls_variant = v; return SS_OK;
+}
 extern "C" int ss_context_set_compute_sph_normals(ss_context *c, int on) { if (!c) return SS_ERR_INVALID_PARAMETER; c->sph_normals = on ? 1 : 0; return SS_OK; }
 extern "C" int ss_surface_copy_normals(const ss_surface *s, float *dst) {
     if (!s || !dst) return SS_ERR_INVALID_PARAMETER;
@@ -487,9 +493,11 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     D.keep_lo = part.enabled ? (int)std::max<int64_t>(part.own_lo - part.halo, 0) : 0;
     D.keep_hi = part.enabled ? (int)std::min<int64_t>(part.own_hi + part.halo, nsd[D.part_axis]) : (int)nsd[0];
     if (!part.enabled) { D.part_axis = 0; D.keep_lo = 0; D.keep_hi = (int)nsd[0]; }
+    int certify_runs = 0;              // upper bound of the candidate runs of a brick (variant 1 keeps one per lane)
     {
         int per_axis = ss_floor_div(6 + D.R, D.be) - ss_floor_div(-D.R, D.be) + 2;
         if (per_axis * per_axis > 128) return ss_fail(SS_ERR_INVALID_PARAMETER, "internal: too many candidate bin runs per brick");
+        certify_runs = per_axis * per_axis;
     }
 
     const bool want_nbrs = p->global_neighborhood_list != 0 && !part.enabled;
@@ -712,7 +720,36 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
         A.wflag = nullptr; A.fix_bricks = nullptr; A.bstate = c->bstate.as<uint8_t>();
         const uint32_t n_work = build_worklist(c, D, nbatch);
         A.work_list = c->list_ls.as<uint32_t>();
-        if (n_work) { launch_levelset(c, dim3(n_work), D, A, c->count_pairs != 0, global_mode); ++ls_launches; }
+        const bool split_certify = c->ls_variant == 1 && !exact_all && certify_runs <= 32;
+        if (n_work && !split_certify) { launch_levelset(c, dim3(n_work), D, A, c->count_pairs != 0, global_mode); ++ls_launches; }
+        if (n_work && split_certify) {
+            // variant 1 (ss_certify.cuh): certification kernel, then the exact pass over the boxes it could not certify
+            const uint32_t nbr_c = nbatch * nbricks;
+            c->wstate.ensure((size_t)nbr_c * SS_LS_WARPS); c->wflag.ensure((size_t)nbr_c * SS_LS_WARPS); c->desc_ls.ensure((size_t)n_work * 16);
+            c->flag_fix.ensure((size_t)nbr_c * 4); c->off_fix.ensure((size_t)nbr_c * 4 + 4); c->fix_list.ensure((size_t)nbr_c * 4);
+            CK(cudaMemsetAsync(c->wstate.p, 0, (size_t)nbr_c * SS_LS_WARPS, st));
+            LAUNCH(c, k_compact_desc, nblk(nbr_c, 256), 256, D, c->flag_ls.as<uint32_t>(), c->off_ls.as<uint32_t>(), nbr_c, c->desc_ls.as<uint4>());
+            SsCertArgs CA{};
+            CA.bin_start = A.bin_start; CA.bin_end = A.bin_end; CA.rec = A.rec; CA.tile_tab = A.tile_tab; CA.brick_rng = A.brick_rng;
+            CA.work_desc = c->desc_ls.as<uint4>(); CA.tiles = A.tiles; CA.wstate = c->wstate.as<uint8_t>();
+            if (global_mode) LAUNCH(c, k_certify<true>, n_work, SS_LS_THREADS, D, CA);
+            else LAUNCH(c, k_certify<false>, n_work, SS_LS_THREADS, D, CA);
+            ++ls_launches;
+            LAUNCH(c, k_wstate_reduce, nblk(nbr_c, 256), 256, c->wstate.as<uint8_t>(), nbr_c, c->bstate.as<uint8_t>(), c->flag_fix.as<uint32_t>(),
+                   c->wflag.as<uint8_t>());
+            cub_excl_scan(c, c->flag_fix.as<uint32_t>(), c->off_fix.as<uint32_t>(), nbr_c);
+            LAUNCH(c, k_compact_list, nblk(nbr_c, 256), 256, c->flag_fix.as<uint32_t>(), c->off_fix.as<uint32_t>(), nbr_c, c->fix_list.as<uint32_t>());
+            uint32_t ln[2] = { 0, 0 };
+            CK(cudaMemcpyAsync(&ln[0], c->off_fix.as<uint32_t>() + (nbr_c - 1), 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(&ln[1], c->flag_fix.as<uint32_t>() + (nbr_c - 1), 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (ln[0] + ln[1]) {
+                SsLsArgs F = A;
+                F.mode = SS_LS_FIX; F.wflag = c->wflag.as<uint8_t>(); F.fix_bricks = c->fix_list.as<uint32_t>();
+                launch_levelset(c, dim3(ln[0] + ln[1]), D, F, c->count_pairs != 0, global_mode);
+                ++ls_launches;
+            }
+        }
         out->tm.bricks_levelset += n_work;
         // bricks that can carry surface (for marching cubes) / markers next to outside points (for the fix-up sweep)
         const uint32_t nbr_b = nbatch * nbricks;

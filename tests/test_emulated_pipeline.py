@@ -56,10 +56,11 @@ def _parity(oracle_mod, g, o, S=64):
     return oracle_mod.mesh_parity(g.mesh.vertices, g.mesh.triangles, g.vertex_edge_keys, o["vertices"], o["triangles"], o["vertex_keys"], S)
 
 
-def _check_bit_exact(emu, oracle_mod, p, kw, exact_everywhere=False, tile_batch=None):
+def _check_bit_exact(emu, oracle_mod, p, kw, exact_everywhere=False, tile_batch=None, variant=0):
     ctx = emu.Context()
     try:
         ctx.set_levelset_exact_everywhere(exact_everywhere)
+        ctx.set_levelset_variant(variant)
         if tile_batch:
             ctx.set_tile_batch(tile_batch)
         g = emu.reconstruct_surface(p, with_debug=True, context=ctx, **kw)
@@ -120,6 +121,12 @@ SEEDED = [
 @pytest.mark.parametrize("name,gen,kw,opts", SEEDED, ids=[s[0] for s in SEEDED])
 def test_emulated_bit_exact_vs_oracle(emu, oracle_mod, name, gen, kw, opts):
     _check_bit_exact(emu, oracle_mod, gen(), kw, **opts)
+
+
+@pytest.mark.parametrize("name,gen,kw,opts", [s for s in SEEDED if s[0] != "exact_everywhere"], ids=[s[0] for s in SEEDED if s[0] != "exact_everywhere"])
+def test_emulated_split_certification_variant(emu, oracle_mod, name, gen, kw, opts):
+    """Level-set variant 1 (ss_certify.cuh: separate certification kernel + exact pass over the failed boxes)."""
+    _check_bit_exact(emu, oracle_mod, gen(), kw, variant=1, **opts)
 
 
 def test_emulated_aabb_filter_and_edge_cases(emu, oracle_mod):

@@ -58,6 +58,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", type=int, default=100)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--variant", type=int, default=0, help="level-set launch structure (ss_context_set_levelset_variant)")
     ap.add_argument("--max-points", type=float, default=6e6, help="skip cases whose grid has more points than this (emulation is slow)")
     a = ap.parse_args()
     import oracle
@@ -82,6 +83,7 @@ def main():
             continue
         ctx = ss.Context()
         ctx.set_levelset_exact_everywhere(opts["exact"])
+        ctx.set_levelset_variant(a.variant)
         if opts["batch"]:
             ctx.set_tile_batch(opts["batch"])
         try:
