@@ -158,6 +158,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS), help="BASELINE config (default cfg4 = the metric's 50 M dam break)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--levelset-variant", type=int, default=0, choices=[0, 1],
+                    help="0: fused certify + exact level-set kernel (default); 1: separate certification kernel (ss_certify.cuh)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -182,6 +184,8 @@ def main():
     import splashsurf_b200 as ss
     from splashsurf_b200 import distributed as ssd
     ctx = ss.Context(local_rank)
+    if args.levelset_variant:
+        ctx.set_levelset_variant(args.levelset_variant)
     kw = dict(RECON_KW)
     if WORKLOADS.get(args.workload):
         kw.update(WORKLOADS[args.workload][1])
@@ -296,6 +300,7 @@ def main():
                            "particles": int(n_total), "r": kw["particle_radius"],
                            "cube_size": f"{kw['cube_size']}r", "smoothing_length": "2.0r", "iso": 0.6, "subdomain_cubes": 64,
                            "parallelism": f"subdomain slabs x{world}" if world > 1 else "single GPU",
+                           "levelset_variant": int(args.levelset_variant),
                            "l2": "inputs (600 MB) and tiles (GBs) exceed the 126 MB L2; no flush needed"},
                 "mesh": {"vertices": int(nv_g if nv_g is not None else nv), "triangles": int(nt_g if nt_g is not None else nt), "subdomains": int(n_sub)},
                 "wall_ms_per_step": wall_ms_max / args.steps, "step_ms_rank0": step_ms, "stage_ms_last_step": stage,

@@ -536,6 +536,19 @@ __device__ __forceinline__ float ss_box_dist2(const SsLanePoint &L, const float4
 //     g(s) = max(0, G0 + G1 s + G2 s^2 + G3 s^3) <= f(sqrt(s))   for all s >= 0
 // (tools/fit_kernel_bound.py: linear program over a fine grid; g captures 94 % of the kernel's volume integral, zero at
 // q = 0.755).  G0 carries an extra -1e-5 safety offset; the comparison keeps a 1e-4 relative margin on top.
+#ifdef SS_EMUL_STATS   // work statistics of the certification sweep, CPU executor only (tools/certify_stats.py)
+// per outcome o (0 certified in ring 0, 1 in ring 1, 2 not certified): [5 o + 0] boxes, [5 o + 1] words visited in ring 0,
+// [5 o + 2] candidates evaluated in ring 0, [5 o + 3], [5 o + 4] same for ring 1
+static std::atomic<unsigned long long> ss_emul_stats[15];
+extern "C" void ss_emul_stats_read(unsigned long long *out, int reset) { for (int k = 0; k < 15; ++k) { out[k] = ss_emul_stats[k]; if (reset) ss_emul_stats[k] = 0; } }
+#define SS_STATS_DECL unsigned long long st_[4] = { 0, 0, 0, 0 };
+#define SS_STATS_WORD(ring, mword) do { st_[2 * (ring)] += 1; st_[2 * (ring) + 1] += __popc(mword); } while (0)
+#define SS_STATS_DONE(outcome) do { if (lane == 0) { ss_emul_stats[5 * (outcome)] += 1; for (int q_ = 0; q_ < 4; ++q_) ss_emul_stats[5 * (outcome) + 1 + q_] += st_[q_]; } } while (0)
+#else
+#define SS_STATS_DECL
+#define SS_STATS_WORD(ring, mword)
+#define SS_STATS_DONE(outcome)
+#endif
 #define SS_G0 0.98199678f
 #define SS_G1 -4.74153665f
 #define SS_G2 8.78317336f
@@ -545,6 +558,7 @@ __device__ __forceinline__ bool ss_certify_box(const SsDev &P, const SsLanePoint
     const float inv_h2 = P.a_hinv * P.a_hinv;
     float sum = 0.0f;
     const int nwords = (C + 31) >> 5;
+    SS_STATS_DECL
     // ring 0: candidates within 0.55 h of the warp box; only if some lane is still short, ring 1: 0.55 h .. 0.8 h.
     // Words are visited starting at the brick's own bin (closest particles first) and the warp stops as soon as every lane
     // has enough.
@@ -556,6 +570,7 @@ __device__ __forceinline__ bool ss_certify_box(const SsDev &P, const SsLanePoint
             bool keep = false;
             if (c < C) { const float db2 = ss_box_dist2(L, s_rec[c]); keep = (db2 < r_hi2) && !(db2 < r_lo2); }
             uint32_t mword = __ballot_sync(0xffffffffu, keep);
+            SS_STATS_WORD(ring, mword);
             if (!mword) continue;
             while (mword) {
                 const int cc = w * 32 + __ffs(mword) - 1;
@@ -567,10 +582,11 @@ __device__ __forceinline__ bool ss_certify_box(const SsDev &P, const SsLanePoint
                 sum = fmaf(fmaxf(g, 0.0f), r.w, sum);
             }
             // lanes outside the tile (clipped boxes) do not need a value
-            if (__all_sync(0xffffffffu, !L.valid || (sum > cert))) return true;
+            if (__all_sync(0xffffffffu, !L.valid || (sum > cert))) { SS_STATS_DONE(ring); return true; }
         }
         r_lo2 = r_hi2; r_hi2 = 0.64f * P.h2;
     }
+    SS_STATS_DONE(2);
     return false;
 }
 
