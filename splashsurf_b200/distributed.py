@@ -135,16 +135,46 @@ def _view(ptr, shape, typestr, device):
     if not ptr or int(np.prod(shape)) == 0:
         dt = {"<f4": torch.float32, "<u4": torch.int32, "<i4": torch.int32, "<i8": torch.int64, "<u8": torch.int64}[typestr]
         return torch.empty(tuple(shape), dtype=dt, device=device)
-    return torch.as_tensor(_CudaView(ptr, shape, typestr.replace("<u4", "<i4").replace("<u8", "<i8")), device=device)
+    typestr = typestr.replace("<u4", "<i4").replace("<u8", "<i8")
+    if device.type != "cuda":        # host memory: only when the runner is driven by the tests' CPU executor of the CUDA sources
+        dt = np.dtype(typestr)
+        buf = (C.c_char * (int(np.prod(shape)) * dt.itemsize)).from_address(int(ptr))
+        return torch.from_numpy(np.frombuffer(buf, dtype=dt).reshape(tuple(shape)))
+    return torch.as_tensor(_CudaView(ptr, shape, typestr), device=device)
+
+
+class _HostEvent:
+    """Stands in for torch.cuda.Event when the runner works on host memory (tests only)."""
+
+    def record(self):
+        import time
+        self.t = time.perf_counter()
+
+    def elapsed_time(self, other) -> float:
+        return (other.t - self.t) * 1e3
+
+
+def _event(device):
+    return torch.cuda.Event(enable_timing=True) if device.type == "cuda" else _HostEvent()
+
+
+def _sync(device):
+    if device.type == "cuda":
+        torch.cuda.synchronize()
+
+
+def _pinned(t: torch.Tensor, device) -> torch.Tensor:
+    return t.pin_memory() if device.type == "cuda" else t
 
 
 class Runner:
     """Drives one reconstruct step on this rank's GPU (world == 1: plain C-ABI call)."""
 
-    def __init__(self, ctx, params, world: int, rank: int, local_rank: int, group=None):
+    def __init__(self, ctx, params, world: int, rank: int, local_rank: int, group=None, device=None):
         self.ctx, self.params, self.world, self.rank, self.local_rank, self.group = ctx, params, world, rank, local_rank, group
         self._out_v = self._out_t = None
-        self.device = torch.device("cuda", local_rank)
+        # `device` is only overridden by the tests that drive the runner over gloo with the CPU executor of the CUDA sources
+        self.device = torch.device("cuda", local_rank) if device is None else torch.device(device)
         self.last_plan: Optional[SlabPlan] = None
 
     # -- input sharding used by the bench: rank r holds a contiguous range of global particle indices
@@ -179,9 +209,9 @@ class Runner:
         out["nsub_owned"] = int(owned.sum())
         if copy_out and self.world == 1:
             if self._out_v is None or self._out_v.numel() < nv * 3:
-                self._out_v = torch.empty(max(nv * 3, 1), dtype=torch.float32).pin_memory()
+                self._out_v = _pinned(torch.empty(max(nv * 3, 1), dtype=torch.float32), self.device)
             if self._out_t is None or self._out_t.numel() < nt * 3:
-                self._out_t = torch.empty(max(nt * 3, 1), dtype=torch.int32).pin_memory()
+                self._out_t = _pinned(torch.empty(max(nt * 3, 1), dtype=torch.int32), self.device)
             rc = L.ss_surface_copy_vertices(s, C.c_void_p(self._out_v.data_ptr()))
             rc |= L.ss_surface_copy_triangles_u32(s, C.c_void_p(self._out_t.data_ptr()))
             if rc:
@@ -199,9 +229,9 @@ class Runner:
 
     def _step_multi(self, x: torch.Tensor, copy_out: bool) -> dict:
         L, p, world, rank = self.ctx._L, self.params, self.world, self.rank
-        t_ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        t_ev = [_event(self.device) for _ in range(3)]
         t_ev[0].record()
-        xd = x.to(self.device, non_blocking=True) if x.device.type != "cuda" else x
+        xd = x.to(self.device, non_blocking=True) if x.device.type != self.device.type else x
         # 1. global bounding box -> the grid of ALL particles (lib.rs:476-516), identical on every rank
         if xd.shape[0]:
             mn, mx = xd.min(dim=0).values, xd.max(dim=0).values
@@ -226,7 +256,7 @@ class Runner:
         own_lo, own_hi = plan.own(rank)
         # 4. local maximum subdomain population -> global maximum (sparse rule, dense_subdomains.rs:1242-1251).  Every rank
         #    makes the same two library calls and the same all-reduce, also ranks that received no particles.
-        torch.cuda.synchronize()
+        _sync(self.device)
         s = C.c_void_p()
         rc = L.ss_reconstruct_partition_f32(self.ctx._h, C.c_void_p(recv.data_ptr()), C.c_uint64(recv.shape[0]), C.byref(p),
                                             C.byref(grid), ax, own_lo, own_hi, plan.halo, C.c_uint64(0), 1, C.byref(s))
@@ -244,7 +274,7 @@ class Runner:
             raise RuntimeError((L.ss_last_error() or b"").decode())
         try:
             t_ev[2].record()
-            torch.cuda.synchronize()
+            _sync(self.device)
             out = self._collect(s, False, n_local=x.shape[0])
             # events on torch's stream bracket the whole step: exchange (NCCL) + both host-synchronous library calls
             out["device_ms"] = t_ev[0].elapsed_time(t_ev[2])
@@ -297,19 +327,19 @@ class Runner:
         cut_pts = torch.tensor([c * S for c in plan.cuts[1:-1]], dtype=torch.int64, device=self.device)
         cand = torch.nonzero((eaxis != plan.axis) & torch.isin(coord, cut_pts)).view(-1).to(torch.int32).contiguous()
         nv_out = C.c_uint64(V.shape[0])
-        torch.cuda.synchronize()
+        _sync(self.device)
         rc = L.ss_weld_meshes(self.ctx._h, C.c_void_p(V.data_ptr()), C.c_void_p(K.data_ptr()), C.c_uint64(V.shape[0]), C.c_void_p(T.data_ptr()),
                               C.c_uint64(T.shape[0]), C.c_void_p(cand.data_ptr()), C.c_uint64(cand.shape[0]), C.byref(nv_out))
         if rc:
             raise RuntimeError((L.ss_last_error() or b"").decode())
         nvg, ntg = int(nv_out.value), int(T.shape[0])
         if self._out_v is None or self._out_v.numel() < nvg * 3:
-            self._out_v = torch.empty(max(nvg * 3, 1), dtype=torch.float32).pin_memory()
+            self._out_v = _pinned(torch.empty(max(nvg * 3, 1), dtype=torch.float32), self.device)
         if self._out_t is None or self._out_t.numel() < ntg * 3:
-            self._out_t = torch.empty(max(ntg * 3, 1), dtype=torch.int32).pin_memory()
+            self._out_t = _pinned(torch.empty(max(ntg * 3, 1), dtype=torch.int32), self.device)
         self._out_v[:nvg * 3].copy_(V[:nvg].view(-1), non_blocking=True)
         self._out_t[:ntg * 3].copy_(T.view(-1), non_blocking=True)
-        torch.cuda.synchronize()
+        _sync(self.device)
         return {"d2h_bytes": nvg * 12 + ntg * 12, "nv_global": nvg, "nt_global": ntg, "keys_global": K[:nvg]}
 
     def gathered_mesh(self, nv: int, nt: int):

@@ -30,6 +30,7 @@ def build_emulated_library() -> str:
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-g", "-ffp-contract=off", "-fno-fast-math", "-w", "-x", "c++", "-DSS_HOST_EMUL",
                                "-I" + cuda_inc, "-include", os.path.join(EMUL_DIR, "cuda_emul.h"), "-shared", "-fPIC", "-pthread",
+                               "-Wl,-Bsymbolic",      # its cuda* definitions must win over a libcudart that torch may have loaded
                                "-o", so, os.path.join(CSRC, "ss_pipeline.cu")])
     return so
 
@@ -282,3 +283,62 @@ def test_emulated_slab_partition_with_idle_rank(emu, oracle_mod):
         assert nrecv[1] == 0
         m = oracle_mod.mesh_parity(v, t, keys, o["vertices"], o["triangles"], o["vertex_keys"], 16)
         assert m["keys_equal"] and m["triangles_equal"] and m["n_not_bitexact"] == 0, m
+
+
+# ------------------------------------------------------------------ the multi-GPU runner end to end: gloo ranks + CPU executor ----
+RUNNER_WORKER = r'''
+import ctypes as C, json, os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["SS_ROOT"])
+import splashsurf_b200 as ss
+from splashsurf_b200 import distributed as ssd, synthetic as syn
+ss._LIB = ss._bind(C.CDLL(os.environ["SS_EMUL_SO"]))          # the CUDA sources on the CPU executor (tests only)
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+case = json.loads(os.environ["SS_CASE"])
+p_all = getattr(syn, case["gen"])(*[tuple(a) if isinstance(a, list) else a for a in case["args"]])
+ctx = ss.Context(0)
+runner = ssd.Runner(ctx, ss.make_params(**case["kw"]), world, rank, 0, device="cpu")
+x = torch.from_numpy(runner.take_local(p_all))
+for it in range(2):                                             # second step reuses the pooled buffers
+    out = runner.step(x, copy_out=True)
+if rank == 0:
+    v, t = runner.gathered_mesh(out["nv_global"], out["nt_global"])
+    np.savez(os.path.join(os.environ["SS_OUT"], "mesh.npz"), v=v, t=t, k=out["keys_global"].numpy(), cuts=np.asarray(out["plan"].cuts))
+json.dump({"recv": out["recv_particles"], "nsub_owned": out["nsub_owned"]}, open(os.path.join(os.environ["SS_OUT"], f"rank{rank}.json"), "w"))
+ctx.close()
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("world,case", [
+    (2, dict(gen="dam_break", args=[[10, 6, 6], [14, 2, 6], 0.025, 501],
+             kw=dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.75, subdomain_num_cubes_per_dim=16, subdomain_grid_auto_disable=False))),
+    (3, dict(gen="jittered_cube", args=[7, 0.025, 502],     # two subdomain layers for three ranks: one rank stays idle
+             kw=dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.75, subdomain_num_cubes_per_dim=16, subdomain_grid_auto_disable=False))),
+], ids=["2_ranks_dam_break", "3_ranks_one_idle"])
+def test_emulated_runner_over_gloo(tmp_path, oracle_mod, world, case):
+    """splashsurf_b200.distributed.Runner._step_multi as the bench drives it (plan, halo exchange, two library calls, max
+    all-reduce, mesh gather + weld), one process per rank over gloo, library = CPU executor; result vs the single-device oracle."""
+    import json
+    import sys
+    from splashsurf_b200 import synthetic as syn
+    so = build_emulated_library()
+    script = tmp_path / "worker.py"
+    script.write_text(RUNNER_WORKER)
+    env = dict(os.environ, SS_ROOT=ROOT, SS_OUT=str(tmp_path), SS_EMUL_SO=so, SS_CASE=json.dumps(case), SS_EMUL_THREADS="3", OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", str(29541 + world), str(script)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    m = np.load(tmp_path / "mesh.npz")
+    p_all = getattr(syn, case["gen"])(*[tuple(a) if isinstance(a, list) else a for a in case["args"]])
+    o = oracle_mod.reconstruct(p_all, **case["kw"])
+    K = m["k"].astype(np.uint64)
+    keys4 = np.stack([(K >> np.uint64(42)) & np.uint64(0xFFFFF), (K >> np.uint64(22)) & np.uint64(0xFFFFF), (K >> np.uint64(2)) & np.uint64(0xFFFFF),
+                      K & np.uint64(3)], axis=1).astype(np.int64)
+    par = oracle_mod.mesh_parity(m["v"], m["t"].astype(np.uint64), keys4, o["vertices"], o["triangles"], o["vertex_keys"], 16)
+    assert par["keys_equal"] and par["triangles_equal"] and par["n_not_bitexact"] == 0, par
+    ranks = [json.load(open(tmp_path / f"rank{k}.json")) for k in range(world)]
+    if world == 3:
+        assert min(r_["nsub_owned"] for r_ in ranks) == 0, ranks          # the idle rank really was idle
