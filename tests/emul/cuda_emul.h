@@ -4,7 +4,7 @@
 //
 //     g++ -x c++ -DSS_HOST_EMUL -include tests/emul/cuda_emul.h splashsurf_b200/csrc/ss_pipeline.cu -> libsplashsurf_emul.so
 //
-// * every CUDA thread of a block runs as a fiber (ucontext); __syncthreads / __ballot_sync / __shfl_*_sync / __all_sync /
+// * every CUDA thread of a block runs as a fiber (a six-register stack switch on x86-64, ucontext elsewhere); __syncthreads / __ballot_sync / __shfl_*_sync / __all_sync /
 //   __syncwarp suspend the fiber until the other live threads of the block / warp have arrived, exactly the semantics the
 //   kernels rely on (a divergent or missing collective dead-locks the scheduler and aborts with a message);
 // * blocks of a launch are spread over host threads; __shared__ is thread-local static storage of the worker;
@@ -58,14 +58,50 @@ constexpr size_t kStack = 256 * 1024;
 enum State { READY, WARP_WAIT, BLOCK_WAIT, DONE };
 enum Op { OP_BALLOT, OP_ALL, OP_ANY, OP_SHFL, OP_SHFL_UP, OP_SHFL_DOWN, OP_SHFL_XOR, OP_SYNCWARP, OP_BAR, OP_BAR_OR };
 
+// Context switch: on x86-64 a six-register stack switch (no signal-mask system calls); ucontext elsewhere.
+#if defined(__x86_64__) && !defined(SS_EMUL_UCONTEXT)
+#define SS_EMUL_FAST_SWITCH 1
+extern "C" void ss_emul_switch(void **save_sp, void *load_sp);
+asm(R"(
+.text
+.globl ss_emul_switch
+.type ss_emul_switch,@function
+ss_emul_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size ss_emul_switch,.-ss_emul_switch
+)");
+#endif
+
 struct Fiber {
+#ifdef SS_EMUL_FAST_SWITCH
+    void *sp;
+#else
     ucontext_t ctx;
+#endif
     State state;
     int op, pred, arg;
     unsigned long long val, res;
 };
 struct Cta {
+#ifdef SS_EMUL_FAST_SWITCH
+    void *sched_sp = nullptr;
+#else
     ucontext_t sched;
+#endif
     Fiber *f = nullptr;
     char *stacks = nullptr;
     int n = 0, cur = 0;
@@ -80,10 +116,28 @@ struct Cta {
 };
 static thread_local Cta *g_cta = nullptr;
 
+static inline void to_scheduler(Cta *C, Fiber &F) {
+#ifdef SS_EMUL_FAST_SWITCH
+    ss_emul_switch(&F.sp, C->sched_sp);
+#else
+    swapcontext(&F.ctx, &C->sched);
+#endif
+}
+static inline void to_fiber(Cta *C, Fiber &F) {
+#ifdef SS_EMUL_FAST_SWITCH
+    ss_emul_switch(&C->sched_sp, F.sp);
+#else
+    swapcontext(&C->sched, &F.ctx);
+#endif
+}
 static void trampoline() {
     Cta *C = g_cta;
     C->entry(C->entry_arg);
     C->f[C->cur].state = DONE;
+#ifdef SS_EMUL_FAST_SWITCH
+    to_scheduler(C, C->f[C->cur]);                              // a finished fiber is never resumed
+    abort();
+#endif
 }
 
 [[noreturn]] static void deadlock(Cta *C) {
@@ -134,11 +188,21 @@ static void run_block(Cta *C, int nthreads, unsigned bdx, unsigned bdy) {
     C->n = nthreads;
     for (int t = 0; t < nthreads; ++t) {
         Fiber &F = C->f[t];
+#ifdef SS_EMUL_FAST_SWITCH
+        // initial frame: six callee-saved register slots, then the entry address that the first switch "returns" to;
+        // after that `ret` the stack pointer is 8 below a 16-byte boundary, as at any function entry
+        uintptr_t top = ((uintptr_t)(C->stacks + (size_t)(t + 1) * kStack)) & ~(uintptr_t)15;
+        void **frame = (void **)(top - 16 - 6 * sizeof(void *));
+        for (int q = 0; q < 6; ++q) frame[q] = nullptr;
+        frame[6] = (void *)&trampoline;
+        F.sp = (void *)frame;
+#else
         getcontext(&F.ctx);
         F.ctx.uc_stack.ss_sp = C->stacks + (size_t)t * kStack;
         F.ctx.uc_stack.ss_size = kStack;
         F.ctx.uc_link = &C->sched;
         makecontext(&F.ctx, trampoline, 0);
+#endif
         F.state = READY;
     }
     int live = nthreads;
@@ -148,7 +212,7 @@ static void run_block(Cta *C, int nthreads, unsigned bdx, unsigned bdy) {
             if (C->f[t].state != READY) continue;
             C->cur = t;
             threadIdx.x = (unsigned)t % bdx; threadIdx.y = ((unsigned)t / bdx) % bdy; threadIdx.z = (unsigned)t / (bdx * bdy);
-            swapcontext(&C->sched, &C->f[t].ctx);
+            to_fiber(C, C->f[t]);
             if (C->f[t].state == DONE) --live;
             progressed = true;
         }
@@ -175,7 +239,7 @@ static inline unsigned long long collective(State st, int op, unsigned long long
     Cta *C = g_cta;
     Fiber &F = C->f[C->cur];
     F.op = op; F.val = val; F.arg = arg; F.pred = pred; F.state = st;
-    swapcontext(&F.ctx, &C->sched);
+    to_scheduler(C, F);
     return F.res;
 }
 
