@@ -1,19 +1,15 @@
 // post_emul.cpp -- steps the per-thread post-processing kernels (splashsurf_b200/csrc/ss_post.cuh) and the binning kernels they
-// depend on (k_bin_keys, k_mark_starts, k_run_counts, k_records) on the CPU, thread by thread.  TEST INFRASTRUCTURE ONLY
+// depend on (k_bin_keys, k_mark_starts, k_run_counts, k_records) on the CPU executor (cuda_emul.h).  TEST INFRASTRUCTURE ONLY
 // (tests/test_post_emulation.py): it checks the kernels' indexing and arithmetic against the oracle without a GPU; the
 // product never links this file.  Sorts and scans (cub on the device) are done by numpy in the test.
-#include "host_shim.h"
+#include "cuda_emul.h"
 #include "../../splashsurf_b200/csrc/ss_kernels.cuh"
 #define SS_POST_KERNELS_ONLY
 #include "../../splashsurf_b200/csrc/ss_post.cuh"
 
-template <typename K, typename... A>
-static void run(uint64_t n, unsigned block, K kernel, A... args) {
-    blockDim.x = block;
-    const unsigned grid = (unsigned)((n + block - 1) / block);
-    gridDim.x = grid;
-    for (unsigned b = 0; b < grid; ++b)
-        for (unsigned t = 0; t < block; ++t) { blockIdx.x = b; threadIdx.x = t; kernel(args...); }
+template <typename... P, typename... A>
+static void run(uint64_t n, unsigned block, void (*kernel)(P...), A... args) {
+    emul::launch(dim3((unsigned)((n + block - 1) / block)), dim3(block), kernel, args...);
 }
 
 extern "C" {

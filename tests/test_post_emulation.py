@@ -1,7 +1,7 @@
 """CPU tests of the DEVICE post-processing kernels (splashsurf_b200/csrc/ss_post.cuh) without a GPU.
 
-tests/emul/post_emul.cpp compiles the kernel sources with g++ behind a host shim and steps them thread by thread; cub's
-sorts / scans are replaced by numpy.  The kernels are per-thread code (no warp or block collectives), so this executes the
+tests/emul/post_emul.cpp compiles the kernel sources with g++ on the CPU executor (tests/emul/cuda_emul.h) and launches
+single kernels; the sorts / scans between them are done by numpy.  The kernels are per-thread code (no warp or block collectives), so this executes the
 same statements the GPU does and checks their indexing (splat-bin queries, CSR construction, iteration buffers) and
 arithmetic against oracle/postprocess.py.  The product never uses this path (it is not a CPU fallback: the harness lives
 under tests/ and is not part of the library)."""
@@ -29,14 +29,14 @@ def _close(a, b, tol=REL):
 @pytest.fixture(scope="module")
 def emul():
     so = os.path.join(EMUL_DIR, "libpost_emul.so")
-    deps = [os.path.join(EMUL_DIR, "post_emul.cpp"), os.path.join(EMUL_DIR, "host_shim.h")] + \
+    deps = [os.path.join(EMUL_DIR, "post_emul.cpp"), os.path.join(EMUL_DIR, "cuda_emul.h")] + \
         [os.path.join(ROOT, "splashsurf_b200", "csrc", f) for f in ("ss_common.cuh", "ss_kernels.cuh", "ss_post.cuh")]
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
     if not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
         pytest.skip("CUDA headers not found")
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-w", "-I" + cuda_inc, "-shared", "-fPIC",
-                               "-o", so, deps[0]])
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-w", "-I" + cuda_inc, "-I" + EMUL_DIR, "-shared", "-fPIC",
+                               "-pthread", "-Wl,-Bsymbolic", "-o", so, deps[0]])
     L = C.CDLL(so)
     L.emul_sizeof_dev.restype = C.c_uint
     L.emul_dev_nbin_sub.restype = C.c_int
