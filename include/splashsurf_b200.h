@@ -243,6 +243,14 @@ int ss_surface_compute_normals_f32(ss_surface *s, int sph);
 /* par_laplacian_smoothing_normals_inplace (postprocessing.rs:56-97) on the surface's normals. */
 int ss_surface_smooth_normals_f32(ss_surface *s, uint32_t iterations);
 
+/* A surface around a caller-supplied mesh (verts nv x 3 f32, tris nt x 3 u32; host or device pointers), so that the mesh-only
+ * entries (laplacian smoothing with explicit / unit weights, area-weighted normals, normal smoothing, connectivity) serve the
+ * reference's free functions of postprocessing.rs / mesh.rs on any mesh.  No particles: the [bins] entries are rejected. */
+int ss_surface_from_mesh_f32(ss_context *ctx, const float *verts, uint64_t nv, const uint32_t *tris, uint64_t nt, ss_surface **out);
+
+/* Replaces the surface's normals by [num_vertices * 3] caller-supplied ones (then ss_surface_smooth_normals_f32 smooths any field). */
+int ss_surface_set_normals_f32(ss_surface *s, const float *normals);
+
 /* TriMesh3d::vertex_vertex_connectivity (mesh.rs:290-306) as CSR, neighbours ascending: offsets [num_vertices + 1],
  * indices [*n_indices]; pass indices = NULL to query *n_indices first. */
 int ss_surface_vertex_connectivity(ss_surface *s, uint64_t *offsets, uint32_t *indices, uint64_t *n_indices);

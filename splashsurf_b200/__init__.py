@@ -132,6 +132,8 @@ def _bind(L):
     L.ss_surface_compute_normals_f32.argtypes = [vp, C.c_int]
     L.ss_surface_smooth_normals_f32.argtypes = [vp, C.c_uint32]
     L.ss_surface_vertex_connectivity.argtypes = [vp, vp, vp, C.POINTER(u64)]
+    L.ss_surface_from_mesh_f32.argtypes = [vp, vp, u64, vp, u64, C.POINTER(vp)]
+    L.ss_surface_set_normals_f32.argtypes = [vp, vp]
     if L.ss_abi_version() != 1:
         raise ImportError("libsplashsurf_b200.so ABI version mismatch")
     return L
@@ -177,6 +179,94 @@ class TriMesh3d:
     @property
     def ncells(self) -> int:
         return len(self.triangles)
+
+    def copy(self) -> "TriMesh3d":
+        return TriMesh3d(self.vertices.copy(), self.triangles.copy())
+
+    def vertex_normals_parallel(self, context=None) -> np.ndarray:
+        """Area-weighted vertex normals on the device (TriMesh3d::par_vertex_normals, mesh.rs:799-906)."""
+        with _MeshSurface(self.vertices, self.triangles, context) as m:
+            _check(m.L, m.L.ss_surface_compute_normals_f32(m.s, 0))
+            out = np.empty((self.nvertices, 3), np.float32)
+            if len(out):
+                _check(m.L, m.L.ss_surface_copy_normals(m.s, out.ctypes.data))
+            return out
+
+    def vertex_vertex_connectivity(self, context=None) -> "VertexVertexConnectivity":
+        """Vertex-vertex connectivity computed on the device (mesh.rs:290-306; neighbours in ascending order)."""
+        with _MeshSurface(self.vertices, self.triangles, context) as m:
+            n = C.c_uint64()
+            off = np.empty(self.nvertices + 1, np.uint64)
+            _check(m.L, m.L.ss_surface_vertex_connectivity(m.s, off.ctypes.data, None, C.byref(n)))
+            idx = np.empty(n.value, np.uint32)
+            _check(m.L, m.L.ss_surface_vertex_connectivity(m.s, off.ctypes.data, idx.ctypes.data if len(idx) else None, C.byref(n)))
+        return VertexVertexConnectivity(off, idx, np.asarray(self.triangles), self.nvertices)
+
+
+class VertexVertexConnectivity:
+    """Mirrors pysplashsurf.VertexVertexConnectivity (CSR storage; the triangles are kept so that device functions taking only
+    a connectivity can rebuild it there)."""
+
+    def __init__(self, offsets: np.ndarray, indices: np.ndarray, triangles: np.ndarray, nvertices: int):
+        self.offsets, self.indices, self._triangles, self._nv = offsets, indices, triangles, int(nvertices)
+
+    def copy_connectivity(self) -> list:
+        return [self.indices[int(self.offsets[i]):int(self.offsets[i + 1])].tolist() for i in range(self._nv)]
+
+    take_connectivity = copy_connectivity
+
+
+class _MeshSurface:
+    """A device surface around an arbitrary triangle mesh (ss_surface_from_mesh_f32) for the mesh-only post-processing entries."""
+
+    def __init__(self, vertices, triangles, context=None):
+        self.ctx = context or default_context()
+        self.L = self.ctx._L
+        v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
+        t = np.ascontiguousarray(triangles).reshape(-1, 3)
+        if len(t) and int(t.max()) >= len(v):
+            raise ValueError("triangle index out of range")
+        t = np.ascontiguousarray(t, dtype=np.uint32)
+        self.s = C.c_void_p()
+        _check(self.L, self.L.ss_surface_from_mesh_f32(self.ctx._h, v.ctypes.data if len(v) else None, len(v), t.ctypes.data if len(t) else None,
+                                                       len(t), C.byref(self.s)))
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.ctx.free_surface(self.s)
+        return False
+
+
+def laplacian_smoothing_parallel(mesh, vertex_connectivity=None, *, iterations: int, beta: float = 1.0, weights, context=None) -> None:
+    """``pysplashsurf.laplacian_smoothing_parallel``: weighted Laplacian smoothing of ``mesh.vertices`` in place
+    (postprocessing.rs:17-53) on the device.  ``vertex_connectivity`` is accepted for signature parity; the device rebuilds it."""
+    m0 = mesh.mesh if isinstance(mesh, MeshWithData) else mesh
+    w = np.ascontiguousarray(weights, dtype=np.float32)
+    if len(w) != m0.nvertices:
+        raise ValueError("one weight per vertex is required")
+    with _MeshSurface(m0.vertices, m0.triangles, context) as m:
+        _check(m.L, m.L.ss_surface_laplacian_smoothing_f32(m.s, int(iterations), C.c_float(float(beta)), w.ctypes.data if len(w) else None))
+        out = np.empty((m0.nvertices, 3), np.float32)
+        _check(m.L, m.L.ss_surface_copy_vertices(m.s, out.ctypes.data if len(out) else None))
+    m0.vertices[...] = out
+
+
+def laplacian_smoothing_normals_parallel(normals: np.ndarray, vertex_connectivity: VertexVertexConnectivity, *, iterations: int, context=None) -> None:
+    """``pysplashsurf.laplacian_smoothing_normals_parallel``: smooths the (N, 3) float32 normal field in place
+    (postprocessing.rs:56-97) on the device."""
+    n = np.asarray(normals)
+    if n.dtype != np.float32 or n.ndim != 2 or n.shape[1] != 3 or len(n) != vertex_connectivity._nv:
+        raise ValueError("normals must be a float32 array of shape (num_vertices, 3)")
+    src = np.ascontiguousarray(n)
+    with _MeshSurface(np.zeros((len(n), 3), np.float32), vertex_connectivity._triangles, context) as m:
+        _check(m.L, m.L.ss_surface_set_normals_f32(m.s, src.ctypes.data if len(src) else None))
+        _check(m.L, m.L.ss_surface_smooth_normals_f32(m.s, int(iterations)))
+        out = np.empty_like(src)
+        if len(out):
+            _check(m.L, m.L.ss_surface_copy_normals(m.s, out.ctypes.data))
+    normals[...] = out
 
 
 class NeighborhoodLists:

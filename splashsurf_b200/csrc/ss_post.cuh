@@ -441,6 +441,50 @@ extern "C" int ss_surface_smooth_normals_f32(ss_surface *s, uint32_t iterations)
     } PP_CATCH
 }
 
+// Wraps a caller-supplied triangle mesh (host or device pointers: verts nv x 3 f32, tris nt x 3 u32) in a surface so that the
+// mesh-only entries above (ss_surface_laplacian_smoothing_f32 with explicit or unit weights, ss_surface_compute_normals_f32 with
+// sph = 0, ss_surface_smooth_normals_f32, ss_surface_vertex_connectivity) serve the reference's free functions
+// par_laplacian_smoothing_inplace / par_laplacian_smoothing_normals_inplace / par_vertex_normals / vertex_vertex_connectivity
+// on any mesh.  There are no particles behind such a surface: the [bins] entries fail with SS_ERR_INVALID_PARAMETER.
+extern "C" int ss_surface_from_mesh_f32(ss_context *c, const float *verts, uint64_t nv, const uint32_t *tris, uint64_t nt, ss_surface **out) {
+    if (!c || !out || (nv && !verts) || (nt && !tris)) return ss_fail(SS_ERR_INVALID_PARAMETER, "NULL argument");
+    *out = nullptr;
+    if (nv >= 0x7fffffffull || nt * 6 >= 0x7fffffffull) return ss_fail(SS_ERR_INDEX_TOO_SMALL, "mesh too large for device post-processing");
+    ss_surface *s = nullptr;
+    try {
+        CK(cudaSetDevice(c->device));
+        cudaStream_t st = c->stream;
+        s = new ss_surface();
+        s->owner = c; s->device = c->device; s->nv = nv; s->nt = nt; s->frame = 0;       // frame 0 never matches a reconstruction
+        s->verts.ensure(std::max<uint64_t>(nv, 1) * 12); s->tris.ensure(std::max<uint64_t>(nt, 1) * 12);
+        if (nv) CK(cudaMemcpyAsync(s->verts.p, verts, nv * 12, cudaMemcpyDefault, st));
+        if (nt) CK(cudaMemcpyAsync(s->tris.p, tris, nt * 12, cudaMemcpyDefault, st));
+        CK(cudaStreamSynchronize(st));
+        *out = s;
+        return SS_OK;
+    } catch (const SsCudaError &err) {
+        if (s) ss_surface_free(s);
+        cudaGetLastError();
+        return ss_fail(err.e == cudaErrorMemoryAllocation ? SS_ERR_OUT_OF_MEMORY : SS_ERR_CUDA, std::string(err.what) + ": " + cudaGetErrorString(err.e));
+    }
+}
+
+// Replaces the surface's normals by caller-supplied ones ([nv * 3], host or device), e.g. to smooth an arbitrary normal field
+// with ss_surface_smooth_normals_f32.
+extern "C" int ss_surface_set_normals_f32(ss_surface *s, const float *normals) {
+    int rc; ss_context *c = pp_context(s, false, &rc);
+    if (!c) return rc;
+    if (!normals && s->nv) return ss_fail(SS_ERR_INVALID_PARAMETER, "NULL argument");
+    try {
+        CK(cudaSetDevice(c->device));
+        s->normals.ensure(std::max<uint64_t>(s->nv, 1) * 12);
+        if (s->nv) CK(cudaMemcpyAsync(s->normals.p, normals, s->nv * 12, cudaMemcpyDefault, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        s->has_normals = 1;
+        return SS_OK;
+    } PP_CATCH
+}
+
 // Vertex -> vertex connectivity of the mesh as CSR (TriMesh3d::vertex_vertex_connectivity, mesh.rs:290-306; neighbours in
 // ascending order).  offsets: [nv + 1] u64, indices: [offsets[nv]] u32; pass indices = NULL to query the size first.
 extern "C" int ss_surface_vertex_connectivity(ss_surface *s, uint64_t *offsets, uint32_t *indices, uint64_t *n_indices) {

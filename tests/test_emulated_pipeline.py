@@ -177,6 +177,7 @@ def test_emulated_postprocessing_pipeline(emu, oracle_mod):
         T.test_pipeline_postprocessing_matches_oracle(emu, oracle_mod, name, kw, post)
     T.test_pipeline_with_particle_aabb_filters_attributes(emu, oracle_mod)
     T.test_c_abi_smoothing_with_explicit_weights_and_connectivity(emu, oracle_mod)
+    T.test_standalone_mesh_functions(emu, oracle_mod)
 
 
 # ------------------------------------------------------------------ slab partition (multi-GPU entries), ranks run one after another ----

@@ -159,3 +159,32 @@ def test_c_abi_smoothing_with_explicit_weights_and_connectivity(ss, oracle_mod):
     finally:
         ctx.free_surface(s)
         ctx.close()
+
+
+@pytest.mark.gpu
+def test_standalone_mesh_functions(ss, oracle_mod):
+    """The mirrors of pysplashsurf's free mesh functions (laplacian_smoothing_parallel, laplacian_smoothing_normals_parallel,
+    TriMesh3d.vertex_normals_parallel / vertex_vertex_connectivity) on a mesh that does not come from a device reconstruction."""
+    from oracle import postprocess as pp
+    from splashsurf_b200 import synthetic
+    x = synthetic.splash((9, 9, 9), 2, 0.025, 231)
+    o = oracle_mod.reconstruct(x, particle_radius=0.025, smoothing_length=2.0, cube_size=0.75)
+    v0, t = np.ascontiguousarray(o["vertices"], np.float32), np.ascontiguousarray(o["triangles"])
+    mesh = ss.TriMesh3d(v0.copy(), t.copy())
+    conn = mesh.vertex_vertex_connectivity()
+    roff, radj = pp.vertex_vertex_connectivity(t, len(v0))
+    assert np.array_equal(conn.offsets.astype(np.int64), roff)
+    lists = conn.copy_connectivity()
+    for i in range(0, len(v0), 13):
+        assert lists[i] == sorted(radj[roff[i]:roff[i + 1]].tolist())
+    n0 = mesh.vertex_normals_parallel()
+    assert np.abs(n0.astype(np.float64) - pp.vertex_normals(v0, t)).max() <= REL
+    w = np.random.default_rng(4).uniform(0, 1, len(v0)).astype(np.float32)
+    ss.laplacian_smoothing_parallel(mesh, conn, iterations=3, beta=0.7, weights=w)
+    assert np.abs(mesh.vertices.astype(np.float64) - pp.laplacian_smoothing(v0, roff, radj, 3, 0.7, w)).max() <= REL
+    n = n0.copy()
+    ss.laplacian_smoothing_normals_parallel(n, conn, iterations=2)
+    assert np.abs(n.astype(np.float64) - pp.laplacian_smoothing_normals(n0, roff, radj, 2)).max() <= REL
+    # particle queries are rejected on such a surface (no particles behind it)
+    with ss._MeshSurface(v0, t) as m:
+        assert m.L.ss_surface_compute_normals_f32(m.s, 1) == 6
