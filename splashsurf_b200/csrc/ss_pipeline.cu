@@ -32,10 +32,17 @@ struct DevBuf {
     void *p = nullptr; size_t cap = 0;
     template <typename T> T *as() const { return (T *)p; }
     void ensure(size_t bytes) {
+#ifdef SS_EMUL_GUARD                      // tests/emul: exact-size allocations in front of a guard page (overrun detection)
+        if (bytes == cap && p) return;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes;
+#else
         if (bytes <= cap) return;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
         size_t want = bytes + bytes / 8 + 256;
+#endif
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) { p = nullptr; throw SsCudaError{ e, "cudaMalloc", __FILE__, __LINE__ }; }
         cap = want;
@@ -43,7 +50,11 @@ struct DevBuf {
     // grow while preserving contents
     void grow_keep(size_t bytes, size_t used, cudaStream_t st) {
         if (bytes <= cap) return;
+#ifdef SS_EMUL_GUARD
+        size_t want = bytes;
+#else
         size_t want = std::max(bytes + bytes / 4, cap * 2) + 256;
+#endif
         void *q = nullptr;
         cudaError_t e = cudaMalloc(&q, want);
         if (e != cudaSuccess) throw SsCudaError{ e, "cudaMalloc", __FILE__, __LINE__ };

@@ -359,8 +359,29 @@ cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
 cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }
 const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
+#ifdef SS_EMUL_GUARD
+// Guarded allocator: the buffer ends (16-byte aligned) right in front of an inaccessible page, so that any read or write
+// past the requested size faults immediately; a header in front keeps the mapping size.  DevBuf allocates without slack
+// in this mode (ss_pipeline.cu), so "requested size" is what the host code really asked for.
+cudaError_t cudaMalloc(void **p, size_t n) {
+    const size_t page = 4096, need = ((n ? n : 1) + 15) & ~(size_t)15;
+    const size_t body = (need + 64 + page - 1) / page * page;
+    char *m = (char *)mmap(nullptr, body + page, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (m == (char *)MAP_FAILED) return cudaErrorMemoryAllocation;
+    mprotect(m + body, page, PROT_NONE);
+    char *user = m + body - need;
+    ((size_t *)(user - 16))[0] = body + page; ((char **)(user - 16))[1] = m;
+    *p = user;
+    return cudaSuccess;
+}
+cudaError_t cudaFree(void *p) {
+    if (p) { char *user = (char *)p; const size_t len = ((size_t *)(user - 16))[0]; char *m = ((char **)(user - 16))[1]; munmap(m, len); }
+    return cudaSuccess;
+}
+#else
 cudaError_t cudaMalloc(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+#endif
 cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { if (n) memmove(d, s, n); return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { if (n) memmove(d, s, n); return cudaSuccess; }
 cudaError_t cudaMemset(void *d, int v, size_t n) { if (n) memset(d, v, n); return cudaSuccess; }

@@ -21,7 +21,10 @@ CSRC = os.path.join(ROOT, "splashsurf_b200", "csrc")
 
 
 def build_emulated_library() -> str:
-    so = os.path.join(EMUL_DIR, "libsplashsurf_emul.so")
+    # SS_EMUL_GUARD=1: every device allocation ends in front of an inaccessible page and has no slack, so that any access
+    # past a buffer's requested size faults (run the suite once in this mode after touching kernels or buffer sizes)
+    guard = bool(os.environ.get("SS_EMUL_GUARD"))
+    so = os.path.join(EMUL_DIR, "libsplashsurf_emul_guard.so" if guard else "libsplashsurf_emul.so")
     deps = [os.path.join(EMUL_DIR, "cuda_emul.h")] + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + \
         [os.path.join(ROOT, "include", "splashsurf_b200.h")]
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
@@ -29,7 +32,7 @@ def build_emulated_library() -> str:
         pytest.skip("CUDA headers not found")
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-g", "-ffp-contract=off", "-fno-fast-math", "-w", "-x", "c++", "-DSS_HOST_EMUL",
-                               "-I" + cuda_inc, "-include", os.path.join(EMUL_DIR, "cuda_emul.h"), "-shared", "-fPIC", "-pthread",
+                               *(["-DSS_EMUL_GUARD"] if guard else []), "-I" + cuda_inc, "-include", os.path.join(EMUL_DIR, "cuda_emul.h"), "-shared", "-fPIC", "-pthread",
                                "-Wl,-Bsymbolic",      # its cuda* definitions must win over a libcudart that torch may have loaded
                                "-o", so, os.path.join(CSRC, "ss_pipeline.cu")])
     return so
