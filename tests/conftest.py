@@ -37,6 +37,12 @@ def ss():
     from splashsurf_b200 import build
     build.build()
     splashsurf_b200.load_library()
+    if os.environ.get("SS_TEST_EMULATED"):
+        # developer switch (never set by the driver): run GPU-marked tests on the CPU executor of the CUDA sources, e.g.
+        #   SS_TEST_EMULATED=1 pytest tests -m gpu -k "not full_size and not dam_ and not multi_gpu and not global_big"
+        import ctypes
+        from test_emulated_pipeline import build_emulated_library
+        splashsurf_b200._LIB = splashsurf_b200._bind(ctypes.CDLL(build_emulated_library()))
     return splashsurf_b200
 
 
