@@ -148,11 +148,9 @@ static void trampoline() {
 }
 
 static void resolve_warp(Cta *C, int lo, int hi) {
-    const int op = C->f[lo].state == DONE ? -1 : C->f[lo].op;
-    int first = -1;
-    for (int t = lo; t < hi; ++t) if (C->f[t].state == WARP_WAIT) { first = t; break; }
+    int first = lo;
+    while (C->f[first].state != WARP_WAIT) ++first;              // the caller guarantees at least one waiting lane
     const int want = C->f[first].op;
-    (void)op;
     unsigned ballot = 0; bool all = true, any = false;
     for (int t = lo; t < hi; ++t) {
         Fiber &F = C->f[t];
