@@ -158,6 +158,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS), help="BASELINE config (default cfg4 = the metric's 50 M dam break)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--runner-protocol", default="two_call", choices=["two_call", "callback"],
+                    help="multi-GPU only: how the global subdomain maximum reaches the library (see distributed.Runner)")
     ap.add_argument("--levelset-variant", type=int, default=0, choices=[0, 1],
                     help="0: fused certify + exact level-set kernel (default); 1: separate certification kernel (ss_certify.cuh)")
     args = ap.parse_args()
@@ -194,7 +196,7 @@ def main():
     # ---- workload (identical on every rank; each rank keeps its slab when world > 1)
     p_all, desc = make_cloud(args.particles, args.workload)
     n_total = len(p_all)
-    runner = ssd.Runner(ctx, params, world, rank, local_rank)
+    runner = ssd.Runner(ctx, params, world, rank, local_rank, protocol=args.runner_protocol)
     p_local = runner.take_local(p_all)
     del p_all
     host_in = torch.from_numpy(p_local).pin_memory()

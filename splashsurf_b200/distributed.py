@@ -170,8 +170,14 @@ def _pinned(t: torch.Tensor, device) -> torch.Tensor:
 class Runner:
     """Drives one reconstruct step on this rank's GPU (world == 1: plain C-ABI call)."""
 
-    def __init__(self, ctx, params, world: int, rank: int, local_rank: int, group=None, device=None):
+    def __init__(self, ctx, params, world: int, rank: int, local_rank: int, group=None, device=None, protocol: str = "two_call"):
         self.ctx, self.params, self.world, self.rank, self.local_rank, self.group = ctx, params, world, rank, local_rank, group
+        # how the global maximum subdomain population (sparse rule) reaches the library: "two_call" = decomposition pre-pass,
+        # all-reduce, full call (verified on 2/4/8 GPUs); "callback" = one call, the library calls back for the all-reduce
+        # after its decomposition (ss_reconstruct_partition_cb_f32; verified over gloo on the CPU executor only)
+        if protocol not in ("two_call", "callback"):
+            raise ValueError("protocol must be 'two_call' or 'callback'")
+        self.protocol = protocol
         self._out_v = self._out_t = None
         # `device` is only overridden by the tests that drive the runner over gloo with the CPU executor of the CUDA sources
         self.device = torch.device("cuda", local_rank) if device is None else torch.device(device)
@@ -258,20 +264,40 @@ class Runner:
         #    makes the same two library calls and the same all-reduce, also ranks that received no particles.
         _sync(self.device)
         s = C.c_void_p()
-        rc = L.ss_reconstruct_partition_f32(self.ctx._h, C.c_void_p(recv.data_ptr()), C.c_uint64(recv.shape[0]), C.byref(p),
-                                            C.byref(grid), ax, own_lo, own_hi, plan.halo, C.c_uint64(0), 1, C.byref(s))
-        if rc:
-            raise RuntimeError((L.ss_last_error() or b"").decode())
-        gmax = torch.tensor([L.ss_surface_max_subdomain_particles(s)], dtype=torch.int64, device=self.device)
-        pre_launches = int(self.ctx.timings(s)["kernel_launches"])
-        self.ctx.free_surface(s)
-        dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=self.group)
-        # 5. this rank's slab
-        s = C.c_void_p()
-        rc = L.ss_reconstruct_partition_f32(self.ctx._h, C.c_void_p(recv.data_ptr()), C.c_uint64(recv.shape[0]), C.byref(p),
-                                            C.byref(grid), ax, own_lo, own_hi, plan.halo, C.c_uint64(int(gmax.item())), 0, C.byref(s))
-        if rc:
-            raise RuntimeError((L.ss_last_error() or b"").decode())
+        pre_launches = 0
+        if self.protocol == "callback":
+            failure = []
+
+            def _reduce(local_max, _user):
+                try:
+                    t = torch.tensor([int(local_max)], dtype=torch.int64, device=self.device)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+                    return int(t.item())
+                except BaseException as exc:                      # ctypes would swallow it: remember and re-raise after the call
+                    failure.append(exc)
+                    return int(local_max)
+            cb = C.CFUNCTYPE(C.c_uint64, C.c_uint64, C.c_void_p)(_reduce)
+            rc = L.ss_reconstruct_partition_cb_f32(self.ctx._h, C.c_void_p(recv.data_ptr()), C.c_uint64(recv.shape[0]), C.byref(p),
+                                                   C.byref(grid), ax, own_lo, own_hi, plan.halo, cb, None, C.byref(s))
+            if failure:
+                raise failure[0]
+            if rc:
+                raise RuntimeError((L.ss_last_error() or b"").decode())
+        else:
+            rc = L.ss_reconstruct_partition_f32(self.ctx._h, C.c_void_p(recv.data_ptr()), C.c_uint64(recv.shape[0]), C.byref(p),
+                                                C.byref(grid), ax, own_lo, own_hi, plan.halo, C.c_uint64(0), 1, C.byref(s))
+            if rc:
+                raise RuntimeError((L.ss_last_error() or b"").decode())
+            gmax = torch.tensor([L.ss_surface_max_subdomain_particles(s)], dtype=torch.int64, device=self.device)
+            pre_launches = int(self.ctx.timings(s)["kernel_launches"])
+            self.ctx.free_surface(s)
+            dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=self.group)
+            # 5. this rank's slab
+            s = C.c_void_p()
+            rc = L.ss_reconstruct_partition_f32(self.ctx._h, C.c_void_p(recv.data_ptr()), C.c_uint64(recv.shape[0]), C.byref(p),
+                                                C.byref(grid), ax, own_lo, own_hi, plan.halo, C.c_uint64(int(gmax.item())), 0, C.byref(s))
+            if rc:
+                raise RuntimeError((L.ss_last_error() or b"").decode())
         try:
             t_ev[2].record()
             _sync(self.device)

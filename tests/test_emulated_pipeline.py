@@ -302,7 +302,7 @@ rank, world = dist.get_rank(), dist.get_world_size()
 case = json.loads(os.environ["SS_CASE"])
 p_all = getattr(syn, case["gen"])(*[tuple(a) if isinstance(a, list) else a for a in case["args"]])
 ctx = ss.Context(0)
-runner = ssd.Runner(ctx, ss.make_params(**case["kw"]), world, rank, 0, device="cpu")
+runner = ssd.Runner(ctx, ss.make_params(**case["kw"]), world, rank, 0, device="cpu", protocol=case.get("protocol", "two_call"))
 x = torch.from_numpy(runner.take_local(p_all))
 for it in range(2):                                             # second step reuses the pooled buffers
     out = runner.step(x, copy_out=True)
@@ -320,7 +320,9 @@ dist.destroy_process_group()
              kw=dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.75, subdomain_num_cubes_per_dim=16, subdomain_grid_auto_disable=False))),
     (3, dict(gen="jittered_cube", args=[7, 0.025, 502],     # two subdomain layers for three ranks: one rank stays idle
              kw=dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.75, subdomain_num_cubes_per_dim=16, subdomain_grid_auto_disable=False))),
-], ids=["2_ranks_dam_break", "3_ranks_one_idle"])
+    (3, dict(gen="jittered_cube", args=[7, 0.025, 503], protocol="callback",      # one library call, all-reduce from the callback
+             kw=dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.75, subdomain_num_cubes_per_dim=16, subdomain_grid_auto_disable=False))),
+], ids=["2_ranks_dam_break", "3_ranks_one_idle", "3_ranks_one_idle_callback"])
 def test_emulated_runner_over_gloo(tmp_path, oracle_mod, world, case):
     """splashsurf_b200.distributed.Runner._step_multi as the bench drives it (plan, halo exchange, two library calls, max
     all-reduce, mesh gather + weld), one process per rank over gloo, library = CPU executor; result vs the single-device oracle."""
@@ -332,7 +334,7 @@ def test_emulated_runner_over_gloo(tmp_path, oracle_mod, world, case):
     script.write_text(RUNNER_WORKER)
     env = dict(os.environ, SS_ROOT=ROOT, SS_OUT=str(tmp_path), SS_EMUL_SO=so, SS_CASE=json.dumps(case), SS_EMUL_THREADS="3", OMP_NUM_THREADS="1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
-           "--master-port", str(29541 + world), str(script)]
+           "--master-port", str(29541 + world + (7 if case.get("protocol") else 0)), str(script)]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-3000:]
     m = np.load(tmp_path / "mesh.npz")
