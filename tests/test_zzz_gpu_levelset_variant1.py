@@ -1,0 +1,42 @@
+"""GPU parity of level-set variant 1 (csrc/ss_certify.cuh: separate certification kernel + exact pass over the boxes it could
+not certify; off by default) against the pinned oracle -- same assertions as the seeded parity tests of the default variant.
+Kept in its own late-sorted file: written after the round's GPU budget was spent, so far it has only run on the CPU executor
+(tests/test_emulated_pipeline.py::test_emulated_split_certification_variant, tools/fuzz_emulated.py --variant 1)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+BASE = dict(particle_radius=0.025, smoothing_length=2.0)
+CASES = [
+    ("cube24", lambda syn: syn.jittered_cube(24, 0.025, 601), dict(BASE, cube_size=0.5)),
+    ("splash_scalar", lambda syn: syn.splash((20, 20, 20), 5, 0.025, 602), dict(BASE, cube_size=0.6, simd=False)),
+    ("splash_S20", lambda syn: syn.splash((18, 18, 18), 4, 0.025, 603), dict(BASE, cube_size=0.6, subdomain_num_cubes_per_dim=20,
+                                                                             subdomain_grid_auto_disable=False)),
+    ("splash_S32_c075", lambda syn: syn.splash((24, 24, 24), 6, 0.025, 604), dict(BASE, cube_size=0.75, subdomain_num_cubes_per_dim=32)),
+    ("global_nodec", lambda syn: syn.splash((14, 14, 14), 4, 0.025, 605), dict(BASE, cube_size=0.75, subdomain_grid=False)),
+    ("dam_small", lambda syn: syn.dam_break_scaled(120_000, 0.01, 606), dict(particle_radius=0.01, smoothing_length=2.0, cube_size=0.5)),
+]
+
+
+@pytest.mark.parametrize("name,gen,kw", CASES, ids=[c[0] for c in CASES])
+def test_cuda_split_certification_bit_exact_vs_oracle(ss, oracle_mod, name, gen, kw):
+    from splashsurf_b200 import synthetic as syn
+    p = gen(syn)
+    o = oracle_mod.reconstruct(p, **kw)
+    ctx = ss.Context()
+    try:
+        ctx.set_levelset_variant(1)
+        g = ss.reconstruct_surface(p, with_debug=True, context=ctx, **kw)
+        assert g.timings["levelset_launches"] >= 2          # certification launch + exact pass (+ fix-up pass)
+        g0 = None
+        ctx.set_levelset_variant(0)
+        g0 = ss.reconstruct_surface(p, with_debug=True, context=ctx, **kw)
+    finally:
+        ctx.close()
+    assert np.array_equal(g.particle_densities, o["particle_densities"])
+    m = oracle_mod.mesh_parity(g.mesh.vertices, g.mesh.triangles, g.vertex_edge_keys, o["vertices"], o["triangles"], o["vertex_keys"],
+                               kw.get("subdomain_num_cubes_per_dim", 64))
+    assert m["keys_equal"] and m["triangles_equal"] and m["n_not_bitexact"] == 0, m
+    # and the two variants agree with each other element for element (same kernels decide and evaluate)
+    assert np.array_equal(g.mesh.vertices, g0.mesh.vertices) and np.array_equal(g.mesh.triangles, g0.mesh.triangles)
