@@ -352,7 +352,7 @@ template <typename T> static inline T atomicMax(T *p, T v) {
 // ------------------------------------------------------------------ CUDA runtime served from host memory ----
 struct EmulEvent { std::chrono::steady_clock::time_point t; };
 extern "C" {
-cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+cudaError_t cudaGetDeviceCount(int *n) { *n = 16; return cudaSuccess; }    // every "device" is this host (multi-rank tests use LOCAL_RANK)
 cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
 cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }

@@ -1,0 +1,54 @@
+"""bench.py's b200 arm executed here, without a GPU: tests/emul/bench_on_executor.py maps torch's CUDA entry points to host
+equivalents and binds the library to the CPU executor of the CUDA sources, then calls bench.main() unchanged.  Checks the
+control flow (single rank and two gloo ranks, every command-line switch) and the contract of the JSON line; the numbers are
+meaningless and never recorded."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+LAUNCHER = os.path.join(ROOT, "tests", "emul", "bench_on_executor.py")
+REQUIRED = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+            "config", "clocks", "e2e", "gpu_launches", "roofline"}
+
+
+def _check_line(out: str, n_gpus: int, steps: int):
+    lines = [l for l in out.splitlines() if l.strip()]
+    assert len(lines) == 1, out[-2000:]                     # exactly ONE line on stdout
+    d = json.loads(lines[0])
+    assert REQUIRED <= set(d), REQUIRED - set(d)
+    assert d["metric"] == json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"]
+    assert d["n_gpus"] == n_gpus and d["steps"] == steps and d["higher_is_better"] is True and d["unit"] == "Mparticles/s"
+    assert d["value"] > 0 and d["ms_per_step"] > 0 and d["gpu_launches"] > 0
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"]) and d["e2e"]["h2d_bytes_per_step"] > 0
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
+    assert "workload" in d["config"] and "model" not in d["config"]
+    return d
+
+
+# (the fixed-size workloads cfg2/cfg3/cfg5 take minutes to hours on the executor; the 1 M-particle cfg2 ran once by hand)
+@pytest.mark.parametrize("extra", [[], ["--levelset-variant", "1", "--no-cpu-baseline"]], ids=["default", "levelset_variant_1"])
+def test_bench_single_rank_on_executor(oracle_mod, extra):
+    cmd = [sys.executable, LAUNCHER, "--particles", "12000", "--steps", "2", "--warmup", "1", "--ref-particles", "8000"] + extra
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, SS_EMUL_THREADS="4"))
+    assert r.returncode == 0, r.stderr[-3000:]
+    d = _check_line(r.stdout, 1, 2)
+    if "--no-cpu-baseline" not in extra:
+        assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
+    if "--levelset-variant" in extra:
+        assert d["config"]["levelset_variant"] == 1 and d["roofline"]["launches_per_step"] >= 2
+
+
+@pytest.mark.parametrize("protocol", ["two_call", "callback"])
+def test_bench_two_ranks_on_executor(oracle_mod, protocol):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29561" if protocol == "two_call" else "29562", LAUNCHER, "--gpus", "2", "--particles", "12000", "--steps", "2",
+           "--warmup", "1", "--runner-protocol", protocol]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, SS_EMUL_THREADS="3", OMP_NUM_THREADS="1"))
+    assert r.returncode == 0, r.stderr[-3000:]
+    d = _check_line(r.stdout, 2, 2)
+    assert d["config"]["parallelism"].endswith("x2") and d["mesh"]["vertices"] > 0
