@@ -9,7 +9,7 @@ import sys
 
 import pytest
 
-from conftest import ROOT
+from conftest import ROOT, free_port
 
 LAUNCHER = os.path.join(ROOT, "tests", "emul", "bench_on_executor.py")
 REQUIRED = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
@@ -46,7 +46,7 @@ def test_bench_single_rank_on_executor(oracle_mod, extra):
 @pytest.mark.parametrize("protocol", ["two_call", "callback"])
 def test_bench_two_ranks_on_executor(oracle_mod, protocol):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29561" if protocol == "two_call" else "29562", LAUNCHER, "--gpus", "2", "--particles", "12000", "--steps", "2",
+           "--master-port", str(free_port()), LAUNCHER, "--gpus", "2", "--particles", "12000", "--steps", "2",
            "--warmup", "1", "--runner-protocol", protocol]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, SS_EMUL_THREADS="3", OMP_NUM_THREADS="1"))
     assert r.returncode == 0, r.stderr[-3000:]

@@ -6,6 +6,8 @@ import sys
 import numpy as np
 import pytest
 
+from conftest import free_port
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 WORKER = r'''
@@ -52,7 +54,7 @@ def test_slab_plan_and_exchange_gloo(tmp_path, oracle_mod):
     script.write_text(WORKER)
     env = dict(os.environ, SS_ROOT=ROOT, SS_OUT=str(tmp_path), OMP_NUM_THREADS="1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", str(script)]
+           "--master-port", str(free_port()), str(script)]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     import json

@@ -14,7 +14,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import ROOT, load_golden
+from conftest import ROOT, free_port, load_golden
 
 EMUL_DIR = os.path.join(ROOT, "tests", "emul")
 CSRC = os.path.join(ROOT, "splashsurf_b200", "csrc")
@@ -334,7 +334,7 @@ def test_emulated_runner_over_gloo(tmp_path, oracle_mod, world, case):
     script.write_text(RUNNER_WORKER)
     env = dict(os.environ, SS_ROOT=ROOT, SS_OUT=str(tmp_path), SS_EMUL_SO=so, SS_CASE=json.dumps(case), SS_EMUL_THREADS="3", OMP_NUM_THREADS="1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
-           "--master-port", str(29541 + world + (7 if case.get("protocol") else 0)), str(script)]
+           "--master-port", str(free_port()), str(script)]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-3000:]
     m = np.load(tmp_path / "mesh.npz")
