@@ -1,10 +1,11 @@
-"""Runs bench.py's own main() without a GPU -- TEST INFRASTRUCTURE (tests/test_bench_dry_run.py).
+"""Runs a GPU-only script of this repo (bench.py, tools/mgpu_check.py, ...) without a GPU -- TEST INFRASTRUCTURE
+(tests/test_bench_dry_run.py):      python tests/emul/run_on_executor.py bench.py --particles 12000 --steps 2 ...
 
-The b200 arm of bench.py can only run on a CUDA device; a Python-level mistake in it would otherwise first show up on the GPU
-box at round end.  This launcher makes the same code run here: the library handle is the CPU executor of the CUDA sources
+Those scripts can only run on a CUDA device; a Python-level mistake in them would otherwise first show up on the GPU box at
+round end.  This launcher makes the same code run here: the library handle is the CPU executor of the CUDA sources
 (tests/emul/cuda_emul.h), torch's CUDA entry points used by bench.py / distributed.Runner are mapped to host equivalents
-(events -> wall clock, pinned / device tensors -> plain host tensors), NCCL -> gloo.  The numbers it prints are meaningless;
-only the control flow and the shape of the JSON line are checked."""
+(events -> wall clock, pinned / device tensors -> plain host tensors), NCCL -> gloo.  The numbers such a run prints are
+meaningless; only the control flow and the shape of the output are checked."""
 import ctypes
 import os
 import sys
@@ -42,6 +43,7 @@ torch.cuda.Event = _Event
 torch.Tensor.pin_memory = lambda self, *a, **k: self
 torch.Tensor.cuda = lambda self, *a, **k: self
 _tensor, _empty, _full, _zeros = torch.tensor, torch.empty, torch.full, torch.zeros
+_cpu = torch.Tensor.cpu
 torch.tensor = lambda *a, **k: _tensor(*a, **_cpu_device(k))
 torch.empty = lambda *a, **k: _empty(*a, **_cpu_device(k))
 torch.full = lambda *a, **k: _full(*a, **_cpu_device(k))
@@ -57,7 +59,8 @@ ss._LIB = ss._bind(ctypes.CDLL(build_emulated_library()))
 _Runner = ssd.Runner
 ssd.Runner = lambda *a, **k: _Runner(*a, **dict(k, device="cpu"))
 
-import bench  # noqa: E402
-
 if __name__ == "__main__":
-    sys.exit(bench.main())
+    import runpy
+    script = sys.argv[1] if os.path.isabs(sys.argv[1]) else os.path.join(ROOT, sys.argv[1])
+    sys.argv = [script] + sys.argv[2:]
+    runpy.run_path(script, run_name="__main__")

@@ -1,4 +1,4 @@
-"""bench.py's b200 arm executed here, without a GPU: tests/emul/bench_on_executor.py maps torch's CUDA entry points to host
+"""bench.py's b200 arm executed here, without a GPU: tests/emul/run_on_executor.py maps torch's CUDA entry points to host
 equivalents and binds the library to the CPU executor of the CUDA sources, then calls bench.main() unchanged.  Checks the
 control flow (single rank and two gloo ranks, every command-line switch) and the contract of the JSON line; the numbers are
 meaningless and never recorded."""
@@ -11,7 +11,7 @@ import pytest
 
 from conftest import ROOT, free_port
 
-LAUNCHER = os.path.join(ROOT, "tests", "emul", "bench_on_executor.py")
+LAUNCHER = os.path.join(ROOT, "tests", "emul", "run_on_executor.py")
 REQUIRED = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
             "config", "clocks", "e2e", "gpu_launches", "roofline"}
 
@@ -33,7 +33,7 @@ def _check_line(out: str, n_gpus: int, steps: int):
 # (the fixed-size workloads cfg2/cfg3/cfg5 take minutes to hours on the executor; the 1 M-particle cfg2 ran once by hand)
 @pytest.mark.parametrize("extra", [[], ["--levelset-variant", "1", "--no-cpu-baseline"]], ids=["default", "levelset_variant_1"])
 def test_bench_single_rank_on_executor(oracle_mod, extra):
-    cmd = [sys.executable, LAUNCHER, "--particles", "12000", "--steps", "2", "--warmup", "1", "--ref-particles", "8000"] + extra
+    cmd = [sys.executable, LAUNCHER, "bench.py", "--particles", "12000", "--steps", "2", "--warmup", "1", "--ref-particles", "8000"] + extra
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, SS_EMUL_THREADS="4"))
     assert r.returncode == 0, r.stderr[-3000:]
     d = _check_line(r.stdout, 1, 2)
@@ -46,7 +46,7 @@ def test_bench_single_rank_on_executor(oracle_mod, extra):
 @pytest.mark.parametrize("protocol", ["two_call", "callback"])
 def test_bench_two_ranks_on_executor(oracle_mod, protocol):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", str(free_port()), LAUNCHER, "--gpus", "2", "--particles", "12000", "--steps", "2",
+           "--master-port", str(free_port()), LAUNCHER, "bench.py", "--gpus", "2", "--particles", "12000", "--steps", "2",
            "--warmup", "1", "--runner-protocol", protocol]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, SS_EMUL_THREADS="3", OMP_NUM_THREADS="1"))
     assert r.returncode == 0, r.stderr[-3000:]

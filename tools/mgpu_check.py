@@ -14,7 +14,7 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     import datetime
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=120))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=int(os.environ.get("SS_MGPU_TIMEOUT", "120"))))
     ok = True
     cases = [
         ("splash", syn.splash((60, 20, 20), 8, 0.025, 31), dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.5)),
