@@ -33,6 +33,9 @@ class SlabPlan:
     cuts: List[int]            # world+1 cut positions: rank r owns subdomain indices [cuts[r], cuts[r+1])
     srad: int                  # ghost reach in subdomains (ceil(margin / subdomain size))
     halo: int                  # density-only subdomain layers kept around a slab (= srad)
+    margin: float = 0.0        # ghost particle margin (dense_subdomains.rs:120-121)
+    sub_size: float = 0.0      # edge length of a subdomain
+    gmin_axis: Optional[float] = None   # subdomain grid aabb.min along `axis` (set by plan_partition)
 
     def own(self, r: int):
         return self.cuts[r], self.cuts[r + 1]
@@ -45,6 +48,19 @@ class SlabPlan:
             return 0, 0
         reach = self.halo + self.srad + 1
         return lo - reach, hi + reach
+
+    def recv_interval(self, r: int):
+        """Coordinate interval (along the axis) of the particles rank r needs: the members -- owned or ghost -- of the
+        subdomain layers [own_lo - halo, own_hi + halo) lie within the ghost margin of that range of layers.  A little slack
+        (0.2 % of the margin plus a few float32 ulps of the coordinate) makes it a superset of what the library's f32
+        classifier keeps; the library filters exactly.  Far tighter than `recv_range`'s whole layers."""
+        lo, hi = self.own(r)
+        if hi <= lo or self.gmin_axis is None:
+            return 0.0, 0.0
+        a = self.gmin_axis + (lo - self.halo) * self.sub_size
+        b = self.gmin_axis + (hi + self.halo) * self.sub_size
+        slack = self.margin * 1.002 + 1e-5 * (abs(a) + abs(b) + self.sub_size)
+        return a - slack, b + slack
 
 
 def balanced_cuts(hist: np.ndarray, world: int) -> List[int]:
@@ -74,7 +90,7 @@ def make_plan(grid_ncells, subdomain_cubes: int, cube_size: float, compact_suppo
     margin = np.float32(np.float32(np.ceil(h32 / c32) * c32) * np.float32(1.01))
     srad = int(np.ceil(margin / np.float32(c32 * np.float32(S))))
     hist = np.zeros(nsd[ax]) if hist_axis is None else np.asarray(hist_axis)
-    return SlabPlan(ax, nsd[ax], balanced_cuts(hist, world), srad, srad)
+    return SlabPlan(ax, nsd[ax], balanced_cuts(hist, world), srad, srad, float(margin), float(np.float32(c32 * np.float32(S))))
 
 
 def plan_partition(x: torch.Tensor, grid_min, grid_ncells, S: int, cube_size: float, compact_support: float, world: int, group=None):
@@ -96,6 +112,7 @@ def plan_partition(x: torch.Tensor, grid_min, grid_ncells, S: int, cube_size: fl
     tiles = occ.view(nsd[0], nsd[1], nsd[2]).sum(dim=other).to(torch.float64)
     work = hist + TILE_COST_PARTICLES * tiles
     plan = make_plan(grid_ncells, S, cube_size, compact_support, work.cpu().numpy(), world, axis=ax)
+    plan.gmin_axis = float(grid_min[ax])
     return plan, layer
 
 
@@ -105,19 +122,29 @@ def owner_layer(x_axis: torch.Tensor, gmin: float, sub_size: float) -> torch.Ten
     return torch.floor((x_axis.to(torch.float64) - float(gmin)) / float(sub_size)).to(torch.int64)
 
 
-def exchange_particles(x_local: torch.Tensor, layer: torch.Tensor, plan: SlabPlan, world: int, group=None):
-    """Variable all-to-all: returns (particles for this rank in ascending global order, counts received per source)."""
-    los = torch.tensor([plan.recv_range(r)[0] for r in range(world)], dtype=torch.int64, device=x_local.device)
-    his = torch.tensor([plan.recv_range(r)[1] for r in range(world)], dtype=torch.int64, device=x_local.device)
-    masks = (layer[None, :] >= los[:, None]) & (layer[None, :] < his[:, None])          # (world, n)
+def exchange_particles(x_local: torch.Tensor, layer: torch.Tensor, plan: SlabPlan, world: int, group=None, payload: Optional[torch.Tensor] = None):
+    """Variable all-to-all: returns (particles for this rank in ascending global order, counts received per source).
+    A particle goes to every rank whose kept layers it can be a member of: by coordinate interval (`recv_interval`) when the
+    plan knows the grid origin, else by whole owner layers (`recv_range`).  `payload` ((n, 3) rows, default: the particles
+    themselves) is what travels; the routing always comes from `x_local`."""
+    if plan.gmin_axis is not None and x_local.shape[1] >= 3:
+        coord = x_local[:, plan.axis].to(torch.float64)
+        los = torch.tensor([plan.recv_interval(r)[0] for r in range(world)], dtype=torch.float64, device=x_local.device)
+        his = torch.tensor([plan.recv_interval(r)[1] for r in range(world)], dtype=torch.float64, device=x_local.device)
+        masks = (coord[None, :] >= los[:, None]) & (coord[None, :] < his[:, None])      # (world, n)
+    else:
+        los = torch.tensor([plan.recv_range(r)[0] for r in range(world)], dtype=torch.int64, device=x_local.device)
+        his = torch.tensor([plan.recv_range(r)[1] for r in range(world)], dtype=torch.int64, device=x_local.device)
+        masks = (layer[None, :] >= los[:, None]) & (layer[None, :] < his[:, None])      # (world, n)
     idx = torch.nonzero(masks)                                                           # row-major: by rank, then ascending index
-    send = x_local[idx[:, 1]].contiguous()
+    data = x_local if payload is None else payload
+    send = data[idx[:, 1]].contiguous()
     counts = [int(v) for v in masks.sum(dim=1).tolist()]
     cnt_in = torch.tensor(counts, dtype=torch.int64, device=x_local.device)
     cnt_out = torch.empty(world, dtype=torch.int64, device=x_local.device)
     dist.all_to_all_single(cnt_out, cnt_in, group=group)
     out_counts = [int(v) for v in cnt_out.tolist()]
-    recv = torch.empty((sum(out_counts), 3), dtype=x_local.dtype, device=x_local.device)
+    recv = torch.empty((sum(out_counts), 3), dtype=data.dtype, device=x_local.device)
     dist.all_to_all_single(recv.view(-1), send.view(-1), output_split_sizes=[3 * v for v in out_counts],
                            input_split_sizes=[3 * v for v in counts], group=group)
     return recv, out_counts

@@ -36,7 +36,7 @@ hist = torch.tensor([float(n)])
 recv, counts = ssd.exchange_particles(x, layer, plan, world)
 # same exchange on the ids to learn which global particles arrived, in which order
 ids3 = torch.stack([gid, gid, gid], dim=1)
-recv_ids, _ = ssd.exchange_particles(ids3, layer, plan, world)
+recv_ids, _ = ssd.exchange_particles(x, layer, plan, world, payload=ids3)
 ids = recv_ids[:, 0].to(torch.int64).numpy()
 # an empty rank (no particles at all) must go through the same collectives without hanging
 empty = x[:0]
@@ -78,9 +78,16 @@ def test_slab_plan_and_exchange_gloo(tmp_path, oracle_mod):
         assert res[k]["match"]
         assert (np.diff(ids) > 0).all(), "exchange must keep ascending global particle order"
         lo, hi = cuts[k] - srad, cuts[k + 1] + srad            # kept subdomain layers (owned + density halo)
-        # every particle that can be a member of a kept layer: owner layer within srad of the kept range
-        need = (own + srad >= lo) & (own - srad < hi)
-        assert set(np.nonzero(need)[0].tolist()) <= set(ids.tolist())
+        # every particle that is a member (owner or ghost) of a kept layer: within the ghost margin of the kept range, in
+        # the reference's f32 arithmetic (dense_subdomains.rs:1846-1851: distance to the face < margin)
+        lo_face = gmin + np.float32(lo) * dx
+        hi_face = gmin + np.float32(hi) * dx
+        need = ((lo_face - xa) < margin) & ((xa - hi_face) < margin)
+        got = set(ids.tolist())
+        assert set(np.nonzero(need)[0].tolist()) <= got
+        # and the routing is tight: nothing farther than 1.05 margins from the kept range travels
+        far = ((lo_face - xa) > np.float32(1.05) * margin) | ((xa - hi_face) > np.float32(1.05) * margin)
+        assert not (set(np.nonzero(far)[0].tolist()) & got)
         minc = gmin + own.astype(np.float32) * dx
         near_lo = (xa - minc) < margin                        # really a ghost of the layer below
         assert near_lo.any()
