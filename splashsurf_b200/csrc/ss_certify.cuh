@@ -11,7 +11,8 @@
 // bricks), exactly like the boxes the fix-up sweep flags.  Results are identical to the fused pass by construction: the same
 // ss_certify_box decides, the same SS_LS_FIX code evaluates.
 //
-// Per-box state wstate[brick * 16 + box] : 0 untouched (all zero), 1 every valid point carries SS_MARKER, 2 needs exact values.
+// Per-box state wstate[brick * 16 + box] : 0 untouched (all zero), 1 every valid point carries SS_MARKER, 2 needs exact values,
+// 3 exact values already in place (no candidate within the support of any point of the box: the pre-zeroed tile IS the result).
 #pragma once
 
 struct SsCertArgs {
@@ -43,6 +44,17 @@ __device__ __forceinline__ void ss_mark_boxes(const SsDev &P, uint8_t *__restric
     for (int a = i0 >> 1; a <= min((i0 + W.dx - 1) >> 1, 3); ++a)
         for (int b = j0 >> 2; b <= min((j0 + W.dy - 1) >> 2, 1); ++b)
             for (int c = k0 >> 2; c <= min((k0 + W.dz - 1) >> 2, 1); ++c) wstate[base + (size_t)(a * 4 + b * 2 + c)] = value;
+}
+
+// true when some staged candidate lies within the kernel support of the warp's point box (the cull of ss_exact_box)
+template <bool GLOBAL>
+__device__ __forceinline__ bool ss_box_has_candidate(const SsDev &P, const SsLanePoint &L, bool sparse, const float4 *s_rec, int C, int lane) {
+    const float cull2 = (GLOBAL ? P.rev2 : (sparse ? P.h2m : P.h2)) * 1.0001f;
+    for (int w = 0; w < ((C + 31) >> 5); ++w) {
+        const int c = w * 32 + lane;
+        if (__any_sync(0xffffffffu, c < C && ss_box_dist2(L, s_rec[c < C ? c : 0]) < cull2)) return true;
+    }
+    return false;
 }
 
 template <bool GLOBAL>
@@ -119,7 +131,8 @@ k_certify(SsDev P, SsCertArgs A) {
         if (L.warp_valid) {
             const bool ok = ss_certify_box(P, L, s_rec, C, lane, w0);
             if (ok && L.valid) A.tiles[L.out_idx] = SS_MARKER;
-            if (lane == 0) A.wstate[(size_t)desc.x * SS_LS_WARPS + warp] = ok ? 1 : 2;
+            const uint8_t st = ok ? 1 : (ss_box_has_candidate<GLOBAL>(P, L, sparse, s_rec, C, lane) ? 2 : 3);
+            if (lane == 0) A.wstate[(size_t)desc.x * SS_LS_WARPS + warp] = st;
         }
     }
     if (has_ext) {
@@ -127,27 +140,28 @@ k_certify(SsDev P, SsCertArgs A) {
         if (L.warp_valid) {
             const bool ok = ss_certify_box(P, L, s_rec, C, lane, w0);
             if (ok && L.valid) A.tiles[L.out_idx] = SS_MARKER;
-            if (lane == 0) ss_mark_boxes(P, A.wstate, tile_idx, vbx, vby, vbz, We, ok ? 1 : 2);
+            const uint8_t st = ok ? 1 : (ss_box_has_candidate<GLOBAL>(P, L, sparse, s_rec, C, lane) ? 2 : 3);
+            if (lane == 0) ss_mark_boxes(P, A.wstate, tile_idx, vbx, vby, vbz, We, st);
         }
     }
 }
 
-// per brick: state = max over its boxes (0 untouched, 1 certified, 2 has / needs exact values), and the flags of the exact
-// launch: need[b] = some box of b failed, wflag = per-box "evaluate exactly"
+// per brick: state = max over its boxes (0 untouched, 1 certified, 2 has exact values -- box states 2 and 3), and the flags of
+// the exact launch: need[b] = some box of b is in state 2, wflag = per-box "evaluate exactly"
 __global__ void k_wstate_reduce(const uint8_t *__restrict__ wstate, uint32_t nbricks, uint8_t *__restrict__ bstate, uint32_t *__restrict__ need,
                                 uint8_t *__restrict__ wflag) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nbricks) return;
     const uint4 w = *reinterpret_cast<const uint4 *>(wstate + (size_t)b * SS_LS_WARPS);
     const uint32_t q[4] = { w.x, w.y, w.z, w.w };
-    uint32_t mx = 0, f[4];
+    uint32_t mx = 0, any_need = 0, f[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         f[k] = 0;
 #pragma unroll
-        for (int s = 0; s < 32; s += 8) { const uint32_t v = (q[k] >> s) & 0xffu; mx = max(mx, v); if (v == 2u) f[k] |= 1u << s; }
+        for (int s = 0; s < 32; s += 8) { const uint32_t v = (q[k] >> s) & 0xffu; mx = max(mx, min(v, 2u)); if (v == 2u) { f[k] |= 1u << s; any_need = 1u; } }
     }
     bstate[b] = (uint8_t)mx;
-    need[b] = mx == 2u ? 1u : 0u;
+    need[b] = any_need;
     *reinterpret_cast<uint4 *>(wflag + (size_t)b * SS_LS_WARPS) = make_uint4(f[0], f[1], f[2], f[3]);
 }
