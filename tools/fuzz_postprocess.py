@@ -69,7 +69,7 @@ def main():
                     # unit vectors g / |g|: where the SPH gradient nearly cancels, 1-ulp differences of the (smoothed) vertex
                     # positions are amplified by 1 / |g|; such vertices are rare, so the bulk must agree tightly and the
                     # worst vertex loosely
-                    assert np.quantile(d, 0.99) <= 2e-4 and d.max() <= 5e-2, (k, float(np.quantile(d, 0.99)), float(d.max()))
+                    assert np.quantile(d, 0.99) <= 5e-4 and d.max() <= 5e-2, (k, float(np.quantile(d, 0.99)), float(d.max()))
                 else:
                     assert d.max() / scale <= 5e-5, (k, float(d.max() / scale))
             done += 1
