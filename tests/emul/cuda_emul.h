@@ -359,7 +359,7 @@ cudaError_t cudaGetLastError(void) { return cudaSuccess; }
 const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
 #ifdef SS_EMUL_GUARD
 // Guarded allocator: the buffer ends (16-byte aligned) right in front of an inaccessible page, so that any read or write
-// past the requested size faults immediately; a header in front keeps the mapping size.  DevBuf allocates without slack
+// past the requested size faults immediately, and starts out filled with 0xCD (cudaMalloc returns uninitialised memory); a header in front keeps the mapping size.  DevBuf allocates without slack
 // in this mode (ss_pipeline.cu), so "requested size" is what the host code really asked for.
 cudaError_t cudaMalloc(void **p, size_t n) {
     const size_t page = 4096, need = ((n ? n : 1) + 15) & ~(size_t)15;
@@ -369,6 +369,7 @@ cudaError_t cudaMalloc(void **p, size_t n) {
     mprotect(m + body, page, PROT_NONE);
     char *user = m + body - need;
     ((size_t *)(user - 16))[0] = body + page; ((char **)(user - 16))[1] = m;
+    memset(user, 0xCD, need);                                   // cudaMalloc does not zero: reads of uninitialised memory show up
     *p = user;
     return cudaSuccess;
 }
@@ -377,7 +378,11 @@ cudaError_t cudaFree(void *p) {
     return cudaSuccess;
 }
 #else
-cudaError_t cudaMalloc(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaMalloc(void **p, size_t n) {
+    *p = malloc(n ? n : 1);
+    if (*p && getenv("SS_EMUL_POISON")) memset(*p, 0xCD, n ? n : 1);   // optional: make reads of uninitialised device memory visible
+    return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
 cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
 #endif
 cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { if (n) memmove(d, s, n); return cudaSuccess; }
