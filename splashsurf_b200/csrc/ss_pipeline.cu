@@ -440,6 +440,184 @@ struct Partition {
     void *max_reduce_user = nullptr;
 };
 
+// Level set of one batch of tiles: work list, certification + exact values (fused kernel, or variant 1: certification kernel +
+// exact pass), brick classification, fix-up sweep.  Leaves the tiles, the per-brick states and the marching-cubes brick list
+// (c->list_mc, *n_mc_out entries) in the context scratch.
+static int levelset_batch(ss_context *c, const SsDev &D, uint32_t nbatch, unsigned nbricks, bool exact_all, int certify_runs, bool global_mode,
+                          ss_surface *out, uint64_t &ls_launches, uint64_t &fix_points, uint32_t *n_mc_out) {
+    cudaStream_t st = c->stream;
+    SsLsArgs A{};
+    A.bin_start = c->tab_a.as<uint32_t>(); A.bin_end = c->tab_b.as<uint32_t>(); A.rec = c->rec.as<float4>();
+    A.ksplit = c->ksplit.as<int>(); A.pidx = c->val_a.as<uint32_t>();
+    A.tile_tab = c->tile_tab.as<SsTile>(); A.brick_rng = c->brick_rng.as<int2>(); A.tiles = c->tiles.as<float>();
+    A.pairs = c->count_pairs ? c->pairs.as<unsigned long long>() : nullptr;
+    A.mode = exact_all ? SS_LS_EXACT_ALL : SS_LS_CERTIFY;
+    A.wflag = nullptr; A.fix_bricks = nullptr; A.bstate = c->bstate.as<uint8_t>();
+    const uint32_t n_work = build_worklist(c, D, nbatch);
+    A.work_list = c->list_ls.as<uint32_t>();
+    const bool split_certify = c->ls_variant == 1 && !exact_all && certify_runs <= 32;
+    if (n_work && !split_certify) { launch_levelset(c, dim3(n_work), D, A, c->count_pairs != 0, global_mode); ++ls_launches; }
+    if (n_work && split_certify) {
+        // variant 1 (ss_certify.cuh): certification kernel, then the exact pass over the boxes it could not certify
+        const uint32_t nbr_c = nbatch * nbricks;
+        c->wstate.ensure((size_t)nbr_c * SS_LS_WARPS); c->wflag.ensure((size_t)nbr_c * SS_LS_WARPS); c->desc_ls.ensure((size_t)n_work * 16);
+        c->flag_fix.ensure((size_t)nbr_c * 4); c->off_fix.ensure((size_t)nbr_c * 4 + 4); c->fix_list.ensure((size_t)nbr_c * 4);
+        CK(cudaMemsetAsync(c->wstate.p, 0, (size_t)nbr_c * SS_LS_WARPS, st));
+        LAUNCH(c, k_compact_desc, nblk(nbr_c, 256), 256, D, c->flag_ls.as<uint32_t>(), c->off_ls.as<uint32_t>(), nbr_c, c->desc_ls.as<uint4>());
+        SsCertArgs CA{};
+        CA.bin_start = A.bin_start; CA.bin_end = A.bin_end; CA.rec = A.rec; CA.tile_tab = A.tile_tab; CA.brick_rng = A.brick_rng;
+        CA.work_desc = c->desc_ls.as<uint4>(); CA.tiles = A.tiles; CA.wstate = c->wstate.as<uint8_t>();
+        if (global_mode) LAUNCH(c, k_certify<true>, n_work, SS_LS_THREADS, D, CA);
+        else LAUNCH(c, k_certify<false>, n_work, SS_LS_THREADS, D, CA);
+        ++ls_launches;
+        LAUNCH(c, k_wstate_reduce, nblk(nbr_c, 256), 256, c->wstate.as<uint8_t>(), nbr_c, c->bstate.as<uint8_t>(), c->flag_fix.as<uint32_t>(),
+               c->wflag.as<uint8_t>());
+        cub_excl_scan(c, c->flag_fix.as<uint32_t>(), c->off_fix.as<uint32_t>(), nbr_c);
+        LAUNCH(c, k_compact_list, nblk(nbr_c, 256), 256, c->flag_fix.as<uint32_t>(), c->off_fix.as<uint32_t>(), nbr_c, c->fix_list.as<uint32_t>());
+        uint32_t ln[2] = { 0, 0 };
+        CK(cudaMemcpyAsync(&ln[0], c->off_fix.as<uint32_t>() + (nbr_c - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&ln[1], c->flag_fix.as<uint32_t>() + (nbr_c - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (ln[0] + ln[1]) {
+            SsLsArgs F = A;
+            F.mode = SS_LS_FIX; F.wflag = c->wflag.as<uint8_t>(); F.fix_bricks = c->fix_list.as<uint32_t>();
+            launch_levelset(c, dim3(ln[0] + ln[1]), D, F, c->count_pairs != 0, global_mode);
+            ++ls_launches;
+        }
+    }
+    out->tm.bricks_levelset += n_work;
+    // bricks that can carry surface (for marching cubes) / markers next to outside points (for the fix-up sweep)
+    const uint32_t nbr_b = nbatch * nbricks;
+    c->flag_mc.ensure((size_t)nbr_b * 4); c->flag_fix.ensure((size_t)nbr_b * 4); c->off_mc.ensure((size_t)nbr_b * 4 + 4); c->off_fix.ensure((size_t)nbr_b * 4 + 4);
+    c->list_mc.ensure((size_t)nbr_b * 4); c->list_fix.ensure((size_t)nbr_b * 4);
+    LAUNCH(c, k_brick_classify, nblk(nbr_b, 256), 256, D, c->bstate.as<uint8_t>(), nbr_b, c->flag_mc.as<uint32_t>(), c->flag_fix.as<uint32_t>());
+    cub_excl_scan(c, c->flag_mc.as<uint32_t>(), c->off_mc.as<uint32_t>(), nbr_b);
+    cub_excl_scan(c, c->flag_fix.as<uint32_t>(), c->off_fix.as<uint32_t>(), nbr_b);
+    LAUNCH(c, k_compact_list, nblk(nbr_b, 256), 256, c->flag_mc.as<uint32_t>(), c->off_mc.as<uint32_t>(), nbr_b, c->list_mc.as<uint32_t>());
+    LAUNCH(c, k_compact_list, nblk(nbr_b, 256), 256, c->flag_fix.as<uint32_t>(), c->off_fix.as<uint32_t>(), nbr_b, c->list_fix.as<uint32_t>());
+    uint32_t lc[4] = { 0, 0, 0, 0 };
+    CK(cudaMemcpyAsync(&lc[0], c->off_mc.as<uint32_t>() + (nbr_b - 1), 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&lc[1], c->flag_mc.as<uint32_t>() + (nbr_b - 1), 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&lc[2], c->off_fix.as<uint32_t>() + (nbr_b - 1), 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&lc[3], c->flag_fix.as<uint32_t>() + (nbr_b - 1), 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const uint32_t n_mc = lc[0] + lc[1], n_fixscan = lc[2] + lc[3];
+    out->tm.bricks_total += nbr_b; out->tm.bricks_mc += n_mc; out->tm.bricks_fixscan += n_fixscan;
+    if (!exact_all && n_fixscan) {
+        // exact values for certified points that turn out to lie on a surface-crossing edge
+        const size_t nbr = (size_t)nbatch * nbricks;
+        c->wflag.ensure(nbr * SS_LS_WARPS); c->brick_seen.ensure(nbr * 4); c->fix_list.ensure(nbr * 4); c->nflag.ensure(8);
+        CK(cudaMemsetAsync(c->wflag.p, 0, nbr * SS_LS_WARPS, st));
+        CK(cudaMemsetAsync(c->brick_seen.p, 0, nbr * 4, st));
+        CK(cudaMemsetAsync(c->nflag.p, 0, 8, st));
+        LAUNCH(c, k_fixup_flags, n_fixscan, SS_TP_THREADS, D, c->tiles.as<float>(), c->list_fix.as<uint32_t>(), c->wflag.as<uint8_t>(),
+               c->brick_seen.as<uint32_t>(), c->fix_list.as<uint32_t>(), c->nflag.as<uint32_t>());
+        uint32_t nfl[2] = { 0, 0 };
+        CK(cudaMemcpyAsync(nfl, c->nflag.p, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (nfl[0]) {
+            A.mode = SS_LS_FIX; A.wflag = c->wflag.as<uint8_t>(); A.fix_bricks = c->fix_list.as<uint32_t>();
+            launch_levelset(c, dim3(nfl[0]), D, A, c->count_pairs != 0, global_mode);
+            ++ls_launches;
+            fix_points += nfl[1];
+        }
+    }
+    *n_mc_out = n_mc;
+    return SS_OK;
+}
+
+// Marching cubes over the listed bricks of one batch: count, scan the brick totals, emit vertices, emit triangles; appends to
+// the surface's mesh buffers and to the boundary-vertex list.
+static int marching_cubes_batch(ss_context *c, const SsDev &D, bool global_mode, uint32_t n_mc, ss_surface *out, uint64_t &vtotal, uint64_t &ttotal) {
+    cudaStream_t st = c->stream;
+    uint64_t bv = 0, bt = 0;
+    if (n_mc) {
+        if (global_mode) LAUNCH(c, k_mc_count<true>, n_mc, SS_TP_THREADS, D, c->tiles.as<float>(), c->list_mc.as<uint32_t>(), c->vmask.as<uint8_t>(), c->vcnt.as<uint32_t>(), c->tcnt.as<uint32_t>());
+        else LAUNCH(c, k_mc_count<false>, n_mc, SS_TP_THREADS, D, c->tiles.as<float>(), c->list_mc.as<uint32_t>(), c->vmask.as<uint8_t>(), c->vcnt.as<uint32_t>(), c->tcnt.as<uint32_t>());
+        cub_excl_scan(c, c->vcnt.as<uint32_t>(), c->vblk_off.as<uint32_t>(), n_mc);
+        cub_excl_scan(c, c->tcnt.as<uint32_t>(), c->tblk_off.as<uint32_t>(), n_mc);
+    }
+    uint32_t bc = 0;
+    CK(cudaMemcpyAsync(&bc, c->bcount.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (n_mc) {
+        uint32_t lv[2] = { 0, 0 }, lt[2] = { 0, 0 };
+        CK(cudaMemcpyAsync(&lv[1], c->vcnt.as<uint32_t>() + (n_mc - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&lt[1], c->tcnt.as<uint32_t>() + (n_mc - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&lv[0], c->vblk_off.as<uint32_t>() + (n_mc - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&lt[0], c->tblk_off.as<uint32_t>() + (n_mc - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        bv = (uint64_t)lv[0] + lv[1]; bt = (uint64_t)lt[0] + lt[1];
+    }
+    if (vtotal + bv >= 0xfffffff0ull || (ttotal + bt) * 3 >= 0xffffffffffull) return ss_fail(SS_ERR_INDEX_TOO_SMALL, "mesh too large for 32-bit vertex ids");
+    if (bv || bt) {
+        out->verts.grow_keep((vtotal + bv) * 12, vtotal * 12, st);
+        out->vkeys.grow_keep((vtotal + bv) * 8, vtotal * 8, st);
+        out->tris.grow_keep((ttotal + bt) * 12, ttotal * 12, st);
+        // boundary list can hold at most every vertex of the batch
+        c->bkeys_a.grow_keep(((size_t)bc + bv) * 8, (size_t)bc * 8, st);
+        c->bids_a.grow_keep(((size_t)bc + bv) * 4, (size_t)bc * 4, st);
+        SsMcOut O{};
+        O.verts = out->verts.as<float>(); O.tris = out->tris.as<uint32_t>(); O.vkeys = out->vkeys.as<unsigned long long>();
+        O.bkeys = c->bkeys_a.as<unsigned long long>(); O.bids = c->bids_a.as<uint32_t>(); O.bcount = c->bcount.as<uint32_t>();
+        O.vbase = (uint32_t)vtotal; O.tbase = (uint32_t)ttotal; O.bcap = (uint32_t)std::min<size_t>((size_t)bc + bv, 0xffffffffu);
+        if (global_mode) {
+            LAUNCH(c, k_mc_verts<true>, n_mc, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->vblk_off.as<uint32_t>(),
+                   c->vcnt.as<uint32_t>(), c->voff.as<uint32_t>(), c->tile_tab.as<SsTile>(), c->list_mc.as<uint32_t>(), O);
+            LAUNCH(c, k_mc_tris<true>, n_mc, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->tblk_off.as<uint32_t>(),
+                   c->tcnt.as<uint32_t>(), c->voff.as<uint32_t>(), c->list_mc.as<uint32_t>(), O);
+        } else {
+            LAUNCH(c, k_mc_verts<false>, n_mc, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->vblk_off.as<uint32_t>(),
+                   c->vcnt.as<uint32_t>(), c->voff.as<uint32_t>(), c->tile_tab.as<SsTile>(), c->list_mc.as<uint32_t>(), O);
+            LAUNCH(c, k_mc_tris<false>, n_mc, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->tblk_off.as<uint32_t>(),
+                   c->tcnt.as<uint32_t>(), c->voff.as<uint32_t>(), c->list_mc.as<uint32_t>(), O);
+        }
+        vtotal += bv; ttotal += bt;
+    }
+    return SS_OK;
+}
+
+// Stitching: weld duplicated boundary vertices (same MC edge key), compact the vertices, remap the triangle indices.
+static int weld_boundary_vertices(ss_context *c, ss_surface *out, uint64_t vtotal, uint64_t ttotal, uint64_t &nv_final_out, uint32_t &bc_out) {
+    cudaStream_t st = c->stream;
+    uint32_t bc = 0;
+    CK(cudaMemcpyAsync(&bc, c->bcount.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    uint64_t nv_final = vtotal;
+    if (vtotal && bc) {
+        c->bkeys_b.ensure((size_t)bc * 8); c->bids_b.ensure((size_t)bc * 4);
+        size_t tmp = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->bkeys_a.as<unsigned long long>(), c->bkeys_b.as<unsigned long long>(),
+                                           c->bids_a.as<uint32_t>(), c->bids_b.as<uint32_t>(), (int)bc, 0, 64, st));
+        c->cub_tmp.ensure(tmp);
+        CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, c->bkeys_a.as<unsigned long long>(), c->bkeys_b.as<unsigned long long>(),
+                                           c->bids_a.as<uint32_t>(), c->bids_b.as<uint32_t>(), (int)bc, 0, 64, st));
+        c->launches += 17;
+        c->remap.ensure(vtotal * 4); c->keep.ensure(vtotal * 4); c->newid.ensure(vtotal * 4 + 4);
+        LAUNCH(c, k_iota_keep, nblk(vtotal, 256), 256, (uint32_t)vtotal, c->remap.as<uint32_t>(), c->keep.as<uint32_t>());
+        LAUNCH(c, k_weld_runs, nblk(bc, 256), 256, c->bkeys_b.as<unsigned long long>(), c->bids_b.as<uint32_t>(), bc,
+               c->remap.as<uint32_t>(), c->keep.as<uint32_t>());
+        cub_excl_scan(c, c->keep.as<uint32_t>(), c->newid.as<uint32_t>(), (uint32_t)vtotal);
+        uint32_t lk = 0, ln = 0;
+        CK(cudaMemcpyAsync(&lk, c->keep.as<uint32_t>() + (vtotal - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&ln, c->newid.as<uint32_t>() + (vtotal - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        nv_final = (uint64_t)lk + ln;
+        // compact into fresh buffers (swap)
+        DevBuf nverts = c->o_verts2, nkeys = c->o_vkeys2;
+        c->o_verts2 = DevBuf(); c->o_vkeys2 = DevBuf();
+        nverts.ensure(std::max<uint64_t>(vtotal, 1) * 12); nkeys.ensure(std::max<uint64_t>(vtotal, 1) * 8);
+        LAUNCH(c, k_compact_verts, nblk(vtotal, 256), 256, (uint32_t)vtotal, c->keep.as<uint32_t>(), c->newid.as<uint32_t>(),
+               out->verts.as<float>(), out->vkeys.as<unsigned long long>(), nverts.as<float>(), nkeys.as<unsigned long long>());
+        LAUNCH(c, k_remap_tris, nblk(ttotal * 3, 256), 256, ttotal * 3, c->remap.as<uint32_t>(), c->newid.as<uint32_t>(), out->tris.as<uint32_t>());
+        CK(cudaStreamSynchronize(st));
+        c->o_verts2 = out->verts; c->o_vkeys2 = out->vkeys;     // keep the pre-weld buffers for the next frame
+        out->verts = nverts; out->vkeys = nkeys;
+    }
+    nv_final_out = nv_final; bc_out = bc;
+    return SS_OK;
+}
+
 static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params_f32 *p, ss_surface *out, const Partition &part = Partition(),
                               bool global_mode = false) {
     const uint64_t n = PP.n;
@@ -722,82 +900,9 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
         CK(cudaMemsetAsync(c->bstate.p, 0, (size_t)nbatch * nbricks, st));
         CK(cudaMemsetAsync(c->vmask.p, 0, (size_t)nbatch * np3, st));
         CK(cudaEventRecord(c->ev[10], st));
-        SsLsArgs A{};
-        A.bin_start = c->tab_a.as<uint32_t>(); A.bin_end = c->tab_b.as<uint32_t>(); A.rec = c->rec.as<float4>();
-        A.ksplit = c->ksplit.as<int>(); A.pidx = c->val_a.as<uint32_t>();
-        A.tile_tab = c->tile_tab.as<SsTile>(); A.brick_rng = c->brick_rng.as<int2>(); A.tiles = c->tiles.as<float>();
-        A.pairs = c->count_pairs ? c->pairs.as<unsigned long long>() : nullptr;
-        A.mode = exact_all ? SS_LS_EXACT_ALL : SS_LS_CERTIFY;
-        A.wflag = nullptr; A.fix_bricks = nullptr; A.bstate = c->bstate.as<uint8_t>();
-        const uint32_t n_work = build_worklist(c, D, nbatch);
-        A.work_list = c->list_ls.as<uint32_t>();
-        const bool split_certify = c->ls_variant == 1 && !exact_all && certify_runs <= 32;
-        if (n_work && !split_certify) { launch_levelset(c, dim3(n_work), D, A, c->count_pairs != 0, global_mode); ++ls_launches; }
-        if (n_work && split_certify) {
-            // variant 1 (ss_certify.cuh): certification kernel, then the exact pass over the boxes it could not certify
-            const uint32_t nbr_c = nbatch * nbricks;
-            c->wstate.ensure((size_t)nbr_c * SS_LS_WARPS); c->wflag.ensure((size_t)nbr_c * SS_LS_WARPS); c->desc_ls.ensure((size_t)n_work * 16);
-            c->flag_fix.ensure((size_t)nbr_c * 4); c->off_fix.ensure((size_t)nbr_c * 4 + 4); c->fix_list.ensure((size_t)nbr_c * 4);
-            CK(cudaMemsetAsync(c->wstate.p, 0, (size_t)nbr_c * SS_LS_WARPS, st));
-            LAUNCH(c, k_compact_desc, nblk(nbr_c, 256), 256, D, c->flag_ls.as<uint32_t>(), c->off_ls.as<uint32_t>(), nbr_c, c->desc_ls.as<uint4>());
-            SsCertArgs CA{};
-            CA.bin_start = A.bin_start; CA.bin_end = A.bin_end; CA.rec = A.rec; CA.tile_tab = A.tile_tab; CA.brick_rng = A.brick_rng;
-            CA.work_desc = c->desc_ls.as<uint4>(); CA.tiles = A.tiles; CA.wstate = c->wstate.as<uint8_t>();
-            if (global_mode) LAUNCH(c, k_certify<true>, n_work, SS_LS_THREADS, D, CA);
-            else LAUNCH(c, k_certify<false>, n_work, SS_LS_THREADS, D, CA);
-            ++ls_launches;
-            LAUNCH(c, k_wstate_reduce, nblk(nbr_c, 256), 256, c->wstate.as<uint8_t>(), nbr_c, c->bstate.as<uint8_t>(), c->flag_fix.as<uint32_t>(),
-                   c->wflag.as<uint8_t>());
-            cub_excl_scan(c, c->flag_fix.as<uint32_t>(), c->off_fix.as<uint32_t>(), nbr_c);
-            LAUNCH(c, k_compact_list, nblk(nbr_c, 256), 256, c->flag_fix.as<uint32_t>(), c->off_fix.as<uint32_t>(), nbr_c, c->fix_list.as<uint32_t>());
-            uint32_t ln[2] = { 0, 0 };
-            CK(cudaMemcpyAsync(&ln[0], c->off_fix.as<uint32_t>() + (nbr_c - 1), 4, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(&ln[1], c->flag_fix.as<uint32_t>() + (nbr_c - 1), 4, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            if (ln[0] + ln[1]) {
-                SsLsArgs F = A;
-                F.mode = SS_LS_FIX; F.wflag = c->wflag.as<uint8_t>(); F.fix_bricks = c->fix_list.as<uint32_t>();
-                launch_levelset(c, dim3(ln[0] + ln[1]), D, F, c->count_pairs != 0, global_mode);
-                ++ls_launches;
-            }
-        }
-        out->tm.bricks_levelset += n_work;
-        // bricks that can carry surface (for marching cubes) / markers next to outside points (for the fix-up sweep)
-        const uint32_t nbr_b = nbatch * nbricks;
-        c->flag_mc.ensure((size_t)nbr_b * 4); c->flag_fix.ensure((size_t)nbr_b * 4); c->off_mc.ensure((size_t)nbr_b * 4 + 4); c->off_fix.ensure((size_t)nbr_b * 4 + 4);
-        c->list_mc.ensure((size_t)nbr_b * 4); c->list_fix.ensure((size_t)nbr_b * 4);
-        LAUNCH(c, k_brick_classify, nblk(nbr_b, 256), 256, D, c->bstate.as<uint8_t>(), nbr_b, c->flag_mc.as<uint32_t>(), c->flag_fix.as<uint32_t>());
-        cub_excl_scan(c, c->flag_mc.as<uint32_t>(), c->off_mc.as<uint32_t>(), nbr_b);
-        cub_excl_scan(c, c->flag_fix.as<uint32_t>(), c->off_fix.as<uint32_t>(), nbr_b);
-        LAUNCH(c, k_compact_list, nblk(nbr_b, 256), 256, c->flag_mc.as<uint32_t>(), c->off_mc.as<uint32_t>(), nbr_b, c->list_mc.as<uint32_t>());
-        LAUNCH(c, k_compact_list, nblk(nbr_b, 256), 256, c->flag_fix.as<uint32_t>(), c->off_fix.as<uint32_t>(), nbr_b, c->list_fix.as<uint32_t>());
-        uint32_t lc[4] = { 0, 0, 0, 0 };
-        CK(cudaMemcpyAsync(&lc[0], c->off_mc.as<uint32_t>() + (nbr_b - 1), 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(&lc[1], c->flag_mc.as<uint32_t>() + (nbr_b - 1), 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(&lc[2], c->off_fix.as<uint32_t>() + (nbr_b - 1), 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(&lc[3], c->flag_fix.as<uint32_t>() + (nbr_b - 1), 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        const uint32_t n_mc = lc[0] + lc[1], n_fixscan = lc[2] + lc[3];
-        out->tm.bricks_total += nbr_b; out->tm.bricks_mc += n_mc; out->tm.bricks_fixscan += n_fixscan;
-        if (!exact_all && n_fixscan) {
-            // exact values for certified points that turn out to lie on a surface-crossing edge
-            const size_t nbr = (size_t)nbatch * nbricks;
-            c->wflag.ensure(nbr * SS_LS_WARPS); c->brick_seen.ensure(nbr * 4); c->fix_list.ensure(nbr * 4); c->nflag.ensure(8);
-            CK(cudaMemsetAsync(c->wflag.p, 0, nbr * SS_LS_WARPS, st));
-            CK(cudaMemsetAsync(c->brick_seen.p, 0, nbr * 4, st));
-            CK(cudaMemsetAsync(c->nflag.p, 0, 8, st));
-            LAUNCH(c, k_fixup_flags, n_fixscan, SS_TP_THREADS, D, c->tiles.as<float>(), c->list_fix.as<uint32_t>(), c->wflag.as<uint8_t>(),
-                   c->brick_seen.as<uint32_t>(), c->fix_list.as<uint32_t>(), c->nflag.as<uint32_t>());
-            uint32_t nfl[2] = { 0, 0 };
-            CK(cudaMemcpyAsync(nfl, c->nflag.p, 8, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            if (nfl[0]) {
-                A.mode = SS_LS_FIX; A.wflag = c->wflag.as<uint8_t>(); A.fix_bricks = c->fix_list.as<uint32_t>();
-                launch_levelset(c, dim3(nfl[0]), D, A, c->count_pairs != 0, global_mode);
-                ++ls_launches;
-                fix_points += nfl[1];
-            }
-        }
+        uint32_t n_mc = 0;
+        rc = levelset_batch(c, D, nbatch, nbricks, exact_all, certify_runs, global_mode, out, ls_launches, fix_points, &n_mc);
+        if (rc) return rc;
         CK(cudaEventRecord(c->ev[11], st));
         // optional parity tap
         if (c->keep_tile_flat >= 0) {
@@ -807,51 +912,8 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
                 CK(cudaStreamSynchronize(st));
             }
         }
-        // marching cubes over the listed bricks: count, scan the brick totals, emit vertices, emit triangles
-        uint64_t bv = 0, bt = 0;
-        if (n_mc) {
-            if (global_mode) LAUNCH(c, k_mc_count<true>, n_mc, SS_TP_THREADS, D, c->tiles.as<float>(), c->list_mc.as<uint32_t>(), c->vmask.as<uint8_t>(), c->vcnt.as<uint32_t>(), c->tcnt.as<uint32_t>());
-            else LAUNCH(c, k_mc_count<false>, n_mc, SS_TP_THREADS, D, c->tiles.as<float>(), c->list_mc.as<uint32_t>(), c->vmask.as<uint8_t>(), c->vcnt.as<uint32_t>(), c->tcnt.as<uint32_t>());
-            cub_excl_scan(c, c->vcnt.as<uint32_t>(), c->vblk_off.as<uint32_t>(), n_mc);
-            cub_excl_scan(c, c->tcnt.as<uint32_t>(), c->tblk_off.as<uint32_t>(), n_mc);
-        }
-        uint32_t bc = 0;
-        CK(cudaMemcpyAsync(&bc, c->bcount.p, 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        if (n_mc) {
-            uint32_t lv[2] = { 0, 0 }, lt[2] = { 0, 0 };
-            CK(cudaMemcpyAsync(&lv[1], c->vcnt.as<uint32_t>() + (n_mc - 1), 4, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(&lt[1], c->tcnt.as<uint32_t>() + (n_mc - 1), 4, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(&lv[0], c->vblk_off.as<uint32_t>() + (n_mc - 1), 4, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(&lt[0], c->tblk_off.as<uint32_t>() + (n_mc - 1), 4, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            bv = (uint64_t)lv[0] + lv[1]; bt = (uint64_t)lt[0] + lt[1];
-        }
-        if (vtotal + bv >= 0xfffffff0ull || (ttotal + bt) * 3 >= 0xffffffffffull) return ss_fail(SS_ERR_INDEX_TOO_SMALL, "mesh too large for 32-bit vertex ids");
-        if (bv || bt) {
-            out->verts.grow_keep((vtotal + bv) * 12, vtotal * 12, st);
-            out->vkeys.grow_keep((vtotal + bv) * 8, vtotal * 8, st);
-            out->tris.grow_keep((ttotal + bt) * 12, ttotal * 12, st);
-            // boundary list can hold at most every vertex of the batch
-            c->bkeys_a.grow_keep(((size_t)bc + bv) * 8, (size_t)bc * 8, st);
-            c->bids_a.grow_keep(((size_t)bc + bv) * 4, (size_t)bc * 4, st);
-            SsMcOut O{};
-            O.verts = out->verts.as<float>(); O.tris = out->tris.as<uint32_t>(); O.vkeys = out->vkeys.as<unsigned long long>();
-            O.bkeys = c->bkeys_a.as<unsigned long long>(); O.bids = c->bids_a.as<uint32_t>(); O.bcount = c->bcount.as<uint32_t>();
-            O.vbase = (uint32_t)vtotal; O.tbase = (uint32_t)ttotal; O.bcap = (uint32_t)std::min<size_t>((size_t)bc + bv, 0xffffffffu);
-            if (global_mode) {
-                LAUNCH(c, k_mc_verts<true>, n_mc, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->vblk_off.as<uint32_t>(),
-                       c->vcnt.as<uint32_t>(), c->voff.as<uint32_t>(), c->tile_tab.as<SsTile>(), c->list_mc.as<uint32_t>(), O);
-                LAUNCH(c, k_mc_tris<true>, n_mc, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->tblk_off.as<uint32_t>(),
-                       c->tcnt.as<uint32_t>(), c->voff.as<uint32_t>(), c->list_mc.as<uint32_t>(), O);
-            } else {
-                LAUNCH(c, k_mc_verts<false>, n_mc, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->vblk_off.as<uint32_t>(),
-                       c->vcnt.as<uint32_t>(), c->voff.as<uint32_t>(), c->tile_tab.as<SsTile>(), c->list_mc.as<uint32_t>(), O);
-                LAUNCH(c, k_mc_tris<false>, n_mc, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->tblk_off.as<uint32_t>(),
-                       c->tcnt.as<uint32_t>(), c->voff.as<uint32_t>(), c->list_mc.as<uint32_t>(), O);
-            }
-            vtotal += bv; ttotal += bt;
-        }
+        rc = marching_cubes_batch(c, D, global_mode, n_mc, out, vtotal, ttotal);
+        if (rc) return rc;
         CK(cudaEventRecord(c->ev[6], st));
         CK(cudaEventSynchronize(c->ev[6]));
         float a = 0.f, b = 0.f;
@@ -861,41 +923,11 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     }
     CK(cudaEventRecord(c->ev[7], st));
 
-    // ---- stitching: weld duplicated boundary vertices, compact, remap triangle indices
-    uint32_t bc = 0;
-    CK(cudaMemcpyAsync(&bc, c->bcount.p, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    // ---- stitching
     uint64_t nv_final = vtotal;
-    if (vtotal && bc) {
-        c->bkeys_b.ensure((size_t)bc * 8); c->bids_b.ensure((size_t)bc * 4);
-        size_t tmp = 0;
-        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->bkeys_a.as<unsigned long long>(), c->bkeys_b.as<unsigned long long>(),
-                                           c->bids_a.as<uint32_t>(), c->bids_b.as<uint32_t>(), (int)bc, 0, 64, st));
-        c->cub_tmp.ensure(tmp);
-        CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, c->bkeys_a.as<unsigned long long>(), c->bkeys_b.as<unsigned long long>(),
-                                           c->bids_a.as<uint32_t>(), c->bids_b.as<uint32_t>(), (int)bc, 0, 64, st));
-        c->launches += 17;
-        c->remap.ensure(vtotal * 4); c->keep.ensure(vtotal * 4); c->newid.ensure(vtotal * 4 + 4);
-        LAUNCH(c, k_iota_keep, nblk(vtotal, 256), 256, (uint32_t)vtotal, c->remap.as<uint32_t>(), c->keep.as<uint32_t>());
-        LAUNCH(c, k_weld_runs, nblk(bc, 256), 256, c->bkeys_b.as<unsigned long long>(), c->bids_b.as<uint32_t>(), bc,
-               c->remap.as<uint32_t>(), c->keep.as<uint32_t>());
-        cub_excl_scan(c, c->keep.as<uint32_t>(), c->newid.as<uint32_t>(), (uint32_t)vtotal);
-        uint32_t lk = 0, ln = 0;
-        CK(cudaMemcpyAsync(&lk, c->keep.as<uint32_t>() + (vtotal - 1), 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(&ln, c->newid.as<uint32_t>() + (vtotal - 1), 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        nv_final = (uint64_t)lk + ln;
-        // compact into fresh buffers (swap)
-        DevBuf nverts = c->o_verts2, nkeys = c->o_vkeys2;
-        c->o_verts2 = DevBuf(); c->o_vkeys2 = DevBuf();
-        nverts.ensure(std::max<uint64_t>(vtotal, 1) * 12); nkeys.ensure(std::max<uint64_t>(vtotal, 1) * 8);
-        LAUNCH(c, k_compact_verts, nblk(vtotal, 256), 256, (uint32_t)vtotal, c->keep.as<uint32_t>(), c->newid.as<uint32_t>(),
-               out->verts.as<float>(), out->vkeys.as<unsigned long long>(), nverts.as<float>(), nkeys.as<unsigned long long>());
-        LAUNCH(c, k_remap_tris, nblk(ttotal * 3, 256), 256, ttotal * 3, c->remap.as<uint32_t>(), c->newid.as<uint32_t>(), out->tris.as<uint32_t>());
-        CK(cudaStreamSynchronize(st));
-        c->o_verts2 = out->verts; c->o_vkeys2 = out->vkeys;     // keep the pre-weld buffers for the next frame
-        out->verts = nverts; out->vkeys = nkeys;
-    }
+    uint32_t bc = 0;
+    rc = weld_boundary_vertices(c, out, vtotal, ttotal, nv_final, bc);
+    if (rc) return rc;
     out->nv = nv_final; out->nt = ttotal;
     c->hint_nv = vtotal; c->hint_nt = ttotal; c->hint_bc = bc;
     {
