@@ -440,6 +440,89 @@ struct Partition {
     void *max_reduce_user = nullptr;
 };
 
+// SPH densities (and optional CSR neighbour lists) of the filtered particles: per-subdomain cell lists on the h-lattice with
+// ordered neighbour sums (dense_subdomains.rs:496-646), or one cell list over the whole domain in global mode.
+static int stage_densities(ss_context *c, const SsDev &D, const float *d_xyz, uint64_t n, uint32_t M, uint32_t nsub, uint64_t g_ns_cells,
+                           bool global_mode, bool want_nbrs, ss_surface *out, float *d_rho) {
+    cudaStream_t st = c->stream;
+    if ((uint64_t)nsub * (uint64_t)D.ns_stride >= 0xffffffffull || (uint64_t)nsub * (uint64_t)D.nbin_sub >= 0xffffffffull)
+        return ss_fail(SS_ERR_INDEX_TOO_SMALL, "too many non-empty subdomains for 32-bit cell keys");
+    c->err.ensure(4);
+    CK(cudaMemsetAsync(c->err.p, 0, 4, st));
+    // membership arrays: cid (compressed subdomain), val_b (particle); keys -> key_a, sorted -> key_b? key_b is in use
+    // (flat ids are no longer needed after cid): reuse key_b as sort output, val_a as sorted payload.
+    if (!global_mode) {
+    LAUNCH(c, k_ns_keys, nblk(M, 256), 256, D, d_xyz, M, c->cid.as<uint32_t>(), c->sub_flat.as<uint32_t>(), c->val_b.as<uint32_t>(),
+           c->key_a.as<uint32_t>(), c->err.as<int>());
+    const uint64_t ns_keys = (uint64_t)nsub * D.ns_stride;
+    cub_sort_pairs(c, c->key_a.as<uint32_t>(), c->key_b.as<uint32_t>(), c->val_b.as<uint32_t>(), c->val_a.as<uint32_t>(), M, bits_for(ns_keys));
+    c->tab_a.ensure(ns_keys * 4); c->tab_b.ensure(ns_keys * 4);
+    CK(cudaMemsetAsync(c->tab_a.p, 0xff, ns_keys * 4, st));
+    LAUNCH(c, k_mark_starts, nblk(M, 256), 256, c->key_b.as<uint32_t>(), M, c->tab_a.as<uint32_t>(), (uint32_t)ns_keys);
+    LAUNCH(c, k_run_counts, nblk(M, 256), 256, c->key_b.as<uint32_t>(), M, c->tab_b.as<uint32_t>(), (uint32_t)ns_keys);
+    c->spos.ensure((size_t)M * 16);
+    LAUNCH(c, k_gather_pos, nblk(M, 256), 256, d_xyz, c->val_a.as<uint32_t>(), M, c->spos.as<float4>());
+    unsigned long long *d_ncnt = nullptr;
+    if (want_nbrs) { out->nbr_off.ensure((n + 1) * 8); d_ncnt = out->nbr_off.as<unsigned long long>(); CK(cudaMemsetAsync(d_ncnt, 0, (n + 1) * 8, st)); }
+    LAUNCH(c, k_density<false>, nblk(M, 128), 128, D, M, c->key_b.as<uint32_t>(), c->spos.as<float4>(), c->sub_flat.as<uint32_t>(),
+           c->tab_a.as<uint32_t>(), c->tab_b.as<uint32_t>(), d_rho, d_ncnt, (const unsigned long long *)nullptr, (uint32_t *)nullptr);
+    if (want_nbrs) {
+        const uint64_t total = scan_neighbor_counts(c, d_ncnt, n);
+        out->nbr_idx.ensure(std::max<uint64_t>(total, 1) * 4);
+        LAUNCH(c, k_density<true>, nblk(M, 128), 128, D, M, c->key_b.as<uint32_t>(), c->spos.as<float4>(), c->sub_flat.as<uint32_t>(),
+               c->tab_a.as<uint32_t>(), c->tab_b.as<uint32_t>(), d_rho, (unsigned long long *)nullptr, (const unsigned long long *)d_ncnt, out->nbr_idx.as<uint32_t>());
+        out->has_neighbors = 1; out->n_neighbors = total;
+    }
+    } else {
+        // one cell list over the whole domain; particles (not memberships) are the entries
+        const uint32_t n32 = (uint32_t)n;
+        c->gkey_a.ensure((size_t)n32 * 4); c->gkey_b.ensure((size_t)n32 * 4); c->gval_a.ensure((size_t)n32 * 4); c->gval_b.ensure((size_t)n32 * 4);
+        LAUNCH(c, k_ns_keys_global, nblk(n32, 256), 256, D, d_xyz, n32, c->gkey_a.as<uint32_t>(), c->gval_a.as<uint32_t>(), c->err.as<int>());
+        cub_sort_pairs(c, c->gkey_a.as<uint32_t>(), c->gkey_b.as<uint32_t>(), c->gval_a.as<uint32_t>(), c->gval_b.as<uint32_t>(), n32, bits_for(g_ns_cells));
+        c->tab_a.ensure(g_ns_cells * 4); c->tab_b.ensure(g_ns_cells * 4);
+        CK(cudaMemsetAsync(c->tab_a.p, 0xff, g_ns_cells * 4, st));
+        LAUNCH(c, k_mark_starts, nblk(n32, 256), 256, c->gkey_b.as<uint32_t>(), n32, c->tab_a.as<uint32_t>(), (uint32_t)g_ns_cells);
+        LAUNCH(c, k_run_counts, nblk(n32, 256), 256, c->gkey_b.as<uint32_t>(), n32, c->tab_b.as<uint32_t>(), (uint32_t)g_ns_cells);
+        c->spos.ensure((size_t)n32 * 16);
+        LAUNCH(c, k_gather_pos, nblk(n32, 256), 256, d_xyz, c->gval_b.as<uint32_t>(), n32, c->spos.as<float4>());
+        unsigned long long *d_ncnt = nullptr;
+        if (want_nbrs) { out->nbr_off.ensure((n + 1) * 8); d_ncnt = out->nbr_off.as<unsigned long long>(); CK(cudaMemsetAsync(d_ncnt, 0, (n + 1) * 8, st)); }
+        LAUNCH(c, k_density_global<false>, nblk(n32, 128), 128, D, n32, c->gkey_b.as<uint32_t>(), c->spos.as<float4>(), c->tab_a.as<uint32_t>(),
+               c->tab_b.as<uint32_t>(), d_rho, d_ncnt, (const unsigned long long *)nullptr, (uint32_t *)nullptr);
+        if (want_nbrs) {
+            const uint64_t total = scan_neighbor_counts(c, d_ncnt, n);
+            out->nbr_idx.ensure(std::max<uint64_t>(total, 1) * 4);
+            LAUNCH(c, k_density_global<true>, nblk(n32, 128), 128, D, n32, c->gkey_b.as<uint32_t>(), c->spos.as<float4>(), c->tab_a.as<uint32_t>(),
+                   c->tab_b.as<uint32_t>(), d_rho, (unsigned long long *)nullptr, (const unsigned long long *)d_ncnt, out->nbr_idx.as<uint32_t>());
+            out->has_neighbors = 1; out->n_neighbors = total;
+        }
+    }
+    return SS_OK;
+}
+
+// Splat bins: memberships sorted by (subdomain, 8^3-point brick bin) + the particle records (x, y, z, V) the level set gathers.
+// val_b still holds the membership particle indices in subdomain order (stable input for the bin sort).
+static int stage_binning(ss_context *c, const SsDev &D, const float *d_xyz, const float *d_rho, uint32_t M, uint32_t nsub, bool partitioned) {
+    cudaStream_t st = c->stream;
+    LAUNCH(c, k_bin_keys, nblk(M, 256), 256, D, d_xyz, M, c->cid.as<uint32_t>(), c->sub_flat.as<uint32_t>(), c->val_b.as<uint32_t>(),
+           partitioned ? c->sub_owned.as<uint8_t>() : nullptr, c->key_a.as<uint32_t>());
+    cub_sort_pairs(c, c->key_a.as<uint32_t>(), c->key_b.as<uint32_t>(), c->val_b.as<uint32_t>(), c->val_a.as<uint32_t>(), M, 32);
+    const uint64_t bin_keys = (uint64_t)nsub * D.nbin_sub;
+    c->tab_a.ensure(bin_keys * 4); c->tab_b.ensure(bin_keys * 4);
+    CK(cudaMemsetAsync(c->tab_a.p, 0xff, bin_keys * 4, st));
+    LAUNCH(c, k_mark_starts, nblk(M, 256), 256, c->key_b.as<uint32_t>(), M, c->tab_a.as<uint32_t>(), (uint32_t)bin_keys);
+    LAUNCH(c, k_run_counts, nblk(M, 256), 256, c->key_b.as<uint32_t>(), M, c->tab_b.as<uint32_t>(), (uint32_t)bin_keys);
+    c->rec.ensure((size_t)M * 16); c->ksplit.ensure((size_t)M * 4);
+    LAUNCH(c, k_records, nblk(M, 256), 256, D, d_xyz, d_rho, M, c->key_b.as<uint32_t>(), c->val_a.as<uint32_t>(),
+           c->sub_flat.as<uint32_t>(), c->rec.as<float4>(), c->ksplit.as<int>());
+    int h_err = 0;
+    CK(cudaMemcpyAsync(&h_err, c->err.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(c->ev[5], st));
+    CK(cudaStreamSynchronize(st));
+    if (h_err) return ss_fail(SS_ERR_INVALID_PARAMETER, "particle outside of its subdomain's neighbourhood-search grid (reference: panic)");
+    return SS_OK;
+}
+
 // Level set of one batch of tiles: work list, certification + exact values (fused kernel, or variant 1: certification kernel +
 // exact pass), brick classification, fix-up sweep.  Leaves the tiles, the per-brick states and the marching-cubes brick list
 // (c->list_mc, *n_mc_out entries) in the context scratch.
@@ -772,79 +855,12 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     CK(cudaMemcpyAsync(c->sub_sparse.p, out->sub_sparse.data(), nsub, cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(c->ev[3], st));
 
-    // ---- densities: per-subdomain cell lists on the h-lattice, ordered neighbour sums
-    if ((uint64_t)nsub * (uint64_t)D.ns_stride >= 0xffffffffull || (uint64_t)nsub * (uint64_t)D.nbin_sub >= 0xffffffffull)
-        return ss_fail(SS_ERR_INDEX_TOO_SMALL, "too many non-empty subdomains for 32-bit cell keys");
-    c->err.ensure(4);
-    CK(cudaMemsetAsync(c->err.p, 0, 4, st));
-    // membership arrays: cid (compressed subdomain), val_b (particle); keys -> key_a, sorted -> key_b? key_b is in use
-    // (flat ids are no longer needed after cid): reuse key_b as sort output, val_a as sorted payload.
-    if (!global_mode) {
-    LAUNCH(c, k_ns_keys, nblk(M, 256), 256, D, d_xyz, M, c->cid.as<uint32_t>(), c->sub_flat.as<uint32_t>(), c->val_b.as<uint32_t>(),
-           c->key_a.as<uint32_t>(), c->err.as<int>());
-    const uint64_t ns_keys = (uint64_t)nsub * D.ns_stride;
-    cub_sort_pairs(c, c->key_a.as<uint32_t>(), c->key_b.as<uint32_t>(), c->val_b.as<uint32_t>(), c->val_a.as<uint32_t>(), M, bits_for(ns_keys));
-    c->tab_a.ensure(ns_keys * 4); c->tab_b.ensure(ns_keys * 4);
-    CK(cudaMemsetAsync(c->tab_a.p, 0xff, ns_keys * 4, st));
-    LAUNCH(c, k_mark_starts, nblk(M, 256), 256, c->key_b.as<uint32_t>(), M, c->tab_a.as<uint32_t>(), (uint32_t)ns_keys);
-    LAUNCH(c, k_run_counts, nblk(M, 256), 256, c->key_b.as<uint32_t>(), M, c->tab_b.as<uint32_t>(), (uint32_t)ns_keys);
-    c->spos.ensure((size_t)M * 16);
-    LAUNCH(c, k_gather_pos, nblk(M, 256), 256, d_xyz, c->val_a.as<uint32_t>(), M, c->spos.as<float4>());
-    unsigned long long *d_ncnt = nullptr;
-    if (want_nbrs) { out->nbr_off.ensure((n + 1) * 8); d_ncnt = out->nbr_off.as<unsigned long long>(); CK(cudaMemsetAsync(d_ncnt, 0, (n + 1) * 8, st)); }
-    LAUNCH(c, k_density<false>, nblk(M, 128), 128, D, M, c->key_b.as<uint32_t>(), c->spos.as<float4>(), c->sub_flat.as<uint32_t>(),
-           c->tab_a.as<uint32_t>(), c->tab_b.as<uint32_t>(), d_rho, d_ncnt, (const unsigned long long *)nullptr, (uint32_t *)nullptr);
-    if (want_nbrs) {
-        const uint64_t total = scan_neighbor_counts(c, d_ncnt, n);
-        out->nbr_idx.ensure(std::max<uint64_t>(total, 1) * 4);
-        LAUNCH(c, k_density<true>, nblk(M, 128), 128, D, M, c->key_b.as<uint32_t>(), c->spos.as<float4>(), c->sub_flat.as<uint32_t>(),
-               c->tab_a.as<uint32_t>(), c->tab_b.as<uint32_t>(), d_rho, (unsigned long long *)nullptr, (const unsigned long long *)d_ncnt, out->nbr_idx.as<uint32_t>());
-        out->has_neighbors = 1; out->n_neighbors = total;
-    }
-    } else {
-        // one cell list over the whole domain; particles (not memberships) are the entries
-        const uint32_t n32 = (uint32_t)n;
-        c->gkey_a.ensure((size_t)n32 * 4); c->gkey_b.ensure((size_t)n32 * 4); c->gval_a.ensure((size_t)n32 * 4); c->gval_b.ensure((size_t)n32 * 4);
-        LAUNCH(c, k_ns_keys_global, nblk(n32, 256), 256, D, d_xyz, n32, c->gkey_a.as<uint32_t>(), c->gval_a.as<uint32_t>(), c->err.as<int>());
-        cub_sort_pairs(c, c->gkey_a.as<uint32_t>(), c->gkey_b.as<uint32_t>(), c->gval_a.as<uint32_t>(), c->gval_b.as<uint32_t>(), n32, bits_for(g_ns_cells));
-        c->tab_a.ensure(g_ns_cells * 4); c->tab_b.ensure(g_ns_cells * 4);
-        CK(cudaMemsetAsync(c->tab_a.p, 0xff, g_ns_cells * 4, st));
-        LAUNCH(c, k_mark_starts, nblk(n32, 256), 256, c->gkey_b.as<uint32_t>(), n32, c->tab_a.as<uint32_t>(), (uint32_t)g_ns_cells);
-        LAUNCH(c, k_run_counts, nblk(n32, 256), 256, c->gkey_b.as<uint32_t>(), n32, c->tab_b.as<uint32_t>(), (uint32_t)g_ns_cells);
-        c->spos.ensure((size_t)n32 * 16);
-        LAUNCH(c, k_gather_pos, nblk(n32, 256), 256, d_xyz, c->gval_b.as<uint32_t>(), n32, c->spos.as<float4>());
-        unsigned long long *d_ncnt = nullptr;
-        if (want_nbrs) { out->nbr_off.ensure((n + 1) * 8); d_ncnt = out->nbr_off.as<unsigned long long>(); CK(cudaMemsetAsync(d_ncnt, 0, (n + 1) * 8, st)); }
-        LAUNCH(c, k_density_global<false>, nblk(n32, 128), 128, D, n32, c->gkey_b.as<uint32_t>(), c->spos.as<float4>(), c->tab_a.as<uint32_t>(),
-               c->tab_b.as<uint32_t>(), d_rho, d_ncnt, (const unsigned long long *)nullptr, (uint32_t *)nullptr);
-        if (want_nbrs) {
-            const uint64_t total = scan_neighbor_counts(c, d_ncnt, n);
-            out->nbr_idx.ensure(std::max<uint64_t>(total, 1) * 4);
-            LAUNCH(c, k_density_global<true>, nblk(n32, 128), 128, D, n32, c->gkey_b.as<uint32_t>(), c->spos.as<float4>(), c->tab_a.as<uint32_t>(),
-                   c->tab_b.as<uint32_t>(), d_rho, (unsigned long long *)nullptr, (const unsigned long long *)d_ncnt, out->nbr_idx.as<uint32_t>());
-            out->has_neighbors = 1; out->n_neighbors = total;
-        }
-    }
+    // ---- densities, then the splat bins
+    rc = stage_densities(c, D, d_xyz, n, M, nsub, g_ns_cells, global_mode, want_nbrs, out, d_rho);
+    if (rc) return rc;
     CK(cudaEventRecord(c->ev[4], st));
-
-    // ---- splat binning: (subdomain, 8^3-point brick) bins + particle records
-    // val_b still holds the membership particle indices in subdomain order (stable input for the bin sort)
-    LAUNCH(c, k_bin_keys, nblk(M, 256), 256, D, d_xyz, M, c->cid.as<uint32_t>(), c->sub_flat.as<uint32_t>(), c->val_b.as<uint32_t>(),
-           part.enabled ? c->sub_owned.as<uint8_t>() : nullptr, c->key_a.as<uint32_t>());
-    cub_sort_pairs(c, c->key_a.as<uint32_t>(), c->key_b.as<uint32_t>(), c->val_b.as<uint32_t>(), c->val_a.as<uint32_t>(), M, 32);
-    const uint64_t bin_keys = (uint64_t)nsub * D.nbin_sub;
-    c->tab_a.ensure(bin_keys * 4); c->tab_b.ensure(bin_keys * 4);
-    CK(cudaMemsetAsync(c->tab_a.p, 0xff, bin_keys * 4, st));
-    LAUNCH(c, k_mark_starts, nblk(M, 256), 256, c->key_b.as<uint32_t>(), M, c->tab_a.as<uint32_t>(), (uint32_t)bin_keys);
-    LAUNCH(c, k_run_counts, nblk(M, 256), 256, c->key_b.as<uint32_t>(), M, c->tab_b.as<uint32_t>(), (uint32_t)bin_keys);
-    c->rec.ensure((size_t)M * 16); c->ksplit.ensure((size_t)M * 4);
-    LAUNCH(c, k_records, nblk(M, 256), 256, D, d_xyz, d_rho, M, c->key_b.as<uint32_t>(), c->val_a.as<uint32_t>(),
-           c->sub_flat.as<uint32_t>(), c->rec.as<float4>(), c->ksplit.as<int>());
-    int h_err = 0;
-    CK(cudaMemcpyAsync(&h_err, c->err.p, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaEventRecord(c->ev[5], st));
-    CK(cudaStreamSynchronize(st));
-    if (h_err) return ss_fail(SS_ERR_INVALID_PARAMETER, "particle outside of its subdomain's neighbourhood-search grid (reference: panic)");
+    rc = stage_binning(c, D, d_xyz, d_rho, M, nsub, part.enabled != 0);
+    if (rc) return rc;
 
     // ---- level set + marching cubes over batches of subdomain tiles
     const size_t np3 = (size_t)D.np * D.np * D.np;
