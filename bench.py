@@ -105,15 +105,16 @@ def make_cloud(n_target, workload="cfg4"):
     return syn.dam_break_scaled(n_target, 0.01, 3), f"synthetic dam-break scaled to ~{n_target} particles (cfg-4 proportions, r=0.01, seed 3)"
 
 
-def time_reference(p, repeats):
+def time_reference(p, repeats, kw=None):
     """The reference's own CPU implementation (pysplashsurf 0.14.0 wheel, rayon + AVX2) on all host cores."""
     import oracle
     ps = oracle.reference()
+    kw = kw or RECON_KW
     best = None
     for _ in range(repeats):
         t = time.perf_counter()
-        r = ps.reconstruct_surface(p, particle_radius=RECON_KW["particle_radius"], smoothing_length=RECON_KW["smoothing_length"],
-                                   cube_size=RECON_KW["cube_size"], iso_surface_threshold=RECON_KW["iso_surface_threshold"],
+        r = ps.reconstruct_surface(p, particle_radius=kw["particle_radius"], smoothing_length=kw["smoothing_length"],
+                                   cube_size=kw["cube_size"], iso_surface_threshold=kw["iso_surface_threshold"],
                                    multi_threading=True, simd=True, subdomain_grid=True, subdomain_num_cubes_per_dim=64)
         dt = time.perf_counter() - t
         best = dt if best is None else min(best, dt)
@@ -122,30 +123,92 @@ def time_reference(p, repeats):
     return best, nv, nt
 
 
+def cpu_stage_tree(p, kw):
+    """Per-stage wall times of the reference CLI pipeline (`splashsurf reconstruct -v`, cli.rs:124-130, README.md:198-231) on
+    the particle set `p`, parsed from the profile tree it logs.  Runs in a child process (the tree goes to the child's stderr).
+    Returns {} when anything goes wrong -- it is a side-by-side diagnostic, never part of a timed region."""
+    import re, tempfile
+    try:
+        d = tempfile.mkdtemp(prefix="ss_stage_")
+        xyz = os.path.join(d, "cloud.xyz")
+        np.ascontiguousarray(p, dtype="<f4").tofile(xyz)
+        code = ("import sys; sys.path.insert(0, %r); import oracle; ps = oracle.reference(); "
+                "ps.run_splashsurf(['splashsurf', 'reconstruct', %r, '-r=%r', '-l=%r', '-c=%r', '-t=%r', '-o', %r, '-v'])"
+                % (ROOT, xyz, kw["particle_radius"], kw["smoothing_length"], kw["cube_size"], kw["iso_surface_threshold"], os.path.join(d, "out.vtk")))
+        res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
+        out = {}
+        want = {"surface reconstruction subdomain-grid": "total", "decomposition": "decomposition", "compute_global_density_vector": "density",
+                "reconstruction": "levelset_plus_marching_cubes", "stitching": "stitching",
+                "density grid loop (avx)": "levelset_dense_cpu_seconds_summed", "density grid loop (sparse)": "levelset_sparse_cpu_seconds_summed",
+                "mc triangulation loop": "marching_cubes_cpu_seconds_summed"}
+        for line in (res.stdout + "\n" + res.stderr).splitlines():
+            m = re.search(r"\]\s+([^:\]]+?): [^,]*, ([0-9.]+)ms avg, (\d+) calls? \(total: ([0-9.]+)s\)", line)
+            if not m:
+                continue
+            name, avg_ms, calls, total_s = m.group(1).strip(), float(m.group(2)), int(m.group(3)), float(m.group(4))
+            key = want.get(name)
+            if key is None:
+                continue
+            if key.endswith("_summed"):
+                out[key] = out.get(key, 0.0) + total_s
+            elif key not in out:
+                out[key] = avg_ms if calls == 1 else total_s * 1e3
+        for f in os.listdir(d):
+            os.remove(os.path.join(d, f))
+        os.rmdir(d)
+        return out
+    except Exception as e:      # noqa: BLE001
+        return {"error": str(e)[:200]}
+
+
+def workload_config(args, desc, n_total, kw, parallelism):
+    wl = args.workload
+    return {"workload": (wl + ": " if wl != "cfg4" else ("cfg-4: " if n_total >= 50_000_000 else "cfg-4 (scaled): ")) + desc,
+            "particles": int(n_total), "r": kw["particle_radius"], "cube_size": f"{kw['cube_size']}r", "smoothing_length": "2.0r", "iso": 0.6,
+            "subdomain_cubes": 64, "parallelism": parallelism}
+
+
 def run_reference(args):
+    """The reference's own CPU implementation on the SAME cloud as the b200 arm (every step = one full reconstruct_surface of
+    the whole workload, all host threads).  `--ref-particles N` is an explicit opt-out (bounded sample, flagged in config)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import oracle
-    n_sample = args.ref_particles
-    p, desc = make_cloud(n_sample)
+    kw = dict(RECON_KW)
+    if WORKLOADS.get(args.workload):
+        kw.update(WORKLOADS[args.workload][1])
+    bounded = args.ref_particles is not None
+    p, desc = make_cloud(args.ref_particles if bounded else args.particles, args.workload)
     if not oracle.reference_available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (reference wheel) not present on this box"}))
         return 0
-    for _ in range(min(args.warmup, 1)):
-        time_reference(p, 1)
-    times = []
-    for _ in range(args.steps):
-        dt, nv, nt = time_reference(p, 1)
-        times.append(dt)
+    budget_s = float(os.environ.get("SS_REF_BUDGET_S", "1500"))
+    t_start = time.perf_counter()
+    times, warm_done, nv, nt = [], 0, 0, 0
+    steps, warmup = args.steps, args.warmup
+    for i in range(args.warmup + args.steps):
+        dt, nv, nt = time_reference(p, 1, kw)
+        if i < warmup:
+            warm_done += 1
+        else:
+            times.append(dt)
+        # budget guard: the whole arm has to end within the driver's limit even on a slow host; drop warm-ups first, then steps
+        left = budget_s - (time.perf_counter() - t_start)
+        if i + 1 < warmup and (warmup - i - 1 + steps) * dt > left:
+            warmup = i + 1
+        if len(times) >= 1 and (steps - len(times)) * dt > left:
+            break
     ms = 1e3 * float(np.mean(times))
     val = len(p) / (ms * 1e-3) / 1e6
+    cfg = workload_config(args, desc, len(p), kw, f"rayon, {os.cpu_count()} host threads")
+    cfg["bounded_sample"] = bool(bounded)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mparticles/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": {"workload": "cfg-4 dam break (bounded sample): " + desc, "particles": int(len(p)),
-                                                            "r": 0.01, "cube_size": "0.5r", "smoothing_length": "2.0r", "subdomain_cubes": 64},
+            "steps": len(times), "warmup": warm_done, "steps_requested": args.steps, "warmup_requested": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": val, "unit": "Mparticles/s", "cores": os.cpu_count(), "kind": "reference",
-                             "sample": f"{len(p)} particles of the same dam break, pysplashsurf 0.14.0 wheel (portable manylinux build, runtime AVX2), all host threads"},
+                             "sample": f"all {len(p)} particles of the workload per step, pysplashsurf 0.14.0 wheel (portable manylinux build, runtime AVX2), all host threads"},
             "e2e": {"value": val, "unit": "Mparticles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
             "mesh": {"vertices": nv, "triangles": nt}}
     print(json.dumps(line))
@@ -158,7 +221,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--particles", type=int, default=50_000_400, help="target particle count of the dam break (default: cfg-4)")
-    ap.add_argument("--ref-particles", type=int, default=2_000_000, help="bounded sample for the CPU reference")
+    ap.add_argument("--ref-particles", type=int, default=None,
+                    help="--impl reference only: time a bounded sample of this many particles instead of the whole workload (opt-out, flagged)")
+    ap.add_argument("--cpu-sample-particles", type=int, default=2_000_000, help="size of the bounded sample of the cpu_baseline leg")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS), help="BASELINE config (default cfg4 = the metric's 50 M dam break)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -284,12 +349,19 @@ def main():
         ach = ls_bytes / ls_s / 1e9 if ls_s > 0 else 0.0
         flops = (pairs / args.steps) * 30.0
         traffic, traffic_note = None, None
+        from splashsurf_b200 import build as ssbuild
+        src_sha = ssbuild.source_hash()
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "levelset_traffic.json")))
-            traffic = tj["dram_bytes"] / tj["particles_exact"] * n_total / max(ls_launches / args.steps, 1.0)
-            traffic_note = "per launch; scaled by particle count from " + tj["source"]
-        except Exception:
-            pass
+            if tj.get("source_sha") != src_sha:
+                traffic_note = f"refused: profiles/levelset_traffic.json was captured on source {tj.get('source_sha')}, this build is {src_sha}"
+            elif tj.get("particles") != int(n_total) and tj.get("scale_by_particles") is not True:
+                traffic_note = f"refused: capture was taken on {tj.get('particles')} particles, this run has {n_total}"
+            else:
+                traffic = float(tj["dram_bytes_per_launch"]) * (n_total / tj["particles"])
+                traffic_note = tj.get("source", "")
+        except Exception as e:      # noqa: BLE001
+            traffic_note = f"no capture: {e}"
         roof = {"bound": "hbm", "kernel": "k_levelset", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "traffic_note": traffic_note,
                 "peak_source": peak_src, "launches_per_step": ls_launches / args.steps, "ms_per_step": ls_ms / args.steps,
@@ -302,25 +374,30 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "Mparticles/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": (args.workload + ": " if args.workload != "cfg4" else ("cfg-4: " if n_total >= 50_000_000 else "cfg-4 (scaled): ")) + desc,
-                           "particles": int(n_total), "r": kw["particle_radius"],
-                           "cube_size": f"{kw['cube_size']}r", "smoothing_length": "2.0r", "iso": 0.6, "subdomain_cubes": 64,
-                           "parallelism": f"subdomain slabs x{world}" if world > 1 else "single GPU",
-                           "levelset_variant": int(args.levelset_variant),
-                           "l2": "inputs (600 MB) and tiles (GBs) exceed the 126 MB L2; no flush needed"},
+                "config": dict(workload_config(args, desc, n_total, kw, f"subdomain slabs x{world}" if world > 1 else "single GPU"),
+                               levelset_variant=int(args.levelset_variant),
+                               l2="inputs (600 MB) and tiles (GBs) exceed the 126 MB L2; no flush needed"),
                 "mesh": {"vertices": int(nv_g if nv_g is not None else nv), "triangles": int(nt_g if nt_g is not None else nt), "subdomains": int(n_sub)},
                 "wall_ms_per_step": wall_ms_max / args.steps, "step_ms_rank0": step_ms, "stage_ms_last_step": stage,
                 "e2e": {"value": e2e_val, "unit": "Mparticles/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(len(p_local) * 12 * world),
                         "d2h_bytes_per_step": int(d2h)},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "source_sha": src_sha}
         if not args.no_cpu_baseline and world == 1:
             try:
                 import oracle
                 if oracle.reference_available():
-                    ps, _ = make_cloud(args.ref_particles)
-                    dt, _, _ = time_reference(ps, 2)
+                    ps, _ = make_cloud(args.cpu_sample_particles, "cfg4")
+                    dt, _, _ = time_reference(ps, 2, RECON_KW)
                     line["cpu_baseline"] = {"value": len(ps) / dt / 1e6, "unit": "Mparticles/s", "cores": os.cpu_count(), "kind": "reference",
                                             "sample": f"{len(ps)}-particle dam break (same generator), best of 2, pysplashsurf 0.14.0 wheel on all host threads"}
+                    # stage by stage beside the GPU's stage_ms: the reference CLI's own profile tree on the same sample
+                    line["cpu_stage_ms"] = dict(cpu_stage_tree(ps, RECON_KW), particles=int(len(ps)),
+                                                note="wall ms of `splashsurf reconstruct -v` stages on the bounded sample; *_cpu_seconds_summed are summed over worker threads")
+                    # the GPU on the very same sample, for a like-for-like stage comparison
+                    rs = ss.reconstruct_surface(ps, context=ctx, **RECON_KW)
+                    rs = ss.reconstruct_surface(ps, context=ctx, **RECON_KW)
+                    line["gpu_stage_ms_same_sample"] = {k: round(float(v), 3) for k, v in rs.timings.items()
+                                                        if k in ("decomposition", "density", "binning", "levelset", "marching_cubes", "stitching", "total_device", "upload")}
                 else:
                     line["cpu_baseline"] = {"value": None, "unit": "Mparticles/s", "cores": os.cpu_count(), "kind": "reference", "sample": "oracle/_ref missing"}
             except Exception as e:   # the baseline must never take the bench line down

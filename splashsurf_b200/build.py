@@ -9,7 +9,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsplashsurf_b200.so")
 SOURCES = ["ss_pipeline.cu"]
-DEPS = ["ss_pipeline.cu", "ss_kernels.cuh", "ss_common.cuh", "mc_lut.inc", os.path.join("..", "..", "include", "splashsurf_b200.h")]
+
+
+def deps():
+    """Every file of csrc/ plus the public header: editing any of them makes the library stale."""
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(HERE, "..", "include", "splashsurf_b200.h")]
+
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -20,11 +25,21 @@ NVCC_FLAGS = [
 ]
 
 
+def source_hash() -> str:
+    """sha256 (first 16 hex digits) over the CUDA sources and the public header: identifies the code a profile was taken on."""
+    import hashlib
+    h = hashlib.sha256()
+    for d in deps():
+        if d.endswith((".cu", ".cuh", ".inc", ".h")):
+            h.update(open(d, "rb").read())
+    return h.hexdigest()[:16]
+
+
 def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS) or os.path.getmtime(__file__) > t
+    return any(os.path.getmtime(d) > t for d in deps()) or os.path.getmtime(__file__) > t
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -33,7 +33,7 @@ def _check_line(out: str, n_gpus: int, steps: int):
 # (the fixed-size workloads cfg2/cfg3/cfg5 take minutes to hours on the executor; the 1 M-particle cfg2 ran once by hand)
 @pytest.mark.parametrize("extra", [[], ["--levelset-variant", "1", "--no-cpu-baseline"]], ids=["default", "levelset_variant_1"])
 def test_bench_single_rank_on_executor(oracle_mod, extra):
-    cmd = [sys.executable, LAUNCHER, "bench.py", "--particles", "12000", "--steps", "2", "--warmup", "1", "--ref-particles", "8000"] + extra
+    cmd = [sys.executable, LAUNCHER, "bench.py", "--particles", "12000", "--steps", "2", "--warmup", "1", "--cpu-sample-particles", "8000"] + extra
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, SS_EMUL_THREADS="4"))
     assert r.returncode == 0, r.stderr[-3000:]
     d = _check_line(r.stdout, 1, 2)

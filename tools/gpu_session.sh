@@ -1,17 +1,20 @@
 #!/bin/bash
-# One GPU-box session that answers the open questions of round 1 (run under gpurun, ONE GPU):
-#
-#   gpurun --timeout 1500 -- 'bash tools/gpu_session.sh'
-#
-# Everything is wrapped in `timeout`; outputs go to gpurun_out/ (merged back by gpurun).  Nothing printed under ncu is a
-# bench value.  Order: correctness first, then the two level-set variants, then profiles.
+# One-GPU session (run under gpurun):   git rev-parse HEAD > .revision; gpurun --timeout 2400 -- 'bash tools/gpu_session.sh [stages]'
+# Stages (default: all):  tests variant parity bench ref launches ncu post memcheck
+# Everything is wrapped in `timeout`; outputs go to gpurun_out/ (merged back by gpurun).  Nothing printed under ncu is a bench value.
 set -u
 mkdir -p gpurun_out
 cd "${GRAFT_REPO_ROOT:-.}"
+STAGES="${*:-tests variant parity bench ref launches ncu post memcheck}"
+has() { [[ " $STAGES " == *" $1 "* ]]; }
+TAG=${SS_TAG:-r2}
 
-echo "== gpu tests"; timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -15 | tee gpurun_out/pytest_gpu.log
-echo "== parity of level-set variant 1 on the GPU (same assertions as the seeded parity tests)"
-timeout 600 python - <<'PY' 2>&1 | tee gpurun_out/variant1_parity.log
+if has tests; then
+  echo "== gpu tests"; timeout 1200 python -m pytest tests -q -m gpu -x 2>&1 | tail -15 | tee gpurun_out/pytest_gpu_$TAG.log
+fi
+if has variant; then
+  echo "== parity of level-set variant 1 on the GPU (same assertions as the seeded parity tests)"
+  timeout 600 python - <<'PY' 2>&1 | tee gpurun_out/variant1_parity_$TAG.log
 import sys; sys.path.insert(0, "tests"); sys.path.insert(0, ".")
 import numpy as np, oracle, splashsurf_b200 as ss
 from splashsurf_b200 import synthetic as syn
@@ -27,19 +30,55 @@ for name, gen, kw in G.SEEDED:
     print(name, "ok" if ok else m, g.timings["levelset_launches"])
 print("variant 1:", "ALL BIT-EXACT" if not bad else f"{bad} MISMATCHES")
 PY
-for v in 0 1; do
-  echo "== bench, level-set variant $v"
-  timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --levelset-variant $v > gpurun_out/bench_variant$v.json 2> gpurun_out/bench_variant$v.err
-  tail -c 600 gpurun_out/bench_variant$v.json
-done
-echo "== post-processing entries"; timeout 300 python tools/bench_postprocess.py --particles 10000000 > gpurun_out/bench_postprocess.json 2>&1; tail -c 800 gpurun_out/bench_postprocess.json
-echo "== launch list (default bench command, 2 steps)"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_r2.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
-for v in 0 1; do
-  k=$([ $v = 0 ] && echo k_levelset || echo k_certify)
-  echo "== ncu --set full of $k (4 M particles)"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -o gpurun_out/prof_${k}_r2 -f \
-      python bench.py --particles 4000000 --steps 1 --warmup 1 --no-cpu-baseline --levelset-variant $v > gpurun_out/ncu_$k.log 2>&1
-done
-echo "== memcheck on a small case"; timeout 600 compute-sanitizer --tool memcheck python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/memcheck.log
+fi
+if has parity; then
+  for wl in cfg3 cfg4; do
+    echo "== full-size parity vs the reference wheel, $wl"
+    timeout 900 python tools/parity_full.py --workload $wl --out gpurun_out/parity_${wl}_1gpu.json 2> gpurun_out/parity_${wl}_1gpu.err | cut -c1-1500
+    tail -3 gpurun_out/parity_${wl}_1gpu.err
+  done
+fi
+if has bench; then
+  for v in ${SS_VARIANTS:-0 1}; do
+    echo "== bench, level-set variant $v"
+    extra=$([ $v = 0 ] && echo "" || echo "--no-cpu-baseline")
+    timeout 900 python bench.py --steps 5 --warmup 3 $extra --levelset-variant $v > gpurun_out/bench_variant${v}_$TAG.json 2> gpurun_out/bench_variant${v}_$TAG.err
+    python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/bench_variant${v}_$TAG.json"))
+    print({k: d.get(k) for k in ("value", "ms_per_step", "e2e", "stage_ms_last_step", "cpu_baseline", "cpu_stage_ms", "gpu_stage_ms_same_sample", "mesh")})
+    print(d["roofline"])
+except Exception as e:
+    print("bench failed:", e); print(open("gpurun_out/bench_variant${v}_$TAG.err").read()[-1500:])
+PY
+  done
+  echo "== bench cfg3"
+  timeout 600 python bench.py --workload cfg3 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_cfg3_$TAG.json 2> gpurun_out/bench_cfg3_$TAG.err; cut -c1-700 gpurun_out/bench_cfg3_$TAG.json
+fi
+if has ref; then
+  echo "== reference arm on the full workload"
+  timeout 1200 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference_$TAG.json 2> gpurun_out/bench_reference_$TAG.err; cut -c1-900 gpurun_out/bench_reference_$TAG.json
+fi
+if has launches; then
+  echo "== launch list (default bench command, 2 steps)"
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches_$TAG.csv \
+      python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench_$TAG.log 2>&1
+  wc -l gpurun_out/launches_$TAG.csv
+fi
+if has ncu; then
+  echo "== ncu --set full: k_levelset (both launches) + k_density on cfg3 (10 M particles)"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_levelset|k_density' -c 3 -o gpurun_out/prof_levelset_density_$TAG -f \
+      python bench.py --workload cfg3 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full_$TAG.log 2>&1
+  echo "== ncu --set full: k_certify (variant 1) on cfg3"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_certify' -c 1 -o gpurun_out/prof_certify_$TAG -f \
+      python bench.py --workload cfg3 --steps 1 --warmup 1 --no-cpu-baseline --levelset-variant 1 > gpurun_out/ncu_full_v1_$TAG.log 2>&1
+  ls -la gpurun_out/*.ncu-rep
+fi
+if has post; then
+  echo "== post-processing entries"; timeout 300 python tools/bench_postprocess.py --particles 10000000 > gpurun_out/bench_postprocess_$TAG.json 2>&1; tail -c 800 gpurun_out/bench_postprocess_$TAG.json
+fi
+if has memcheck; then
+  echo "== memcheck on a small case"; timeout 600 compute-sanitizer --tool memcheck python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/memcheck_$TAG.log
+fi
+echo "== session done"
