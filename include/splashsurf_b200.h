@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SS_ABI_VERSION 1
+#define SS_ABI_VERSION 2
 
 /* Error codes.  1..7 mirror ReconstructionError / GridConstructionError
  * (splashsurf_lib/src/lib.rs:289-314, uniform_grid.rs:147-169); the reference's panics on a non-positive
@@ -94,6 +94,7 @@ typedef struct ss_timings {
     uint64_t bricks_levelset;    /* non-empty bricks evaluated by the level-set kernel (CTAs launched) */
     uint64_t bricks_mc;          /* bricks swept by marching cubes (can hold surface) */
     uint64_t bricks_fixscan;     /* bricks swept for certified points next to outside points */
+    double levelset_cert_evals;  /* lower-bound evaluations (particle x grid point) of the certification pass (count_pairs, variant 2) */
 } ss_timings;
 
 typedef struct ss_context ss_context;   /* device + stream + reusable device buffers */

@@ -55,7 +55,8 @@ class _Timings(C.Structure):
                 ("binning", C.c_float), ("levelset", C.c_float), ("marching_cubes", C.c_float), ("stitching", C.c_float),
                 ("total_device", C.c_float), ("kernel_launches", C.c_uint64), ("levelset_launches", C.c_uint64),
                 ("levelset_fixup_points", C.c_uint64), ("levelset_pairs", C.c_double),
-                ("bricks_total", C.c_uint64), ("bricks_levelset", C.c_uint64), ("bricks_mc", C.c_uint64), ("bricks_fixscan", C.c_uint64)]
+                ("bricks_total", C.c_uint64), ("bricks_levelset", C.c_uint64), ("bricks_mc", C.c_uint64), ("bricks_fixscan", C.c_uint64),
+                ("levelset_cert_evals", C.c_double)]
 
 
 _LIB = None
@@ -134,7 +135,7 @@ def _bind(L):
     L.ss_surface_vertex_connectivity.argtypes = [vp, vp, vp, C.POINTER(u64)]
     L.ss_surface_from_mesh_f32.argtypes = [vp, vp, u64, vp, u64, C.POINTER(vp)]
     L.ss_surface_set_normals_f32.argtypes = [vp, vp]
-    if L.ss_abi_version() != 1:
+    if L.ss_abi_version() != 2:
         raise ImportError("libsplashsurf_b200.so ABI version mismatch")
     return L
 

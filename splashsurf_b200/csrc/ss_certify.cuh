@@ -165,3 +165,273 @@ __global__ void k_wstate_reduce(const uint8_t *__restrict__ wstate, uint32_t nbr
     need[b] = any_need;
     *reinterpret_cast<uint4 *>(wflag + (size_t)b * SS_LS_WARPS) = make_uint4(f[0], f[1], f[2], f[3]);
 }
+
+// ====================================================================================================================
+// Level-set variant 2: warp-per-brick certification, TMA-staged, packed FP32 (sm_100a).
+//
+// One WARP owns one 8x8x8-point brick from start to finish, so the kernel has no CTA barrier at all:
+//   1. lanes 0..nruns-1 each look up one candidate run ((X, Y) bin column, Z contiguous) and a shuffle scan lays the runs out
+//      back to back in the warp's private slice of shared memory;
+//   2. every lane that owns a non-empty run issues ONE bulk asynchronous copy (cp.async.bulk, TMA engine) for it; the copies
+//      complete on the warp's mbarrier -- no per-record loads, no register staging;
+//   3. level 1 (once per brick): lane = candidate; squared distances to the eight 4x4x4-point sub-boxes of the brick are built
+//      from per-axis half-brick distances, giving one byte per candidate: bit b = "within ring 0 (0.55 h) of sub-box b";
+//   4. level 2 (per sub-box): lane = TWO grid points (k, k+1) of the 4x4x4 box.  The ring-0 candidates (ballot over the mask
+//      bytes) are folded into both running lower bounds with packed arithmetic: d^2 = (dz, dz')^2 + (dx^2 + dy^2) as one
+//      FFMA2, the cubic bound g(d^2) as three FFMA2, clamp, and one FFMA2 for the volume-weighted sum -- 13 instructions per
+//      candidate for two points.  The sub-box is certified when all 64 sums exceed threshold * (1 + 1e-4); a ring-1 sweep
+//      (0.55 h .. 0.76 h, where g vanishes) follows only for the few boxes that are still short;
+//   5. certified sub-boxes store SS_MARKER, the others raise their per-box flag for the exact pass (k_levelset, SS_LS_FIX).
+// The +1 planes of tiles with 8 k + 1 points per axis (extension tasks) reuse the scalar one-point-per-lane sweep.
+// Soundness is that of variant 0/1: every term of the reference's sum is >= 0 and g <= W / sigma, so a certified point is
+// inside for the reference too; failing to certify only costs time.  Results are therefore identical by construction.
+#include "ss_sm100.cuh"
+
+#define SS_CW_WARPS 6                  // bricks in flight per CTA (6 x 7.5 KB of static shared memory)
+#define SS_CW_THREADS (SS_CW_WARPS * 32)
+#define SS_CW_CAP 448                  // candidates staged per brick (bulk fluid at h = 4 r: 216 for c = 0.5 r, 373 for c = 0.45 r)
+#define SS_CW_MAXRUNS 32               // candidate runs per brick: one per lane
+
+struct SsCwArgs {
+    const uint32_t *bin_start, *bin_end;
+    const float4 *rec;
+    const SsTile *tile_tab;
+    const int2 *brick_rng;
+    const uint4 *work_desc;            // per listed brick: (linear brick index, tile, bx | by << 10 | bz << 20, 0)
+    uint32_t n_work;
+    float *tiles;
+    uint8_t *wstate;                   // [batch][nb^3][16]
+    unsigned long long *evals;         // optional work counter: candidate evaluations of the certification (lane-level)
+    float g1, g2, g3;                  // cubic bound in d^2: g = G0 + g1 d2 + g2 d2^2 + g3 d2^3 (G_k / h^(2k), host-computed)
+    float r0sq, r1sq;                  // ring radii squared: (0.55 h)^2, (0.76 h)^2
+};
+
+struct __align__(16) SsCwSlice {
+    float4 rec[SS_CW_CAP];
+    uint8_t mask[SS_CW_CAP];
+    unsigned long long mbar;
+    unsigned long long pad_;
+};
+
+// squared distance of coordinate u to the interval [lo, hi]
+__device__ __forceinline__ float ss_axis_d2(float u, float lo, float hi) { const float d = fmaxf(fmaxf(lo - u, u - hi), 0.0f); return d * d; }
+
+
+// Folds the candidates flagged in `mword` (bit = index into wrec) into the two running lower bounds of a lane (points k, k + 1):
+//   d^2 = (dz, dz')^2 + (dx^2 + dy^2),  sum += max(g(d^2), 0) * V   with g = G0 + g1 d2 + g2 d2^2 + g3 d2^3 <= W / sigma.
+// Two candidates per iteration (independent accumulators); an odd tail re-reads the last record with zero volume.
+struct SsCwPoint { float gx, gy; ss_f2 ngz; float g1, g2, g3; };
+__device__ __forceinline__ void ss_cw_eval(const SsCwPoint &Q, const float4 r, const float vol, ss_f2 &sum) {
+    const float dx = r.x - Q.gx, dy = r.y - Q.gy;
+    const float t = fmaf(dx, dx, dy * dy);
+    const ss_f2 dz = ss_add2(ss_pack(r.z, r.z), Q.ngz);
+    const ss_f2 d2 = ss_fma2(dz, dz, ss_pack(t, t));
+    ss_f2 g = ss_fma2(d2, ss_pack(Q.g3, Q.g3), ss_pack(Q.g2, Q.g2));
+    g = ss_fma2(d2, g, ss_pack(Q.g1, Q.g1));
+    g = ss_fma2(d2, g, ss_pack(SS_G0, SS_G0));
+    float ga, gb;
+    ss_unpack(g, ga, gb);
+    sum = ss_fma2(ss_pack(fmaxf(ga, 0.0f), fmaxf(gb, 0.0f)), ss_pack(vol, vol), sum);
+}
+__device__ __forceinline__ void ss_cw_accumulate(const SsCwPoint &Q, const float4 *wrec, uint32_t mword, ss_f2 &sum0, ss_f2 &sum1) {
+    while (mword) {
+        const int b0 = __ffs(mword) - 1;
+        mword &= mword - 1;
+        const bool two = mword != 0u;
+        const int b1 = two ? __ffs(mword) - 1 : b0;
+        mword &= mword - 1;                                     // no-op when mword is already 0
+        const float4 ra = wrec[b0], rb = wrec[b1];
+        ss_cw_eval(Q, ra, ra.w, sum0);
+        ss_cw_eval(Q, rb, two ? rb.w : 0.0f, sum1);
+    }
+}
+
+template <bool GLOBAL, bool COUNT>
+__global__ void __launch_bounds__(SS_CW_THREADS, 4)
+k_certify_warp(SsDev P, SsCwArgs A) {
+    __shared__ SsCwSlice s_slice[SS_CW_WARPS];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    SsCwSlice &S = s_slice[wib];
+    const uint32_t work = blockIdx.x * SS_CW_WARPS + wib;
+    if (work >= A.n_work) return;
+    if (lane == 0) { ss_mbar_init(&S.mbar, 1); ss_mbar_fence_init(); }
+    const int nb = P.nb;
+    const uint4 desc = A.work_desc[work];
+    const int tile_idx = (int)desc.y;
+    const int bx = (int)(desc.z & 1023u), by = (int)((desc.z >> 10) & 1023u), bz = (int)(desc.z >> 20);
+    const bool ext = P.ext_bricks != 0;
+    const bool ex = ext && bx == nb - 2, ey = ext && by == nb - 2, ez = ext && bz == nb - 2;
+    const SsTile T = A.tile_tab[tile_idx];
+    const bool sparse = GLOBAL || T.sparse != 0;
+    uint8_t *const wst = A.wstate + (size_t)desc.x * SS_LS_WARPS;
+
+    // ---- candidate runs: one per lane, exclusive prefix by shuffles
+    int2 rx = A.brick_rng[bx], ry = A.brick_rng[by], rz = A.brick_rng[bz];
+    if (ex) rx.y = A.brick_rng[bx + 1].y;
+    if (ey) ry.y = A.brick_rng[by + 1].y;
+    if (ez) rz.y = A.brick_rng[bz + 1].y;
+    const int nyr = ry.y - ry.x + 1;
+    const int nruns = (rx.y - rx.x + 1) * nyr;                  // host guarantees <= SS_CW_MAXRUNS for this variant
+    uint32_t run_a = 0, run_len = 0;
+    if (lane < nruns) {
+        const int X = rx.x + lane / nyr, Y = ry.x + lane % nyr;
+        uint32_t a = 0xffffffffu, b = 0;
+        const uint32_t base = T.s * (uint32_t)P.nbin_sub + (uint32_t)((X * P.nbin + Y) * P.nbin);
+        for (int Z = rz.x; Z <= rz.y; ++Z) {
+            const uint32_t st = A.bin_start[base + Z];
+            if (st != 0xffffffffu) { if (a == 0xffffffffu) a = st; b = A.bin_end[base + Z]; }
+        }
+        if (a != 0xffffffffu) { run_a = a; run_len = b - a; }
+    }
+    uint32_t incl = run_len;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
+    const uint32_t run_dst = incl - run_len;
+    const int C = (int)__shfl_sync(0xffffffffu, incl, 31);
+    if (C == 0) return;                                         // tile is pre-zeroed: phi = 0 exactly (wstate stays 0)
+
+    if (C > SS_CW_CAP) {
+        // oversized brick: everything goes to the exact pass (k_levelset's oversized path honours the per-box flags)
+        if (lane < SS_LS_WARPS) {
+            const int i0 = bx * 8 + (lane >> 2) * 2, j0 = by * 8 + ((lane >> 1) & 1) * 4, k0 = bz * 8 + (lane & 1) * 4;
+            if (i0 < P.np && j0 < P.np && k0 < P.np) wst[lane] = 2;
+        }
+        if (ex || ey || ez) {
+            for (int t = 0; t < 10; ++t) {
+                SsWarpBox We; int vbx, vby, vbz;
+                if (!ss_ext_task(t, bx, by, bz, ex, ey, ez, We, vbx, vby, vbz)) continue;
+                if (lane == 0 && We.i0 < P.np && We.j0 < P.np && We.k0 < P.np) ss_mark_boxes(P, A.wstate, tile_idx, vbx, vby, vbz, We, 2);
+            }
+        }
+        return;
+    }
+
+    // ---- stage the runs: bulk asynchronous copies (TMA engine) completing on the warp's mbarrier
+    __syncwarp();                                               // barrier initialised before anyone arrives / copies
+    if (lane == 0) ss_mbar_arrive_expect_tx(&S.mbar, (uint32_t)C * 16u);
+    __syncwarp();
+    if (run_len) ss_bulk_g2s(&S.rec[run_dst], A.rec + run_a, run_len * 16u, &S.mbar);
+    __syncwarp();
+    ss_mbar_wait(&S.mbar, 0);
+
+    // ---- level 1: per candidate, ring-0 membership for the eight sub-boxes (bit b = a * 4 + bb * 2 + cc: upper half in x, y, z)
+    const int nwords = (C + 31) >> 5;
+    const int pmax = P.np - 1;
+    // world coordinates of the half-brick point intervals [lo, hi] per axis (culling only; same expression as ss_lane_point's box)
+    float xl0, xl1, xh0, xh1, yl0, yl1, yh0, yh1, zl0, zl1, zh0, zh1;
+    {
+        const int ox = bx * 8, oy = by * 8, oz = bz * 8;
+        xl0 = fmaf((float)(T.gbase[0] + min(ox, pmax)), P.c, P.gmin[0]);     xh0 = fmaf((float)(T.gbase[0] + min(ox + 3, pmax)), P.c, P.gmin[0]);
+        xl1 = fmaf((float)(T.gbase[0] + min(ox + 4, pmax)), P.c, P.gmin[0]); xh1 = fmaf((float)(T.gbase[0] + min(ox + 7, pmax)), P.c, P.gmin[0]);
+        yl0 = fmaf((float)(T.gbase[1] + min(oy, pmax)), P.c, P.gmin[1]);     yh0 = fmaf((float)(T.gbase[1] + min(oy + 3, pmax)), P.c, P.gmin[1]);
+        yl1 = fmaf((float)(T.gbase[1] + min(oy + 4, pmax)), P.c, P.gmin[1]); yh1 = fmaf((float)(T.gbase[1] + min(oy + 7, pmax)), P.c, P.gmin[1]);
+        zl0 = fmaf((float)(T.gbase[2] + min(oz, pmax)), P.c, P.gmin[2]);     zh0 = fmaf((float)(T.gbase[2] + min(oz + 3, pmax)), P.c, P.gmin[2]);
+        zl1 = fmaf((float)(T.gbase[2] + min(oz + 4, pmax)), P.c, P.gmin[2]); zh1 = fmaf((float)(T.gbase[2] + min(oz + 7, pmax)), P.c, P.gmin[2]);
+    }
+    for (int w = 0; w < nwords; ++w) {
+        const int c = w * 32 + lane;
+        if (c < C) {
+            float4 r = S.rec[c];
+            if (GLOBAL) { int im[3]; float d0[3]; if (!ss_global_candidate(P, r, im, d0)) { r.w = 0.0f; S.rec[c].w = 0.0f; } }   // skipped particle: no volume
+            const float ax0 = ss_axis_d2(r.x, xl0, xh0), ax1 = ss_axis_d2(r.x, xl1, xh1);
+            const float ay0 = ss_axis_d2(r.y, yl0, yh0), ay1 = ss_axis_d2(r.y, yl1, yh1);
+            const float az0 = ss_axis_d2(r.z, zl0, zh0), az1 = ss_axis_d2(r.z, zl1, zh1);
+            const float xy00 = ax0 + ay0, xy01 = ax0 + ay1, xy10 = ax1 + ay0, xy11 = ax1 + ay1;
+            uint32_t m = 0;
+            m |= (xy00 + az0 < A.r0sq) ? 1u : 0u;   m |= (xy00 + az1 < A.r0sq) ? 2u : 0u;
+            m |= (xy01 + az0 < A.r0sq) ? 4u : 0u;   m |= (xy01 + az1 < A.r0sq) ? 8u : 0u;
+            m |= (xy10 + az0 < A.r0sq) ? 16u : 0u;  m |= (xy10 + az1 < A.r0sq) ? 32u : 0u;
+            m |= (xy11 + az0 < A.r0sq) ? 64u : 0u;  m |= (xy11 + az1 < A.r0sq) ? 128u : 0u;
+            S.mask[c] = (uint8_t)m;
+        }
+    }
+    __syncwarp();
+
+    // ---- level 2: the eight 4x4x4 sub-boxes; lane = points (i, j, k) and (i, j, k + 1)
+    const float cert = (P.thr + fabsf(P.thr) * 1.0e-4f + 1.0e-30f) / P.a_sigma;     // compare the un-normalised sum
+    const float cull2 = (GLOBAL ? P.rev2 : (sparse ? P.h2m : P.h2)) * 1.0001f;
+    const int li = lane >> 3, lj = (lane >> 1) & 3, lk = (lane & 1) * 2;
+    unsigned long long n_eval = 0;
+    for (int b = 0; b < 8; ++b) {
+        const int ha = (b >> 2) & 1, hb = (b >> 1) & 1, hc = b & 1;
+        const int i0 = bx * 8 + 4 * ha, j0 = by * 8 + 4 * hb, k0 = bz * 8 + 4 * hc;
+        if (i0 > pmax || j0 > pmax || k0 > pmax) continue;                           // sub-box outside the tile (warp-uniform)
+        const int i = i0 + li, j = j0 + lj, k = k0 + lk;
+        const bool row_ok = i <= pmax && j <= pmax;
+        const bool vA = row_ok && k <= pmax, vB = row_ok && k + 1 <= pmax;
+        // grid point coordinates from GLOBAL indices, the reference's expressions (ss_lane_point)
+        const float gx = __fadd_rn(__fmul_rn((float)(T.gbase[0] + i), P.c), P.gmin[0]);
+        const float gy = __fadd_rn(__fmul_rn((float)(T.gbase[1] + j), P.c), P.gmin[1]);
+        const float fkA = (float)(T.gbase[2] + k), fkB = (float)(T.gbase[2] + k + 1);
+        const float gzA = sparse ? __fadd_rn(P.gmin[2], __fmul_rn(fkA, P.c)) : __fmaf_rn(fkA, P.c, P.gmin[2]);
+        const float gzB = sparse ? __fadd_rn(P.gmin[2], __fmul_rn(fkB, P.c)) : __fmaf_rn(fkB, P.c, P.gmin[2]);
+        SsCwPoint Q;
+        Q.gx = gx; Q.gy = gy; Q.ngz = ss_pack(-gzA, -gzB); Q.g1 = A.g1; Q.g2 = A.g2; Q.g3 = A.g3;
+        ss_f2 sum0 = ss_pack(0.0f, 0.0f), sum1 = ss_pack(0.0f, 0.0f);
+        bool done = false;
+        uint32_t any_r0 = 0;
+        // ring 0: candidates flagged for this sub-box, closest bins first is not needed: a 64-point box uses nearly all of them
+        for (int w = 0; w < nwords && !done; ++w) {
+            const int c = w * 32 + lane;
+            const uint32_t mbit = (c < C) ? ((uint32_t)S.mask[c] >> b) & 1u : 0u;
+            uint32_t mword = __ballot_sync(0xffffffffu, mbit != 0u);
+            if (!mword) continue;
+            any_r0 = 1;
+            if (COUNT) n_eval += 2ull * (unsigned)__popc(mword);
+            ss_cw_accumulate(Q, S.rec + w * 32, mword, sum0, sum1);
+            float sa, sb;
+            ss_unpack(ss_add2(sum0, sum1), sa, sb);
+            done = __all_sync(0xffffffffu, (!vA || sa > cert) && (!vB || sb > cert));
+        }
+        uint32_t any_sup = any_r0;
+        if (!done) {
+            // ring 1: the remaining candidates the bound can see (g vanishes at 0.755 h), tested against this sub-box directly
+            const float bxl = ha ? xl1 : xl0, bxh = ha ? xh1 : xh0, byl = hb ? yl1 : yl0, byh = hb ? yh1 : yh0, bzl = hc ? zl1 : zl0, bzh = hc ? zh1 : zh0;
+            for (int w = 0; w < nwords && !done; ++w) {
+                const int c = w * 32 + lane;
+                bool keep = false, sup = false;
+                if (c < C) {
+                    const float4 r = S.rec[c];
+                    const float db2 = ss_axis_d2(r.x, bxl, bxh) + ss_axis_d2(r.y, byl, byh) + ss_axis_d2(r.z, bzl, bzh);
+                    sup = db2 < cull2;
+                    keep = (db2 < A.r1sq) && (((uint32_t)S.mask[c] >> b) & 1u) == 0u;
+                }
+                any_sup |= __ballot_sync(0xffffffffu, sup);
+                uint32_t mword = __ballot_sync(0xffffffffu, keep);
+                if (!mword) continue;
+                if (COUNT) n_eval += 2ull * (unsigned)__popc(mword);
+                ss_cw_accumulate(Q, S.rec + w * 32, mword, sum0, sum1);
+                float sa, sb;
+                ss_unpack(ss_add2(sum0, sum1), sa, sb);
+                done = __all_sync(0xffffffffu, (!vA || sa > cert) && (!vB || sb > cert));
+            }
+        }
+        if (done) {
+            float *out = A.tiles + (size_t)tile_idx * P.np * P.np * P.np + ((size_t)i * P.np + j) * P.np + k;
+            if (vA) out[0] = SS_MARKER;
+            if (vB) out[1] = SS_MARKER;
+        }
+        // per-box state of the two standard 2x4x4 boxes this sub-box covers: 1 markers, 2 needs exact values, 3 exact zeros in place
+        if (lane < 2) {
+            const int is = i0 + 2 * lane;                      // first plane of the standard box
+            if (is <= pmax) wst[(2 * ha + lane) * 4 + hb * 2 + hc] = done ? 1 : (any_sup ? 2 : 3);
+        }
+    }
+
+    // ---- extension tasks (planes at index np - 1): scalar one-point-per-lane sweep over the staged candidates
+    if (ex || ey || ez) {
+        for (int t = 0; t < 10; ++t) {
+            SsWarpBox We; int vbx, vby, vbz;
+            if (!ss_ext_task(t, bx, by, bz, ex, ey, ez, We, vbx, vby, vbz)) continue;
+            const SsLanePoint L = ss_lane_point(P, T, We, tile_idx, lane, sparse);
+            if (!L.warp_valid) continue;
+            const bool ok = ss_certify_box(P, L, S.rec, C, lane, 0);
+            if (ok && L.valid) A.tiles[L.out_idx] = SS_MARKER;
+            const uint8_t st = ok ? 1 : (ss_box_has_candidate<GLOBAL>(P, L, sparse, S.rec, C, lane) ? 2 : 3);
+            if (lane == 0) ss_mark_boxes(P, A.wstate, tile_idx, vbx, vby, vbz, We, st);
+        }
+    }
+    if (COUNT && A.evals) {
+        for (int o = 16; o > 0; o >>= 1) n_eval += __shfl_xor_sync(0xffffffffu, n_eval, o);
+        if (lane == 0 && n_eval) atomicAdd(A.evals, n_eval);
+    }
+}

@@ -220,21 +220,35 @@ __global__ void k_gather_pos(const float *__restrict__ xyz, const uint32_t *__re
 // FILL = false: densities (+ optional neighbour counts); FILL = true: writes the neighbour indices (global particle ids, in
 // the reference's order) into the CSR array prepared from those counts (Parameters::global_neighborhood_list,
 // dense_subdomains.rs:617-639).
+// Membership entries whose particle lies inside its subdomain's half-open AABB (aabb.rs:220-222): only those get a density.
+// Roughly half of the entries are ghosts, so k_density runs over the compacted list of the others (full warps).
+__global__ void k_density_flags(SsDev P, uint32_t m, const uint32_t *__restrict__ key, const float4 *__restrict__ spos,
+                                const uint32_t *__restrict__ sub_flat, uint32_t *__restrict__ flag) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= m) return;
+    const uint32_t s = key[e] / (uint32_t)P.ns_stride;
+    const float4 pi = spos[e];
+    const SsSubGeom g = ss_sub_geom(P, sub_flat[s]);
+    const bool inside = (pi.x >= g.smin[0] && pi.y >= g.smin[1] && pi.z >= g.smin[2]) &&
+                        (pi.x < g.smax[0] && pi.y < g.smax[1] && pi.z < g.smax[2]);
+    flag[e] = inside ? 1u : 0u;
+}
+
 template <bool FILL>
 __global__ void __launch_bounds__(128)
-k_density(SsDev P, uint32_t m, const uint32_t *__restrict__ key, const float4 *__restrict__ spos,
+k_density(SsDev P, uint32_t m, const uint32_t *__restrict__ list, const uint32_t *__restrict__ list_off, const uint32_t *__restrict__ list_flag,
+          const uint32_t *__restrict__ key, const float4 *__restrict__ spos,
           const uint32_t *__restrict__ sub_flat, const uint32_t *__restrict__ cstart, const uint32_t *__restrict__ cend,
           float *__restrict__ rho, unsigned long long *__restrict__ nbr_count, const unsigned long long *__restrict__ nbr_off,
           uint32_t *__restrict__ nbr_idx) {
-    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= m) return;
+    // `list` holds the entries with a particle inside its subdomain (ascending); its length is list_off[m-1] + list_flag[m-1]
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= list_off[m - 1] + list_flag[m - 1]) return;
+    const uint32_t e = list[tid];
     uint32_t k = key[e];
     uint32_t s = k / (uint32_t)P.ns_stride, cell = k - s * (uint32_t)P.ns_stride;
     float4 pi = spos[e];
     SsSubGeom g = ss_sub_geom(P, sub_flat[s]);
-    bool inside = (pi.x >= g.smin[0] && pi.y >= g.smin[1] && pi.z >= g.smin[2]) &&
-                  (pi.x < g.smax[0] && pi.y < g.smax[1] && pi.z < g.smax[2]);       // aabb.rs:220-222
-    if (!inside) return;
     SsNsGrid ns = ss_ns_grid(P, g);
     int c0 = (int)cell / (P.nsD * P.nsD), c1 = ((int)cell / P.nsD) % P.nsD, c2 = (int)cell % P.nsD;
     // Phase 1 collects the squared distances of the neighbours (d^2 < h^2) in visiting order, phase 2 evaluates the kernel

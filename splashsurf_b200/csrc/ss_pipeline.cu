@@ -91,7 +91,7 @@ struct ss_context {
     // reusable scratch
     DevBuf xyz, xyz_f, filt_flag, filt_flag32, filt_off, aabb, cnt, off, key_a, key_b, val_a, val_b, cid, cub_tmp,
         sub_flat, sub_off, sub_sparse, sub_owned, gkey_a, gkey_b, gval_a, gval_b, flags, scan, spos, rho, tab_a, tab_b, rec, ksplit, batch_subs, tiles, vcnt,
-        tcnt, vmask, voff, vblk_off, tblk_off, tile_tab, brick_rng, bstate, flag_ls, off_ls, list_ls, flag_mc, flag_fix, off_mc, off_fix, list_mc, list_fix, wflag, wstate, desc_ls, brick_seen, fix_list, nflag, bkeys_a, bkeys_b, bids_a, bids_b, bcount, remap, keep, newid, err, pairs;
+        tcnt, vmask, voff, vblk_off, tblk_off, tile_tab, brick_rng, bstate, flag_ls, off_ls, list_ls, flag_mc, flag_fix, off_mc, off_fix, list_mc, list_fix, wflag, wstate, desc_ls, dflag, doff, dlist, brick_seen, fix_list, nflag, bkeys_a, bkeys_b, bids_a, bids_b, bcount, remap, keep, newid, err, pairs;
     uint64_t launches = 0;
     // result buffers handed to surfaces and returned by ss_surface_free (avoids cudaMalloc/cudaFree per frame,
     // the analogue of the reference's ReconstructionWorkspace, workspace.rs:12-79)
@@ -242,7 +242,7 @@ extern "C" void ss_context_destroy(ss_context *c) {
     DevBuf *bufs[] = { &c->xyz, &c->xyz_f, &c->filt_flag, &c->filt_flag32, &c->filt_off, &c->aabb, &c->cnt, &c->off, &c->key_a, &c->key_b,
                        &c->val_a, &c->val_b, &c->cid, &c->cub_tmp, &c->sub_flat, &c->sub_off, &c->sub_sparse, &c->sub_owned, &c->gkey_a, &c->gkey_b, &c->gval_a, &c->gval_b, &c->flags, &c->scan,
                        &c->spos, &c->rho, &c->tab_a, &c->tab_b, &c->rec, &c->ksplit, &c->batch_subs, &c->tiles, &c->vcnt, &c->tcnt,
-                       &c->vmask, &c->voff, &c->vblk_off, &c->tblk_off, &c->tile_tab, &c->brick_rng, &c->bstate, &c->flag_ls, &c->off_ls, &c->list_ls, &c->flag_mc, &c->flag_fix, &c->off_mc, &c->off_fix, &c->list_mc, &c->list_fix, &c->wflag, &c->wstate, &c->desc_ls, &c->brick_seen, &c->fix_list, &c->nflag, &c->bkeys_a, &c->bkeys_b, &c->bids_a, &c->bids_b, &c->bcount, &c->remap, &c->keep, &c->newid,
+                       &c->vmask, &c->voff, &c->vblk_off, &c->tblk_off, &c->tile_tab, &c->brick_rng, &c->bstate, &c->flag_ls, &c->off_ls, &c->list_ls, &c->flag_mc, &c->flag_fix, &c->off_mc, &c->off_fix, &c->list_mc, &c->list_fix, &c->wflag, &c->wstate, &c->desc_ls, &c->dflag, &c->doff, &c->dlist, &c->brick_seen, &c->fix_list, &c->nflag, &c->bkeys_a, &c->bkeys_b, &c->bids_a, &c->bids_b, &c->bcount, &c->remap, &c->keep, &c->newid,
                        &c->err, &c->pairs, &c->o_verts, &c->o_tris, &c->o_vkeys, &c->o_rho, &c->o_verts2, &c->o_vkeys2, &c->o_normals };
     for (DevBuf *b : bufs) b->release();
     c->post.release_all();
@@ -255,7 +255,7 @@ extern "C" int ss_context_keep_levelset_tile(ss_context *c, int64_t flat) { if (
 extern "C" int ss_context_set_tile_batch(ss_context *c, uint32_t m) { if (!c) return SS_ERR_INVALID_PARAMETER; c->max_tiles = m; return SS_OK; }
 extern "C" int ss_context_set_levelset_exact_everywhere(ss_context *c, int on) { if (!c) return SS_ERR_INVALID_PARAMETER; c->ls_exact_all = on ? 1 : 0; return SS_OK; }
 extern "C" int ss_context_set_levelset_variant(ss_context *c, int v) {
-    if (!c || v < 0 || v > 1) return ss_fail(SS_ERR_INVALID_PARAMETER, "level-set variant must be 0 or 1");
+    if (!c || v < 0 || v > 2) return ss_fail(SS_ERR_INVALID_PARAMETER, "level-set variant must be 0, 1 or 2");
     c->ls_variant = v; return SS_OK;
 }
 extern "C" int ss_context_set_compute_sph_normals(ss_context *c, int on) { if (!c) return SS_ERR_INVALID_PARAMETER; c->sph_normals = on ? 1 : 0; return SS_OK; }
@@ -464,12 +464,19 @@ static int stage_densities(ss_context *c, const SsDev &D, const float *d_xyz, ui
     LAUNCH(c, k_gather_pos, nblk(M, 256), 256, d_xyz, c->val_a.as<uint32_t>(), M, c->spos.as<float4>());
     unsigned long long *d_ncnt = nullptr;
     if (want_nbrs) { out->nbr_off.ensure((n + 1) * 8); d_ncnt = out->nbr_off.as<unsigned long long>(); CK(cudaMemsetAsync(d_ncnt, 0, (n + 1) * 8, st)); }
-    LAUNCH(c, k_density<false>, nblk(M, 128), 128, D, M, c->key_b.as<uint32_t>(), c->spos.as<float4>(), c->sub_flat.as<uint32_t>(),
+    // entries with the particle inside the subdomain (every particle is inside at most one: <= n of them), compacted
+    c->dflag.ensure((size_t)M * 4); c->doff.ensure((size_t)M * 4 + 4); c->dlist.ensure(std::max<uint64_t>(n, 1) * 4);
+    LAUNCH(c, k_density_flags, nblk(M, 256), 256, D, M, c->key_b.as<uint32_t>(), c->spos.as<float4>(), c->sub_flat.as<uint32_t>(), c->dflag.as<uint32_t>());
+    cub_excl_scan(c, c->dflag.as<uint32_t>(), c->doff.as<uint32_t>(), M);
+    LAUNCH(c, k_compact_list, nblk(M, 256), 256, c->dflag.as<uint32_t>(), c->doff.as<uint32_t>(), M, c->dlist.as<uint32_t>());
+    LAUNCH(c, k_density<false>, nblk(n, 128), 128, D, M, c->dlist.as<uint32_t>(), c->doff.as<uint32_t>(), c->dflag.as<uint32_t>(),
+           c->key_b.as<uint32_t>(), c->spos.as<float4>(), c->sub_flat.as<uint32_t>(),
            c->tab_a.as<uint32_t>(), c->tab_b.as<uint32_t>(), d_rho, d_ncnt, (const unsigned long long *)nullptr, (uint32_t *)nullptr);
     if (want_nbrs) {
         const uint64_t total = scan_neighbor_counts(c, d_ncnt, n);
         out->nbr_idx.ensure(std::max<uint64_t>(total, 1) * 4);
-        LAUNCH(c, k_density<true>, nblk(M, 128), 128, D, M, c->key_b.as<uint32_t>(), c->spos.as<float4>(), c->sub_flat.as<uint32_t>(),
+        LAUNCH(c, k_density<true>, nblk(n, 128), 128, D, M, c->dlist.as<uint32_t>(), c->doff.as<uint32_t>(), c->dflag.as<uint32_t>(),
+               c->key_b.as<uint32_t>(), c->spos.as<float4>(), c->sub_flat.as<uint32_t>(),
                c->tab_a.as<uint32_t>(), c->tab_b.as<uint32_t>(), d_rho, (unsigned long long *)nullptr, (const unsigned long long *)d_ncnt, out->nbr_idx.as<uint32_t>());
         out->has_neighbors = 1; out->n_neighbors = total;
     }
@@ -538,7 +545,7 @@ static int levelset_batch(ss_context *c, const SsDev &D, uint32_t nbatch, unsign
     A.wflag = nullptr; A.fix_bricks = nullptr; A.bstate = c->bstate.as<uint8_t>();
     const uint32_t n_work = build_worklist(c, D, nbatch);
     A.work_list = c->list_ls.as<uint32_t>();
-    const bool split_certify = c->ls_variant == 1 && !exact_all && certify_runs <= 32;
+    const bool split_certify = c->ls_variant >= 1 && !exact_all && certify_runs <= 32;
     if (n_work && !split_certify) { launch_levelset(c, dim3(n_work), D, A, c->count_pairs != 0, global_mode); ++ls_launches; }
     if (n_work && split_certify) {
         // variant 1 (ss_certify.cuh): certification kernel, then the exact pass over the boxes it could not certify
@@ -550,7 +557,19 @@ static int levelset_batch(ss_context *c, const SsDev &D, uint32_t nbatch, unsign
         SsCertArgs CA{};
         CA.bin_start = A.bin_start; CA.bin_end = A.bin_end; CA.rec = A.rec; CA.tile_tab = A.tile_tab; CA.brick_rng = A.brick_rng;
         CA.work_desc = c->desc_ls.as<uint4>(); CA.tiles = A.tiles; CA.wstate = c->wstate.as<uint8_t>();
-        if (global_mode) LAUNCH(c, k_certify<true>, n_work, SS_LS_THREADS, D, CA);
+        if (c->ls_variant == 2) {
+            // warp-per-brick certification: TMA-staged candidates, packed FP32 (ss_certify.cuh, variant 2)
+            SsCwArgs W{};
+            W.bin_start = A.bin_start; W.bin_end = A.bin_end; W.rec = A.rec; W.tile_tab = A.tile_tab; W.brick_rng = A.brick_rng;
+            W.work_desc = c->desc_ls.as<uint4>(); W.n_work = n_work; W.tiles = A.tiles; W.wstate = c->wstate.as<uint8_t>();
+            W.evals = c->count_pairs ? c->pairs.as<unsigned long long>() + 1 : nullptr;
+            const double ih2 = 1.0 / ((double)D.h * (double)D.h);
+            W.g1 = (float)((double)SS_G1 * ih2); W.g2 = (float)((double)SS_G2 * ih2 * ih2); W.g3 = (float)((double)SS_G3 * ih2 * ih2 * ih2);
+            W.r0sq = 0.3025f * D.h2; W.r1sq = 0.58f * D.h2;
+            const unsigned grid_cw = (n_work + SS_CW_WARPS - 1) / SS_CW_WARPS;
+            if (global_mode) { if (c->count_pairs) LAUNCH(c, (k_certify_warp<true, true>), grid_cw, SS_CW_THREADS, D, W); else LAUNCH(c, (k_certify_warp<true, false>), grid_cw, SS_CW_THREADS, D, W); }
+            else { if (c->count_pairs) LAUNCH(c, (k_certify_warp<false, true>), grid_cw, SS_CW_THREADS, D, W); else LAUNCH(c, (k_certify_warp<false, false>), grid_cw, SS_CW_THREADS, D, W); }
+        } else if (global_mode) LAUNCH(c, k_certify<true>, n_work, SS_LS_THREADS, D, CA);
         else LAUNCH(c, k_certify<false>, n_work, SS_LS_THREADS, D, CA);
         ++ls_launches;
         LAUNCH(c, k_wstate_reduce, nblk(nbr_c, 256), 256, c->wstate.as<uint8_t>(), nbr_c, c->bstate.as<uint8_t>(), c->flag_fix.as<uint32_t>(),
@@ -878,9 +897,9 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     c->tiles.ensure(max_tiles * np3 * 4); c->voff.ensure(max_tiles * np3 * 4); c->vmask.ensure(max_tiles * np3);
     c->vcnt.ensure(nblk_max * 4 + 4); c->tcnt.ensure(nblk_max * 4 + 4); c->vblk_off.ensure(nblk_max * 4 + 4); c->tblk_off.ensure(nblk_max * 4 + 4);
     c->tile_tab.ensure(max_tiles * sizeof(SsTile)); c->brick_rng.ensure((size_t)D.nb * sizeof(int2)); c->bstate.ensure(nblk_max);
-    c->bcount.ensure(4); c->pairs.ensure(8);
+    c->bcount.ensure(4); c->pairs.ensure(16);
     CK(cudaMemsetAsync(c->bcount.p, 0, 4, st));
-    CK(cudaMemsetAsync(c->pairs.p, 0, 8, st));
+    CK(cudaMemsetAsync(c->pairs.p, 0, 16, st));
     {   // candidate bin range of brick b along one axis: bins overlapping [8b - R, 8b + 7 + R)
         std::vector<int2> h_rng(D.nb);
         for (int bb = 0; bb < D.nb; ++bb) {
@@ -983,9 +1002,9 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     T.levelset = ls_ms; T.marching_cubes = mc_ms;
     CK(cudaEventElapsedTime(&ms, c->ev[7], c->ev[8])); T.stitching = ms;
     T.levelset_launches = ls_launches; T.levelset_fixup_points = fix_points;
-    unsigned long long h_pairs = 0;
-    CK(cudaMemcpy(&h_pairs, c->pairs.p, 8, cudaMemcpyDeviceToHost));
-    T.levelset_pairs = (double)h_pairs;
+    unsigned long long h_pairs[2] = { 0, 0 };
+    CK(cudaMemcpy(h_pairs, c->pairs.p, 16, cudaMemcpyDeviceToHost));
+    T.levelset_pairs = (double)h_pairs[0]; T.levelset_cert_evals = (double)h_pairs[1];
     return SS_OK;
 }
 

@@ -133,6 +133,13 @@ def test_emulated_split_certification_variant(emu, oracle_mod, name, gen, kw, op
     _check_bit_exact(emu, oracle_mod, gen(), kw, variant=1, **opts)
 
 
+@pytest.mark.parametrize("name,gen,kw,opts", [s for s in SEEDED if s[0] != "exact_everywhere"], ids=[s[0] for s in SEEDED if s[0] != "exact_everywhere"])
+def test_emulated_warp_per_brick_certification(emu, oracle_mod, name, gen, kw, opts):
+    """Level-set variant 2 (ss_certify.cuh: warp-per-brick certification, bulk-copy staging, packed FP32; the executor runs the
+    portable definitions of ss_sm100.cuh)."""
+    _check_bit_exact(emu, oracle_mod, gen(), kw, variant=2, **opts)
+
+
 def test_emulated_aabb_filter_and_edge_cases(emu, oracle_mod):
     p = _splash((10, 10, 10), 2, 0.025, 320)
     kw = dict(BASE, cube_size=0.6, aabb_min=[-0.05, -0.05, -0.05], aabb_max=[0.4, 1.2, 0.45])

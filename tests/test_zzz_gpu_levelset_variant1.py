@@ -19,14 +19,15 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("name,gen,kw", CASES, ids=[c[0] for c in CASES])
-def test_cuda_split_certification_bit_exact_vs_oracle(ss, oracle_mod, name, gen, kw):
+def test_cuda_split_certification_bit_exact_vs_oracle(ss, oracle_mod, name, gen, kw, variant):
     from splashsurf_b200 import synthetic as syn
     p = gen(syn)
     o = oracle_mod.reconstruct(p, **kw)
     ctx = ss.Context()
     try:
-        ctx.set_levelset_variant(1)
+        ctx.set_levelset_variant(variant)
         g = ss.reconstruct_surface(p, with_debug=True, context=ctx, **kw)
         assert g.timings["levelset_launches"] >= 2          # certification launch + exact pass (+ fix-up pass)
         g0 = None

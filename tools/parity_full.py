@@ -99,12 +99,18 @@ def keys_from_positions(v, gmin, cell):
     return pack(torch.cat([ijk, axis[:, None]], 1)), amb, rq.to(torch.int64)
 
 
-def match_reference_keys(rv, gv, gk, gmin, cell):
-    """Assign to every reference vertex the index of the CUDA vertex on the same grid edge.  Returns (assign, stats)."""
+def match_reference_keys(rv, rt, gv, gt, gk, gmin, cell):
+    """Assign to every reference vertex the index of the CUDA vertex on the same grid edge.  Returns (assign, stats).
+
+    Unambiguous vertices: by the key derived from the position.  Ambiguous vertices (within TOL_CELLS of a lattice point P):
+    candidates are the CUDA vertices on the six edges incident to P; the candidate that shares the most mesh neighbours with
+    the reference vertex wins (neighbours = unambiguous vertices of its triangles, already matched), ties by distance."""
     import torch
+    dev = rv.device
     kr, amb, P = keys_from_positions(rv, gmin, cell)
     sk, perm = torch.sort(gk)
     n = len(sk)
+    nvg = len(gv)
 
     def lookup(keys):
         pos = torch.searchsorted(sk, keys).clamp(max=max(n - 1, 0))
@@ -122,38 +128,59 @@ def match_reference_keys(rv, gv, gk, gmin, cell):
             for off in (0, -1):
                 pk = Pa.clone()
                 pk[:, ax] += off
-                c = lookup(pack(torch.cat([pk, torch.full((len(pk), 1), ax, dtype=torch.int64, device=pk.device)], 1)))
+                c = lookup(pack(torch.cat([pk, torch.full((len(pk), 1), ax, dtype=torch.int64, device=dev)], 1)))
                 d = (gv[c.clamp(min=0)].double() - rv[ia].double()).abs().max(1).values
-                d = torch.where(c >= 0, d, torch.full_like(d, float("inf")))
+                d = torch.where(c >= 0, d, torch.full_like(d, 1.0e3))
                 cands.append(c); dists.append(d)
-        cands, dists = torch.stack(cands, 1), torch.stack(dists, 1)
-        srt = torch.argsort(dists, dim=1)
-        cands, dists = cands.gather(1, srt), dists.gather(1, srt)
+        cands, dists = torch.stack(cands, 1), torch.stack(dists, 1)           # (nA, 6)
+        # -- shared-neighbour score
+        row_of = torch.full((len(rv),), -1, dtype=torch.int64, device=dev)
+        row_of[ia] = torch.arange(len(ia), device=dev)
+        tsel = rt[amb[rt].any(1)]                                              # reference triangles touching an ambiguous vertex
+        src = torch.cat([tsel[:, [0, 0, 1, 1, 2, 2]].reshape(-1)])
+        dst = torch.cat([tsel[:, [1, 2, 0, 2, 0, 1]].reshape(-1)])
+        keep = amb[src] & ~amb[dst] & (assign[dst] >= 0)
+        src_row, nb = row_of[src[keep]], assign[dst[keep]]                      # (E,), neighbours as CUDA vertex ids
+        is_cand = torch.zeros(nvg, dtype=torch.bool, device=dev)
+        is_cand[cands[cands >= 0]] = True
+        gsel = gt[is_cand[gt].any(1)]
+        gs = gsel[:, [0, 0, 1, 1, 2, 2]].reshape(-1)
+        gd = gsel[:, [1, 2, 0, 2, 0, 1]].reshape(-1)
+        gkeep = is_cand[gs]
+        gedges = torch.unique(gs[gkeep] * nvg + gd[gkeep])                      # sorted
+        score = torch.zeros(cands.shape, dtype=torch.int64, device=dev)
+        for kcol in range(6):
+            ck = cands[src_row, kcol]
+            q = ck.clamp(min=0) * nvg + nb
+            pos = torch.searchsorted(gedges, q).clamp(max=max(len(gedges) - 1, 0))
+            hit = (gedges[pos] == q) & (ck >= 0) if len(gedges) else torch.zeros_like(ck, dtype=torch.bool)
+            score[:, kcol].index_add_(0, src_row, hit.to(torch.int64))
+        rank = -score.double() * 1.0e6 + dists                                 # more shared neighbours first, then nearer
+        srt = torch.argsort(rank, dim=1)
+        cands, dists, score = cands.gather(1, srt), dists.gather(1, srt), score.gather(1, srt)
         assign[ia] = cands[:, 0]
-        # resolve double assignments (several vertices at one lattice point): smallest distance keeps its candidate, the
-        # others move on to their next-nearest free candidate
-        taken = torch.bincount(assign[assign >= 0], minlength=len(gk))
+        taken = torch.bincount(assign[assign >= 0], minlength=nvg)
         conflicted = ia[(assign[ia] >= 0) & (taken[assign[ia].clamp(min=0)] > 1)]
         stats["n_ambiguous_conflicts"] = int(len(conflicted))
-        if 0 < len(conflicted) <= 200000:
-            pos_in_ia = {int(a): j for j, a in enumerate(ia.tolist())}
-            a_cpu, c_cpu, d_cpu = assign.cpu().numpy(), cands.cpu().numpy(), dists.cpu().numpy()
+        if 0 < len(conflicted) <= 500000:
+            # the best-ranked claimant keeps a contested candidate, the others move on to their next free candidate
+            a_cpu, c_cpu, r_cpu = assign.cpu().numpy(), cands.cpu().numpy(), rank.gather(1, srt).cpu().numpy()
             conf = conflicted.cpu().numpy()
-            rows = [pos_in_ia[int(a)] for a in conf]
-            order = np.argsort([d_cpu[r, 0] for r in rows])
-            all_taken = np.zeros(len(gk), dtype=bool)
+            rows = row_of[conflicted].cpu().numpy()
+            order = np.argsort(r_cpu[rows, 0], kind="stable")
+            all_taken = np.zeros(nvg, dtype=bool)
             all_taken[a_cpu[a_cpu >= 0]] = True
             all_taken[a_cpu[conf]] = False
             for oi in order:
-                a, r = int(conf[oi]), rows[oi]
+                a, r = int(conf[oi]), int(rows[oi])
                 a_cpu[a] = -1
                 for c in c_cpu[r]:
                     if c >= 0 and not all_taken[c]:
                         a_cpu[a] = int(c); all_taken[c] = True; break
-            assign = torch.from_numpy(a_cpu).to(rv.device)
+            assign = torch.from_numpy(a_cpu).to(dev)
     stats["n_unmatched"] = int((assign < 0).sum())
     ok = assign >= 0
-    stats["bijective"] = bool(stats["n_unmatched"] == 0 and len(rv) == len(gv) and int(torch.bincount(assign[ok], minlength=len(gk)).max()) == 1)
+    stats["bijective"] = bool(stats["n_unmatched"] == 0 and len(rv) == len(gv) and int(torch.bincount(assign[ok], minlength=nvg).max()) == 1)
     return assign, stats
 
 
@@ -162,7 +189,7 @@ def compare(rv, rt, gv, gt, gk4, gmin, cell, S):
     import torch
     out = {"nv": [int(len(rv)), int(len(gv))], "nt": [int(len(rt)), int(len(gt))]}
     gk = pack(gk4)
-    assign, st = match_reference_keys(rv, gv, gk, gmin, cell)
+    assign, st = match_reference_keys(rv, rt, gv, gt, gk, gmin, cell)
     out.update(st)
     out["keys_equal"] = bool(st["bijective"])
     gvc, gtc, gkc = canonicalize(gv, gt, gk)
