@@ -75,6 +75,12 @@ if has ncu; then
       python bench.py --workload cfg3 --steps 1 --warmup 1 --no-cpu-baseline --levelset-variant 1 > gpurun_out/ncu_full_v1_$TAG.log 2>&1
   ls -la gpurun_out/*.ncu-rep
 fi
+if has ncu2; then
+  echo "== ncu --set full, level-set variant 2 on cfg3: k_density, k_certify_warp, k_levelset (exact pass, fix-up pass)"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_certify_warp|k_density|k_levelset' -c 4 -o gpurun_out/prof_variant2_$TAG -f \
+      python bench.py --workload cfg3 --steps 1 --warmup 1 --no-cpu-baseline --levelset-variant 2 > gpurun_out/ncu_full_v2_$TAG.log 2>&1
+  ls -la gpurun_out/prof_variant2_$TAG.ncu-rep
+fi
 if has post; then
   echo "== post-processing entries"; timeout 300 python tools/bench_postprocess.py --particles 10000000 > gpurun_out/bench_postprocess_$TAG.json 2>&1; tail -c 800 gpurun_out/bench_postprocess_$TAG.json
 fi
