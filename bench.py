@@ -229,7 +229,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--runner-protocol", default="two_call", choices=["two_call", "callback"],
                     help="multi-GPU only: how the global subdomain maximum reaches the library (see distributed.Runner)")
-    ap.add_argument("--levelset-variant", type=int, default=0, choices=[0, 1],
+    ap.add_argument("--levelset-variant", type=int, default=0, choices=[0, 1, 2],
                     help="0: fused certify + exact level-set kernel (default); 1: separate certification kernel (ss_certify.cuh)")
     args = ap.parse_args()
     if args.impl == "reference":
