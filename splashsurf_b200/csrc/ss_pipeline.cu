@@ -7,6 +7,7 @@
 #include "../../include/splashsurf_b200.h"
 #include "ss_kernels.cuh"
 #include "ss_certify.cuh"
+#include "ss_exact.cuh"
 
 #ifndef SS_HOST_EMUL               // (tests/emul/cuda_emul.h compiles this file with g++ to step the kernels on the CPU)
 #include <cub/cub.cuh>
@@ -91,7 +92,7 @@ struct ss_context {
     // reusable scratch
     DevBuf xyz, xyz_f, filt_flag, filt_flag32, filt_off, aabb, cnt, off, key_a, key_b, val_a, val_b, cid, cub_tmp,
         sub_flat, sub_off, sub_sparse, sub_owned, gkey_a, gkey_b, gval_a, gval_b, flags, scan, spos, rho, tab_a, tab_b, rec, ksplit, batch_subs, tiles, vcnt,
-        tcnt, vmask, voff, vblk_off, tblk_off, tile_tab, brick_rng, bstate, flag_ls, off_ls, list_ls, flag_mc, flag_fix, off_mc, off_fix, list_mc, list_fix, wflag, wstate, desc_ls, dflag, doff, dlist, brick_seen, fix_list, nflag, bkeys_a, bkeys_b, bids_a, bids_b, bcount, remap, keep, newid, err, pairs;
+        tcnt, vmask, voff, vblk_off, tblk_off, tile_tab, brick_rng, bstate, flag_ls, off_ls, list_ls, flag_mc, flag_fix, off_mc, off_fix, list_mc, list_fix, wflag, wstate, desc_ls, dflag, doff, dlist, fallback, brick_seen, fix_list, nflag, bkeys_a, bkeys_b, bids_a, bids_b, bcount, remap, keep, newid, err, pairs;
     uint64_t launches = 0;
     // result buffers handed to surfaces and returned by ss_surface_free (avoids cudaMalloc/cudaFree per frame,
     // the analogue of the reference's ReconstructionWorkspace, workspace.rs:12-79)
@@ -242,7 +243,7 @@ extern "C" void ss_context_destroy(ss_context *c) {
     DevBuf *bufs[] = { &c->xyz, &c->xyz_f, &c->filt_flag, &c->filt_flag32, &c->filt_off, &c->aabb, &c->cnt, &c->off, &c->key_a, &c->key_b,
                        &c->val_a, &c->val_b, &c->cid, &c->cub_tmp, &c->sub_flat, &c->sub_off, &c->sub_sparse, &c->sub_owned, &c->gkey_a, &c->gkey_b, &c->gval_a, &c->gval_b, &c->flags, &c->scan,
                        &c->spos, &c->rho, &c->tab_a, &c->tab_b, &c->rec, &c->ksplit, &c->batch_subs, &c->tiles, &c->vcnt, &c->tcnt,
-                       &c->vmask, &c->voff, &c->vblk_off, &c->tblk_off, &c->tile_tab, &c->brick_rng, &c->bstate, &c->flag_ls, &c->off_ls, &c->list_ls, &c->flag_mc, &c->flag_fix, &c->off_mc, &c->off_fix, &c->list_mc, &c->list_fix, &c->wflag, &c->wstate, &c->desc_ls, &c->dflag, &c->doff, &c->dlist, &c->brick_seen, &c->fix_list, &c->nflag, &c->bkeys_a, &c->bkeys_b, &c->bids_a, &c->bids_b, &c->bcount, &c->remap, &c->keep, &c->newid,
+                       &c->vmask, &c->voff, &c->vblk_off, &c->tblk_off, &c->tile_tab, &c->brick_rng, &c->bstate, &c->flag_ls, &c->off_ls, &c->list_ls, &c->flag_mc, &c->flag_fix, &c->off_mc, &c->off_fix, &c->list_mc, &c->list_fix, &c->wflag, &c->wstate, &c->desc_ls, &c->dflag, &c->doff, &c->dlist, &c->fallback, &c->brick_seen, &c->fix_list, &c->nflag, &c->bkeys_a, &c->bkeys_b, &c->bids_a, &c->bids_b, &c->bcount, &c->remap, &c->keep, &c->newid,
                        &c->err, &c->pairs, &c->o_verts, &c->o_tris, &c->o_vkeys, &c->o_rho, &c->o_verts2, &c->o_vkeys2, &c->o_normals };
     for (DevBuf *b : bufs) b->release();
     c->post.release_all();
@@ -530,6 +531,35 @@ static int stage_binning(ss_context *c, const SsDev &D, const float *d_xyz, cons
     return SS_OK;
 }
 
+
+// Exact values for the flagged boxes of `n_bricks` listed bricks.  Variant 2: warp-per-brick kernel (ss_exact.cuh), bricks it
+// cannot take come back in a fallback list and go through k_levelset (SS_LS_FIX) like in the other variants.
+static void launch_exact(ss_context *c, const SsDev &D, const SsLsArgs &F, uint32_t n_bricks, bool global_mode, uint64_t &ls_launches) {
+    if (!n_bricks) return;
+    const bool count = c->count_pairs != 0;
+    if (c->ls_variant != 2) { launch_levelset(c, dim3(n_bricks), D, F, count, global_mode); ++ls_launches; return; }
+    cudaStream_t st = c->stream;
+    c->fallback.ensure(((size_t)n_bricks + 1) * 4);
+    CK(cudaMemsetAsync(c->fallback.p, 0, 4, st));
+    SsXwArgs X{};
+    X.bin_start = F.bin_start; X.bin_end = F.bin_end; X.rec = F.rec; X.ksplit = F.ksplit; X.pidx = F.pidx; X.tile_tab = F.tile_tab;
+    X.brick_rng = F.brick_rng; X.bricks = F.fix_bricks; X.n_bricks = n_bricks; X.wflag = F.wflag; X.tiles = F.tiles;
+    X.fallback = c->fallback.as<uint32_t>(); X.pairs = F.pairs;
+    const unsigned grid = (n_bricks + SS_XW_WARPS - 1) / SS_XW_WARPS;
+    if (global_mode) { if (count) LAUNCH(c, (k_exact_warp<true, true>), grid, SS_XW_THREADS, D, X); else LAUNCH(c, (k_exact_warp<true, false>), grid, SS_XW_THREADS, D, X); }
+    else { if (count) LAUNCH(c, (k_exact_warp<false, true>), grid, SS_XW_THREADS, D, X); else LAUNCH(c, (k_exact_warp<false, false>), grid, SS_XW_THREADS, D, X); }
+    ++ls_launches;
+    uint32_t n_fb = 0;
+    CK(cudaMemcpyAsync(&n_fb, c->fallback.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (n_fb) {
+        SsLsArgs G = F;
+        G.fix_bricks = c->fallback.as<uint32_t>() + 1;
+        launch_levelset(c, dim3(n_fb), D, G, count, global_mode);
+        ++ls_launches;
+    }
+}
+
 // Level set of one batch of tiles: work list, certification + exact values (fused kernel, or variant 1: certification kernel +
 // exact pass), brick classification, fix-up sweep.  Leaves the tiles, the per-brick states and the marching-cubes brick list
 // (c->list_mc, *n_mc_out entries) in the context scratch.
@@ -583,8 +613,7 @@ static int levelset_batch(ss_context *c, const SsDev &D, uint32_t nbatch, unsign
         if (ln[0] + ln[1]) {
             SsLsArgs F = A;
             F.mode = SS_LS_FIX; F.wflag = c->wflag.as<uint8_t>(); F.fix_bricks = c->fix_list.as<uint32_t>();
-            launch_levelset(c, dim3(ln[0] + ln[1]), D, F, c->count_pairs != 0, global_mode);
-            ++ls_launches;
+            launch_exact(c, D, F, ln[0] + ln[1], global_mode, ls_launches);
         }
     }
     out->tm.bricks_levelset += n_work;
@@ -619,8 +648,8 @@ static int levelset_batch(ss_context *c, const SsDev &D, uint32_t nbatch, unsign
         CK(cudaStreamSynchronize(st));
         if (nfl[0]) {
             A.mode = SS_LS_FIX; A.wflag = c->wflag.as<uint8_t>(); A.fix_bricks = c->fix_list.as<uint32_t>();
-            launch_levelset(c, dim3(nfl[0]), D, A, c->count_pairs != 0, global_mode);
-            ++ls_launches;
+            if (split_certify) launch_exact(c, D, A, nfl[0], global_mode, ls_launches);
+            else { launch_levelset(c, dim3(nfl[0]), D, A, c->count_pairs != 0, global_mode); ++ls_launches; }
             fix_points += nfl[1];
         }
     }
@@ -889,9 +918,15 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     const size_t per_tile = np3 * (4 + 4 + 1) + (size_t)nbricks * (SS_LS_WARPS + 8 + 1 + 16) + 256;
     // as many tiles per batch as fit a third of the free memory (fewer host synchronisations per frame); the brick index
     // tile * nb^3 + ... must stay below 2^31
-    size_t max_tiles = c->max_tiles ? c->max_tiles : std::max<size_t>(1, (free_b / 3) / per_tile);
-    max_tiles = std::min<size_t>(max_tiles, std::max<size_t>(1, (size_t)0x7fffffff / nbricks / 2));
     const uint32_t nown = (uint32_t)owned_list.size();
+    // The tile buffers of the previous frame are reused whenever they hold all tiles or at least half of what a fresh
+    // allocation would get: the amount of free memory wobbles from frame to frame (result buffers in flight), and re-allocating
+    // tens of GB costs ~100 ms.
+    const size_t have_tiles = c->tiles.cap / (np3 * 4);
+    const size_t reusable = c->tiles.cap + c->voff.cap + c->vmask.cap;
+    size_t want_tiles = std::max<size_t>(1, ((free_b + reusable) / 3) / per_tile);
+    size_t max_tiles = c->max_tiles ? c->max_tiles : ((have_tiles >= nown || have_tiles >= want_tiles / 2) && have_tiles ? have_tiles : want_tiles);
+    max_tiles = std::min<size_t>(max_tiles, std::max<size_t>(1, (size_t)0x7fffffff / nbricks / 2));
     max_tiles = std::min<size_t>(max_tiles, std::max<uint32_t>(nown, 1));
     const size_t nblk_max = max_tiles * nbricks;
     c->tiles.ensure(max_tiles * np3 * 4); c->voff.ensure(max_tiles * np3 * 4); c->vmask.ensure(max_tiles * np3);

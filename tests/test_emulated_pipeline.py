@@ -140,6 +140,14 @@ def test_emulated_warp_per_brick_certification(emu, oracle_mod, name, gen, kw, o
     _check_bit_exact(emu, oracle_mod, gen(), kw, variant=2, **opts)
 
 
+@pytest.mark.parametrize("n,sigma", [(600, 0.004), (400, 0.02), (260, 0.01)], ids=["oversized_brick", "list_overflow", "dense_cluster"])
+def test_emulated_warp_per_brick_clustered_particles(emu, oracle_mod, n, sigma):
+    """Variant 2 on pathological clustering: more candidates than a warp's slice holds (whole brick falls back to k_levelset),
+    more candidates in the support of one sub-box than its list holds, and a dense cluster that still fits."""
+    kw = dict(BASE, cube_size=0.5, subdomain_grid_auto_disable=False)
+    _check_bit_exact(emu, oracle_mod, np.random.default_rng(n).normal(0, sigma, (n, 3)).astype(np.float32), kw, variant=2)
+
+
 def test_emulated_aabb_filter_and_edge_cases(emu, oracle_mod):
     p = _splash((10, 10, 10), 2, 0.025, 320)
     kw = dict(BASE, cube_size=0.6, aabb_min=[-0.05, -0.05, -0.05], aabb_max=[0.4, 1.2, 0.45])

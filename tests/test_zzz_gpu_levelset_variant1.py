@@ -41,3 +41,20 @@ def test_cuda_split_certification_bit_exact_vs_oracle(ss, oracle_mod, name, gen,
     assert m["keys_equal"] and m["triangles_equal"] and m["n_not_bitexact"] == 0, m
     # and the two variants agree with each other element for element (same kernels decide and evaluate)
     assert np.array_equal(g.mesh.vertices, g0.mesh.vertices) and np.array_equal(g.mesh.triangles, g0.mesh.triangles)
+
+
+@pytest.mark.parametrize("n,sigma", [(3000, 0.004), (400, 0.02), (260, 0.01)], ids=["oversized_brick", "list_overflow", "dense_cluster"])
+def test_cuda_warp_per_brick_clustered_particles(ss, oracle_mod, n, sigma):
+    """Variant 2 on pathological clustering (fallback of whole bricks to k_levelset, sub-box list overflow)."""
+    kw = dict(BASE, cube_size=0.5, subdomain_grid_auto_disable=False)
+    p = np.random.default_rng(n).normal(0, sigma, (n, 3)).astype(np.float32)
+    o = oracle_mod.reconstruct(p, **kw)
+    ctx = ss.Context()
+    try:
+        ctx.set_levelset_variant(2)
+        g = ss.reconstruct_surface(p, with_debug=True, context=ctx, **kw)
+    finally:
+        ctx.close()
+    assert np.array_equal(g.particle_densities, o["particle_densities"])
+    m = oracle_mod.mesh_parity(g.mesh.vertices, g.mesh.triangles, g.vertex_edge_keys, o["vertices"], o["triangles"], o["vertex_keys"], 64)
+    assert m["keys_equal"] and m["triangles_equal"] and m["n_not_bitexact"] == 0, m

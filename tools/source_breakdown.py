@@ -32,7 +32,9 @@ def function_map(rev, path):
 
 def main():
     rep, rev = sys.argv[1], sys.argv[2]
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
+    kern = ["--kernel-name", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else []     # optional: one kernel of a multi-kernel report
+    nth = ["--launch-skip", sys.argv[4], "--launch-count", "1"] if len(sys.argv) > 4 else []
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] + kern + nth,
                          capture_output=True, text=True, check=True).stdout
     maps = {}
     agg, smp, src = collections.Counter(), collections.Counter(), {}
@@ -46,7 +48,12 @@ def main():
         elif r and r[0] == "Line No":
             col = r.index("Instructions Executed"); col_s = r.index("# Samples")
         elif col is not None and r and r[0].isdigit():
-            agg[(cur, int(r[0]))] += int(r[col]); smp[(cur, int(r[0]))] += int(r[col_s]); src[(cur, int(r[0]))] = r[1]
+            def num(v):
+                try:
+                    return int(v)
+                except ValueError:
+                    return 0
+            agg[(cur, int(r[0]))] += num(r[col]); smp[(cur, int(r[0]))] += num(r[col_s]); src[(cur, int(r[0]))] = r[1]
     total = sum(agg.values())
     per_func, per_func_s = collections.Counter(), collections.Counter()
     total_s = max(sum(smp.values()), 1)
