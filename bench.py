@@ -8,7 +8,7 @@ the library's stream around every step); `e2e` runs the same call through the C 
 copied host->device and the mesh copied device->host inside the timed region.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--particles M] [--impl reference]
-                  [--workload cfg2|cfg3|cfg4|cfg5] [--levelset-variant 0|1] [--runner-protocol two_call|callback]
+                  [--workload cfg2|cfg3|cfg4|cfg5] [--levelset-variant 0|1|2] [--runner-protocol two_call|callback]
 
 (The defaults are the measured configuration: level-set variant 0, two-call runner protocol.  tests/test_bench_dry_run.py
 runs this file's main() on the CPU executor of the CUDA sources to check its control flow and the JSON contract.)
@@ -229,8 +229,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--runner-protocol", default="two_call", choices=["two_call", "callback"],
                     help="multi-GPU only: how the global subdomain maximum reaches the library (see distributed.Runner)")
-    ap.add_argument("--levelset-variant", type=int, default=0, choices=[0, 1, 2],
-                    help="0: fused certify + exact level-set kernel (default); 1: separate certification kernel (ss_certify.cuh)")
+    ap.add_argument("--levelset-variant", type=int, default=2, choices=[0, 1, 2],
+                    help="2 (default): warp-per-brick certification + exact kernels (TMA staging, packed FP32); 1: CTA-per-brick certification kernel; 0: fused k_levelset")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -255,8 +255,7 @@ def main():
     import splashsurf_b200 as ss
     from splashsurf_b200 import distributed as ssd
     ctx = ss.Context(local_rank)
-    if args.levelset_variant:
-        ctx.set_levelset_variant(args.levelset_variant)
+    ctx.set_levelset_variant(args.levelset_variant)
     kw = dict(RECON_KW)
     if WORKLOADS.get(args.workload):
         kw.update(WORKLOADS[args.workload][1])

@@ -200,8 +200,9 @@ int ss_surface_timings(const ss_surface *s, ss_timings *out);
  * - count_pairs: count in-support kernel evaluations into ss_timings.levelset_pairs (instrumented kernel). */
 int ss_context_set_tile_batch(ss_context *ctx, uint32_t max_tiles);
 int ss_context_set_levelset_exact_everywhere(ss_context *ctx, int on);
-/* Level-set launch structure: 0 (default) = fused certification + exact pass per brick (k_levelset); 1 = certification in its
- * own barrier-light kernel followed by an exact pass over the boxes it could not certify (ss_certify.cuh).  Same results. */
+/* Level-set launch structure (same results): 2 (default) = warp-per-brick certification kernel (bulk-copy staging, packed FP32)
+ * + warp-per-brick exact pass over the boxes it could not certify; 1 = CTA-per-brick certification kernel + k_levelset exact
+ * pass; 0 = fused certification + exact pass per brick (k_levelset). */
 int ss_context_set_levelset_variant(ss_context *ctx, int variant);
 int ss_context_set_count_pairs(ss_context *ctx, int on);
 

@@ -187,9 +187,9 @@ __global__ void k_wstate_reduce(const uint8_t *__restrict__ wstate, uint32_t nbr
 // inside for the reference too; failing to certify only costs time.  Results are therefore identical by construction.
 #include "ss_sm100.cuh"
 
-#define SS_CW_WARPS 6                  // bricks in flight per CTA (6 x 7.5 KB of static shared memory)
+#define SS_CW_WARPS 4                  // bricks in flight per CTA (4 x 9.8 KB of static shared memory)
 #define SS_CW_THREADS (SS_CW_WARPS * 32)
-#define SS_CW_CAP 448                  // candidates staged per brick (bulk fluid at h = 4 r: 216 for c = 0.5 r, 373 for c = 0.45 r)
+#define SS_CW_CAP 384                  // candidates staged per brick (bulk fluid at h = 4 r: 216 for c = 0.5 r, 373 for c = 0.45 r)
 #define SS_CW_MAXRUNS 32               // candidate runs per brick: one per lane
 
 struct SsCwArgs {
@@ -206,9 +206,13 @@ struct SsCwArgs {
     float r0sq, r1sq;                  // ring radii squared: (0.55 h)^2, (0.76 h)^2
 };
 
+#define SS_CW_PAIRS 24                 // capacity of one sub-box's ring-0 list in candidate PAIRS (bulk fluid: ~13); extra candidates are dropped (sound)
+// one list entry = two candidates, component-interleaved so that every packed operand is an aligned 64-bit register pair
+struct __align__(16) SsCwPair { float x[2], y[2], z[2], v[2]; };
 struct __align__(16) SsCwSlice {
-    float4 rec[SS_CW_CAP];
-    uint8_t mask[SS_CW_CAP];
+    float4 rec[SS_CW_CAP];             // staged candidate records (bulk-copy destination)
+    SsCwPair list[4][SS_CW_PAIRS];     // ring-0 lists of the four sub-boxes of one x-half of the brick
+    uint16_t cidx[SS_CW_CAP];          // candidates within ring 0 of the whole brick (pre-filter)
     unsigned long long mbar;
     unsigned long long pad_;
 };
@@ -246,8 +250,34 @@ __device__ __forceinline__ void ss_cw_accumulate(const SsCwPoint &Q, const float
     }
 }
 
+// Ring-0 fold over a pair list: lane = grid points (k, k + 1); each iteration folds TWO candidates into both points, every
+// operand a natural register pair (x, y, z, V of the two candidates):
+//   (dx, dx') = (x, x') - gx;  (dy, dy') likewise;  t = dx^2 + dy^2 (packed);  per point: d2 = dz^2 + t,  g(d2) by Horner,
+//   sum += max(g, 0) * (V, V')
+// 16 FMA-pipe + 4 ALU instructions per pair for two points.  sumA / sumB hold the two candidates' partial sums side by side.
+__device__ __forceinline__ void ss_cw_fold_pairs(const SsCwPoint &Q, float ngzA, float ngzB, const SsCwPair *list, int first, int last, ss_f2 &sumA, ss_f2 &sumB) {
+    const ss_f2 G0 = ss_pack(SS_G0, SS_G0), G1 = ss_pack(Q.g1, Q.g1), G2 = ss_pack(Q.g2, Q.g2), G3 = ss_pack(Q.g3, Q.g3);
+    const ss_f2 ngx = ss_pack(-Q.gx, -Q.gx), ngy = ss_pack(-Q.gy, -Q.gy), nza = ss_pack(ngzA, ngzA), nzb = ss_pack(ngzB, ngzB);
+#pragma unroll 2
+    for (int n = first; n < last; ++n) {
+        const SsCwPair &E = list[n];
+        const ss_f2 dx = ss_add2(ss_pack(E.x[0], E.x[1]), ngx), dy = ss_add2(ss_pack(E.y[0], E.y[1]), ngy);
+        const ss_f2 t = ss_fma2(dx, dx, ss_mul2(dy, dy));
+        const ss_f2 z = ss_pack(E.z[0], E.z[1]), v = ss_pack(E.v[0], E.v[1]);
+        const ss_f2 dza = ss_add2(z, nza), dzb = ss_add2(z, nzb);
+        const ss_f2 d2a = ss_fma2(dza, dza, t), d2b = ss_fma2(dzb, dzb, t);
+        ss_f2 ga = ss_fma2(d2a, G3, G2), gb = ss_fma2(d2b, G3, G2);
+        ga = ss_fma2(d2a, ga, G1); gb = ss_fma2(d2b, gb, G1);
+        ga = ss_fma2(d2a, ga, G0); gb = ss_fma2(d2b, gb, G0);
+        float a0, a1, b0, b1;
+        ss_unpack(ga, a0, a1); ss_unpack(gb, b0, b1);
+        sumA = ss_fma2(ss_pack(fmaxf(a0, 0.0f), fmaxf(a1, 0.0f)), v, sumA);
+        sumB = ss_fma2(ss_pack(fmaxf(b0, 0.0f), fmaxf(b1, 0.0f)), v, sumB);
+    }
+}
+
 template <bool GLOBAL, bool COUNT>
-__global__ void __launch_bounds__(SS_CW_THREADS, 4)
+__global__ void __launch_bounds__(SS_CW_THREADS, 5)
 k_certify_warp(SsDev P, SsCwArgs A) {
     __shared__ SsCwSlice s_slice[SS_CW_WARPS];
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -327,94 +357,131 @@ k_certify_warp(SsDev P, SsCwArgs A) {
         zl0 = fmaf((float)(T.gbase[2] + min(oz, pmax)), P.c, P.gmin[2]);     zh0 = fmaf((float)(T.gbase[2] + min(oz + 3, pmax)), P.c, P.gmin[2]);
         zl1 = fmaf((float)(T.gbase[2] + min(oz + 4, pmax)), P.c, P.gmin[2]); zh1 = fmaf((float)(T.gbase[2] + min(oz + 7, pmax)), P.c, P.gmin[2]);
     }
+    // ---- pre-filter: candidates within ring 0 of the whole brick, compacted (sub-box distances are never smaller)
+    int n0 = 0;
     for (int w = 0; w < nwords; ++w) {
         const int c = w * 32 + lane;
+        bool keep = false;
         if (c < C) {
-            float4 r = S.rec[c];
-            if (GLOBAL) { int im[3]; float d0[3]; if (!ss_global_candidate(P, r, im, d0)) { r.w = 0.0f; S.rec[c].w = 0.0f; } }   // skipped particle: no volume
-            const float ax0 = ss_axis_d2(r.x, xl0, xh0), ax1 = ss_axis_d2(r.x, xl1, xh1);
-            const float ay0 = ss_axis_d2(r.y, yl0, yh0), ay1 = ss_axis_d2(r.y, yl1, yh1);
-            const float az0 = ss_axis_d2(r.z, zl0, zh0), az1 = ss_axis_d2(r.z, zl1, zh1);
-            const float xy00 = ax0 + ay0, xy01 = ax0 + ay1, xy10 = ax1 + ay0, xy11 = ax1 + ay1;
-            uint32_t m = 0;
-            m |= (xy00 + az0 < A.r0sq) ? 1u : 0u;   m |= (xy00 + az1 < A.r0sq) ? 2u : 0u;
-            m |= (xy01 + az0 < A.r0sq) ? 4u : 0u;   m |= (xy01 + az1 < A.r0sq) ? 8u : 0u;
-            m |= (xy10 + az0 < A.r0sq) ? 16u : 0u;  m |= (xy10 + az1 < A.r0sq) ? 32u : 0u;
-            m |= (xy11 + az0 < A.r0sq) ? 64u : 0u;  m |= (xy11 + az1 < A.r0sq) ? 128u : 0u;
-            S.mask[c] = (uint8_t)m;
+            const float4 r = S.rec[c];
+            if (GLOBAL) { int im[3]; float d0[3]; if (!ss_global_candidate(P, r, im, d0)) S.rec[c].w = 0.0f; }   // skipped particle: no volume
+            keep = ss_axis_d2(r.x, xl0, xh1) + ss_axis_d2(r.y, yl0, yh1) + ss_axis_d2(r.z, zl0, zh1) < A.r0sq;
         }
+        const uint32_t mword = __ballot_sync(0xffffffffu, keep);
+        if (keep) S.cidx[n0 + __popc(mword & ((1u << lane) - 1u))] = (uint16_t)c;
+        n0 += __popc(mword);
     }
     __syncwarp();
 
-    // ---- level 2: the eight 4x4x4 sub-boxes; lane = points (i, j, k) and (i, j, k + 1)
+    // ---- level 2: the eight 4x4x4 sub-boxes, one x-half of the brick at a time; lane = points (i, j, k) and (i, j, k + 1)
     const float cert = (P.thr + fabsf(P.thr) * 1.0e-4f + 1.0e-30f) / P.a_sigma;     // compare the un-normalised sum
     const float cull2 = (GLOBAL ? P.rev2 : (sparse ? P.h2m : P.h2)) * 1.0001f;
     const int li = lane >> 3, lj = (lane >> 1) & 3, lk = (lane & 1) * 2;
     unsigned long long n_eval = 0;
-    for (int b = 0; b < 8; ++b) {
-        const int ha = (b >> 2) & 1, hb = (b >> 1) & 1, hc = b & 1;
-        const int i0 = bx * 8 + 4 * ha, j0 = by * 8 + 4 * hb, k0 = bz * 8 + 4 * hc;
-        if (i0 > pmax || j0 > pmax || k0 > pmax) continue;                           // sub-box outside the tile (warp-uniform)
-        const int i = i0 + li, j = j0 + lj, k = k0 + lk;
-        const bool row_ok = i <= pmax && j <= pmax;
-        const bool vA = row_ok && k <= pmax, vB = row_ok && k + 1 <= pmax;
-        // grid point coordinates from GLOBAL indices, the reference's expressions (ss_lane_point)
-        const float gx = __fadd_rn(__fmul_rn((float)(T.gbase[0] + i), P.c), P.gmin[0]);
-        const float gy = __fadd_rn(__fmul_rn((float)(T.gbase[1] + j), P.c), P.gmin[1]);
-        const float fkA = (float)(T.gbase[2] + k), fkB = (float)(T.gbase[2] + k + 1);
-        const float gzA = sparse ? __fadd_rn(P.gmin[2], __fmul_rn(fkA, P.c)) : __fmaf_rn(fkA, P.c, P.gmin[2]);
-        const float gzB = sparse ? __fadd_rn(P.gmin[2], __fmul_rn(fkB, P.c)) : __fmaf_rn(fkB, P.c, P.gmin[2]);
-        SsCwPoint Q;
-        Q.gx = gx; Q.gy = gy; Q.ngz = ss_pack(-gzA, -gzB); Q.g1 = A.g1; Q.g2 = A.g2; Q.g3 = A.g3;
-        ss_f2 sum0 = ss_pack(0.0f, 0.0f), sum1 = ss_pack(0.0f, 0.0f);
-        bool done = false;
-        uint32_t any_r0 = 0;
-        // ring 0: candidates flagged for this sub-box, closest bins first is not needed: a 64-point box uses nearly all of them
-        for (int w = 0; w < nwords && !done; ++w) {
-            const int c = w * 32 + lane;
-            const uint32_t mbit = (c < C) ? ((uint32_t)S.mask[c] >> b) & 1u : 0u;
-            uint32_t mword = __ballot_sync(0xffffffffu, mbit != 0u);
-            if (!mword) continue;
-            any_r0 = 1;
-            if (COUNT) n_eval += 2ull * (unsigned)__popc(mword);
-            ss_cw_accumulate(Q, S.rec + w * 32, mword, sum0, sum1);
-            float sa, sb;
-            ss_unpack(ss_add2(sum0, sum1), sa, sb);
-            done = __all_sync(0xffffffffu, (!vA || sa > cert) && (!vB || sb > cert));
+    for (int ha = 0; ha < 2; ++ha) {
+        if (bx * 8 + 4 * ha > pmax) break;
+        // ---- ring-0 lists of the four sub-boxes (hb, hc) of this half: pair-interleaved records, closest-first is not needed
+        int cnt0 = 0, cnt1 = 0, cnt2 = 0, cnt3 = 0;
+        const float axl = ha ? xl1 : xl0, axh = ha ? xh1 : xh0;
+        for (int w0 = 0; w0 < n0; w0 += 32) {
+            const int q = w0 + lane;
+            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+            uint32_t m = 0;
+            if (q < n0) {
+                r = S.rec[S.cidx[q]];
+                const float ax = ss_axis_d2(r.x, axl, axh);
+                const float xy0 = ax + ss_axis_d2(r.y, yl0, yh0), xy1 = ax + ss_axis_d2(r.y, yl1, yh1);
+                const float az0 = ss_axis_d2(r.z, zl0, zh0), az1 = ss_axis_d2(r.z, zl1, zh1);
+                m = ((xy0 + az0 < A.r0sq) ? 1u : 0u) | ((xy0 + az1 < A.r0sq) ? 2u : 0u) | ((xy1 + az0 < A.r0sq) ? 4u : 0u) | ((xy1 + az1 < A.r0sq) ? 8u : 0u);
+            }
+#define SS_CW_APPEND(s4, cnt_)                                                                                   \
+            {                                                                                                            \
+                const uint32_t bal = __ballot_sync(0xffffffffu, (m >> (s4)) & 1u);                                       \
+                const int pos = cnt_ + __popc(bal & ((1u << lane) - 1u));                                                \
+                if (((m >> (s4)) & 1u) && pos < 2 * SS_CW_PAIRS) {                                                       \
+                    SsCwPair &E = S.list[s4][pos >> 1];                                                                  \
+                    E.x[pos & 1] = r.x; E.y[pos & 1] = r.y; E.z[pos & 1] = r.z; E.v[pos & 1] = r.w;                      \
+                }                                                                                                        \
+                cnt_ = min(cnt_ + __popc(bal), 2 * SS_CW_PAIRS);                                                         \
+            }
+            SS_CW_APPEND(0, cnt0) SS_CW_APPEND(1, cnt1) SS_CW_APPEND(2, cnt2) SS_CW_APPEND(3, cnt3)
+#undef SS_CW_APPEND
         }
-        uint32_t any_sup = any_r0;
-        if (!done) {
-            // ring 1: the remaining candidates the bound can see (g vanishes at 0.755 h), tested against this sub-box directly
-            const float bxl = ha ? xl1 : xl0, bxh = ha ? xh1 : xh0, byl = hb ? yl1 : yl0, byh = hb ? yh1 : yh0, bzl = hc ? zl1 : zl0, bzh = hc ? zh1 : zh0;
-            for (int w = 0; w < nwords && !done; ++w) {
-                const int c = w * 32 + lane;
-                bool keep = false, sup = false;
-                if (c < C) {
-                    const float4 r = S.rec[c];
-                    const float db2 = ss_axis_d2(r.x, bxl, bxh) + ss_axis_d2(r.y, byl, byh) + ss_axis_d2(r.z, bzl, bzh);
-                    sup = db2 < cull2;
-                    keep = (db2 < A.r1sq) && (((uint32_t)S.mask[c] >> b) & 1u) == 0u;
-                }
-                any_sup |= __ballot_sync(0xffffffffu, sup);
-                uint32_t mword = __ballot_sync(0xffffffffu, keep);
-                if (!mword) continue;
-                if (COUNT) n_eval += 2ull * (unsigned)__popc(mword);
-                ss_cw_accumulate(Q, S.rec + w * 32, mword, sum0, sum1);
-                float sa, sb;
-                ss_unpack(ss_add2(sum0, sum1), sa, sb);
+        __syncwarp();
+        // odd lists: the free half of the last pair repeats its partner with zero volume
+        const int cnt_l = lane == 0 ? cnt0 : (lane == 1 ? cnt1 : (lane == 2 ? cnt2 : cnt3));
+        if (lane < 4 && (cnt_l & 1)) {
+            SsCwPair &E = S.list[lane][cnt_l >> 1];
+            E.x[1] = E.x[0]; E.y[1] = E.y[0]; E.z[1] = E.z[0]; E.v[1] = 0.0f;
+        }
+        __syncwarp();
+        for (int s4 = 0; s4 < 4; ++s4) {
+            const int hb = s4 >> 1, hc = s4 & 1;
+            const int i0 = bx * 8 + 4 * ha, j0 = by * 8 + 4 * hb, k0 = bz * 8 + 4 * hc;
+            if (j0 > pmax || k0 > pmax) continue;                                        // sub-box outside the tile (warp-uniform)
+            const int i = i0 + li, j = j0 + lj, k = k0 + lk;
+            const bool row_ok = i <= pmax && j <= pmax;
+            const bool vA = row_ok && k <= pmax, vB = row_ok && k + 1 <= pmax;
+            // grid point coordinates from GLOBAL indices, the reference's expressions (ss_lane_point)
+            const float gx = __fadd_rn(__fmul_rn((float)(T.gbase[0] + i), P.c), P.gmin[0]);
+            const float gy = __fadd_rn(__fmul_rn((float)(T.gbase[1] + j), P.c), P.gmin[1]);
+            const float fkA = (float)(T.gbase[2] + k), fkB = (float)(T.gbase[2] + k + 1);
+            const float gzA = sparse ? __fadd_rn(P.gmin[2], __fmul_rn(fkA, P.c)) : __fmaf_rn(fkA, P.c, P.gmin[2]);
+            const float gzB = sparse ? __fadd_rn(P.gmin[2], __fmul_rn(fkB, P.c)) : __fmaf_rn(fkB, P.c, P.gmin[2]);
+            SsCwPoint Q;
+            Q.gx = gx; Q.gy = gy; Q.ngz = ss_pack(-gzA, -gzB); Q.g1 = A.g1; Q.g2 = A.g2; Q.g3 = A.g3;
+            const int ns4 = s4 == 0 ? cnt0 : (s4 == 1 ? cnt1 : (s4 == 2 ? cnt2 : cnt3));
+            const int npairs = (ns4 + 1) >> 1;
+            ss_f2 sumA = ss_pack(0.0f, 0.0f), sumB = ss_pack(0.0f, 0.0f);
+            bool done = false;
+            float sa = 0.0f, sb = 0.0f;
+            // ring 0 in chunks of four pairs, checking after each chunk
+            for (int first = 0; first < npairs && !done; first += 4) {
+                const int last = min(first + 4, npairs);
+                ss_cw_fold_pairs(Q, -gzA, -gzB, S.list[s4], first, last, sumA, sumB);
+                if (COUNT) n_eval += 4ull * (unsigned)(last - first);
+                float a0, a1, b0, b1;
+                ss_unpack(sumA, a0, a1); ss_unpack(sumB, b0, b1);
+                sa = a0 + a1; sb = b0 + b1;
                 done = __all_sync(0xffffffffu, (!vA || sa > cert) && (!vB || sb > cert));
             }
+            uint32_t any_sup = ns4 ? 1u : 0u;
+            if (!done) {
+                // ring 1: the remaining candidates the bound can see (g vanishes at 0.755 h), tested against this sub-box directly;
+                // "not in ring 0" is the complement of the very comparison that built the list, so nobody is counted twice
+                ss_f2 sum0 = ss_pack(sa, sb), sum1 = ss_pack(0.0f, 0.0f);
+                const float bxl = axl, bxh = axh, byl = hb ? yl1 : yl0, byh = hb ? yh1 : yh0, bzl = hc ? zl1 : zl0, bzh = hc ? zh1 : zh0;
+                for (int w = 0; w < nwords && !done; ++w) {
+                    const int c = w * 32 + lane;
+                    bool keep = false, sup = false;
+                    if (c < C) {
+                        const float4 r = S.rec[c];
+                        const float db2 = (ss_axis_d2(r.x, bxl, bxh) + ss_axis_d2(r.y, byl, byh)) + ss_axis_d2(r.z, bzl, bzh);
+                        sup = db2 < cull2;
+                        keep = (db2 < A.r1sq) && !(db2 < A.r0sq);
+                    }
+                    any_sup |= __ballot_sync(0xffffffffu, sup);
+                    const uint32_t mword = __ballot_sync(0xffffffffu, keep);
+                    if (!mword) continue;
+                    if (COUNT) n_eval += 2ull * (unsigned)__popc(mword);
+                    ss_cw_accumulate(Q, S.rec + w * 32, mword, sum0, sum1);
+                    float ta, tb;
+                    ss_unpack(ss_add2(sum0, sum1), ta, tb);
+                    done = __all_sync(0xffffffffu, (!vA || ta > cert) && (!vB || tb > cert));
+                }
+            }
+            if (done) {
+                float *out = A.tiles + (size_t)tile_idx * P.np * P.np * P.np + ((size_t)i * P.np + j) * P.np + k;
+                if (vA) out[0] = SS_MARKER;
+                if (vB) out[1] = SS_MARKER;
+            }
+            // per-box state of the two standard 2x4x4 boxes this sub-box covers: 1 markers, 2 needs exact values, 3 exact zeros in place
+            if (lane < 2) {
+                const int is = i0 + 2 * lane;                      // first plane of the standard box
+                if (is <= pmax) wst[(2 * ha + lane) * 4 + hb * 2 + hc] = done ? 1 : (any_sup ? 2 : 3);
+            }
         }
-        if (done) {
-            float *out = A.tiles + (size_t)tile_idx * P.np * P.np * P.np + ((size_t)i * P.np + j) * P.np + k;
-            if (vA) out[0] = SS_MARKER;
-            if (vB) out[1] = SS_MARKER;
-        }
-        // per-box state of the two standard 2x4x4 boxes this sub-box covers: 1 markers, 2 needs exact values, 3 exact zeros in place
-        if (lane < 2) {
-            const int is = i0 + 2 * lane;                      // first plane of the standard box
-            if (is <= pmax) wst[(2 * ha + lane) * 4 + hb * 2 + hc] = done ? 1 : (any_sup ? 2 : 3);
-        }
+        __syncwarp();                                              // the lists are rebuilt for the other half
     }
 
     // ---- extension tasks (planes at index np - 1): scalar one-point-per-lane sweep over the staged candidates

@@ -86,7 +86,7 @@ struct ss_context {
     uint32_t max_tiles = 0;          // 0 = auto
     int64_t keep_tile_flat = -1;
     int ls_exact_all = 0;            // 1: evaluate every grid point exactly (no certification)
-    int ls_variant = 0;              // 1: certification in its own barrier-light kernel (ss_certify.cuh)
+    int ls_variant = 2;              // 2 (default): warp-per-brick certification + exact kernels (ss_certify.cuh, ss_exact.cuh); 1: CTA-per-brick certification kernel; 0: fused k_levelset
     int count_pairs = 0;             // 1: count in-support evaluations (work model; slower)
     int sph_normals = 0;             // 1: SPH normals at the mesh vertices (sph_interpolation.rs:82-133)
     // reusable scratch

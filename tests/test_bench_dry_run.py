@@ -31,7 +31,7 @@ def _check_line(out: str, n_gpus: int, steps: int):
 
 
 # (the fixed-size workloads cfg2/cfg3/cfg5 take minutes to hours on the executor; the 1 M-particle cfg2 ran once by hand)
-@pytest.mark.parametrize("extra", [[], ["--levelset-variant", "1", "--no-cpu-baseline"]], ids=["default", "levelset_variant_1"])
+@pytest.mark.parametrize("extra", [[], ["--levelset-variant", "1", "--no-cpu-baseline"], ["--levelset-variant", "0", "--no-cpu-baseline"]], ids=["default", "levelset_variant_1", "levelset_variant_0"])
 def test_bench_single_rank_on_executor(oracle_mod, extra):
     cmd = [sys.executable, LAUNCHER, "bench.py", "--particles", "12000", "--steps", "2", "--warmup", "1", "--cpu-sample-particles", "8000"] + extra
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, SS_EMUL_THREADS="4"))
@@ -39,8 +39,8 @@ def test_bench_single_rank_on_executor(oracle_mod, extra):
     d = _check_line(r.stdout, 1, 2)
     if "--no-cpu-baseline" not in extra:
         assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
-    if "--levelset-variant" in extra:
-        assert d["config"]["levelset_variant"] == 1 and d["roofline"]["launches_per_step"] >= 2
+    want = int(extra[extra.index("--levelset-variant") + 1]) if "--levelset-variant" in extra else 2
+    assert d["config"]["levelset_variant"] == want and d["roofline"]["launches_per_step"] >= (2 if want else 1)
 
 
 @pytest.mark.parametrize("protocol", ["two_call", "callback"])

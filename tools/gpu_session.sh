@@ -77,7 +77,7 @@ if has ncu; then
 fi
 if has ncu2; then
   echo "== ncu --set full, level-set variant 2 on cfg3: k_density, k_certify_warp, k_levelset (exact pass, fix-up pass)"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_certify_warp|k_density|k_levelset' -c 4 -o gpurun_out/prof_variant2_$TAG -f \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_certify_warp|k_exact_warp|k_density<' -c 4 -o gpurun_out/prof_variant2_$TAG -f \
       python bench.py --workload cfg3 --steps 1 --warmup 1 --no-cpu-baseline --levelset-variant 2 > gpurun_out/ncu_full_v2_$TAG.log 2>&1
   ls -la gpurun_out/prof_variant2_$TAG.ncu-rep
 fi
