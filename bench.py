@@ -227,7 +227,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS), help="BASELINE config (default cfg4 = the metric's 50 M dam break)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--runner-protocol", default="two_call", choices=["two_call", "callback"],
+    ap.add_argument("--runner-protocol", default="callback", choices=["two_call", "callback"],
                     help="multi-GPU only: how the global subdomain maximum reaches the library (see distributed.Runner)")
     ap.add_argument("--levelset-variant", type=int, default=2, choices=[0, 1, 2],
                     help="2 (default): warp-per-brick certification + exact kernels (TMA staging, packed FP32); 1: CTA-per-brick certification kernel; 0: fused k_levelset")

@@ -139,6 +139,16 @@ int ss_reconstruct_partition_cb_f32(ss_context *ctx, const float *xyz, uint64_t 
                                     const ss_grid_f32 *grid, int axis, int64_t own_lo, int64_t own_hi, int64_t halo,
                                     uint64_t (*max_reduce)(uint64_t local_max, void *user), void *user, ss_surface **out);
 uint64_t ss_surface_max_subdomain_particles(const ss_surface *s);
+/* Slab-plan statistics of this rank's particles (DEVICE pointers): hist[nsd_axis] = particles per subdomain layer along `axis`,
+ * occ[nsd_x * nsd_y * nsd_z] = 1 for every subdomain slot that owns a particle (x-major flat index).  The caller sums / max-reduces
+ * them across ranks (NCCL) and cuts the layers into slabs. */
+int ss_partition_stats_f32(ss_context *ctx, const float *xyz_dev, uint64_t n, const ss_grid_f32 *grid, uint32_t subdomain_cubes,
+                           int axis, uint32_t *hist_dev, uint32_t *occ_dev);
+/* Halo packing for the one exchange step: destination d receives the particles with lo[d] <= xyz[axis] < hi[d] (a particle may go
+ * to several destinations), grouped by destination, ascending index inside a destination.  Call once with send_dev == NULL to
+ * get counts_out[world] (host), then with a device buffer of sum(counts) * 3 floats. */
+int ss_partition_pack_f32(ss_context *ctx, const float *xyz_dev, uint64_t n, int axis, const double *lo, const double *hi,
+                          uint32_t world, uint64_t *counts_out, float *send_dev);
 const unsigned long long *ss_surface_device_vertex_keys(const ss_surface *s);   /* nv u64 MC edge keys, device memory */
 int ss_surface_copy_subdomain_owned(const ss_surface *s, uint8_t *dst);          /* 1: owned, 0: density-only halo */
 /* Welds vertices with equal MC edge key in a concatenation of per-rank meshes (all pointers DEVICE memory; `cand`

@@ -92,8 +92,9 @@ struct ss_context {
     // reusable scratch
     DevBuf xyz, xyz_f, filt_flag, filt_flag32, filt_off, aabb, cnt, off, key_a, key_b, val_a, val_b, cid, cub_tmp,
         sub_flat, sub_off, sub_sparse, sub_owned, gkey_a, gkey_b, gval_a, gval_b, flags, scan, spos, rho, tab_a, tab_b, rec, ksplit, batch_subs, tiles, vcnt,
-        tcnt, vmask, voff, vblk_off, tblk_off, tile_tab, brick_rng, bstate, flag_ls, off_ls, list_ls, flag_mc, flag_fix, off_mc, off_fix, list_mc, list_fix, wflag, wstate, desc_ls, dflag, doff, dlist, fallback, brick_seen, fix_list, nflag, bkeys_a, bkeys_b, bids_a, bids_b, bcount, remap, keep, newid, err, pairs;
+        tcnt, vmask, voff, vblk_off, tblk_off, tile_tab, brick_rng, bstate, flag_ls, off_ls, list_ls, flag_mc, flag_fix, off_mc, off_fix, list_mc, list_fix, wflag, wstate, desc_ls, dflag, doff, dlist, fallback, pack_cnt, pack_off, brick_seen, fix_list, nflag, bkeys_a, bkeys_b, bids_a, bids_b, bcount, remap, keep, newid, err, pairs;
     uint64_t launches = 0;
+    uint64_t pack_n = 0; uint32_t pack_world = 0;   // ss_partition_pack_f32: count phase the scatter phase must match
     // result buffers handed to surfaces and returned by ss_surface_free (avoids cudaMalloc/cudaFree per frame,
     // the analogue of the reference's ReconstructionWorkspace, workspace.rs:12-79)
     DevBuf o_verts, o_tris, o_vkeys, o_rho, o_verts2, o_vkeys2, o_normals;
@@ -243,7 +244,7 @@ extern "C" void ss_context_destroy(ss_context *c) {
     DevBuf *bufs[] = { &c->xyz, &c->xyz_f, &c->filt_flag, &c->filt_flag32, &c->filt_off, &c->aabb, &c->cnt, &c->off, &c->key_a, &c->key_b,
                        &c->val_a, &c->val_b, &c->cid, &c->cub_tmp, &c->sub_flat, &c->sub_off, &c->sub_sparse, &c->sub_owned, &c->gkey_a, &c->gkey_b, &c->gval_a, &c->gval_b, &c->flags, &c->scan,
                        &c->spos, &c->rho, &c->tab_a, &c->tab_b, &c->rec, &c->ksplit, &c->batch_subs, &c->tiles, &c->vcnt, &c->tcnt,
-                       &c->vmask, &c->voff, &c->vblk_off, &c->tblk_off, &c->tile_tab, &c->brick_rng, &c->bstate, &c->flag_ls, &c->off_ls, &c->list_ls, &c->flag_mc, &c->flag_fix, &c->off_mc, &c->off_fix, &c->list_mc, &c->list_fix, &c->wflag, &c->wstate, &c->desc_ls, &c->dflag, &c->doff, &c->dlist, &c->fallback, &c->brick_seen, &c->fix_list, &c->nflag, &c->bkeys_a, &c->bkeys_b, &c->bids_a, &c->bids_b, &c->bcount, &c->remap, &c->keep, &c->newid,
+                       &c->vmask, &c->voff, &c->vblk_off, &c->tblk_off, &c->tile_tab, &c->brick_rng, &c->bstate, &c->flag_ls, &c->off_ls, &c->list_ls, &c->flag_mc, &c->flag_fix, &c->off_mc, &c->off_fix, &c->list_mc, &c->list_fix, &c->wflag, &c->wstate, &c->desc_ls, &c->dflag, &c->doff, &c->dlist, &c->fallback, &c->pack_cnt, &c->pack_off, &c->brick_seen, &c->fix_list, &c->nflag, &c->bkeys_a, &c->bkeys_b, &c->bids_a, &c->bids_b, &c->bcount, &c->remap, &c->keep, &c->newid,
                        &c->err, &c->pairs, &c->o_verts, &c->o_tris, &c->o_vkeys, &c->o_rho, &c->o_verts2, &c->o_vkeys2, &c->o_normals };
     for (DevBuf *b : bufs) b->release();
     c->post.release_all();
@@ -1127,6 +1128,127 @@ extern "C" int ss_levelset_tile_f32(ss_context *c, const float *xyz, const float
     }
 }
 
+// ------------------------------------------------------------------ multi-GPU: plan statistics + halo packing ----
+// Slab plan input: particles per subdomain layer along the partition axis + occupancy of every subdomain slot (work model of
+// distributed.py: particles + a fixed cost per occupied tile).  Owner cells are computed in plain f32: the plan only balances.
+__global__ void k_part_stats(const float *__restrict__ xyz, uint32_t n, float3 gmin, float inv_sub, int3 nsd, int axis,
+                             uint32_t *__restrict__ hist, uint32_t *__restrict__ occ) {
+    __shared__ uint32_t s_hist[1024];
+    const int nax = axis == 0 ? nsd.x : (axis == 1 ? nsd.y : nsd.z);
+    for (int t = threadIdx.x; t < nax && t < 1024; t += blockDim.x) s_hist[t] = 0;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int ix = min(max((int)floorf((xyz[3 * (uint64_t)i] - gmin.x) * inv_sub), 0), nsd.x - 1);
+        const int iy = min(max((int)floorf((xyz[3 * (uint64_t)i + 1] - gmin.y) * inv_sub), 0), nsd.y - 1);
+        const int iz = min(max((int)floorf((xyz[3 * (uint64_t)i + 2] - gmin.z) * inv_sub), 0), nsd.z - 1);
+        const int ia = axis == 0 ? ix : (axis == 1 ? iy : iz);
+        if (ia < 1024) atomicAdd(&s_hist[ia], 1u); else atomicAdd(&hist[ia], 1u);
+        occ[(ix * nsd.y + iy) * nsd.z + iz] = 1u;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nax && t < 1024; t += blockDim.x) if (s_hist[t]) atomicAdd(&hist[t], s_hist[t]);
+}
+extern "C" int ss_partition_stats_f32(ss_context *c, const float *xyz, uint64_t n, const ss_grid_f32 *grid, uint32_t S, int axis,
+                                      uint32_t *hist, uint32_t *occ) {
+    if (!c || !grid || !hist || !occ || (n && !xyz) || axis < 0 || axis > 2 || S < 1) return ss_fail(SS_ERR_INVALID_PARAMETER, "bad argument");
+    if (n >= 0xfffffff0ull) return ss_fail(SS_ERR_INDEX_TOO_SMALL, "too many particles");
+    try {
+        CK(cudaSetDevice(c->device));
+        int3 nsd;
+        nsd.x = (int)((grid->cells_per_dim[0] + S - 1) / S); nsd.y = (int)((grid->cells_per_dim[1] + S - 1) / S); nsd.z = (int)((grid->cells_per_dim[2] + S - 1) / S);
+        const int nax = axis == 0 ? nsd.x : (axis == 1 ? nsd.y : nsd.z);
+        CK(cudaMemsetAsync(hist, 0, (size_t)nax * 4, c->stream));
+        CK(cudaMemsetAsync(occ, 0, (size_t)nsd.x * nsd.y * nsd.z * 4, c->stream));
+        if (n) {
+            const float sub = fmulr(grid->cell_size, (float)S);
+            const unsigned blocks = (unsigned)std::min<uint64_t>(nblk(n, 256), 148 * 8);
+            LAUNCH(c, k_part_stats, blocks, 256, xyz, (uint32_t)n, make_float3(grid->aabb_min[0], grid->aabb_min[1], grid->aabb_min[2]), 1.0f / sub, nsd, axis, hist, occ);
+        }
+        CK(cudaStreamSynchronize(c->stream));
+        return SS_OK;
+    } catch (const SsCudaError &err) {
+        cudaGetLastError();
+        return ss_fail(SS_ERR_CUDA, std::string(err.what) + ": " + cudaGetErrorString(err.e));
+    }
+}
+
+// Halo packing: destination d takes the particles with lo[d] <= coordinate < hi[d] along the partition axis (one particle may
+// go to several destinations), ascending particle index preserved inside every destination.  One warp walks a chunk of
+// SS_PACK_CHUNK particles in index order; pass 0 counts per (destination, chunk), an exclusive scan over the destination-major
+// count table gives every chunk its output offset, pass 1 scatters.
+#define SS_PACK_CHUNK 2048
+#define SS_PACK_MAXW 64
+struct SsPackIv { double lo[SS_PACK_MAXW], hi[SS_PACK_MAXW]; };
+template <bool SCATTER>
+__global__ void k_part_pack(const float *__restrict__ xyz, uint32_t n, int axis, SsPackIv iv, int world, uint32_t nchunks,
+                            uint32_t *__restrict__ table /* [world][nchunks]: counts in, offsets for SCATTER */, float *__restrict__ send) {
+    const uint32_t chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (chunk >= nchunks) return;
+    const uint32_t first = chunk * SS_PACK_CHUNK, last = min(first + SS_PACK_CHUNK, n);
+    for (int d = 0; d < world; ++d) {
+        const double lo = iv.lo[d], hi = iv.hi[d];
+        uint32_t run = SCATTER ? table[(size_t)d * nchunks + chunk] : 0u;
+        for (uint32_t base = first; base < last; base += 32) {
+            const uint32_t i = base + lane;
+            bool in = false;
+            float x = 0.f, y = 0.f, z = 0.f;
+            if (i < last) {
+                x = xyz[3 * (uint64_t)i]; y = xyz[3 * (uint64_t)i + 1]; z = xyz[3 * (uint64_t)i + 2];
+                const double cax = (double)(axis == 0 ? x : (axis == 1 ? y : z));
+                in = cax >= lo && cax < hi;
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, in);
+            if (SCATTER && in) {
+                const uint64_t o = (uint64_t)run + __popc(bal & ((1u << lane) - 1u));
+                send[3 * o] = x; send[3 * o + 1] = y; send[3 * o + 2] = z;
+            }
+            run += __popc(bal);
+        }
+        if (!SCATTER && lane == 0) table[(size_t)d * nchunks + chunk] = run;
+    }
+}
+// Two-phase: send == NULL counts (counts_out[world], host) and leaves the offset table in the context; the second call with a
+// device buffer of sum(counts) * 3 floats scatters.  xyz is DEVICE memory.
+extern "C" int ss_partition_pack_f32(ss_context *c, const float *xyz, uint64_t n, int axis, const double *lo, const double *hi, uint32_t world,
+                                     uint64_t *counts_out, float *send) {
+    if (!c || !lo || !hi || !counts_out || (n && !xyz) || axis < 0 || axis > 2 || world < 1 || world > SS_PACK_MAXW) return ss_fail(SS_ERR_INVALID_PARAMETER, "bad argument");
+    if (n >= 0xfffffff0ull) return ss_fail(SS_ERR_INDEX_TOO_SMALL, "too many particles");
+    try {
+        CK(cudaSetDevice(c->device));
+        cudaStream_t st = c->stream;
+        const uint32_t nchunks = (uint32_t)((n + SS_PACK_CHUNK - 1) / SS_PACK_CHUNK);
+        for (uint32_t d = 0; d < world; ++d) counts_out[d] = 0;
+        if (!n) return SS_OK;
+        SsPackIv iv{};
+        for (uint32_t d = 0; d < world; ++d) { iv.lo[d] = lo[d]; iv.hi[d] = hi[d]; }
+        const size_t tab = (size_t)world * nchunks;
+        c->pack_cnt.ensure(tab * 4); c->pack_off.ensure(tab * 4 + 4);
+        const unsigned blocks = nblk((uint64_t)nchunks * 32, 128);
+        if (!send) {
+            LAUNCH(c, k_part_pack<false>, blocks, 128, xyz, (uint32_t)n, axis, iv, (int)world, nchunks, c->pack_cnt.as<uint32_t>(), (float *)nullptr);
+            cub_excl_scan(c, c->pack_cnt.as<uint32_t>(), c->pack_off.as<uint32_t>(), (uint32_t)tab);
+            std::vector<uint32_t> h_off(world), h_last(2);
+            for (uint32_t d = 0; d < world; ++d) CK(cudaMemcpyAsync(&h_off[d], c->pack_off.as<uint32_t>() + (size_t)d * nchunks, 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(&h_last[0], c->pack_off.as<uint32_t>() + (tab - 1), 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(&h_last[1], c->pack_cnt.as<uint32_t>() + (tab - 1), 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            const uint64_t total = (uint64_t)h_last[0] + h_last[1];
+            for (uint32_t d = 0; d < world; ++d) counts_out[d] = (d + 1 < world ? h_off[d + 1] : total) - h_off[d];
+            c->pack_n = n; c->pack_world = world;
+        } else {
+            if (c->pack_n != n || c->pack_world != world) return ss_fail(SS_ERR_INVALID_PARAMETER, "ss_partition_pack_f32: scatter phase without a matching count phase");
+            LAUNCH(c, k_part_pack<true>, blocks, 128, xyz, (uint32_t)n, axis, iv, (int)world, nchunks, c->pack_off.as<uint32_t>(), send);
+            CK(cudaStreamSynchronize(st));
+            c->pack_n = 0;
+        }
+        return SS_OK;
+    } catch (const SsCudaError &err) {
+        cudaGetLastError();
+        return ss_fail(err.e == cudaErrorMemoryAllocation ? SS_ERR_OUT_OF_MEMORY : SS_ERR_CUDA, std::string(err.what) + ": " + cudaGetErrorString(err.e));
+    }
+}
+
 // ------------------------------------------------------------------ multi-GPU: one rank's slab of subdomains ----
 static int reconstruct_partition_impl(ss_context *c, const float *xyz, uint64_t n_in, const ss_params_f32 *p, const ss_grid_f32 *grid,
                                       int axis, int64_t own_lo, int64_t own_hi, int64_t halo, uint64_t global_max_particles,
@@ -1141,9 +1263,17 @@ extern "C" int ss_reconstruct_partition_cb_f32(ss_context *c, const float *xyz, 
                                                uint64_t (*max_reduce)(uint64_t local_max, void *user), void *user, ss_surface **out) {
     return reconstruct_partition_impl(c, xyz, n_in, p, grid, axis, own_lo, own_hi, halo, 0, 0, max_reduce, user, out);
 }
+struct ReduceOnce {
+    uint64_t (*fn)(uint64_t, void *); void *user; bool done = false;
+    static uint64_t call(uint64_t v, void *self) { ReduceOnce *r = (ReduceOnce *)self; r->done = true; return r->fn(v, r->user); }
+    ~ReduceOnce() { if (fn && !done) { done = true; fn(0, user); } }
+};
 static int reconstruct_partition_impl(ss_context *c, const float *xyz, uint64_t n_in, const ss_params_f32 *p, const ss_grid_f32 *grid,
                                       int axis, int64_t own_lo, int64_t own_hi, int64_t halo, uint64_t global_max_particles,
                                       int stop_after_decomposition, uint64_t (*max_reduce)(uint64_t, void *), void *user, ss_surface **out) {
+    // The max-reduce callback is a collective: it runs exactly once on EVERY exit path below (argument errors, error returns and
+    // CUDA failures included), so that a rank that fails cannot leave the others blocked in their all-reduce.
+    ReduceOnce once{ max_reduce, user };
     if (!c || !out || !grid) return ss_fail(SS_ERR_INVALID_PARAMETER, "NULL argument");
     *out = nullptr;
     int rc = validate_params(p);
@@ -1165,7 +1295,7 @@ static int reconstruct_partition_impl(ss_context *c, const float *xyz, uint64_t 
         Partition part;
         part.enabled = 1; part.axis = axis; part.own_lo = own_lo; part.own_hi = own_hi; part.halo = halo;
         part.global_max_particles = global_max_particles; part.stop_after_decomposition = stop_after_decomposition;
-        part.max_reduce = max_reduce; part.max_reduce_user = user;
+        part.max_reduce = max_reduce ? &ReduceOnce::call : nullptr; part.max_reduce_user = &once;
         rc = run_subdomain_grid(c, P, p, s, part);
         if (rc) { ss_surface_free(s); return rc; }
         float ms = 0.f;

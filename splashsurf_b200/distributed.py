@@ -197,7 +197,7 @@ def _pinned(t: torch.Tensor, device) -> torch.Tensor:
 class Runner:
     """Drives one reconstruct step on this rank's GPU (world == 1: plain C-ABI call)."""
 
-    def __init__(self, ctx, params, world: int, rank: int, local_rank: int, group=None, device=None, protocol: str = "two_call"):
+    def __init__(self, ctx, params, world: int, rank: int, local_rank: int, group=None, device=None, protocol: str = "callback"):
         self.ctx, self.params, self.world, self.rank, self.local_rank, self.group = ctx, params, world, rank, local_rank, group
         # how the global maximum subdomain population (sparse rule) reaches the library: "two_call" = decomposition pre-pass,
         # all-reduce, full call (verified on 2/4/8 GPUs); "callback" = one call, the library calls back for the all-reduce
@@ -206,6 +206,8 @@ class Runner:
             raise ValueError("protocol must be 'two_call' or 'callback'")
         self.protocol = protocol
         self._out_v = self._out_t = None
+        self._seg = None; self._seg_path = None; self._seg_gen = 0; self._seg_registered = False; self._layout = None
+        self.want_keys = False           # also publish the MC edge keys of the assembled vertices (parity tools)
         # `device` is only overridden by the tests that drive the runner over gloo with the CPU executor of the CUDA sources
         self.device = torch.device("cuda", local_rank) if device is None else torch.device(device)
         self.last_plan: Optional[SlabPlan] = None
@@ -261,140 +263,298 @@ class Runner:
         return self._step_multi(x, copy_out)
 
     def _step_multi(self, x: torch.Tensor, copy_out: bool) -> dict:
-        L, p, world, rank = self.ctx._L, self.params, self.world, self.rank
-        t_ev = [_event(self.device) for _ in range(3)]
-        t_ev[0].record()
-        xd = x.to(self.device, non_blocking=True) if x.device.type != self.device.type else x
-        # 1. global bounding box -> the grid of ALL particles (lib.rs:476-516), identical on every rank
-        if xd.shape[0]:
-            mn, mx = xd.min(dim=0).values, xd.max(dim=0).values
-        else:
-            mn = torch.full((3,), float("inf"), device=self.device); mx = -mn
-        dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=self.group)
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
-        corners = torch.stack([mn, mx]).cpu().numpy().astype(np.float32)
+        L, p, world, rank, dev = self.ctx._L, self.params, self.world, self.rank, self.device
         from . import _Grid
+        t_ev = [_event(dev) for _ in range(3)]
+        t_ev[0].record()
+        xd = x.to(dev, non_blocking=True) if x.device.type != dev.type else x
+        n = int(xd.shape[0])
+        S = int(p.subdomain_num_cubes_per_dim)
+        # 1. global bounding box with ONE all-reduce (MAX over [-min, max]) -> the grid of ALL particles (lib.rs:476-516)
+        if n:
+            mn, mx = torch.aminmax(xd, dim=0)
+            box = torch.cat([-mn, mx])
+        else:
+            box = torch.full((6,), float("-inf"), device=dev)
+        dist.all_reduce(box, op=dist.ReduceOp.MAX, group=self.group)
+        b = box.cpu().numpy().astype(np.float32)                    # host sync: also orders the upload before the library calls
+        corners = np.ascontiguousarray(np.stack([-b[:3], b[3:]]))
         grid = _Grid()
         rc = L.ss_grid_for_reconstruction_f32(self.ctx._h, C.c_void_p(corners.ctypes.data), C.c_uint64(2), C.byref(p), C.byref(grid))
         if rc:
             raise RuntimeError((L.ss_last_error() or b"").decode())
-        # 2. slab plan balanced by a work model (particles + occupied tiles per layer)
-        plan, layer = plan_partition(xd, [float(v) for v in grid.aabb_min], [int(v) for v in grid.cells_per_dim], int(p.subdomain_num_cubes_per_dim),
-                                     float(p.cube_size), float(p.compact_support_radius), world, self.group)
-        ax = plan.axis
+        ncells = [int(v) for v in grid.cells_per_dim]
+        if int(p.spatial_decomposition) == 1 and int(p.auto_disable) and max(ncells) <= int(1.2 * S):
+            # lib.rs:421-440: small domains take the global (non-decomposed) arithmetic -> one rank does it, the others idle
+            return self._step_small_domain(xd, copy_out, t_ev)
+        # 2. slab plan from the library's statistics kernel (particles per layer + occupied tiles), summed over ranks
+        nsd = [(nc + S - 1) // S for nc in ncells]
+        ax = int(np.argmax(nsd))
+        stats = torch.empty(nsd[ax] + nsd[0] * nsd[1] * nsd[2], dtype=torch.int32, device=dev)
+        rc = L.ss_partition_stats_f32(self.ctx._h, C.c_void_p(xd.data_ptr()), C.c_uint64(n), C.byref(grid), C.c_uint32(S), ax,
+                                      C.c_void_p(stats.data_ptr()), C.c_void_p(stats.data_ptr() + 4 * nsd[ax]))
+        if rc:
+            raise RuntimeError((L.ss_last_error() or b"").decode())
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=self.group)
+        h = stats.cpu().numpy()
+        occ = (h[nsd[ax]:] > 0).reshape(nsd)
+        tiles = occ.sum(axis=tuple(d for d in range(3) if d != ax)).astype(np.float64)
+        work = h[:nsd[ax]].astype(np.float64) + TILE_COST_PARTICLES * tiles
+        plan = make_plan(ncells, S, float(p.cube_size), float(p.compact_support_radius), work, world, axis=ax)
+        plan.gmin_axis = float(grid.aabb_min[ax])
         self.last_plan = plan
-        # 3. halo exchange (variable all-to-all over NCCL); keeps ascending global particle order
-        recv, counts = exchange_particles(xd, layer, plan, world, self.group)
+        # 3. halo exchange: the library packs per destination (stable), NCCL moves it; ascending global particle order is kept
+        iv = [plan.recv_interval(r) for r in range(world)]
+        lo = (C.c_double * world)(*[v[0] for v in iv]); hi = (C.c_double * world)(*[v[1] for v in iv])
+        counts = (C.c_uint64 * world)()
+        rc = L.ss_partition_pack_f32(self.ctx._h, C.c_void_p(xd.data_ptr()), C.c_uint64(n), ax, lo, hi, C.c_uint32(world), counts, None)
+        if rc:
+            raise RuntimeError((L.ss_last_error() or b"").decode())
+        counts = [int(v) for v in counts]
+        send = torch.empty((sum(counts), 3), dtype=torch.float32, device=dev)
+        if n:
+            rc = L.ss_partition_pack_f32(self.ctx._h, C.c_void_p(xd.data_ptr()), C.c_uint64(n), ax, lo, hi, C.c_uint32(world), (C.c_uint64 * world)(),
+                                         C.c_void_p(send.data_ptr()))
+            if rc:
+                raise RuntimeError((L.ss_last_error() or b"").decode())
+        cnt_in = torch.tensor(counts, dtype=torch.int64, device=dev)
+        cnt_out = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_to_all_single(cnt_out, cnt_in, group=self.group)
+        out_counts = [int(v) for v in cnt_out.tolist()]
+        recv = torch.empty((sum(out_counts), 3), dtype=torch.float32, device=dev)
+        dist.all_to_all_single(recv.view(-1), send.view(-1), output_split_sizes=[3 * v for v in out_counts],
+                               input_split_sizes=[3 * v for v in counts], group=self.group)
         t_ev[1].record()
         own_lo, own_hi = plan.own(rank)
-        # 4. local maximum subdomain population -> global maximum (sparse rule, dense_subdomains.rs:1242-1251).  Every rank
-        #    makes the same two library calls and the same all-reduce, also ranks that received no particles.
-        _sync(self.device)
+        _sync(dev)                                                  # the exchange has landed before the library (own stream) reads it
+        # 4. this rank's slab.  The global maximum subdomain population (sparse rule, dense_subdomains.rs:1242-1251) is max-reduced
+        #    from inside the call ("callback") or by a decomposition pre-pass ("two_call"); every rank issues the same collectives.
         s = C.c_void_p()
         pre_launches = 0
+        failure = []
+        recv_ptr = C.c_void_p(recv.data_ptr())
+        if getattr(self, "_test_fail_rank", None) == rank:          # fault injection for tests/test_distributed_cpu.py: a NULL particle pointer
+            recv_ptr = C.c_void_p(None)
         if self.protocol == "callback":
-            failure = []
-
             def _reduce(local_max, _user):
                 try:
-                    t = torch.tensor([int(local_max)], dtype=torch.int64, device=self.device)
+                    t = torch.tensor([int(local_max)], dtype=torch.int64, device=dev)
                     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
                     return int(t.item())
                 except BaseException as exc:                      # ctypes would swallow it: remember and re-raise after the call
                     failure.append(exc)
                     return int(local_max)
             cb = C.CFUNCTYPE(C.c_uint64, C.c_uint64, C.c_void_p)(_reduce)
-            rc = L.ss_reconstruct_partition_cb_f32(self.ctx._h, C.c_void_p(recv.data_ptr()), C.c_uint64(recv.shape[0]), C.byref(p),
+            rc = L.ss_reconstruct_partition_cb_f32(self.ctx._h, recv_ptr, C.c_uint64(recv.shape[0]), C.byref(p),
                                                    C.byref(grid), ax, own_lo, own_hi, plan.halo, cb, None, C.byref(s))
-            if failure:
-                raise failure[0]
-            if rc:
-                raise RuntimeError((L.ss_last_error() or b"").decode())
         else:
-            rc = L.ss_reconstruct_partition_f32(self.ctx._h, C.c_void_p(recv.data_ptr()), C.c_uint64(recv.shape[0]), C.byref(p),
+            rc = L.ss_reconstruct_partition_f32(self.ctx._h, recv_ptr, C.c_uint64(recv.shape[0]), C.byref(p),
                                                 C.byref(grid), ax, own_lo, own_hi, plan.halo, C.c_uint64(0), 1, C.byref(s))
-            if rc:
-                raise RuntimeError((L.ss_last_error() or b"").decode())
-            gmax = torch.tensor([L.ss_surface_max_subdomain_particles(s)], dtype=torch.int64, device=self.device)
-            pre_launches = int(self.ctx.timings(s)["kernel_launches"])
-            self.ctx.free_surface(s)
-            dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=self.group)
-            # 5. this rank's slab
-            s = C.c_void_p()
-            rc = L.ss_reconstruct_partition_f32(self.ctx._h, C.c_void_p(recv.data_ptr()), C.c_uint64(recv.shape[0]), C.byref(p),
-                                                C.byref(grid), ax, own_lo, own_hi, plan.halo, C.c_uint64(int(gmax.item())), 0, C.byref(s))
-            if rc:
-                raise RuntimeError((L.ss_last_error() or b"").decode())
+            local_max = 0
+            if not rc:
+                local_max = L.ss_surface_max_subdomain_particles(s)
+                pre_launches = int(self.ctx.timings(s)["kernel_launches"])
+                self.ctx.free_surface(s)
+            gmax = torch.tensor([local_max], dtype=torch.int64, device=dev)
+            dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=self.group)       # issued on every rank, also after a failed pre-pass
+            if not rc:
+                s = C.c_void_p()
+                rc = L.ss_reconstruct_partition_f32(self.ctx._h, C.c_void_p(recv.data_ptr()), C.c_uint64(recv.shape[0]), C.byref(p),
+                                                    C.byref(grid), ax, own_lo, own_hi, plan.halo, C.c_uint64(int(gmax.item())), 0, C.byref(s))
+        # 5. the status is part of the protocol: every rank learns whether any rank failed and raises together (no rank is
+        #    left waiting in a later collective)
+        msg = (L.ss_last_error() or b"").decode() if rc else ""
+        status = torch.tensor([int(rc) if not failure else 255], dtype=torch.int32, device=dev)
+        dist.all_reduce(status, op=dist.ReduceOp.MAX, group=self.group)
+        if failure:
+            raise failure[0]
+        if int(status.item()):
+            if s and not rc:
+                self.ctx.free_surface(s)
+            raise RuntimeError(f"rank {rank}: {msg}" if rc else f"rank {rank}: another rank failed (code {int(status.item())})")
         try:
             t_ev[2].record()
-            _sync(self.device)
-            out = self._collect(s, False, n_local=x.shape[0])
-            # events on torch's stream bracket the whole step: exchange (NCCL) + both host-synchronous library calls
+            _sync(dev)
+            out = self._collect(s, False, n_local=n)
+            # events on torch's stream bracket the whole step: exchange (NCCL) + the host-synchronous library calls
             out["device_ms"] = t_ev[0].elapsed_time(t_ev[2])
             out["launches"] += pre_launches
             out["recv_particles"] = int(recv.shape[0])
             out["exchange_ms"] = t_ev[0].elapsed_time(t_ev[1])
             out["plan"] = plan
             if copy_out:
-                out.update(self._gather_mesh(s, plan))
+                out.update(self._assemble_mesh(s, plan))
             return out
         finally:
             self.ctx.free_surface(s)
 
-    # -- mesh assembly on rank 0: concatenate per-rank meshes, weld the vertices on inter-slab faces, copy to host
-    def _gather_mesh(self, s, plan: SlabPlan) -> dict:
-        L, world, rank = self.ctx._L, self.world, self.rank
-        nv, nt = L.ss_surface_num_vertices(s), L.ss_surface_num_triangles(s)
-        v = _view(L.ss_surface_device_vertices(s), (nv, 3), "<f4", self.device)
-        t = _view(L.ss_surface_device_triangles(s), (nt, 3), "<u4", self.device)
-        k = _view(L.ss_surface_device_vertex_keys(s), (nv,), "<u8", self.device)
-        sizes = torch.tensor([nv, nt], dtype=torch.int64, device=self.device)
-        all_sizes = [torch.empty_like(sizes) for _ in range(world)]
-        dist.all_gather(all_sizes, sizes, group=self.group)
-        all_sizes = [tuple(int(a) for a in z.tolist()) for z in all_sizes]
+    # -- domains at most 1.2 subdomains wide (auto_disable rule): all particles go to rank 0, which takes the single-GPU entry
+    def _step_small_domain(self, xd: torch.Tensor, copy_out: bool, t_ev) -> dict:
+        world, rank, dev = self.world, self.rank, self.device
+        sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([xd.shape[0]], dtype=torch.int64, device=dev), group=self.group)
+        sizes = [int(v.item()) for v in sizes]
+        parts = [torch.empty((m, 3), dtype=torch.float32, device=dev) for m in sizes]
+        pad = max(sizes + [1])
+        buf = torch.zeros((pad, 3), dtype=torch.float32, device=dev)
+        buf[:xd.shape[0]] = xd
+        bufs = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(bufs, buf, group=self.group)
+        allp = torch.cat([bufs[r][:sizes[r]] for r in range(world)]).contiguous()
+        _sync(dev)
+        out = self._step_single(allp.data_ptr(), allp.shape[0] if rank == 0 else 0, copy_out and rank == 0)
+        t_ev[2].record(); _sync(dev)
+        out["device_ms"] = t_ev[0].elapsed_time(t_ev[2])
+        out["recv_particles"] = int(allp.shape[0]) if rank == 0 else 0
+        out["plan"] = SlabPlan(0, 1, [0] + [1] * world, 0, 0)
         if rank != 0:
-            if nv:
-                dist.send(v.contiguous(), 0, group=self.group); dist.send(k.contiguous(), 0, group=self.group)
-            if nt:
-                dist.send(t.contiguous(), 0, group=self.group)
-            return {"d2h_bytes": 0, "nv_global": None, "nt_global": None}
-        vs, ks, ts, off = [v.clone()], [k.clone()], [t.clone()], nv
-        for r in range(1, world):
-            rv, rt = all_sizes[r]
-            bv = torch.empty((rv, 3), dtype=torch.float32, device=self.device)
-            bk = torch.empty((rv,), dtype=torch.int64, device=self.device)
-            bt = torch.empty((rt, 3), dtype=torch.int32, device=self.device)
-            if rv:
-                dist.recv(bv, r, group=self.group); dist.recv(bk, r, group=self.group)
-            if rt:
-                dist.recv(bt, r, group=self.group)
-            vs.append(bv); ks.append(bk); ts.append(bt + off)
-            off += rv
-        V, K, T = torch.cat(vs).contiguous(), torch.cat(ks).contiguous(), torch.cat(ts).contiguous()
-        # candidates: vertices on an inter-slab face = edge not along the partition axis whose point index along the
-        # axis is a multiple of S at a cut (key layout: i << 42 | j << 22 | k << 2 | axis)
+            out.update(nv=0, nt=0, nsub=0, nsub_owned=0, memberships=0.0)
+        if copy_out:
+            nvnt = torch.tensor([out["nv"], out["nt"]], dtype=torch.int64, device=dev)
+            dist.broadcast(nvnt, 0, group=self.group)
+            out["nv_global"], out["nt_global"] = (int(nvnt[0]), int(nvnt[1])) if rank == 0 else (None, None)
+            out["small_domain"] = True
+        return out
+
+    # -- shared host segment for the assembled mesh: every rank copies its part device -> host over its own PCIe link
+    def _host_segment(self, nbytes: int):
+        if self._seg is not None and self._seg.numel() >= nbytes:
+            return self._seg
+        import os
+        want = int(nbytes * 1.25) + (1 << 20)
+        if self.device.type != "cuda":
+            self._seg_path = None                                  # tests on host memory: plain private buffer, gathered through gloo
+            self._seg = torch.empty(want, dtype=torch.uint8)
+            return self._seg
+        name = f"/dev/shm/ss_b200_mesh_{os.environ.get('MASTER_PORT', '0')}_{self._seg_gen}"
+        self._seg_gen += 1
+        if self.rank == 0:
+            with open(name, "wb") as f:
+                f.truncate(want)
+        dist.barrier(group=self.group)
+        if self._seg is not None and self._seg_registered:
+            torch.cuda.cudart().cudaHostUnregister(self._seg.data_ptr())
+        self._seg = torch.from_file(name, shared=True, size=want, dtype=torch.uint8)
+        torch.cuda.cudart().cudaHostRegister(self._seg.data_ptr(), want, 0)      # page-locked: asynchronous device -> host copies at link speed
+        self._seg_registered = True
+        dist.barrier(group=self.group)
+        if self.rank == 0:
+            try:
+                if self._seg_path:
+                    os.unlink(self._seg_path)
+            except OSError:
+                pass
+        self._seg_path = name
+        return self._seg
+
+    # -- mesh assembly: duplicates on the faces between slabs are resolved against the LOWER neighbour by MC edge key (the copy
+    #    of the lowest subdomain wins, as in the single-GPU weld), global vertex ids are rank-major, and every rank writes its own
+    #    vertices / triangles into the shared host segment.  Only face keys and a few counters travel between GPUs.
+    def _assemble_mesh(self, s, plan: SlabPlan) -> dict:
+        L, world, rank, dev = self.ctx._L, self.world, self.rank, self.device
+        nv, nt = L.ss_surface_num_vertices(s), L.ss_surface_num_triangles(s)
+        v = _view(L.ss_surface_device_vertices(s), (nv, 3), "<f4", dev)
+        t = _view(L.ss_surface_device_triangles(s), (nt, 3), "<u4", dev)
+        k = _view(L.ss_surface_device_vertex_keys(s), (nv,), "<u8", dev)
         S = int(self.params.subdomain_num_cubes_per_dim)
         shift = (42, 22, 2)[plan.axis]
-        coord = (K >> shift) & 0xFFFFF
-        eaxis = K & 3
-        cut_pts = torch.tensor([c * S for c in plan.cuts[1:-1]], dtype=torch.int64, device=self.device)
-        cand = torch.nonzero((eaxis != plan.axis) & torch.isin(coord, cut_pts)).view(-1).to(torch.int32).contiguous()
-        nv_out = C.c_uint64(V.shape[0])
-        _sync(self.device)
-        rc = L.ss_weld_meshes(self.ctx._h, C.c_void_p(V.data_ptr()), C.c_void_p(K.data_ptr()), C.c_uint64(V.shape[0]), C.c_void_p(T.data_ptr()),
-                              C.c_uint64(T.shape[0]), C.c_void_p(cand.data_ptr()), C.c_uint64(cand.shape[0]), C.byref(nv_out))
-        if rc:
-            raise RuntimeError((L.ss_last_error() or b"").decode())
-        nvg, ntg = int(nv_out.value), int(T.shape[0])
-        if self._out_v is None or self._out_v.numel() < nvg * 3:
-            self._out_v = _pinned(torch.empty(max(nvg * 3, 1), dtype=torch.float32), self.device)
-        if self._out_t is None or self._out_t.numel() < ntg * 3:
-            self._out_t = _pinned(torch.empty(max(ntg * 3, 1), dtype=torch.int32), self.device)
-        self._out_v[:nvg * 3].copy_(V[:nvg].view(-1), non_blocking=True)
-        self._out_t[:ntg * 3].copy_(T.view(-1), non_blocking=True)
-        _sync(self.device)
-        return {"d2h_bytes": nvg * 12 + ntg * 12, "nv_global": nvg, "nt_global": ntg, "keys_global": K[:nvg]}
+        own_lo, own_hi = plan.own(rank)
+        coord = (k >> shift) & 0xFFFFF
+        onface = (k & 3) != plan.axis
+        up_idx = torch.nonzero(onface & (coord == own_hi * S)).view(-1)        # my vertices a higher rank may duplicate
+        lo_idx = torch.nonzero(onface & (coord == own_lo * S)).view(-1) if own_lo > 0 else up_idx[:0]
+        # round 1: sizes
+        sz = torch.tensor([nv, nt, up_idx.numel()], dtype=torch.int64, device=dev)
+        all_sz = [torch.empty_like(sz) for _ in range(world)]
+        dist.all_gather(all_sz, sz, group=self.group)
+        all_sz = torch.stack(all_sz).cpu().numpy()
+        fmax = max(int(all_sz[:, 2].max()), 1)
+        # round 2: upper-face keys of every rank
+        mine = torch.full((fmax,), -1, dtype=torch.int64, device=dev)
+        mine[:up_idx.numel()] = k[up_idx]
+        allk = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allk, mine, group=self.group)
+        # my duplicates: lower-face vertices whose key a lower rank published
+        keep = torch.ones(nv, dtype=torch.bool, device=dev)
+        dup_src_rank = dup_src_pos = None
+        if rank > 0 and lo_idx.numel():
+            lower = torch.cat([allk[q][:int(all_sz[q, 2])] for q in range(rank)])
+            owner = torch.cat([torch.full((int(all_sz[q, 2]),), q, dtype=torch.int64, device=dev) for q in range(rank)])
+            posin = torch.cat([torch.arange(int(all_sz[q, 2]), dtype=torch.int64, device=dev) for q in range(rank)])
+            if lower.numel():
+                sk, order = torch.sort(lower)
+                mykeys = k[lo_idx]
+                pos = torch.searchsorted(sk, mykeys).clamp(max=sk.numel() - 1)
+                hit = sk[pos] == mykeys
+                dup_v = lo_idx[hit]
+                keep[dup_v] = False
+                dup_src_rank, dup_src_pos = owner[order[pos[hit]]], posin[order[pos[hit]]]
+        newid = torch.cumsum(keep, 0, dtype=torch.int64) - 1                     # compacted local ids
+        nkeep = int(newid[-1].item()) + 1 if nv else 0
+        # round 3: kept counts + compacted ids of my upper-face vertices (they are never dropped: different plane)
+        pub = torch.full((fmax + 1,), -1, dtype=torch.int64, device=dev)
+        pub[0] = nkeep
+        pub[1:1 + up_idx.numel()] = newid[up_idx]
+        allp = [torch.empty_like(pub) for _ in range(world)]
+        dist.all_gather(allp, pub, group=self.group)
+        nkeeps = [int(a[0].item()) for a in allp]
+        voff = [0]
+        for q in range(world):
+            voff.append(voff[-1] + nkeeps[q])
+        toff = [0]
+        for q in range(world):
+            toff.append(toff[-1] + int(all_sz[q, 1]))
+        nvg, ntg = voff[-1], toff[-1]
+        gid = newid + voff[rank]
+        if dup_src_rank is not None and dup_src_rank.numel():
+            table = torch.stack([a[1:] for a in allp])                            # (world, fmax) compacted local ids of upper-face vertices
+            offs = torch.tensor(voff[:-1], dtype=torch.int64, device=dev)
+            gid[dup_v] = table[dup_src_rank, dup_src_pos] + offs[dup_src_rank]
+        tg = gid[t.to(torch.int64).view(-1)].to(torch.int32) if nt else torch.empty(0, dtype=torch.int32, device=dev)
+        vk = v[keep].contiguous()
+        want_keys = self.want_keys
+        nbytes = nvg * 12 + ntg * 12 + (nvg * 8 if want_keys else 0)
+        seg = self._host_segment(nbytes + 64)
+        self._layout = (nvg, ntg, want_keys)
+        sv = seg[:nvg * 12].view(torch.float32)
+        st = seg[nvg * 12:nvg * 12 + ntg * 12].view(torch.int32)
+        if dev.type == "cuda":
+            sv[voff[rank] * 3:voff[rank + 1] * 3].copy_(vk.view(-1), non_blocking=True)
+            st[toff[rank] * 3:toff[rank + 1] * 3].copy_(tg, non_blocking=True)
+            if want_keys:
+                base = (nvg * 12 + ntg * 12 + 7) // 8 * 8
+                seg[base:base + nvg * 8].view(torch.int64)[voff[rank]:voff[rank + 1]].copy_(k[keep], non_blocking=True)
+            _sync(dev)
+            dist.barrier(group=self.group)                                        # every part has landed in the shared segment
+        else:
+            # host-memory runs (tests): no shared segment, rank 0 gathers the parts through the process group
+            parts_v = [torch.empty(nkeeps[q] * 3, dtype=torch.float32) for q in range(world)]
+            parts_t = [torch.empty(int(all_sz[q, 1]) * 3, dtype=torch.int32) for q in range(world)]
+            parts_k = [torch.empty(nkeeps[q], dtype=torch.int64) for q in range(world)]
+            pad_v, pad_t = max(nkeeps + [1]) * 3, max(int(all_sz[:, 1].max()), 1) * 3
+            bv = torch.zeros(pad_v, dtype=torch.float32); bv[:nkeep * 3] = vk.view(-1)
+            bt = torch.zeros(pad_t, dtype=torch.int32); bt[:nt * 3] = tg
+            bk = torch.zeros(pad_v // 3, dtype=torch.int64); bk[:nkeep] = k[keep]
+            gv = [torch.empty_like(bv) for _ in range(world)]; gt = [torch.empty_like(bt) for _ in range(world)]; gk = [torch.empty_like(bk) for _ in range(world)]
+            dist.all_gather(gv, bv, group=self.group); dist.all_gather(gt, bt, group=self.group); dist.all_gather(gk, bk, group=self.group)
+            for q in range(world):
+                sv[voff[q] * 3:voff[q + 1] * 3] = gv[q][:nkeeps[q] * 3]
+                st[toff[q] * 3:toff[q + 1] * 3] = gt[q][:int(all_sz[q, 1]) * 3]
+            if want_keys:
+                base = (nvg * 12 + ntg * 12 + 7) // 8 * 8
+                sk8 = seg[base:base + nvg * 8].view(torch.int64)
+                for q in range(world):
+                    sk8[voff[q]:voff[q + 1]] = gk[q][:nkeeps[q]]
+        res = {"d2h_bytes": nkeep * 12 + nt * 12, "nv_global": nvg if rank == 0 else None, "nt_global": ntg if rank == 0 else None,
+               "nv_total": nvg, "nt_total": ntg}
+        if want_keys and rank == 0:
+            base = (nvg * 12 + ntg * 12 + 7) // 8 * 8
+            res["keys_global"] = seg[base:base + nvg * 8].view(torch.int64).clone()
+        return res
 
     def gathered_mesh(self, nv: int, nt: int):
-        """Host copies of the last gathered mesh (rank 0)."""
-        return self._out_v[:nv * 3].view(-1, 3).numpy().copy(), self._out_t[:nt * 3].view(-1, 3).numpy().copy()
+        """Host copies of the last assembled mesh (any rank can read the shared segment; tests: rank 0)."""
+        if getattr(self, "_layout", None) is None:              # single-GPU / small-domain path
+            return self._out_v[:nv * 3].view(-1, 3).numpy().copy(), self._out_t[:nt * 3].view(-1, 3).numpy().copy()
+        seg = self._seg
+        return seg[:nv * 12].view(torch.float32).view(-1, 3).numpy().copy(), seg[nv * 12:nv * 12 + nt * 12].view(torch.int32).view(-1, 3).numpy().copy()

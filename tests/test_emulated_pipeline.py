@@ -318,6 +318,7 @@ case = json.loads(os.environ["SS_CASE"])
 p_all = getattr(syn, case["gen"])(*[tuple(a) if isinstance(a, list) else a for a in case["args"]])
 ctx = ss.Context(0)
 runner = ssd.Runner(ctx, ss.make_params(**case["kw"]), world, rank, 0, device="cpu", protocol=case.get("protocol", "two_call"))
+runner.want_keys = True
 x = torch.from_numpy(runner.take_local(p_all))
 for it in range(2):                                             # second step reuses the pooled buffers
     out = runner.step(x, copy_out=True)
@@ -363,3 +364,52 @@ def test_emulated_runner_over_gloo(tmp_path, oracle_mod, world, case):
     ranks = [json.load(open(tmp_path / f"rank{k}.json")) for k in range(world)]
     if world == 3:
         assert min(r_["nsub_owned"] for r_ in ranks) == 0, ranks          # the idle rank really was idle
+
+
+FAIL_WORKER = r'''
+import ctypes as C, json, os, sys
+import numpy as np, torch, torch.distributed as dist, datetime
+sys.path.insert(0, os.environ["SS_ROOT"])
+import splashsurf_b200 as ss
+from splashsurf_b200 import distributed as ssd, synthetic as syn
+ss._LIB = ss._bind(C.CDLL(os.environ["SS_EMUL_SO"]))
+dist.init_process_group("gloo", timeout=datetime.timedelta(seconds=60))
+rank, world = dist.get_rank(), dist.get_world_size()
+p_all = syn.dam_break((10, 6, 6), (14, 2, 6), 0.025, 501)
+kw = dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.75, subdomain_num_cubes_per_dim=16, subdomain_grid_auto_disable=False)
+ctx = ss.Context(0)
+runner = ssd.Runner(ctx, ss.make_params(**kw), world, rank, 0, device="cpu", protocol=os.environ["SS_PROTOCOL"])
+runner._test_fail_rank = 1
+x = torch.from_numpy(runner.take_local(p_all))
+try:
+    runner.step(x, copy_out=False)
+    outcome = "no error"
+except RuntimeError as e:
+    outcome = "raised: " + str(e)[:120]
+json.dump({"outcome": outcome}, open(os.path.join(os.environ["SS_OUT"], f"rank{rank}.json"), "w"))
+runner._test_fail_rank = None
+out = runner.step(x, copy_out=False)                             # and the group is still usable afterwards
+json.dump({"outcome": outcome, "nv_after": int(out["nv"])}, open(os.path.join(os.environ["SS_OUT"], f"rank{rank}.json"), "w"))
+ctx.close()
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("protocol", ["callback", "two_call"])
+def test_emulated_runner_failure_on_one_rank_raises_everywhere(tmp_path, protocol):
+    """A failing library call on one rank must not leave the other ranks blocked in a collective: the max-reduce still happens
+    on the failing rank (ss_pipeline.cu: ReduceOnce) and the status all-reduce makes every rank raise."""
+    import json
+    import sys
+    so = build_emulated_library()
+    script = tmp_path / "worker.py"
+    script.write_text(FAIL_WORKER)
+    env = dict(os.environ, SS_ROOT=ROOT, SS_OUT=str(tmp_path), SS_EMUL_SO=so, SS_PROTOCOL=protocol, SS_EMUL_THREADS="3", OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(free_port()), str(script)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = [json.load(open(tmp_path / f"rank{k}.json")) for k in range(2)]
+    assert all(x["outcome"].startswith("raised") for x in res), res
+    assert "xyz is NULL" in res[1]["outcome"] and "another rank failed" in res[0]["outcome"], res
+    assert res[0]["nv_after"] + res[1]["nv_after"] > 0

@@ -25,6 +25,7 @@ def main():
         ctx = ss.Context(local)
         params = ss.make_params(**kw)
         runner = ssd.Runner(ctx, params, world, rank, local)
+        runner.want_keys = True
         x = torch.from_numpy(runner.take_local(p_all)).cuda()
         res = runner.step(x, copy_out=True)
         if rank == 0:

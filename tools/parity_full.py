@@ -245,6 +245,7 @@ def main():
         if args.levelset_variant is not None:
             ctx.set_levelset_variant(args.levelset_variant)
         runner = ssd.Runner(ctx, ss.make_params(**kw), world, rank, local)
+        runner.want_keys = True
         x = torch.from_numpy(runner.take_local(p)).cuda()
         del p
         t0 = time.perf_counter()
