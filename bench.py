@@ -227,7 +227,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS), help="BASELINE config (default cfg4 = the metric's 50 M dam break)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--runner-protocol", default="callback", choices=["two_call", "callback"],
+    ap.add_argument("--runner-protocol", default="two_call", choices=["two_call", "callback"],
                     help="multi-GPU only: how the global subdomain maximum reaches the library (see distributed.Runner)")
     ap.add_argument("--levelset-variant", type=int, default=2, choices=[0, 1, 2],
                     help="2 (default): warp-per-brick certification + exact kernels (TMA staging, packed FP32); 1: CTA-per-brick certification kernel; 0: fused k_levelset")
@@ -332,9 +332,12 @@ def main():
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t0)
     t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    tb = torch.tensor([float(d2h)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tb, op=dist.ReduceOp.SUM)            # every rank copies its own part of the mesh to the shared host segment
     e2e_ms = t.item() / args.steps
+    d2h = int(tb.item())
     e2e_val = n_total / (e2e_ms * 1e-3) / 1e6
 
     if rank == 0:

@@ -197,7 +197,7 @@ def _pinned(t: torch.Tensor, device) -> torch.Tensor:
 class Runner:
     """Drives one reconstruct step on this rank's GPU (world == 1: plain C-ABI call)."""
 
-    def __init__(self, ctx, params, world: int, rank: int, local_rank: int, group=None, device=None, protocol: str = "callback"):
+    def __init__(self, ctx, params, world: int, rank: int, local_rank: int, group=None, device=None, protocol: str = "two_call"):
         self.ctx, self.params, self.world, self.rank, self.local_rank, self.group = ctx, params, world, rank, local_rank, group
         # how the global maximum subdomain population (sparse rule) reaches the library: "two_call" = decomposition pre-pass,
         # all-reduce, full call (verified on 2/4/8 GPUs); "callback" = one call, the library calls back for the all-reduce
@@ -208,6 +208,8 @@ class Runner:
         self._out_v = self._out_t = None
         self._seg = None; self._seg_path = None; self._seg_gen = 0; self._seg_registered = False; self._layout = None
         self.want_keys = False           # also publish the MC edge keys of the assembled vertices (parity tools)
+        self.balance_feedback = True     # slab cuts learn from the measured per-rank time of earlier frames
+        self._layer_scale = None; self._layer_key = None
         # `device` is only overridden by the tests that drive the runner over gloo with the CPU executor of the CUDA sources
         self.device = torch.device("cuda", local_rank) if device is None else torch.device(device)
         self.last_plan: Optional[SlabPlan] = None
@@ -300,6 +302,11 @@ class Runner:
         occ = (h[nsd[ax]:] > 0).reshape(nsd)
         tiles = occ.sum(axis=tuple(d for d in range(3) if d != ax)).astype(np.float64)
         work = h[:nsd[ax]].astype(np.float64) + TILE_COST_PARTICLES * tiles
+        # feedback from earlier frames: layers whose rank took longer than the mean weigh more (frames are temporally coherent)
+        if self.balance_feedback and self._layer_scale is not None and self._layer_key == (ax, nsd[ax]):
+            work = work * self._layer_scale
+        else:
+            self._layer_scale, self._layer_key = np.ones(nsd[ax]), (ax, nsd[ax])
         plan = make_plan(ncells, S, float(p.cube_size), float(p.compact_support_radius), work, world, axis=ax)
         plan.gmin_axis = float(grid.aabb_min[ax])
         self.last_plan = plan
@@ -364,14 +371,27 @@ class Runner:
         # 5. the status is part of the protocol: every rank learns whether any rank failed and raises together (no rank is
         #    left waiting in a later collective)
         msg = (L.ss_last_error() or b"").decode() if rc else ""
-        status = torch.tensor([int(rc) if not failure else 255], dtype=torch.int32, device=dev)
+        status = torch.zeros(1 + world, dtype=torch.float64, device=dev)       # [worst return code, library ms of every rank]
+        status[0] = float(int(rc) if not failure else 255)
+        if not rc and not failure:
+            status[1 + rank] = float(self.ctx.timings(s)["total_device"])
         dist.all_reduce(status, op=dist.ReduceOp.MAX, group=self.group)
+        status = status.cpu().numpy()
         if failure:
             raise failure[0]
-        if int(status.item()):
+        if int(status[0]):
             if s and not rc:
                 self.ctx.free_surface(s)
-            raise RuntimeError(f"rank {rank}: {msg}" if rc else f"rank {rank}: another rank failed (code {int(status.item())})")
+            raise RuntimeError(f"rank {rank}: {msg}" if rc else f"rank {rank}: another rank failed (code {int(status[0])})")
+        if self.balance_feedback:
+            t_r = status[1:]
+            busy = [r for r in range(world) if plan.own(r)[1] > plan.own(r)[0]]
+            mean = float(np.mean([t_r[r] for r in busy])) if busy else 0.0
+            if mean > 0:
+                for r in busy:
+                    a, bnd = plan.own(r)
+                    self._layer_scale[a:bnd] *= float(np.clip((t_r[r] / mean) ** 0.7, 0.7, 1.4))
+                self._layer_scale = np.clip(self._layer_scale / self._layer_scale.mean(), 0.2, 5.0)
         try:
             t_ev[2].record()
             _sync(dev)
@@ -423,29 +443,41 @@ class Runner:
         import os
         want = int(nbytes * 1.25) + (1 << 20)
         if self.device.type != "cuda":
-            self._seg_path = None                                  # tests on host memory: plain private buffer, gathered through gloo
-            self._seg = torch.empty(want, dtype=torch.uint8)
+            self._seg = torch.empty(want, dtype=torch.uint8)       # tests on host memory: private buffer, parts gathered through gloo
             return self._seg
-        name = f"/dev/shm/ss_b200_mesh_{os.environ.get('MASTER_PORT', '0')}_{self._seg_gen}"
+        self._release_segment()
+        name = [f"/dev/shm/ss_b200_mesh_{os.getpid()}_{id(self) & 0xffffff:x}_{self._seg_gen}"]
         self._seg_gen += 1
+        dist.broadcast_object_list(name, src=0, group=self.group)  # rank 0 names the segment
+        name = name[0]
         if self.rank == 0:
             with open(name, "wb") as f:
                 f.truncate(want)
         dist.barrier(group=self.group)
-        if self._seg is not None and self._seg_registered:
-            torch.cuda.cudart().cudaHostUnregister(self._seg.data_ptr())
         self._seg = torch.from_file(name, shared=True, size=want, dtype=torch.uint8)
-        torch.cuda.cudart().cudaHostRegister(self._seg.data_ptr(), want, 0)      # page-locked: asynchronous device -> host copies at link speed
-        self._seg_registered = True
+        # page-locked: asynchronous device -> host copies at link speed, all ranks in parallel
+        err = torch.cuda.cudart().cudaHostRegister(self._seg.data_ptr(), want, 0)
+        self._seg_registered = (int(err) == 0) if err is not None else True
         dist.barrier(group=self.group)
         if self.rank == 0:
-            try:
-                if self._seg_path:
-                    os.unlink(self._seg_path)
-            except OSError:
-                pass
-        self._seg_path = name
+            os.unlink(name)                                        # the mappings keep the segment alive
         return self._seg
+
+    def _release_segment(self):
+        if self._seg is not None and self._seg_registered and self.device.type == "cuda":
+            torch.cuda.synchronize()
+            torch.cuda.cudart().cudaHostUnregister(self._seg.data_ptr())
+        self._seg = None; self._seg_registered = False; self._layout = None
+
+    def close(self):
+        """Releases the shared host segment (unregisters it before the mapping goes away)."""
+        self._release_segment()
+
+    def __del__(self):
+        try:
+            self._release_segment()
+        except Exception:
+            pass
 
     # -- mesh assembly: duplicates on the faces between slabs are resolved against the LOWER neighbour by MC edge key (the copy
     #    of the lowest subdomain wins, as in the single-GPU weld), global vertex ids are rank-major, and every rank writes its own

@@ -38,6 +38,7 @@ def main():
             good = m["keys_equal"] and m["triangles_equal"] and m["n_not_bitexact"] == 0
             print(f"[{name}] world={world} cuts={res['plan'].cuts} axis={res['plan'].axis} recv={res['recv_particles']} of {len(p_all)} -> {m}", flush=True)
             ok &= bool(good)
+        runner.close()
         ctx.close()
         dist.barrier()
     flag = torch.tensor([1 if ok else 0], device="cuda")

@@ -256,6 +256,7 @@ def main():
         if rank == 0:
             v, t = runner.gathered_mesh(r["nv_global"], r["nt_global"])
             K = r["keys_global"].to(dev)
+            runner.close()
             ctx.close()
             gv, gt = torch.from_numpy(v).to(dev), torch.from_numpy(t.astype(np.int64)).to(dev)
             gvc, gtc, gkc = canonicalize(gv, gt, K)
@@ -274,6 +275,7 @@ def main():
             if args.out:
                 json.dump(res, open(args.out, "w"), indent=1)
         else:
+            runner.close()
             ctx.close()
         dist.barrier()
         dist.destroy_process_group()
