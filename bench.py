@@ -227,6 +227,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS), help="BASELINE config (default cfg4 = the metric's 50 M dam break)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sph-normals", action="store_true", help="also compute SPH normals at the mesh vertices (cfg-5; sph_interpolation.rs:82-133)")
     ap.add_argument("--runner-protocol", default="two_call", choices=["two_call", "callback"],
                     help="multi-GPU only: how the global subdomain maximum reaches the library (see distributed.Runner)")
     ap.add_argument("--levelset-variant", type=int, default=2, choices=[0, 1, 2],
@@ -256,6 +257,8 @@ def main():
     from splashsurf_b200 import distributed as ssd
     ctx = ss.Context(local_rank)
     ctx.set_levelset_variant(args.levelset_variant)
+    if args.sph_normals:
+        ss._check(ctx._L, ctx._L.ss_context_set_compute_sph_normals(ctx._h, 1))
     kw = dict(RECON_KW)
     if WORKLOADS.get(args.workload):
         kw.update(WORKLOADS[args.workload][1])
@@ -265,6 +268,7 @@ def main():
     p_all, desc = make_cloud(args.particles, args.workload)
     n_total = len(p_all)
     runner = ssd.Runner(ctx, params, world, rank, local_rank, protocol=args.runner_protocol)
+    runner.ctx_normals = bool(args.sph_normals)
     p_local = runner.take_local(p_all)
     del p_all
     host_in = torch.from_numpy(p_local).pin_memory()
@@ -377,7 +381,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": dict(workload_config(args, desc, n_total, kw, f"subdomain slabs x{world}" if world > 1 else "single GPU"),
-                               levelset_variant=int(args.levelset_variant),
+                               levelset_variant=int(args.levelset_variant), sph_normals=bool(args.sph_normals),
                                l2="inputs (600 MB) and tiles (GBs) exceed the 126 MB L2; no flush needed"),
                 "mesh": {"vertices": int(nv_g if nv_g is not None else nv), "triangles": int(nt_g if nt_g is not None else nt), "subdomains": int(n_sub)},
                 "wall_ms_per_step": wall_ms_max / args.steps, "step_ms_rank0": step_ms, "stage_ms_last_step": stage,

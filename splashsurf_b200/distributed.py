@@ -208,6 +208,7 @@ class Runner:
         self._out_v = self._out_t = None
         self._seg = None; self._seg_path = None; self._seg_gen = 0; self._seg_registered = False; self._layout = None
         self.want_keys = False           # also publish the MC edge keys of the assembled vertices (parity tools)
+        self.ctx_normals = False         # set by the caller when ss_context_set_compute_sph_normals is on: normals join the assembled mesh
         self.balance_feedback = True     # slab cuts learn from the measured per-rank time of earlier frames
         self._layer_scale = None; self._layer_key = None
         # `device` is only overridden by the tests that drive the runner over gloo with the CPU executor of the CUDA sources
@@ -387,10 +388,11 @@ class Runner:
             t_r = status[1:]
             busy = [r for r in range(world) if plan.own(r)[1] > plan.own(r)[0]]
             mean = float(np.mean([t_r[r] for r in busy])) if busy else 0.0
-            if mean > 0:
+            # adapt only while the slowest rank is more than 4 % above the mean: a settled plan keeps its buffers (no re-allocation)
+            if mean > 0 and max(t_r[r] for r in busy) > 1.04 * mean:
                 for r in busy:
                     a, bnd = plan.own(r)
-                    self._layer_scale[a:bnd] *= float(np.clip((t_r[r] / mean) ** 0.7, 0.7, 1.4))
+                    self._layer_scale[a:bnd] *= float(np.clip(t_r[r] / mean, 0.6, 1.6))
                 self._layer_scale = np.clip(self._layer_scale / self._layer_scale.mean(), 0.2, 5.0)
         try:
             t_ev[2].record()
@@ -545,9 +547,13 @@ class Runner:
         tg = gid[t.to(torch.int64).view(-1)].to(torch.int32) if nt else torch.empty(0, dtype=torch.int32, device=dev)
         vk = v[keep].contiguous()
         want_keys = self.want_keys
-        nbytes = nvg * 12 + ntg * 12 + (nvg * 8 if want_keys else 0)
+        nptr = L.ss_surface_device_normals(s)                                     # SPH normals travel with the vertices when they were computed
+        has_n = torch.tensor([1 if (nptr or nv == 0) else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(has_n, op=dist.ReduceOp.MIN, group=self.group)
+        has_n = bool(int(has_n.item())) and bool(self.ctx_normals)
+        nbytes = nvg * 12 + ntg * 12 + (nvg * 8 if want_keys else 0) + 8 + (nvg * 12 if has_n else 0)
         seg = self._host_segment(nbytes + 64)
-        self._layout = (nvg, ntg, want_keys)
+        self._layout = (nvg, ntg, want_keys, has_n)
         sv = seg[:nvg * 12].view(torch.float32)
         st = seg[nvg * 12:nvg * 12 + ntg * 12].view(torch.int32)
         if dev.type == "cuda":
@@ -556,6 +562,10 @@ class Runner:
             if want_keys:
                 base = (nvg * 12 + ntg * 12 + 7) // 8 * 8
                 seg[base:base + nvg * 8].view(torch.int64)[voff[rank]:voff[rank + 1]].copy_(k[keep], non_blocking=True)
+            if has_n:
+                nbase = ((nvg * 12 + ntg * 12 + 7) // 8 * 8) + (nvg * 8 if want_keys else 0)
+                nk = _view(nptr, (nv, 3), "<f4", dev)[keep].contiguous() if nv else torch.empty((0, 3), dtype=torch.float32, device=dev)
+                seg[nbase:nbase + nvg * 12].view(torch.float32)[voff[rank] * 3:voff[rank + 1] * 3].copy_(nk.view(-1), non_blocking=True)
             _sync(dev)
             dist.barrier(group=self.group)                                        # every part has landed in the shared segment
         else:
@@ -577,7 +587,7 @@ class Runner:
                 sk8 = seg[base:base + nvg * 8].view(torch.int64)
                 for q in range(world):
                     sk8[voff[q]:voff[q + 1]] = gk[q][:nkeeps[q]]
-        res = {"d2h_bytes": nkeep * 12 + nt * 12, "nv_global": nvg if rank == 0 else None, "nt_global": ntg if rank == 0 else None,
+        res = {"d2h_bytes": nkeep * 12 + nt * 12 + (nkeep * 12 if has_n else 0), "has_normals": has_n, "nv_global": nvg if rank == 0 else None, "nt_global": ntg if rank == 0 else None,
                "nv_total": nvg, "nt_total": ntg}
         if want_keys and rank == 0:
             base = (nvg * 12 + ntg * 12 + 7) // 8 * 8
