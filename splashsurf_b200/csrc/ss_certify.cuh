@@ -187,9 +187,12 @@ __global__ void k_wstate_reduce(const uint8_t *__restrict__ wstate, uint32_t nbr
 // inside for the reference too; failing to certify only costs time.  Results are therefore identical by construction.
 #include "ss_sm100.cuh"
 
-#define SS_CW_WARPS 4                  // bricks in flight per CTA (4 x 9.8 KB of static shared memory)
-#define SS_CW_THREADS (SS_CW_WARPS * 32)
-#define SS_CW_CAP 384                  // candidates staged per brick (bulk fluid at h = 4 r: 216 for c = 0.5 r, 373 for c = 0.45 r)
+// two instantiations: up to 3 candidate bins per axis (h <= 8 cells; bulk fluid at h = 4 r, c = 0.5 r: 216 candidates) and wider
+// reaches (c = 0.45 r: 343 .. 512 candidates, depending on how the 4.44-cell lattice falls into the 32-cell reach)
+#define SS_CW_CAP_S 384                // candidates staged per brick, small variant: 4 bricks in flight per CTA (4 x 9.8 KB)
+#define SS_CW_WARPS_S 4
+#define SS_CW_CAP_L 576                // large variant: 3 bricks in flight per CTA (3 x 13.1 KB)
+#define SS_CW_WARPS_L 3
 #define SS_CW_MAXRUNS 32               // candidate runs per brick: one per lane
 
 struct SsCwArgs {
@@ -209,10 +212,11 @@ struct SsCwArgs {
 #define SS_CW_PAIRS 24                 // capacity of one sub-box's ring-0 list in candidate PAIRS (bulk fluid: ~13); extra candidates are dropped (sound)
 // one list entry = two candidates, component-interleaved so that every packed operand is an aligned 64-bit register pair
 struct __align__(16) SsCwPair { float x[2], y[2], z[2], v[2]; };
+template <int CAP>
 struct __align__(16) SsCwSlice {
-    float4 rec[SS_CW_CAP];             // staged candidate records (bulk-copy destination)
+    float4 rec[CAP];                   // staged candidate records (bulk-copy destination)
     SsCwPair list[4][SS_CW_PAIRS];     // ring-0 lists of the four sub-boxes of one x-half of the brick
-    uint16_t cidx[SS_CW_CAP];          // candidates within ring 0 of the whole brick (pre-filter)
+    uint16_t cidx[CAP];                // candidates within ring 0 of the whole brick (pre-filter)
     unsigned long long mbar;
     unsigned long long pad_;
 };
@@ -276,13 +280,13 @@ __device__ __forceinline__ void ss_cw_fold_pairs(const SsCwPoint &Q, float ngzA,
     }
 }
 
-template <bool GLOBAL, bool COUNT>
-__global__ void __launch_bounds__(SS_CW_THREADS, 5)
+template <bool GLOBAL, bool COUNT, int CAP, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 20 / WARPS)
 k_certify_warp(SsDev P, SsCwArgs A) {
-    __shared__ SsCwSlice s_slice[SS_CW_WARPS];
+    __shared__ SsCwSlice<CAP> s_slice[WARPS];
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    SsCwSlice &S = s_slice[wib];
-    const uint32_t work = blockIdx.x * SS_CW_WARPS + wib;
+    SsCwSlice<CAP> &S = s_slice[wib];
+    const uint32_t work = blockIdx.x * WARPS + wib;
     if (work >= A.n_work) return;
     if (lane == 0) { ss_mbar_init(&S.mbar, 1); ss_mbar_fence_init(); }
     const int nb = P.nb;
@@ -319,7 +323,7 @@ k_certify_warp(SsDev P, SsCwArgs A) {
     const int C = (int)__shfl_sync(0xffffffffu, incl, 31);
     if (C == 0) return;                                         // tile is pre-zeroed: phi = 0 exactly (wstate stays 0)
 
-    if (C > SS_CW_CAP) {
+    if (C > CAP) {
         // oversized brick: everything goes to the exact pass (k_levelset's oversized path honours the per-box flags)
         if (lane < SS_LS_WARPS) {
             const int i0 = bx * 8 + (lane >> 2) * 2, j0 = by * 8 + ((lane >> 1) & 1) * 4, k0 = bz * 8 + (lane & 1) * 4;

@@ -16,9 +16,9 @@
 // Bricks this kernel cannot take (more candidates than its slice holds) are appended to a fallback list for k_levelset.
 #pragma once
 
-#define SS_XW_WARPS 3                  // bricks in flight per CTA (3 x 12.3 KB of static shared memory)
+#define SS_XW_WARPS 3                  // bricks in flight per CTA (3 x 13.5 KB of static shared memory)
 #define SS_XW_THREADS (SS_XW_WARPS * 32)
-#define SS_XW_CAP 448                  // candidates staged per brick
+#define SS_XW_CAP 512                  // candidates staged per brick
 #define SS_XW_LIST 224                 // candidates within the support of one 4x4x4 sub-box
 
 struct SsXwArgs {
@@ -36,16 +36,27 @@ struct SsXwArgs {
     unsigned long long *pairs;         // work counter (in-support evaluations), only with COUNT
 };
 
-struct __align__(16) SsXwSlice {
-    float4 rec[SS_XW_CAP];
-    unsigned long long key[512];       // (particle index << 32) | slot, sorted ascending
-    uint16_t ks[SS_XW_CAP];            // AVX-remainder split per slot
-    uint16_t list[SS_XW_LIST];         // slots within the support of the current sub-box, ascending particle index
+template <int CAP, int LIST, int KEYS>
+struct __align__(16) SsXwSliceT {
+    float4 rec[CAP];
+    unsigned long long key[KEYS];      // (particle index << 32) | slot, sorted ascending
+    uint16_t ks[CAP];                  // AVX-remainder split per slot
+    uint16_t list[LIST];               // slots within the support of the current sub-box, ascending particle index
     unsigned long long mbar;
     unsigned long long pad_;
 };
+typedef SsXwSliceT<SS_XW_CAP, SS_XW_LIST, 512> SsXwSlice;
+// Dense clusters (overlapping droplets, cfg-5): the same kernel with one warp per CTA and a 108 KB slice of dynamic shared memory
+#define SS_XW_BIG_CAP 4096
+#define SS_XW_BIG_LIST 2048
+typedef SsXwSliceT<SS_XW_BIG_CAP, SS_XW_BIG_LIST, SS_XW_BIG_CAP> SsXwSliceBig;
+#ifdef SS_HOST_EMUL
+static thread_local __align__(16) unsigned char ss_dyn_smem[sizeof(SsXwSliceBig)];
+#else
+extern __shared__ __align__(16) unsigned char ss_dyn_smem[];
+#endif
 
-// warp-synchronous bitonic sort of n (power of two, <= 512) keys in shared memory
+// warp-synchronous bitonic sort of n (power of two) keys in shared memory
 __device__ __forceinline__ void ss_warp_bitonic(unsigned long long *keys, int n, int lane) {
     for (int k = 2; k <= n; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
@@ -82,14 +93,8 @@ __device__ __forceinline__ ss_f2 ss_kernel_avx2(const SsDev &P, float ra, float 
     return ss_pack(qa <= 0.5f ? ia : oa, qb <= 0.5f ? ib : ob);
 }
 
-template <bool GLOBAL, bool COUNT>
-__global__ void __launch_bounds__(SS_XW_THREADS, 6)
-k_exact_warp(SsDev P, SsXwArgs A) {
-    __shared__ SsXwSlice s_slice[SS_XW_WARPS];
-    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    SsXwSlice &S = s_slice[wib];
-    const uint32_t work = blockIdx.x * SS_XW_WARPS + wib;
-    if (work >= A.n_bricks) return;
+template <bool GLOBAL, bool COUNT, int CAP, int LIST, typename SLICE>
+__device__ __forceinline__ void ss_exact_brick(const SsDev &P, const SsXwArgs &A, SLICE &S, const uint32_t work, const int lane) {
     if (lane == 0) { ss_mbar_init(&S.mbar, 1); ss_mbar_fence_init(); }
     const int nb = P.nb;
     const uint32_t brick_lin = A.bricks[work];
@@ -147,7 +152,7 @@ k_exact_warp(SsDev P, SsXwArgs A) {
         }
         return;
     }
-    if (C > SS_XW_CAP) {
+    if (C > CAP) {
         if (lane == 0) A.fallback[1 + atomicAdd(&A.fallback[0], 1u)] = brick_lin;
         return;
     }
@@ -207,10 +212,10 @@ k_exact_warp(SsDev P, SsXwArgs A) {
             }
             const uint32_t mword = __ballot_sync(0xffffffffu, keep);
             const int pos = nlist + __popc(mword & ((1u << lane) - 1u));
-            if (keep && pos < SS_XW_LIST) S.list[pos] = (uint16_t)slot;
+            if (keep && pos < LIST) S.list[pos] = (uint16_t)slot;
             nlist += __popc(mword);
         }
-        if (nlist > SS_XW_LIST) overflow = true;
+        if (nlist > LIST) overflow = true;
         __syncwarp();
         if (overflow) {
             // pathological clustering: leave the whole brick to k_levelset (its flags are untouched; values written so far are exact)
@@ -273,4 +278,22 @@ k_exact_warp(SsDev P, SsXwArgs A) {
         for (int o = 16; o > 0; o >>= 1) np_ += __shfl_xor_sync(0xffffffffu, np_, o);
         if (lane == 0 && np_) atomicAdd(A.pairs, np_);
     }
+}
+
+template <bool GLOBAL, bool COUNT>
+__global__ void __launch_bounds__(SS_XW_THREADS, 5)
+k_exact_warp(SsDev P, SsXwArgs A) {
+    __shared__ SsXwSlice s_slice[SS_XW_WARPS];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t work = blockIdx.x * SS_XW_WARPS + wib;
+    if (work >= A.n_bricks) return;
+    ss_exact_brick<GLOBAL, COUNT, SS_XW_CAP, SS_XW_LIST>(P, A, s_slice[wib], work, lane);
+}
+
+// one warp per CTA, slice in dynamic shared memory (sizeof(SsXwSliceBig) bytes): bricks with up to 4096 candidates
+template <bool GLOBAL, bool COUNT>
+__global__ void __launch_bounds__(32, 2)
+k_exact_warp_big(SsDev P, SsXwArgs A) {
+    if (blockIdx.x >= A.n_bricks) return;
+    ss_exact_brick<GLOBAL, COUNT, SS_XW_BIG_CAP, SS_XW_BIG_LIST>(P, A, *reinterpret_cast<SsXwSliceBig *>(ss_dyn_smem), blockIdx.x, (int)(threadIdx.x & 31));
 }

@@ -29,6 +29,10 @@ struct SsCudaError { cudaError_t e; const char *what; const char *file; int line
 #define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) throw SsCudaError{ _e, #call, __FILE__, __LINE__ }; } while (0)
 
 // ------------------------------------------------------------------ device buffers ----
+// Growth slack of the pooled buffers in eighths of the request: 1 (12.5 %) for whole-domain runs; partitioned (multi-GPU) runs use 4
+// (50 %), because the slab plan -- and with it every per-rank size -- moves a little from frame to frame while it balances, and
+// re-allocating the scratch costs far more than the memory it saves (each rank holds 1/N of the data anyway).
+static int g_devbuf_slack_eighths = 1;
 struct DevBuf {
     void *p = nullptr; size_t cap = 0;
     template <typename T> T *as() const { return (T *)p; }
@@ -42,7 +46,7 @@ struct DevBuf {
         if (bytes <= cap) return;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
-        size_t want = bytes + bytes / 8 + 256;
+        size_t want = bytes + (bytes / 8) * (size_t)g_devbuf_slack_eighths + 256;
 #endif
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) { p = nullptr; throw SsCudaError{ e, "cudaMalloc", __FILE__, __LINE__ }; }
@@ -92,8 +96,9 @@ struct ss_context {
     // reusable scratch
     DevBuf xyz, xyz_f, filt_flag, filt_flag32, filt_off, aabb, cnt, off, key_a, key_b, val_a, val_b, cid, cub_tmp,
         sub_flat, sub_off, sub_sparse, sub_owned, gkey_a, gkey_b, gval_a, gval_b, flags, scan, spos, rho, tab_a, tab_b, rec, ksplit, batch_subs, tiles, vcnt,
-        tcnt, vmask, voff, vblk_off, tblk_off, tile_tab, brick_rng, bstate, flag_ls, off_ls, list_ls, flag_mc, flag_fix, off_mc, off_fix, list_mc, list_fix, wflag, wstate, desc_ls, dflag, doff, dlist, fallback, pack_cnt, pack_off, brick_seen, fix_list, nflag, bkeys_a, bkeys_b, bids_a, bids_b, bcount, remap, keep, newid, err, pairs;
+        tcnt, vmask, voff, vblk_off, tblk_off, tile_tab, brick_rng, bstate, flag_ls, off_ls, list_ls, flag_mc, flag_fix, off_mc, off_fix, list_mc, list_fix, wflag, wstate, desc_ls, dflag, doff, dlist, fallback, fallback2, pack_cnt, pack_off, brick_seen, fix_list, nflag, bkeys_a, bkeys_b, bids_a, bids_b, bcount, remap, keep, newid, err, pairs;
     uint64_t launches = 0;
+    int big_attr_set = 0;            // dynamic shared memory opt-in of k_exact_warp_big done
     uint64_t pack_n = 0; uint32_t pack_world = 0;   // ss_partition_pack_f32: count phase the scatter phase must match
     // result buffers handed to surfaces and returned by ss_surface_free (avoids cudaMalloc/cudaFree per frame,
     // the analogue of the reference's ReconstructionWorkspace, workspace.rs:12-79)
@@ -178,6 +183,10 @@ static inline unsigned nblk(uint64_t n, unsigned t) { return (unsigned)((n + t -
 #define SS_LAUNCH(kern, grid, block, stream, ...) kern<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
 #endif
 #define LAUNCH(ctx, kern, grid, block, ...) do { SS_LAUNCH(kern, grid, block, (ctx)->stream, __VA_ARGS__); (ctx)->launches++; } while (0)
+#ifndef SS_LAUNCH_DYN
+#define SS_LAUNCH_DYN(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+#define LAUNCH_DYN(ctx, kern, grid, block, smem, ...) do { SS_LAUNCH_DYN(kern, grid, block, smem, (ctx)->stream, __VA_ARGS__); (ctx)->launches++; } while (0)
 
 static void cub_sort_pairs(ss_context *c, const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout,
                            uint32_t n, int end_bit) {
@@ -244,7 +253,7 @@ extern "C" void ss_context_destroy(ss_context *c) {
     DevBuf *bufs[] = { &c->xyz, &c->xyz_f, &c->filt_flag, &c->filt_flag32, &c->filt_off, &c->aabb, &c->cnt, &c->off, &c->key_a, &c->key_b,
                        &c->val_a, &c->val_b, &c->cid, &c->cub_tmp, &c->sub_flat, &c->sub_off, &c->sub_sparse, &c->sub_owned, &c->gkey_a, &c->gkey_b, &c->gval_a, &c->gval_b, &c->flags, &c->scan,
                        &c->spos, &c->rho, &c->tab_a, &c->tab_b, &c->rec, &c->ksplit, &c->batch_subs, &c->tiles, &c->vcnt, &c->tcnt,
-                       &c->vmask, &c->voff, &c->vblk_off, &c->tblk_off, &c->tile_tab, &c->brick_rng, &c->bstate, &c->flag_ls, &c->off_ls, &c->list_ls, &c->flag_mc, &c->flag_fix, &c->off_mc, &c->off_fix, &c->list_mc, &c->list_fix, &c->wflag, &c->wstate, &c->desc_ls, &c->dflag, &c->doff, &c->dlist, &c->fallback, &c->pack_cnt, &c->pack_off, &c->brick_seen, &c->fix_list, &c->nflag, &c->bkeys_a, &c->bkeys_b, &c->bids_a, &c->bids_b, &c->bcount, &c->remap, &c->keep, &c->newid,
+                       &c->vmask, &c->voff, &c->vblk_off, &c->tblk_off, &c->tile_tab, &c->brick_rng, &c->bstate, &c->flag_ls, &c->off_ls, &c->list_ls, &c->flag_mc, &c->flag_fix, &c->off_mc, &c->off_fix, &c->list_mc, &c->list_fix, &c->wflag, &c->wstate, &c->desc_ls, &c->dflag, &c->doff, &c->dlist, &c->fallback, &c->fallback2, &c->pack_cnt, &c->pack_off, &c->brick_seen, &c->fix_list, &c->nflag, &c->bkeys_a, &c->bkeys_b, &c->bids_a, &c->bids_b, &c->bcount, &c->remap, &c->keep, &c->newid,
                        &c->err, &c->pairs, &c->o_verts, &c->o_tris, &c->o_vkeys, &c->o_rho, &c->o_verts2, &c->o_vkeys2, &c->o_normals };
     for (DevBuf *b : bufs) b->release();
     c->post.release_all();
@@ -554,10 +563,34 @@ static void launch_exact(ss_context *c, const SsDev &D, const SsLsArgs &F, uint3
     CK(cudaMemcpyAsync(&n_fb, c->fallback.p, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (n_fb) {
-        SsLsArgs G = F;
-        G.fix_bricks = c->fallback.as<uint32_t>() + 1;
-        launch_levelset(c, dim3(n_fb), D, G, count, global_mode);
+        // dense clusters: the same kernel with a 108 KB slice per warp (up to 4096 candidates per brick)
+        c->fallback2.ensure(((size_t)n_fb + 1) * 4);
+        CK(cudaMemsetAsync(c->fallback2.p, 0, 4, st));
+        SsXwArgs Y = X;
+        Y.bricks = c->fallback.as<uint32_t>() + 1; Y.n_bricks = n_fb; Y.fallback = c->fallback2.as<uint32_t>();
+        const size_t dyn = sizeof(SsXwSliceBig);
+        if (!c->big_attr_set) {
+#ifndef SS_HOST_EMUL
+            CK(cudaFuncSetAttribute(k_exact_warp_big<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            CK(cudaFuncSetAttribute(k_exact_warp_big<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            CK(cudaFuncSetAttribute(k_exact_warp_big<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            CK(cudaFuncSetAttribute(k_exact_warp_big<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+#endif
+            c->big_attr_set = 1;
+        }
+        if (global_mode) { if (count) LAUNCH_DYN(c, (k_exact_warp_big<true, true>), n_fb, 32, dyn, D, Y); else LAUNCH_DYN(c, (k_exact_warp_big<true, false>), n_fb, 32, dyn, D, Y); }
+        else { if (count) LAUNCH_DYN(c, (k_exact_warp_big<false, true>), n_fb, 32, dyn, D, Y); else LAUNCH_DYN(c, (k_exact_warp_big<false, false>), n_fb, 32, dyn, D, Y); }
         ++ls_launches;
+        uint32_t n_fb2 = 0;
+        CK(cudaMemcpyAsync(&n_fb2, c->fallback2.p, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (n_fb2) {
+            // beyond that: k_levelset's O(C^2) selection path (extreme clustering only)
+            SsLsArgs G = F;
+            G.fix_bricks = c->fallback2.as<uint32_t>() + 1;
+            launch_levelset(c, dim3(n_fb2), D, G, count, global_mode);
+            ++ls_launches;
+        }
     }
 }
 
@@ -597,9 +630,12 @@ static int levelset_batch(ss_context *c, const SsDev &D, uint32_t nbatch, unsign
             const double ih2 = 1.0 / ((double)D.h * (double)D.h);
             W.g1 = (float)((double)SS_G1 * ih2); W.g2 = (float)((double)SS_G2 * ih2 * ih2); W.g3 = (float)((double)SS_G3 * ih2 * ih2 * ih2);
             W.r0sq = 0.3025f * D.h2; W.r1sq = 0.58f * D.h2;
-            const unsigned grid_cw = (n_work + SS_CW_WARPS - 1) / SS_CW_WARPS;
-            if (global_mode) { if (c->count_pairs) LAUNCH(c, (k_certify_warp<true, true>), grid_cw, SS_CW_THREADS, D, W); else LAUNCH(c, (k_certify_warp<true, false>), grid_cw, SS_CW_THREADS, D, W); }
-            else { if (c->count_pairs) LAUNCH(c, (k_certify_warp<false, true>), grid_cw, SS_CW_THREADS, D, W); else LAUNCH(c, (k_certify_warp<false, false>), grid_cw, SS_CW_THREADS, D, W); }
+            const bool cw_small = certify_runs <= 16;            // at most 4 candidate bins per axis (3 + the extension plane)
+#define SS_CW_GO(G_, C_) do { if (cw_small) LAUNCH(c, (k_certify_warp<G_, C_, SS_CW_CAP_S, SS_CW_WARPS_S>), (n_work + SS_CW_WARPS_S - 1) / SS_CW_WARPS_S, SS_CW_WARPS_S * 32, D, W); \
+                                 else LAUNCH(c, (k_certify_warp<G_, C_, SS_CW_CAP_L, SS_CW_WARPS_L>), (n_work + SS_CW_WARPS_L - 1) / SS_CW_WARPS_L, SS_CW_WARPS_L * 32, D, W); } while (0)
+            if (global_mode) { if (c->count_pairs) SS_CW_GO(true, true); else SS_CW_GO(true, false); }
+            else { if (c->count_pairs) SS_CW_GO(false, true); else SS_CW_GO(false, false); }
+#undef SS_CW_GO
         } else if (global_mode) LAUNCH(c, k_certify<true>, n_work, SS_LS_THREADS, D, CA);
         else LAUNCH(c, k_certify<false>, n_work, SS_LS_THREADS, D, CA);
         ++ls_launches;
@@ -1289,6 +1325,7 @@ static int reconstruct_partition_impl(ss_context *c, const float *xyz, uint64_t 
         s->device = c->device; s->n_in = n_in;
         c->launches = 0;
         Prepared P;
+        g_devbuf_slack_eighths = 4;
         rc = prepare_particles(c, xyz, n_in, p, P, nullptr, grid);
         if (rc) { ss_surface_free(s); return rc; }
         s->n = P.n; s->grid = P.grid; s->used_decomposition = 1;

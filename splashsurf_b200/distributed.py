@@ -375,7 +375,8 @@ class Runner:
         status = torch.zeros(1 + world, dtype=torch.float64, device=dev)       # [worst return code, library ms of every rank]
         status[0] = float(int(rc) if not failure else 255)
         if not rc and not failure:
-            status[1 + rank] = float(self.ctx.timings(s)["total_device"])
+            tm = self.ctx.timings(s)      # kernel time of the stages (event-bracketed; allocation stalls of a changing plan stay out)
+            status[1 + rank] = float(sum(tm[k] for k in ("decomposition", "density", "binning", "levelset", "marching_cubes", "stitching")))
         dist.all_reduce(status, op=dist.ReduceOp.MAX, group=self.group)
         status = status.cpu().numpy()
         if failure:

@@ -290,6 +290,7 @@ static void launch(dim3 grid, dim3 block, void (*kernel)(P...), A... args) {
 }  // namespace emul
 
 #define SS_LAUNCH(kern, grid, block, stream, ...) emul::launch(dim3(grid), dim3(block), kern, __VA_ARGS__)
+#define SS_LAUNCH_DYN(kern, grid, block, smem, stream, ...) emul::launch(dim3(grid), dim3(block), kern, __VA_ARGS__)   // dynamic shared memory: a static worker-local array (ss_exact.cuh)
 
 // ------------------------------------------------------------------ device intrinsics ----
 static inline void __syncthreads() { emul::collective(emul::BLOCK_WAIT, emul::OP_BAR, 0, 0, 0); }

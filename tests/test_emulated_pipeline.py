@@ -140,10 +140,11 @@ def test_emulated_warp_per_brick_certification(emu, oracle_mod, name, gen, kw, o
     _check_bit_exact(emu, oracle_mod, gen(), kw, variant=2, **opts)
 
 
-@pytest.mark.parametrize("n,sigma", [(600, 0.004), (400, 0.02), (260, 0.01)], ids=["oversized_brick", "list_overflow", "dense_cluster"])
+@pytest.mark.parametrize("n,sigma", [(600, 0.004), (400, 0.02), (260, 0.01), (4500, 0.004)], ids=["oversized_brick", "list_overflow", "dense_cluster", "extreme_cluster"])
 def test_emulated_warp_per_brick_clustered_particles(emu, oracle_mod, n, sigma):
-    """Variant 2 on pathological clustering: more candidates than a warp's slice holds (whole brick falls back to k_levelset),
-    more candidates in the support of one sub-box than its list holds, and a dense cluster that still fits."""
+    """Variant 2 on pathological clustering: more candidates than a warp's slice holds (brick goes to the 4096-candidate variant of
+    the exact kernel), more candidates in the support of one sub-box than its list holds, a dense cluster that still fits, and
+    more than 4096 candidates around one brick (last resort: k_levelset's selection path)."""
     kw = dict(BASE, cube_size=0.5, subdomain_grid_auto_disable=False)
     _check_bit_exact(emu, oracle_mod, np.random.default_rng(n).normal(0, sigma, (n, 3)).astype(np.float32), kw, variant=2)
 

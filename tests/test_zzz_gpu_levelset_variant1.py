@@ -43,7 +43,7 @@ def test_cuda_split_certification_bit_exact_vs_oracle(ss, oracle_mod, name, gen,
     assert np.array_equal(g.mesh.vertices, g0.mesh.vertices) and np.array_equal(g.mesh.triangles, g0.mesh.triangles)
 
 
-@pytest.mark.parametrize("n,sigma", [(3000, 0.004), (400, 0.02), (260, 0.01)], ids=["oversized_brick", "list_overflow", "dense_cluster"])
+@pytest.mark.parametrize("n,sigma", [(3000, 0.004), (400, 0.02), (260, 0.01), (6000, 0.004)], ids=["oversized_brick", "list_overflow", "dense_cluster", "extreme_cluster"])
 def test_cuda_warp_per_brick_clustered_particles(ss, oracle_mod, n, sigma):
     """Variant 2 on pathological clustering (fallback of whole bricks to k_levelset, sub-box list overflow)."""
     kw = dict(BASE, cube_size=0.5, subdomain_grid_auto_disable=False)

@@ -81,6 +81,17 @@ if has ncu2; then
       python bench.py --workload cfg3 --steps 1 --warmup 1 --no-cpu-baseline --levelset-variant 2 > gpurun_out/ncu_full_v2_$TAG.log 2>&1
   ls -la gpurun_out/prof_variant2_$TAG.ncu-rep
 fi
+if has cfg5; then
+  echo "== cfg-5 (200 M splash, c = 0.45 r, SPH normals) on one GPU"
+  timeout 1200 python bench.py --workload cfg5 --sph-normals --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_cfg5_1gpu_$TAG.json 2> gpurun_out/bench_cfg5_1gpu_$TAG.err
+  cut -c1-1800 gpurun_out/bench_cfg5_1gpu_$TAG.json; tail -3 gpurun_out/bench_cfg5_1gpu_$TAG.err | cut -c1-300
+fi
+if has ncu5; then
+  echo "== ncu --set full on cfg-5: k_certify_warp, k_exact_warp, k_exact_warp_big, k_sph_normals"
+  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'k_certify_warp|k_exact_warp|k_sph_normals' -c 5 -o gpurun_out/prof_cfg5_$TAG -f \
+      python bench.py --workload cfg5 --sph-normals --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_cfg5_$TAG.log 2>&1
+  ls -la gpurun_out/prof_cfg5_$TAG.ncu-rep
+fi
 if has post; then
   echo "== post-processing entries"; timeout 300 python tools/bench_postprocess.py --particles 10000000 > gpurun_out/bench_postprocess_$TAG.json 2>&1; tail -c 800 gpurun_out/bench_postprocess_$TAG.json
 fi
