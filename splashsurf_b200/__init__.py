@@ -113,6 +113,7 @@ def _bind(L):
     L.ss_context_set_tile_batch.argtypes = [vp, C.c_uint32]
     L.ss_context_set_levelset_exact_everywhere.argtypes = [vp, C.c_int]
     L.ss_context_set_levelset_variant.argtypes = [vp, C.c_int]
+    L.ss_context_set_density_variant.argtypes = [vp, C.c_int]
     L.ss_context_set_count_pairs.argtypes = [vp, C.c_int]
     L.ss_context_set_compute_sph_normals.argtypes = [vp, C.c_int]
     L.ss_surface_copy_normals.argtypes = [vp, vp]
@@ -334,8 +335,13 @@ class Context:
         _check(self._L, self._L.ss_context_set_levelset_exact_everywhere(self._h, int(bool(on))))
 
     def set_levelset_variant(self, variant: int):
-        """0: fused certify + exact level-set kernel (default); 1: separate certification kernel (same results)."""
+        """2 (default): warp-per-brick certification + exact kernels; 1: CTA-per-brick certification kernel; 0: fused kernel
+        (same results)."""
         _check(self._L, self._L.ss_context_set_levelset_variant(self._h, int(variant)))
+
+    def set_density_variant(self, variant: int):
+        """1 (default): cell-cooperative density kernel; 0: thread-per-particle kernel (same results)."""
+        _check(self._L, self._L.ss_context_set_density_variant(self._h, int(variant)))
 
     def set_count_pairs(self, on: bool):
         _check(self._L, self._L.ss_context_set_count_pairs(self._h, int(bool(on))))

@@ -234,17 +234,13 @@ __global__ void k_density_flags(SsDev P, uint32_t m, const uint32_t *__restrict_
     flag[e] = inside ? 1u : 0u;
 }
 
+// The ordered neighbour sum of ONE membership entry `e` (thread-serial): the per-particle routine of k_density and the
+// fallback of the cell-cooperative kernel (ss_density.cuh) for oversized cells.
 template <bool FILL>
-__global__ void __launch_bounds__(128)
-k_density(SsDev P, uint32_t m, const uint32_t *__restrict__ list, const uint32_t *__restrict__ list_off, const uint32_t *__restrict__ list_flag,
-          const uint32_t *__restrict__ key, const float4 *__restrict__ spos,
-          const uint32_t *__restrict__ sub_flat, const uint32_t *__restrict__ cstart, const uint32_t *__restrict__ cend,
-          float *__restrict__ rho, unsigned long long *__restrict__ nbr_count, const unsigned long long *__restrict__ nbr_off,
-          uint32_t *__restrict__ nbr_idx) {
-    // `list` holds the entries with a particle inside its subdomain (ascending); its length is list_off[m-1] + list_flag[m-1]
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= list_off[m - 1] + list_flag[m - 1]) return;
-    const uint32_t e = list[tid];
+__device__ __forceinline__ void ss_density_entry(const SsDev &P, const uint32_t e, const uint32_t *__restrict__ key, const float4 *__restrict__ spos,
+                                                 const uint32_t *__restrict__ sub_flat, const uint32_t *__restrict__ cstart, const uint32_t *__restrict__ cend,
+                                                 float *__restrict__ rho, unsigned long long *__restrict__ nbr_count,
+                                                 const unsigned long long *__restrict__ nbr_off, uint32_t *__restrict__ nbr_idx) {
     uint32_t k = key[e];
     uint32_t s = k / (uint32_t)P.ns_stride, cell = k - s * (uint32_t)P.ns_stride;
     float4 pi = spos[e];
@@ -291,6 +287,19 @@ k_density(SsDev P, uint32_t m, const uint32_t *__restrict__ list, const uint32_t
     for (int n = 0; n < nl; ++n) acc = __fadd_rn(acc, ss_kernel_scalar(P, __fsqrt_rn(d2list[n])));
     if (nbr_count) nbr_count[__float_as_uint(pi.w)] = ncount;
     rho[__float_as_uint(pi.w)] = __fmul_rn(acc, P.rest_mass);
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+k_density(SsDev P, uint32_t m, const uint32_t *__restrict__ list, const uint32_t *__restrict__ list_off, const uint32_t *__restrict__ list_flag,
+          const uint32_t *__restrict__ key, const float4 *__restrict__ spos,
+          const uint32_t *__restrict__ sub_flat, const uint32_t *__restrict__ cstart, const uint32_t *__restrict__ cend,
+          float *__restrict__ rho, unsigned long long *__restrict__ nbr_count, const unsigned long long *__restrict__ nbr_off,
+          uint32_t *__restrict__ nbr_idx) {
+    // `list` holds the entries with a particle inside its subdomain (ascending); its length is list_off[m-1] + list_flag[m-1]
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= list_off[m - 1] + list_flag[m - 1]) return;
+    ss_density_entry<FILL>(P, list[tid], key, spos, sub_flat, cstart, cend, rho, nbr_count, nbr_off, nbr_idx);
 }
 
 

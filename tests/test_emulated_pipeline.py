@@ -60,11 +60,12 @@ def _parity(oracle_mod, g, o, S=64):
     return oracle_mod.mesh_parity(g.mesh.vertices, g.mesh.triangles, g.vertex_edge_keys, o["vertices"], o["triangles"], o["vertex_keys"], S)
 
 
-def _check_bit_exact(emu, oracle_mod, p, kw, exact_everywhere=False, tile_batch=None, variant=0):
+def _check_bit_exact(emu, oracle_mod, p, kw, exact_everywhere=False, tile_batch=None, variant=0, density_variant=1):
     ctx = emu.Context()
     try:
         ctx.set_levelset_exact_everywhere(exact_everywhere)
         ctx.set_levelset_variant(variant)
+        ctx.set_density_variant(density_variant)
         if tile_batch:
             ctx.set_tile_batch(tile_batch)
         g = emu.reconstruct_surface(p, with_debug=True, context=ctx, **kw)
@@ -147,6 +148,26 @@ def test_emulated_warp_per_brick_clustered_particles(emu, oracle_mod, n, sigma):
     more than 4096 candidates around one brick (last resort: k_levelset's selection path)."""
     kw = dict(BASE, cube_size=0.5, subdomain_grid_auto_disable=False)
     _check_bit_exact(emu, oracle_mod, np.random.default_rng(n).normal(0, sigma, (n, 3)).astype(np.float32), kw, variant=2)
+
+
+@pytest.mark.parametrize("case", ["certify_default", "scalar_arithmetic", "clump_rounds_and_pool_overflow", "clump_oversized_cell", "clumps_in_a_cube"])
+def test_emulated_density_kernel_variants(emu, oracle_mod, case):
+    """Both density kernels (ss_density.cuh: one warp per h-cell, default; k_density: one thread per particle) against the oracle,
+    including the cell-cooperative kernel's escape routes: more than 16 particles of one cell (several rounds), a hit list that
+    does not fit the pool (thread-serial routine for that particle), more candidates than the slice holds (whole cell)."""
+    kw = dict(BASE, cube_size=0.5, subdomain_grid_auto_disable=False)
+    if case in ("certify_default", "scalar_arithmetic"):
+        _, gen, kw, _ = [s for s in SEEDED if s[0] == case][0]
+        p = gen()
+    elif case == "clump_rounds_and_pool_overflow":
+        p = np.random.default_rng(7).normal(0, 0.01, (251, 3)).astype(np.float32)      # ~31 particles per cell, ~250 hits each
+    elif case == "clump_oversized_cell":
+        p = np.random.default_rng(8).normal(0.05, 0.004, (420, 3)).astype(np.float32)  # 420 candidates in one cell
+    else:
+        rng = np.random.default_rng(9)
+        p = np.concatenate([_cube(9, 0.025, 311), rng.normal(0.2, 0.006, (90, 3)).astype(np.float32), rng.normal(0.33, 0.003, (40, 3)).astype(np.float32)])
+    for dv in (1, 0):
+        _check_bit_exact(emu, oracle_mod, p, kw, variant=2, density_variant=dv)
 
 
 def test_emulated_aabb_filter_and_edge_cases(emu, oracle_mod):

@@ -58,3 +58,31 @@ def test_cuda_warp_per_brick_clustered_particles(ss, oracle_mod, n, sigma):
     assert np.array_equal(g.particle_densities, o["particle_densities"])
     m = oracle_mod.mesh_parity(g.mesh.vertices, g.mesh.triangles, g.vertex_edge_keys, o["vertices"], o["triangles"], o["vertex_keys"], 64)
     assert m["keys_equal"] and m["triangles_equal"] and m["n_not_bitexact"] == 0, m
+
+
+@pytest.mark.parametrize("case", ["cube24", "splash_scalar", "dam_small", "clump_rounds_and_pool_overflow", "clump_oversized_cell"])
+def test_cuda_density_kernel_variants(ss, oracle_mod, case):
+    """Cell-cooperative density kernel (default, csrc/ss_density.cuh) and the thread-per-particle kernel: densities bit-equal to
+    the oracle and to each other, including the cooperative kernel's escape routes (rounds of 16 particles, pool overflow,
+    oversized cell)."""
+    from splashsurf_b200 import synthetic as syn
+    kw = dict(BASE, cube_size=0.5, subdomain_grid_auto_disable=False)
+    if case == "clump_rounds_and_pool_overflow":
+        p = np.random.default_rng(7).normal(0, 0.01, (251, 3)).astype(np.float32)
+    elif case == "clump_oversized_cell":
+        p = np.random.default_rng(8).normal(0.05, 0.004, (420, 3)).astype(np.float32)
+    else:
+        _, gen, kw = [c for c in CASES if c[0] == case][0]
+        p = gen(syn)
+    o = oracle_mod.reconstruct(p, **kw)
+    rho = []
+    for dv in (1, 0):
+        ctx = ss.Context()
+        try:
+            ctx.set_density_variant(dv)
+            g = ss.reconstruct_surface(p, with_debug=True, context=ctx, **kw)
+        finally:
+            ctx.close()
+        assert np.array_equal(g.particle_densities, o["particle_densities"]), dv
+        rho.append(g.particle_densities)
+    assert np.array_equal(rho[0], rho[1])
