@@ -46,8 +46,13 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index=0):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+    def __init__(self, gpu_index="0"):
+        self.rows, self.proc, self.gpu, self.first = [], None, gpu_index, 0
+
+    def mark(self):
+        """Start of the timed region: only samples taken from here on are reported (the process itself is started before the
+        warm-up, so that NVML's start-up on a multi-GPU box does not fall into the timed steps)."""
+        self.first = len(self.rows)
 
     def start(self):
         try:
@@ -71,7 +76,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in self.rows[self.first:]:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
@@ -281,11 +286,14 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident steps
+    # one nvidia-smi process (rank 0) watches every GPU of the job; started before the warm-up, read from the timed region on
+    sampler = ClockSampler(",".join(str(g) for g in range(world)) if world > 1 else str(local_rank))
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         res = runner.step(dev_in, copy_out=False)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark()
     dev_ms, ls_ms, launches, pairs, ls_launches = 0.0, 0.0, 0, 0.0, 0
     step_ms = []
     t0 = time.perf_counter()
@@ -313,10 +321,11 @@ def main():
     launches = int(agg[6])
     # one instrumented step (outside the timed region) for the work model of the level-set kernel
     ctx.set_count_pairs(True)
-    pairs_t = torch.tensor([runner.step(dev_in, copy_out=False)["timings"]["levelset_pairs"] * args.steps], dtype=torch.float64, device="cuda")
+    tm_c = runner.step(dev_in, copy_out=False)["timings"]
+    pairs_t = torch.tensor([tm_c["levelset_pairs"] * args.steps, tm_c.get("levelset_cert_evals", 0.0) * args.steps], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(pairs_t, op=dist.ReduceOp.SUM)
-    pairs = float(pairs_t.item())
+    pairs, cert_evals = float(pairs_t[0].item()), float(pairs_t[1].item())
     ctx.set_count_pairs(False)
     fixups = res["timings"].get("levelset_fixup_points", 0)
     stage = {k: round(v, 3) for k, v in res["timings"].items() if isinstance(v, float)}
@@ -356,15 +365,17 @@ def main():
         flops = (pairs / args.steps) * 30.0
         traffic, traffic_note = None, None
         from splashsurf_b200 import build as ssbuild
-        src_sha = ssbuild.source_hash()
+        src_sha, ls_sha = ssbuild.source_hash(), ssbuild.levelset_source_hash()
         try:
+            # DRAM bytes of the level-set kernels of ONE step (certification + exact pass + fix-up pass) from an `ncu --set full`
+            # capture of this very workload; only accepted when the level-set sources are the ones the capture was taken on
             tj = json.load(open(os.path.join(ROOT, "profiles", "levelset_traffic.json")))
-            if tj.get("source_sha") != src_sha:
-                traffic_note = f"refused: profiles/levelset_traffic.json was captured on source {tj.get('source_sha')}, this build is {src_sha}"
-            elif tj.get("particles") != int(n_total) and tj.get("scale_by_particles") is not True:
-                traffic_note = f"refused: capture was taken on {tj.get('particles')} particles, this run has {n_total}"
+            if tj.get("levelset_source_sha") != ls_sha:
+                traffic_note = f"refused: profiles/levelset_traffic.json was captured on level-set sources {tj.get('levelset_source_sha')}, this build is {ls_sha}"
+            elif tj.get("particles") != int(n_total) or tj.get("workload") != args.workload or world != 1:
+                traffic_note = f"refused: capture was taken on {tj.get('workload')} / {tj.get('particles')} particles / 1 GPU, this run is {args.workload} / {n_total} / {world} GPU(s)"
             else:
-                traffic = float(tj["dram_bytes_per_launch"]) * (n_total / tj["particles"])
+                traffic = float(tj["dram_bytes_per_step"])
                 traffic_note = tj.get("source", "")
         except Exception as e:      # noqa: BLE001
             traffic_note = f"no capture: {e}"
@@ -376,7 +387,12 @@ def main():
                 "fp32": {"achieved_tflops": flops / ls_s / 1e12 if ls_s > 0 else 0.0, "peak_tflops": FP32_PEAK_TFLOPS,
                          "frac": (flops / ls_s / 1e12) / FP32_PEAK_TFLOPS if ls_s > 0 else 0.0,
                          "model": "exactly evaluated in-support particle-gridpoint pairs x 30 flop", "pairs_per_step": pairs / args.steps,
-                         "fixup_points_per_step": int(fixups)}}
+                         "fixup_points_per_step": int(fixups),
+                         # everything the level-set kernels evaluate: + the lower-bound evaluations of the certification pass
+                         # (d^2 from the shared dx^2 + dy^2: 2 flop, cubic bound by Horner: 6, clamp: 1, volume-weighted sum: 2)
+                         "cert_evals_per_step": cert_evals / args.steps,
+                         "achieved_tflops_incl_certification": (flops + (cert_evals / args.steps) * 11.0) / ls_s / 1e12 if ls_s > 0 else 0.0,
+                         "frac_incl_certification": ((flops + (cert_evals / args.steps) * 11.0) / ls_s / 1e12) / FP32_PEAK_TFLOPS if ls_s > 0 else 0.0}}
         line = {"metric": METRIC, "value": value, "unit": "Mparticles/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
@@ -387,7 +403,7 @@ def main():
                 "wall_ms_per_step": wall_ms_max / args.steps, "step_ms_rank0": step_ms, "stage_ms_last_step": stage,
                 "e2e": {"value": e2e_val, "unit": "Mparticles/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(len(p_local) * 12 * world),
                         "d2h_bytes_per_step": int(d2h)},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "source_sha": src_sha}
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "source_sha": src_sha, "levelset_source_sha": ls_sha}
         if not args.no_cpu_baseline and world == 1:
             try:
                 import oracle

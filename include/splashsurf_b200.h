@@ -218,6 +218,10 @@ int ss_context_set_levelset_variant(ss_context *ctx, int variant);
  * bulk copies, ordered hit lists by ballot (csrc/ss_density.cuh); 0 = one thread per particle (k_density).  Replaces the
  * per-particle neighbour loop of neighborhood_search.rs:396-433 + density_map.rs:169-185. */
 int ss_context_set_density_variant(ss_context *ctx, int variant);
+/* Brick passes of the subdomain path (same mesh; vertex / triangle order inside a brick differs): 1 (default) = one warp per
+ * 8x8x8-point brick, marching cubes in two launches (count, emit) and the marker fix-up sweep on row bit masks (csrc/ss_mc.cuh);
+ * 0 = one CTA per brick, three marching-cubes launches.  Replaces dense_subdomains.rs:1470-1568. */
+int ss_context_set_mc_variant(ss_context *ctx, int variant);
 int ss_context_set_count_pairs(ss_context *ctx, int on);
 
 /* ---- SPH normals at the mesh vertices: SphInterpolator::interpolate_normals (sph_interpolation.rs:82-133) as used by the

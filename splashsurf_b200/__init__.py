@@ -114,6 +114,7 @@ def _bind(L):
     L.ss_context_set_levelset_exact_everywhere.argtypes = [vp, C.c_int]
     L.ss_context_set_levelset_variant.argtypes = [vp, C.c_int]
     L.ss_context_set_density_variant.argtypes = [vp, C.c_int]
+    L.ss_context_set_mc_variant.argtypes = [vp, C.c_int]
     L.ss_context_set_count_pairs.argtypes = [vp, C.c_int]
     L.ss_context_set_compute_sph_normals.argtypes = [vp, C.c_int]
     L.ss_surface_copy_normals.argtypes = [vp, vp]
@@ -338,6 +339,10 @@ class Context:
         """2 (default): warp-per-brick certification + exact kernels; 1: CTA-per-brick certification kernel; 0: fused kernel
         (same results)."""
         _check(self._L, self._L.ss_context_set_levelset_variant(self._h, int(variant)))
+
+    def set_mc_variant(self, variant: int):
+        """1 (default): warp-per-brick marching cubes + fix-up sweep; 0: CTA-per-brick passes (same mesh, other vertex order)."""
+        _check(self._L, self._L.ss_context_set_mc_variant(self._h, int(variant)))
 
     def set_density_variant(self, variant: int):
         """1 (default): cell-cooperative density kernel; 0: thread-per-particle kernel (same results)."""

@@ -25,14 +25,26 @@ NVCC_FLAGS = [
 ]
 
 
-def source_hash() -> str:
-    """sha256 (first 16 hex digits) over the CUDA sources and the public header: identifies the code a profile was taken on."""
+def source_hash(only=None) -> str:
+    """sha256 (first 16 hex digits) over the CUDA sources and the public header: identifies the code a profile was taken on.
+    `only`: restrict to these file names of csrc/ (e.g. the files that define one stage's kernels)."""
     import hashlib
     h = hashlib.sha256()
     for d in deps():
+        if only is not None and os.path.basename(d) not in only:
+            continue
         if d.endswith((".cu", ".cuh", ".inc", ".h")):
             h.update(open(d, "rb").read())
     return h.hexdigest()[:16]
+
+
+# the files that define the level-set kernels (certification, exact pass, shared device helpers): a DRAM-traffic capture of the
+# level-set stage stays valid while these are unchanged
+LEVELSET_SOURCES = ("ss_certify.cuh", "ss_exact.cuh", "ss_kernels.cuh", "ss_sm100.cuh", "ss_common.cuh")
+
+
+def levelset_source_hash() -> str:
+    return source_hash(only=LEVELSET_SOURCES)
 
 
 def needs_build() -> bool:

@@ -9,6 +9,7 @@
 #include "ss_certify.cuh"
 #include "ss_exact.cuh"
 #include "ss_density.cuh"
+#include "ss_mc.cuh"
 
 #ifndef SS_HOST_EMUL               // (tests/emul/cuda_emul.h compiles this file with g++ to step the kernels on the CPU)
 #include <cub/cub.cuh>
@@ -94,6 +95,7 @@ struct ss_context {
     int ls_variant = 2;              // 2 (default): warp-per-brick certification + exact kernels (ss_certify.cuh, ss_exact.cuh); 1: CTA-per-brick certification kernel; 0: fused k_levelset
     int count_pairs = 0;             // 1: count in-support evaluations (work model; slower)
     int density_variant = 1;         // 1 (default): cell-cooperative density kernel (ss_density.cuh); 0: thread-per-particle k_density
+    int mc_variant = 1;              // 1 (default): warp-per-brick marching cubes (count + emit) and fix-up sweep (ss_mc.cuh); 0: CTA-per-brick passes
     int sm_count = 148;              // streaming multiprocessors of the device (persistent-kernel grid sizing)
     int sph_normals = 0;             // 1: SPH normals at the mesh vertices (sph_interpolation.rs:82-133)
     // reusable scratch
@@ -276,6 +278,10 @@ extern "C" int ss_context_set_levelset_exact_everywhere(ss_context *c, int on) {
 extern "C" int ss_context_set_density_variant(ss_context *c, int v) {
     if (!c || v < 0 || v > 1) return ss_fail(SS_ERR_INVALID_PARAMETER, "density variant must be 0 or 1");
     c->density_variant = v; return SS_OK;
+}
+extern "C" int ss_context_set_mc_variant(ss_context *c, int v) {
+    if (!c || v < 0 || v > 1) return ss_fail(SS_ERR_INVALID_PARAMETER, "marching-cubes variant must be 0 or 1");
+    c->mc_variant = v; return SS_OK;
 }
 extern "C" int ss_context_set_levelset_variant(ss_context *c, int v) {
     if (!c || v < 0 || v > 2) return ss_fail(SS_ERR_INVALID_PARAMETER, "level-set variant must be 0, 1 or 2");
@@ -704,6 +710,10 @@ static int levelset_batch(ss_context *c, const SsDev &D, uint32_t nbatch, unsign
         CK(cudaMemsetAsync(c->wflag.p, 0, nbr * SS_LS_WARPS, st));
         CK(cudaMemsetAsync(c->brick_seen.p, 0, nbr * 4, st));
         CK(cudaMemsetAsync(c->nflag.p, 0, 8, st));
+        if (c->mc_variant == 1 && !global_mode)
+            LAUNCH(c, k_fixup_flags_warp, (n_fixscan + SS_MW_WARPS - 1) / SS_MW_WARPS, SS_MW_WARPS * 32, D, c->tiles.as<float>(), c->list_fix.as<uint32_t>(), n_fixscan,
+                   c->wflag.as<uint8_t>(), c->fix_list.as<uint32_t>(), c->nflag.as<uint32_t>());
+        else
         LAUNCH(c, k_fixup_flags, n_fixscan, SS_TP_THREADS, D, c->tiles.as<float>(), c->list_fix.as<uint32_t>(), c->wflag.as<uint8_t>(),
                c->brick_seen.as<uint32_t>(), c->fix_list.as<uint32_t>(), c->nflag.as<uint32_t>());
         uint32_t nfl[2] = { 0, 0 };
@@ -725,8 +735,11 @@ static int levelset_batch(ss_context *c, const SsDev &D, uint32_t nbatch, unsign
 static int marching_cubes_batch(ss_context *c, const SsDev &D, bool global_mode, uint32_t n_mc, ss_surface *out, uint64_t &vtotal, uint64_t &ttotal) {
     cudaStream_t st = c->stream;
     uint64_t bv = 0, bt = 0;
+    const bool warp_mc = c->mc_variant == 1 && !global_mode;       // ss_mc.cuh: one warp per brick, count + emit
     if (n_mc) {
-        if (global_mode) LAUNCH(c, k_mc_count<true>, n_mc, SS_TP_THREADS, D, c->tiles.as<float>(), c->list_mc.as<uint32_t>(), c->vmask.as<uint8_t>(), c->vcnt.as<uint32_t>(), c->tcnt.as<uint32_t>());
+        if (warp_mc) LAUNCH(c, k_mc_count_warp, (n_mc + SS_MW_WARPS - 1) / SS_MW_WARPS, SS_MW_WARPS * 32, D, c->tiles.as<float>(), c->list_mc.as<uint32_t>(), n_mc,
+                            c->vmask.as<uint8_t>(), c->voff.as<uint32_t>(), c->vcnt.as<uint32_t>(), c->tcnt.as<uint32_t>());
+        else if (global_mode) LAUNCH(c, k_mc_count<true>, n_mc, SS_TP_THREADS, D, c->tiles.as<float>(), c->list_mc.as<uint32_t>(), c->vmask.as<uint8_t>(), c->vcnt.as<uint32_t>(), c->tcnt.as<uint32_t>());
         else LAUNCH(c, k_mc_count<false>, n_mc, SS_TP_THREADS, D, c->tiles.as<float>(), c->list_mc.as<uint32_t>(), c->vmask.as<uint8_t>(), c->vcnt.as<uint32_t>(), c->tcnt.as<uint32_t>());
         cub_excl_scan(c, c->vcnt.as<uint32_t>(), c->vblk_off.as<uint32_t>(), n_mc);
         cub_excl_scan(c, c->tcnt.as<uint32_t>(), c->tblk_off.as<uint32_t>(), n_mc);
@@ -755,7 +768,11 @@ static int marching_cubes_batch(ss_context *c, const SsDev &D, bool global_mode,
         O.verts = out->verts.as<float>(); O.tris = out->tris.as<uint32_t>(); O.vkeys = out->vkeys.as<unsigned long long>();
         O.bkeys = c->bkeys_a.as<unsigned long long>(); O.bids = c->bids_a.as<uint32_t>(); O.bcount = c->bcount.as<uint32_t>();
         O.vbase = (uint32_t)vtotal; O.tbase = (uint32_t)ttotal; O.bcap = (uint32_t)std::min<size_t>((size_t)bc + bv, 0xffffffffu);
-        if (global_mode) {
+        if (warp_mc) {
+            LAUNCH(c, k_mc_emit_warp, (n_mc + SS_MW_WARPS - 1) / SS_MW_WARPS, SS_MW_WARPS * 32, D, c->tiles.as<float>(), c->list_mc.as<uint32_t>(), n_mc,
+                   c->vmask.as<uint8_t>(), c->voff.as<uint32_t>(), c->vcnt.as<uint32_t>(), c->tcnt.as<uint32_t>(), c->vblk_off.as<uint32_t>(),
+                   c->tblk_off.as<uint32_t>(), c->flag_mc.as<uint32_t>(), c->off_mc.as<uint32_t>(), c->tile_tab.as<SsTile>(), O);
+        } else if (global_mode) {
             LAUNCH(c, k_mc_verts<true>, n_mc, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->vblk_off.as<uint32_t>(),
                    c->vcnt.as<uint32_t>(), c->voff.as<uint32_t>(), c->tile_tab.as<SsTile>(), c->list_mc.as<uint32_t>(), O);
             LAUNCH(c, k_mc_tris<true>, n_mc, SS_TP_THREADS, D, c->tiles.as<float>(), c->vmask.as<uint8_t>(), c->tblk_off.as<uint32_t>(),

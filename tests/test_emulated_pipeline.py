@@ -60,12 +60,13 @@ def _parity(oracle_mod, g, o, S=64):
     return oracle_mod.mesh_parity(g.mesh.vertices, g.mesh.triangles, g.vertex_edge_keys, o["vertices"], o["triangles"], o["vertex_keys"], S)
 
 
-def _check_bit_exact(emu, oracle_mod, p, kw, exact_everywhere=False, tile_batch=None, variant=0, density_variant=1):
+def _check_bit_exact(emu, oracle_mod, p, kw, exact_everywhere=False, tile_batch=None, variant=0, density_variant=1, mc_variant=1):
     ctx = emu.Context()
     try:
         ctx.set_levelset_exact_everywhere(exact_everywhere)
         ctx.set_levelset_variant(variant)
         ctx.set_density_variant(density_variant)
+        ctx.set_mc_variant(mc_variant)
         if tile_batch:
             ctx.set_tile_batch(tile_batch)
         g = emu.reconstruct_surface(p, with_debug=True, context=ctx, **kw)
@@ -168,6 +169,13 @@ def test_emulated_density_kernel_variants(emu, oracle_mod, case):
         p = np.concatenate([_cube(9, 0.025, 311), rng.normal(0.2, 0.006, (90, 3)).astype(np.float32), rng.normal(0.33, 0.003, (40, 3)).astype(np.float32)])
     for dv in (1, 0):
         _check_bit_exact(emu, oracle_mod, p, kw, variant=2, density_variant=dv)
+
+
+@pytest.mark.parametrize("name,gen,kw,opts", [s for s in SEEDED if s[0] != "global_no_decomposition"], ids=[s[0] for s in SEEDED if s[0] != "global_no_decomposition"])
+def test_emulated_cta_per_brick_passes(emu, oracle_mod, name, gen, kw, opts):
+    """The CTA-per-brick marching-cubes / fix-up passes (mc variant 0; the default is the warp-per-brick set of ss_mc.cuh, which
+    every other test of this file runs) still produce the reference's mesh."""
+    _check_bit_exact(emu, oracle_mod, gen(), kw, variant=2, mc_variant=0, **opts)
 
 
 def test_emulated_aabb_filter_and_edge_cases(emu, oracle_mod):

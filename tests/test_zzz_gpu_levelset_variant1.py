@@ -86,3 +86,25 @@ def test_cuda_density_kernel_variants(ss, oracle_mod, case):
         assert np.array_equal(g.particle_densities, o["particle_densities"]), dv
         rho.append(g.particle_densities)
     assert np.array_equal(rho[0], rho[1])
+
+
+@pytest.mark.parametrize("name,gen,kw", [c for c in CASES if c[0] != "global_nodec"], ids=[c[0] for c in CASES if c[0] != "global_nodec"])
+def test_cuda_brick_pass_variants(ss, oracle_mod, name, gen, kw):
+    """Warp-per-brick marching cubes + fix-up sweep (default, csrc/ss_mc.cuh) and the CTA-per-brick passes: both meshes equal the
+    oracle's after canonical ordering (the order of vertices / triangles inside a brick differs between the two)."""
+    from splashsurf_b200 import synthetic as syn
+    p = gen(syn)
+    o = oracle_mod.reconstruct(p, **kw)
+    counts = []
+    for mv in (1, 0):
+        ctx = ss.Context()
+        try:
+            ctx.set_mc_variant(mv)
+            g = ss.reconstruct_surface(p, with_debug=True, context=ctx, **kw)
+        finally:
+            ctx.close()
+        m = oracle_mod.mesh_parity(g.mesh.vertices, g.mesh.triangles, g.vertex_edge_keys, o["vertices"], o["triangles"], o["vertex_keys"],
+                                   kw.get("subdomain_num_cubes_per_dim", 64))
+        assert m["keys_equal"] and m["triangles_equal"] and m["n_not_bitexact"] == 0, (mv, m)
+        counts.append((g.mesh.nvertices, g.mesh.ncells))
+    assert counts[0] == counts[1]
