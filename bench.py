@@ -237,6 +237,8 @@ def main():
                     help="multi-GPU only: how the global subdomain maximum reaches the library (see distributed.Runner)")
     ap.add_argument("--levelset-variant", type=int, default=2, choices=[0, 1, 2],
                     help="2 (default): warp-per-brick certification + exact kernels (TMA staging, packed FP32); 1: CTA-per-brick certification kernel; 0: fused k_levelset")
+    ap.add_argument("--density-variant", type=int, default=2, choices=[0, 1, 2], help="2 (default) / 1: cell-cooperative density kernel (staging by loads / bulk copies); 0: thread per particle")
+    ap.add_argument("--mc-variant", type=int, default=1, choices=[0, 1], help="1 (default): warp-per-brick marching cubes / fix-up sweep; 0: CTA per brick")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -262,6 +264,8 @@ def main():
     from splashsurf_b200 import distributed as ssd
     ctx = ss.Context(local_rank)
     ctx.set_levelset_variant(args.levelset_variant)
+    ctx.set_density_variant(args.density_variant)
+    ctx.set_mc_variant(args.mc_variant)
     if args.sph_normals:
         ss._check(ctx._L, ctx._L.ss_context_set_compute_sph_normals(ctx._h, 1))
     kw = dict(RECON_KW)
@@ -329,6 +333,9 @@ def main():
     ctx.set_count_pairs(False)
     fixups = res["timings"].get("levelset_fixup_points", 0)
     stage = {k: round(v, 3) for k, v in res["timings"].items() if isinstance(v, float)}
+    bricks = {k: int(v) for k, v in res["timings"].items() if k.startswith("bricks_")}
+    if res.get("phase_ms"):
+        sys.stderr.write(f"[rank {rank}] runner phases of the last step (host ms): {res['phase_ms']}\n")
 
     # ---- end to end through the C ABI with host buffers (pinned input, mesh copied back)
     for _ in range(min(args.warmup, 2)):
@@ -397,10 +404,11 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": dict(workload_config(args, desc, n_total, kw, f"subdomain slabs x{world}" if world > 1 else "single GPU"),
-                               levelset_variant=int(args.levelset_variant), sph_normals=bool(args.sph_normals),
+                               levelset_variant=int(args.levelset_variant), density_variant=int(args.density_variant), mc_variant=int(args.mc_variant),
+                               sph_normals=bool(args.sph_normals),
                                l2="inputs (600 MB) and tiles (GBs) exceed the 126 MB L2; no flush needed"),
                 "mesh": {"vertices": int(nv_g if nv_g is not None else nv), "triangles": int(nt_g if nt_g is not None else nt), "subdomains": int(n_sub)},
-                "wall_ms_per_step": wall_ms_max / args.steps, "step_ms_rank0": step_ms, "stage_ms_last_step": stage,
+                "wall_ms_per_step": wall_ms_max / args.steps, "step_ms_rank0": step_ms, "stage_ms_last_step": stage, "bricks_last_step_rank0": bricks, "runner_phase_ms_last_step_rank0": res.get("phase_ms"),
                 "e2e": {"value": e2e_val, "unit": "Mparticles/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(len(p_local) * 12 * world),
                         "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "source_sha": src_sha, "levelset_source_sha": ls_sha}

@@ -345,7 +345,8 @@ class Context:
         _check(self._L, self._L.ss_context_set_mc_variant(self._h, int(variant)))
 
     def set_density_variant(self, variant: int):
-        """1 (default): cell-cooperative density kernel; 0: thread-per-particle kernel (same results)."""
+        """2 (default) / 1: cell-cooperative density kernel (candidates staged by loads / by bulk copies); 0: thread-per-particle
+        kernel (same results)."""
         _check(self._L, self._L.ss_context_set_density_variant(self._h, int(variant)))
 
     def set_count_pairs(self, on: bool):

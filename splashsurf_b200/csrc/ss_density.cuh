@@ -28,6 +28,7 @@
 #define SS_DC_POOL 640                 // hit pool of one round of particles, in floats
 #define SS_DC_MAXP 16                  // particles per round
 #define SS_DC_RESERVE 128              // free pool entries required before a particle starts (bulk: ~33 hits per particle)
+#define SS_DC_CHUNK 32                 // consecutive cells a persistent warp takes at a time
 
 struct __align__(16) SsDcSlice {
     float4 cand[SS_DC_CAP];            // staged candidate positions (x, y, z, particle index bits), visiting order
@@ -97,6 +98,10 @@ __device__ __forceinline__ void ss_dc_flush(const SsDev &P, const SsDcArgs &A, S
     nround = 0; total = 0;
 }
 
+// TMA = true: the candidate runs are staged by bulk asynchronous copies (one per run, completing on the warp's mbarrier);
+// TMA = false: by ordinary 16-byte loads, one run per step with lane = entry (no per-copy service time of the TMA unit, which
+// bounds the kernel when the runs are only a few hundred bytes long).
+template <bool TMA>
 __global__ void __launch_bounds__(SS_DC_WARPS * 32)
 k_density_cells(SsDev P, SsDcArgs A) {
     __shared__ SsDcSlice s_slice[SS_DC_WARPS];
@@ -104,35 +109,53 @@ k_density_cells(SsDev P, SsDcArgs A) {
     SsDcSlice &S = s_slice[wib];
     const uint32_t n_cells = A.list_off[A.m - 1] + A.list_flag[A.m - 1];
     const uint32_t n_warps = gridDim.x * SS_DC_WARPS;
-    if (lane == 0) { ss_mbar_init(&S.mbar, 1); ss_mbar_fence_init(); }
+    if (TMA) { if (lane == 0) { ss_mbar_init(&S.mbar, 1); ss_mbar_fence_init(); } }
     __syncwarp();
     uint32_t phase = 0;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    for (uint32_t w = blockIdx.x * SS_DC_WARPS + wib; w < n_cells; w += n_warps) {
+    // persistent warps over chunks of SS_DC_CHUNK consecutive cells: neighbouring cells share their subdomain (geometry is
+    // recomputed only when it changes) and their candidate runs (L2 locality)
+    uint32_t s_cached = 0xffffffffu;
+    SsSubGeom g{};
+    SsNsGrid ns{};
+    for (uint32_t w0 = (blockIdx.x * SS_DC_WARPS + wib) * SS_DC_CHUNK; w0 < n_cells; w0 += n_warps * SS_DC_CHUNK) {
+      const uint32_t w1 = min(w0 + (uint32_t)SS_DC_CHUNK, n_cells);
+      for (uint32_t w = w0; w < w1; ++w) {
         const uint32_t a0 = A.list[w];
         const uint32_t k = A.key[a0];
         const uint32_t s = k / (uint32_t)P.ns_stride, cell = k - s * (uint32_t)P.ns_stride;
         const int nown = (int)(A.cend[k] - a0);
-        const SsSubGeom g = ss_sub_geom(P, A.sub_flat[s]);
-        const SsNsGrid ns = ss_ns_grid(P, g);
+        if (s != s_cached) { g = ss_sub_geom(P, A.sub_flat[s]); ns = ss_ns_grid(P, g); s_cached = s; }
         const int c0 = (int)cell / (P.nsD * P.nsD), c1 = ((int)cell / P.nsD) % P.nsD, c2 = (int)cell % P.nsD;
 
-        // ---- the 27 candidate runs in visiting order: (-1,0,1)^3 x-major without the centre, then the own cell
-        uint32_t run_a = 0, run_len = 0;
-        if (lane < 27) {
-            const int f = lane == 26 ? 13 : (lane < 13 ? lane : lane + 1);
-            const int q0 = c0 + f / 9 - 1, q1 = c1 + (f / 3) % 3 - 1, q2 = c2 + f % 3 - 1;
-            if (q0 >= 0 && q1 >= 0 && q2 >= 0 && q0 < ns.nc[0] && q1 < ns.nc[1] && q2 < ns.nc[2]) {
-                const uint32_t kk = s * (uint32_t)P.ns_stride + (uint32_t)((q0 * P.nsD + q1) * P.nsD + q2);
-                const uint32_t a = A.cstart[kk];
-                if (a != 0xffffffffu) { run_a = a; run_len = A.cend[kk] - a; }
+        // ---- candidate runs.  Visiting order: (-1,0,1)^3 x-major without the centre, then the own cell.  The three z-cells of one
+        // (sx, sy) column have consecutive keys, so their entries are ONE contiguous run of the sorted array: 9 runs, lane = column.
+        // Only the centre column is out of order (own cell last): it is staged as it lies and the order is restored by index
+        // arithmetic (ss_dc_phys).
+        uint32_t run_a = 0, run_len = 0, own_before = 0;
+        if (lane < 9) {
+            const int q0 = c0 + lane / 3 - 1, q1 = c1 + lane % 3 - 1;
+            if (q0 >= 0 && q1 >= 0 && q0 < ns.nc[0] && q1 < ns.nc[1]) {
+                const uint32_t kb = s * (uint32_t)P.ns_stride + (uint32_t)((q0 * P.nsD + q1) * P.nsD);
+                uint32_t a = 0xffffffffu, b = 0;
+#pragma unroll
+                for (int dz = -1; dz <= 1; ++dz) {
+                    const int q2 = c2 + dz;
+                    if (q2 < 0 || q2 >= ns.nc[2]) continue;
+                    const uint32_t st = A.cstart[kb + q2];
+                    if (st != 0xffffffffu) { if (a == 0xffffffffu) a = st; b = A.cend[kb + q2]; }
+                }
+                if (a != 0xffffffffu) { run_a = a; run_len = b - a; }
+                if (lane == 4) own_before = a0 - a;             // entries of the cell (0, 0, -1): they precede the own cell in its run
             }
         }
         uint32_t incl = run_len;
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
+        for (int o = 1; o < 16; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
         const uint32_t run_dst = incl - run_len;
-        const int C = (int)__shfl_sync(0xffffffffu, incl, 31);
-        const int self_off = (int)__shfl_sync(0xffffffffu, run_dst, 26);
+        const int C = (int)__shfl_sync(0xffffffffu, incl, 8);
+        // physical position of the own cell inside the staged array, and where it sits in the visiting order (at the end)
+        const int own_phys = (int)(__shfl_sync(0xffffffffu, run_dst, 4) + __shfl_sync(0xffffffffu, own_before, 4));
+        const int own_log = C - nown;
 
         if (C > SS_DC_CAP) {
             // dense cluster: thread-serial routine, lane = particle of the cell
@@ -146,23 +169,33 @@ k_density_cells(SsDev P, SsDcArgs A) {
             continue;
         }
 
-        // ---- stage the runs: bulk asynchronous copies (TMA engine) completing on the warp's mbarrier
-        ss_fence_proxy_async();                                    // the previous cell's reads of the slice precede these writes
-        __syncwarp();
-        if (lane == 0) ss_mbar_arrive_expect_tx(&S.mbar, (uint32_t)C * 16u);
-        __syncwarp();
-        if (run_len) ss_bulk_g2s(&S.cand[run_dst], A.spos + run_a, run_len * 16u, &S.mbar);
-        __syncwarp();
-        ss_mbar_wait(&S.mbar, phase);
-        phase ^= 1u;
+        // ---- stage the runs
+        if (TMA) {
+            ss_fence_proxy_async();                                // the previous cell's reads of the slice precede these writes
+            __syncwarp();
+            if (lane == 0) ss_mbar_arrive_expect_tx(&S.mbar, (uint32_t)C * 16u);
+            __syncwarp();
+            if (run_len) ss_bulk_g2s(&S.cand[run_dst], A.spos + run_a, run_len * 16u, &S.mbar);
+            __syncwarp();
+            ss_mbar_wait(&S.mbar, phase);
+            phase ^= 1u;
+        } else {
+            __syncwarp();                                          // the previous cell's reads of the slice are done
+#pragma unroll
+            for (int r = 0; r < 9; ++r) {
+                const uint32_t a = __shfl_sync(0xffffffffu, run_a, r), len = __shfl_sync(0xffffffffu, run_len, r), dst = __shfl_sync(0xffffffffu, run_dst, r);
+                for (uint32_t t = lane; t < len; t += 32) S.cand[dst + t] = A.spos[a + t];
+            }
+            __syncwarp();
+        }
 
-        // ---- per particle of the cell: ordered hit list (lane = candidate), pooled per round of particles
+        // ---- per particle of the cell: ordered hit list (lane = candidate in VISITING order), pooled per round of particles
         int nround = 0, total = 0;
         for (int t = 0; t < nown; ++t) {
-            const float4 pi = S.cand[self_off + t];
+            const float4 pi = S.cand[own_phys + t];
             if (!((pi.x >= g.smin[0] && pi.y >= g.smin[1] && pi.z >= g.smin[2]) && (pi.x < g.smax[0] && pi.y < g.smax[1] && pi.z < g.smax[2]))) continue;
             if (nround == SS_DC_MAXP || total > SS_DC_POOL - SS_DC_RESERVE) { SS_DC_NOTE(nround == SS_DC_MAXP ? "round full" : "pool nearly full"); ss_dc_flush(P, A, S, lane, nround, total); }
-            const int selfc = self_off + t;
+            const int selfc = own_log + t;
             int cnt = 0;
             bool over = false;
             for (int cb = 0; cb < C; cb += 32) {
@@ -170,7 +203,9 @@ k_density_cells(SsDev P, SsDcArgs A) {
                 bool hit = false;
                 float d2 = 0.0f;
                 if (c < C && c != selfc) {
-                    const float4 pj = S.cand[c];
+                    // visiting order -> staged position: the own cell's entries are visited last but lie inside the centre column
+                    const int cp = c < own_phys ? c : (c < own_log ? c + nown : own_phys + (c - own_log));
+                    const float4 pj = S.cand[cp];
                     const float dx = __fsub_rn(pj.x, pi.x), dy = __fsub_rn(pj.y, pi.y), dz = __fsub_rn(pj.z, pi.z);
                     d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
                     hit = d2 < P.h2;
@@ -186,5 +221,6 @@ k_density_cells(SsDev P, SsDcArgs A) {
             ++nround;
         }
         ss_dc_flush(P, A, S, lane, nround, total);
+      }
     }
 }

@@ -94,7 +94,7 @@ struct ss_context {
     int ls_exact_all = 0;            // 1: evaluate every grid point exactly (no certification)
     int ls_variant = 2;              // 2 (default): warp-per-brick certification + exact kernels (ss_certify.cuh, ss_exact.cuh); 1: CTA-per-brick certification kernel; 0: fused k_levelset
     int count_pairs = 0;             // 1: count in-support evaluations (work model; slower)
-    int density_variant = 1;         // 1 (default): cell-cooperative density kernel (ss_density.cuh); 0: thread-per-particle k_density
+    int density_variant = 2;         // cell-cooperative density kernel (ss_density.cuh), candidates staged by 2 (default): 16-byte loads, 1: bulk copies; 0: thread-per-particle k_density
     int mc_variant = 1;              // 1 (default): warp-per-brick marching cubes (count + emit) and fix-up sweep (ss_mc.cuh); 0: CTA-per-brick passes
     int sm_count = 148;              // streaming multiprocessors of the device (persistent-kernel grid sizing)
     int sph_normals = 0;             // 1: SPH normals at the mesh vertices (sph_interpolation.rs:82-133)
@@ -276,7 +276,7 @@ extern "C" int ss_context_keep_levelset_tile(ss_context *c, int64_t flat) { if (
 extern "C" int ss_context_set_tile_batch(ss_context *c, uint32_t m) { if (!c) return SS_ERR_INVALID_PARAMETER; c->max_tiles = m; return SS_OK; }
 extern "C" int ss_context_set_levelset_exact_everywhere(ss_context *c, int on) { if (!c) return SS_ERR_INVALID_PARAMETER; c->ls_exact_all = on ? 1 : 0; return SS_OK; }
 extern "C" int ss_context_set_density_variant(ss_context *c, int v) {
-    if (!c || v < 0 || v > 1) return ss_fail(SS_ERR_INVALID_PARAMETER, "density variant must be 0 or 1");
+    if (!c || v < 0 || v > 2) return ss_fail(SS_ERR_INVALID_PARAMETER, "density variant must be 0, 1 or 2");
     c->density_variant = v; return SS_OK;
 }
 extern "C" int ss_context_set_mc_variant(ss_context *c, int v) {
@@ -495,7 +495,7 @@ static int stage_densities(ss_context *c, const SsDev &D, const float *d_xyz, ui
     if (want_nbrs) { out->nbr_off.ensure((n + 1) * 8); d_ncnt = out->nbr_off.as<unsigned long long>(); CK(cudaMemsetAsync(d_ncnt, 0, (n + 1) * 8, st)); }
     // entries with the particle inside the subdomain (every particle is inside at most one: <= n of them), compacted
     c->dflag.ensure((size_t)M * 4); c->doff.ensure((size_t)M * 4 + 4); c->dlist.ensure(std::max<uint64_t>(n, 1) * 4);
-    if (c->density_variant == 1 && !want_nbrs) {
+    if (c->density_variant >= 1 && !want_nbrs) {
         // cell-cooperative kernel (ss_density.cuh): one warp per h-cell that holds a particle inside its subdomain (<= n cells), persistent grid
         LAUNCH(c, k_density_cell_flags, nblk(M, 256), 256, D, M, c->key_b.as<uint32_t>(), c->spos.as<float4>(), c->sub_flat.as<uint32_t>(),
                c->tab_b.as<uint32_t>(), c->dflag.as<uint32_t>());
@@ -506,7 +506,8 @@ static int stage_densities(ss_context *c, const SsDev &D, const float *d_xyz, ui
         DA.key = c->key_b.as<uint32_t>(); DA.spos = c->spos.as<float4>(); DA.sub_flat = c->sub_flat.as<uint32_t>();
         DA.cstart = c->tab_a.as<uint32_t>(); DA.cend = c->tab_b.as<uint32_t>(); DA.rho = d_rho; DA.nbr_count = nullptr;
         const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)c->sm_count * 7u, ((uint64_t)n + SS_DC_WARPS - 1) / SS_DC_WARPS);
-        LAUNCH(c, k_density_cells, std::max(grid, 1u), SS_DC_WARPS * 32, D, DA);
+        if (c->density_variant == 1) LAUNCH(c, k_density_cells<true>, std::max(grid, 1u), SS_DC_WARPS * 32, D, DA);
+        else LAUNCH(c, k_density_cells<false>, std::max(grid, 1u), SS_DC_WARPS * 32, D, DA);
     } else {
     LAUNCH(c, k_density_flags, nblk(M, 256), 256, D, M, c->key_b.as<uint32_t>(), c->spos.as<float4>(), c->sub_flat.as<uint32_t>(), c->dflag.as<uint32_t>());
     cub_excl_scan(c, c->dflag.as<uint32_t>(), c->doff.as<uint32_t>(), M);

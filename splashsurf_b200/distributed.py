@@ -268,8 +268,10 @@ class Runner:
     def _step_multi(self, x: torch.Tensor, copy_out: bool) -> dict:
         L, p, world, rank, dev = self.ctx._L, self.params, self.world, self.rank, self.device
         from . import _Grid
+        import time
         t_ev = [_event(dev) for _ in range(3)]
         t_ev[0].record()
+        t_host = [time.perf_counter()]          # host clock after each phase (every phase ends in a host sync): where the runner's time goes
         xd = x.to(dev, non_blocking=True) if x.device.type != dev.type else x
         n = int(xd.shape[0])
         S = int(p.subdomain_num_cubes_per_dim)
@@ -282,6 +284,7 @@ class Runner:
         dist.all_reduce(box, op=dist.ReduceOp.MAX, group=self.group)
         b = box.cpu().numpy().astype(np.float32)                    # host sync: also orders the upload before the library calls
         corners = np.ascontiguousarray(np.stack([-b[:3], b[3:]]))
+        t_host.append(time.perf_counter())      # 1: bounding box
         grid = _Grid()
         rc = L.ss_grid_for_reconstruction_f32(self.ctx._h, C.c_void_p(corners.ctypes.data), C.c_uint64(2), C.byref(p), C.byref(grid))
         if rc:
@@ -311,6 +314,7 @@ class Runner:
         plan = make_plan(ncells, S, float(p.cube_size), float(p.compact_support_radius), work, world, axis=ax)
         plan.gmin_axis = float(grid.aabb_min[ax])
         self.last_plan = plan
+        t_host.append(time.perf_counter())      # 2: statistics + plan
         # 3. halo exchange: the library packs per destination (stable), NCCL moves it; ascending global particle order is kept
         iv = [plan.recv_interval(r) for r in range(world)]
         lo = (C.c_double * world)(*[v[0] for v in iv]); hi = (C.c_double * world)(*[v[1] for v in iv])
@@ -335,6 +339,7 @@ class Runner:
         t_ev[1].record()
         own_lo, own_hi = plan.own(rank)
         _sync(dev)                                                  # the exchange has landed before the library (own stream) reads it
+        t_host.append(time.perf_counter())      # 3: pack + exchange
         # 4. this rank's slab.  The global maximum subdomain population (sparse rule, dense_subdomains.rs:1242-1251) is max-reduced
         #    from inside the call ("callback") or by a decomposition pre-pass ("two_call"); every rank issues the same collectives.
         s = C.c_void_p()
@@ -365,13 +370,16 @@ class Runner:
                 self.ctx.free_surface(s)
             gmax = torch.tensor([local_max], dtype=torch.int64, device=dev)
             dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=self.group)       # issued on every rank, also after a failed pre-pass
+            gmax_i = int(gmax.item())
+            t_host.append(time.perf_counter())  # 4: decomposition pre-pass + max-reduce (two_call only)
             if not rc:
                 s = C.c_void_p()
                 rc = L.ss_reconstruct_partition_f32(self.ctx._h, C.c_void_p(recv.data_ptr()), C.c_uint64(recv.shape[0]), C.byref(p),
-                                                    C.byref(grid), ax, own_lo, own_hi, plan.halo, C.c_uint64(int(gmax.item())), 0, C.byref(s))
+                                                    C.byref(grid), ax, own_lo, own_hi, plan.halo, C.c_uint64(gmax_i), 0, C.byref(s))
         # 5. the status is part of the protocol: every rank learns whether any rank failed and raises together (no rank is
         #    left waiting in a later collective)
         msg = (L.ss_last_error() or b"").decode() if rc else ""
+        t_host.append(time.perf_counter())      # 5 (4 with the callback protocol): the library call
         status = torch.zeros(1 + world, dtype=torch.float64, device=dev)       # [worst return code, library ms of every rank]
         status[0] = float(int(rc) if not failure else 255)
         if not rc and not failure:
@@ -405,6 +413,9 @@ class Runner:
             out["recv_particles"] = int(recv.shape[0])
             out["exchange_ms"] = t_ev[0].elapsed_time(t_ev[1])
             out["plan"] = plan
+            t_host.append(time.perf_counter())
+            names = ["bbox", "stats_plan", "pack_exchange"] + (["prepass_maxreduce"] if self.protocol == "two_call" else []) + ["library", "status_collect"]
+            out["phase_ms"] = {k: round(1e3 * (t_host[i + 1] - t_host[i]), 3) for i, k in enumerate(names) if i + 1 < len(t_host)}
             if copy_out:
                 out.update(self._assemble_mesh(s, plan))
             return out

@@ -60,7 +60,7 @@ def _parity(oracle_mod, g, o, S=64):
     return oracle_mod.mesh_parity(g.mesh.vertices, g.mesh.triangles, g.vertex_edge_keys, o["vertices"], o["triangles"], o["vertex_keys"], S)
 
 
-def _check_bit_exact(emu, oracle_mod, p, kw, exact_everywhere=False, tile_batch=None, variant=0, density_variant=1, mc_variant=1):
+def _check_bit_exact(emu, oracle_mod, p, kw, exact_everywhere=False, tile_batch=None, variant=0, density_variant=2, mc_variant=1):
     ctx = emu.Context()
     try:
         ctx.set_levelset_exact_everywhere(exact_everywhere)
@@ -167,7 +167,7 @@ def test_emulated_density_kernel_variants(emu, oracle_mod, case):
     else:
         rng = np.random.default_rng(9)
         p = np.concatenate([_cube(9, 0.025, 311), rng.normal(0.2, 0.006, (90, 3)).astype(np.float32), rng.normal(0.33, 0.003, (40, 3)).astype(np.float32)])
-    for dv in (1, 0):
+    for dv in (2, 1, 0):
         _check_bit_exact(emu, oracle_mod, p, kw, variant=2, density_variant=dv)
 
 

@@ -76,7 +76,7 @@ def test_cuda_density_kernel_variants(ss, oracle_mod, case):
         p = gen(syn)
     o = oracle_mod.reconstruct(p, **kw)
     rho = []
-    for dv in (1, 0):
+    for dv in (2, 1, 0):
         ctx = ss.Context()
         try:
             ctx.set_density_variant(dv)
@@ -85,7 +85,7 @@ def test_cuda_density_kernel_variants(ss, oracle_mod, case):
             ctx.close()
         assert np.array_equal(g.particle_densities, o["particle_densities"]), dv
         rho.append(g.particle_densities)
-    assert np.array_equal(rho[0], rho[1])
+    assert np.array_equal(rho[0], rho[1]) and np.array_equal(rho[0], rho[2])
 
 
 @pytest.mark.parametrize("name,gen,kw", [c for c in CASES if c[0] != "global_nodec"], ids=[c[0] for c in CASES if c[0] != "global_nodec"])

@@ -81,6 +81,25 @@ if has ncu2; then
       python bench.py --workload cfg3 --steps 1 --warmup 1 --no-cpu-baseline --levelset-variant 2 > gpurun_out/ncu_full_v2_$TAG.log 2>&1
   ls -la gpurun_out/prof_variant2_$TAG.ncu-rep
 fi
+if has ab; then
+  echo "== A/B: density variant 0, mc variant 0 (level-set variant 2)"
+  for ab in "--density-variant 0" "--mc-variant 0"; do
+    timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline $ab > gpurun_out/bench_ab_$TAG.json 2> gpurun_out/bench_ab_$TAG.err
+    python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/bench_ab_$TAG.json")); print("$ab", {k: d.get(k) for k in ("value", "ms_per_step", "stage_ms_last_step")})
+except Exception as e:
+    print("bench failed:", e); print(open("gpurun_out/bench_ab_$TAG.err").read()[-1500:])
+PY
+  done
+fi
+if has launches5; then
+  echo "== launch list of one cfg-5 step (200 M splash, SPH normals)"
+  timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches_cfg5_$TAG.csv \
+      python bench.py --workload cfg5 --sph-normals --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_bench_cfg5_$TAG.log 2>&1
+  wc -l gpurun_out/launches_cfg5_$TAG.csv
+fi
 if has cfg5; then
   echo "== cfg-5 (200 M splash, c = 0.45 r, SPH normals) on one GPU"
   timeout 1200 python bench.py --workload cfg5 --sph-normals --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_cfg5_1gpu_$TAG.json 2> gpurun_out/bench_cfg5_1gpu_$TAG.err
