@@ -92,8 +92,11 @@ WORKLOADS = {
     "cfg4": None,    # default: dam break (50 M, or scaled with --particles)
     "cfg2": ("synthetic jittered cube 100^3 = 1 M particles (r=0.025, seed 1234)", dict(particle_radius=0.025)),
     "cfg3": ("synthetic dam-break 10 M (column 200x230x200 + sheet 400x10x200, r=0.01, seed 2)", dict()),
-    "cfg5": ("synthetic splash 200 M (body 540x583x540 + droplets, r=0.005, seed 4), cube 0.45 r",
+    "cfg5": ("synthetic splash 200 M (body 540x583x540 + ~340 disjoint droplets of radius 10..40 d above it, r=0.005, seed 4), cube 0.45 r",
              dict(particle_radius=0.005, cube_size=0.45)),
+    # the round-2 first-run cloud: droplet lattices superimposed at 2-3x rest density (stress case for the dense-cluster routes)
+    "cfg5_overlap": ("synthetic splash 200 M with superimposed droplets (body 540x583x540, r=0.005, seed 4), cube 0.45 r",
+                     dict(particle_radius=0.005, cube_size=0.45)),
 }
 
 
@@ -103,8 +106,8 @@ def make_cloud(n_target, workload="cfg4"):
         return syn.jittered_cube(100, 0.025, 1234), WORKLOADS["cfg2"][0]
     if workload == "cfg3":
         return syn.dam_break_10m(), WORKLOADS["cfg3"][0]
-    if workload == "cfg5":
-        return syn.splash_200m(), WORKLOADS["cfg5"][0]
+    if workload in ("cfg5", "cfg5_overlap"):
+        return syn.splash_200m(overlap=workload == "cfg5_overlap"), WORKLOADS[workload][0]
     if n_target >= 50_000_000:
         return syn.dam_break_50m(), "synthetic dam-break 50 M (column 340x370x340 + sheet 1063x20x340, r=0.01, seed 3)"
     return syn.dam_break_scaled(n_target, 0.01, 3), f"synthetic dam-break scaled to ~{n_target} particles (cfg-4 proportions, r=0.01, seed 3)"

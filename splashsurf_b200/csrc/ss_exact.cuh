@@ -50,6 +50,11 @@ typedef SsXwSliceT<SS_XW_CAP, SS_XW_LIST, 512> SsXwSlice;
 #define SS_XW_BIG_CAP 4096
 #define SS_XW_BIG_LIST 2048
 typedef SsXwSliceT<SS_XW_BIG_CAP, SS_XW_BIG_LIST, SS_XW_BIG_CAP> SsXwSliceBig;
+// in between: up to 1024 candidates (two or three overlapping bodies of fluid), one warp per CTA, 27 KB of static shared memory ->
+// 8 bricks in flight per SM instead of the big variant's 2
+#define SS_XW_MID_CAP 1024
+#define SS_XW_MID_LIST 640
+typedef SsXwSliceT<SS_XW_MID_CAP, SS_XW_MID_LIST, SS_XW_MID_CAP> SsXwSliceMid;
 #ifdef SS_HOST_EMUL
 static thread_local __align__(16) unsigned char ss_dyn_smem[sizeof(SsXwSliceBig)];
 #else
@@ -288,6 +293,15 @@ k_exact_warp(SsDev P, SsXwArgs A) {
     const uint32_t work = blockIdx.x * SS_XW_WARPS + wib;
     if (work >= A.n_bricks) return;
     ss_exact_brick<GLOBAL, COUNT, SS_XW_CAP, SS_XW_LIST>(P, A, s_slice[wib], work, lane);
+}
+
+// one warp per CTA: bricks with up to 1024 candidates
+template <bool GLOBAL, bool COUNT>
+__global__ void __launch_bounds__(32, 8)
+k_exact_warp_mid(SsDev P, SsXwArgs A) {
+    __shared__ SsXwSliceMid s_slice;
+    if (blockIdx.x >= A.n_bricks) return;
+    ss_exact_brick<GLOBAL, COUNT, SS_XW_MID_CAP, SS_XW_MID_LIST>(P, A, s_slice, blockIdx.x, (int)(threadIdx.x & 31));
 }
 
 // one warp per CTA, slice in dynamic shared memory (sizeof(SsXwSliceBig) bytes): bricks with up to 4096 candidates

@@ -101,7 +101,7 @@ struct ss_context {
     // reusable scratch
     DevBuf xyz, xyz_f, filt_flag, filt_flag32, filt_off, aabb, cnt, off, key_a, key_b, val_a, val_b, cid, cub_tmp,
         sub_flat, sub_off, sub_sparse, sub_owned, gkey_a, gkey_b, gval_a, gval_b, flags, scan, spos, rho, tab_a, tab_b, rec, ksplit, batch_subs, tiles, vcnt,
-        tcnt, vmask, voff, vblk_off, tblk_off, tile_tab, brick_rng, bstate, flag_ls, off_ls, list_ls, flag_mc, flag_fix, off_mc, off_fix, list_mc, list_fix, wflag, wstate, desc_ls, dflag, doff, dlist, fallback, fallback2, pack_cnt, pack_off, brick_seen, fix_list, nflag, bkeys_a, bkeys_b, bids_a, bids_b, bcount, remap, keep, newid, err, pairs;
+        tcnt, vmask, voff, vblk_off, tblk_off, tile_tab, brick_rng, bstate, flag_ls, off_ls, list_ls, flag_mc, flag_fix, off_mc, off_fix, list_mc, list_fix, wflag, wstate, desc_ls, dflag, doff, dlist, fallback, fallback2, fallback3, pack_cnt, pack_off, brick_seen, fix_list, nflag, bkeys_a, bkeys_b, bids_a, bids_b, bcount, remap, keep, newid, err, pairs;
     uint64_t launches = 0;
     int big_attr_set = 0;            // dynamic shared memory opt-in of k_exact_warp_big done
     uint64_t pack_n = 0; uint32_t pack_world = 0;   // ss_partition_pack_f32: count phase the scatter phase must match
@@ -263,7 +263,7 @@ extern "C" void ss_context_destroy(ss_context *c) {
     DevBuf *bufs[] = { &c->xyz, &c->xyz_f, &c->filt_flag, &c->filt_flag32, &c->filt_off, &c->aabb, &c->cnt, &c->off, &c->key_a, &c->key_b,
                        &c->val_a, &c->val_b, &c->cid, &c->cub_tmp, &c->sub_flat, &c->sub_off, &c->sub_sparse, &c->sub_owned, &c->gkey_a, &c->gkey_b, &c->gval_a, &c->gval_b, &c->flags, &c->scan,
                        &c->spos, &c->rho, &c->tab_a, &c->tab_b, &c->rec, &c->ksplit, &c->batch_subs, &c->tiles, &c->vcnt, &c->tcnt,
-                       &c->vmask, &c->voff, &c->vblk_off, &c->tblk_off, &c->tile_tab, &c->brick_rng, &c->bstate, &c->flag_ls, &c->off_ls, &c->list_ls, &c->flag_mc, &c->flag_fix, &c->off_mc, &c->off_fix, &c->list_mc, &c->list_fix, &c->wflag, &c->wstate, &c->desc_ls, &c->dflag, &c->doff, &c->dlist, &c->fallback, &c->fallback2, &c->pack_cnt, &c->pack_off, &c->brick_seen, &c->fix_list, &c->nflag, &c->bkeys_a, &c->bkeys_b, &c->bids_a, &c->bids_b, &c->bcount, &c->remap, &c->keep, &c->newid,
+                       &c->vmask, &c->voff, &c->vblk_off, &c->tblk_off, &c->tile_tab, &c->brick_rng, &c->bstate, &c->flag_ls, &c->off_ls, &c->list_ls, &c->flag_mc, &c->flag_fix, &c->off_mc, &c->off_fix, &c->list_mc, &c->list_fix, &c->wflag, &c->wstate, &c->desc_ls, &c->dflag, &c->doff, &c->dlist, &c->fallback, &c->fallback2, &c->fallback3, &c->pack_cnt, &c->pack_off, &c->brick_seen, &c->fix_list, &c->nflag, &c->bkeys_a, &c->bkeys_b, &c->bids_a, &c->bids_b, &c->bcount, &c->remap, &c->keep, &c->newid,
                        &c->err, &c->pairs, &c->o_verts, &c->o_tris, &c->o_vkeys, &c->o_rho, &c->o_verts2, &c->o_vkeys2, &c->o_normals };
     for (DevBuf *b : bufs) b->release();
     c->post.release_all();
@@ -595,35 +595,41 @@ static void launch_exact(ss_context *c, const SsDev &D, const SsLsArgs &F, uint3
     uint32_t n_fb = 0;
     CK(cudaMemcpyAsync(&n_fb, c->fallback.p, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (n_fb) {
-        // dense clusters: the same kernel with a 108 KB slice per warp (up to 4096 candidates per brick)
-        c->fallback2.ensure(((size_t)n_fb + 1) * 4);
-        CK(cudaMemsetAsync(c->fallback2.p, 0, 4, st));
+    // dense clusters: the same kernel with one warp per CTA and a larger slice -- up to 1024 candidates per brick (27 KB, static;
+    // list: fallback -> leftovers in fallback2), then up to 4096 (108 KB of dynamic shared memory; leftovers in fallback3)
+    for (int stage = 0; stage < 2 && n_fb; ++stage) {
+        DevBuf &in = stage == 0 ? c->fallback : c->fallback2, &left = stage == 0 ? c->fallback2 : c->fallback3;
+        left.ensure(((size_t)n_fb + 1) * 4);
+        CK(cudaMemsetAsync(left.p, 0, 4, st));
         SsXwArgs Y = X;
-        Y.bricks = c->fallback.as<uint32_t>() + 1; Y.n_bricks = n_fb; Y.fallback = c->fallback2.as<uint32_t>();
-        const size_t dyn = sizeof(SsXwSliceBig);
-        if (!c->big_attr_set) {
+        Y.bricks = in.as<uint32_t>() + 1; Y.n_bricks = n_fb; Y.fallback = left.as<uint32_t>();
+        if (stage == 0) {
+            if (global_mode) { if (count) LAUNCH(c, (k_exact_warp_mid<true, true>), n_fb, 32, D, Y); else LAUNCH(c, (k_exact_warp_mid<true, false>), n_fb, 32, D, Y); }
+            else { if (count) LAUNCH(c, (k_exact_warp_mid<false, true>), n_fb, 32, D, Y); else LAUNCH(c, (k_exact_warp_mid<false, false>), n_fb, 32, D, Y); }
+        } else {
+            const size_t dyn = sizeof(SsXwSliceBig);
+            if (!c->big_attr_set) {
 #ifndef SS_HOST_EMUL
-            CK(cudaFuncSetAttribute(k_exact_warp_big<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-            CK(cudaFuncSetAttribute(k_exact_warp_big<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-            CK(cudaFuncSetAttribute(k_exact_warp_big<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-            CK(cudaFuncSetAttribute(k_exact_warp_big<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+                CK(cudaFuncSetAttribute(k_exact_warp_big<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+                CK(cudaFuncSetAttribute(k_exact_warp_big<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+                CK(cudaFuncSetAttribute(k_exact_warp_big<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+                CK(cudaFuncSetAttribute(k_exact_warp_big<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
 #endif
-            c->big_attr_set = 1;
+                c->big_attr_set = 1;
+            }
+            if (global_mode) { if (count) LAUNCH_DYN(c, (k_exact_warp_big<true, true>), n_fb, 32, dyn, D, Y); else LAUNCH_DYN(c, (k_exact_warp_big<true, false>), n_fb, 32, dyn, D, Y); }
+            else { if (count) LAUNCH_DYN(c, (k_exact_warp_big<false, true>), n_fb, 32, dyn, D, Y); else LAUNCH_DYN(c, (k_exact_warp_big<false, false>), n_fb, 32, dyn, D, Y); }
         }
-        if (global_mode) { if (count) LAUNCH_DYN(c, (k_exact_warp_big<true, true>), n_fb, 32, dyn, D, Y); else LAUNCH_DYN(c, (k_exact_warp_big<true, false>), n_fb, 32, dyn, D, Y); }
-        else { if (count) LAUNCH_DYN(c, (k_exact_warp_big<false, true>), n_fb, 32, dyn, D, Y); else LAUNCH_DYN(c, (k_exact_warp_big<false, false>), n_fb, 32, dyn, D, Y); }
         ++ls_launches;
-        uint32_t n_fb2 = 0;
-        CK(cudaMemcpyAsync(&n_fb2, c->fallback2.p, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&n_fb, left.p, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        if (n_fb2) {
-            // beyond that: k_levelset's O(C^2) selection path (extreme clustering only)
-            SsLsArgs G = F;
-            G.fix_bricks = c->fallback2.as<uint32_t>() + 1;
-            launch_levelset(c, dim3(n_fb2), D, G, count, global_mode);
-            ++ls_launches;
-        }
+    }
+    if (n_fb) {
+        // beyond 4096 candidates: k_levelset's O(C^2) selection path (extreme clustering only)
+        SsLsArgs G = F;
+        G.fix_bricks = c->fallback3.as<uint32_t>() + 1;
+        launch_levelset(c, dim3(n_fb), D, G, count, global_mode);
+        ++ls_launches;
     }
 }
 

@@ -73,9 +73,13 @@ def splash(n_body=(60, 65, 60), n_droplets: int = 12, r: float = 0.005, seed: in
     return _jitter(np.concatenate(parts, axis=0), d, rng)
 
 
-def splash_200m(scale: float = 1.0, seed: int = 4) -> np.ndarray:
-    """cfg-5: dam-break body 540x583x540 (r = 0.005) plus lattice-ball droplets of radius U[10, 40] d at random centres above
-    it, added until N = 200 M (~340 droplets).  `scale` < 1 shrinks every lattice count (for tests / smaller boxes)."""
+def splash_200m(scale: float = 1.0, seed: int = 4, overlap: bool = False) -> np.ndarray:
+    """cfg-5: dam-break body 540x583x540 (r = 0.005) plus lattice-ball droplets of radius U[10, 40] d above it, added until
+    N = 200 M (~340 droplets).  Droplet centres are rejection-sampled so that no two droplets touch (a gap of 2 d between their
+    surfaces; the air space above the body is made as tall as that needs): particles of an incompressible fluid do not
+    interpenetrate, and superimposed lattices would be a 2-3x rest-density cloud that no SPH frame contains.  `overlap=True`
+    gives the round-2 first-run cloud (random centres in a shallow layer, heavily superimposed droplets) as a stress case for
+    the dense-cluster escape routes.  `scale` < 1 shrinks every lattice count (tests / smaller boxes)."""
     r = 0.005
     d = 2.0 * r
     rng = np.random.default_rng(seed)
@@ -84,9 +88,18 @@ def splash_200m(scale: float = 1.0, seed: int = 4) -> np.ndarray:
     n = len(parts[0])
     target = int(200_000_000 * scale ** 3)
     top = nb[1] * d
+    placed = []                                     # (centre, radius) of the droplets so far
+    height = 500.0                                  # air space for droplet centres, in units of scale * d
     while n < target:
         rad = rng.uniform(10.0, 40.0) * scale * d
-        ctr = np.array([rng.uniform(0, nb[0] * d), top + rad + rng.uniform(2.0, 60.0) * scale * d, rng.uniform(0, nb[2] * d)])
+        for attempt in range(4000):
+            ctr = np.array([rng.uniform(0, nb[0] * d), top + rad + rng.uniform(2.0, 60.0 if overlap else height) * scale * d, rng.uniform(0, nb[2] * d)])
+            if overlap or all(np.linalg.norm(ctr - c0) >= rad + r0 + 2.0 * d for c0, r0 in placed):
+                break
+        else:
+            height *= 1.5                           # crowded: raise the ceiling and draw again
+            continue
+        placed.append((ctr, rad))
         m = int(np.ceil(rad / d))
         ball = _lattice(2 * m + 1, 2 * m + 1, 2 * m + 1, d, origin=tuple(ctr - m * d))
         ball = ball[np.linalg.norm(ball - ctr[None].astype(np.float32), axis=1) <= rad]

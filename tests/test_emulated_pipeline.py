@@ -142,7 +142,8 @@ def test_emulated_warp_per_brick_certification(emu, oracle_mod, name, gen, kw, o
     _check_bit_exact(emu, oracle_mod, gen(), kw, variant=2, **opts)
 
 
-@pytest.mark.parametrize("n,sigma", [(600, 0.004), (400, 0.02), (260, 0.01), (4500, 0.004)], ids=["oversized_brick", "list_overflow", "dense_cluster", "extreme_cluster"])
+@pytest.mark.parametrize("n,sigma", [(600, 0.004), (1500, 0.004), (400, 0.02), (260, 0.01), (4500, 0.004)],
+                         ids=["oversized_brick_1024_variant", "oversized_brick_4096_variant", "list_overflow", "dense_cluster", "extreme_cluster"])
 def test_emulated_warp_per_brick_clustered_particles(emu, oracle_mod, n, sigma):
     """Variant 2 on pathological clustering: more candidates than a warp's slice holds (brick goes to the 4096-candidate variant of
     the exact kernel), more candidates in the support of one sub-box than its list holds, a dense cluster that still fits, and

@@ -82,8 +82,8 @@ if has ncu2; then
   ls -la gpurun_out/prof_variant2_$TAG.ncu-rep
 fi
 if has ab; then
-  echo "== A/B: density variant 0, mc variant 0 (level-set variant 2)"
-  for ab in "--density-variant 0" "--mc-variant 0"; do
+  echo "== A/B against the defaults (level-set variant 2, density variant 2, mc variant 1)"
+  for ab in ${SS_AB:-"--density-variant=1" "--density-variant=0" "--mc-variant=0"}; do
     timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline $ab > gpurun_out/bench_ab_$TAG.json 2> gpurun_out/bench_ab_$TAG.err
     python - <<PY
 import json
@@ -93,6 +93,13 @@ except Exception as e:
     print("bench failed:", e); print(open("gpurun_out/bench_ab_$TAG.err").read()[-1500:])
 PY
   done
+fi
+if has ncu4; then
+  echo "== ncu --set full on the bench workload (cfg-4, 50 M): density, certification, exact pass (+ fix-up pass), fix-up sweep, marching cubes"
+  python -c "from splashsurf_b200 import build; print(build.source_hash(), build.levelset_source_hash())" > gpurun_out/source_sha_$TAG.txt
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_certify_warp|k_exact_warp|k_density_cells|k_mc_count_warp|k_mc_emit_warp|k_fixup_flags_warp' -c 7 \
+      -o gpurun_out/prof_cfg4_$TAG -f python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_full_cfg4_$TAG.log 2>&1
+  ls -la gpurun_out/prof_cfg4_$TAG.ncu-rep; cat gpurun_out/source_sha_$TAG.txt
 fi
 if has launches5; then
   echo "== launch list of one cfg-5 step (200 M splash, SPH normals)"
