@@ -268,6 +268,30 @@ int ss_surface_smooth_normals_f32(ss_surface *s, uint32_t iterations);
  * reference's free functions of postprocessing.rs / mesh.rs on any mesh.  No particles: the [bins] entries are rejected. */
 int ss_surface_from_mesh_f32(ss_context *ctx, const float *verts, uint64_t nv, const uint32_t *tris, uint64_t nt, ss_surface **out);
 
+/* Replaces the mesh of a surface (host or device arrays) and keeps its link to the reconstruction it came from, so that the
+ * particle-based entries above (smoothing weights, SPH normals, attribute interpolation) run on the new vertices -- the hook for
+ * the host-side steps below inside the pipeline (reconstruct.rs:1058-1092 runs them before everything else).  Cached adjacency,
+ * weights and normals are dropped; marching-cubes edge keys no longer apply. */
+int ss_surface_replace_mesh_f32(ss_surface *s, const float *verts, uint64_t nv, const uint32_t *tris, uint64_t nt);
+
+/* ---- sequential half-edge algorithms, HOST code like in the reference (no context, no device needed).
+ * In place on host arrays: verts [*nv x 3] f32, tris [*nt x 3] u32; *nv / *nt are updated (never grow).  keep_vertices != 0 keeps
+ * vertices that lost all their triangles (halfedge_mesh.rs:92-100, :446-497).  Optional output: the vertex-vertex connectivity of
+ * the result in half-edge order as CSR (conn_offsets: nv_in + 1 entries, conn_indices: capacity 3 * nt_in), which the reference
+ * returns as Vec<Vec<usize>>.
+ *
+ * marching_cubes_cleanup (postprocessing.rs:99-242, "mesh displacement" after Moore & Warren): every vertex is assigned its nearest
+ * grid point; neighbouring vertices with the same grid point are merged by half-edge collapses (halfedge_mesh.rs:204-373) into their
+ * running average, for at most max_iter sweeps.  max_rel_snap_distance < 0 = None; else only vertices within that distance (in cell
+ * sizes) of the grid point take part.  `grid` is the marching-cubes grid of the reconstruction (ss_surface_grid). */
+int ss_mesh_cleanup_f32(float *verts, uint64_t *nv, uint32_t *tris, uint64_t *nt, const ss_grid_f32 *grid, float max_rel_snap_distance,
+                        uint64_t max_iter, int keep_vertices, uint64_t *conn_offsets, uint32_t *conn_indices);
+/* decimation (postprocessing.rs:244-686): merges the single and double "barnacle" configurations of marching-cubes meshes.  The
+ * reference walks hash sets / maps of candidates; here they are walked in ascending vertex order (same result whenever no vertex is
+ * claimed by two candidates, which the candidate filters make the rule). */
+int ss_mesh_decimation_f32(float *verts, uint64_t *nv, uint32_t *tris, uint64_t *nt, int keep_vertices, uint64_t *conn_offsets,
+                           uint32_t *conn_indices);
+
 /* Replaces the surface's normals by [num_vertices * 3] caller-supplied ones (then ss_surface_smooth_normals_f32 smooths any field). */
 int ss_surface_set_normals_f32(ss_surface *s, const float *normals);
 

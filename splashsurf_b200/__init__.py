@@ -139,6 +139,9 @@ def _bind(L):
     L.ss_surface_vertex_connectivity.argtypes = [vp, vp, vp, C.POINTER(u64)]
     L.ss_surface_from_mesh_f32.argtypes = [vp, vp, u64, vp, u64, C.POINTER(vp)]
     L.ss_surface_set_normals_f32.argtypes = [vp, vp]
+    L.ss_surface_replace_mesh_f32.argtypes = [vp, vp, u64, vp, u64]
+    L.ss_mesh_cleanup_f32.argtypes = [vp, C.POINTER(u64), vp, C.POINTER(u64), C.POINTER(_Grid), C.c_float, u64, C.c_int, vp, vp]
+    L.ss_mesh_decimation_f32.argtypes = [vp, C.POINTER(u64), vp, C.POINTER(u64), C.c_int, vp, vp]
     if L.ss_abi_version() != 2:
         raise ImportError("libsplashsurf_b200.so ABI version mismatch")
     return L
@@ -219,6 +222,47 @@ class VertexVertexConnectivity:
         return [self.indices[int(self.offsets[i]):int(self.offsets[i + 1])].tolist() for i in range(self._nv)]
 
     take_connectivity = copy_connectivity
+
+
+def _grid_struct(grid: "UniformGrid") -> _Grid:
+    g = _Grid()
+    for d in range(3):
+        g.aabb_min[d] = float(grid.aabb.min[d]); g.aabb_max[d] = float(grid.aabb.max[d])
+        g.points_per_dim[d] = int(grid.npoints_per_dim[d]); g.cells_per_dim[d] = int(grid.ncells_per_dim[d])
+    g.cell_size = float(grid.cell_size)
+    return g
+
+
+def _host_mesh_op(mesh: "TriMesh3d", call) -> "VertexVertexConnectivity":
+    """Runs an in-place host mesh operation of the library (ss_mesh_*_f32) on `mesh` and returns the connectivity it reports."""
+    L = load_library()
+    v = np.ascontiguousarray(mesh.vertices, dtype=np.float32).copy()
+    t = np.ascontiguousarray(mesh.triangles, dtype=np.uint32).copy()
+    nv, nt = C.c_uint64(len(v)), C.c_uint64(len(t))
+    off = np.zeros(len(v) + 1, np.uint64)
+    idx = np.empty(max(3 * len(t), 1), np.uint32)
+    _check(L, call(L, v.ctypes.data if len(v) else None, C.byref(nv), t.ctypes.data if len(t) else None, C.byref(nt), off.ctypes.data, idx.ctypes.data))
+    mesh.vertices = v[:nv.value].copy()
+    mesh.triangles = t[:nt.value].astype(np.uint64)
+    off = off[:nv.value + 1].copy()
+    return VertexVertexConnectivity(off, idx[:int(off[-1])].copy(), mesh.triangles, nv.value)
+
+
+def marching_cubes_cleanup(mesh: "TriMesh3d", grid: "UniformGrid", *, max_rel_snap_dist: Optional[float] = None, max_iter: int = 5,
+                           keep_vertices: bool = False) -> "VertexVertexConnectivity":
+    """``pysplashsurf.marching_cubes_cleanup`` (postprocessing.rs:99-242): simplifies a marching-cubes mesh in place by merging
+    vertices that share their nearest grid point; returns the vertex-vertex connectivity of the result.  Host code in the library
+    (sequential half-edge collapses, as in the reference)."""
+    g = _grid_struct(grid)
+    snap = -1.0 if max_rel_snap_dist is None else float(max_rel_snap_dist)
+    return _host_mesh_op(mesh, lambda L, v, nv, t, nt, off, idx: L.ss_mesh_cleanup_f32(v, nv, t, nt, C.byref(g), C.c_float(snap), int(max_iter),
+                                                                                        int(bool(keep_vertices)), off, idx))
+
+
+def barnacle_decimation(mesh: "TriMesh3d", *, keep_vertices: bool = False) -> "VertexVertexConnectivity":
+    """``pysplashsurf.barnacle_decimation`` (postprocessing.rs:244-686): merges the single and double barnacle configurations of a
+    marching-cubes mesh in place; returns the vertex-vertex connectivity of the result."""
+    return _host_mesh_op(mesh, lambda L, v, nv, t, nt, off, idx: L.ss_mesh_decimation_f32(v, nv, t, nt, int(bool(keep_vertices)), off, idx))
 
 
 class _MeshSurface:
@@ -541,13 +585,17 @@ def reconstruction_pipeline(particles, *, attributes_to_interpolate=None, partic
     Laplacian smoothing, SPH or area-weighted normals (at the smoothed vertices), normal smoothing and SPH interpolation of
     float32 particle attributes.  Returns ``(MeshWithData, SurfaceReconstruction)``; the reconstruction holds the raw mesh.
 
-    The remaining switches of the reference pipeline (mesh cleanup, barnacle decimation, quad conversion, mesh AABB clamping,
-    mesh checks) are sequential half-edge / CPU steps outside the device path and raise NotImplementedError when enabled."""
-    passive = ("mesh_cleanup_snap_dist", "keep_vertices", "quad_max_edge_diag_ratio", "quad_max_normal_angle", "quad_max_interior_angle",
-               "mesh_aabb_clamp_vertices")
+    ``mesh_cleanup`` (+ ``mesh_cleanup_snap_dist``, 5 sweeps) and ``decimate_barnacles`` (+ ``keep_vertices``) run first, as in
+    reconstruct.rs:1058-1092 -- sequential half-edge collapses on the host (library entries ss_mesh_cleanup_f32 /
+    ss_mesh_decimation_f32), after which the new mesh goes back to the device for the remaining steps.  The other switches of the
+    reference pipeline (quad conversion, mesh AABB clamping, mesh checks) raise NotImplementedError when enabled."""
+    passive = ("mesh_cleanup", "decimate_barnacles", "mesh_cleanup_snap_dist", "keep_vertices", "quad_max_edge_diag_ratio", "quad_max_normal_angle",
+               "quad_max_interior_angle", "mesh_aabb_clamp_vertices")
     enabled = [k for k, v in post.items() if v not in (False, None, 0) and k not in passive]
     if enabled:
         raise NotImplementedError(f"post-processing not provided by the device path: {enabled}")
+    mesh_cleanup, decimate_barnacles = bool(post.get("mesh_cleanup", False)), bool(post.get("decimate_barnacles", False))
+    keep_vertices, snap_dist = bool(post.get("keep_vertices", False)), post.get("mesh_cleanup_snap_dist", None)
     arr = np.asarray(particles)
     if arr.dtype != np.float32:
         raise TypeError("unsupported scalar type: the device path reconstructs float32 particles only")
@@ -571,7 +619,17 @@ def reconstruction_pipeline(particles, *, attributes_to_interpolate=None, partic
     s = ctx.reconstruct_raw(arr.ctypes.data, len(arr), p)
     try:
         rec = _collect(ctx, s, len(arr), p, with_debug, False)                  # raw mesh, densities, grids
-        nv = rec.mesh.nvertices
+        out_mesh = rec.mesh
+        if mesh_cleanup or decimate_barnacles:                                  # reconstruct.rs:1058-1092
+            out_mesh = rec.mesh.copy()
+            if mesh_cleanup:
+                marching_cubes_cleanup(out_mesh, rec.grid, max_rel_snap_dist=snap_dist, max_iter=5, keep_vertices=keep_vertices)
+            if decimate_barnacles:
+                barnacle_decimation(out_mesh, keep_vertices=keep_vertices)
+            t32 = np.ascontiguousarray(out_mesh.triangles, dtype=np.uint32)
+            _check(L, L.ss_surface_replace_mesh_f32(s, out_mesh.vertices.ctypes.data if out_mesh.nvertices else None, out_mesh.nvertices,
+                                                    t32.ctypes.data if len(t32) else None, len(t32)))
+        nv = out_mesh.nvertices
         point = {}
         weights_used = bool(mesh_smoothing_weights)
         if weights_used:                                                        # reconstruct.rs:1159-1258 (at the raw vertices)
@@ -582,7 +640,7 @@ def reconstruction_pipeline(particles, *, attributes_to_interpolate=None, partic
                 point["wnn"], point["sw"] = wnn, sw
         if mesh_smoothing_iters is not None:                                    # reconstruct.rs:1261-1279, beta = 1
             _check(L, L.ss_surface_laplacian_smoothing_f32(s, int(mesh_smoothing_iters), C.c_float(1.0), None))
-        verts = rec.mesh.vertices
+        verts = out_mesh.vertices
         if mesh_smoothing_iters:
             verts = np.empty((nv, 3), np.float32)
             _check(L, L.ss_surface_copy_vertices(s, verts.ctypes.data))
@@ -609,7 +667,7 @@ def reconstruction_pipeline(particles, *, attributes_to_interpolate=None, partic
             _check(L, L.ss_surface_interpolate_quantity_f32(s, vals.ctypes.data if len(vals) else None, dim, 1, out.ctypes.data if nv else None))
             point[name] = out
         rec.normals = point.get("normals")
-        mesh = TriMesh3d(verts, rec.mesh.triangles)
+        mesh = TriMesh3d(verts, out_mesh.triangles)
         return MeshWithData(mesh, point, {}), rec
     finally:
         ctx.free_surface(s)

@@ -1613,3 +1613,4 @@ extern "C" int ss_surface_copy_neighbor_lists(const ss_surface *s, uint64_t *off
 extern "C" int ss_surface_timings(const ss_surface *s, ss_timings *o) { if (!s || !o) return SS_ERR_INVALID_PARAMETER; *o = s->tm; return SS_OK; }
 
 #include "ss_post.cuh"
+#include "ss_meshproc.inc"

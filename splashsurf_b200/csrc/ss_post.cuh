@@ -469,6 +469,31 @@ extern "C" int ss_surface_from_mesh_f32(ss_context *c, const float *verts, uint6
     }
 }
 
+// Replaces the mesh of a surface (host or device arrays), e.g. after the host-side clean-up / decimation of SURVEY 8(f.4), and keeps
+// the surface's link to its reconstruction: the SPH-based entries (smoothing weights, SPH normals, attribute interpolation) keep
+// working on the new vertices.  Cached adjacency, weights and normals are dropped; the marching-cubes edge keys no longer apply.
+extern "C" int ss_surface_replace_mesh_f32(ss_surface *s, const float *verts, uint64_t nv, const uint32_t *tris, uint64_t nt) {
+    int rc; ss_context *c = pp_context(s, false, &rc);
+    if (!c) return rc;
+    if ((nv && !verts) || (nt && !tris)) return ss_fail(SS_ERR_INVALID_PARAMETER, "NULL argument");
+    if (nv >= 0x7fffffffull || nt * 6 >= 0x7fffffffull) return ss_fail(SS_ERR_INDEX_TOO_SMALL, "mesh too large for device post-processing");
+    try {
+        CK(cudaSetDevice(c->device));
+        cudaStream_t st = c->stream;
+        s->verts.ensure(std::max<uint64_t>(nv, 1) * 12); s->tris.ensure(std::max<uint64_t>(nt, 1) * 12);
+        if (nv) CK(cudaMemcpyAsync(s->verts.p, verts, nv * 12, cudaMemcpyDefault, st));
+        if (nt) CK(cudaMemcpyAsync(s->tris.p, tris, nt * 12, cudaMemcpyDefault, st));
+        CK(cudaStreamSynchronize(st));
+        s->nv = nv; s->nt = nt;
+        s->has_adj = s->has_inc = s->has_weights = s->has_normals = 0;
+        s->vkeys.release();
+        return SS_OK;
+    } catch (const SsCudaError &err) {
+        cudaGetLastError();
+        return ss_fail(err.e == cudaErrorMemoryAllocation ? SS_ERR_OUT_OF_MEMORY : SS_ERR_CUDA, std::string(err.what) + ": " + cudaGetErrorString(err.e));
+    }
+}
+
 // Replaces the surface's normals by caller-supplied ones ([nv * 3], host or device), e.g. to smooth an arbitrary normal field
 // with ss_surface_smooth_normals_f32.
 extern "C" int ss_surface_set_normals_f32(ss_surface *s, const float *normals) {

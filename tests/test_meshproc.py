@@ -1,0 +1,99 @@
+"""marching-cubes clean-up and barnacle decimation (host code of the library, csrc/ss_meshproc.inc) against the
+reference's own outputs -- a committed fixture generated from the reference wheel (tools/make_golden_meshproc.py) and, where the
+wheel is present (build container and GPU box), live runs on further meshes.  Both algorithms are sequential and deterministic
+for a given vertex / triangle order, so parity is bit-exact: vertex positions, triangle indices and their order.  These tests need
+no GPU: the entries take host arrays and no context."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+
+def _grid(ss, g):
+    return ss.UniformGrid(ss.Aabb3d(g["grid_min"], g["grid_max"]), float(g["cell_size"]), [int(v) for v in g["npoints"]], [int(v) for v in g["ncells"]])
+
+
+def _same(mesh, v, t):
+    return mesh.vertices.shape == v.shape and np.array_equal(mesh.vertices.view(np.uint32), v.view(np.uint32)) and \
+        mesh.triangles.shape == t.shape and np.array_equal(mesh.triangles, t.astype(np.uint64))
+
+
+@pytest.mark.parametrize("tag,snap,keep", [("cleanup", None, False), ("cleanup_snap03", 0.3, False), ("cleanup_keep", None, True)])
+def test_marching_cubes_cleanup_matches_reference_fixture(ss, tag, snap, keep):
+    g = load_golden("meshproc_ref")
+    m = ss.TriMesh3d(g["vertices"].copy(), g["triangles"].astype(np.uint64))
+    conn = ss.marching_cubes_cleanup(m, _grid(ss, g), max_rel_snap_dist=snap, max_iter=5, keep_vertices=keep)
+    assert _same(m, g[tag + "_v"], g[tag + "_t"])
+    # the connectivity it returns is the one of the new mesh (halfedge_mesh.rs:92-100)
+    lists = conn.copy_connectivity()
+    assert len(lists) == m.nvertices
+    want = [set() for _ in range(m.nvertices)]
+    for a, b, c in m.triangles.astype(np.int64):
+        want[a] |= {b, c}; want[b] |= {a, c}; want[c] |= {a, b}
+    assert all(set(l) == w and len(l) == len(w) for l, w in zip(lists, want))
+    if keep:
+        assert m.nvertices == len(g["vertices"]) and sum(1 for l in lists if not l) == len(g["vertices"]) - len(g["cleanup_v"])
+
+
+def test_barnacle_decimation_matches_reference_fixture(ss):
+    g = load_golden("meshproc_ref")
+    m = ss.TriMesh3d(g["vertices"].copy(), g["triangles"].astype(np.uint64))
+    conn = ss.barnacle_decimation(m)
+    assert _same(m, g["decimated_v"], g["decimated_t"])
+    assert len(g["decimated_v"]) < len(g["vertices"])                      # the fixture does contain barnacle configurations
+    # connectivity: same neighbour sets as the reference reports (their order inside a list follows the order of the collapses,
+    # which the reference takes from a hash map)
+    assert np.array_equal(conn.offsets, g["decimated_conn_offsets"])
+    mine = np.concatenate([sorted(l) for l in conn.copy_connectivity()]).astype(np.uint32)
+    assert np.array_equal(mine, g["decimated_conn_sorted"])
+    # chained like the pipeline does (reconstruct.rs:1058-1092): clean-up, then decimation
+    m2 = ss.TriMesh3d(g["cleanup_snap03_v"].copy(), g["cleanup_snap03_t"].astype(np.uint64))
+    ss.barnacle_decimation(m2)
+    assert _same(m2, g["cleanup_snap03_decimated_v"], g["cleanup_snap03_decimated_t"])
+
+
+def test_meshproc_edge_cases(ss):
+    g = load_golden("meshproc_ref")
+    grid = _grid(ss, g)
+    empty = ss.TriMesh3d(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint64))
+    assert ss.marching_cubes_cleanup(empty, grid).copy_connectivity() == [] and empty.nvertices == 0
+    assert ss.barnacle_decimation(empty).copy_connectivity() == []
+    # a single triangle (every edge is a boundary edge: nothing can collapse, halfedge_mesh.rs:204-256)
+    one = ss.TriMesh3d(np.array([[0.1, 0.1, 0.1], [0.12, 0.1, 0.1], [0.1, 0.12, 0.1]], np.float32) + g["grid_min"], np.array([[0, 1, 2]], np.uint64))
+    ss.marching_cubes_cleanup(one, grid)
+    assert one.nvertices == 3 and one.ncells == 1
+    # a vertex outside of the grid: the reference panics (unwrap); here an error code
+    bad = ss.TriMesh3d(np.array([[1e6, 0, 0], [0, 0, 0], [0, 1, 0]], np.float32), np.array([[0, 1, 2]], np.uint64))
+    with pytest.raises(ss.SplashsurfError) as e:
+        ss.marching_cubes_cleanup(bad, grid)
+    assert e.value.code == 6                                               # SS_ERR_INVALID_PARAMETER
+    with pytest.raises(ss.SplashsurfError):
+        ss.barnacle_decimation(ss.TriMesh3d(np.zeros((2, 3), np.float32), np.array([[0, 1, 5]], np.uint64)))      # index out of range
+
+
+@pytest.mark.parametrize("case", ["cube_c05", "dam_snap05_keep"])
+def test_meshproc_matches_reference_live(ss, oracle_mod, case):
+    """Live against the wheel on other meshes (larger, other cell sizes), when the wheel is present."""
+    if not oracle_mod.reference_available():
+        pytest.skip("reference wheel not unpacked (oracle/_ref)")
+    from splashsurf_b200 import synthetic as syn
+    ps = oracle_mod.reference()
+    if case == "cube_c05":
+        p, kw, snap, keep = syn.jittered_cube(14, 0.025, 5), dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.5), None, False
+    else:
+        p, kw, snap, keep = syn.dam_break_scaled(30000, 0.01, 9), dict(particle_radius=0.01, smoothing_length=2.0, cube_size=0.6), 0.5, True
+    rec = ps.reconstruct_surface(p, iso_surface_threshold=0.6, subdomain_grid=True, **kw)
+    rg = rec.grid
+    grid = ss.UniformGrid(ss.Aabb3d(np.asarray(rg.aabb.min, np.float32), np.asarray(rg.aabb.max, np.float32)), float(rg.cell_size),
+                          list(rg.npoints_per_dim), list(rg.ncells_per_dim))
+    v0, t0 = np.array(rec.mesh.vertices, np.float32), np.array(rec.mesh.triangles, np.uint64)
+    ref = rec.mesh.copy()
+    ps.marching_cubes_cleanup(ref, rg, max_rel_snap_dist=snap, max_iter=5, keep_vertices=keep)
+    mine = ss.TriMesh3d(v0.copy(), t0.copy())
+    ss.marching_cubes_cleanup(mine, grid, max_rel_snap_dist=snap, max_iter=5, keep_vertices=keep)
+    assert _same(mine, np.asarray(ref.vertices), np.asarray(ref.triangles))
+    for start_v, start_t, start_ref in [(v0, t0, rec.mesh.copy()), (mine.vertices, mine.triangles, ref)]:
+        ps.barnacle_decimation(start_ref, keep_vertices=keep)
+        m = ss.TriMesh3d(start_v.copy(), start_t.copy())
+        ss.barnacle_decimation(m, keep_vertices=keep)
+        assert _same(m, np.asarray(start_ref.vertices), np.asarray(start_ref.triangles))

@@ -188,3 +188,42 @@ def test_standalone_mesh_functions(ss, oracle_mod):
     # particle queries are rejected on such a surface (no particles behind it)
     with ss._MeshSurface(v0, t) as m:
         assert m.L.ss_surface_compute_normals_f32(m.s, 1) == 6
+
+
+@pytest.mark.gpu
+def test_pipeline_with_mesh_cleanup_and_decimation(ss, oracle_mod):
+    """SURVEY 8(f.4) inside the pipeline mirror (reconstruct.rs:1058-1092): clean-up + decimation run first (host), the new mesh
+    goes back to the device, and the particle-based steps (weights, smoothing, SPH normals, attribute interpolation) run on it.
+    Checked against (a) the same steps composed by hand from the free functions and the oracle's post-processing on the cleaned
+    mesh, and (b) the reference pipeline's mesh sizes when the wheel is present (its raw mesh has another vertex order, so the
+    collapse sequence -- and with it single vertices -- may differ)."""
+    from oracle import postprocess as pp
+    from splashsurf_b200 import synthetic as syn
+    x = syn.splash((12, 12, 12), 3, 0.025, 515)
+    kw = dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.75, iso_surface_threshold=0.6)
+    rho_attr = np.linspace(0.0, 1.0, len(x), dtype=np.float32)
+    post = dict(mesh_smoothing_iters=3, mesh_smoothing_weights=True, compute_normals=True, sph_normals=True, output_mesh_smoothing_weights=True)
+    mwd, rec = ss.reconstruction_pipeline(x, attributes_to_interpolate={"a": rho_attr}, mesh_cleanup=True, mesh_cleanup_snap_dist=0.5,
+                                          decimate_barnacles=True, **kw, **post)
+    # (a) by hand: raw mesh -> free functions -> oracle post-processing of that mesh
+    raw = ss.reconstruct_surface(x, **kw)
+    m = raw.mesh.copy()
+    ss.marching_cubes_cleanup(m, raw.grid, max_rel_snap_dist=0.5, max_iter=5)
+    ss.barnacle_decimation(m)
+    assert m.nvertices < raw.mesh.nvertices and mwd.mesh.nvertices == m.nvertices and np.array_equal(mwd.mesh.triangles, m.triangles)
+    o = oracle_mod.reconstruct(x, **kw)
+    _, h, _ = oracle_mod.absolute_params(kw["particle_radius"], kw["smoothing_length"], kw["cube_size"])
+    want = pp.pipeline(x, o["particle_densities"], m.vertices, m.triangles.astype(np.int64), particle_radius=0.025, rest_density=1000.0,
+                       compact_support_radius=float(h), attributes={"a": rho_attr}, sph_normals_fn=oracle_mod.sph_normals,
+                       **{k: v for k, v in post.items() if k != "output_mesh_smoothing_weights"})
+    scale = float(np.abs(want["vertices"]).max())
+    assert float(np.abs(mwd.mesh.vertices - want["vertices"]).max()) <= REL * scale
+    for name in ("wnn", "sw", "a"):
+        assert float(np.abs(mwd.point_attributes[name] - want[name]).max()) <= REL * max(float(np.abs(want[name]).max()), 1.0), name
+    assert float(np.abs(mwd.point_attributes["normals"] - want["normals"]).max()) <= 5e-5
+    # (b) the reference pipeline on the same particles
+    if oracle_mod.reference_available():
+        ps = oracle_mod.reference()
+        rm, _ = ps.reconstruction_pipeline(x, mesh_cleanup=True, mesh_cleanup_snap_dist=0.5, decimate_barnacles=True, subdomain_grid=True, **kw, **post)
+        rv, rt = len(np.asarray(rm.mesh.vertices)), len(np.asarray(rm.mesh.triangles))
+        assert abs(rv - mwd.mesh.nvertices) <= 0.01 * rv and abs(rt - mwd.mesh.ncells) <= 0.01 * rt, (rv, rt, mwd.mesh.nvertices, mwd.mesh.ncells)
