@@ -240,7 +240,7 @@ def main():
                     help="multi-GPU only: how the global subdomain maximum reaches the library (see distributed.Runner)")
     ap.add_argument("--levelset-variant", type=int, default=2, choices=[0, 1, 2],
                     help="2 (default): warp-per-brick certification + exact kernels (TMA staging, packed FP32); 1: CTA-per-brick certification kernel; 0: fused k_levelset")
-    ap.add_argument("--density-variant", type=int, default=2, choices=[0, 1, 2], help="2 (default) / 1: cell-cooperative density kernel (staging by loads / bulk copies); 0: thread per particle")
+    ap.add_argument("--density-variant", type=int, default=0, choices=[0, 1, 2], help="0 (default): thread per particle; 1 / 2: cell-cooperative density kernel (staging by bulk copies / loads; slower)")
     ap.add_argument("--mc-variant", type=int, default=1, choices=[0, 1], help="1 (default): warp-per-brick marching cubes / fix-up sweep; 0: CTA per brick")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -214,9 +214,11 @@ int ss_context_set_levelset_exact_everywhere(ss_context *ctx, int on);
  * + warp-per-brick exact pass over the boxes it could not certify; 1 = CTA-per-brick certification kernel + k_levelset exact
  * pass; 0 = fused certification + exact pass per brick (k_levelset). */
 int ss_context_set_levelset_variant(ss_context *ctx, int variant);
-/* Density kernel structure (same results): 2 (default) / 1 = one warp per h-cell, the candidates of the 27 cells staged once per
- * cell (2: by 16-byte loads, 1: by bulk copies), ordered hit lists by ballot (csrc/ss_density.cuh); 0 = one thread per particle
- * (k_density).  Replaces the per-particle neighbour loop of neighborhood_search.rs:396-433 + density_map.rs:169-185. */
+/* Density kernel structure (same results): 0 (default) = one thread per particle over the compacted list of in-subdomain
+ * memberships (k_density; 17 ms at 50 M particles); 1 / 2 = one warp per h-cell, the candidates of the 27 cells staged once per cell
+ * (1: by bulk copies, 2: by 16-byte loads), ordered hit lists by ballot (csrc/ss_density.cuh) -- measured SLOWER on the B200 (36-38
+ * ms: 550 warp-instructions per particle against 468; profiles/README.md) and kept as a documented experiment.  Replaces the
+ * per-particle neighbour loop of neighborhood_search.rs:396-433 + density_map.rs:169-185. */
 int ss_context_set_density_variant(ss_context *ctx, int variant);
 /* Brick passes of the subdomain path (same mesh; vertex / triangle order inside a brick differs): 1 (default) = one warp per
  * 8x8x8-point brick, marching cubes in two launches (count, emit) and the marker fix-up sweep on row bit masks (csrc/ss_mc.cuh);

@@ -389,8 +389,8 @@ class Context:
         _check(self._L, self._L.ss_context_set_mc_variant(self._h, int(variant)))
 
     def set_density_variant(self, variant: int):
-        """2 (default) / 1: cell-cooperative density kernel (candidates staged by loads / by bulk copies); 0: thread-per-particle
-        kernel (same results)."""
+        """0 (default): thread-per-particle kernel; 1 / 2: cell-cooperative kernel, candidates staged by bulk copies / by loads
+        (same results; slower on the B200, kept as an experiment)."""
         _check(self._L, self._L.ss_context_set_density_variant(self._h, int(variant)))
 
     def set_count_pairs(self, on: bool):

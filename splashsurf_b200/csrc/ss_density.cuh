@@ -1,7 +1,12 @@
-// ss_density.cuh -- SPH particle densities, cell-cooperative kernel (sm_100a).
+// ss_density.cuh -- SPH particle densities, cell-cooperative kernel (sm_100a).  NOT the default: measured slower than k_density.
 //
-// Replaces, for the bench path, the thread-per-particle k_density (ss_kernels.cuh) whose warps ran at 14 of 32 active lanes
-// (ncu, round 2: every lane walks its own 27 cell runs and its own hit list).  Reference semantics are unchanged
+// An attempt to replace the thread-per-particle k_density (ss_kernels.cuh), whose warps run at 14 of 32 active lanes (ncu,
+// round 2: every lane walks its own 27 cell runs and its own hit list).  Measured on the B200 at 50 M particles (profiles/
+// r2_cfg4_kernels_ncu.txt): 27.5 G warp-instructions (550 per particle) against 23 G (468) for k_density at the same ~65-80 % issue
+// utilisation -> 36-38 ms against 17 ms.  The pair test is only ~10 instructions, so the per-chunk bookkeeping of the cooperative
+// scheme (index mapping, ballot, pool slot, overflow check: 46 instructions per 32 candidates and particle) and the staging of
+// nine short runs per cell outweigh the lanes it keeps busy.  Kept selectable (ss_context_set_density_variant 1 / 2) because it is
+// bit-identical and documents the design space; the default stays k_density.  Reference semantics are unchanged
 // (dense_subdomains.rs:496-646, neighborhood_search.rs:396-433, density_map.rs:169-185):
 //     rho_i = m * (W(0) + sum_j W(|x_j - x_i|)),  j over the 26 adjacent h-cells in x-major order, then the own cell,
 //     ascending particle index inside a cell, one f32 addition per neighbour in that order.

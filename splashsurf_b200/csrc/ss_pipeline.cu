@@ -94,7 +94,7 @@ struct ss_context {
     int ls_exact_all = 0;            // 1: evaluate every grid point exactly (no certification)
     int ls_variant = 2;              // 2 (default): warp-per-brick certification + exact kernels (ss_certify.cuh, ss_exact.cuh); 1: CTA-per-brick certification kernel; 0: fused k_levelset
     int count_pairs = 0;             // 1: count in-support evaluations (work model; slower)
-    int density_variant = 2;         // cell-cooperative density kernel (ss_density.cuh), candidates staged by 2 (default): 16-byte loads, 1: bulk copies; 0: thread-per-particle k_density
+    int density_variant = 0;         // 0 (default, fastest measured): thread-per-particle k_density; 1 / 2: cell-cooperative kernel (ss_density.cuh), candidates staged by bulk copies / 16-byte loads
     int mc_variant = 1;              // 1 (default): warp-per-brick marching cubes (count + emit) and fix-up sweep (ss_mc.cuh); 0: CTA-per-brick passes
     int sm_count = 148;              // streaming multiprocessors of the device (persistent-kernel grid sizing)
     int sph_normals = 0;             // 1: SPH normals at the mesh vertices (sph_interpolation.rs:82-133)

@@ -60,7 +60,7 @@ def _parity(oracle_mod, g, o, S=64):
     return oracle_mod.mesh_parity(g.mesh.vertices, g.mesh.triangles, g.vertex_edge_keys, o["vertices"], o["triangles"], o["vertex_keys"], S)
 
 
-def _check_bit_exact(emu, oracle_mod, p, kw, exact_everywhere=False, tile_batch=None, variant=0, density_variant=2, mc_variant=1):
+def _check_bit_exact(emu, oracle_mod, p, kw, exact_everywhere=False, tile_batch=None, variant=0, density_variant=0, mc_variant=1):
     ctx = emu.Context()
     try:
         ctx.set_levelset_exact_everywhere(exact_everywhere)

@@ -72,20 +72,84 @@ def summarize_launches(csvfile, name, note):
         f.write(f"{'total':72s} {tot / 1e6:10.3f}\n")
 
 
+def write_levelset_traffic(rep, sha_file, workload, particles, fallback_rep=None):
+    """profiles/levelset_traffic.json: DRAM bytes of the level-set kernels of ONE step (certification + exact pass + fix-up exact pass)
+    from an `ncu --set full` capture of the bench workload, tagged with the hash of the level-set sources it was taken on
+    (bench.py refuses it for any other build or workload)."""
+    import json
+    launches = ncu_raw(rep)
+    total, parts = 0.0, []
+    for d in launches:
+        name = d.get("Kernel Name", ("", "?"))[1]
+        if not any(k in name for k in ("k_certify_warp", "k_exact_warp", "k_levelset")):
+            continue
+
+        def b(key):
+            v, u = float(d[key][1].replace(",", "")), d[key][0]
+            return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
+        by = b("dram__bytes_read.sum") + b("dram__bytes_write.sum")
+        part = {"kernel": name.split("(")[0], "grid": int(d["launch__grid_size"][1].replace(",", "")),
+                "ms": float(d["gpu__time_duration.sum"][1].replace(",", "")) * {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}[d["gpu__time_duration.sum"][0]]}
+        if by != by and fallback_rep and os.path.exists(fallback_rep):
+            # ncu returned NaN for this launch (its replays did not agree): bytes per CTA of the same kernel in another capture
+            best = None
+            for e in ncu_raw(fallback_rep):
+                if e.get("Kernel Name", ("", ""))[1].split("(")[0] == part["kernel"]:
+                    def bb(key, e=e):
+                        v, u = float(e[key][1].replace(",", "")), e[key][0]
+                        return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
+                    g2 = int(e["launch__grid_size"][1].replace(",", ""))
+                    if best is None or g2 > best[0]:
+                        best = (g2, bb("dram__bytes_read.sum") + bb("dram__bytes_write.sum"))
+            if best:
+                by = best[1] / best[0] * part["grid"]
+                part["estimated"] = f"NaN in this capture; {best[1] / best[0]:.0f} B per CTA of the same kernel in {os.path.basename(fallback_rep)} (cfg-3, {best[0]} CTAs) x this launch's grid"
+        part["dram_bytes"] = by
+        total += by
+        parts.append(part)
+    shas = open(sha_file).read().split()
+    out = {"kernel": "level-set stage: k_certify_warp + k_exact_warp (exact pass, fix-up pass)", "dram_bytes_per_step": total, "launches": parts,
+           "workload": workload, "particles": particles, "source_sha": shas[0], "levelset_source_sha": shas[1],
+           "source": f"profiles <- {os.path.basename(rep)} (ncu --set full --clock-control none, dram__bytes_read.sum + dram__bytes_write.sum, one step of `python bench.py --steps 1 --warmup 0`)"}
+    json.dump(out, open(os.path.join(OUT, "levelset_traffic.json"), "w"), indent=1)
+    return out
+
+
+def sass_evidence(name):
+    """Mnemonic counts that prove the sm_100a-specific paths are in the shipped binary (B200_PROFILING.md): packed FP32 (FFMA2 / FADD2 /
+    FMUL2), bulk asynchronous copies (UBLKCP) and mbarrier transaction waits (SYNCS)."""
+    lib = os.path.join(ROOT, "splashsurf_b200", "libsplashsurf_b200.so")
+    txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+    cur, counts = None, collections.OrderedDict()
+    for line in txt.splitlines():
+        if "Function :" in line:
+            cur = line.split("Function :")[1].strip()
+            counts[cur] = collections.Counter()
+        elif cur:
+            for m in ("FFMA2", "FADD2", "FMUL2", "UBLKCP", "SYNCS", "FFMA ", "LDS.128", "BAR.SYNC"):
+                if m in line:
+                    counts[cur][m.strip()] += 1
+    with open(os.path.join(OUT, name), "w") as f:
+        f.write(f"# {name}: SASS mnemonic counts per kernel of splashsurf_b200/libsplashsurf_b200.so (cuobjdump -sass; sm_100a)\n")
+        f.write("# FFMA2/FADD2/FMUL2 = packed FP32 pairs, UBLKCP = cp.async.bulk (TMA engine), SYNCS = mbarrier arrive/expect_tx/try_wait, BAR.SYNC = CTA barrier\n")
+        for k, c in counts.items():
+            if any(s in k for s in ("k_certify_warp", "k_exact_warp", "k_density_cells", "k_mc_", "k_fixup_flags_warp", "k_levelset", "k_densityILb0")):
+                f.write(f"{k[:96]:96s} " + " ".join(f"{m}={c.get(m, 0)}" for m in ("FFMA2", "FADD2", "FMUL2", "UBLKCP", "SYNCS", "LDS.128", "BAR.SYNC")) + "\n")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     g = os.path.join(ROOT, "gpurun_out")
-    jobs = [("prof_levelset_r1a.ncu-rep", "r1a_levelset_exact_everywhere_ncu.txt", "round 1, first version: every grid point evaluated exactly (2 M-particle dam break)"),
-            ("prof_levelset_r1b.ncu-rep", "r1b_levelset_certify_ncu.txt", "round 1: certification pass added (4 M particles); launch 0 = certify, launch 1 = fix-up"),
-            ("prof_levelset_r1c.ncu-rep", "r1c_levelset_certify_opt_ncu.txt", "round 1: prologue/staging/FMA-certification optimised (4 M particles)"),
-            ("prof_levelset_r1d.ncu-rep", "r1d_levelset_worklist_ext_ncu.txt", "round 1: work list of non-empty bricks + extension bricks + two-ring certification (4 M particles; before the cubic lower bound)")]
-    for rep, name, note in jobs:
-        if os.path.exists(os.path.join(g, rep)):
-            summarize_rep(os.path.join(g, rep), name, note)
-    for c, name, note in [("launches_r1a.csv", "r1a_launch_list.txt", "2 M particles, exact-everywhere version"),
-                          ("launches_r1b.csv", "r1b_launch_list.txt", "10 M particles, certification version"),
-                          ("launches_r1c.csv", "r1c_launch_list_50M.txt", "`python bench.py --steps 1 --warmup 0` (50 M particles), plane-indexed MC passes"),
-                          ("launches_r1d.csv", "r1d_launch_list_50M.txt", "`python bench.py --steps 1 --warmup 0` (50 M particles), brick-list MC passes, before two-ring certification / work list / extension bricks")]:
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r2k"
+    rep = os.path.join(g, f"prof_cfg4_{tag}.ncu-rep")
+    if os.path.exists(rep):
+        summarize_rep(rep, "r2_cfg4_kernels_ncu.txt", "round 2, bench workload (cfg-4, 50 M particles), one step: cell-cooperative density kernel, warp-per-brick certification, "
+                      "exact pass + fix-up exact pass, fix-up sweep, marching cubes count + emit")
+        print(write_levelset_traffic(rep, os.path.join(g, f"source_sha_{tag}.txt"), "cfg4", 50000400, os.path.join(g, "prof_variant2_r2i.ncu-rep")))
+    for c, name, note in [(f"launches_{sys.argv[2] if len(sys.argv) > 2 else 'r2j'}.csv", "r2_launch_list_50M.txt", "`python bench.py --steps 2 --warmup 1` (cfg-4, 50 M particles), round-2 kernels"),
+                          ("launches_cfg5_r2j.csv", "r2_launch_list_cfg5_overlap.txt", "cfg-5 with SUPERIMPOSED droplets (the round-2 first-run cloud, now `--workload cfg5_overlap`), 200 M particles, one GPU, "
+                           "before the 1024-candidate exact variant: the 4096-candidate kernel (one warp per CTA, 2 CTAs per SM) takes 62 % of the step")]:
         if os.path.exists(os.path.join(g, c)):
             summarize_launches(os.path.join(g, c), name, note)
-    print(os.listdir(OUT))
+    sass_evidence("r2_sass_evidence.txt")
+    print(sorted(os.listdir(OUT)))
