@@ -27,7 +27,7 @@ fi
 if has bench; then
   for proto in ${SS_PROTOCOLS:-callback two_call}; do
     echo "== bench, $N ranks, runner protocol $proto"
-    run $N 900 29641 bench.py --gpus "$N" --steps 10 --warmup 5 --runner-protocol $proto > gpurun_out/bench_${N}gpu_${proto}_$TAG.json 2> gpurun_out/bench_${N}gpu_${proto}_$TAG.err
+    run $N 900 29641 bench.py --gpus "$N" --steps ${SS_STEPS:-20} --warmup 5 --runner-protocol $proto > gpurun_out/bench_${N}gpu_${proto}_$TAG.json 2> gpurun_out/bench_${N}gpu_${proto}_$TAG.err
     python - <<PY
 import json
 try:
