@@ -236,7 +236,7 @@ def main():
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS), help="BASELINE config (default cfg4 = the metric's 50 M dam break)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sph-normals", action="store_true", help="also compute SPH normals at the mesh vertices (cfg-5; sph_interpolation.rs:82-133)")
-    ap.add_argument("--runner-protocol", default="two_call", choices=["two_call", "callback"],
+    ap.add_argument("--runner-protocol", default="stats", choices=["stats", "two_call", "callback"],
                     help="multi-GPU only: how the global subdomain maximum reaches the library (see distributed.Runner)")
     ap.add_argument("--levelset-variant", type=int, default=2, choices=[0, 1, 2],
                     help="2 (default): warp-per-brick certification + exact kernels (TMA staging, packed FP32); 1: CTA-per-brick certification kernel; 0: fused k_levelset")

@@ -144,6 +144,13 @@ uint64_t ss_surface_max_subdomain_particles(const ss_surface *s);
  * them across ranks (NCCL) and cuts the layers into slabs. */
 int ss_partition_stats_f32(ss_context *ctx, const float *xyz_dev, uint64_t n, const ss_grid_f32 *grid, uint32_t subdomain_cubes,
                            int axis, uint32_t *hist_dev, uint32_t *occ_dev);
+/* Plan statistics with the exact ghost classifier (dense_subdomains.rs:1810-1905): members[slot] = how many of these particles are
+ * members (owner or ghost) of subdomain `slot` (nsd_x * nsd_y * nsd_z u32, device memory); hist as in ss_partition_stats_f32.  Summed
+ * over all ranks, max(members) is the global maximum subdomain population of the sparse rule (:1242-1251), so a runner can pass it
+ * to ss_reconstruct_partition_f32 directly (no decomposition pre-pass, no callback), and members > 0 marks the occupied tiles. */
+int ss_partition_members_f32(ss_context *ctx, const float *xyz_dev, uint64_t n, const ss_params_f32 *params, const ss_grid_f32 *grid, int axis,
+                             uint32_t *hist_dev, uint32_t *members_dev);
+
 /* Halo packing for the one exchange step: destination d receives the particles with lo[d] <= xyz[axis] < hi[d] (a particle may go
  * to several destinations), grouped by destination, ascending index inside a destination.  Call once with send_dev == NULL to
  * get counts_out[world] (host), then with a device buffer of sum(counts) * 3 floats. */

@@ -124,6 +124,7 @@ def _bind(L):
     L.ss_reconstruct_partition_f32.argtypes = [vp, vp, u64, C.POINTER(_Params), C.POINTER(_Grid), C.c_int, i64, i64, i64, u64, C.c_int, C.POINTER(vp)]
     L.ss_reconstruct_partition_cb_f32.argtypes = [vp, vp, u64, C.POINTER(_Params), C.POINTER(_Grid), C.c_int, i64, i64, i64, vp, vp, C.POINTER(vp)]
     L.ss_partition_stats_f32.argtypes = [vp, vp, u64, C.POINTER(_Grid), C.c_uint32, C.c_int, vp, vp]
+    L.ss_partition_members_f32.argtypes = [vp, vp, u64, C.POINTER(_Params), C.POINTER(_Grid), C.c_int, vp, vp]
     L.ss_partition_pack_f32.argtypes = [vp, vp, u64, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_uint32, C.POINTER(C.c_uint64), vp]
     L.ss_surface_max_subdomain_particles.argtypes = [vp]
     L.ss_surface_max_subdomain_particles.restype = u64

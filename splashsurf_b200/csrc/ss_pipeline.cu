@@ -1258,6 +1258,59 @@ extern "C" int ss_partition_stats_f32(ss_context *c, const float *xyz, uint64_t 
     }
 }
 
+// Plan statistics with the EXACT classifier: `members[slot]` = number of particles of this rank's input that are members (owner or
+// ghost, dense_subdomains.rs:1810-1905) of subdomain `slot` -- summed over the ranks this is the subdomain's population, so the
+// global maximum (sparse rule, dense_subdomains.rs:1242-1251) is known BEFORE any rank decomposes: the runner needs neither the
+// decomposition pre-pass nor the callback.  `hist` as in ss_partition_stats_f32 (owner layer counts, for the balance only).
+__global__ void k_part_members(SsDev P, const float *__restrict__ xyz, uint32_t n, int axis, uint32_t *__restrict__ hist, uint32_t *__restrict__ members) {
+    __shared__ uint32_t s_hist[1024];
+    const int nax = P.nsd[axis];
+    for (int t = threadIdx.x; t < nax && t < 1024; t += blockDim.x) s_hist[t] = 0;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float px = xyz[3 * (uint64_t)i], py = xyz[3 * (uint64_t)i + 1], pz = xyz[3 * (uint64_t)i + 2];
+        const float pc = axis == 0 ? px : (axis == 1 ? py : pz);
+        const int ia = min(max(ss_cell_of(pc, P.gmin[axis], P.sub_size), 0), nax - 1);
+        if (ia < 1024) atomicAdd(&s_hist[ia], 1u); else atomicAdd(&hist[ia], 1u);
+        ss_classify(P, px, py, pz, [&](int, int flat) { atomicAdd(&members[flat], 1u); });
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nax && t < 1024; t += blockDim.x) if (s_hist[t]) atomicAdd(&hist[t], s_hist[t]);
+}
+extern "C" int ss_partition_members_f32(ss_context *c, const float *xyz, uint64_t n, const ss_params_f32 *p, const ss_grid_f32 *grid, int axis,
+                                        uint32_t *hist, uint32_t *members) {
+    if (!c || !grid || !hist || !members || (n && !xyz) || axis < 0 || axis > 2) return ss_fail(SS_ERR_INVALID_PARAMETER, "bad argument");
+    int rc = validate_params(p);
+    if (rc) return rc;
+    if (n >= 0xfffffff0ull) return ss_fail(SS_ERR_INDEX_TOO_SMALL, "too many particles");
+    try {
+        CK(cudaSetDevice(c->device));
+        // the decomposition parameters exactly as run_subdomain_grid derives them (dense_subdomains.rs:89-244)
+        const int64_t S = (int64_t)p->subdomain_num_cubes_per_dim;
+        const float h = p->compact_support_radius, cs = p->cube_size;
+        SsDev D{};
+        D.sub_size = fmulr(cs, (float)S);
+        D.margin = fmulr(fmulr(ceilf(fdivr(h, cs)), cs), 1.01f);
+        D.srad = (int)ceilf(fdivr(D.margin, D.sub_size));
+        if (D.srad > 8) return ss_fail(SS_ERR_INVALID_PARAMETER, "ghost margin spans more than 8 subdomains; increase subdomain_num_cubes_per_dim");
+        uint64_t nslots = 1;
+        for (int d = 0; d < 3; ++d) { D.gmin[d] = grid->aabb_min[d]; D.nsd[d] = (int)((grid->cells_per_dim[d] + S - 1) / S); nslots *= (uint64_t)D.nsd[d]; }
+        if (nslots >= 2147483647ull) return ss_fail(SS_ERR_INDEX_TOO_SMALL, "too many subdomain slots");
+        D.part_axis = 0; D.keep_lo = 0; D.keep_hi = 0x7fffffff;
+        CK(cudaMemsetAsync(hist, 0, (size_t)D.nsd[axis] * 4, c->stream));
+        CK(cudaMemsetAsync(members, 0, (size_t)nslots * 4, c->stream));
+        if (n) {
+            const unsigned blocks = (unsigned)std::min<uint64_t>(nblk(n, 256), (uint64_t)c->sm_count * 8);
+            LAUNCH(c, k_part_members, blocks, 256, D, xyz, (uint32_t)n, axis, hist, members);
+        }
+        CK(cudaStreamSynchronize(c->stream));
+        return SS_OK;
+    } catch (const SsCudaError &err) {
+        cudaGetLastError();
+        return ss_fail(SS_ERR_CUDA, std::string(err.what) + ": " + cudaGetErrorString(err.e));
+    }
+}
+
 // Halo packing: destination d takes the particles with lo[d] <= coordinate < hi[d] along the partition axis (one particle may
 // go to several destinations), ascending particle index preserved inside every destination.  One warp walks a chunk of
 // SS_PACK_CHUNK particles in index order; pass 0 counts per (destination, chunk), an exclusive scan over the destination-major

@@ -43,7 +43,7 @@ def test_bench_single_rank_on_executor(oracle_mod, extra):
     assert d["config"]["levelset_variant"] == want and d["roofline"]["launches_per_step"] >= (2 if want else 1)
 
 
-@pytest.mark.parametrize("protocol", ["two_call", "callback"])
+@pytest.mark.parametrize("protocol", ["stats", "two_call", "callback"])
 def test_bench_two_ranks_on_executor(oracle_mod, protocol):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", str(free_port()), LAUNCHER, "bench.py", "--gpus", "2", "--particles", "12000", "--steps", "2",

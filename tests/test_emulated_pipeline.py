@@ -348,7 +348,7 @@ rank, world = dist.get_rank(), dist.get_world_size()
 case = json.loads(os.environ["SS_CASE"])
 p_all = getattr(syn, case["gen"])(*[tuple(a) if isinstance(a, list) else a for a in case["args"]])
 ctx = ss.Context(0)
-runner = ssd.Runner(ctx, ss.make_params(**case["kw"]), world, rank, 0, device="cpu", protocol=case.get("protocol", "two_call"))
+runner = ssd.Runner(ctx, ss.make_params(**case["kw"]), world, rank, 0, device="cpu", protocol=case.get("protocol", "stats"))
 runner.want_keys = True
 x = torch.from_numpy(runner.take_local(p_all))
 for it in range(2):                                             # second step reuses the pooled buffers
@@ -369,7 +369,11 @@ dist.destroy_process_group()
              kw=dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.75, subdomain_num_cubes_per_dim=16, subdomain_grid_auto_disable=False))),
     (3, dict(gen="jittered_cube", args=[7, 0.025, 503], protocol="callback",      # one library call, all-reduce from the callback
              kw=dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.75, subdomain_num_cubes_per_dim=16, subdomain_grid_auto_disable=False))),
-], ids=["2_ranks_dam_break", "3_ranks_one_idle", "3_ranks_one_idle_callback"])
+    (2, dict(gen="splash", args=[[8, 8, 8], 3, 0.025, 504], protocol="two_call",       # decomposition pre-pass + all-reduce + full call
+             kw=dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.75, subdomain_num_cubes_per_dim=16, subdomain_grid_auto_disable=False))),
+    (2, dict(gen="splash", args=[[8, 8, 8], 3, 0.025, 504],                            # same cloud, default protocol: sparse subdomains decided from the statistics
+             kw=dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.75, subdomain_num_cubes_per_dim=16, subdomain_grid_auto_disable=False))),
+], ids=["2_ranks_dam_break", "3_ranks_one_idle", "3_ranks_one_idle_callback", "2_ranks_splash_two_call", "2_ranks_splash_stats"])
 def test_emulated_runner_over_gloo(tmp_path, oracle_mod, world, case):
     """splashsurf_b200.distributed.Runner._step_multi as the bench drives it (plan, halo exchange, two library calls, max
     all-reduce, mesh gather + weld), one process per rank over gloo, library = CPU executor; result vs the single-device oracle."""
@@ -426,7 +430,7 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("protocol", ["callback", "two_call"])
+@pytest.mark.parametrize("protocol", ["stats", "callback", "two_call"])
 def test_emulated_runner_failure_on_one_rank_raises_everywhere(tmp_path, protocol):
     """A failing library call on one rank must not leave the other ranks blocked in a collective: the max-reduce still happens
     on the failing rank (ss_pipeline.cu: ReduceOnce) and the status all-reduce makes every rank raise."""
