@@ -25,7 +25,7 @@ if has parity; then
   tail -2 gpurun_out/parity_cfg4_${N}gpu.err | cut -c1-300
 fi
 if has bench; then
-  for proto in ${SS_PROTOCOLS:-callback two_call}; do
+  for proto in ${SS_PROTOCOLS:-stats}; do
     echo "== bench, $N ranks, runner protocol $proto"
     run $N 900 29641 bench.py --gpus "$N" --steps ${SS_STEPS:-20} --warmup 5 --runner-protocol $proto > gpurun_out/bench_${N}gpu_${proto}_$TAG.json 2> gpurun_out/bench_${N}gpu_${proto}_$TAG.err
     python - <<PY
@@ -36,12 +36,12 @@ try:
 except Exception as e:
     print("bench failed:", e); print(open("gpurun_out/bench_${N}gpu_${proto}_$TAG.err").read()[-2500:])
 PY
-    grep "device ms/step" gpurun_out/bench_${N}gpu_${proto}_$TAG.err | cut -c1-160
+    grep "device ms/step\|runner phases" gpurun_out/bench_${N}gpu_${proto}_$TAG.err | cut -c1-260
   done
 fi
 if has cfg5; then
   echo "== cfg-5 (200 M splash, c = 0.45 r, SPH normals) at $N ranks"
-  run $N 1500 29651 bench.py --gpus "$N" --workload cfg5 --steps 3 --warmup 2 --sph-normals > gpurun_out/bench_cfg5_${N}gpu_$TAG.json 2> gpurun_out/bench_cfg5_${N}gpu_$TAG.err
-  cut -c1-1500 gpurun_out/bench_cfg5_${N}gpu_$TAG.json; tail -5 gpurun_out/bench_cfg5_${N}gpu_$TAG.err | cut -c1-300
+  run $N 1500 29651 bench.py --gpus "$N" --workload cfg5 --steps ${SS_CFG5_STEPS:-6} --warmup ${SS_CFG5_WARMUP:-6} --sph-normals > gpurun_out/bench_cfg5_${N}gpu_$TAG.json 2> gpurun_out/bench_cfg5_${N}gpu_$TAG.err
+  cut -c1-1500 gpurun_out/bench_cfg5_${N}gpu_$TAG.json; grep "device ms/step\|runner phases" gpurun_out/bench_cfg5_${N}gpu_$TAG.err | cut -c1-260
 fi
 echo "== session done"
