@@ -763,7 +763,7 @@ static int marching_cubes_batch(ss_context *c, const SsDev &D, bool global_mode,
         CK(cudaStreamSynchronize(st));
         bv = (uint64_t)lv[0] + lv[1]; bt = (uint64_t)lt[0] + lt[1];
     }
-    if (vtotal + bv >= 0xfffffff0ull || (ttotal + bt) * 3 >= 0xffffffffffull) return ss_fail(SS_ERR_INDEX_TOO_SMALL, "mesh too large for 32-bit vertex ids");
+    if (vtotal + bv >= 0xfffffff0ull || ttotal + bt >= 0xfffffff0ull) return ss_fail(SS_ERR_INDEX_TOO_SMALL, "mesh too large for 32-bit vertex / triangle ids");
     if (bv || bt) {
         out->verts.grow_keep((vtotal + bv) * 12, vtotal * 12, st);
         out->vkeys.grow_keep((vtotal + bv) * 8, vtotal * 8, st);

@@ -247,6 +247,11 @@ static void cub_sort_keys64(ss_context *c, const unsigned long long *in, unsigne
 static uint32_t pp_build_csr(ss_context *c, uint32_t n, uint32_t nv, int key_bits, DevBuf &row, DevBuf &idx) {
     cudaStream_t st = c->stream;
     PostScratch &S = c->post;
+    if (n == 0) {                                   // vertices without triangles: empty adjacency lists, like the reference
+        row.ensure(((size_t)nv + 1) * 4); idx.ensure(4);
+        CK(cudaMemsetAsync(row.p, 0, ((size_t)nv + 1) * 4, st));
+        return 0;
+    }
     S.keys_b.ensure((size_t)n * 8); S.flag.ensure((size_t)n * 4); S.scan.ensure((size_t)n * 4 + 4);
     cub_sort_keys64(c, S.keys_a.as<unsigned long long>(), S.keys_b.as<unsigned long long>(), n, key_bits);
     LAUNCH(c, k_pp_flag_unique, nblk(n, 256), 256, S.keys_b.as<unsigned long long>(), n, S.flag.as<uint32_t>());
@@ -268,7 +273,7 @@ static void pp_vertex_adjacency(ss_context *c, ss_surface *s) {          // vert
     if (s->has_adj) return;
     const uint32_t nt = (uint32_t)s->nt, nv = (uint32_t)s->nv;
     c->post.keys_a.ensure((size_t)nt * 6 * 8);
-    LAUNCH(c, k_pp_edge_keys, nblk(nt, 256), 256, s->tris.as<uint32_t>(), nt, c->post.keys_a.as<unsigned long long>());
+    if (nt) LAUNCH(c, k_pp_edge_keys, nblk(nt, 256), 256, s->tris.as<uint32_t>(), nt, c->post.keys_a.as<unsigned long long>());
     pp_build_csr(c, nt * 6, nv, 64, s->adj_row, s->adj_idx);             // 64 bits: the degenerate-pair sentinel sorts last
     s->has_adj = 1;
 }
@@ -276,7 +281,7 @@ static void pp_vertex_triangles(ss_context *c, ss_surface *s) {          // vert
     if (s->has_inc) return;
     const uint32_t nt = (uint32_t)s->nt, nv = (uint32_t)s->nv;
     c->post.keys_a.ensure((size_t)nt * 3 * 8);
-    LAUNCH(c, k_pp_corner_keys, nblk(nt, 256), 256, s->tris.as<uint32_t>(), nt, c->post.keys_a.as<unsigned long long>());
+    if (nt) LAUNCH(c, k_pp_corner_keys, nblk(nt, 256), 256, s->tris.as<uint32_t>(), nt, c->post.keys_a.as<unsigned long long>());
     pp_build_csr(c, nt * 3, nv, 32 + bits_for(nv), s->inc_row, s->inc_idx);
     s->has_inc = 1;
 }

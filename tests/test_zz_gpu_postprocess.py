@@ -227,3 +227,12 @@ def test_pipeline_with_mesh_cleanup_and_decimation(ss, oracle_mod):
         rm, _ = ps.reconstruction_pipeline(x, mesh_cleanup=True, mesh_cleanup_snap_dist=0.5, decimate_barnacles=True, subdomain_grid=True, **kw, **post)
         rv, rt = len(np.asarray(rm.mesh.vertices)), len(np.asarray(rm.mesh.triangles))
         assert abs(rv - mwd.mesh.nvertices) <= 0.01 * rv and abs(rt - mwd.mesh.ncells) <= 0.01 * rt, (rv, rt, mwd.mesh.nvertices, mwd.mesh.ncells)
+
+
+@pytest.mark.gpu
+def test_mesh_without_triangles_has_empty_connectivity(ss):
+    """Vertices without any triangle (e.g. what `keep_vertices` leaves behind): empty adjacency lists like the reference's
+    vertex_vertex_connectivity (their normals are 0/0 = NaN there as well: mesh.rs:879-906 normalises unconditionally)."""
+    m = ss.TriMesh3d(np.random.default_rng(3).random((7, 3)).astype(np.float32), np.zeros((0, 3), np.uint64))
+    assert m.vertex_vertex_connectivity().copy_connectivity() == [[] for _ in range(7)]
+    assert np.isnan(m.vertex_normals_parallel()).all()
