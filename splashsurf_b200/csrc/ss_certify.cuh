@@ -381,6 +381,9 @@ k_certify_warp(SsDev P, SsCwArgs A) {
     const float cert = (P.thr + fabsf(P.thr) * 1.0e-4f + 1.0e-30f) / P.a_sigma;     // compare the un-normalised sum
     const float cull2 = (GLOBAL ? P.rev2 : (sparse ? P.h2m : P.h2)) * 1.0001f;
     const int li = lane >> 3, lj = (lane >> 1) & 3, lk = (lane & 1) * 2;
+    // this lane's first point of sub-box (0, 0, 0); the other sub-boxes are constant strides away
+    float *const lane_out = A.tiles + (size_t)tile_idx * P.np * P.np * P.np + ((size_t)(bx * 8 + li) * P.np + (by * 8 + lj)) * P.np + (bz * 8 + lk);
+    const int np1 = P.np, np2 = P.np * P.np;
     unsigned long long n_eval = 0;
     for (int ha = 0; ha < 2; ++ha) {
         if (bx * 8 + 4 * ha > pmax) break;
@@ -475,7 +478,7 @@ k_certify_warp(SsDev P, SsCwArgs A) {
                 }
             }
             if (done) {
-                float *out = A.tiles + (size_t)tile_idx * P.np * P.np * P.np + ((size_t)i * P.np + j) * P.np + k;
+                float *out = lane_out + (4 * ha * np2 + 4 * hb * np1 + 4 * hc);
                 if (vA) out[0] = SS_MARKER;
                 if (vB) out[1] = SS_MARKER;
             }

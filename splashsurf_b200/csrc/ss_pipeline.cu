@@ -1055,7 +1055,9 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
         CK(cudaMemcpyAsync(c->tile_tab.p, h_tiles.data(), (size_t)nbatch * sizeof(SsTile), cudaMemcpyHostToDevice, st));
         CK(cudaMemsetAsync(c->tiles.p, 0, (size_t)nbatch * np3 * 4, st));
         CK(cudaMemsetAsync(c->bstate.p, 0, (size_t)nbatch * nbricks, st));
-        CK(cudaMemsetAsync(c->vmask.p, 0, (size_t)nbatch * np3, st));
+        // edge masks: the CTA-per-brick marching-cubes passes read the mask of every point of a listed brick (zero = no vertex); the
+        // warp-per-brick passes only read masks their count pass wrote, so they need no zero-fill (4 GB at 50 M particles)
+        if (global_mode || c->mc_variant != 1) CK(cudaMemsetAsync(c->vmask.p, 0, (size_t)nbatch * np3, st));
         CK(cudaEventRecord(c->ev[10], st));
         uint32_t n_mc = 0;
         rc = levelset_batch(c, D, nbatch, nbricks, exact_all, certify_runs, global_mode, out, ls_launches, fix_points, &n_mc);
