@@ -296,8 +296,8 @@ int ss_surface_replace_mesh_f32(ss_surface *s, const float *verts, uint64_t nv, 
 int ss_mesh_cleanup_f32(float *verts, uint64_t *nv, uint32_t *tris, uint64_t *nt, const ss_grid_f32 *grid, float max_rel_snap_distance,
                         uint64_t max_iter, int keep_vertices, uint64_t *conn_offsets, uint32_t *conn_indices);
 /* decimation (postprocessing.rs:244-686): merges the single and double "barnacle" configurations of marching-cubes meshes.  The
- * reference walks hash sets / maps of candidates; here they are walked in ascending vertex order (same result whenever no vertex is
- * claimed by two candidates, which the candidate filters make the rule). */
+ * reference walks hash sets / maps of candidates (std HashMap + fxhash); their iteration order is restated, so the result is the
+ * reference's, vertex for vertex, also where two candidates claim the same vertex. */
 int ss_mesh_decimation_f32(float *verts, uint64_t *nv, uint32_t *tris, uint64_t *nt, int keep_vertices, uint64_t *conn_offsets,
                            uint32_t *conn_indices);
 

@@ -41,11 +41,12 @@ def test_barnacle_decimation_matches_reference_fixture(ss):
     conn = ss.barnacle_decimation(m)
     assert _same(m, g["decimated_v"], g["decimated_t"])
     assert len(g["decimated_v"]) < len(g["vertices"])                      # the fixture does contain barnacle configurations
-    # connectivity: same neighbour sets as the reference reports (their order inside a list follows the order of the collapses,
-    # which the reference takes from a hash map)
+    # connectivity: same neighbour sets as the reference reports
     assert np.array_equal(conn.offsets, g["decimated_conn_offsets"])
     mine = np.concatenate([sorted(l) for l in conn.copy_connectivity()]).astype(np.uint32)
     assert np.array_equal(mine, g["decimated_conn_sorted"])
+    # ... and in the same order inside every list: the collapses happened in the reference's sequence (its hash maps' iteration order)
+    assert np.array_equal(conn.indices, g["decimated_conn"])
     # chained like the pipeline does (reconstruct.rs:1058-1092): clean-up, then decimation
     m2 = ss.TriMesh3d(g["cleanup_snap03_v"].copy(), g["cleanup_snap03_t"].astype(np.uint64))
     ss.barnacle_decimation(m2)

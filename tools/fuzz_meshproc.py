@@ -1,0 +1,75 @@
+#!/usr/bin/env python3
+"""Differential fuzzing of the host mesh clean-up / barnacle decimation (csrc/ss_meshproc.inc) against the REFERENCE
+WHEEL (oracle/_ref): random small clouds -> the wheel's own marching-cubes mesh -> marching_cubes_cleanup / barnacle_decimation in both
+implementations on the same input; vertices and triangles must be identical bit for bit.  No GPU needed.
+
+    python tools/fuzz_meshproc.py --cases 200 --seed 0
+"""
+import argparse, os, sys, time
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+def same(mesh, ref):
+    v, t = np.asarray(ref.vertices), np.asarray(ref.triangles)
+    return mesh.vertices.shape == v.shape and np.array_equal(mesh.vertices.view(np.uint32), v.view(np.uint32)) and \
+        mesh.triangles.shape == t.shape and np.array_equal(mesh.triangles, t)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cases", type=int, default=100)
+    ap.add_argument("--seed", type=int, default=0)
+    a = ap.parse_args()
+    import oracle
+    import splashsurf_b200 as ss
+    from fuzz_emulated import random_case
+    ps = oracle.reference()
+    bad = done = 0
+    t0 = time.time()
+    for i in range(a.cases):
+        seed = a.seed * 1_000_003 + i
+        rng = np.random.default_rng(seed)
+        x, kw, _ = random_case(rng)
+        kw = {k: v for k, v in kw.items() if k in ("particle_radius", "smoothing_length", "cube_size", "iso_surface_threshold", "rest_density")}
+        try:
+            rec = ps.reconstruct_surface(x, subdomain_grid=True, **kw)
+        except BaseException:                       # the reference panics on some random parameter sets
+            continue
+        if len(np.asarray(rec.mesh.vertices)) == 0 or len(np.asarray(rec.mesh.vertices)) > 400_000:
+            continue
+        rg = rec.grid
+        grid = ss.UniformGrid(ss.Aabb3d(np.asarray(rg.aabb.min, np.float32), np.asarray(rg.aabb.max, np.float32)), float(rg.cell_size),
+                              list(rg.npoints_per_dim), list(rg.ncells_per_dim))
+        v0, t0_ = np.array(rec.mesh.vertices, np.float32), np.array(rec.mesh.triangles, np.uint64)
+        snap = [None, 0.25, 0.5, 1.0][int(rng.integers(0, 4))]
+        keep = bool(rng.integers(0, 2))
+        ref = rec.mesh.copy()
+        ps.marching_cubes_cleanup(ref, rg, max_rel_snap_dist=snap, max_iter=int(rng.integers(1, 6)) if False else 5, keep_vertices=keep)
+        mine = ss.TriMesh3d(v0.copy(), t0_.copy())
+        ss.marching_cubes_cleanup(mine, grid, max_rel_snap_dist=snap, max_iter=5, keep_vertices=keep)
+        ok1 = same(mine, ref)
+        ref2 = rec.mesh.copy()
+        ps.barnacle_decimation(ref2, keep_vertices=keep)
+        mine2 = ss.TriMesh3d(v0.copy(), t0_.copy())
+        ss.barnacle_decimation(mine2, keep_vertices=keep)
+        ok2 = same(mine2, ref2)
+        ref3 = ref.copy()
+        ps.barnacle_decimation(ref3, keep_vertices=keep)
+        ss.barnacle_decimation(mine, keep_vertices=keep)
+        ok3 = same(mine, ref3)
+        done += 1
+        if not (ok1 and ok2 and ok3):
+            bad += 1
+            print(f"[{seed}] MISMATCH cleanup={ok1} decimation={ok2} cleanup+decimation={ok3} nv={len(v0)} snap={snap} keep={keep} {kw}")
+        elif done % 20 == 0:
+            print(f"[{seed}] ok nv={len(v0)} -> {mine.nvertices} ({time.time() - t0:.0f}s)", flush=True)
+    print(f"{done} meshes, {bad} mismatches, {time.time() - t0:.0f}s")
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

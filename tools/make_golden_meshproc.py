@@ -34,6 +34,7 @@ out["decimated_v"], out["decimated_t"] = np.asarray(m.vertices, np.float32), np.
 conn = c.copy_connectivity()
 out["decimated_conn_offsets"] = np.concatenate([[0], np.cumsum([len(l) for l in conn])]).astype(np.uint64)
 out["decimated_conn_sorted"] = np.concatenate([sorted(l) for l in conn]).astype(np.uint32)
+out["decimated_conn"] = np.concatenate([list(l) for l in conn]).astype(np.uint32)      # in the reference's half-edge order
 path = os.path.join(ROOT, "tests", "golden", "meshproc_ref.npz")
 np.savez_compressed(path, **out)
 print({k: v.shape for k, v in out.items()}, os.path.getsize(path) // 1024, "KiB")
