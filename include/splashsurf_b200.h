@@ -173,6 +173,11 @@ int ss_levelset_tile_f32(ss_context *ctx, const float *xyz, const float *rho, ui
                          float cube_size, const int64_t subdomain_ijk[3], uint32_t subdomain_cubes,
                          float compact_support_radius, float particle_rest_mass, int mode, float *tile_out);
 
+/* Page-locked host memory (cudaHostAlloc) for callers that have no CUDA binding of their own: result copies into it run at PCIe
+ * speed.  NULL on failure. */
+void *ss_host_alloc_pinned(uint64_t bytes);
+void ss_host_free_pinned(void *p);
+
 /* ---- result accessors (sizes first, then copies into caller-provided HOST buffers) ---- */
 uint64_t ss_surface_num_vertices(const ss_surface *s);
 uint64_t ss_surface_num_triangles(const ss_surface *s);

@@ -140,6 +140,10 @@ def _bind(L):
     L.ss_surface_vertex_connectivity.argtypes = [vp, vp, vp, C.POINTER(u64)]
     L.ss_surface_from_mesh_f32.argtypes = [vp, vp, u64, vp, u64, C.POINTER(vp)]
     L.ss_surface_set_normals_f32.argtypes = [vp, vp]
+    L.ss_host_alloc_pinned.argtypes = [u64]
+    L.ss_host_alloc_pinned.restype = vp
+    L.ss_host_free_pinned.argtypes = [vp]
+    L.ss_host_free_pinned.restype = None
     L.ss_surface_replace_mesh_f32.argtypes = [vp, vp, u64, vp, u64]
     L.ss_mesh_cleanup_f32.argtypes = [vp, C.POINTER(u64), vp, C.POINTER(u64), C.POINTER(_Grid), C.c_float, u64, C.c_int, vp, vp]
     L.ss_mesh_decimation_f32.argtypes = [vp, C.POINTER(u64), vp, C.POINTER(u64), C.c_int, vp, vp]
@@ -361,9 +365,14 @@ class Context:
         h = C.c_void_p()
         _check(self._L, self._L.ss_context_create(int(device), C.byref(h)))
         self._h = h
+        # opt-in: reconstruct_surface / reconstruction_pipeline return their big arrays (vertices, triangles, densities) as views of
+        # page-locked buffers owned by this context -- no fresh pages, copies at PCIe speed -- that the NEXT reconstruction on the
+        # context overwrites (copy what must outlive it)
+        self.reuse_host_buffers = False
 
     def close(self):
         if getattr(self, "_h", None):
+            self._free_host_pool()
             self._L.ss_context_destroy(self._h)
             self._h = None
 
@@ -372,6 +381,31 @@ class Context:
             self.close()
         except Exception:
             pass
+
+    def host_array(self, name: str, shape, dtype) -> np.ndarray:
+        """A numpy view of a page-locked host buffer owned by this context (grown on demand, reused by name): what
+        `reuse_host_buffers` hands out as result arrays.  Valid until the next call that asks for the same name, or `close`."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        pool = self.__dict__.setdefault("_host_pool", {})
+        ptr, cap = pool.get(name, (None, 0))
+        if cap < n or ptr is None:
+            if ptr:
+                self._L.ss_host_free_pinned(ptr)
+            cap = int(n * 1.25) + 4096
+            ptr = self._L.ss_host_alloc_pinned(cap)
+            if not ptr:
+                pool.pop(name, None)
+                raise MemoryError(f"cannot page-lock {cap} bytes for {name}")
+            pool[name] = (ptr, cap)
+        buf = (C.c_char * max(n, 1)).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def _free_host_pool(self):
+        for ptr, _ in self.__dict__.get("_host_pool", {}).values():
+            if ptr:
+                self._L.ss_host_free_pinned(ptr)
+        self.__dict__["_host_pool"] = {}
 
     def set_tile_batch(self, max_tiles: int):
         _check(self._L, self._L.ss_context_set_tile_batch(self._h, int(max_tiles)))
@@ -491,9 +525,13 @@ def reconstruct_surface(particles, *, particle_radius: float, rest_density: floa
 def _collect(ctx: Context, s, n_in: int, p: _Params, debug: bool, tile: bool) -> SurfaceReconstruction:
     L = ctx._L
     nv, nt, n = L.ss_surface_num_vertices(s), L.ss_surface_num_triangles(s), L.ss_surface_num_particles(s)
-    verts = np.empty((nv, 3), dtype=np.float32)
-    tris = np.empty((nt, 3), dtype=np.uint64)
-    dens = np.empty(n, dtype=np.float32)
+    if getattr(ctx, "reuse_host_buffers", False):
+        # opt-in: the big result arrays are views of page-locked buffers of the context, overwritten by its next reconstruction
+        verts, tris, dens = ctx.host_array("vertices", (nv, 3), np.float32), ctx.host_array("triangles", (nt, 3), np.uint64), ctx.host_array("densities", (n,), np.float32)
+    else:
+        verts = np.empty((nv, 3), dtype=np.float32)
+        tris = np.empty((nt, 3), dtype=np.uint64)
+        dens = np.empty(n, dtype=np.float32)
     _check(L, L.ss_surface_copy_vertices(s, verts.ctypes.data))
     _check(L, L.ss_surface_copy_triangles_u64(s, tris.ctypes.data))
     _check(L, L.ss_surface_copy_particle_densities(s, dens.ctypes.data))

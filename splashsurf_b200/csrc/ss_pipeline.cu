@@ -1626,6 +1626,14 @@ extern "C" int ss_surface_copy_particle_inside_aabb(const ss_surface *s, uint8_t
     memcpy(dst, s->inside_aabb.data(), s->inside_aabb.size());
     return SS_OK;
 }
+// Page-locked host memory for callers without a CUDA binding of their own (the Python mirror's reusable result buffers): device ->
+// host copies into it run at PCIe speed and touch no fresh pages.
+extern "C" void *ss_host_alloc_pinned(uint64_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void ss_host_free_pinned(void *p) { if (p) cudaFreeHost(p); }
 extern "C" const float *ss_surface_device_vertices(const ss_surface *s) { return s ? s->verts.as<float>() : nullptr; }
 extern "C" const uint32_t *ss_surface_device_triangles(const ss_surface *s) { return s ? s->tris.as<uint32_t>() : nullptr; }
 extern "C" const float *ss_surface_device_densities(const ss_surface *s) { return s ? s->rho.as<float>() : nullptr; }

@@ -646,107 +646,3 @@ class Runner:
         seg = self._seg
         return seg[:nv * 12].view(torch.float32).view(-1, 3).numpy().copy(), seg[nv * 12:nv * 12 + nt * 12].view(torch.int32).view(-1, 3).numpy().copy()
 
-
-# ---------------------------------------------------------------------------- frame sequences on one GPU ----
-class FrameStream:
-    """Reconstructs a SEQUENCE of frames on one GPU with two frames in flight: while frame i is being computed, the particles of
-    frame i + 1 are uploaded and the mesh of frame i - 1 is downloaded (copy engines, separate CUDA streams), so that a sequence costs
-    max(compute, copies) per frame instead of their sum.  The reference reconstructs frame sequences too (splashsurf/src/
-    reconstruct.rs: `--start-index` / `--end-index`, optionally several files at once); it has no copies to hide.  Latency of a
-    single frame is unchanged.
-
-        fs = FrameStream(ctx, params)
-        fs.submit(frame0)                       # pinned (n, 3) float32 host tensor: upload starts
-        for nxt in frames[1:] + [None]:
-            if nxt is not None:
-                fs.submit(nxt)                  # upload of the next frame overlaps ...
-            done = fs.advance()                 # ... the compute of the current one; returns the PREVIOUS frame's mesh (or None)
-        last = fs.drain()
-
-    Results are views of two alternating pinned host buffers: consume (or copy) them before the second-next `advance`."""
-
-    def __init__(self, ctx, params, device=None):
-        self.ctx, self.params = ctx, params
-        # `device` is only overridden by the tests that drive this class with the CPU executor of the CUDA sources (host memory,
-        # synchronous copies)
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self._cuda = self.device.type == "cuda"
-        self.up = torch.cuda.Stream(self.device) if self._cuda else None
-        self.down = torch.cuda.Stream(self.device) if self._cuda else None
-        self._in = [None, None]; self._in_ev = [None, None]; self._n = [0, 0]
-        self._submitted = 0; self._computed = 0
-        self._out_v = [None, None]; self._out_t = [None, None]
-        self._pending = None                      # (surface handle, nv, nt, slot, event) of the frame whose download is in flight
-        self.last_timings = None
-
-    def submit(self, host_x: torch.Tensor):
-        """Starts the upload of the next frame (a pinned (n, 3) float32 host tensor; it must stay untouched until `advance`)."""
-        if self._submitted - self._computed >= 2:
-            raise RuntimeError("two frames are already waiting: call advance() first")
-        slot = self._submitted % 2
-        n = int(host_x.shape[0])
-        if self._in[slot] is None or self._in[slot].shape[0] < n:
-            self._in[slot] = torch.empty((max(n, 1), 3), dtype=torch.float32, device=self.device)
-        ev = None
-        if self._cuda:
-            with torch.cuda.stream(self.up):
-                self._in[slot][:n].copy_(host_x, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(self.up)
-        else:
-            self._in[slot][:n].copy_(host_x)
-        self._in_ev[slot], self._n[slot] = ev, n
-        self._submitted += 1
-
-    def _start_download(self, s, slot):
-        L = self.ctx._L
-        nv, nt = L.ss_surface_num_vertices(s), L.ss_surface_num_triangles(s)
-        if self._out_v[slot] is None or self._out_v[slot].numel() < nv * 3:
-            self._out_v[slot] = _pinned(torch.empty(max(int(nv * 3 * 1.1), 1), dtype=torch.float32), self.device)
-        if self._out_t[slot] is None or self._out_t[slot].numel() < nt * 3:
-            self._out_t[slot] = _pinned(torch.empty(max(int(nt * 3 * 1.1), 1), dtype=torch.int32), self.device)
-        v = _view(L.ss_surface_device_vertices(s), (nv * 3,), "<f4", self.device)
-        t = _view(L.ss_surface_device_triangles(s), (nt * 3,), "<u4", self.device)
-        ev = None
-        if self._cuda:
-            with torch.cuda.stream(self.down):
-                self._out_v[slot][:nv * 3].copy_(v, non_blocking=True)
-                self._out_t[slot][:nt * 3].copy_(t, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(self.down)
-        else:
-            self._out_v[slot][:nv * 3].copy_(v); self._out_t[slot][:nt * 3].copy_(t)
-        self._pending = (s, nv, nt, slot, ev)
-
-    def _finish_download(self):
-        if self._pending is None:
-            return None
-        s, nv, nt, slot, ev = self._pending
-        if ev is not None:
-            ev.synchronize()
-        self.ctx.free_surface(s)
-        self._pending = None
-        return {"vertices": self._out_v[slot][:nv * 3].view(-1, 3), "triangles": self._out_t[slot][:nt * 3].view(-1, 3), "nv": nv, "nt": nt}
-
-    def advance(self):
-        """Computes the oldest submitted frame; returns the mesh of the frame computed by the PREVIOUS call (None the first time)."""
-        if self._computed >= self._submitted:
-            raise RuntimeError("no frame submitted")
-        slot = self._computed % 2
-        if self._in_ev[slot] is not None:
-            self._in_ev[slot].synchronize()                              # the upload of this frame (started one call ago) has landed
-        # the previous frame's download was started at the end of the previous call and runs during this compute
-        s = self.ctx.reconstruct_raw(self._in[slot].data_ptr(), self._n[slot], self.params)   # host-synchronous; copies proceed meanwhile
-        self.last_timings = self.ctx.timings(s)
-        prev = self._finish_download()
-        self._computed += 1
-        self._start_download(s, slot)
-        return prev
-
-    def drain(self):
-        """Waits for the last download; returns that frame's mesh."""
-        return self._finish_download()
-
-    def close(self):
-        if self._pending is not None:
-            self._finish_download()

@@ -403,6 +403,8 @@ cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) {
     *ms = std::chrono::duration<float, std::milli>(((EmulEvent *)b)->t - ((EmulEvent *)a)->t).count();
     return cudaSuccess;
 }
+cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
 cudaError_t cudaMemGetInfo(size_t *f, size_t *t) { *f = (size_t)6 << 30; *t = (size_t)8 << 30; return cudaSuccess; }
 cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *p) {
     memset(a, 0, sizeof(*a)); a->type = cudaMemoryTypeUnregistered; a->hostPointer = (void *)p; return cudaSuccess;

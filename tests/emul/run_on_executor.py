@@ -58,8 +58,6 @@ from test_emulated_pipeline import build_emulated_library  # noqa: E402
 ss._LIB = ss._bind(ctypes.CDLL(build_emulated_library()))
 _Runner = ssd.Runner
 ssd.Runner = lambda *a, **k: _Runner(*a, **dict(k, device="cpu"))
-_FrameStream = ssd.FrameStream
-ssd.FrameStream = lambda *a, **k: _FrameStream(*a, **dict(k, device="cpu"))
 
 if __name__ == "__main__":
     import runpy

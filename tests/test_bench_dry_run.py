@@ -41,8 +41,8 @@ def test_bench_single_rank_on_executor(oracle_mod, extra):
         assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
     want = int(extra[extra.index("--levelset-variant") + 1]) if "--levelset-variant" in extra else 2
     assert d["config"]["levelset_variant"] == want and d["roofline"]["launches_per_step"] >= (2 if want else 1)
-    # the two extra end-to-end readings of a single-GPU run: frame sequence with two frames in flight, documented front-end call
-    assert d["e2e_stream"]["frames_in_flight"] == 2 and d["e2e_stream"]["value"] > 0 and d["e2e_frontend"]["value"] > 0
+    # the extra end-to-end reading of a single-GPU run: the documented front-end call on a pageable numpy array
+    assert d["e2e_frontend"]["value"] > 0
 
 
 @pytest.mark.parametrize("protocol", ["stats", "two_call", "callback"])

@@ -1,5 +1,5 @@
 """GPU parity for subdomain sizes whose point count is not 8k+1 (partial last brick, no extension bricks), against the pinned
-oracle, and the frame-sequence API."""
+oracle."""
 import numpy as np
 import pytest
 
@@ -23,33 +23,23 @@ def test_cuda_subdomain_size_not_multiple_of_8(ss, oracle_mod, S):
     assert m["keys_equal"] and m["triangles_equal"] and m["n_not_bitexact"] == 0, m
 
 
-@pytest.mark.gpu
-def test_cuda_frame_stream_matches_serial_calls(ss):
-    """distributed.FrameStream (two frames in flight: upload of frame i+1 and download of frame i-1 during the compute of frame i)
-    returns, frame by frame, exactly what serial reconstruct_surface calls return -- different clouds per frame, so a mixed-up
-    buffer would show."""
-    import torch
-    from splashsurf_b200 import distributed as ssd, synthetic as syn
+
+def test_cuda_reusable_host_buffers(ss, oracle_mod):
+    """Context.reuse_host_buffers: the result arrays are views of the context's page-locked buffers -- same values as the default
+    (freshly allocated) arrays, and overwritten by the next reconstruction on the context."""
+    from splashsurf_b200 import synthetic as syn
     kw = dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.5)
-    frames = [syn.jittered_cube(14 + 2 * k, 0.025, 900 + k) for k in range(5)]
+    a, b = syn.jittered_cube(14, 0.025, 31), syn.jittered_cube(12, 0.025, 32)
     ctx = ss.Context()
     try:
-        want = [ss.reconstruct_surface(p, context=ctx, **kw) for p in frames]
-        fs = ssd.FrameStream(ctx, ss.make_params(**kw))
-        pinned = [torch.from_numpy(p).pin_memory() for p in frames]
-        got = []
-        fs.submit(pinned[0])
-        for k in range(len(frames)):
-            if k + 1 < len(frames):
-                fs.submit(pinned[k + 1])
-            prev = fs.advance()
-            if prev is not None:
-                got.append((prev["vertices"].numpy().copy(), prev["triangles"].numpy().copy()))
-        last = fs.drain()
-        got.append((last["vertices"].numpy().copy(), last["triangles"].numpy().copy()))
-        fs.close()
+        want_a, want_b = ss.reconstruct_surface(a, context=ctx, **kw), ss.reconstruct_surface(b, context=ctx, **kw)
+        ctx.reuse_host_buffers = True
+        ra = ss.reconstruct_surface(a, context=ctx, **kw)
+        assert np.array_equal(ra.mesh.vertices, want_a.mesh.vertices) and np.array_equal(ra.mesh.triangles, want_a.mesh.triangles)
+        assert np.array_equal(ra.particle_densities, want_a.particle_densities)
+        keep = ra.mesh.vertices.copy()
+        rb = ss.reconstruct_surface(b, context=ctx, **kw)
+        assert np.array_equal(rb.mesh.vertices, want_b.mesh.vertices) and np.array_equal(rb.mesh.triangles, want_b.mesh.triangles)
+        assert np.array_equal(keep, want_a.mesh.vertices)
     finally:
         ctx.close()
-    assert len(got) == len(frames)
-    for (v, t), w in zip(got, want):
-        assert np.array_equal(v, w.mesh.vertices) and np.array_equal(t.astype(np.uint64), w.mesh.triangles)
