@@ -173,6 +173,11 @@ int ss_levelset_tile_f32(ss_context *ctx, const float *xyz, const float *rho, ui
                          float cube_size, const int64_t subdomain_ijk[3], uint32_t subdomain_cubes,
                          float compact_support_radius, float particle_rest_mass, int mode, float *tile_out);
 
+/* Result copies into pageable host memory larger than four chunks are staged through page-locked buffers and scattered by several
+ * host threads (parallel first touch of fresh arrays; ss_surface_copy_triangles_u64 widens on the host).  Chunk size, default and
+ * maximum 32 MiB; smaller values only make sense for tests. */
+int ss_context_set_copy_chunk_bytes(ss_context *ctx, uint64_t bytes);
+
 /* Page-locked host memory (cudaHostAlloc) for callers that have no CUDA binding of their own: result copies into it run at PCIe
  * speed.  NULL on failure. */
 void *ss_host_alloc_pinned(uint64_t bytes);

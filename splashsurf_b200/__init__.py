@@ -115,6 +115,7 @@ def _bind(L):
     L.ss_context_set_levelset_variant.argtypes = [vp, C.c_int]
     L.ss_context_set_density_variant.argtypes = [vp, C.c_int]
     L.ss_context_set_mc_variant.argtypes = [vp, C.c_int]
+    L.ss_context_set_copy_chunk_bytes.argtypes = [vp, u64]
     L.ss_context_set_count_pairs.argtypes = [vp, C.c_int]
     L.ss_context_set_compute_sph_normals.argtypes = [vp, C.c_int]
     L.ss_surface_copy_normals.argtypes = [vp, vp]

@@ -96,6 +96,9 @@ struct ss_context {
     int count_pairs = 0;             // 1: count in-support evaluations (work model; slower)
     int density_variant = 0;         // 0 (default, fastest measured): thread-per-particle k_density; 1 / 2: cell-cooperative kernel (ss_density.cuh), candidates staged by bulk copies / 16-byte loads
     int mc_variant = 1;              // 1 (default): warp-per-brick marching cubes (count + emit) and fix-up sweep (ss_mc.cuh); 0: CTA-per-brick passes
+    void *h_stage[2] = { nullptr, nullptr };   // page-locked staging buffers of the result copies (copy_out), allocated on first use
+    size_t stage_bytes = (size_t)32 << 20;     // chunk size of the staged result copies (copies below 4 chunks are plain)
+    cudaEvent_t ev_stage[2] = { nullptr, nullptr };
     int sm_count = 148;              // streaming multiprocessors of the device (persistent-kernel grid sizing)
     int sph_normals = 0;             // 1: SPH normals at the mesh vertices (sph_interpolation.rs:82-133)
     // reusable scratch
@@ -241,6 +244,7 @@ extern "C" int ss_context_create(int device, ss_context **out) {
         c->sm_count = 3;
 #endif
         for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
+        for (auto &ev : c->ev_stage) CK(cudaEventCreate(&ev));
         {
             signed char table[256][16];
             ss_mc_unpack(table);
@@ -268,6 +272,8 @@ extern "C" void ss_context_destroy(ss_context *c) {
     for (DevBuf *b : bufs) b->release();
     c->post.release_all();
     for (auto &ev : c->ev) cudaEventDestroy(ev);
+    for (auto &ev : c->ev_stage) if (ev) cudaEventDestroy(ev);
+    for (auto &h : c->h_stage) if (h) cudaFreeHost(h);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -278,6 +284,10 @@ extern "C" int ss_context_set_levelset_exact_everywhere(ss_context *c, int on) {
 extern "C" int ss_context_set_density_variant(ss_context *c, int v) {
     if (!c || v < 0 || v > 2) return ss_fail(SS_ERR_INVALID_PARAMETER, "density variant must be 0, 1 or 2");
     c->density_variant = v; return SS_OK;
+}
+extern "C" int ss_context_set_copy_chunk_bytes(ss_context *c, uint64_t bytes) {
+    if (!c || bytes < 4096 || bytes > ((uint64_t)32 << 20) || (bytes & 3)) return ss_fail(SS_ERR_INVALID_PARAMETER, "copy chunk must be 4 KiB .. 32 MiB, a multiple of 4");
+    c->stage_bytes = (size_t)bytes; return SS_OK;
 }
 extern "C" int ss_context_set_mc_variant(ss_context *c, int v) {
     if (!c || v < 0 || v > 1) return ss_fail(SS_ERR_INVALID_PARAMETER, "marching-cubes variant must be 0 or 1");
@@ -306,22 +316,68 @@ struct Prepared {
     float upload_ms = 0.f;
 };
 
+// Result copies device -> host.  A plain cudaMemcpy into PAGEABLE memory is staged by the driver and, into freshly allocated arrays
+// (what a numpy front end hands in), page-faults single-threaded: ~3 GB/s measured for the 2.5 GB of a 50 M-particle result.  Large
+// copies therefore go through two page-locked staging buffers at PCIe speed, and a few host threads scatter each chunk into the
+// destination (parallel first touch) while the next chunk is in flight; `widen` turns u32 triangle indices into the reference's
+// usize on the way (half the PCIe bytes of converting on the device).  Destinations that are page-locked already take one cudaMemcpy.
+#include <thread>
+#define SS_STAGE_BYTES_MAX ((size_t)32 << 20)
+#define SS_STAGE_THREADS 8
+static void scatter_chunk(char *dst, const char *stage, size_t n_src_bytes, bool widen) {
+    const size_t nthreads = n_src_bytes >= ((size_t)1 << 20) ? SS_STAGE_THREADS : 1;
+    auto work = [&](size_t t) {
+        const size_t per = ((n_src_bytes / 4 + nthreads - 1) / nthreads) * 4;           // multiples of one 4-byte element
+        const size_t lo = std::min(n_src_bytes, t * per), hi = std::min(n_src_bytes, lo + per);
+        if (!widen) { memcpy(dst + lo, stage + lo, hi - lo); return; }
+        const uint32_t *in = reinterpret_cast<const uint32_t *>(stage + lo);
+        uint64_t *out = reinterpret_cast<uint64_t *>(dst) + lo / 4;
+        for (size_t e = 0; e < (hi - lo) / 4; ++e) out[e] = in[e];
+    };
+    if (nthreads == 1) { work(0); return; }
+    std::thread th[SS_STAGE_THREADS];
+    for (size_t t = 1; t < nthreads; ++t) th[t] = std::thread(work, t);
+    work(0);
+    for (size_t t = 1; t < nthreads; ++t) th[t].join();
+}
+// The same staging for the upload of a large PAGEABLE particle array (a numpy array handed to the front end): host threads gather a
+// chunk into a page-locked buffer while the previous chunk travels; page-locked inputs take one asynchronous copy.
+static void upload_particles(ss_context *c, void *dst_dev, const void *src, size_t bytes, bool pinned_src) {
+    const size_t chunk = c->stage_bytes;
+    if (pinned_src || bytes < 4 * chunk) { CK(cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyHostToDevice, c->stream)); return; }
+    for (int q = 0; q < 2; ++q) if (!c->h_stage[q]) {
+        if (cudaHostAlloc(&c->h_stage[q], SS_STAGE_BYTES_MAX, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); c->h_stage[q] = nullptr; }
+    }
+    if (!c->h_stage[0] || !c->h_stage[1]) { CK(cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyHostToDevice, c->stream)); return; }
+    const size_t nchunks = (bytes + chunk - 1) / chunk;
+    for (size_t k = 0; k < nchunks; ++k) {
+        const size_t off = k * chunk, n = std::min(chunk, bytes - off);
+        if (k >= 2) CK(cudaEventSynchronize(c->ev_stage[k & 1]));     // the copy that last read this staging buffer is done
+        scatter_chunk(static_cast<char *>(c->h_stage[k & 1]), static_cast<const char *>(src) + off, n, false);
+        CK(cudaMemcpyAsync(static_cast<char *>(dst_dev) + off, c->h_stage[k & 1], n, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaEventRecord(c->ev_stage[k & 1], c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));                             // the staging buffers are free again when this returns
+}
+
 static int prepare_particles(ss_context *c, const float *xyz, uint64_t n_in, const ss_params_f32 *p, Prepared &P,
                              std::vector<uint8_t> *inside_out, const ss_grid_f32 *given_grid = nullptr) {
     if (n_in > 0xfffffff0ull) return ss_fail(SS_ERR_INDEX_TOO_SMALL, "more than 2^32 particles are not supported by one device");
     const float *d_in = nullptr;
     cudaPointerAttributes attr{};
     bool on_device = false;
+    bool pinned_host = false;
     if (xyz && n_in) {
         cudaError_t e = cudaPointerGetAttributes(&attr, xyz);
         if (e == cudaSuccess && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged)) on_device = true;
+        else if (e == cudaSuccess && attr.type == cudaMemoryTypeHost) pinned_host = true;
         else cudaGetLastError();
     }
     CK(cudaEventRecord(c->ev[0], c->stream));
     if (on_device) d_in = xyz;
     else if (n_in) {
         c->xyz.ensure(n_in * 12);
-        CK(cudaMemcpyAsync(c->xyz.p, xyz, n_in * 12, cudaMemcpyHostToDevice, c->stream));
+        upload_particles(c, c->xyz.p, xyz, n_in * 12, pinned_host);
         d_in = c->xyz.as<float>();
     }
     CK(cudaEventRecord(c->ev[1], c->stream));
@@ -1597,27 +1653,68 @@ extern "C" int ss_surface_subdomain_grid(const ss_surface *s, ss_grid_f32 *o) {
     if (!s->used_decomposition) return ss_fail(SS_ERR_INVALID_PARAMETER, "no subdomain grid: decomposition was not used");
     grid_to_abi(s->subgrid, o); return SS_OK;
 }
-static int copy_out(const ss_surface *s, void *dst, const void *src, size_t bytes) {
+static int copy_out(const ss_surface *s, void *dst, const void *src, size_t bytes, bool widen = false) {
     if (!s || (!dst && bytes)) return ss_fail(SS_ERR_INVALID_PARAMETER, "NULL argument");
     if (!bytes) return SS_OK;
     cudaSetDevice(s->device);
-    cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) return ss_fail(SS_ERR_CUDA, cudaGetErrorString(e));
-    return SS_OK;
+    ss_context *c = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_ctx_mutex);
+        if (s->owner && g_live_contexts.count(s->owner)) c = s->owner;
+    }
+    bool pinned_dst = false;
+    {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, dst) == cudaSuccess) pinned_dst = at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+        else cudaGetLastError();
+    }
+    const size_t SS_STAGE_BYTES = c ? c->stage_bytes : SS_STAGE_BYTES_MAX;                // chunk size (tests shrink it)
+    if (!c || (pinned_dst && !widen) || bytes < 4 * SS_STAGE_BYTES) {
+        if (!widen) {
+            cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) return ss_fail(SS_ERR_CUDA, cudaGetErrorString(e));
+            return SS_OK;
+        }
+        std::vector<uint32_t> tmp(bytes / 4);
+        cudaError_t e = cudaMemcpy(tmp.data(), src, bytes, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return ss_fail(SS_ERR_CUDA, cudaGetErrorString(e));
+        scatter_chunk(static_cast<char *>(dst), reinterpret_cast<const char *>(tmp.data()), bytes, true);
+        return SS_OK;
+    }
+    try {
+        for (int q = 0; q < 2; ++q) if (!c->h_stage[q]) {
+            if (cudaHostAlloc(&c->h_stage[q], SS_STAGE_BYTES_MAX, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); c->h_stage[q] = nullptr; }
+        }
+        if (!c->h_stage[0] || !c->h_stage[1]) {                      // cannot page-lock: the plain copy still works
+            if (widen) { std::vector<uint32_t> tmp(bytes / 4); CK(cudaMemcpy(tmp.data(), src, bytes, cudaMemcpyDeviceToHost)); scatter_chunk(static_cast<char *>(dst), reinterpret_cast<const char *>(tmp.data()), bytes, true); }
+            else CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+            return SS_OK;
+        }
+        cudaStream_t st = c->stream;
+        const size_t nchunks = (bytes + SS_STAGE_BYTES - 1) / SS_STAGE_BYTES;
+        auto issue = [&](size_t k) {
+            const size_t off = k * SS_STAGE_BYTES, n = std::min(SS_STAGE_BYTES, bytes - off);
+            CK(cudaMemcpyAsync(c->h_stage[k & 1], static_cast<const char *>(src) + off, n, cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(c->ev_stage[k & 1], st));
+        };
+        issue(0);
+        for (size_t k = 0; k < nchunks; ++k) {
+            if (k + 1 < nchunks) issue(k + 1);                       // its staging buffer was scattered in the previous iteration
+            CK(cudaEventSynchronize(c->ev_stage[k & 1]));
+            const size_t off = k * SS_STAGE_BYTES, n = std::min(SS_STAGE_BYTES, bytes - off);
+            scatter_chunk(static_cast<char *>(dst) + (widen ? 2 * off : off), static_cast<const char *>(c->h_stage[k & 1]), n, widen);
+        }
+        return SS_OK;
+    } catch (const SsCudaError &err) {
+        cudaGetLastError();
+        return ss_fail(SS_ERR_CUDA, std::string(err.what) + ": " + cudaGetErrorString(err.e));
+    }
 }
 extern "C" int ss_surface_copy_vertices(const ss_surface *s, float *dst) { return copy_out(s, dst, s ? s->verts.p : nullptr, s ? s->nv * 12 : 0); }
 extern "C" int ss_surface_copy_triangles_u32(const ss_surface *s, uint32_t *dst) { return copy_out(s, dst, s ? s->tris.p : nullptr, s ? s->nt * 12 : 0); }
-extern "C" int ss_surface_copy_triangles_u64(const ss_surface *s, uint64_t *dst) {
+extern "C" int ss_surface_copy_triangles_u64(const ss_surface *s, uint64_t *dst) {      /* usize like the reference: widened on the host */
     if (!s || (!dst && s->nt)) return ss_fail(SS_ERR_INVALID_PARAMETER, "NULL argument");
-    if (!s->nt) return SS_OK;
-    cudaSetDevice(s->device);
-    void *tmp = nullptr;
-    if (cudaMalloc(&tmp, s->nt * 24) != cudaSuccess) return ss_fail(SS_ERR_OUT_OF_MEMORY, "cudaMalloc failed");
-    SS_LAUNCH(k_tris_to_u64, nblk(s->nt * 3, 256), 256, (cudaStream_t)0, s->nt * 3, s->tris.as<uint32_t>(), (unsigned long long *)tmp);
-    cudaError_t e = cudaMemcpy(dst, tmp, s->nt * 24, cudaMemcpyDeviceToHost);
-    cudaFree(tmp);
-    if (e != cudaSuccess) return ss_fail(SS_ERR_CUDA, cudaGetErrorString(e));
-    return SS_OK;
+    return copy_out(s, dst, s->tris.p, s->nt * 12, true);
 }
 extern "C" int ss_surface_copy_particle_densities(const ss_surface *s, float *dst) { return copy_out(s, dst, s ? s->rho.p : nullptr, s ? s->n * 4 : 0); }
 extern "C" int ss_surface_copy_particle_inside_aabb(const ss_surface *s, uint8_t *dst) {

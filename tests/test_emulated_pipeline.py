@@ -448,3 +448,38 @@ def test_emulated_runner_failure_on_one_rank_raises_everywhere(tmp_path, protoco
     assert all(x["outcome"].startswith("raised") for x in res), res
     assert "xyz is NULL" in res[1]["outcome"] and "another rank failed" in res[0]["outcome"], res
     assert res[0]["nv_after"] + res[1]["nv_after"] > 0
+
+
+def test_emulated_large_result_copies_take_the_staged_path(emu, oracle_mod):
+    """Result copies larger than four chunks (32 MiB each by default) go device -> page-locked staging -> destination with several
+    host threads, and the u32 -> u64 widening of the triangle indices happens on the host; smaller ones are one plain copy.  Both
+    must deliver the same bytes: the same surface copied with the default chunk (plain path) and with 64 KiB chunks (staged path)."""
+    x = _cube(20, 0.025, 777)
+    kw = dict(BASE, cube_size=0.5)
+    ctx = emu.Context()
+    try:
+        p = emu.make_params(**kw)
+        xs = np.ascontiguousarray(x)
+        s = ctx.reconstruct_raw(xs.ctypes.data, len(xs), p)
+        L = ctx._L
+        nv, nt = L.ss_surface_num_vertices(s), L.ss_surface_num_triangles(s)
+        got = []
+        for chunk in (32 << 20, 64 << 10, 4096 + 4):
+            assert L.ss_context_set_copy_chunk_bytes(ctx._h, chunk) == 0
+            t32 = np.full((nt, 3), 0xdeadbeef, np.uint32); t64 = np.full((nt, 3), 7, np.uint64); v = np.full((nv, 3), np.nan, np.float32)
+            assert L.ss_surface_copy_triangles_u32(s, t32.ctypes.data) == 0 and L.ss_surface_copy_triangles_u64(s, t64.ctypes.data) == 0
+            assert L.ss_surface_copy_vertices(s, v.ctypes.data) == 0
+            got.append((v, t32, t64))
+        assert nt * 12 >= 4 * (64 << 10)                               # the small chunk sizes really took the staged path
+        for v, t32, t64 in got[1:]:
+            assert np.array_equal(v, got[0][0]) and np.array_equal(t32, got[0][1]) and np.array_equal(t64, got[0][2])
+        assert np.array_equal(got[0][1].astype(np.uint64), got[0][2]) and int(got[0][2].max()) == nv - 1
+        assert L.ss_context_set_copy_chunk_bytes(ctx._h, 100) != 0     # out of range
+        ctx.free_surface(s)
+        # the upload of a pageable particle array is staged the same way: 20^3 particles = 96 KB > 4 chunks of 4100 bytes
+        assert L.ss_context_set_copy_chunk_bytes(ctx._h, 4096 + 4) == 0
+        g = emu.reconstruct_surface(x, context=ctx, **kw)
+        o = oracle_mod.reconstruct(x, **kw)
+        assert np.array_equal(g.particle_densities, o["particle_densities"]) and g.mesh.nvertices == len(o["vertices"])
+    finally:
+        ctx.close()
