@@ -95,6 +95,8 @@ typedef struct ss_timings {
     uint64_t bricks_mc;          /* bricks swept by marching cubes (can hold surface) */
     uint64_t bricks_fixscan;     /* bricks swept for certified points next to outside points */
     double levelset_cert_evals;  /* lower-bound evaluations (particle x grid point) of the certification pass (count_pairs, variant 2) */
+    double tile_setup;           /* ms between the end of binning and the first level-set kernel, summed over the tile batches: buffer
+                                    (re)allocation, tile table upload, zero-fill of the tiles */
 } ss_timings;
 
 typedef struct ss_context ss_context;   /* device + stream + reusable device buffers */

@@ -56,7 +56,7 @@ class _Timings(C.Structure):
                 ("total_device", C.c_float), ("kernel_launches", C.c_uint64), ("levelset_launches", C.c_uint64),
                 ("levelset_fixup_points", C.c_uint64), ("levelset_pairs", C.c_double),
                 ("bricks_total", C.c_uint64), ("bricks_levelset", C.c_uint64), ("bricks_mc", C.c_uint64), ("bricks_fixscan", C.c_uint64),
-                ("levelset_cert_evals", C.c_double)]
+                ("levelset_cert_evals", C.c_double), ("tile_setup", C.c_double)]
 
 
 _LIB = None

@@ -477,10 +477,13 @@ k_certify_warp(SsDev P, SsCwArgs A) {
                     done = __all_sync(0xffffffffu, (!vA || ta > cert) && (!vB || tb > cert));
                 }
             }
-            if (done) {
+            if (done || !any_sup) {
+                // certified: markers; no candidate within the support of the sub-box: the value is exactly 0 (stored, so that the
+                // tiles need no zero-fill beforehand)
                 float *out = lane_out + (4 * ha * np2 + 4 * hb * np1 + 4 * hc);
-                if (vA) out[0] = SS_MARKER;
-                if (vB) out[1] = SS_MARKER;
+                const float val = done ? SS_MARKER : 0.0f;
+                if (vA) out[0] = val;
+                if (vB) out[1] = val;
             }
             // per-box state of the two standard 2x4x4 boxes this sub-box covers: 1 markers, 2 needs exact values, 3 exact zeros in place
             if (lane < 2) {
@@ -501,11 +504,46 @@ k_certify_warp(SsDev P, SsCwArgs A) {
             const bool ok = ss_certify_box(P, L, S.rec, C, lane, 0);
             if (ok && L.valid) A.tiles[L.out_idx] = SS_MARKER;
             const uint8_t st = ok ? 1 : (ss_box_has_candidate<GLOBAL>(P, L, sparse, S.rec, C, lane) ? 2 : 3);
+            if (st == 3 && L.valid) A.tiles[L.out_idx] = 0.0f;        // exact zero, stored (no zero-fill of the tiles beforehand)
             if (lane == 0) ss_mark_boxes(P, A.wstate, tile_idx, vbx, vby, vbz, We, st);
         }
     }
     if (COUNT && A.evals) {
         for (int o = 16; o > 0; o >>= 1) n_eval += __shfl_xor_sync(0xffffffffu, n_eval, o);
         if (lane == 0 && n_eval) atomicAdd(A.evals, n_eval);
+    }
+}
+
+
+// Level-set variant 2 leaves the tiles un-zeroed (16 GB of memset at 50 M particles): every value a later pass can read is written by
+// the certification / exact kernels -- except in bricks nobody evaluated (no candidate particle: state 0), whose exact value is 0.
+// Readers (fix-up sweep, marching cubes) touch the listed bricks and at most one brick around them, so only untouched bricks with a
+// listed brick in their 3x3x3 neighbourhood (themselves included) are filled.  One warp per brick of the batch.
+__global__ void __launch_bounds__(256)
+k_zero_untouched(SsDev P, const uint8_t *__restrict__ bstate, const uint32_t *__restrict__ flag_mc, const uint32_t *__restrict__ flag_fix,
+                 uint32_t nbricks_total, float *__restrict__ tiles) {
+    const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (b >= nbricks_total || bstate[b] != 0) return;
+    const int nb = P.nb;
+    uint32_t q = b;
+    const int bz = (int)(q % (uint32_t)nb); q /= (uint32_t)nb;
+    const int by = (int)(q % (uint32_t)nb); q /= (uint32_t)nb;
+    const int bx = (int)(q % (uint32_t)nb);
+    const uint32_t tile = q / (uint32_t)nb;
+    bool listed = false;
+    if (lane < 27) {
+        const int x = bx + lane / 9 - 1, y = by + (lane / 3) % 3 - 1, z = bz + lane % 3 - 1;
+        if (x >= 0 && y >= 0 && z >= 0 && x < nb && y < nb && z < nb) {
+            const uint32_t o = ((tile * (uint32_t)nb + (uint32_t)x) * (uint32_t)nb + (uint32_t)y) * (uint32_t)nb + (uint32_t)z;
+            listed = (flag_mc[o] | flag_fix[o]) != 0u;
+        }
+    }
+    if (!__any_sync(0xffffffffu, listed)) return;
+    const int np = P.np;
+    float *t = tiles + (size_t)tile * np * np * np;
+    for (int p = lane; p < 512; p += 32) {
+        const int i = bx * 8 + (p >> 6), j = by * 8 + ((p >> 3) & 7), k = bz * 8 + (p & 7);
+        if (i < np && j < np && k < np) t[((size_t)i * np + j) * np + k] = 0.0f;
     }
 }

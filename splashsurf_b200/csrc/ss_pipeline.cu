@@ -758,6 +758,9 @@ static int levelset_batch(ss_context *c, const SsDev &D, uint32_t nbatch, unsign
     cub_excl_scan(c, c->flag_fix.as<uint32_t>(), c->off_fix.as<uint32_t>(), nbr_b);
     LAUNCH(c, k_compact_list, nblk(nbr_b, 256), 256, c->flag_mc.as<uint32_t>(), c->off_mc.as<uint32_t>(), nbr_b, c->list_mc.as<uint32_t>());
     LAUNCH(c, k_compact_list, nblk(nbr_b, 256), 256, c->flag_fix.as<uint32_t>(), c->off_fix.as<uint32_t>(), nbr_b, c->list_fix.as<uint32_t>());
+    if (c->ls_variant == 2 && split_certify && !global_mode)       // the tiles were not zero-filled: untouched bricks a later pass can read
+        LAUNCH(c, k_zero_untouched, nblk((uint64_t)nbr_b * 32, 256), 256, D, c->bstate.as<uint8_t>(), c->flag_mc.as<uint32_t>(), c->flag_fix.as<uint32_t>(),
+               nbr_b, c->tiles.as<float>());
     uint32_t lc[4] = { 0, 0, 0, 0 };
     CK(cudaMemcpyAsync(&lc[0], c->off_mc.as<uint32_t>() + (nbr_b - 1), 4, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&lc[1], c->flag_mc.as<uint32_t>() + (nbr_b - 1), 4, cudaMemcpyDeviceToHost, st));
@@ -1093,7 +1096,7 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     c->bkeys_a.ensure(bcap * 8); c->bids_a.ensure(bcap * 4);
     size_t vcap = std::max<size_t>(1 << 16, c->hint_nv + c->hint_nv / 8), tcap = std::max<size_t>(1 << 17, c->hint_nt + c->hint_nt / 8);
     out->verts.ensure(vcap * 12); out->vkeys.ensure(vcap * 8); out->tris.ensure(tcap * 12);
-    float ls_ms = 0.f, mc_ms = 0.f;
+    float ls_ms = 0.f, mc_ms = 0.f, setup_ms = 0.f;
     uint64_t ls_launches = 0, fix_points = 0;
     out->tile.clear();
     const bool exact_all = c->ls_exact_all || c->keep_tile_flat >= 0;
@@ -1109,12 +1112,21 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
             T.s = sid; T.sparse = (out->sub_sparse[sid] || !D.simd) ? 1u : 0u;
         }
         CK(cudaMemcpyAsync(c->tile_tab.p, h_tiles.data(), (size_t)nbatch * sizeof(SsTile), cudaMemcpyHostToDevice, st));
-        CK(cudaMemsetAsync(c->tiles.p, 0, (size_t)nbatch * np3 * 4, st));
+        // level-set variant 2 writes every value a later pass reads (markers, exact values, exact zeros) and fills the untouched
+        // bricks next to listed ones itself (k_zero_untouched): no zero-fill of the tiles (16 GB at 50 M particles)
+        const bool lazy_zero = c->ls_variant == 2 && !exact_all && certify_runs <= 32 && !global_mode;
+        if (!lazy_zero) CK(cudaMemsetAsync(c->tiles.p, 0, (size_t)nbatch * np3 * 4, st));
         CK(cudaMemsetAsync(c->bstate.p, 0, (size_t)nbatch * nbricks, st));
         // edge masks: the CTA-per-brick marching-cubes passes read the mask of every point of a listed brick (zero = no vertex); the
         // warp-per-brick passes only read masks their count pass wrote, so they need no zero-fill (4 GB at 50 M particles)
         if (global_mode || c->mc_variant != 1) CK(cudaMemsetAsync(c->vmask.p, 0, (size_t)nbatch * np3, st));
         CK(cudaEventRecord(c->ev[10], st));
+        {   // set-up time of this batch: from the end of binning (first batch) / of the previous batch's marching cubes to here
+            CK(cudaEventSynchronize(c->ev[10]));
+            float su = 0.f;
+            CK(cudaEventElapsedTime(&su, s0 == 0 ? c->ev[5] : c->ev[6], c->ev[10]));
+            setup_ms += su;
+        }
         uint32_t n_mc = 0;
         rc = levelset_batch(c, D, nbatch, nbricks, exact_all, certify_runs, global_mode, out, ls_launches, fix_points, &n_mc);
         if (rc) return rc;
@@ -1179,7 +1191,7 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     CK(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); T.decomposition = ms;
     CK(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4])); T.density = ms;
     CK(cudaEventElapsedTime(&ms, c->ev[4], c->ev[5])); T.binning = ms;
-    T.levelset = ls_ms; T.marching_cubes = mc_ms;
+    T.levelset = ls_ms; T.marching_cubes = mc_ms; T.tile_setup = setup_ms;
     CK(cudaEventElapsedTime(&ms, c->ev[7], c->ev[8])); T.stitching = ms;
     T.levelset_launches = ls_launches; T.levelset_fixup_points = fix_points;
     unsigned long long h_pairs[2] = { 0, 0 };
