@@ -1058,8 +1058,6 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
 
     // ---- level set + marching cubes over batches of subdomain tiles
     const size_t np3 = (size_t)D.np * D.np * D.np;
-    size_t free_b = 0, total_b = 0;
-    CK(cudaMemGetInfo(&free_b, &total_b));
     const unsigned nbricks = (unsigned)(D.nb * D.nb * D.nb);
     const size_t per_tile = np3 * (4 + 4 + 1) + (size_t)nbricks * (SS_LS_WARPS + 8 + 1 + 16) + 256;
     // as many tiles per batch as fit a third of the free memory (fewer host synchronisations per frame); the brick index
@@ -1067,11 +1065,20 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     const uint32_t nown = (uint32_t)owned_list.size();
     // The tile buffers of the previous frame are reused whenever they hold all tiles or at least half of what a fresh
     // allocation would get: the amount of free memory wobbles from frame to frame (result buffers in flight), and re-allocating
-    // tens of GB costs ~100 ms.
-    const size_t have_tiles = c->tiles.cap / (np3 * 4);
-    const size_t reusable = c->tiles.cap + c->voff.cap + c->vmask.cap;
-    size_t want_tiles = std::max<size_t>(1, ((free_b + reusable) / 3) / per_tile);
-    size_t max_tiles = c->max_tiles ? c->max_tiles : ((have_tiles >= nown || have_tiles >= want_tiles / 2) && have_tiles ? have_tiles : want_tiles);
+    // tens of GB costs ~100 ms.  The free memory is only queried when the buffers do not hold all tiles: cudaMemGetInfo takes a
+    // device-wide lock, and with an `nvidia-smi -lms 200` sampler running beside the process (bench.py's clock record) it was
+    // measured to stall here for up to 100 ms on every step the sampler's query fell into (tile_setup in the timings).
+    const size_t have_tiles = std::min(c->tiles.cap / (np3 * 4), std::min(c->voff.cap / (np3 * 4), c->vmask.cap / np3));
+    size_t max_tiles;
+    if (c->max_tiles) max_tiles = c->max_tiles;
+    else if (have_tiles >= nown && have_tiles) max_tiles = have_tiles;
+    else {
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        const size_t reusable = c->tiles.cap + c->voff.cap + c->vmask.cap;
+        const size_t want_tiles = std::max<size_t>(1, ((free_b + reusable) / 3) / per_tile);
+        max_tiles = (have_tiles >= want_tiles / 2 && have_tiles) ? have_tiles : want_tiles;
+    }
     max_tiles = std::min<size_t>(max_tiles, std::max<size_t>(1, (size_t)0x7fffffff / nbricks / 2));
     max_tiles = std::min<size_t>(max_tiles, std::max<uint32_t>(nown, 1));
     const size_t nblk_max = max_tiles * nbricks;
