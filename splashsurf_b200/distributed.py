@@ -231,6 +231,10 @@ class Runner:
         self.ctx_normals = False         # set by the caller when ss_context_set_compute_sph_normals is on: normals join the assembled mesh
         self.balance_feedback = True     # slab cuts learn from the measured per-rank time of earlier frames
         self._layer_scale = None; self._layer_key = None
+        # ... for a few frames; then the best cuts seen are kept (a plan that keeps moving keeps re-allocating: one 150 ms step in
+        # twenty was measured at 8 GPUs) until the slowest rank drifts 15 % above the time they were chosen for
+        self.explore_frames = 4
+        self._explore_left = self.explore_frames; self._best_t = float("inf"); self._best_cuts = None; self._frozen_cuts = None; self._drift = 0
         # `device` is only overridden by the tests that drive the runner over gloo with the CPU executor of the CUDA sources
         self.device = torch.device("cuda", local_rank) if device is None else torch.device(device)
         self.last_plan: Optional[SlabPlan] = None
@@ -341,7 +345,10 @@ class Runner:
             work = work * self._layer_scale
         else:
             self._layer_scale, self._layer_key = np.ones(nsd[ax]), (ax, nsd[ax])
+            self._explore_left, self._best_t, self._best_cuts, self._frozen_cuts = self.explore_frames, float("inf"), None, None
         plan = make_plan(ncells, S, float(p.cube_size), float(p.compact_support_radius), work, world, axis=ax)
+        if self.balance_feedback and self._frozen_cuts is not None:
+            plan.cuts = list(self._frozen_cuts)                     # settled: same slabs as the best frame so far
         plan.gmin_axis = float(grid.aabb_min[ax])
         self.last_plan = plan
         t_host.append(time.perf_counter())      # 2: statistics + plan
@@ -430,12 +437,25 @@ class Runner:
             t_r = status[1:]
             busy = [r for r in range(world) if plan.own(r)[1] > plan.own(r)[0]]
             mean = float(np.mean([t_r[r] for r in busy])) if busy else 0.0
-            # adapt only while the slowest rank is more than 4 % above the mean: a settled plan keeps its buffers (no re-allocation)
-            if mean > 0 and max(t_r[r] for r in busy) > 1.04 * mean:
-                for r in busy:
-                    a, bnd = plan.own(r)
-                    self._layer_scale[a:bnd] *= float(np.clip(t_r[r] / mean, 0.6, 1.6))
-                self._layer_scale = np.clip(self._layer_scale / self._layer_scale.mean(), 0.2, 5.0)
+            worst = max(float(t_r[r]) for r in busy) if busy else 0.0
+            if self._frozen_cuts is not None:
+                # the cloud has moved on (three frames in a row 15 % slower than when the cuts were chosen; one slow frame is noise):
+                # explore again
+                self._drift = self._drift + 1 if worst > 1.15 * self._best_t else 0
+                if self._drift >= 3:
+                    self._explore_left, self._best_t, self._best_cuts, self._frozen_cuts, self._drift = max(self.explore_frames - 1, 1), float("inf"), None, None, 0
+            elif mean > 0:
+                if worst < self._best_t:
+                    self._best_t, self._best_cuts = worst, list(plan.cuts)
+                # adapt only while the slowest rank is more than 4 % above the mean
+                if worst > 1.04 * mean:
+                    for r in busy:
+                        a, bnd = plan.own(r)
+                        self._layer_scale[a:bnd] *= float(np.clip(t_r[r] / mean, 0.6, 1.6))
+                    self._layer_scale = np.clip(self._layer_scale / self._layer_scale.mean(), 0.2, 5.0)
+                self._explore_left -= 1
+                if self._explore_left <= 0:
+                    self._frozen_cuts = list(self._best_cuts)
         try:
             t_ev[2].record()
             _sync(dev)

@@ -351,12 +351,14 @@ ctx = ss.Context(0)
 runner = ssd.Runner(ctx, ss.make_params(**case["kw"]), world, rank, 0, device="cpu", protocol=case.get("protocol", "stats"))
 runner.want_keys = True
 x = torch.from_numpy(runner.take_local(p_all))
-for it in range(2):                                             # second step reuses the pooled buffers
+cuts_seen = []
+for it in range(int(case.get("steps", 2))):                     # later steps reuse the pooled buffers; from step 5 on the plan is settled
     out = runner.step(x, copy_out=True)
+    cuts_seen.append(list(out["plan"].cuts))
 if rank == 0:
     v, t = runner.gathered_mesh(out["nv_global"], out["nt_global"])
     np.savez(os.path.join(os.environ["SS_OUT"], "mesh.npz"), v=v, t=t, k=out["keys_global"].numpy(), cuts=np.asarray(out["plan"].cuts))
-json.dump({"recv": out["recv_particles"], "nsub_owned": out["nsub_owned"]}, open(os.path.join(os.environ["SS_OUT"], f"rank{rank}.json"), "w"))
+json.dump({"recv": out["recv_particles"], "nsub_owned": out["nsub_owned"], "cuts_seen": cuts_seen}, open(os.path.join(os.environ["SS_OUT"], f"rank{rank}.json"), "w"))
 ctx.close()
 dist.destroy_process_group()
 '''
@@ -373,7 +375,9 @@ dist.destroy_process_group()
              kw=dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.75, subdomain_num_cubes_per_dim=16, subdomain_grid_auto_disable=False))),
     (2, dict(gen="splash", args=[[8, 8, 8], 3, 0.025, 504],                            # same cloud, default protocol: sparse subdomains decided from the statistics
              kw=dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.75, subdomain_num_cubes_per_dim=16, subdomain_grid_auto_disable=False))),
-], ids=["2_ranks_dam_break", "3_ranks_one_idle", "3_ranks_one_idle_callback", "2_ranks_splash_two_call", "2_ranks_splash_stats"])
+    (2, dict(gen="dam_break", args=[[10, 6, 6], [14, 2, 6], 0.025, 505], steps=8,     # feedback for four frames, then the best cuts are kept
+             kw=dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.75, subdomain_num_cubes_per_dim=16, subdomain_grid_auto_disable=False))),
+], ids=["2_ranks_dam_break", "3_ranks_one_idle", "3_ranks_one_idle_callback", "2_ranks_splash_two_call", "2_ranks_splash_stats", "2_ranks_8_frames_plan_settles"])
 def test_emulated_runner_over_gloo(tmp_path, oracle_mod, world, case):
     """splashsurf_b200.distributed.Runner._step_multi as the bench drives it (plan, halo exchange, two library calls, max
     all-reduce, mesh gather + weld), one process per rank over gloo, library = CPU executor; result vs the single-device oracle."""
@@ -399,6 +403,10 @@ def test_emulated_runner_over_gloo(tmp_path, oracle_mod, world, case):
     ranks = [json.load(open(tmp_path / f"rank{k}.json")) for k in range(world)]
     if world == 3:
         assert min(r_["nsub_owned"] for r_ in ranks) == 0, ranks          # the idle rank really was idle
+    assert all(r_["cuts_seen"] == ranks[0]["cuts_seen"] for r_ in ranks)  # every rank took the same plan decisions
+    if case.get("steps", 2) >= 7:
+        seen = ranks[0]["cuts_seen"]
+        assert all(c == seen[4] for c in seen[4:]) and seen[4] in seen[:4], seen   # settled on one of the explored plans
 
 
 FAIL_WORKER = r'''
