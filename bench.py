@@ -8,10 +8,12 @@ the library's stream around every step); `e2e` runs the same call through the C 
 copied host->device and the mesh copied device->host inside the timed region.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--particles M] [--impl reference]
-                  [--workload cfg2|cfg3|cfg4|cfg5] [--levelset-variant 0|1|2] [--runner-protocol two_call|callback]
+                  [--workload cfg2|cfg3|cfg4|cfg5|cfg5_overlap] [--levelset-variant 0|1|2] [--density-variant 0|1|2] [--mc-variant 0|1]
+                  [--runner-protocol stats|two_call|callback] [--sph-normals] [--no-cpu-baseline] [--no-extra-e2e]
 
-(The defaults are the measured configuration: level-set variant 0, two-call runner protocol.  tests/test_bench_dry_run.py
-runs this file's main() on the CPU executor of the CUDA sources to check its control flow and the JSON contract.)
+(The defaults are the measured configuration: level-set variant 2, density variant 0, marching-cubes variant 1, "stats" runner
+protocol.  tests/test_bench_dry_run.py runs this file's main() on the CPU executor of the CUDA sources to check its control flow
+and the JSON contract.)
 """
 import argparse
 import json
