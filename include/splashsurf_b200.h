@@ -313,6 +313,14 @@ int ss_mesh_cleanup_f32(float *verts, uint64_t *nv, uint32_t *tris, uint64_t *nt
 int ss_mesh_decimation_f32(float *verts, uint64_t *nv, uint32_t *tris, uint64_t *nt, int keep_vertices, uint64_t *conn_offsets,
                            uint32_t *conn_indices);
 
+/* convert_tris_to_quads (postprocessing.rs:689-910): pairs of triangles sharing an edge become quads when all four edges are within
+ * [1 / limit, limit] x diagonal / sqrt(2), no interior angle exceeds max_interior_angle_rad and the two triangle normals are within
+ * normal_angle_limit_rad.  Outputs: the remaining triangles (capacity nt x 3, in input order) and the quads (capacity nt / 2 x 4, in the
+ * reference's order -- its hash-set iteration order is restated).  Vertices are unchanged.  Host code. */
+int ss_mesh_tris_to_quads_f32(const float *verts, uint64_t nv, const uint32_t *tris, uint64_t nt, float non_squareness_limit,
+                              float normal_angle_limit_rad, float max_interior_angle_rad, uint32_t *tris_out, uint64_t *nt_out,
+                              uint32_t *quads_out, uint64_t *nq_out);
+
 /* Replaces the surface's normals by [num_vertices * 3] caller-supplied ones (then ss_surface_smooth_normals_f32 smooths any field). */
 int ss_surface_set_normals_f32(ss_surface *s, const float *normals);
 

@@ -148,6 +148,7 @@ def _bind(L):
     L.ss_surface_replace_mesh_f32.argtypes = [vp, vp, u64, vp, u64]
     L.ss_mesh_cleanup_f32.argtypes = [vp, C.POINTER(u64), vp, C.POINTER(u64), C.POINTER(_Grid), C.c_float, u64, C.c_int, vp, vp]
     L.ss_mesh_decimation_f32.argtypes = [vp, C.POINTER(u64), vp, C.POINTER(u64), C.c_int, vp, vp]
+    L.ss_mesh_tris_to_quads_f32.argtypes = [vp, u64, vp, u64, C.c_float, C.c_float, C.c_float, vp, C.POINTER(u64), vp, C.POINTER(u64)]
     if L.ss_abi_version() != 2:
         raise ImportError("libsplashsurf_b200.so ABI version mismatch")
     return L
@@ -269,6 +270,37 @@ def barnacle_decimation(mesh: "TriMesh3d", *, keep_vertices: bool = False) -> "V
     """``pysplashsurf.barnacle_decimation`` (postprocessing.rs:244-686): merges the single and double barnacle configurations of a
     marching-cubes mesh in place; returns the vertex-vertex connectivity of the result."""
     return _host_mesh_op(mesh, lambda L, v, nv, t, nt, off, idx: L.ss_mesh_decimation_f32(v, nv, t, nt, int(bool(keep_vertices)), off, idx))
+
+
+@dataclass
+class MixedTriQuadMesh3d:
+    """Mirrors pysplashsurf.MixedTriQuadMesh3d (mesh.rs): vertices plus triangle and quad cells."""
+    vertices: np.ndarray
+    _triangles: np.ndarray
+    _quads: np.ndarray
+
+    def get_triangles(self) -> np.ndarray:
+        return self._triangles
+
+    def get_quads(self) -> np.ndarray:
+        return self._quads
+
+
+def convert_tris_to_quads(mesh: "TriMesh3d", *, non_squareness_limit: float = 1.75, normal_angle_limit: float = 10.0,
+                          max_interior_angle: float = 135.0) -> MixedTriQuadMesh3d:
+    """``pysplashsurf.convert_tris_to_quads`` (postprocessing.rs:689-910; angles in degrees): merges pairs of triangles sharing an edge
+    into quads.  Returns a new mesh; the input is not modified.  Host code in the library, cells in the reference's order."""
+    L = load_library()
+    v = np.ascontiguousarray(mesh.vertices, dtype=np.float32)
+    t = np.ascontiguousarray(mesh.triangles, dtype=np.uint32)
+    to = np.empty((max(len(t), 1), 3), np.uint32)
+    qo = np.empty((max(len(t) // 2, 1), 4), np.uint32)
+    nt, nq = C.c_uint64(0), C.c_uint64(0)
+    rad = lambda deg: float(np.float32(float(deg) * (np.pi / 180.0)))      # f64::to_radians, then `as f32` (pysplashsurf/src/postprocessing.rs:45-58)
+    _check(L, L.ss_mesh_tris_to_quads_f32(v.ctypes.data if len(v) else None, len(v), t.ctypes.data if len(t) else None, len(t),
+                                          C.c_float(float(np.float32(non_squareness_limit))), C.c_float(rad(normal_angle_limit)),
+                                          C.c_float(rad(max_interior_angle)), to.ctypes.data, C.byref(nt), qo.ctypes.data, C.byref(nq)))
+    return MixedTriQuadMesh3d(v.copy(), to[:nt.value].astype(np.uint64), qo[:nq.value].astype(np.uint64))
 
 
 class _MeshSurface:
@@ -627,10 +659,12 @@ def reconstruction_pipeline(particles, *, attributes_to_interpolate=None, partic
 
     ``mesh_cleanup`` (+ ``mesh_cleanup_snap_dist``, 5 sweeps) and ``decimate_barnacles`` (+ ``keep_vertices``) run first, as in
     reconstruct.rs:1058-1092 -- sequential half-edge collapses on the host (library entries ss_mesh_cleanup_f32 /
-    ss_mesh_decimation_f32), after which the new mesh goes back to the device for the remaining steps.  The other switches of the
-    reference pipeline (quad conversion, mesh AABB clamping, mesh checks) raise NotImplementedError when enabled."""
-    passive = ("mesh_cleanup", "decimate_barnacles", "mesh_cleanup_snap_dist", "keep_vertices", "quad_max_edge_diag_ratio", "quad_max_normal_angle",
-               "quad_max_interior_angle", "mesh_aabb_clamp_vertices")
+    ss_mesh_decimation_f32), after which the new mesh goes back to the device for the remaining steps.  ``generate_quads`` (+
+    ``quad_max_edge_diag_ratio`` / ``quad_max_normal_angle`` / ``quad_max_interior_angle``) runs last (reconstruct.rs:1410-1441, host):
+    the returned mesh is then a MixedTriQuadMesh3d.  The remaining switches of the reference pipeline (mesh AABB clamping, mesh
+    checks) raise NotImplementedError when enabled."""
+    passive = ("mesh_cleanup", "decimate_barnacles", "mesh_cleanup_snap_dist", "keep_vertices", "generate_quads", "quad_max_edge_diag_ratio",
+               "quad_max_normal_angle", "quad_max_interior_angle", "mesh_aabb_clamp_vertices")
     enabled = [k for k, v in post.items() if v not in (False, None, 0) and k not in passive]
     if enabled:
         raise NotImplementedError(f"post-processing not provided by the device path: {enabled}")
@@ -708,6 +742,10 @@ def reconstruction_pipeline(particles, *, attributes_to_interpolate=None, partic
             point[name] = out
         rec.normals = point.get("normals")
         mesh = TriMesh3d(verts, out_mesh.triangles)
+        if post.get("generate_quads", False):                                  # reconstruct.rs:1410-1441
+            mesh = convert_tris_to_quads(mesh, non_squareness_limit=post.get("quad_max_edge_diag_ratio", 1.75),
+                                         normal_angle_limit=post.get("quad_max_normal_angle", 10.0),
+                                         max_interior_angle=post.get("quad_max_interior_angle", 135.0))
         return MeshWithData(mesh, point, {}), rec
     finally:
         ctx.free_surface(s)

@@ -53,6 +53,18 @@ def test_barnacle_decimation_matches_reference_fixture(ss):
     assert _same(m2, g["cleanup_snap03_decimated_v"], g["cleanup_snap03_decimated_t"])
 
 
+@pytest.mark.parametrize("tag,qkw", [("quads", {}), ("quads_strict", dict(non_squareness_limit=1.3, normal_angle_limit=4.0, max_interior_angle=110.0))])
+def test_convert_tris_to_quads_matches_reference_fixture(ss, tag, qkw):
+    """postprocessing.rs:689-910: remaining triangles and quads, in the reference's cell order (its hash-set iteration order)."""
+    g = load_golden("meshproc_ref")
+    q = ss.convert_tris_to_quads(ss.TriMesh3d(g["vertices"].copy(), g["triangles"].astype(np.uint64)), **qkw)
+    assert np.array_equal(q.get_triangles(), g[tag + "_t"].astype(np.uint64)) and np.array_equal(q.get_quads(), g[tag + "_q"].astype(np.uint64))
+    assert len(q.get_quads()) > 100 and len(q.get_triangles()) + 2 * len(q.get_quads()) == len(g["triangles"])
+    assert np.array_equal(q.vertices, g["vertices"])
+    empty = ss.convert_tris_to_quads(ss.TriMesh3d(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint64)))
+    assert len(empty.get_triangles()) == 0 and len(empty.get_quads()) == 0
+
+
 def test_meshproc_edge_cases(ss):
     g = load_golden("meshproc_ref")
     grid = _grid(ss, g)
@@ -93,6 +105,10 @@ def test_meshproc_matches_reference_live(ss, oracle_mod, case):
     mine = ss.TriMesh3d(v0.copy(), t0.copy())
     ss.marching_cubes_cleanup(mine, grid, max_rel_snap_dist=snap, max_iter=5, keep_vertices=keep)
     assert _same(mine, np.asarray(ref.vertices), np.asarray(ref.triangles))
+    for src in (rec.mesh, ref):                                   # quads from the raw and from the cleaned mesh
+        q = ps.convert_tris_to_quads(src)
+        m = ss.convert_tris_to_quads(ss.TriMesh3d(np.array(src.vertices, np.float32), np.array(src.triangles, np.uint64)))
+        assert np.array_equal(m.get_triangles(), np.asarray(q.get_triangles())) and np.array_equal(m.get_quads(), np.asarray(q.get_quads()))
     for start_v, start_t, start_ref in [(v0, t0, rec.mesh.copy()), (mine.vertices, mine.triangles, ref)]:
         ps.barnacle_decimation(start_ref, keep_vertices=keep)
         m = ss.TriMesh3d(start_v.copy(), start_t.copy())

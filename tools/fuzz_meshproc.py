@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Differential fuzzing of the host mesh clean-up / barnacle decimation (csrc/ss_meshproc.inc) against the REFERENCE
-WHEEL (oracle/_ref): random small clouds -> the wheel's own marching-cubes mesh -> marching_cubes_cleanup / barnacle_decimation in both
+WHEEL (oracle/_ref): random small clouds -> the wheel's own marching-cubes mesh -> marching_cubes_cleanup / barnacle_decimation / convert_tris_to_quads in both
 implementations on the same input; vertices and triangles must be identical bit for bit.  No GPU needed.
 
     python tools/fuzz_meshproc.py --cases 200 --seed 0
@@ -61,10 +61,17 @@ def main():
         ps.barnacle_decimation(ref3, keep_vertices=keep)
         ss.barnacle_decimation(mine, keep_vertices=keep)
         ok3 = same(mine, ref3)
+        qkw = dict(non_squareness_limit=float(rng.choice([1.3, 1.75, 2.5])), normal_angle_limit=float(rng.choice([4.0, 10.0, 30.0])),
+                   max_interior_angle=float(rng.choice([110.0, 135.0, 170.0])))
+        ok4 = True
+        for src in (rec.mesh, ref3):                          # quads from the raw mesh and from the cleaned + decimated one
+            q = ps.convert_tris_to_quads(src, **qkw)
+            mq = ss.convert_tris_to_quads(ss.TriMesh3d(np.array(src.vertices, np.float32), np.array(src.triangles, np.uint64)), **qkw)
+            ok4 = ok4 and np.array_equal(mq.get_triangles(), np.asarray(q.get_triangles())) and np.array_equal(mq.get_quads(), np.asarray(q.get_quads()))
         done += 1
-        if not (ok1 and ok2 and ok3):
+        if not (ok1 and ok2 and ok3 and ok4):
             bad += 1
-            print(f"[{seed}] MISMATCH cleanup={ok1} decimation={ok2} cleanup+decimation={ok3} nv={len(v0)} snap={snap} keep={keep} {kw}")
+            print(f"[{seed}] MISMATCH cleanup={ok1} decimation={ok2} cleanup+decimation={ok3} quads={ok4} nv={len(v0)} snap={snap} keep={keep} {kw} {qkw}")
         elif done % 20 == 0:
             print(f"[{seed}] ok nv={len(v0)} -> {mine.nvertices} ({time.time() - t0:.0f}s)", flush=True)
     print(f"{done} meshes, {bad} mismatches, {time.time() - t0:.0f}s")

@@ -35,6 +35,9 @@ conn = c.copy_connectivity()
 out["decimated_conn_offsets"] = np.concatenate([[0], np.cumsum([len(l) for l in conn])]).astype(np.uint64)
 out["decimated_conn_sorted"] = np.concatenate([sorted(l) for l in conn]).astype(np.uint32)
 out["decimated_conn"] = np.concatenate([list(l) for l in conn]).astype(np.uint32)      # in the reference's half-edge order
+for tag, src, qkw in [("quads", rec.mesh, {}), ("quads_strict", rec.mesh, dict(non_squareness_limit=1.3, normal_angle_limit=4.0, max_interior_angle=110.0))]:
+    q = ps.convert_tris_to_quads(src, **qkw)                    # postprocessing.rs:689-910 (cells in the reference's order)
+    out[tag + "_t"], out[tag + "_q"] = np.asarray(q.get_triangles()).astype(np.uint32), np.asarray(q.get_quads()).astype(np.uint32)
 path = os.path.join(ROOT, "tests", "golden", "meshproc_ref.npz")
 np.savez_compressed(path, **out)
 print({k: v.shape for k, v in out.items()}, os.path.getsize(path) // 1024, "KiB")
