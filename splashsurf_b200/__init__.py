@@ -35,6 +35,9 @@ class SplashsurfError(RuntimeError):
         self.message = message
 
 
+SS_ERR_MESH_CHECK = 200      # Python mirror only: a mesh consistency check of reconstruction_pipeline failed (the reference returns an error)
+
+
 class _Params(C.Structure):
     _fields_ = [
         ("particle_radius", C.c_float), ("rest_density", C.c_float), ("compact_support_radius", C.c_float),
@@ -301,6 +304,96 @@ def convert_tris_to_quads(mesh: "TriMesh3d", *, non_squareness_limit: float = 1.
                                           C.c_float(float(np.float32(non_squareness_limit))), C.c_float(rad(normal_angle_limit)),
                                           C.c_float(rad(max_interior_angle)), to.ctypes.data, C.byref(nt), qo.ctypes.data, C.byref(nq)))
     return MixedTriQuadMesh3d(v.copy(), to[:nt.value].astype(np.uint64), qo[:nq.value].astype(np.uint64))
+
+
+def _edge_table(tris: np.ndarray):
+    """Undirected edges of a triangle array: (unique sorted vertex pairs, incident face count per unique edge, inverse index per half-edge
+    in (triangle, local edge) order)."""
+    t = np.asarray(tris, dtype=np.int64)
+    he = np.stack([t[:, [0, 1]], t[:, [1, 2]], t[:, [2, 0]]], axis=1).reshape(-1, 2)      # half-edge (t, e) at row 3 t + e
+    und = np.sort(he, axis=1)
+    uniq, inv, cnt = np.unique(und, axis=0, return_inverse=True, return_counts=True)
+    return uniq, cnt, inv.reshape(-1)
+
+
+def find_non_manifold_vertices(mesh: "TriMesh3d") -> np.ndarray:
+    """TriMesh3d::find_non_manifold_vertices (mesh.rs:1007-1090): vertices whose incident triangles do not form ONE fan, i.e. are not
+    all connected through edges at that vertex.  Host code (numpy + scipy's connected components), ascending vertex index."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    t = np.asarray(mesh.triangles, dtype=np.int64)
+    nt = len(t)
+    if nt == 0:
+        return np.zeros(0, np.int64)
+    _, _, inv = _edge_table(t)
+    # corner node id = 3 * triangle + local corner; half-edge (t, e) joins corners e and (e + 1) % 3 of triangle t to the same edge
+    order = np.argsort(inv, kind="stable")
+    same = inv[order][1:] == inv[order][:-1]
+    a, b = order[:-1][same], order[1:][same]                   # consecutive half-edges of one undirected edge
+    ta, ea, tb, eb = a // 3, a % 3, b // 3, b % 3
+    va0, va1 = t[ta, ea], t[ta, (ea + 1) % 3]
+    vb0 = t[tb, eb]
+    # connect the corners that sit on the same vertex
+    ca0, ca1 = 3 * ta + ea, 3 * ta + (ea + 1) % 3
+    cb0, cb1 = 3 * tb + eb, 3 * tb + (eb + 1) % 3
+    flip = vb0 != va0                                          # opposite orientation: b's first corner is a's second vertex
+    src = np.concatenate([ca0, ca1])
+    dst = np.concatenate([np.where(flip, cb1, cb0), np.where(flip, cb0, cb1)])
+    n_nodes = 3 * nt
+    g = coo_matrix((np.ones(len(src), np.int8), (src, dst)), shape=(n_nodes, n_nodes))
+    _, label = connected_components(g, directed=False)
+    vert_of_corner = t.reshape(-1)
+    pairs = np.unique(np.stack([vert_of_corner, label], axis=1), axis=0)
+    verts, fans = np.unique(pairs[:, 0], return_counts=True)
+    return verts[fans > 1]
+
+
+def check_mesh_consistency(mesh: "TriMesh3d", grid: "UniformGrid", *, check_closed: bool = True, check_manifold: bool = True,
+                           debug: bool = False) -> Optional[str]:
+    """``pysplashsurf.check_mesh_consistency`` (marching_cubes.rs:129-213): None if the mesh is closed (no edge with a single incident
+    triangle) / manifold (no edge with more than two incident triangles, no vertex with more than one triangle fan), else a text with
+    the reference's messages.  Host code."""
+    uniq, cnt, _ = _edge_table(mesh.triangles)
+    n_boundary, n_nm_edges = int((cnt == 1).sum()), int((cnt > 2).sum())
+    nm_verts = find_non_manifold_vertices(mesh)
+    if (not check_closed or n_boundary == 0) and (not check_manifold or (n_nm_edges == 0 and len(nm_verts) == 0)):
+        return None
+    msgs = []
+    if check_closed and n_boundary:
+        msgs.append(f"Mesh is not closed. It has {n_boundary} boundary edges (edges that are connected to only one triangle).")
+        if debug:
+            msgs += [f"\tboundary edge {e.tolist()}" for e in uniq[cnt == 1]]
+    if check_manifold and n_nm_edges:
+        msgs.append(f"Mesh is not manifold. It has {n_nm_edges} non-manifold edges (edges that are connected to more than two triangles).")
+        if debug:
+            msgs += [f"\tnon-manifold edge {e.tolist()}" for e in uniq[cnt > 2]]
+    if check_manifold and len(nm_verts):
+        msgs.append(f"Mesh is not manifold. It has {len(nm_verts)} non-manifold vertices (vertices with more than one triangle fan).")
+        if debug:
+            msgs.append(f"\tNon-manifold vertices: {nm_verts.tolist()}")
+    return "\n".join(msgs)
+
+
+def clamp_mesh_with_aabb(mesh: "TriMesh3d", aabb_min, aabb_max, *, clamp_vertices: bool = True, keep_vertices: bool = False, point_attributes=None):
+    """Mesh3d::par_clamp_with_aabb (mesh.rs:334-371) as the pipeline applies it (reconstruct.rs:1394-1408): keeps the triangles with at
+    least one vertex inside the half-open box [min, max) (aabb.rs:220-222), drops the vertices no kept triangle uses (unless
+    `keep_vertices`), then clamps the remaining vertices into the box.  Returns (TriMesh3d, filtered point attributes).  Host code."""
+    v = np.asarray(mesh.vertices, dtype=np.float32)
+    t = np.asarray(mesh.triangles)
+    mn, mx = np.asarray(aabb_min, np.float32), np.asarray(aabb_max, np.float32)
+    inside = np.all(v >= mn, axis=1) & np.all(v < mx, axis=1)
+    keep_t = inside[t.astype(np.int64)].any(axis=1) if len(t) else np.zeros(0, bool)
+    t2 = t[keep_t]
+    attrs = dict(point_attributes or {})
+    if not keep_vertices:
+        used = np.zeros(len(v), bool)
+        used[t2.astype(np.int64).reshape(-1)] = True
+        newid = np.cumsum(used) - 1
+        v = v[used]
+        t2 = newid[t2.astype(np.int64)].astype(t.dtype)
+        attrs = {k: np.asarray(a)[used] for k, a in attrs.items()}
+    v = np.clip(v, mn, mx) if clamp_vertices else v.copy()
+    return TriMesh3d(np.ascontiguousarray(v, dtype=np.float32), t2), attrs
 
 
 class _MeshSurface:
@@ -661,10 +754,12 @@ def reconstruction_pipeline(particles, *, attributes_to_interpolate=None, partic
     reconstruct.rs:1058-1092 -- sequential half-edge collapses on the host (library entries ss_mesh_cleanup_f32 /
     ss_mesh_decimation_f32), after which the new mesh goes back to the device for the remaining steps.  ``generate_quads`` (+
     ``quad_max_edge_diag_ratio`` / ``quad_max_normal_angle`` / ``quad_max_interior_angle``) runs last (reconstruct.rs:1410-1441, host):
-    the returned mesh is then a MixedTriQuadMesh3d.  The remaining switches of the reference pipeline (mesh AABB clamping, mesh
-    checks) raise NotImplementedError when enabled."""
+    the returned mesh is then a MixedTriQuadMesh3d.  ``mesh_aabb_min`` / ``mesh_aabb_max`` (+ ``mesh_aabb_clamp_vertices``) clamp the
+    finished mesh (reconstruct.rs:1394-1408) and ``check_mesh_closed`` / ``check_mesh_manifold`` raise SplashsurfError with the
+    reference's message when the check fails (:1445-1470).  Only ``check_mesh_orientation`` is not provided (NotImplementedError)."""
     passive = ("mesh_cleanup", "decimate_barnacles", "mesh_cleanup_snap_dist", "keep_vertices", "generate_quads", "quad_max_edge_diag_ratio",
-               "quad_max_normal_angle", "quad_max_interior_angle", "mesh_aabb_clamp_vertices")
+               "quad_max_normal_angle", "quad_max_interior_angle", "mesh_aabb_min", "mesh_aabb_max", "mesh_aabb_clamp_vertices",
+               "check_mesh_closed", "check_mesh_manifold", "check_mesh_debug")
     enabled = [k for k, v in post.items() if v not in (False, None, 0) and k not in passive]
     if enabled:
         raise NotImplementedError(f"post-processing not provided by the device path: {enabled}")
@@ -742,6 +837,14 @@ def reconstruction_pipeline(particles, *, attributes_to_interpolate=None, partic
             point[name] = out
         rec.normals = point.get("normals")
         mesh = TriMesh3d(verts, out_mesh.triangles)
+        if post.get("mesh_aabb_min") is not None and post.get("mesh_aabb_max") is not None:     # reconstruct.rs:1394-1408
+            mesh, point = clamp_mesh_with_aabb(mesh, post["mesh_aabb_min"], post["mesh_aabb_max"], clamp_vertices=bool(post.get("mesh_aabb_clamp_vertices", True)),
+                                               keep_vertices=keep_vertices, point_attributes=point)
+        if (post.get("check_mesh_closed") or post.get("check_mesh_manifold")) and not post.get("generate_quads", False):   # :1445-1470
+            problems = check_mesh_consistency(mesh, rec.grid, check_closed=bool(post.get("check_mesh_closed")),
+                                              check_manifold=bool(post.get("check_mesh_manifold")), debug=bool(post.get("check_mesh_debug")))
+            if problems:
+                raise SplashsurfError(SS_ERR_MESH_CHECK, problems)
         if post.get("generate_quads", False):                                  # reconstruct.rs:1410-1441
             mesh = convert_tris_to_quads(mesh, non_squareness_limit=post.get("quad_max_edge_diag_ratio", 1.75),
                                          normal_angle_limit=post.get("quad_max_normal_angle", 10.0),

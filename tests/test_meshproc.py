@@ -114,3 +114,73 @@ def test_meshproc_matches_reference_live(ss, oracle_mod, case):
         m = ss.TriMesh3d(start_v.copy(), start_t.copy())
         ss.barnacle_decimation(m, keep_vertices=keep)
         assert _same(m, np.asarray(start_ref.vertices), np.asarray(start_ref.triangles))
+
+
+def _tetra(offset, base):
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], np.float32) + np.asarray(offset, np.float32)
+    t = np.array([[0, 2, 1], [0, 1, 3], [1, 2, 3], [0, 3, 2]], np.uint64) + base
+    return v, t
+
+
+def test_check_mesh_consistency_and_clamp_unit_cases(ss):
+    """marching_cubes.rs:129-213 / mesh.rs:334-371, :1007-1090 on hand-made meshes: a closed tetrahedron, an open one, two tetrahedra
+    glued at one vertex (non-manifold vertex) and at one edge (non-manifold edge: four incident faces)."""
+    grid = ss.UniformGrid(ss.Aabb3d(np.zeros(3, np.float32), np.full(3, 4, np.float32)), 1.0, [5, 5, 5], [4, 4, 4])
+    v, t = _tetra([0, 0, 0], 0)
+    closed = ss.TriMesh3d(v, t)
+    assert ss.check_mesh_consistency(closed, grid) is None and len(ss.find_non_manifold_vertices(closed)) == 0
+    opened = ss.TriMesh3d(v, t[:3])
+    msg = ss.check_mesh_consistency(opened, grid)
+    assert msg.startswith("Mesh is not closed. It has 3 boundary edges") and ss.check_mesh_consistency(opened, grid, check_closed=False) is None
+    # two tetrahedra sharing vertex 0 only
+    v2, t2 = _tetra([-2, -2, -2], 4)
+    vv = np.concatenate([v, v2[1:]]); t2 = np.where(t2 == 4, 0, t2 - 1)
+    glued = ss.TriMesh3d(vv, np.concatenate([t, t2]))
+    assert ss.find_non_manifold_vertices(glued).tolist() == [0]
+    msg = ss.check_mesh_consistency(glued, grid, debug=True)
+    assert "1 non-manifold vertices" in msg and "Non-manifold vertices: [0]" in msg and ss.check_mesh_consistency(glued, grid, check_manifold=False) is None
+    # two tetrahedra sharing the edge (0, 1): that edge has four incident faces
+    w = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [0, -1, 0], [0, 0, -1]], np.float32)
+    ta = np.array([[0, 2, 1], [0, 1, 3], [1, 2, 3], [0, 3, 2]], np.uint64)
+    tb = np.array([[0, 1, 4], [0, 5, 1], [1, 5, 4], [0, 4, 5]], np.uint64)
+    msg = ss.check_mesh_consistency(ss.TriMesh3d(w, np.concatenate([ta, tb])), grid)
+    assert "1 non-manifold edges" in msg
+    # clamp: triangles with a vertex inside [min, max) stay, unused vertices go, the rest is clamped into the box
+    m, attrs = ss.clamp_mesh_with_aabb(closed, [-0.5, -0.5, 0.5], [2, 2, 2], point_attributes={"a": np.arange(4.0)})
+    assert m.ncells == 3 and m.nvertices == 4 and float(m.vertices[:, 2].min()) == 0.5 and attrs["a"].tolist() == [0.0, 1.0, 2.0, 3.0]
+    m, attrs = ss.clamp_mesh_with_aabb(closed, [0.5, -0.5, -0.5], [2, 2, 2], clamp_vertices=False, point_attributes={"a": np.arange(4.0)})
+    assert m.ncells == 3 and np.array_equal(m.vertices, closed.vertices)            # every vertex is still used by a kept triangle
+    m, _ = ss.clamp_mesh_with_aabb(closed, [5, 5, 5], [6, 6, 6])
+    assert m.ncells == 0 and m.nvertices == 0
+    m, _ = ss.clamp_mesh_with_aabb(closed, [5, 5, 5], [6, 6, 6], keep_vertices=True, clamp_vertices=False)
+    assert m.ncells == 0 and m.nvertices == 4
+
+
+def test_clamp_and_checks_match_reference_live(ss, oracle_mod):
+    """The reference pipeline's mesh-AABB clamp (same input mesh: its own raw mesh) and check_mesh_consistency, on random boxes."""
+    if not oracle_mod.reference_available():
+        pytest.skip("reference wheel not unpacked (oracle/_ref)")
+    import re
+    from splashsurf_b200 import synthetic as syn
+    ps = oracle_mod.reference()
+    p = syn.splash((12, 12, 12), 4, 0.025, 91)
+    kw = dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.75, iso_surface_threshold=0.6, subdomain_grid=True)
+    rec = ps.reconstruct_surface(p, **kw)
+    v, t = np.array(rec.mesh.vertices, np.float32), np.array(rec.mesh.triangles, np.uint64)
+    g = rec.grid
+    grid = ss.UniformGrid(ss.Aabb3d(np.asarray(g.aabb.min, np.float32), np.asarray(g.aabb.max, np.float32)), float(g.cell_size), list(g.npoints_per_dim), list(g.ncells_per_dim))
+    assert ps.check_mesh_consistency(rec.mesh, g) is None and ss.check_mesh_consistency(ss.TriMesh3d(v, t), grid) is None
+    lo, hi = v.min(0), v.max(0)
+    rng = np.random.default_rng(5)
+    for trial in range(12):
+        c = lo + rng.random(3) * (hi - lo); e = rng.uniform(0.05, 0.3, 3) * (hi - lo)
+        a, b = (c - e).tolist(), (c + e).tolist()
+        keep, clampv = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+        mw, _ = ps.reconstruction_pipeline(p, mesh_aabb_min=a, mesh_aabb_max=b, mesh_aabb_clamp_vertices=clampv, keep_vertices=keep, mesh_smoothing_weights=False, **kw)
+        cm, _ = ss.clamp_mesh_with_aabb(ss.TriMesh3d(v, t), a, b, clamp_vertices=clampv, keep_vertices=keep)
+        assert np.array_equal(np.asarray(mw.mesh.vertices), cm.vertices) and np.array_equal(np.asarray(mw.mesh.triangles), cm.triangles)
+        r, mine = ps.check_mesh_consistency(mw.mesh, g, debug=True), ss.check_mesh_consistency(cm, grid, debug=True)
+        head = lambda s_: [l for l in (s_ or "None").split("\n") if not l.startswith("\t")]       # noqa: E731
+        assert head(r) == head(mine)
+        if r and "Non-manifold vertices" in r:
+            assert sorted(int(x) for x in re.findall(r"\d+", r.split("Non-manifold vertices:")[1])) == ss.find_non_manifold_vertices(cm).tolist()

@@ -236,3 +236,31 @@ def test_mesh_without_triangles_has_empty_connectivity(ss):
     m = ss.TriMesh3d(np.random.default_rng(3).random((7, 3)).astype(np.float32), np.zeros((0, 3), np.uint64))
     assert m.vertex_vertex_connectivity().copy_connectivity() == [[] for _ in range(7)]
     assert np.isnan(m.vertex_normals_parallel()).all()
+
+
+@pytest.mark.gpu
+def test_pipeline_quads_mesh_aabb_and_checks(ss, oracle_mod):
+    """The remaining switches of the pipeline mirror: generate_quads (reconstruct.rs:1410-1441), mesh_aabb_min / max (+ clamp,
+    :1394-1408) and check_mesh_closed / check_mesh_manifold (:1445-1470) -- composed exactly like the free functions on the raw mesh."""
+    from splashsurf_b200 import synthetic as syn
+    x = syn.splash((10, 10, 10), 2, 0.025, 616)
+    kw = dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.75, iso_surface_threshold=0.6)
+    raw = ss.reconstruct_surface(x, **kw)
+    # quads
+    mwd, _ = ss.reconstruction_pipeline(x, generate_quads=True, quad_max_normal_angle=15.0, mesh_smoothing_weights=False, **kw)
+    want = ss.convert_tris_to_quads(raw.mesh, normal_angle_limit=15.0)
+    assert np.array_equal(mwd.mesh.get_quads(), want.get_quads()) and np.array_equal(mwd.mesh.get_triangles(), want.get_triangles())
+    assert len(want.get_quads()) > 0
+    # a closed, manifold mesh passes the checks; clamping it to a box opens it, and the closedness check then fails like the reference's
+    ss.reconstruction_pipeline(x, check_mesh_closed=True, check_mesh_manifold=True, mesh_smoothing_weights=False, **kw)
+    lo, hi = raw.mesh.vertices.min(0), raw.mesh.vertices.max(0)
+    a, b = (lo + 0.2 * (hi - lo)).tolist(), (lo + 0.7 * (hi - lo)).tolist()
+    mwd, _ = ss.reconstruction_pipeline(x, mesh_aabb_min=a, mesh_aabb_max=b, mesh_smoothing_weights=False, compute_normals=True, **kw)
+    cm, _ = ss.clamp_mesh_with_aabb(raw.mesh, a, b)
+    assert np.array_equal(mwd.mesh.vertices, cm.vertices) and np.array_equal(mwd.mesh.triangles, cm.triangles)
+    assert mwd.point_attributes["normals"].shape == cm.vertices.shape and 0 < cm.ncells < raw.mesh.ncells
+    with pytest.raises(ss.SplashsurfError) as e:
+        ss.reconstruction_pipeline(x, mesh_aabb_min=a, mesh_aabb_max=b, check_mesh_closed=True, mesh_smoothing_weights=False, **kw)
+    assert e.value.code == ss.SS_ERR_MESH_CHECK and "Mesh is not closed" in e.value.message
+    with pytest.raises(NotImplementedError):
+        ss.reconstruction_pipeline(x, check_mesh_orientation=True, **kw)
