@@ -420,7 +420,8 @@ def main():
                 traffic_note = tj.get("source", "")
         except Exception as e:      # noqa: BLE001
             traffic_note = f"no capture: {e}"
-        roof = {"bound": "hbm", "kernel": "k_levelset", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+        ls_kernel = {2: "level-set stage: k_certify_warp + k_exact_warp", 1: "level-set stage: k_certify + k_levelset (fix mode)", 0: "k_levelset"}[int(args.levelset_variant)]
+        roof = {"bound": "hbm", "kernel": ls_kernel, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "traffic_note": traffic_note,
                 "peak_source": peak_src, "launches_per_step": ls_launches / args.steps, "ms_per_step": ls_ms / args.steps,
                 "algorithmic_bytes_per_step": ls_bytes,
