@@ -374,6 +374,25 @@ def check_mesh_consistency(mesh: "TriMesh3d", grid: "UniformGrid", *, check_clos
     return "\n".join(msgs)
 
 
+def find_flipped_faces(mesh: "TriMesh3d") -> np.ndarray:
+    """The orientation check of the pipeline (reconstruct.rs:1481-1507): triangles whose unit normal makes an angle of more than 0.99 pi
+    with the area-weighted normal of one of their vertices.  Host code; ascending triangle index."""
+    v = np.asarray(mesh.vertices, dtype=np.float32)
+    t = np.asarray(mesh.triangles, dtype=np.int64)
+    if len(t) == 0:
+        return np.zeros(0, np.int64)
+    cr = np.cross(v[t[:, 1]] - v[t[:, 0]], v[t[:, 2]] - v[t[:, 0]]).astype(np.float32)        # area-weighted (mesh.rs:842-906)
+    vn = np.zeros_like(v)
+    for c in range(3):
+        np.add.at(vn, t[:, c], cr)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        tn = cr / np.linalg.norm(cr, axis=1, keepdims=True)
+        n1 = vn[t]                                                                             # (T, 3 corners, 3)
+        cang = np.einsum("tcd,td->tc", n1, tn) / (np.linalg.norm(n1, axis=2) * np.linalg.norm(tn, axis=1, keepdims=True))
+        ang = np.arccos(np.clip(cang, -1.0, 1.0))
+    return np.nonzero((ang > np.pi * 0.99).any(axis=1))[0]
+
+
 def clamp_mesh_with_aabb(mesh: "TriMesh3d", aabb_min, aabb_max, *, clamp_vertices: bool = True, keep_vertices: bool = False, point_attributes=None):
     """Mesh3d::par_clamp_with_aabb (mesh.rs:334-371) as the pipeline applies it (reconstruct.rs:1394-1408): keeps the triangles with at
     least one vertex inside the half-open box [min, max) (aabb.rs:220-222), drops the vertices no kept triangle uses (unless
@@ -756,10 +775,10 @@ def reconstruction_pipeline(particles, *, attributes_to_interpolate=None, partic
     ``quad_max_edge_diag_ratio`` / ``quad_max_normal_angle`` / ``quad_max_interior_angle``) runs last (reconstruct.rs:1410-1441, host):
     the returned mesh is then a MixedTriQuadMesh3d.  ``mesh_aabb_min`` / ``mesh_aabb_max`` (+ ``mesh_aabb_clamp_vertices``) clamp the
     finished mesh (reconstruct.rs:1394-1408) and ``check_mesh_closed`` / ``check_mesh_manifold`` raise SplashsurfError with the
-    reference's message when the check fails (:1445-1470).  Only ``check_mesh_orientation`` is not provided (NotImplementedError)."""
+    reference's message when the check fails (:1445-1470); ``check_mesh_orientation`` likewise (:1481-1541)."""
     passive = ("mesh_cleanup", "decimate_barnacles", "mesh_cleanup_snap_dist", "keep_vertices", "generate_quads", "quad_max_edge_diag_ratio",
                "quad_max_normal_angle", "quad_max_interior_angle", "mesh_aabb_min", "mesh_aabb_max", "mesh_aabb_clamp_vertices",
-               "check_mesh_closed", "check_mesh_manifold", "check_mesh_debug")
+               "check_mesh_closed", "check_mesh_manifold", "check_mesh_orientation", "check_mesh_debug")
     enabled = [k for k, v in post.items() if v not in (False, None, 0) and k not in passive]
     if enabled:
         raise NotImplementedError(f"post-processing not provided by the device path: {enabled}")
@@ -845,6 +864,10 @@ def reconstruction_pipeline(particles, *, attributes_to_interpolate=None, partic
                                               check_manifold=bool(post.get("check_mesh_manifold")), debug=bool(post.get("check_mesh_debug")))
             if problems:
                 raise SplashsurfError(SS_ERR_MESH_CHECK, problems)
+        if post.get("check_mesh_orientation") and not post.get("generate_quads", False):          # reconstruct.rs:1481-1541
+            flipped = find_flipped_faces(mesh)
+            if len(flipped):
+                raise SplashsurfError(SS_ERR_MESH_CHECK, f"Mesh is not consistently oriented. Found {len(flipped)} faces with normals flipped relative to adjacent vertices.")
         if post.get("generate_quads", False):                                  # reconstruct.rs:1410-1441
             mesh = convert_tris_to_quads(mesh, non_squareness_limit=post.get("quad_max_edge_diag_ratio", 1.75),
                                          normal_angle_limit=post.get("quad_max_normal_angle", 10.0),

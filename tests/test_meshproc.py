@@ -122,6 +122,18 @@ def _tetra(offset, base):
     return v, t
 
 
+def _flat_sheet(n=6):
+    """n x n quads of the z = 0 plane, two triangles each, all oriented +z."""
+    g = np.stack(np.meshgrid(np.arange(n + 1), np.arange(n + 1), indexing="ij"), -1).reshape(-1, 2)
+    v = np.concatenate([g, np.zeros((len(g), 1))], axis=1).astype(np.float32)
+    idx = lambda i, j: i * (n + 1) + j          # noqa: E731
+    t = []
+    for i in range(n):
+        for j in range(n):
+            t += [(idx(i, j), idx(i + 1, j), idx(i + 1, j + 1)), (idx(i, j), idx(i + 1, j + 1), idx(i, j + 1))]
+    return v, np.array(t, np.uint64)
+
+
 def test_check_mesh_consistency_and_clamp_unit_cases(ss):
     """marching_cubes.rs:129-213 / mesh.rs:334-371, :1007-1090 on hand-made meshes: a closed tetrahedron, an open one, two tetrahedra
     glued at one vertex (non-manifold vertex) and at one edge (non-manifold edge: four incident faces)."""
@@ -145,6 +157,12 @@ def test_check_mesh_consistency_and_clamp_unit_cases(ss):
     tb = np.array([[0, 1, 4], [0, 5, 1], [1, 5, 4], [0, 4, 5]], np.uint64)
     msg = ss.check_mesh_consistency(ss.TriMesh3d(w, np.concatenate([ta, tb])), grid)
     assert "1 non-manifold edges" in msg
+    # orientation: a consistently oriented mesh has no flipped face; a reversed triangle of a flat sheet is anti-parallel to the normals of its vertices
+    assert len(ss.find_flipped_faces(closed)) == 0
+    sheet_v, sheet_t = _flat_sheet()
+    assert len(ss.find_flipped_faces(ss.TriMesh3d(sheet_v, sheet_t))) == 0
+    bad_t = sheet_t.copy(); bad_t[31] = bad_t[31][[0, 2, 1]]                                  # an interior triangle, reversed
+    assert ss.find_flipped_faces(ss.TriMesh3d(sheet_v, bad_t)).tolist() == [31]
     # clamp: triangles with a vertex inside [min, max) stay, unused vertices go, the rest is clamped into the box
     m, attrs = ss.clamp_mesh_with_aabb(closed, [-0.5, -0.5, 0.5], [2, 2, 2], point_attributes={"a": np.arange(4.0)})
     assert m.ncells == 3 and m.nvertices == 4 and float(m.vertices[:, 2].min()) == 0.5 and attrs["a"].tolist() == [0.0, 1.0, 2.0, 3.0]

@@ -262,5 +262,4 @@ def test_pipeline_quads_mesh_aabb_and_checks(ss, oracle_mod):
     with pytest.raises(ss.SplashsurfError) as e:
         ss.reconstruction_pipeline(x, mesh_aabb_min=a, mesh_aabb_max=b, check_mesh_closed=True, mesh_smoothing_weights=False, **kw)
     assert e.value.code == ss.SS_ERR_MESH_CHECK and "Mesh is not closed" in e.value.message
-    with pytest.raises(NotImplementedError):
-        ss.reconstruction_pipeline(x, check_mesh_orientation=True, **kw)
+    ss.reconstruction_pipeline(x, check_mesh_orientation=True, mesh_smoothing_weights=False, **kw)       # a marching-cubes mesh is consistently oriented
