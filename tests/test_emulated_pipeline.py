@@ -491,3 +491,22 @@ def test_emulated_large_result_copies_take_the_staged_path(emu, oracle_mod):
         assert np.array_equal(g.particle_densities, o["particle_densities"]) and g.mesh.nvertices == len(o["vertices"])
     finally:
         ctx.close()
+
+
+def test_emulated_cli_with_postprocessing(emu, tmp_path):
+    """`python -m splashsurf_b200 reconstruct` with the reference CLI's post-processing switches (clean-up, decimation, smoothing, normals,
+    mesh checks, quads) -- control flow of the thin harness on the CPU executor."""
+    from splashsurf_b200 import io, __main__ as cli
+    p = _splash((8, 8, 8), 2, 0.025, 3)
+    src = str(tmp_path / "in.xyz")
+    io.write_xyz(src, p)
+    base = ["reconstruct", src, "-r", "0.025", "-l", "2.0", "-c", "0.75"]
+    assert cli.main(base + ["-o", str(tmp_path / "a.obj")]) == 0
+    v0, t0 = io.read_obj(str(tmp_path / "a.obj"))[:2]
+    assert cli.main(base + ["--mesh-cleanup", "on", "--decimate-barnacles", "on", "--mesh-smoothing-iters", "5", "--mesh-smoothing-weights", "on",
+                            "--normals", "on", "--sph-normals", "on", "--check-mesh", "on", "-o", str(tmp_path / "b.obj")]) == 0
+    v1, t1 = io.read_obj(str(tmp_path / "b.obj"))[:2]
+    assert 0 < len(v1) < len(v0) and 0 < len(t1) < len(t0)
+    assert cli.main(base + ["--generate-quads", "on", "-o", str(tmp_path / "c.npz")]) == 0
+    z = np.load(tmp_path / "c.npz")
+    assert len(z["quads"]) > 0 and len(z["triangles"]) + 2 * len(z["quads"]) == len(t0)
