@@ -262,7 +262,9 @@ def marching_cubes_cleanup(mesh: "TriMesh3d", grid: "UniformGrid", *, max_rel_sn
                            keep_vertices: bool = False) -> "VertexVertexConnectivity":
     """``pysplashsurf.marching_cubes_cleanup`` (postprocessing.rs:99-242): simplifies a marching-cubes mesh in place by merging
     vertices that share their nearest grid point; returns the vertex-vertex connectivity of the result.  Host code in the library
-    (sequential half-edge collapses, as in the reference)."""
+    (sequential half-edge collapses, as in the reference).  Accepts a TriMesh3d or a MeshWithData (its attributes are NOT carried over
+    to the new vertex set; the pipeline applies the clean-up before any attribute exists)."""
+    mesh = getattr(mesh, "mesh", mesh)
     g = _grid_struct(grid)
     snap = -1.0 if max_rel_snap_dist is None else float(max_rel_snap_dist)
     return _host_mesh_op(mesh, lambda L, v, nv, t, nt, off, idx: L.ss_mesh_cleanup_f32(v, nv, t, nt, C.byref(g), C.c_float(snap), int(max_iter),
@@ -288,11 +290,24 @@ class MixedTriQuadMesh3d:
     def get_quads(self) -> np.ndarray:
         return self._quads
 
+    @property
+    def nvertices(self) -> int:
+        return len(self.vertices)
+
+    @property
+    def ncells(self) -> int:
+        return len(self._triangles) + len(self._quads)
+
 
 def convert_tris_to_quads(mesh: "TriMesh3d", *, non_squareness_limit: float = 1.75, normal_angle_limit: float = 10.0,
                           max_interior_angle: float = 135.0) -> MixedTriQuadMesh3d:
     """``pysplashsurf.convert_tris_to_quads`` (postprocessing.rs:689-910; angles in degrees): merges pairs of triangles sharing an edge
-    into quads.  Returns a new mesh; the input is not modified.  Host code in the library, cells in the reference's order."""
+    into quads.  Returns a new mesh; the input is not modified.  Host code in the library, cells in the reference's order.  A
+    MeshWithData comes back as a MeshWithData around the quad mesh with its point attributes (cell attributes are dropped, as in
+    reconstruct.rs:1424-1437)."""
+    if hasattr(mesh, "point_attributes"):
+        q = convert_tris_to_quads(mesh.mesh, non_squareness_limit=non_squareness_limit, normal_angle_limit=normal_angle_limit, max_interior_angle=max_interior_angle)
+        return MeshWithData(q, dict(mesh.point_attributes), {})
     L = load_library()
     v = np.ascontiguousarray(mesh.vertices, dtype=np.float32)
     t = np.ascontiguousarray(mesh.triangles, dtype=np.uint32)
@@ -352,7 +367,8 @@ def check_mesh_consistency(mesh: "TriMesh3d", grid: "UniformGrid", *, check_clos
                            debug: bool = False) -> Optional[str]:
     """``pysplashsurf.check_mesh_consistency`` (marching_cubes.rs:129-213): None if the mesh is closed (no edge with a single incident
     triangle) / manifold (no edge with more than two incident triangles, no vertex with more than one triangle fan), else a text with
-    the reference's messages.  Host code."""
+    the reference's messages.  Host code.  Accepts a TriMesh3d or a MeshWithData."""
+    mesh = getattr(mesh, "mesh", mesh)
     uniq, cnt, _ = _edge_table(mesh.triangles)
     n_boundary, n_nm_edges = int((cnt == 1).sum()), int((cnt > 2).sum())
     nm_verts = find_non_manifold_vertices(mesh)

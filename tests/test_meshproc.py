@@ -202,3 +202,13 @@ def test_clamp_and_checks_match_reference_live(ss, oracle_mod):
         assert head(r) == head(mine)
         if r and "Non-manifold vertices" in r:
             assert sorted(int(x) for x in re.findall(r"\d+", r.split("Non-manifold vertices:")[1])) == ss.find_non_manifold_vertices(cm).tolist()
+
+
+def test_half_edge_connectivity_kat(ss):
+    """halfedge_mesh.rs:564-590 (test_half_edge_mesh): the vertex connectivity a half-edge mesh reports for two triangles sharing an
+    edge equals TriMesh3d::vertex_vertex_connectivity up to order."""
+    v = np.array([[0, 1, 0], [1, 0, 0], [1, 2, 0], [2, 1, 0]], np.float32)
+    t = np.array([[0, 1, 2], [1, 3, 2]], np.uint64)
+    m = ss.TriMesh3d(v, t)
+    conn = ss.barnacle_decimation(m, keep_vertices=True).copy_connectivity()        # no barnacles: the mesh comes back unchanged
+    assert np.array_equal(m.triangles, t) and [sorted(c) for c in conn] == [[1, 2], [0, 2, 3], [0, 1, 3], [1, 2]]

@@ -263,3 +263,25 @@ def test_pipeline_quads_mesh_aabb_and_checks(ss, oracle_mod):
         ss.reconstruction_pipeline(x, mesh_aabb_min=a, mesh_aabb_max=b, check_mesh_closed=True, mesh_smoothing_weights=False, **kw)
     assert e.value.code == ss.SS_ERR_MESH_CHECK and "Mesh is not closed" in e.value.message
     ss.reconstruction_pipeline(x, check_mesh_orientation=True, mesh_smoothing_weights=False, **kw)       # a marching-cubes mesh is consistently oriented
+
+
+@pytest.mark.gpu
+def test_reference_python_tests_check_consistency_and_quads(ss):
+    """pysplashsurf/tests/test_basic.py:193-268 (check_consistency_test, tris_to_quads_test) and test_calling.py:35 on the same anchor file
+    with this package in the place of pysplashsurf."""
+    import os
+    from conftest import GOLDEN
+    particles = np.load(os.path.join(GOLDEN, "cfg1_particles.npy"))
+    rec = ss.reconstruct_surface(particles, particle_radius=0.025, rest_density=1000.0, smoothing_length=2.0, cube_size=1.0, iso_surface_threshold=0.6)
+    assert ss.check_mesh_consistency(rec.mesh, rec.grid) is None
+    mwd, rec2 = ss.reconstruction_pipeline(particles, particle_radius=0.025, rest_density=1000.0, smoothing_length=2.0, cube_size=1.0,
+                                           iso_surface_threshold=0.6, mesh_smoothing_iters=5, output_mesh_smoothing_weights=True)
+    assert ss.check_mesh_consistency(mwd, rec2.grid) is None
+    q = ss.convert_tris_to_quads(mwd)
+    assert type(q.mesh) is ss.MixedTriQuadMesh3d and q.nvertices == mwd.nvertices and q.ncells < mwd.ncells
+    tris, quads = q.mesh.get_triangles(), q.mesh.get_quads()
+    assert tris.dtype in (np.uint32, np.uint64) and quads.dtype in (np.uint32, np.uint64)
+    assert tris.shape[1] == 3 and quads.shape[1] == 4 and len(tris) + 2 * len(quads) == mwd.ncells
+    assert set(q.point_attributes) == set(mwd.point_attributes)
+    ss.marching_cubes_cleanup(mwd, rec2.grid)                       # test_calling.py:35: accepts a MeshWithData
+    assert mwd.mesh.nvertices < rec2.mesh.nvertices
