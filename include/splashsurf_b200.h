@@ -298,7 +298,8 @@ int ss_surface_replace_mesh_f32(ss_surface *s, const float *verts, uint64_t nv, 
 /* ---- sequential half-edge algorithms, HOST code like in the reference (no context, no device needed).
  * In place on host arrays: verts [*nv x 3] f32, tris [*nt x 3] u32; *nv / *nt are updated (never grow).  keep_vertices != 0 keeps
  * vertices that lost all their triangles (halfedge_mesh.rs:92-100, :446-497).  Optional output: the vertex-vertex connectivity of
- * the result in half-edge order as CSR (conn_offsets: nv_in + 1 entries, conn_indices: capacity 3 * nt_in), which the reference
+ * the result in half-edge order as CSR (conn_offsets: nv_in + 1 entries, conn_indices: capacity 6 * nt_in = twice the edges of an
+ * open mesh; 3 * nt_in suffices for a closed one), which the reference
  * returns as Vec<Vec<usize>>.
  *
  * marching_cubes_cleanup (postprocessing.rs:99-242, "mesh displacement" after Moore & Warren): every vertex is assigned its nearest

@@ -250,7 +250,7 @@ def _host_mesh_op(mesh: "TriMesh3d", call) -> "VertexVertexConnectivity":
     t = np.ascontiguousarray(mesh.triangles, dtype=np.uint32).copy()
     nv, nt = C.c_uint64(len(v)), C.c_uint64(len(t))
     off = np.zeros(len(v) + 1, np.uint64)
-    idx = np.empty(max(3 * len(t), 1), np.uint32)
+    idx = np.empty(max(6 * len(t), 1), np.uint32)           # sum of the valences = 2 x edges <= 6 x triangles (3 x for a closed mesh)
     _check(L, call(L, v.ctypes.data if len(v) else None, C.byref(nv), t.ctypes.data if len(t) else None, C.byref(nt), off.ctypes.data, idx.ctypes.data))
     mesh.vertices = v[:nv.value].copy()
     mesh.triangles = t[:nt.value].astype(np.uint64)
