@@ -41,7 +41,8 @@ enum {
     SS_ERR_INVALID_DOMAIN = 8,           /* DensityMapError::InvalidDomain (density_map.rs:48-61) */
     SS_ERR_CUDA = 100,                   /* CUDA runtime failure; see ss_last_error() */
     SS_ERR_NO_DEVICE = 101,              /* no CUDA device: the product never falls back to a CPU path */
-    SS_ERR_OUT_OF_MEMORY = 102
+    SS_ERR_OUT_OF_MEMORY = 102,
+    SS_ERR_IO = 103                      /* a mesh file could not be opened or written (anyhow errors of the reference's writers) */
 };
 
 /* Mirrors splashsurf_lib::Parameters<f32> (lib.rs:158-189) + GridDecompositionParameters (lib.rs:140-145).
@@ -321,6 +322,33 @@ int ss_mesh_decimation_f32(float *verts, uint64_t *nv, uint32_t *tris, uint64_t 
 int ss_mesh_tris_to_quads_f32(const float *verts, uint64_t nv, const uint32_t *tris, uint64_t nt, float non_squareness_limit,
                               float normal_angle_limit_rad, float max_interior_angle_rad, uint32_t *tris_out, uint64_t *nt_out,
                               uint32_t *quads_out, uint64_t *nq_out);
+
+/* ---- the mesh writers of `splashsurf reconstruct -o <file>` (splashsurf/src/io.rs:276-316 write_mesh -> vtk_format.rs:188-211
+ * write_vtk(mesh, file, "mesh"), ply_format.rs:190-267 mesh_to_ply, obj_format.rs:17-71 mesh_to_obj).  HOST code, multi-threaded formatting,
+ * output byte for byte the reference CLI's file for the same mesh and attributes.  A mesh is vertices + triangles (+ quads of a
+ * MixedTriQuadMesh3d: cells are the triangles followed by the quads, postprocessing.rs:901-903) with u32 or u64 indices; attributes
+ * mirror OwnedAttributeData (mesh.rs): f32 scalars, f32 3-vectors, u64 scalars, one entry per vertex / per cell.
+ *   .vtk  legacy BINARY unstructured grid, every attribute as SCALARS <name> float|unsigned_long 1|3 + default lookup table
+ *   .ply  binary_little_endian: x y z + point attributes per vertex ("normals" as nx ny nz, u64 as uint); cell attributes are not written
+ *   .obj  v / vn (a point attribute named "normals") / f lines, numbers as Rust's `{}` prints them (shortest round trip, no exponent)
+ * format SS_MESH_FORMAT_AUTO picks by the extension (case-insensitive) with the reference's error messages.  threads 0 = up to 16. */
+#define SS_ATTR_SCALAR_F32 0
+#define SS_ATTR_VECTOR3_F32 1
+#define SS_ATTR_SCALAR_U64 2
+#define SS_MESH_FORMAT_AUTO 0
+#define SS_MESH_FORMAT_VTK 1
+#define SS_MESH_FORMAT_PLY 2
+#define SS_MESH_FORMAT_OBJ 3
+typedef struct ss_mesh_attribute {
+    const char *name;
+    int32_t kind;                        /* SS_ATTR_* */
+    const void *data;
+} ss_mesh_attribute;
+int ss_write_mesh_f32(const char *path, int format, const float *verts, uint64_t nv, const void *tris, uint64_t nt, const void *quads,
+                      uint64_t nq, int index_bytes, const ss_mesh_attribute *point_attrs, uint32_t n_point_attrs,
+                      const ss_mesh_attribute *cell_attrs, uint32_t n_cell_attrs, uint32_t threads);
+/* One f32 as the OBJ writer prints it (Rust `{}`), NUL-terminated; 64 bytes always suffice. */
+int ss_format_f32(float value, char *out, uint64_t capacity);
 
 /* Replaces the surface's normals by [num_vertices * 3] caller-supplied ones (then ss_surface_smooth_normals_f32 smooths any field). */
 int ss_surface_set_normals_f32(ss_surface *s, const float *normals);

@@ -35,6 +35,10 @@ class SplashsurfError(RuntimeError):
         self.message = message
 
 
+# error codes of the C ABI (include/splashsurf_b200.h)
+SS_OK, SS_ERR_INVALID_CELL_SIZE, SS_ERR_DEGENERATE_AABB, SS_ERR_INCONSISTENT_AABB, SS_ERR_INDEX_TOO_SMALL, SS_ERR_REAL_TOO_SMALL = 0, 1, 2, 3, 4, 5
+SS_ERR_INVALID_PARAMETER, SS_ERR_UNSUPPORTED, SS_ERR_INVALID_DOMAIN = 6, 7, 8
+SS_ERR_CUDA, SS_ERR_NO_DEVICE, SS_ERR_OUT_OF_MEMORY, SS_ERR_IO = 100, 101, 102, 103
 SS_ERR_MESH_CHECK = 200      # Python mirror only: a mesh consistency check of reconstruction_pipeline failed (the reference returns an error)
 
 
@@ -80,6 +84,11 @@ def load_library():
                           f"(run `python -m splashsurf_b200.build`); there is no CPU fallback")
     _LIB = _bind(C.CDLL(path))
     return _LIB
+
+
+class _MeshAttribute(C.Structure):
+    """ss_mesh_attribute (include/splashsurf_b200.h)."""
+    _fields_ = [("name", C.c_char_p), ("kind", C.c_int32), ("data", C.c_void_p)]
 
 
 def _bind(L):
@@ -152,6 +161,9 @@ def _bind(L):
     L.ss_mesh_cleanup_f32.argtypes = [vp, C.POINTER(u64), vp, C.POINTER(u64), C.POINTER(_Grid), C.c_float, u64, C.c_int, vp, vp]
     L.ss_mesh_decimation_f32.argtypes = [vp, C.POINTER(u64), vp, C.POINTER(u64), C.c_int, vp, vp]
     L.ss_mesh_tris_to_quads_f32.argtypes = [vp, u64, vp, u64, C.c_float, C.c_float, C.c_float, vp, C.POINTER(u64), vp, C.POINTER(u64)]
+    L.ss_write_mesh_f32.argtypes = [C.c_char_p, C.c_int, vp, u64, vp, u64, vp, u64, C.c_int, C.POINTER(_MeshAttribute), C.c_uint32,
+                                    C.POINTER(_MeshAttribute), C.c_uint32, C.c_uint32]
+    L.ss_format_f32.argtypes = [C.c_float, C.c_char_p, u64]
     if L.ss_abi_version() != 2:
         raise ImportError("libsplashsurf_b200.so ABI version mismatch")
     return L
@@ -769,6 +781,68 @@ class MeshWithData:
     @property
     def ncells(self) -> int:
         return self.mesh.ncells
+
+    def write_to_file(self, path, *, file_format: Optional[str] = None) -> None:
+        """``pysplashsurf.MeshWithData.write_to_file``; the file is the one the reference CLI writes for this mesh (`write_mesh`)."""
+        write_mesh(path, self, file_format=file_format)
+
+
+_MESH_FORMATS = {None: 0, "vtk": 1, "vtk42": 1, "ply": 2, "obj": 3}
+
+
+def write_mesh(path, mesh, *, point_attributes: Optional[dict] = None, cell_attributes: Optional[dict] = None, file_format: Optional[str] = None,
+               threads: int = 0) -> None:
+    """``splashsurf::io::write_mesh`` (splashsurf/src/io.rs:276-316): writes a TriMesh3d, MixedTriQuadMesh3d, MeshWithData or a
+    ``(vertices, triangles)`` pair to ``.vtk`` (legacy binary), ``.ply`` (binary little endian) or ``.obj``, picked by the extension
+    unless ``file_format`` names one.  Native multi-threaded writer (ss_write_mesh_f32); the bytes are those of the reference CLI's file
+    for the same mesh and attributes (float32 scalars / 3-vectors and uint64 scalars; a point attribute called "normals" becomes the
+    vn lines of an OBJ and nx / ny / nz of a PLY)."""
+    if hasattr(mesh, "point_attributes"):
+        point_attributes = {**mesh.point_attributes, **(point_attributes or {})}
+        cell_attributes = {**mesh.cell_attributes, **(cell_attributes or {})}
+        mesh = mesh.mesh
+    if isinstance(mesh, tuple):
+        verts, tris, quads = mesh[0], mesh[1], (mesh[2] if len(mesh) > 2 else None)
+    elif isinstance(mesh, MixedTriQuadMesh3d):
+        verts, tris, quads = mesh.vertices, mesh.get_triangles(), mesh.get_quads()
+    else:
+        verts, tris, quads = mesh.vertices, mesh.triangles, None
+    if file_format not in _MESH_FORMATS:
+        raise ValueError(f"unsupported mesh file format {file_format!r}")
+    L = load_library()
+    v = np.ascontiguousarray(verts, dtype=np.float32).reshape(-1, 3)
+    t = np.asarray(tris)
+    idt = np.uint32 if t.dtype.itemsize == 4 and t.dtype.kind in "ui" else np.uint64
+    t = np.ascontiguousarray(t, dtype=idt).reshape(-1, 3)
+    q = np.ascontiguousarray(quads if quads is not None else np.zeros((0, 4)), dtype=idt).reshape(-1, 4)
+    if len(t) and int(t.max()) >= len(v) or len(q) and int(q.max()) >= len(v):
+        raise ValueError("cell refers to a vertex that does not exist")
+    keep = []
+
+    def table(attrs, n, what):
+        arr = (_MeshAttribute * max(1, len(attrs or {})))()
+        for i, (name, a) in enumerate((attrs or {}).items()):
+            a = np.asarray(a)
+            if a.dtype.kind in "ui" and a.ndim == 1:
+                a, kind = np.ascontiguousarray(a, dtype=np.uint64), 2
+            elif a.ndim == 1:
+                a, kind = np.ascontiguousarray(a, dtype=np.float32), 0
+            elif a.ndim == 2 and a.shape[1] == 3:
+                a, kind = np.ascontiguousarray(a, dtype=np.float32), 1
+            else:
+                raise ValueError(f"{what} attribute {name!r}: expected shape (n,) or (n, 3)")
+            if len(a) != n:
+                raise ValueError(f"{what} attribute {name!r} has {len(a)} entries for {n} {what}s")
+            keep.append(a)
+            nm = str(name).encode()
+            keep.append(nm)
+            arr[i] = _MeshAttribute(nm, kind, a.ctypes.data if len(a) else None)
+        return arr, len(attrs or {})
+    pa, npa = table(point_attributes, len(v), "point")
+    ca, nca = table(cell_attributes, len(t) + len(q), "cell")
+    _check(L, L.ss_write_mesh_f32(os.fspath(path).encode(), _MESH_FORMATS[file_format], v.ctypes.data if len(v) else None, len(v),
+                                  t.ctypes.data if len(t) else None, len(t), q.ctypes.data if len(q) else None, len(q), t.dtype.itemsize,
+                                  pa, npa, ca, nca, int(threads)))
 
 
 def reconstruction_pipeline(particles, *, attributes_to_interpolate=None, particle_radius: float, rest_density: float = 1000.0,

@@ -3,7 +3,8 @@
 A thin stand-in for `splashsurf reconstruct` (splashsurf/src/reconstruct.rs:36-380): the relative `-l` / `-c` values are multiplied
 by the particle radius like the reference CLI does (reconstruct.rs:628-629); the post-processing switches (`--mesh-cleanup`,
 `--decimate-barnacles`, `--mesh-smoothing-iters`, `--normals`, `--sph-normals`, `--generate-quads`, `--mesh-aabb-min/-max`,
-`--check-mesh`) go through `reconstruction_pipeline` with the reference's option names and defaults."""
+`--check-mesh`) go through `reconstruction_pipeline` with the reference's option names and defaults, and the output file (`.vtk`,
+`.ply`, `.obj` with the attributes the reference writes) comes from the library's writer, byte for byte the reference CLI's file."""
 import argparse
 import sys
 import time
@@ -28,13 +29,15 @@ def main(argv=None):
     # post-processing, names and defaults of the reference CLI (reconstruct.rs:150-300)
     r.add_argument("--normals", choices=["on", "off"], default="off")
     r.add_argument("--normals-smoothing-iters", type=int, default=None)
-    r.add_argument("--mesh-cleanup", choices=["on", "off"], default="off")
+    r.add_argument("--mesh-cleanup", choices=["on", "off"], default=None)        # on by default when smoothing runs (reconstruct.rs:200-213)
     r.add_argument("--mesh-cleanup-snap-dist", type=float, default=None)
     r.add_argument("--decimate-barnacles", choices=["on", "off"], default="off")
     r.add_argument("--keep-verts", choices=["on", "off"], default="off")
     r.add_argument("--mesh-smoothing-iters", type=int, default=None)
     r.add_argument("--mesh-smoothing-weights", choices=["on", "off"], default="off")
     r.add_argument("--mesh-smoothing-weights-normalization", type=float, default=13.0)
+    r.add_argument("--output-smoothing-weights", choices=["on", "off"], default="off")
+    r.add_argument("--output-raw-normals", choices=["on", "off"], default="off")
     r.add_argument("--generate-quads", choices=["on", "off"], default="off")
     r.add_argument("--quad-max-edge-diag-ratio", type=float, default=1.75)
     r.add_argument("--quad-max-normal-angle", type=float, default=10.0)
@@ -45,7 +48,7 @@ def main(argv=None):
     r.add_argument("--check-mesh", choices=["on", "off"], default="off")
     r.add_argument("-o", "--output-file", default=None)
     a = ap.parse_args(argv)
-    from . import io, reconstruct_surface, reconstruction_pipeline
+    from . import MeshWithData, io, reconstruct_surface, reconstruction_pipeline
     p = io.read_particles(a.input)
     t = time.perf_counter()
     on = lambda v: v == "on"         # noqa: E731
@@ -53,41 +56,38 @@ def main(argv=None):
     base = dict(particle_radius=a.particle_radius, rest_density=a.rest_density, smoothing_length=a.smoothing_length, cube_size=a.cube_size,
                 iso_surface_threshold=a.surface_threshold, simd=on(a.simd), subdomain_grid=on(a.subdomain_grid), subdomain_grid_auto_disable=False,
                 subdomain_num_cubes_per_dim=a.subdomain_cubes)
+    if a.mesh_cleanup is None:
+        a.mesh_cleanup = "on" if a.mesh_smoothing_iters not in (None, 0) else "off"
     post = any([on(a.normals), on(a.mesh_cleanup), on(a.decimate_barnacles), a.mesh_smoothing_iters is not None, on(a.generate_quads),
                 a.mesh_aabb_min is not None, on(a.check_mesh)])
-    quads = normals = None
     if post:
-        mwd, _ = reconstruction_pipeline(p, compute_normals=on(a.normals) or on(a.sph_normals), sph_normals=on(a.sph_normals),
+        # --sph-normals only selects how --normals are computed (reconstruct.rs:1094-1149)
+        out, _ = reconstruction_pipeline(p, compute_normals=on(a.normals), sph_normals=on(a.sph_normals),
                                          normals_smoothing_iters=a.normals_smoothing_iters, mesh_smoothing_iters=a.mesh_smoothing_iters,
                                          mesh_smoothing_weights=on(a.mesh_smoothing_weights),
-                                         mesh_smoothing_weights_normalization=a.mesh_smoothing_weights_normalization, mesh_cleanup=on(a.mesh_cleanup),
+                                         mesh_smoothing_weights_normalization=a.mesh_smoothing_weights_normalization,
+                                         output_mesh_smoothing_weights=on(a.output_smoothing_weights), output_raw_normals=on(a.output_raw_normals),
+                                         mesh_cleanup=on(a.mesh_cleanup),
                                          mesh_cleanup_snap_dist=a.mesh_cleanup_snap_dist, decimate_barnacles=on(a.decimate_barnacles),
                                          keep_vertices=on(a.keep_verts), generate_quads=on(a.generate_quads),
                                          quad_max_edge_diag_ratio=a.quad_max_edge_diag_ratio, quad_max_normal_angle=a.quad_max_normal_angle,
                                          quad_max_interior_angle=a.quad_max_interior_angle, mesh_aabb_min=a.mesh_aabb_min, mesh_aabb_max=a.mesh_aabb_max,
                                          mesh_aabb_clamp_vertices=on(a.mesh_aabb_clamp_verts), check_mesh_closed=on(a.check_mesh),
                                          check_mesh_manifold=on(a.check_mesh), check_mesh_orientation=on(a.check_mesh), **base)
-        verts, normals = mwd.mesh.vertices, mwd.point_attributes.get("normals")
-        if on(a.generate_quads):
-            tris, quads = mwd.mesh.get_triangles(), mwd.mesh.get_quads()
-        else:
-            tris = mwd.mesh.triangles
     else:
-        res = reconstruct_surface(p, sph_normals=on(a.sph_normals), **base)
-        verts, tris, normals = res.mesh.vertices, res.mesh.triangles, res.normals
+        out = MeshWithData(reconstruct_surface(p, **base).mesh, {}, {})
     dt = time.perf_counter() - t
-    print(f"{len(p)} particles -> {len(verts)} vertices, {len(tris)} triangles" + (f", {len(quads)} quads" if quads is not None else "") + f" in {dt:.3f} s",
+    quads = out.mesh.get_quads() if on(a.generate_quads) else None
+    tris = out.mesh.get_triangles() if on(a.generate_quads) else out.mesh.triangles
+    print(f"{len(p)} particles -> {out.nvertices} vertices, {len(tris)} triangles" + (f", {len(quads)} quads" if quads is not None else "") + f" in {dt:.3f} s",
           file=sys.stderr)
     if a.output_file:
-        if quads is not None and not a.output_file.endswith(".npz"):
-            raise SystemExit("mixed triangle / quad meshes are written as .npz only")
-        if a.output_file.endswith(".obj"):
-            io.write_obj(a.output_file, verts, tris, normals)
-        elif a.output_file.endswith(".vtk"):
-            io.write_vtk_mesh(a.output_file, verts, tris)
+        if a.output_file.endswith(".npz"):
+            np.savez(a.output_file, vertices=out.mesh.vertices, triangles=tris, **({"quads": quads} if quads is not None else {}), **out.point_attributes)
         else:
-            np.savez(a.output_file, vertices=verts, triangles=tris, **({"quads": quads} if quads is not None else {}),
-                     **({"normals": normals} if normals is not None else {}))
+            t = time.perf_counter()
+            io.write_mesh(a.output_file, out)              # .vtk / .ply / .obj as the reference CLI writes them (io.rs:276-316)
+            print(f"wrote {a.output_file} in {time.perf_counter() - t:.3f} s", file=sys.stderr)
     return 0
 
 

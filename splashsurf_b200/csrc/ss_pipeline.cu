@@ -1793,3 +1793,4 @@ extern "C" int ss_surface_timings(const ss_surface *s, ss_timings *o) { if (!s |
 
 #include "ss_post.cuh"
 #include "ss_meshproc.inc"
+#include "ss_meshio.inc"

@@ -510,3 +510,17 @@ def test_emulated_cli_with_postprocessing(emu, tmp_path):
     assert cli.main(base + ["--generate-quads", "on", "-o", str(tmp_path / "c.npz")]) == 0
     z = np.load(tmp_path / "c.npz")
     assert len(z["quads"]) > 0 and len(z["triangles"]) + 2 * len(z["quads"]) == len(t0)
+    # output files as the reference CLI writes them: attributes travel in .vtk / .ply, quads in every format; smoothing switches the
+    # clean-up on unless told otherwise (reconstruct.rs:200-213)
+    sm = ["--mesh-smoothing-iters=2", "--mesh-smoothing-weights=on", "--output-smoothing-weights=on", "--normals=on"]
+    assert cli.main(base + sm + ["-o", str(tmp_path / "d.vtk")]) == 0
+    assert cli.main(base + sm + ["-o", str(tmp_path / "d.ply")]) == 0
+    assert cli.main(base + sm + ["--mesh-cleanup=off", "-o", str(tmp_path / "e.ply")]) == 0
+    vd, td, qd, pa, ca = io.read_vtk_mesh(str(tmp_path / "d.vtk"))
+    vp, tp, qp, pp = io.read_ply_mesh(str(tmp_path / "d.ply"))
+    assert list(pa) == ["wnn", "sw", "normals"] == list(pp) and ca == {} and np.array_equal(vd, vp) and np.array_equal(td, tp)
+    assert all(np.array_equal(pa[k], pp[k]) for k in pa) and pa["normals"].shape == (len(vd), 3)
+    assert len(vd) < len(io.read_ply_mesh(str(tmp_path / "e.ply"))[0]) == len(v0)          # the clean-up ran by default
+    assert cli.main(base + ["--generate-quads=on", "--normals=on", "-o", str(tmp_path / "q.vtk")]) == 0
+    vq, tq, qq, paq, _ = io.read_vtk_mesh(str(tmp_path / "q.vtk"))
+    assert np.array_equal(tq, z["triangles"]) and np.array_equal(qq, z["quads"]) and list(paq) == ["normals"]
