@@ -3,7 +3,7 @@
 A thin stand-in for `splashsurf reconstruct` (splashsurf/src/reconstruct.rs:36-380): the relative `-l` / `-c` values are multiplied
 by the particle radius like the reference CLI does (reconstruct.rs:628-629); the post-processing switches (`--mesh-cleanup`,
 `--decimate-barnacles`, `--mesh-smoothing-iters`, `--normals`, `--sph-normals`, `--generate-quads`, `--mesh-aabb-min/-max`,
-`--check-mesh`) go through `reconstruction_pipeline` with the reference's option names and defaults, and the output file (`.vtk`,
+`--check-mesh`, `-a <attribute>` from a VTK particle file) go through `reconstruction_pipeline` with the reference's option names and defaults, and the output file (`.vtk`,
 `.ply`, `.obj` with the attributes the reference writes) comes from the library's writer, byte for byte the reference CLI's file."""
 import argparse
 import sys
@@ -26,6 +26,7 @@ def main(argv=None):
     r.add_argument("--subdomain-grid", choices=["on", "off"], default="on")
     r.add_argument("--simd", choices=["on", "off"], default="on")
     r.add_argument("--sph-normals", choices=["on", "off"], default="off")
+    r.add_argument("-a", "--interpolate_attribute", dest="interpolate_attributes", action="append", default=[], metavar="ATTRIBUTE_NAME")
     # post-processing, names and defaults of the reference CLI (reconstruct.rs:150-300)
     r.add_argument("--normals", choices=["on", "off"], default="off")
     r.add_argument("--normals-smoothing-iters", type=int, default=None)
@@ -58,11 +59,12 @@ def main(argv=None):
                 subdomain_num_cubes_per_dim=a.subdomain_cubes)
     if a.mesh_cleanup is None:
         a.mesh_cleanup = "on" if a.mesh_smoothing_iters not in (None, 0) else "off"
-    post = any([on(a.normals), on(a.mesh_cleanup), on(a.decimate_barnacles), a.mesh_smoothing_iters is not None, on(a.generate_quads),
+    attrs = io.read_particle_attributes(a.input, a.interpolate_attributes)
+    post = any([bool(attrs), on(a.normals), on(a.mesh_cleanup), on(a.decimate_barnacles), a.mesh_smoothing_iters is not None, on(a.generate_quads),
                 a.mesh_aabb_min is not None, on(a.check_mesh)])
     if post:
         # --sph-normals only selects how --normals are computed (reconstruct.rs:1094-1149)
-        out, _ = reconstruction_pipeline(p, compute_normals=on(a.normals), sph_normals=on(a.sph_normals),
+        out, _ = reconstruction_pipeline(p, attributes_to_interpolate=attrs, compute_normals=on(a.normals), sph_normals=on(a.sph_normals),
                                          normals_smoothing_iters=a.normals_smoothing_iters, mesh_smoothing_iters=a.mesh_smoothing_iters,
                                          mesh_smoothing_weights=on(a.mesh_smoothing_weights),
                                          mesh_smoothing_weights_normalization=a.mesh_smoothing_weights_normalization,

@@ -162,3 +162,84 @@ def read_vtk_mesh(path: str):
             attrs[name] = a.astype(a.dtype.newbyteorder("<")).reshape((n, comps) if comps > 1 else (n,))
         out.append(attrs)
     return verts, np.ascontiguousarray(tris), np.ascontiguousarray(quads), out[0], out[1]
+
+
+_VTK_TYPES = {b"float": ">f4", b"double": ">f8", b"int": ">i4", b"unsigned_int": ">u4", b"long": ">i8", b"unsigned_long": ">u8",
+              b"short": ">i2", b"unsigned_short": ">u2", b"char": ">i1", b"unsigned_char": ">u1"}
+
+
+def read_vtk_point_data(path: str) -> dict:
+    """POINT_DATA arrays of a legacy BINARY VTK file as written by SPlisHSPlasH and by the reference (SCALARS + lookup table, VECTORS / NORMALS,
+    FIELD arrays): name -> array of shape (n,) or (n, components) in the file's type."""
+    b = open(path, "rb").read()
+    if b.split(b"\n", 3)[2].strip().upper() != b"BINARY":
+        raise ValueError("only BINARY legacy VTK files are read")
+    k = b.find(b"POINT_DATA")
+    if k < 0:
+        return {}
+
+    def line(o):
+        while o < len(b) and b[o:o + 1] in b" \n\r\t":
+            o += 1
+        e = b.find(b"\n", o)
+        e = len(b) if e < 0 else e
+        return b[o:e].split(), e + 1
+
+    def array(o, typ, n):
+        if typ not in _VTK_TYPES:
+            raise ValueError(f"unsupported VTK data type {typ.decode()}")
+        a = np.frombuffer(b, _VTK_TYPES[typ], n, o)
+        return a.astype(a.dtype.newbyteorder("<")), o + a.nbytes
+    tok, o = line(k)
+    n = int(tok[1])
+    out = {}
+    while True:
+        tok, o2 = line(o)
+        if not tok or tok[0] in (b"CELL_DATA", b"POINT_DATA"):
+            break
+        kind = tok[0]
+        if kind == b"SCALARS":
+            comps = int(tok[3]) if len(tok) > 3 else 1
+            tok2, o3 = line(o2)
+            if tok2[:1] == [b"LOOKUP_TABLE"]:
+                o2 = o3
+            a, o = array(o2, tok[2], n * comps)
+            out[tok[1].decode()] = a.reshape(n, comps) if comps > 1 else a
+        elif kind in (b"VECTORS", b"NORMALS"):
+            a, o = array(o2, tok[2], 3 * n)
+            out[tok[1].decode()] = a.reshape(n, 3)
+        elif kind == b"FIELD":
+            o = o2
+            for _ in range(int(tok[2])):
+                t2, o = line(o)
+                comps, tuples = int(t2[1]), int(t2[2])
+                a, o = array(o, t2[3], comps * tuples)
+                out[t2[0].decode()] = a.reshape(tuples, comps) if comps > 1 else a
+        else:
+            raise ValueError(f"unsupported POINT_DATA entry {kind.decode()}")
+    return out
+
+
+def read_particle_attributes(path: str, names) -> dict:
+    """The `-a / --interpolate_attribute` inputs of the reference CLI (reconstruct.rs:196-198; vtk_format.rs:96-140, :318-346): named point
+    attributes of a VTK particle file as float32 -- scalars stored as u32 / f32 / f64, 3-vectors stored as f32 / f64; anything else is an
+    error, like in the reference."""
+    if not names:
+        return {}
+    if not path.endswith(".vtk"):
+        raise ValueError("attributes are read from legacy .vtk particle files only")
+    data = read_vtk_point_data(path)
+    out = {}
+    for name in names:
+        if name not in data:
+            raise ValueError(f"Attribute {name} not found in VTK file")
+        a = data[name]
+        if a.ndim == 1 and (a.dtype.kind == "f" or a.dtype == np.uint32):
+            out[name] = np.ascontiguousarray(a, dtype=np.float32)
+        elif a.ndim == 2 and a.shape[1] == 3 and a.dtype.kind == "f":
+            out[name] = np.ascontiguousarray(a, dtype=np.float32)
+        elif a.ndim == 1 or a.shape[1] == 3:
+            raise ValueError(f'Attribute "{name}": unsupported VTK data type for {"scalars" if a.ndim == 1 else "vectors"}')
+        else:
+            raise ValueError(f'Attribute "{name}": unsupported number of components ({a.shape[1]}) in VTK IO buffer')
+    return out

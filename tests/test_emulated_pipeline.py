@@ -524,3 +524,34 @@ def test_emulated_cli_with_postprocessing(emu, tmp_path):
     assert cli.main(base + ["--generate-quads=on", "--normals=on", "-o", str(tmp_path / "q.vtk")]) == 0
     vq, tq, qq, paq, _ = io.read_vtk_mesh(str(tmp_path / "q.vtk"))
     assert np.array_equal(tq, z["triangles"]) and np.array_equal(qq, z["quads"]) and list(paq) == ["normals"]
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/data/bunny_frame_14_7705_particles.vtk"), reason="reference tree only exists in the build container")
+def test_emulated_cli_end_to_end_against_reference_cli_with_attributes(emu, oracle_mod, tmp_path):
+    """The whole harness path on a reference fixture (SPlisHSPlasH VTK with `id` and `velocity` point data): particle + attribute readers,
+    clean-up (on by default with smoothing), weighted smoothing, normals, SPH interpolation of both attributes (`-a`), PLY writer -- beside
+    the REFERENCE CLI with the same command line.  Same file size, same attribute order; vertices matched by position (the reference's
+    vertex order is not fixed), triangle sets equal, values within the f32 summation-order tolerance of DESIGN 3a."""
+    if not oracle_mod.reference_available():
+        pytest.skip("oracle/_ref not unpacked")
+    import subprocess, sys
+    from scipy.spatial import cKDTree
+    from splashsurf_b200 import io, __main__ as cli
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = "import sys; sys.path.insert(0, %r); import oracle; oracle.reference().run_splashsurf(['splashsurf'] + sys.argv[1:])" % root
+    args = ["reconstruct", "/root/reference/data/bunny_frame_14_7705_particles.vtk", "-r=0.025", "-l=2.0", "-c=0.5", "-a", "velocity", "-a", "id",
+            "--normals=on", "--mesh-smoothing-iters=2", "--mesh-smoothing-weights=on", "--output-smoothing-weights=on"]
+    ref, ours = str(tmp_path / "ref.ply"), str(tmp_path / "ours.ply")
+    subprocess.check_call([sys.executable, "-c", code, *args, "-o", ref, "-q"])
+    assert cli.main(args + ["-o", ours]) == 0
+    assert os.path.getsize(ref) == os.path.getsize(ours)
+    v1, t1, _, a1 = io.read_ply_mesh(ref)
+    v2, t2, _, a2 = io.read_ply_mesh(ours)
+    assert list(a1) == list(a2) == ["wnn", "sw", "normals", "velocity", "id"] and len(v1) == len(v2) > 40000 and len(t1) == len(t2)
+    d, idx = cKDTree(v2).query(v1)
+    assert d.max() < 2e-6 and len(np.unique(idx)) == len(v1)
+    assert set(map(tuple, np.sort(idx[t1], axis=1))) == set(map(tuple, np.sort(t2.astype(np.int64), axis=1)))
+    for k in a1:
+        assert np.abs(a1[k] - a2[k][idx]).max() <= 5e-6 * max(1.0, float(np.abs(a1[k]).max())) + 2e-5, k
+    with pytest.raises(ValueError, match="Attribute pressure not found in VTK file"):
+        cli.main(args[:5] + ["-a", "pressure"])

@@ -194,3 +194,42 @@ def test_obj_numbers_against_the_reference_writer_on_arbitrary_values(ss, oracle
     subprocess.check_call([sys.executable, "-c", code, "convert", "--mesh", str(tmp_path / "in.ply"), "-o", str(tmp_path / "ref.obj"), "--overwrite", "-q"])
     ss.write_mesh(str(tmp_path / "our.obj"), (v, tri), threads=3)
     assert open(tmp_path / "our.obj", "rb").read() == open(tmp_path / "ref.obj", "rb").read()
+
+
+def test_vtk_point_data_reader(ss, tmp_path):
+    """POINT_DATA of legacy binary VTK files: SCALARS (+ lookup table), VECTORS and FIELD arrays as SPlisHSPlasH writes them; the attribute
+    loader converts like vtk_format.rs:318-346 (u32 / f32 / f64 scalars, f32 / f64 vectors -> f32) and refuses the rest."""
+    from splashsurf_b200 import io
+    n = 5
+    pts = np.arange(3 * n, dtype=">f4")
+    ids = (np.arange(n) + 7).astype(">u4")
+    vel = (np.arange(3 * n) * 0.5).astype(">f4")
+    dens = np.linspace(1, 2, n).astype(">f8")
+    tens = np.zeros(9 * n, ">f4")
+    path = str(tmp_path / "p.vtk")
+    with open(path, "wb") as f:
+        f.write(b"# vtk DataFile Version 4.1\nSPlisHSPlasH particle data\nBINARY\nDATASET UNSTRUCTURED_GRID\n")
+        f.write(b"POINTS %d float\n" % n + pts.tobytes() + b"\n")
+        f.write(b"CELLS %d %d\n" % (n, 2 * n) + np.stack([np.ones(n), np.arange(n)], 1).astype(">i4").tobytes() + b"\n")
+        f.write(b"CELL_TYPES %d\n" % n + np.ones(n, ">i4").tobytes() + b"\n")
+        f.write(b"POINT_DATA %d\n" % n)
+        f.write(b"SCALARS id unsigned_int 1\nLOOKUP_TABLE id_table\n" + ids.tobytes() + b"\n")
+        f.write(b"VECTORS force float\n" + vel.tobytes() + b"\n")
+        f.write(b"FIELD FieldData 3\nvelocity 3 %d float\n" % n + vel.tobytes() + b"\ndensity 1 %d double\n" % n + dens.tobytes() +
+                b"\nstress 9 %d float\n" % n + tens.tobytes() + b"\n")
+    assert np.array_equal(io.read_particles(path), pts.astype("<f4").reshape(n, 3))
+    d = io.read_vtk_point_data(path)
+    assert list(d) == ["id", "force", "velocity", "density", "stress"] and d["id"].dtype == np.uint32 and d["density"].dtype == np.float64
+    assert np.array_equal(d["id"], ids) and np.array_equal(d["velocity"], vel.reshape(n, 3)) and d["stress"].shape == (n, 9)
+    a = io.read_particle_attributes(path, ["velocity", "id", "density"])
+    assert all(v.dtype == np.float32 for v in a.values()) and a["velocity"].shape == (n, 3) and np.array_equal(a["id"], ids.astype(np.float32))
+    with pytest.raises(ValueError, match="Attribute pressure not found in VTK file"):
+        io.read_particle_attributes(path, ["pressure"])
+    with pytest.raises(ValueError, match="unsupported number of components"):
+        io.read_particle_attributes(path, ["stress"])
+    assert io.read_particle_attributes(path, []) == {}
+    # files of this package's own writer carry their attributes as SCALARS
+    ss.write_mesh(str(tmp_path / "m.vtk"), (pts.astype("<f4").reshape(n, 3), np.array([[0, 1, 2]], np.uint32)),
+                  point_attributes={"w": np.ones(n, np.float32), "nrm": np.ones((n, 3), np.float32)})
+    d = io.read_vtk_point_data(str(tmp_path / "m.vtk"))
+    assert d["w"].shape == (n,) and d["nrm"].shape == (n, 3)
