@@ -347,6 +347,9 @@ typedef struct ss_mesh_attribute {
 int ss_write_mesh_f32(const char *path, int format, const float *verts, uint64_t nv, const void *tris, uint64_t nt, const void *quads,
                       uint64_t nq, int index_bytes, const ss_mesh_attribute *point_attrs, uint32_t n_point_attrs,
                       const ss_mesh_attribute *cell_attrs, uint32_t n_cell_attrs, uint32_t threads);
+/* Test knob: items (vertices / cells / values) per work chunk of the writer's thread pipeline, process-wide; 0 restores the built-in sizes
+ * (32 Ki lines of an OBJ, 64 Ki PLY records, 256 Ki - 1 Mi VTK values).  The file written does not depend on it. */
+int ss_meshio_set_chunk_items(uint64_t items);
 /* One f32 as the OBJ writer prints it (Rust `{}`), NUL-terminated; 64 bytes always suffice. */
 int ss_format_f32(float value, char *out, uint64_t capacity);
 

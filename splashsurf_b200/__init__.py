@@ -164,6 +164,7 @@ def _bind(L):
     L.ss_write_mesh_f32.argtypes = [C.c_char_p, C.c_int, vp, u64, vp, u64, vp, u64, C.c_int, C.POINTER(_MeshAttribute), C.c_uint32,
                                     C.POINTER(_MeshAttribute), C.c_uint32, C.c_uint32]
     L.ss_format_f32.argtypes = [C.c_float, C.c_char_p, u64]
+    L.ss_meshio_set_chunk_items.argtypes = [u64]
     if L.ss_abi_version() != 2:
         raise ImportError("libsplashsurf_b200.so ABI version mismatch")
     return L

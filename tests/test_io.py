@@ -60,6 +60,14 @@ def test_mesh_writers_reproduce_reference_files(ss, tmp_path, case):
     for threads in (1, 3, 0):
         v, t, q, attrs = _rewrite_and_compare(ss, stem + ".ply", stem, tmp_path, threads)
     assert ("wnn" in attrs and "sw" in attrs) if case == "attr" else len(q) > 0
+    # tiny chunks: hundreds of hand-overs between the formatting threads and the writing thread in every section of every format
+    L = ss.load_library()
+    try:
+        for items, threads in ((7, 5), (1, 2), (64, 16)):
+            assert L.ss_meshio_set_chunk_items(items) == 0
+            _rewrite_and_compare(ss, stem + ".ply", stem, tmp_path, threads)
+    finally:
+        L.ss_meshio_set_chunk_items(0)
     # u32 and u64 indices, tuple input and the per-format helpers write the same bytes
     from splashsurf_b200 import io
     if case == "attr":
