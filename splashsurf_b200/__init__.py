@@ -13,7 +13,8 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from dataclasses import dataclass
+from dataclasses import dataclass, field
+from enum import Enum
 from typing import Optional, Sequence
 
 import numpy as np
@@ -178,9 +179,26 @@ def _check(L, rc: int):
 # ---------------------------------------------------------------------------- result types ----
 @dataclass
 class Aabb3d:
-    """Mirrors pysplashsurf.Aabb3d (min / max corners)."""
+    """Mirrors pysplashsurf.Aabb3d (min / max corners; aabb.rs)."""
     min: np.ndarray
     max: np.ndarray
+
+    @staticmethod
+    def from_min_max(min, max) -> "Aabb3d":                # noqa: A002 - the reference's argument names
+        return Aabb3d(np.asarray(min, dtype=np.float64).reshape(3).copy(), np.asarray(max, dtype=np.float64).reshape(3).copy())
+
+    @staticmethod
+    def from_points(points) -> "Aabb3d":
+        """Smallest AABB around the points (aabb.rs `from_points`); zero-sized at the origin for an empty set."""
+        pts = np.asarray(points).reshape(-1, 3)
+        if len(pts) == 0:
+            return Aabb3d(np.zeros(3), np.zeros(3))
+        return Aabb3d(pts.min(axis=0).astype(np.float64), pts.max(axis=0).astype(np.float64))
+
+    def contains_point(self, point) -> bool:
+        """Half-open towards the max corner, like the reference."""
+        q = np.asarray(point, dtype=np.float64).reshape(3)
+        return bool(np.all(q >= np.asarray(self.min, np.float64)) and np.all(q < np.asarray(self.max, np.float64)))
 
 
 @dataclass
@@ -211,8 +229,16 @@ class TriMesh3d:
     def ncells(self) -> int:
         return len(self.triangles)
 
+    @property
+    def dtype(self):
+        return np.dtype(np.float32)
+
     def copy(self) -> "TriMesh3d":
         return TriMesh3d(self.vertices.copy(), self.triangles.copy())
+
+    def write_to_file(self, path, *, file_format: Optional[str] = None) -> None:
+        """``pysplashsurf.TriMesh3d.write_to_file``; the file is the reference CLI's (`write_mesh`), by extension or `file_format`."""
+        write_mesh(path, self, file_format=file_format)
 
     def vertex_normals_parallel(self, context=None) -> np.ndarray:
         """Area-weighted vertex normals on the device (TriMesh3d::par_vertex_normals, mesh.rs:799-906)."""
@@ -302,6 +328,16 @@ class MixedTriQuadMesh3d:
 
     def get_quads(self) -> np.ndarray:
         return self._quads
+
+    @property
+    def dtype(self):
+        return np.dtype(np.float32)
+
+    def copy(self) -> "MixedTriQuadMesh3d":
+        return MixedTriQuadMesh3d(self.vertices.copy(), self._triangles.copy(), self._quads.copy())
+
+    def write_to_file(self, path, *, file_format: Optional[str] = None) -> None:
+        write_mesh(path, self, file_format=file_format)
 
     @property
     def nvertices(self) -> int:
@@ -768,12 +804,22 @@ def density_grid_loop(subdomain_particles, subdomain_particle_densities, *, glob
     return out
 
 
+class MeshType(Enum):
+    """pysplashsurf.MeshType: the kind of mesh a MeshWithData wraps."""
+    Tri3d = 0
+    MixedTriQuad3d = 1
+
+
 @dataclass
 class MeshWithData:
     """Mirrors pysplashsurf.MeshWithData for the attributes this package can produce."""
     mesh: TriMesh3d
-    point_attributes: dict
-    cell_attributes: dict
+    point_attributes: dict = field(default_factory=dict)
+    cell_attributes: dict = field(default_factory=dict)
+
+    def __post_init__(self):
+        if not isinstance(self.mesh, (TriMesh3d, MixedTriQuadMesh3d)):
+            raise TypeError("unsupported mesh type, expected TriMesh3d or MixedTriQuadMesh3d")
 
     @property
     def nvertices(self) -> int:
@@ -782,6 +828,39 @@ class MeshWithData:
     @property
     def ncells(self) -> int:
         return self.mesh.ncells
+
+    @property
+    def dtype(self):
+        return np.dtype(np.float32)
+
+    @property
+    def mesh_type(self) -> "MeshType":
+        return MeshType.MixedTriQuad3d if isinstance(self.mesh, MixedTriQuadMesh3d) else MeshType.Tri3d
+
+    def copy_mesh(self):
+        return self.mesh.copy()
+
+    def copy(self) -> "MeshWithData":
+        return MeshWithData(self.mesh.copy(), {k: np.array(v) for k, v in self.point_attributes.items()},
+                            {k: np.array(v) for k, v in self.cell_attributes.items()})
+
+    @staticmethod
+    def _attribute(attribute, n: int, what: str) -> np.ndarray:
+        """pysplashsurf/src/mesh.rs add_*_attribute: uint64 (N,), float32 (N,) or float32 (N, 3); the data is copied."""
+        a = np.asarray(attribute)
+        if a.dtype not in (np.dtype(np.uint64), np.dtype(np.float32)):
+            raise TypeError("unsupported attribute data type")
+        if not (a.ndim == 1 or (a.ndim == 2 and a.shape[1] in (1, 3))) or (a.ndim == 2 and a.dtype != np.float32):
+            raise ValueError("expected Nx1 or Nx3 array for Vector3Real attribute data")
+        if len(a) != n:
+            raise ValueError(f"number of attribute values must match number of {what} in the mesh")
+        return np.ascontiguousarray(a.reshape(-1) if a.ndim == 2 and a.shape[1] == 1 else a).copy()
+
+    def add_point_attribute(self, name: str, attribute) -> None:
+        self.point_attributes[str(name)] = self._attribute(attribute, self.nvertices, "vertices")
+
+    def add_cell_attribute(self, name: str, attribute) -> None:
+        self.cell_attributes[str(name)] = self._attribute(attribute, self.ncells, "cells")
 
     def write_to_file(self, path, *, file_format: Optional[str] = None) -> None:
         """``pysplashsurf.MeshWithData.write_to_file``; the file is the one the reference CLI writes for this mesh (`write_mesh`)."""

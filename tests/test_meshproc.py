@@ -212,3 +212,54 @@ def test_half_edge_connectivity_kat(ss):
     m = ss.TriMesh3d(v, t)
     conn = ss.barnacle_decimation(m, keep_vertices=True).copy_connectivity()        # no barnacles: the mesh comes back unchanged
     assert np.array_equal(m.triangles, t) and [sorted(c) for c in conn] == [[1, 2], [0, 2, 3], [0, 1, 3], [1, 2]]
+
+
+def test_mesh_containers_mirror_the_reference_bindings(ss, oracle_mod, tmp_path):
+    """pysplashsurf's mesh containers (pysplashsurf/src/mesh.rs, aabb.rs): MeshWithData(mesh), add_*_attribute with its type / shape / length
+    checks, copy / copy_mesh / mesh_type / dtype, Aabb3d helpers -- same results as the wheel where it is unpacked."""
+    v = np.random.default_rng(0).normal(size=(6, 3)).astype(np.float32)
+    t = np.array([[0, 1, 2], [3, 4, 5]], np.uint64)
+    m = ss.MeshWithData(ss.TriMesh3d(v, t))
+    assert m.dtype == np.float32 and m.mesh.dtype == np.float32 and m.mesh_type == ss.MeshType.Tri3d and m.point_attributes == {} == m.cell_attributes
+    m.add_point_attribute("w", np.zeros(6, np.float32))
+    m.add_point_attribute("v", np.zeros((6, 3), np.float32))
+    m.add_point_attribute("i", np.arange(6, dtype=np.uint64))
+    m.add_point_attribute("w", np.ones(6, np.float32))                     # replaces, keeps its place
+    m.add_cell_attribute("c", np.zeros(2, np.float32))
+    assert list(m.point_attributes) == ["w", "v", "i"] and m.point_attributes["w"].max() == 1.0 and list(m.cell_attributes) == ["c"]
+    with pytest.raises(TypeError, match="unsupported attribute data type"):
+        m.add_point_attribute("d", np.zeros(6, np.float64))
+    with pytest.raises(TypeError, match="unsupported attribute data type"):
+        m.add_point_attribute("d", np.zeros(6, np.int32))
+    with pytest.raises(ValueError, match="expected Nx1 or Nx3 array"):
+        m.add_point_attribute("d", np.zeros((6, 2), np.float32))
+    with pytest.raises(ValueError, match="must match number of vertices"):
+        m.add_point_attribute("d", np.zeros(3, np.float32))
+    with pytest.raises(ValueError, match="must match number of cells"):
+        m.add_cell_attribute("d", np.zeros(3, np.float32))
+    with pytest.raises(TypeError, match="unsupported mesh type"):
+        ss.MeshWithData(m)
+    c = m.copy()
+    c.point_attributes["w"][:] = 5
+    c.mesh.vertices[:] = 0
+    assert m.point_attributes["w"].max() == 1.0 and np.array_equal(m.mesh.vertices, v) and type(m.copy_mesh()) is ss.TriMesh3d
+    q = ss.MeshWithData(ss.MixedTriQuadMesh3d(v, t[:1], np.array([[0, 1, 2, 3]], np.uint64)))
+    assert q.mesh_type == ss.MeshType.MixedTriQuad3d and q.ncells == 2 and type(q.copy_mesh()) is ss.MixedTriQuadMesh3d
+    m.mesh.write_to_file(str(tmp_path / "t.obj"))
+    m.write_to_file(str(tmp_path / "m.ply"))
+    q.mesh.write_to_file(str(tmp_path / "q.vtk"))
+    from splashsurf_b200 import io
+    assert len(io.read_obj(str(tmp_path / "t.obj"))[0]) == 6 and list(io.read_ply_mesh(str(tmp_path / "m.ply"))[3]) == ["w", "v", "i"]
+    assert len(io.read_vtk_mesh(str(tmp_path / "q.vtk"))[2]) == 1
+    a = ss.Aabb3d.from_min_max([0, 0, 0], [1, 2, 3])
+    b = ss.Aabb3d.from_points(np.array([[0, 1, 2], [3, -1, 5]], np.float32))
+    assert a.min.dtype == np.float64 and not a.contains_point([1, 1, 1]) and a.contains_point([0, 0, 0]) and not a.contains_point([0.5, 2, 1])
+    assert np.array_equal(b.min, [0, -1, 2]) and np.array_equal(b.max, [3, 1, 5])
+    if oracle_mod.reference_available():
+        ps = oracle_mod.reference()
+        ra = ps.Aabb3d.from_min_max([0, 0, 0], [1, 2, 3])
+        rb = ps.Aabb3d.from_points(np.array([[0, 1, 2], [3, -1, 5]], np.float32))
+        assert np.array_equal(ra.min, a.min) and np.array_equal(rb.max, b.max) and ra.min.dtype == a.min.dtype
+        for pt in ([1, 1, 1], [0, 0, 0], [0.5, 2, 1], [0.999, 1.999, 2.999], [-1e-9, 0, 0]):
+            assert ra.contains_point(pt) == a.contains_point(pt)
+        assert str(ps.MeshType.Tri3d) == str(ss.MeshType.Tri3d) and str(ps.MeshType.MixedTriQuad3d) == str(ss.MeshType.MixedTriQuad3d)
