@@ -54,3 +54,33 @@ def test_bench_two_ranks_on_executor(oracle_mod, protocol):
     assert r.returncode == 0, r.stderr[-3000:]
     d = _check_line(r.stdout, 2, 2)
     assert d["config"]["parallelism"].endswith("x2") and d["mesh"]["vertices"] > 0
+
+
+def test_bench_reference_arm_contract(oracle_mod):
+    """`bench.py --impl reference` (the reference wheel on the host cores): one JSON line with the arm's own metric / config keys, the
+    `cpu_baseline` describing this run and an `e2e` that repeats the line's value with no host<->device traffic."""
+    if not oracle_mod.reference_available():
+        pytest.skip("oracle/_ref not unpacked")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--particles", "20000", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"]
+    assert d["unit"] == "Mparticles/s" and d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 2 and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["bounded_sample"] is False and "workload" in d["config"]
+
+
+def test_bench_reference_arm_under_torchrun_prints_once(oracle_mod):
+    """Launched like the scaling run (N ranks): rank 0 alone runs the reference and prints; the other ranks exit 0 without work."""
+    if not oracle_mod.reference_available():
+        pytest.skip("oracle/_ref not unpacked")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(free_port()),
+           os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--particles", "20000", "--steps", "1", "--warmup", "0"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip().startswith("{")]
+    assert len(lines) == 1 and json.loads(lines[0])["impl"] == "reference" and json.loads(lines[0])["n_gpus"] == 2
