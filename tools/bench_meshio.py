@@ -20,7 +20,6 @@ def main():
     ap.add_argument("--repeat", type=int, default=5)
     ap.add_argument("--json", default=None)
     a = ap.parse_args()
-    import numpy as np
     import splashsurf_b200 as ss
     from splashsurf_b200 import io, synthetic as syn
     code = "import sys; sys.path.insert(0, %r); import oracle; oracle.reference().run_splashsurf(['splashsurf'] + sys.argv[1:])" % ROOT

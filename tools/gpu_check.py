@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Verbose GPU-vs-oracle parity run (debugging aid; the pytest -m gpu suite is the real gate)."""
-import os, sys, time, json
+import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

@@ -1,4 +1,4 @@
-import sys, numpy as np, torch
+import sys, torch
 sys.path.insert(0,'/root/repo')
 import splashsurf_b200 as ss
 from splashsurf_b200 import synthetic as syn, distributed as ssd
