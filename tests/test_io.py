@@ -202,6 +202,17 @@ def test_obj_numbers_against_the_reference_writer_on_arbitrary_values(ss, oracle
     subprocess.check_call([sys.executable, "-c", code, "convert", "--mesh", str(tmp_path / "in.ply"), "-o", str(tmp_path / "ref.obj"), "--overwrite", "-q"])
     ss.write_mesh(str(tmp_path / "our.obj"), (v, tri), threads=3)
     assert open(tmp_path / "our.obj", "rb").read() == open(tmp_path / "ref.obj", "rb").read()
+    # interoperability: the reference's own readers take this package's .ply and .vtk files, and what it writes back is what we write
+    rng = np.random.default_rng(4)
+    mv = rng.normal(size=(200, 3)).astype(np.float32)
+    mt = rng.integers(0, 200, size=(300, 3)).astype(np.uint32)
+    ss.write_mesh(str(tmp_path / "m.vtk"), (mv, mt), point_attributes={"w": rng.random(200).astype(np.float32)})
+    ss.write_mesh(str(tmp_path / "m.ply"), (mv, mt))
+    for src, ext in (("m.vtk", "vtk"), ("m.vtk", "obj"), ("m.ply", "vtk")):
+        out = str(tmp_path / f"conv_{src[2:]}.{ext}")
+        subprocess.check_call([sys.executable, "-c", code, "convert", "--mesh", str(tmp_path / src), "-o", out, "--overwrite", "-q"])
+        ss.write_mesh(str(tmp_path / f"mine.{ext}"), (mv, mt))                # (convert drops attributes)
+        assert open(out, "rb").read() == open(tmp_path / f"mine.{ext}", "rb").read(), (src, ext)
 
 
 def test_vtk_point_data_reader(ss, tmp_path):
