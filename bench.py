@@ -302,6 +302,17 @@ def main():
         sampler.start()
     for _ in range(args.warmup):
         res = runner.step(dev_in, copy_out=False)
+    # The multi-GPU runner tunes its slab cuts from the measured per-rank times of the first frames and then keeps the best plan
+    # (a simulation feeds it thousands of frames).  A short warm-up can end before that: run untimed settling steps until the plan
+    # stands still, plus one for the buffers of the final cuts -- the timed region then measures the steady state.  Counted and
+    # reported (`config.plan_settling_steps`); the same number on every rank, the decision comes from all-reduced times.
+    settling = 0
+    while world > 1 and not runner.plan_settled and settling < 8:
+        res = runner.step(dev_in, copy_out=False)
+        settling += 1
+    if settling:
+        res = runner.step(dev_in, copy_out=False)
+        settling += 1
     barrier()
     sampler.mark()
     dev_ms, ls_ms, launches, pairs, ls_launches = 0.0, 0.0, 0, 0.0, 0
@@ -440,7 +451,7 @@ def main():
                 "dtype": "f32", "data": "synthetic",
                 "config": dict(workload_config(args, desc, n_total, kw, f"subdomain slabs x{world}" if world > 1 else "single GPU"),
                                levelset_variant=int(args.levelset_variant), density_variant=int(args.density_variant), mc_variant=int(args.mc_variant),
-                               sph_normals=bool(args.sph_normals),
+                               sph_normals=bool(args.sph_normals), plan_settling_steps=int(settling),
                                l2="inputs (600 MB) and tiles (GBs) exceed the 126 MB L2; no flush needed"),
                 "mesh": {"vertices": int(nv_g if nv_g is not None else nv), "triangles": int(nt_g if nt_g is not None else nt), "subdomains": int(n_sub)},
                 "wall_ms_per_step": wall_ms_max / args.steps, "step_ms_rank0": step_ms, "stage_ms_last_step": stage, "bricks_last_step_rank0": bricks, "runner_phase_ms_last_step_rank0": res.get("phase_ms"),

@@ -239,6 +239,12 @@ class Runner:
         self.device = torch.device("cuda", local_rank) if device is None else torch.device(device)
         self.last_plan: Optional[SlabPlan] = None
 
+    @property
+    def plan_settled(self) -> bool:
+        """True once the slab cuts no longer move from frame to frame (single rank, feedback off, or the exploration frames are over).
+        The same on every rank: the decision is taken from all-reduced step times."""
+        return self.world == 1 or not self.balance_feedback or self._frozen_cuts is not None
+
     # -- input sharding used by the bench: rank r holds a contiguous range of global particle indices
     def take_local(self, particles: np.ndarray) -> np.ndarray:
         if self.world == 1:

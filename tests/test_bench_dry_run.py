@@ -37,6 +37,7 @@ def test_bench_single_rank_on_executor(oracle_mod, extra):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, SS_EMUL_THREADS="4"))
     assert r.returncode == 0, r.stderr[-3000:]
     d = _check_line(r.stdout, 1, 2)
+    assert d["config"]["plan_settling_steps"] == 0                      # a single GPU has no plan to settle
     if "--no-cpu-baseline" not in extra:
         assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
     want = int(extra[extra.index("--levelset-variant") + 1]) if "--levelset-variant" in extra else 2
@@ -54,6 +55,9 @@ def test_bench_two_ranks_on_executor(oracle_mod, protocol):
     assert r.returncode == 0, r.stderr[-3000:]
     d = _check_line(r.stdout, 2, 2)
     assert d["config"]["parallelism"].endswith("x2") and d["mesh"]["vertices"] > 0
+    # warm-up 1 < the runner's exploration frames: the bench ran untimed settling steps (the same number on both ranks, or the
+    # collectives inside a step would have dead-locked) and says so
+    assert 1 <= d["config"]["plan_settling_steps"] <= 9
 
 
 def test_bench_reference_arm_contract(oracle_mod):
