@@ -265,6 +265,19 @@ def _virtual_ranks(emu, oracle_mod, x, kw, world, use_callback, force_cuts=None)
         local_max.append(L.ss_surface_max_subdomain_particles(s))
         ctx.free_surface(s)
     gmax = max(local_max)
+    # the "stats" protocol gets the same number without any decomposition pre-pass: exact ghost-classifier membership counts of the
+    # rank-local particles, summed over the ranks (ss_partition_members_f32; here over contiguous index ranges like Runner.take_local)
+    nsd = [(nc + S - 1) // S for nc in ncells]
+    members = np.zeros(nsd[0] * nsd[1] * nsd[2], np.int64)
+    hist_sum = np.zeros(nsd[ax], np.int64)
+    for part in np.array_split(np.arange(len(x)), world):
+        xs = np.ascontiguousarray(x[part])
+        hist_r, mem_r = np.zeros(nsd[ax], np.uint32), np.zeros(len(members), np.uint32)
+        assert L.ss_partition_members_f32(ctx._h, xs.ctypes.data if len(xs) else None, len(xs), C.byref(p), C.byref(grid), ax,
+                                          hist_r.ctypes.data, mem_r.ctypes.data) == 0, L.ss_last_error()
+        members += mem_r; hist_sum += hist_r
+    assert int(members.max()) == gmax, (int(members.max()), gmax)
+    assert np.array_equal(hist_sum, hist)
     calls = []
     CB = C.CFUNCTYPE(C.c_uint64, C.c_uint64, C.c_void_p)
 
