@@ -1,15 +1,58 @@
 """`python -m splashsurf_b200 reconstruct <particles> -r <radius> -l <smoothing length> -c <cube size> [-o out.obj]`
 
+and `python -m splashsurf_b200 convert (--particles <file> | --mesh <file>) -o <file> [--overwrite] [--domain-min x y z --domain-max x y z]`
+(splashsurf/src/convert.rs).
+
 A thin stand-in for `splashsurf reconstruct` (splashsurf/src/reconstruct.rs:36-380): the relative `-l` / `-c` values are multiplied
 by the particle radius like the reference CLI does (reconstruct.rs:628-629); the post-processing switches (`--mesh-cleanup`,
 `--decimate-barnacles`, `--mesh-smoothing-iters`, `--normals`, `--sph-normals`, `--generate-quads`, `--mesh-aabb-min/-max`,
-`--check-mesh`, `-a <attribute>` from a VTK particle file) go through `reconstruction_pipeline` with the reference's option names and defaults, and the output file (`.vtk`,
+`--check-mesh`, `-a <attribute>` from a VTK / VTU / BGEO particle file) go through `reconstruction_pipeline` with the reference's option names and defaults, and the output file (`.vtk`,
 `.ply`, `.obj` with the attributes the reference writes) comes from the library's writer, byte for byte the reference CLI's file."""
 import argparse
 import sys
 import time
 
 import numpy as np
+
+
+def convert(a) -> int:
+    """`convert_subcommand` (splashsurf/src/convert.rs:58-152): particles .vtk / .vtu / .bgeo / .ply / .xyz / .json -> .vtk / .bgeo / .json
+    (optionally filtered by a half-open domain box, aabb.rs:220-222), or a triangle mesh .vtk / .ply -> .obj / .vtk / .ply."""
+    import os
+    from . import io, particle_formats as pf
+    if (a.input_particles is None) == (a.input_mesh is None):
+        print("Aborting: " + ("No input file specified, either a particle or mesh input file has to be specified." if a.input_particles is None
+                              else "the argument '--particles' cannot be used with '--mesh'"), file=sys.stderr)
+        return 1
+    if (a.domain_min is None) != (a.domain_max is None):
+        print("Aborting: --domain-min and --domain-max have to be specified together", file=sys.stderr)
+        return 1
+    if not a.overwrite and os.path.exists(a.output_file):
+        print(f'Aborting: Output file "{a.output_file}" already exists. Use overwrite flag to ignore this.', file=sys.stderr)
+        return 1
+    try:
+        if a.input_particles is not None:
+            p = pf.particles_from_file(a.input_particles)
+            if a.domain_min is not None:
+                lo, hi = np.asarray(a.domain_min, np.float64).astype(np.float32), np.asarray(a.domain_max, np.float64).astype(np.float32)
+                p = p[np.all(p >= lo, axis=1) & np.all(p < hi, axis=1)]
+            pf.write_particle_positions(a.output_file, p)
+        else:
+            ext = os.path.splitext(a.input_mesh)[1].lower()
+            if ext == ".vtk":
+                v, t = pf.read_vtk_surface_mesh(a.input_mesh)
+                attrs = {}
+            elif ext == ".ply":
+                v, t, attrs = pf.read_ply_surface_mesh(a.input_mesh)
+            elif not ext:
+                raise ValueError("Unable to detect file format of mesh input file (file name has to end with supported extension)")
+            else:
+                raise ValueError(f'Unsupported file format extension "{ext[1:]}" for reading surface meshes')
+            io.write_mesh(a.output_file, (v, t), point_attributes=attrs or None)
+    except (ValueError, OSError) as e:
+        print(f"Error occurred: {e}", file=sys.stderr)
+        return 1
+    return 0
 
 
 def main(argv=None):
@@ -48,7 +91,17 @@ def main(argv=None):
     r.add_argument("--mesh-aabb-clamp-verts", choices=["on", "off"], default="off")
     r.add_argument("--check-mesh", choices=["on", "off"], default="off")
     r.add_argument("-o", "--output-file", default=None)
+    # `splashsurf convert` (splashsurf/src/convert.rs:13-56)
+    cv = sub.add_parser("convert")
+    cv.add_argument("--particles", dest="input_particles", default=None)
+    cv.add_argument("--mesh", dest="input_mesh", default=None)
+    cv.add_argument("-o", dest="output_file", required=True)
+    cv.add_argument("--overwrite", action="store_true")
+    cv.add_argument("--domain-min", type=float, nargs=3, default=None, metavar=("X_MIN", "Y_MIN", "Z_MIN"))
+    cv.add_argument("--domain-max", type=float, nargs=3, default=None, metavar=("X_MAX", "Y_MAX", "Z_MAX"))
     a = ap.parse_args(argv)
+    if a.cmd == "convert":
+        return convert(a)
     from . import MeshWithData, io, reconstruct_surface, reconstruction_pipeline
     p = io.read_particles(a.input)
     t = time.perf_counter()
@@ -60,6 +113,9 @@ def main(argv=None):
     if a.mesh_cleanup is None:
         a.mesh_cleanup = "on" if a.mesh_smoothing_iters not in (None, 0) else "off"
     attrs = io.read_particle_attributes(a.input, a.interpolate_attributes)
+    for name, arr in attrs.items():
+        if arr.dtype.kind != "f":                      # BGEO Int attributes load as u64; the reference cannot interpolate them either (reconstruct.rs:1387)
+            raise ValueError(f'Interpolation of this attribute type not implemented (attribute "{name}")')
     post = any([bool(attrs), on(a.normals), on(a.mesh_cleanup), on(a.decimate_barnacles), a.mesh_smoothing_iters is not None, on(a.generate_quads),
                 a.mesh_aabb_min is not None, on(a.check_mesh)])
     if post:

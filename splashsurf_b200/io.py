@@ -2,7 +2,7 @@
 the hot path.  Nothing here is on the timed path.
 
 * `.xyz`   raw native-endian f32 triples                      (splashsurf_lib/src/io/xyz_format.rs:10-37)
-* `.vtk`   legacy VTK, BINARY big-endian float POINTS         (fixtures under data/)
+* `.vtk` / `.vtu` / `.ply` / `.bgeo` / `.json` particle files: particle_formats.py (every format the reference reads / writes)
 * `.obj`   `v x y z` / optional `vn` / `f a b c` (1-based; `a//a` with normals)   (splashsurf_lib/src/io/obj_format.rs:17-71)
 * `.ply`   binary little endian, attributes inside the vertex records             (splashsurf_lib/src/io/ply_format.rs:190-267)
 
@@ -24,21 +24,28 @@ def write_xyz(path: str, particles: np.ndarray) -> None:
 
 
 def read_vtk_points(path: str) -> np.ndarray:
-    b = open(path, "rb").read()
-    k = b.index(b"POINTS")
-    e = b.index(b"\n", k)
-    n = int(b[k:e].split()[1])
-    return np.frombuffer(b[e + 1:e + 1 + 12 * n], dtype=">f4").reshape(n, 3).astype("<f4")
+    """POINTS of a legacy (ASCII / BINARY, float / double) or XML VTK file as float32 (vtk_format.rs:141-155)."""
+    from .particle_formats import read_vtk_particles
+    return read_vtk_particles(path)
 
 
 def read_particles(path: str) -> np.ndarray:
-    if path.endswith(".xyz"):
-        return read_xyz(path)
-    if path.endswith(".vtk"):
-        return read_vtk_points(path)
-    if path.endswith(".npy"):
+    """`particles_from_file` (splashsurf_lib/src/io.rs:17-43): .vtk / .vtu / .xyz / .ply / .bgeo / .json by extension (+ .npy)."""
+    if str(path).lower().endswith(".npy"):
         return np.ascontiguousarray(np.load(path), dtype=np.float32).reshape(-1, 3)
-    raise ValueError(f"unsupported particle file: {path}")
+    from .particle_formats import particles_from_file
+    return particles_from_file(path)
+
+
+def write_particles(path: str, particles: np.ndarray, enable_compression: bool = True) -> None:
+    """`write_particle_positions` (splashsurf/src/io.rs:195-235): .vtk / .bgeo / .json by extension (+ .xyz, .npy for the harness)."""
+    low = str(path).lower()
+    if low.endswith(".xyz"):
+        return write_xyz(path, particles)
+    if low.endswith(".npy"):
+        return np.save(path, np.ascontiguousarray(particles, dtype=np.float32))
+    from .particle_formats import write_particle_positions
+    write_particle_positions(path, particles, enable_compression)
 
 
 def write_mesh(path, mesh, **kw) -> None:
@@ -164,82 +171,16 @@ def read_vtk_mesh(path: str):
     return verts, np.ascontiguousarray(tris), np.ascontiguousarray(quads), out[0], out[1]
 
 
-_VTK_TYPES = {b"float": ">f4", b"double": ">f8", b"int": ">i4", b"unsigned_int": ">u4", b"long": ">i8", b"unsigned_long": ">u8",
-              b"short": ">i2", b"unsigned_short": ">u2", b"char": ">i1", b"unsigned_char": ">u1"}
-
-
 def read_vtk_point_data(path: str) -> dict:
-    """POINT_DATA arrays of a legacy BINARY VTK file as written by SPlisHSPlasH and by the reference (SCALARS + lookup table, VECTORS / NORMALS,
-    FIELD arrays): name -> array of shape (n,) or (n, components) in the file's type."""
-    b = open(path, "rb").read()
-    if b.split(b"\n", 3)[2].strip().upper() != b"BINARY":
-        raise ValueError("only BINARY legacy VTK files are read")
-    k = b.find(b"POINT_DATA")
-    if k < 0:
-        return {}
-
-    def line(o):
-        while o < len(b) and b[o:o + 1] in b" \n\r\t":
-            o += 1
-        e = b.find(b"\n", o)
-        e = len(b) if e < 0 else e
-        return b[o:e].split(), e + 1
-
-    def array(o, typ, n):
-        if typ not in _VTK_TYPES:
-            raise ValueError(f"unsupported VTK data type {typ.decode()}")
-        a = np.frombuffer(b, _VTK_TYPES[typ], n, o)
-        return a.astype(a.dtype.newbyteorder("<")), o + a.nbytes
-    tok, o = line(k)
-    n = int(tok[1])
-    out = {}
-    while True:
-        tok, o2 = line(o)
-        if not tok or tok[0] in (b"CELL_DATA", b"POINT_DATA"):
-            break
-        kind = tok[0]
-        if kind == b"SCALARS":
-            comps = int(tok[3]) if len(tok) > 3 else 1
-            tok2, o3 = line(o2)
-            if tok2[:1] == [b"LOOKUP_TABLE"]:
-                o2 = o3
-            a, o = array(o2, tok[2], n * comps)
-            out[tok[1].decode()] = a.reshape(n, comps) if comps > 1 else a
-        elif kind in (b"VECTORS", b"NORMALS"):
-            a, o = array(o2, tok[2], 3 * n)
-            out[tok[1].decode()] = a.reshape(n, 3)
-        elif kind == b"FIELD":
-            o = o2
-            for _ in range(int(tok[2])):
-                t2, o = line(o)
-                comps, tuples = int(t2[1]), int(t2[2])
-                a, o = array(o, t2[3], comps * tuples)
-                out[t2[0].decode()] = a.reshape(tuples, comps) if comps > 1 else a
-        else:
-            raise ValueError(f"unsupported POINT_DATA entry {kind.decode()}")
-    return out
+    """POINT_DATA arrays of a legacy (ASCII / BINARY: SCALARS + lookup table, VECTORS / NORMALS, FIELD arrays) or XML VTK file:
+    name -> array of shape (n,) or (n, components) in the file's type."""
+    from .particle_formats import read_vtk
+    return dict(read_vtk(path).point_data.items())
 
 
 def read_particle_attributes(path: str, names) -> dict:
-    """The `-a / --interpolate_attribute` inputs of the reference CLI (reconstruct.rs:196-198; vtk_format.rs:96-140, :318-346): named point
-    attributes of a VTK particle file as float32 -- scalars stored as u32 / f32 / f64, 3-vectors stored as f32 / f64; anything else is an
-    error, like in the reference."""
-    if not names:
-        return {}
-    if not path.endswith(".vtk"):
-        raise ValueError("attributes are read from legacy .vtk particle files only")
-    data = read_vtk_point_data(path)
-    out = {}
-    for name in names:
-        if name not in data:
-            raise ValueError(f"Attribute {name} not found in VTK file")
-        a = data[name]
-        if a.ndim == 1 and (a.dtype.kind == "f" or a.dtype == np.uint32):
-            out[name] = np.ascontiguousarray(a, dtype=np.float32)
-        elif a.ndim == 2 and a.shape[1] == 3 and a.dtype.kind == "f":
-            out[name] = np.ascontiguousarray(a, dtype=np.float32)
-        elif a.ndim == 1 or a.shape[1] == 3:
-            raise ValueError(f'Attribute "{name}": unsupported VTK data type for {"scalars" if a.ndim == 1 else "vectors"}')
-        else:
-            raise ValueError(f'Attribute "{name}": unsupported number of components ({a.shape[1]}) in VTK IO buffer')
-    return out
+    """The `-a / --interpolate_attribute` inputs of the reference CLI (reconstruct.rs:196-198; splashsurf/src/io.rs:66-190): named point
+    attributes of a VTK / VTU (vtk_format.rs:96-140, :318-346) or BGEO (bgeo_format.rs:45-66) particle file, converted like the reference
+    converts them -- scalars stored as u32 / f32 / f64 and 3-vectors stored as f32 / f64 become float32; anything else is an error."""
+    from .particle_formats import particle_attributes_from_file
+    return particle_attributes_from_file(path, names)

@@ -566,5 +566,5 @@ def test_emulated_cli_end_to_end_against_reference_cli_with_attributes(emu, orac
     assert set(map(tuple, np.sort(idx[t1], axis=1))) == set(map(tuple, np.sort(t2.astype(np.int64), axis=1)))
     for k in a1:
         assert np.abs(a1[k] - a2[k][idx]).max() <= 5e-6 * max(1.0, float(np.abs(a1[k]).max())) + 2e-5, k
-    with pytest.raises(ValueError, match="Attribute pressure not found in VTK file"):
+    with pytest.raises(ValueError, match='Missing attribute\\(s\\) "pressure" in input file'):
         cli.main(args[:5] + ["-a", "pressure"])
