@@ -91,6 +91,25 @@ def main(argv=None):
     r.add_argument("--mesh-aabb-clamp-verts", choices=["on", "off"], default="off")
     r.add_argument("--check-mesh", choices=["on", "off"], default="off")
     r.add_argument("-o", "--output-file", default=None)
+    r.add_argument("--output-dir", default=None)
+    r.add_argument("-s", "--start-index", type=int, default=None)
+    r.add_argument("-e", "--end-index", type=int, default=None)
+    r.add_argument("-d", "--double-precision", choices=["on", "off"], default="off")
+    r.add_argument("--particle-aabb-min", type=float, nargs=3, default=None)
+    r.add_argument("--particle-aabb-max", type=float, nargs=3, default=None)
+    r.add_argument("--mt-files", choices=["on", "off"], default="off")              # accepted: frames are sharded over GPUs instead (--shard / launcher)
+    r.add_argument("--mt-particles", choices=["on", "off"], default="on")
+    r.add_argument("-n", "--num-threads", type=int, default=None)                    # accepted, no meaning on the device
+    r.add_argument("--subdomain-grid-auto-disable", choices=["on", "off"], default="on")
+    r.add_argument("--output-raw-mesh", choices=["on", "off"], default="off")
+    r.add_argument("--check-mesh-closed", choices=["on", "off"], default="off")
+    r.add_argument("--check-mesh-manifold", choices=["on", "off"], default="off")
+    r.add_argument("--check-mesh-orientation", choices=["on", "off"], default="off")
+    r.add_argument("--check-mesh-debug", choices=["on", "off"], default="off")
+    r.add_argument("-q", "--quiet", action="store_true")
+    r.add_argument("-v", action="count", default=0)
+    r.add_argument("--device", type=int, default=None)                               # CUDA device of this process (default: LOCAL_RANK or 0)
+    r.add_argument("--shard", default=None, metavar="I/N")                           # this process takes frames I, I + N, ... (default: RANK / WORLD_SIZE)
     # `splashsurf convert` (splashsurf/src/convert.rs:13-56)
     cv = sub.add_parser("convert")
     cv.add_argument("--particles", dest="input_particles", default=None)
@@ -102,50 +121,151 @@ def main(argv=None):
     a = ap.parse_args(argv)
     if a.cmd == "convert":
         return convert(a)
-    from . import MeshWithData, io, reconstruct_surface, reconstruction_pipeline
-    p = io.read_particles(a.input)
-    t = time.perf_counter()
-    on = lambda v: v == "on"         # noqa: E731
-    # the reference CLI always uses the subdomain grid when it is on (auto_disable is inverted there)
+    return reconstruct(a)
+
+
+def collect_paths(a):
+    """`ReconstructionRunnerPathCollection` (reconstruct.rs:700-963): the (input, output) pairs of one command line.  A "{}" in the
+    input file name makes it a sequence: every file of that directory whose name matches prefix + digits + suffix and whose index lies in
+    [--start-index, --end-index], in natural order; the output name needs a "{}" too (default "<stem with {} -> surface_{}>.vtk").  A
+    single file defaults to "<stem>_surface.vtk".  --output-dir is prepended and created when missing."""
+    import os
+    import re
+    inp = a.input
+    name = os.path.basename(inp)
+    if not name:
+        raise ValueError(f'The input file path "{inp}" does not end with a filename')
+    parent = os.path.dirname(inp)
+    if parent and not os.path.isdir(parent):
+        raise ValueError(f'The parent directory "{parent}" of the input file path "{inp}" does not exist')
+    seq = "{}" in name
+    stem = os.path.splitext(name)[0]
+    if seq:
+        if a.output_file is not None:
+            if "{}" not in a.output_file:
+                raise ValueError(f'The output filename "{a.output_file}" does not contain a place holder "{{}}"')
+            out = a.output_file
+        else:
+            out = stem.replace("{}", "surface_{}") + ".vtk"
+    else:
+        if not os.path.isfile(inp):
+            raise ValueError(f'Input file does not exist: "{inp}"')
+        out = a.output_file if a.output_file is not None else f"{stem}_surface.vtk"
+    if a.start_index is not None and a.end_index is not None and a.start_index > a.end_index:
+        raise ValueError(f'Invalid input sequence range: "{a.start_index} to {a.end_index}"')
+    if a.output_dir is not None:
+        out = os.path.join(a.output_dir, out)
+        d = os.path.dirname(out)
+        if d and not os.path.exists(d):
+            os.makedirs(d, exist_ok=True)
+    if not seq:
+        return [(inp, out)]
+    prefix, suffix = name.split("{}", 1)
+    rx = re.compile(re.escape(prefix) + r"(\d+)" + re.escape(suffix))          # unanchored, like Regex::is_match
+    out_dir, out_pat = os.path.dirname(out), os.path.basename(out)
+
+    def natural(n):
+        return [(0, int(t)) if t.isdigit() else (1, t.lower()) for t in re.split(r"(\d+)", n) if t]
+    paths = []
+    for entry in sorted(os.listdir(parent or "."), key=natural):
+        m = rx.search(entry)
+        if m is None or not os.path.isfile(os.path.join(parent or ".", entry)):
+            continue
+        idx = int(m.group(1))
+        if (a.start_index is not None and idx < a.start_index) or (a.end_index is not None and idx > a.end_index):
+            continue
+        paths.append((os.path.join(parent, entry), os.path.join(out_dir, out_pat.replace("{}", m.group(1)))))
+    return paths
+
+
+def _aabb(lo, hi, what):
+    if (lo is None) != (hi is None):
+        raise ValueError(f"the {what} needs both its min and its max corner")
+    if lo is None:
+        return None, None
+    if any(h < l for l, h in zip(lo, hi)):
+        raise ValueError(f"The user specified {what} min/max values are inconsistent! min: {list(lo)} max: {list(hi)}")
+    if any(h == l for l, h in zip(lo, hi)):
+        raise ValueError(f"The user specified {what} is degenerate! min: {list(lo)} max: {list(hi)}")
+    return list(lo), list(hi)
+
+
+def reconstruct(a) -> int:
+    """`reconstruct_subcommand` (reconstruct.rs:380-440, :1590-1680): one reconstruction (+ post-processing) per input file, the frames of
+    a sequence one after the other on one context (its device buffers are reused from frame to frame).  Under a multi-process launcher
+    (RANK / WORLD_SIZE / LOCAL_RANK in the environment, or --shard i/n) every process takes every n-th frame on its own GPU -- the device
+    version of the reference's --mt-files; no collective is involved."""
+    import os
+    from . import Context, MeshWithData, io, reconstruct_surface, reconstruction_pipeline
+    on = lambda v: str(v).lower() == "on"         # noqa: E731
+    if on(a.double_precision):
+        raise ValueError("--double-precision=on: the device path reconstructs float32 particles only (SURVEY.md 8b)")
+    paths = collect_paths(a)
+    rank, world = 0, 1
+    if a.shard:
+        rank, world = (int(t) for t in a.shard.split("/"))
+    elif "WORLD_SIZE" in os.environ and int(os.environ["WORLD_SIZE"]) > 1:
+        rank, world = int(os.environ.get("RANK", "0")), int(os.environ["WORLD_SIZE"])
+    if not (0 <= rank < world):
+        raise ValueError(f"invalid shard {rank}/{world}")
+    paths = paths[rank::world]
+    device = a.device if a.device is not None else int(os.environ.get("LOCAL_RANK", "0"))
+    pmin, pmax = _aabb(a.particle_aabb_min, a.particle_aabb_max, "particle AABB")
+    mmin, mmax = _aabb(a.mesh_aabb_min, a.mesh_aabb_max, "mesh AABB")
+    # auto_disable is inverted in the reference CLI (reconstruct.rs:635; SURVEY.md 8b): with the defaults the subdomain grid is always used
     base = dict(particle_radius=a.particle_radius, rest_density=a.rest_density, smoothing_length=a.smoothing_length, cube_size=a.cube_size,
-                iso_surface_threshold=a.surface_threshold, simd=on(a.simd), subdomain_grid=on(a.subdomain_grid), subdomain_grid_auto_disable=False,
-                subdomain_num_cubes_per_dim=a.subdomain_cubes)
+                iso_surface_threshold=a.surface_threshold, simd=on(a.simd), subdomain_grid=on(a.subdomain_grid),
+                subdomain_grid_auto_disable=not on(a.subdomain_grid_auto_disable), subdomain_num_cubes_per_dim=a.subdomain_cubes,
+                aabb_min=pmin, aabb_max=pmax, multi_threading=on(a.mt_particles))
     if a.mesh_cleanup is None:
         a.mesh_cleanup = "on" if a.mesh_smoothing_iters not in (None, 0) else "off"
-    attrs = io.read_particle_attributes(a.input, a.interpolate_attributes)
-    for name, arr in attrs.items():
-        if arr.dtype.kind != "f":                      # BGEO Int attributes load as u64; the reference cannot interpolate them either (reconstruct.rs:1387)
-            raise ValueError(f'Interpolation of this attribute type not implemented (attribute "{name}")')
-    post = any([bool(attrs), on(a.normals), on(a.mesh_cleanup), on(a.decimate_barnacles), a.mesh_smoothing_iters is not None, on(a.generate_quads),
-                a.mesh_aabb_min is not None, on(a.check_mesh)])
-    if post:
-        # --sph-normals only selects how --normals are computed (reconstruct.rs:1094-1149)
-        out, _ = reconstruction_pipeline(p, attributes_to_interpolate=attrs, compute_normals=on(a.normals), sph_normals=on(a.sph_normals),
-                                         normals_smoothing_iters=a.normals_smoothing_iters, mesh_smoothing_iters=a.mesh_smoothing_iters,
-                                         mesh_smoothing_weights=on(a.mesh_smoothing_weights),
-                                         mesh_smoothing_weights_normalization=a.mesh_smoothing_weights_normalization,
-                                         output_mesh_smoothing_weights=on(a.output_smoothing_weights), output_raw_normals=on(a.output_raw_normals),
-                                         mesh_cleanup=on(a.mesh_cleanup),
-                                         mesh_cleanup_snap_dist=a.mesh_cleanup_snap_dist, decimate_barnacles=on(a.decimate_barnacles),
-                                         keep_vertices=on(a.keep_verts), generate_quads=on(a.generate_quads),
-                                         quad_max_edge_diag_ratio=a.quad_max_edge_diag_ratio, quad_max_normal_angle=a.quad_max_normal_angle,
-                                         quad_max_interior_angle=a.quad_max_interior_angle, mesh_aabb_min=a.mesh_aabb_min, mesh_aabb_max=a.mesh_aabb_max,
-                                         mesh_aabb_clamp_vertices=on(a.mesh_aabb_clamp_verts), check_mesh_closed=on(a.check_mesh),
-                                         check_mesh_manifold=on(a.check_mesh), check_mesh_orientation=on(a.check_mesh), **base)
-    else:
-        out = MeshWithData(reconstruct_surface(p, **base).mesh, {}, {})
-    dt = time.perf_counter() - t
-    quads = out.mesh.get_quads() if on(a.generate_quads) else None
-    tris = out.mesh.get_triangles() if on(a.generate_quads) else out.mesh.triangles
-    print(f"{len(p)} particles -> {out.nvertices} vertices, {len(tris)} triangles" + (f", {len(quads)} quads" if quads is not None else "") + f" in {dt:.3f} s",
-          file=sys.stderr)
-    if a.output_file:
-        if a.output_file.endswith(".npz"):
-            np.savez(a.output_file, vertices=out.mesh.vertices, triangles=tris, **({"quads": quads} if quads is not None else {}), **out.point_attributes)
-        else:
+    chk = on(a.check_mesh)
+    closed, manifold, orient = chk or on(a.check_mesh_closed), chk or on(a.check_mesh_manifold), chk or on(a.check_mesh_orientation)
+    post = any([bool(a.interpolate_attributes), on(a.normals), on(a.mesh_cleanup), on(a.decimate_barnacles), a.mesh_smoothing_iters is not None,
+                on(a.generate_quads), mmin is not None, closed, manifold, orient])
+    ctx = Context(device) if paths else None
+    try:
+        for k, (src, dst) in enumerate(paths):
+            p = io.read_particles(src)
+            attrs = io.read_particle_attributes(src, a.interpolate_attributes)
+            for name, arr in attrs.items():
+                if arr.dtype.kind != "f":              # BGEO Int attributes load as u64; the reference cannot interpolate them either (reconstruct.rs:1387)
+                    raise ValueError(f'Interpolation of this attribute type not implemented (attribute "{name}")')
             t = time.perf_counter()
-            io.write_mesh(a.output_file, out)              # .vtk / .ply / .obj as the reference CLI writes them (io.rs:276-316)
-            print(f"wrote {a.output_file} in {time.perf_counter() - t:.3f} s", file=sys.stderr)
+            if post:
+                # --sph-normals only selects how --normals are computed (reconstruct.rs:1094-1149)
+                out, rec = reconstruction_pipeline(
+                    p, attributes_to_interpolate=attrs, compute_normals=on(a.normals), sph_normals=on(a.sph_normals),
+                    normals_smoothing_iters=a.normals_smoothing_iters, mesh_smoothing_iters=a.mesh_smoothing_iters,
+                    mesh_smoothing_weights=on(a.mesh_smoothing_weights), mesh_smoothing_weights_normalization=a.mesh_smoothing_weights_normalization,
+                    output_mesh_smoothing_weights=on(a.output_smoothing_weights), output_raw_normals=on(a.output_raw_normals),
+                    mesh_cleanup=on(a.mesh_cleanup), mesh_cleanup_snap_dist=a.mesh_cleanup_snap_dist, decimate_barnacles=on(a.decimate_barnacles),
+                    keep_vertices=on(a.keep_verts), generate_quads=on(a.generate_quads), quad_max_edge_diag_ratio=a.quad_max_edge_diag_ratio,
+                    quad_max_normal_angle=a.quad_max_normal_angle, quad_max_interior_angle=a.quad_max_interior_angle, mesh_aabb_min=mmin,
+                    mesh_aabb_max=mmax, mesh_aabb_clamp_vertices=on(a.mesh_aabb_clamp_verts), check_mesh_closed=closed, check_mesh_manifold=manifold,
+                    check_mesh_orientation=orient, check_mesh_debug=on(a.check_mesh_debug), context=ctx, **base)
+                raw = rec.mesh
+            else:
+                raw = reconstruct_surface(p, context=ctx, **base).mesh
+                out = MeshWithData(raw, {}, {})
+            dt = time.perf_counter() - t
+            quads = out.mesh.get_quads() if on(a.generate_quads) else None
+            tris = out.mesh.get_triangles() if on(a.generate_quads) else out.mesh.triangles
+            if not a.quiet:
+                print(f"[{k + 1}/{len(paths)}] {src}: {len(p)} particles -> {out.nvertices} vertices, {len(tris)} triangles"
+                      + (f", {len(quads)} quads" if quads is not None else "") + f" in {dt:.3f} s", file=sys.stderr)
+            t = time.perf_counter()
+            if on(a.output_raw_mesh):                  # "raw_" + file name beside the output file (reconstruct.rs:1618-1650)
+                io.write_mesh(os.path.join(os.path.dirname(dst), "raw_" + os.path.basename(dst)), MeshWithData(raw, {}, {}))
+            if dst.endswith(".npz"):
+                np.savez(dst, vertices=out.mesh.vertices, triangles=tris, **({"quads": quads} if quads is not None else {}), **out.point_attributes)
+            else:
+                io.write_mesh(dst, out)                # .vtk / .ply / .obj as the reference CLI writes them (io.rs:276-316)
+            if not a.quiet:
+                print(f"wrote {dst} in {time.perf_counter() - t:.3f} s", file=sys.stderr)
+    finally:
+        if ctx is not None:
+            ctx.close()
     return 0
 
 

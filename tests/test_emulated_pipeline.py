@@ -540,6 +540,67 @@ def test_emulated_cli_with_postprocessing(emu, tmp_path):
 
 
 @pytest.mark.skipif(not os.path.exists("/root/reference/data/bunny_frame_14_7705_particles.vtk"), reason="reference tree only exists in the build container")
+def test_emulated_cli_frame_sequence_beside_reference_cli(emu, oracle_mod, tmp_path, monkeypatch):
+    """File sequences like the reference CLI (reconstruct.rs:700-963): "{}" in the input name, -s / -e, default output names, --output-dir,
+    raw_ meshes, the particle AABB, bgeo / json / vtk inputs -- same files as the REFERENCE CLI writes for the same command line (names,
+    sizes, triangle sets after matching vertices by position); frames sharded over processes (--shard / RANK, WORLD_SIZE) give the same files."""
+    import subprocess, sys
+    from scipy.spatial import cKDTree
+    from splashsurf_b200 import io, __main__ as cli
+    frames = tmp_path / "frames"
+    frames.mkdir()
+    for i, ext in ((2, "bgeo"), (9, "bgeo"), (10, "bgeo"), (11, "bgeo"), (30, "bgeo")):
+        io.write_particles(str(frames / f"fluid_{i}_x.{ext}"), _splash((6, 6, 6), 1, 0.025, 40 + i))
+    io.write_particles(str(frames / "other_3.bgeo"), _splash((5, 5, 5), 1, 0.025, 1))
+    (frames / "fluid__x.bgeo").write_bytes(b"not a frame: no digits")
+    common = ["-r=0.025", "-l=2.0", "-c=0.75", "-s", "9", "-e", "11", "--particle-aabb-min", "-1", "-1", "-1", "--particle-aabb-max", "0.2", "2", "2",
+              "--output-raw-mesh=on", "--mesh-smoothing-iters=1", "--mesh-cleanup=off", "--normals=on"]
+    pattern = str(frames / "fluid_{}_x.bgeo")
+    ours, theirs = tmp_path / "ours", tmp_path / "theirs"
+    assert cli.main(["reconstruct", pattern, *common, "--output-dir", str(ours), "-q"]) == 0
+    expect = sorted(f"{pre}fluid_surface_{i}_x.vtk" for i in (9, 10, 11) for pre in ("", "raw_"))
+    assert sorted(os.listdir(ours)) == expect
+    # two processes taking every second frame (the device version of --mt-files): same files
+    sharded = tmp_path / "sharded"
+    assert cli.main(["reconstruct", pattern, *common, "--output-dir", str(sharded), "-q", "--shard", "0/2"]) == 0
+    assert sorted(os.listdir(sharded)) == sorted(f"{pre}fluid_surface_{i}_x.vtk" for i in (9, 11) for pre in ("", "raw_"))
+    monkeypatch.setenv("RANK", "1"); monkeypatch.setenv("WORLD_SIZE", "2"); monkeypatch.setenv("LOCAL_RANK", "0")
+    assert cli.main(["reconstruct", pattern, *common, "--output-dir", str(sharded), "-q"]) == 0
+    monkeypatch.delenv("RANK"); monkeypatch.delenv("WORLD_SIZE"); monkeypatch.delenv("LOCAL_RANK")
+    assert sorted(os.listdir(sharded)) == expect
+    assert all(open(ours / f, "rb").read() == open(sharded / f, "rb").read() for f in expect)
+    # explicit output pattern; a pattern without "{}" is refused; inverted ranges are refused
+    assert cli.main(["reconstruct", pattern, *common[:3], "-o", "m_{}.ply", "--output-dir", str(tmp_path / "pat"), "-e", "2", "-q"]) == 0
+    assert os.listdir(tmp_path / "pat") == ["m_2.ply"]
+    with pytest.raises(ValueError, match="does not contain a place holder"):
+        cli.main(["reconstruct", pattern, *common[:3], "-o", "m.ply"])
+    with pytest.raises(ValueError, match='Invalid input sequence range: "5 to 3"'):
+        cli.main(["reconstruct", pattern, *common[:3], "-s", "5", "-e", "3"])
+    with pytest.raises(ValueError, match="Input file does not exist"):
+        cli.main(["reconstruct", str(frames / "nope.bgeo"), *common[:3]])
+    with pytest.raises(ValueError, match="particle AABB is degenerate"):
+        cli.main(["reconstruct", pattern, *common[:3], "--particle-aabb-min", "0", "0", "0", "--particle-aabb-max", "1", "0", "1"])
+    # a single file without -o: "<stem>_surface.vtk" in the working directory
+    monkeypatch.chdir(tmp_path)
+    assert cli.main(["reconstruct", str(frames / "other_3.bgeo"), *common[:3], "-q"]) == 0
+    assert os.path.isfile(tmp_path / "other_3_surface.vtk")
+    if not oracle_mod.reference_available():
+        return
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = "import sys; sys.path.insert(0, %r); import oracle; oracle.reference().run_splashsurf(['splashsurf'] + sys.argv[1:])" % root
+    subprocess.check_call([sys.executable, "-c", code, "reconstruct", pattern, *common, "--output-dir", str(theirs), "-q"])
+    assert sorted(os.listdir(theirs)) == expect
+    for f in expect:
+        assert os.path.getsize(theirs / f) == os.path.getsize(ours / f), f
+        v1, t1, _, a1, _ = io.read_vtk_mesh(str(theirs / f))
+        v2, t2, _, a2, _ = io.read_vtk_mesh(str(ours / f))
+        assert len(v1) == len(v2) > 500 and list(a1) == list(a2) == ([] if f.startswith("raw_") else ["normals"])
+        d, idx = cKDTree(v2).query(v1)
+        assert d.max() < 2e-6 and len(np.unique(idx)) == len(v1)
+        assert set(map(tuple, np.sort(idx[t1], axis=1))) == set(map(tuple, np.sort(t2.astype(np.int64), axis=1)))
+        assert v1[:, 0].max() < 0.35                      # the particle AABB cut the cloud
+
+
 def test_emulated_cli_end_to_end_against_reference_cli_with_attributes(emu, oracle_mod, tmp_path):
     """The whole harness path on a reference fixture (SPlisHSPlasH VTK with `id` and `velocity` point data): particle + attribute readers,
     clean-up (on by default with smoothing), weighted smoothing, normals, SPH interpolation of both attributes (`-a`), PLY writer -- beside
