@@ -539,7 +539,6 @@ def test_emulated_cli_with_postprocessing(emu, tmp_path):
     assert np.array_equal(tq, z["triangles"]) and np.array_equal(qq, z["quads"]) and list(paq) == ["normals"]
 
 
-@pytest.mark.skipif(not os.path.exists("/root/reference/data/bunny_frame_14_7705_particles.vtk"), reason="reference tree only exists in the build container")
 def test_emulated_cli_frame_sequence_beside_reference_cli(emu, oracle_mod, tmp_path, monkeypatch):
     """File sequences like the reference CLI (reconstruct.rs:700-963): "{}" in the input name, -s / -e, default output names, --output-dir,
     raw_ meshes, the particle AABB, bgeo / json / vtk inputs -- same files as the REFERENCE CLI writes for the same command line (names,
@@ -601,6 +600,7 @@ def test_emulated_cli_frame_sequence_beside_reference_cli(emu, oracle_mod, tmp_p
         assert v1[:, 0].max() < 0.35                      # the particle AABB cut the cloud
 
 
+@pytest.mark.skipif(not os.path.exists("/root/reference/data/bunny_frame_14_7705_particles.vtk"), reason="reference tree only exists in the build container")
 def test_emulated_cli_end_to_end_against_reference_cli_with_attributes(emu, oracle_mod, tmp_path):
     """The whole harness path on a reference fixture (SPlisHSPlasH VTK with `id` and `velocity` point data): particle + attribute readers,
     clean-up (on by default with smoothing), weighted smoothing, normals, SPH interpolation of both attributes (`-a`), PLY writer -- beside
