@@ -55,3 +55,51 @@ def test_cuda_reference_integration_data_sets(ss, oracle_mod, name):
     par = oracle_mod.mesh_parity(g.mesh.vertices, g.mesh.triangles, g.vertex_edge_keys, o["vertices"], o["triangles"], o["vertex_keys"], 64)
     assert par["keys_equal"] and par["triangles_equal"] and par["n_not_bitexact"] == 0, par
     assert ss.check_mesh_consistency(g.mesh, g.grid, check_closed=True, check_manifold=True) is None
+
+
+# ---- hand-made neighbourhood cases of the reference (tests/integration_tests/test_neighborhood_search.rs:11-86), search radius 0.3 = the
+# compact support radius of the reconstruction (h = 2 * smoothing_length * particle_radius = 2 * 2.0 * 0.075, exact in f32)
+def _ns_cases(sr):
+    return [
+        ([[1, 1, 1], [1 + sr, 1 + sr, 1 + sr]], [[], []]),
+        ([[1, 1, 1], [1 + 0.9999 * sr, 1, 1]], [[1], [0]]),
+        ([[1, 1, 1], [1 + sr, 1, 1]], [[1], [0]]),                            # f32: (1 + 0.3) - 1 < 0.3
+        ([[1, 1, 1], [1 + sr * 1.0001, 1, 1]], [[], []]),
+        ([[1, 1, 1], [1 + 0.9 * sr, 1, 1], [1 - 0.9 * sr, 1, 1], [1, 1 + 0.2 * sr, 1]], [[1, 2, 3], [0, 3], [0, 3], [0, 1, 2]]),
+        ([[1, 1, 1], [1 + 0.9 * sr, 1, 1], [1 - 0.9 * sr, 1, 1], [1 - 0.8 * sr, 1, -0.2 * sr], [1, 1 + 0.2 * sr, 1], [1, 1 - 0.2 * sr, 1],
+          [1, 1 + 0.2 * sr, 1 + 0.2 * sr], [1, 1 - 0.2 * sr, 1 - 0.2 * sr]],
+         [[1, 2, 4, 5, 6, 7], [0, 4, 5, 6, 7], [0, 4, 5, 6, 7], [], [0, 1, 2, 5, 6, 7], [0, 1, 2, 4, 6, 7], [0, 1, 2, 4, 5, 7], [0, 1, 2, 4, 5, 6]]),
+    ]
+
+
+def _ns_particles(rows, sr):
+    # the reference builds every coordinate in f32 arithmetic (Vector3<f32>::new(1.0 + 0.9 * search_radius, ...))
+    f = np.float32
+    one, s = f(1.0), f(sr)
+    table = {1: one, 1 + sr: one + s, 1 + 0.9999 * sr: one + f(0.9999) * s, 1 + sr * 1.0001: one + s * f(1.0001), 1 + 0.9 * sr: one + f(0.9) * s,
+             1 - 0.9 * sr: one - f(0.9) * s, 1 + 0.2 * sr: one + f(0.2) * s, 1 - 0.2 * sr: one - f(0.2) * s, 1 - 0.8 * sr: one - f(0.8) * s,
+             -0.2 * sr: f(-0.2) * s}
+    return np.array([[table[v] for v in row] for row in rows], dtype=np.float32)
+
+
+NS_KW = dict(particle_radius=0.075, smoothing_length=2.0, cube_size=1.0)
+
+
+def _check_ns(reconstruct, neighbors_of):
+    for rows, expect in _ns_cases(0.3):
+        p = _ns_particles(rows, 0.3)
+        for extra in (dict(subdomain_grid_auto_disable=False), dict(subdomain_grid=False)):     # per-subdomain search and global search
+            got = neighbors_of(reconstruct(p, **NS_KW, **extra), len(p))
+            assert [sorted(g) for g in got] == expect, (rows, extra, got)
+
+
+def test_oracle_neighborhood_hand_cases(oracle_mod):
+    def nbrs(o, n):
+        off, idx = o["neighbors"]
+        return [idx[off[i]:off[i + 1]].tolist() for i in range(n)]
+    _check_ns(lambda p, **kw: oracle_mod.reconstruct(p, want_neighbors=True, **kw), nbrs)
+
+
+@pytest.mark.gpu
+def test_cuda_neighborhood_hand_cases(ss):
+    _check_ns(lambda p, **kw: ss.reconstruct_surface(p, global_neighborhood_list=True, **kw), lambda g, n: [g.particle_neighbors[i] for i in range(n)])
