@@ -109,6 +109,7 @@ def main(argv=None):
     r.add_argument("-q", "--quiet", action="store_true")
     r.add_argument("-v", action="count", default=0)
     r.add_argument("--device", type=int, default=None)                               # CUDA device of this process (default: LOCAL_RANK or 0)
+    r.add_argument("--partition", choices=["on", "off"], default="off")              # under a multi-process launcher: ONE frame over all GPUs (slab partition)
     r.add_argument("--shard", default=None, metavar="I/N")                           # this process takes frames I, I + N, ... (default: RANK / WORLD_SIZE)
     # `splashsurf convert` (splashsurf/src/convert.rs:13-56)
     cv = sub.add_parser("convert")
@@ -190,6 +191,52 @@ def _aabb(lo, hi, what):
     return list(lo), list(hi)
 
 
+def reconstruct_partitioned(a, paths) -> int:
+    """--partition=on under torchrun: every frame is reconstructed by ALL processes together (slab partition of the subdomain grid, one
+    halo exchange, mesh assembled on rank 0: splashsurf_b200.distributed) -- for clouds that are too large or too slow for one GPU.  Every
+    rank reads its contiguous share of the particles; rank 0 writes the mesh.  The mesh post-processing steps are single-GPU steps and are
+    refused here, except SPH normals (--normals=on --sph-normals=on), which travel with the assembled mesh."""
+    import os
+    import torch.distributed as dist
+    from . import io
+    from .distributed import DistributedReconstructor
+    on = lambda v: str(v).lower() == "on"         # noqa: E731
+    sph = on(a.normals) and on(a.sph_normals)
+    refused = [k for k, v in (("-a", bool(a.interpolate_attributes)), ("--normals without --sph-normals", on(a.normals) and not sph),
+                              ("--mesh-cleanup", on(a.mesh_cleanup or "off")), ("--decimate-barnacles", on(a.decimate_barnacles)),
+                              ("--mesh-smoothing-iters", a.mesh_smoothing_iters is not None), ("--generate-quads", on(a.generate_quads)),
+                              ("--mesh-aabb-min", a.mesh_aabb_min is not None), ("--normals-smoothing-iters", a.normals_smoothing_iters is not None)) if v]
+    if refused:
+        raise ValueError("--partition=on reconstructs without mesh post-processing; not available: " + ", ".join(refused))
+    if not dist.is_initialized():
+        dist.init_process_group(os.environ.get("SS_DIST_BACKEND", "nccl"))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    pmin, pmax = _aabb(a.particle_aabb_min, a.particle_aabb_max, "particle AABB")
+    rec = DistributedReconstructor(sph_normals=sph, device=os.environ.get("SS_RUNNER_DEVICE") or None, particle_radius=a.particle_radius,
+                                   rest_density=a.rest_density, smoothing_length=a.smoothing_length, cube_size=a.cube_size,
+                                   iso_surface_threshold=a.surface_threshold, simd=on(a.simd), subdomain_grid=on(a.subdomain_grid),
+                                   subdomain_grid_auto_disable=not on(a.subdomain_grid_auto_disable), subdomain_num_cubes_per_dim=a.subdomain_cubes,
+                                   aabb_min=pmin, aabb_max=pmax)
+    try:
+        for k, (src, dst) in enumerate(paths):
+            p = io.read_particles(src)
+            n = len(p)
+            t = time.perf_counter()
+            out = rec(p[(n * rank) // world:(n * (rank + 1)) // world])
+            dt = time.perf_counter() - t
+            if rank == 0:
+                if not a.quiet:
+                    print(f"[{k + 1}/{len(paths)}] {src}: {n} particles on {world} GPUs -> {out.nvertices} vertices, {out.ncells} triangles in {dt:.3f} s",
+                          file=sys.stderr)
+                if dst.endswith(".npz"):
+                    np.savez(dst, vertices=out.mesh.vertices, triangles=out.mesh.triangles, **out.point_attributes)
+                else:
+                    io.write_mesh(dst, out)
+    finally:
+        rec.close()
+    return 0
+
+
 def reconstruct(a) -> int:
     """`reconstruct_subcommand` (reconstruct.rs:380-440, :1590-1680): one reconstruction (+ post-processing) per input file, the frames of
     a sequence one after the other on one context (its device buffers are reused from frame to frame).  Under a multi-process launcher
@@ -201,6 +248,8 @@ def reconstruct(a) -> int:
     if on(a.double_precision):
         raise ValueError("--double-precision=on: the device path reconstructs float32 particles only (SURVEY.md 8b)")
     paths = collect_paths(a)
+    if on(a.partition) and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        return reconstruct_partitioned(a, paths)
     rank, world = 0, 1
     if a.shard:
         rank, world = (int(t) for t in a.shard.split("/"))

@@ -229,6 +229,9 @@ class Runner:
         self._seg = None; self._seg_path = None; self._seg_gen = 0; self._seg_registered = False; self._layout = None
         self.want_keys = False           # also publish the MC edge keys of the assembled vertices (parity tools)
         self.ctx_normals = False         # set by the caller when ss_context_set_compute_sph_normals is on: normals join the assembled mesh
+        # parameters that carry a particle AABB: the GRID comes from that box (lib.rs:476-516) while `params` (no box) drive the
+        # partitioned calls on particles the caller has already filtered
+        self.grid_params = None
         self.balance_feedback = True     # slab cuts learn from the measured per-rank time of earlier frames
         self._layer_scale = None; self._layer_key = None
         # ... for a few frames; then the best cuts seen are kept (a plan that keeps moving keeps re-allocating: one 150 ms step in
@@ -238,6 +241,15 @@ class Runner:
         # `device` is only overridden by the tests that drive the runner over gloo with the CPU executor of the CUDA sources
         self.device = torch.device("cuda", local_rank) if device is None else torch.device(device)
         self.last_plan: Optional[SlabPlan] = None
+
+    def gathered_normals(self):
+        """Host copy of the SPH normals of the last assembled mesh (None when they were not computed / not gathered)."""
+        lay = getattr(self, "_layout", None)
+        if lay is None or not lay[3] or self.device.type != "cuda":
+            return None
+        nvg, ntg, want_keys, _ = lay
+        nbase = ((nvg * 12 + ntg * 12 + 7) // 8 * 8) + (nvg * 8 if want_keys else 0)
+        return self._seg[nbase:nbase + nvg * 12].view(torch.float32).view(-1, 3).numpy().copy()
 
     @property
     def plan_settled(self) -> bool:
@@ -254,9 +266,9 @@ class Runner:
         return np.ascontiguousarray(particles[lo:hi])
 
     # -- single GPU
-    def _step_single(self, xyz_ptr: int, n: int, copy_out: bool) -> dict:
+    def _step_single(self, xyz_ptr: int, n: int, copy_out: bool, params=None) -> dict:
         L = self.ctx._L
-        s = self.ctx.reconstruct_raw(xyz_ptr, n, self.params)
+        s = self.ctx.reconstruct_raw(xyz_ptr, n, self.params if params is None else params)
         try:
             return self._collect(s, copy_out, n_local=n)
         finally:
@@ -316,7 +328,8 @@ class Runner:
         corners = np.ascontiguousarray(np.stack([-b[:3], b[3:]]))
         t_host.append(time.perf_counter())      # 1: bounding box
         grid = _Grid()
-        rc = L.ss_grid_for_reconstruction_f32(self.ctx._h, C.c_void_p(corners.ctypes.data), C.c_uint64(2), C.byref(p), C.byref(grid))
+        gp = self.grid_params if self.grid_params is not None else p
+        rc = L.ss_grid_for_reconstruction_f32(self.ctx._h, C.c_void_p(corners.ctypes.data), C.c_uint64(2), C.byref(gp), C.byref(grid))
         if rc:
             raise RuntimeError((L.ss_last_error() or b"").decode())
         ncells = [int(v) for v in grid.cells_per_dim]
@@ -495,7 +508,7 @@ class Runner:
         dist.all_gather(bufs, buf, group=self.group)
         allp = torch.cat([bufs[r][:sizes[r]] for r in range(world)]).contiguous()
         _sync(dev)
-        out = self._step_single(allp.data_ptr(), allp.shape[0] if rank == 0 else 0, copy_out and rank == 0)
+        out = self._step_single(allp.data_ptr(), allp.shape[0] if rank == 0 else 0, copy_out and rank == 0, params=self.grid_params)
         t_ev[2].record(); _sync(dev)
         out["device_ms"] = t_ev[0].elapsed_time(t_ev[2])
         out["recv_particles"] = int(allp.shape[0]) if rank == 0 else 0
@@ -672,3 +685,64 @@ class Runner:
         seg = self._seg
         return seg[:nv * 12].view(torch.float32).view(-1, 3).numpy().copy(), seg[nv * 12:nv * 12 + nt * 12].view(torch.int32).view(-1, 3).numpy().copy()
 
+
+
+# ------------------------------------------------------------------------------------ user-facing call (one frame, N GPUs) ----
+class DistributedReconstructor:
+    """`reconstruct_surface` for ONE particle cloud spread over the ranks of a process group (one process per GPU).
+
+    Every rank passes the particles it holds -- any split of the cloud into contiguous index ranges in rank order (the order matters
+    for bit-identical results: the reference sums in ascending particle index); empty parts are fine.  The call is collective.  Rank 0
+    gets the assembled mesh (vertices, triangles, SPH normals when `sph_normals`), identical to the single-GPU result; the other ranks
+    get None.  Keep the object for a frame sequence: the slab plan settles after a few frames and the buffers are reused.
+
+    The reference has no counterpart (it parallelises over subdomains with rayon inside one process, dense_subdomains.rs:521-526);
+    parameters are those of `pysplashsurf.reconstruct_surface`.  A particle AABB (`aabb_min` / `aabb_max`) defines the grid like in the
+    reference (lib.rs:476-516) and filters every rank's particles before the exchange; the mesh post-processing of
+    `reconstruction_pipeline` is a single-GPU step."""
+
+    def __init__(self, *, sph_normals: bool = False, group=None, device=None, protocol: str = "stats", local_rank: Optional[int] = None, **params):
+        import os
+        import splashsurf_b200 as ss
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised: launch one process per GPU (torchrun) and call init_process_group first")
+        self._ss, self._kw = ss, dict(params)
+        self._aabb = None
+        if params.get("aabb_min") is not None and params.get("aabb_max") is not None:
+            self._aabb = (np.asarray(params["aabb_min"], np.float64).astype(np.float32), np.asarray(params["aabb_max"], np.float64).astype(np.float32))
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        lr = int(os.environ.get("LOCAL_RANK", "0")) if local_rank is None else int(local_rank)
+        self.ctx = ss.Context(lr if device is None else 0)
+        self.sph_normals = bool(sph_normals)
+        if self.sph_normals:
+            ss._check(self.ctx._L, self.ctx._L.ss_context_set_compute_sph_normals(self.ctx._h, 1))
+        no_box = {k: v for k, v in params.items() if k not in ("aabb_min", "aabb_max")}
+        self.runner = Runner(self.ctx, ss.make_params(**no_box), self.world, self.rank, lr, group=group, device=device, protocol=protocol)
+        self.runner.ctx_normals = self.sph_normals
+        if self._aabb is not None:
+            self.runner.grid_params = ss.make_params(**params)
+
+    def __call__(self, particles_local: np.ndarray):
+        ss = self._ss
+        p = np.ascontiguousarray(particles_local, dtype=np.float32).reshape(-1, 3)
+        if self.world == 1:
+            r = ss.reconstruct_surface(p, context=self.ctx, sph_normals=self.sph_normals, **self._kw)
+            return ss.MeshWithData(r.mesh, {"normals": r.normals} if self.sph_normals and r.normals is not None else {}, {})
+        if self._aabb is not None:                    # lib.rs:369-406: particles outside the half-open box take no part
+            p = np.ascontiguousarray(p[np.all(p >= self._aabb[0], axis=1) & np.all(p < self._aabb[1], axis=1)])
+        x = torch.from_numpy(p)
+        if self.runner.device.type == "cuda":
+            x = x.pin_memory()
+        out = self.runner.step(x, copy_out=True)
+        if self.rank != 0:
+            return None
+        v, t = self.runner.gathered_mesh(out["nv_global"], out["nt_global"])
+        attrs = {}
+        n = self.runner.gathered_normals()
+        if n is not None:
+            attrs["normals"] = n
+        return ss.MeshWithData(ss.TriMesh3d(v, t.view(np.uint32).astype(np.uint64)), attrs, {})
+
+    def close(self):
+        self.runner.close()
+        self.ctx.close()

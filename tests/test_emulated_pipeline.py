@@ -422,6 +422,62 @@ def test_emulated_runner_over_gloo(tmp_path, oracle_mod, world, case):
         assert all(c == seen[4] for c in seen[4:]) and seen[4] in seen[:4], seen   # settled on one of the explored plans
 
 
+CLI_PARTITION_WORKER = r'''
+import ctypes as C, os, sys
+sys.path.insert(0, os.environ["SS_ROOT"])
+import splashsurf_b200 as ss
+ss._LIB = ss._bind(C.CDLL(os.environ["SS_EMUL_SO"]))          # the CUDA sources on the CPU executor (tests only)
+from splashsurf_b200 import __main__ as cli
+rc = cli.main(sys.argv[1:])
+import torch.distributed as dist
+if dist.is_initialized():
+    dist.destroy_process_group()
+sys.exit(rc)
+'''
+
+
+def test_emulated_cli_partitioned_frames_over_gloo(emu, tmp_path):
+    """`python -m splashsurf_b200 reconstruct ... --partition=on` under torchrun: every frame of a sequence reconstructed by two processes
+    together (splashsurf_b200.distributed.DistributedReconstructor: slab partition, halo exchange, mesh assembled on rank 0) -- the files
+    hold the same mesh as the single-process CLI writes (same vertices bit for bit, same triangles; only the numbering differs)."""
+    import sys
+    from splashsurf_b200 import io, synthetic as syn, __main__ as cli
+    frames = tmp_path / "f"
+    frames.mkdir()
+    for i in (1, 2):
+        io.write_particles(str(frames / f"dam_{i}.bgeo"), syn.dam_break((10, 6, 6), (14, 2, 6), 0.025, 600 + i))
+    args = ["reconstruct", str(frames / "dam_{}.bgeo"), "-r=0.025", "-l=2.0", "-c=0.75", "--subdomain-cubes", "16", "--particle-aabb-min", "-1", "-1", "-1",
+            "--particle-aabb-max", "0.55", "2", "2", "-q"]
+    assert cli.main(args + ["--output-dir", str(tmp_path / "one")]) == 0
+    script = tmp_path / "worker.py"
+    script.write_text(CLI_PARTITION_WORKER)
+    env = dict(os.environ, SS_ROOT=ROOT, SS_EMUL_SO=build_emulated_library(), SS_EMUL_THREADS="3", OMP_NUM_THREADS="1", SS_DIST_BACKEND="gloo",
+               SS_RUNNER_DEVICE="cpu")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port",
+           str(free_port()), str(script), *args, "--partition=on", "--output-dir", str(tmp_path / "two")]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert sorted(os.listdir(tmp_path / "two")) == sorted(os.listdir(tmp_path / "one")) == ["dam_surface_1.vtk", "dam_surface_2.vtk"]
+    for f in ("dam_surface_1.vtk", "dam_surface_2.vtk"):
+        v1, t1 = io.read_vtk_mesh(str(tmp_path / "one" / f))[:2]
+        v2, t2 = io.read_vtk_mesh(str(tmp_path / "two" / f))[:2]
+        assert len(v1) == len(v2) > 1000 and len(t1) == len(t2)
+        o1, o2 = np.lexsort(v1.T[::-1]), np.lexsort(v2.T[::-1])
+        assert np.array_equal(v1[o1].view(np.uint32), v2[o2].view(np.uint32))                   # the same vertices, bit for bit
+        r1, r2 = np.empty(len(v1), np.int64), np.empty(len(v2), np.int64)
+        r1[o1], r2[o2] = np.arange(len(v1)), np.arange(len(v2))
+
+        def canon(t, rk):
+            t = rk[t.astype(np.int64)]
+            k = np.argmin(t, axis=1)
+            t = np.stack([np.roll(row, -s) for row, s in zip(t, k)]) if len(t) else t
+            return t[np.lexsort(t.T[::-1])]
+        assert np.array_equal(canon(t1, r1), canon(t2, r2))
+    # post-processing is a single-GPU step: refused with a clear message
+    r = subprocess.run(cmd + ["--mesh-smoothing-iters=2"], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "--partition=on reconstructs without mesh post-processing" in r.stderr
+
+
 FAIL_WORKER = r'''
 import ctypes as C, json, os, sys
 import numpy as np, torch, torch.distributed as dist, datetime
