@@ -285,6 +285,20 @@ int ss_surface_compute_normals_f32(ss_surface *s, int sph);
 /* par_laplacian_smoothing_normals_inplace (postprocessing.rs:56-97) on the surface's normals. */
 int ss_surface_smooth_normals_f32(ss_surface *s, uint32_t iterations);
 
+/* ---- splashsurf_lib::sph_interpolation::SphInterpolator at arbitrary points (sph_interpolation.rs:22-258; pysplashsurf.SphInterpolator).
+ * ss_sph_interpolator_create_f32 = SphInterpolator::new (:40-80): particle positions (n x 3), their densities (n), the particle rest
+ * mass and the compact support radius; host or device pointers.  The handle is a surface without a mesh (free it with ss_surface_free);
+ * its particle bins live in the context's scratch, so -- like the [bins] entries above -- it must be used before the next reconstruction or
+ * interpolator on the same context (SS_ERR_INVALID_PARAMETER otherwise).  Sums run in bin order, not in the reference's R-tree order:
+ * results agree to f32 round-off. */
+int ss_sph_interpolator_create_f32(ss_context *ctx, const float *xyz, uint64_t n, const float *densities, float particle_rest_mass,
+                                   float compact_support_radius, ss_surface **out);
+/* interpolate_scalar_quantity / interpolate_vector_quantity (:141-258): values [n * dim] (dim = 1 or 3), points [m * 3], out [m * dim]. */
+int ss_sph_interpolate_quantity_at_f32(ss_surface *interpolator, const float *values, uint32_t dim, const float *points, uint64_t m,
+                                       int first_order_correction, float *out);
+/* interpolate_normals (:82-133): unit SPH normals at the points, out [m * 3] (NaN where no particle lies within the support). */
+int ss_sph_interpolate_normals_at_f32(ss_surface *interpolator, const float *points, uint64_t m, float *out);
+
 /* A surface around a caller-supplied mesh (verts nv x 3 f32, tris nt x 3 u32; host or device pointers), so that the mesh-only
  * entries (laplacian smoothing with explicit / unit weights, area-weighted normals, normal smoothing, connectivity) serve the
  * reference's free functions of postprocessing.rs / mesh.rs on any mesh.  No particles: the [bins] entries are rejected. */

@@ -149,6 +149,9 @@ def _bind(L):
     L.ss_surface_interpolate_quantity_f32.argtypes = [vp, vp, C.c_uint32, C.c_int, vp]
     L.ss_surface_compute_smoothing_weights_f32.argtypes = [vp, C.c_float, vp, vp]
     L.ss_surface_laplacian_smoothing_f32.argtypes = [vp, C.c_uint32, C.c_float, vp]
+    L.ss_sph_interpolator_create_f32.argtypes = [vp, vp, C.c_uint64, vp, C.c_float, C.c_float, C.POINTER(vp)]
+    L.ss_sph_interpolate_quantity_at_f32.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint64, C.c_int, vp]
+    L.ss_sph_interpolate_normals_at_f32.argtypes = [vp, vp, C.c_uint64, vp]
     L.ss_surface_compute_normals_f32.argtypes = [vp, C.c_int]
     L.ss_surface_smooth_normals_f32.argtypes = [vp, C.c_uint32]
     L.ss_surface_vertex_connectivity.argtypes = [vp, vp, vp, C.POINTER(u64)]
@@ -654,6 +657,81 @@ class Context:
         t = _Timings()
         _check(self._L, self._L.ss_surface_timings(s, C.byref(t)))
         return {k: getattr(t, k) for k, _ in _Timings._fields_}
+
+
+class SphInterpolator:
+    """``pysplashsurf.SphInterpolator`` (pysplashsurf/src/sph_interpolation.rs:25-260; splashsurf_lib sph_interpolation.rs:22-258) on the
+    GPU: interpolation of per-particle quantities and of surface normals to arbitrary points with the cubic spline kernel.
+
+    ``SphInterpolator(particle_positions (N, 3) f32, particle_densities (N,) f32, particle_rest_mass, compact_support_radius)``.
+    The particle bins stay on the device inside a context of their own for the lifetime of the object (pass ``context=`` to share one:
+    the interpolator is then only valid until the next reconstruction on that context).  Sums run in bin order instead of the reference's
+    R-tree order: results agree with the reference to f32 round-off."""
+
+    def __init__(self, particle_positions, particle_densities, particle_rest_mass: float, compact_support_radius: float, *, context: Optional["Context"] = None):
+        p, rho = np.asarray(particle_positions), np.asarray(particle_densities)
+        if p.dtype != np.float32 or rho.dtype != np.float32:
+            raise TypeError("unsupported scalar type: the device path interpolates float32 data only")
+        if p.ndim != 2 or p.shape[1] != 3 or rho.shape != (len(p),):
+            raise ValueError("particle_positions must have shape (N, 3) and particle_densities shape (N,)")
+        self._own = context is None
+        self._ctx = Context() if context is None else context
+        self._n = len(p)
+        self._s = C.c_void_p()
+        p, rho = np.ascontiguousarray(p), np.ascontiguousarray(rho)
+        L = self._ctx._L
+        try:
+            _check(L, L.ss_sph_interpolator_create_f32(self._ctx._h, p.ctypes.data if len(p) else None, len(p), rho.ctypes.data if len(p) else None,
+                                                       C.c_float(float(particle_rest_mass)), C.c_float(float(compact_support_radius)), C.byref(self._s)))
+        except Exception:
+            if self._own:
+                self._ctx.close()
+            raise
+
+    @staticmethod
+    def _points(interpolation_points) -> np.ndarray:
+        x = np.asarray(interpolation_points)
+        if x.dtype != np.float32:
+            raise TypeError("unsupported scalar type: the device path interpolates float32 data only")
+        if x.ndim != 2 or x.shape[1] != 3:
+            raise ValueError("interpolation_points must have shape (M, 3)")
+        return np.ascontiguousarray(x)
+
+    def interpolate_quantity(self, particle_quantity, interpolation_points, *, first_order_correction: bool = False) -> np.ndarray:
+        """Interpolates a scalar (N,) or vectorial (N, 3) per-particle quantity to the given points: (M,) or (M, 3)."""
+        q, x = np.asarray(particle_quantity), self._points(interpolation_points)
+        if q.dtype != np.float32:
+            raise TypeError("unsupported scalar type: the device path interpolates float32 data only")
+        if not ((q.ndim == 1 or (q.ndim == 2 and q.shape[1] == 3)) and len(q) == self._n):
+            raise ValueError("particle_quantity must have shape (N,) or (N, 3) with one entry per particle")
+        dim = 1 if q.ndim == 1 else 3
+        q = np.ascontiguousarray(q)
+        out = np.empty((len(x),) if dim == 1 else (len(x), 3), dtype=np.float32)
+        L = self._ctx._L
+        _check(L, L.ss_sph_interpolate_quantity_at_f32(self._s, q.ctypes.data if self._n else None, dim, x.ctypes.data if len(x) else None, len(x),
+                                                       int(bool(first_order_correction)), out.ctypes.data if len(x) else None))
+        return out
+
+    def interpolate_normals(self, interpolation_points) -> np.ndarray:
+        """Surface normals (normalised SPH gradient of the indicator function) at the given points: (M, 3)."""
+        x = self._points(interpolation_points)
+        out = np.empty((len(x), 3), dtype=np.float32)
+        L = self._ctx._L
+        _check(L, L.ss_sph_interpolate_normals_at_f32(self._s, x.ctypes.data if len(x) else None, len(x), out.ctypes.data if len(x) else None))
+        return out
+
+    def close(self):
+        if getattr(self, "_s", None):
+            self._ctx._L.ss_surface_free(self._s)
+            self._s = None
+            if self._own:
+                self._ctx.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 _DEFAULT_CTX: dict = {}

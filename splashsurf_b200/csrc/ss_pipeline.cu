@@ -523,6 +523,9 @@ struct Partition {
     int stop_after_decomposition = 0;   // only report the local maximum (out->max_particles)
     uint64_t (*max_reduce)(uint64_t local_max, void *user) = nullptr;   // all-reduce(MAX) of the local maximum across ranks
     void *max_reduce_user = nullptr;
+    // SphInterpolator entry (ss_sph_interpolator_create_f32): densities supplied by the caller; stop after the particle bins are built
+    const float *given_rho = nullptr;
+    float given_mass = 0.0f;
 };
 
 // SPH densities (and optional CSR neighbour lists) of the filtered particles: per-subdomain cell lists on the h-lattice with
@@ -1048,6 +1051,21 @@ static int run_subdomain_grid(ss_context *c, const Prepared &PP, const ss_params
     CK(cudaMemcpyAsync(c->sub_owned.p, h_owned.data(), nsub, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(c->sub_sparse.p, out->sub_sparse.data(), nsub, cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(c->ev[3], st));
+
+    if (part.given_rho) {
+        // SphInterpolator::new (sph_interpolation.rs:40-80): the caller's densities and the particle bins the queries of ss_post.cuh walk;
+        // no density pass, no level set, no mesh
+        c->err.ensure(4);
+        CK(cudaMemsetAsync(c->err.p, 0, 4, st));
+        CK(cudaMemcpyAsync(d_rho, part.given_rho, (size_t)n * 4, cudaMemcpyDefault, st));
+        CK(cudaEventRecord(c->ev[4], st));
+        rc = stage_binning(c, D, d_xyz, d_rho, M, nsub, false);
+        if (rc) return rc;
+        c->post.D = D; c->post.nsub = nsub; c->post.M = M; c->post.partitioned = 0; c->post.sphere_mass = part.given_mass; c->post.valid = 1;
+        for (int e = 6; e <= 9; ++e) CK(cudaEventRecord(c->ev[e], st));
+        CK(cudaStreamSynchronize(st));
+        return SS_OK;
+    }
 
     // ---- densities, then the splat bins
     rc = stage_densities(c, D, d_xyz, n, M, nsub, g_ns_cells, global_mode, want_nbrs, out, d_rho);

@@ -108,7 +108,10 @@ k_pp_interpolate(SsDev P, SsQuery Q, const float *__restrict__ pts, uint32_t npt
         for (int k = 0; k < DIM; ++k) acc[k] += values[(size_t)j * DIM + k] * w;
         corr += w;
     });
-    const float f = correction ? 1.0f / corr : 1.0f;           // no particle in range: 0 * inf = NaN, like the reference
+    // sph_interpolation.rs:252-254: enable * (1 / correction) + (1 - enable).  No particle in range: 0 * inf = NaN with or without the
+    // correction, like in the reference
+    const float en = correction ? 1.0f : 0.0f;
+    const float f = en * (1.0f / corr) + (1.0f - en);
 #pragma unroll
     for (int k = 0; k < DIM; ++k) out[(size_t)v * DIM + k] = acc[k] * f;
 }
@@ -337,6 +340,130 @@ extern "C" int ss_surface_interpolate_quantity_f32(ss_surface *s, const float *v
         if (dim == 1) LAUNCH(c, k_pp_interpolate<1>, nblk(nv, 128), 128, c->post.D, Q, s->verts.as<float>(), nv, c->post.vals.as<float>(), first_order_correction, c->post.out.as<float>());
         else LAUNCH(c, k_pp_interpolate<3>, nblk(nv, 128), 128, c->post.D, Q, s->verts.as<float>(), nv, c->post.vals.as<float>(), first_order_correction, c->post.out.as<float>());
         CK(cudaMemcpyAsync(out, c->post.out.p, (size_t)nv * dim * 4, cudaMemcpyDefault, st));
+        CK(cudaStreamSynchronize(st));
+        return SS_OK;
+    } PP_CATCH
+}
+
+// ------------------------------------------------------------------ SphInterpolator at arbitrary points ----
+// splashsurf_lib::sph_interpolation::SphInterpolator (sph_interpolation.rs:22-258; Python class pysplashsurf.SphInterpolator): particles,
+// their densities, the rest mass and the compact support radius define the interpolator; quantities and normals are then evaluated at any
+// set of points.  The handle is a surface without a mesh whose particle bins live in the context's scratch: like the [bins] entries above it
+// has to be used before the next reconstruction (or interpolator) on the same context.
+extern "C" int ss_sph_interpolator_create_f32(ss_context *c, const float *xyz, uint64_t n, const float *densities, float particle_rest_mass,
+                                              float compact_support_radius, ss_surface **out) {
+    if (!c || !out) return ss_fail(SS_ERR_INVALID_PARAMETER, "NULL argument");
+    *out = nullptr;
+    if (n && (!xyz || !densities)) return ss_fail(SS_ERR_INVALID_PARAMETER, "xyz / densities is NULL");
+    if (!(compact_support_radius > 0.0f) || !std::isfinite(compact_support_radius)) return ss_fail(SS_ERR_INVALID_PARAMETER, "compact_support_radius must be positive");
+    // the bins only have to cover a ball of radius h around any query point: cubes of h / 2, subdomain tiles of 64 cubes
+    ss_params_f32 p{};
+    p.particle_radius = compact_support_radius * 0.25f; p.rest_density = 1000.0f; p.compact_support_radius = compact_support_radius;
+    p.cube_size = compact_support_radius * 0.5f; p.iso_surface_threshold = 0.6f; p.enable_multi_threading = 1; p.enable_simd = 1;
+    p.spatial_decomposition = 1; p.subdomain_num_cubes_per_dim = 64; p.auto_disable = 0;
+    ss_surface *s = nullptr;
+    try {
+        CK(cudaSetDevice(c->device));
+        s = new ss_surface();
+        s->device = c->device; s->n_in = n;
+        c->launches = 0;
+        Prepared P;
+        int rc = prepare_particles(c, xyz, n, &p, P, nullptr);
+        if (rc) { ss_surface_free(s); return rc; }
+        s->n = P.n; s->grid = P.grid; s->used_decomposition = 1;
+        Partition opt;
+        opt.given_rho = densities; opt.given_mass = particle_rest_mass;
+        rc = run_subdomain_grid(c, P, &p, s, opt, /*global_mode=*/false);
+        if (rc) { ss_surface_free(s); return rc; }
+        s->tm.kernel_launches = c->launches;
+        *out = s;
+        return SS_OK;
+    } catch (const SsCudaError &err) {
+        if (s) ss_surface_free(s);
+        cudaGetLastError();
+        char buf[512];
+        snprintf(buf, sizeof(buf), "%s failed at %s:%d: %s", err.what, err.file, err.line, cudaGetErrorString(err.e));
+        return ss_fail(err.e == cudaErrorMemoryAllocation ? SS_ERR_OUT_OF_MEMORY : SS_ERR_CUDA, buf);
+    } catch (const std::bad_alloc &) {
+        if (s) ss_surface_free(s);
+        return ss_fail(SS_ERR_OUT_OF_MEMORY, "host allocation failed");
+    }
+}
+
+__global__ void k_pp_fill(uint32_t n, float value, float *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = value;
+}
+
+// context of an interpolator handle whose bins are still in place (nullptr + error otherwise); *empty: no particle at all
+static ss_context *pp_interpolator_context(ss_surface *s, bool *empty, int *rc) {
+    *rc = SS_OK; *empty = false;
+    if (!s) { *rc = ss_fail(SS_ERR_INVALID_PARAMETER, "NULL interpolator"); return nullptr; }
+    ss_context *c = s->owner;
+    {
+        std::lock_guard<std::mutex> lk(g_ctx_mutex);
+        if (!c || !g_live_contexts.count(c)) { *rc = ss_fail(SS_ERR_INVALID_PARAMETER, "the context of this interpolator was destroyed"); return nullptr; }
+    }
+    if (c->frame != s->frame) {
+        *rc = ss_fail(SS_ERR_INVALID_PARAMETER, "the particle bins of this interpolator are gone: use it before the next reconstruction / interpolator on its context");
+        return nullptr;
+    }
+    *empty = !c->post.valid;                         // no particle (or none inside the grid): every sum is empty
+    return c;
+}
+
+// SphInterpolator::interpolate_scalar_quantity / interpolate_vector_quantity (sph_interpolation.rs:141-258) at `m` points.
+// values: [num_particles * dim], points: [m * 3], out: [m * dim]; host or device pointers.
+extern "C" int ss_sph_interpolate_quantity_at_f32(ss_surface *s, const float *values, uint32_t dim, const float *points, uint64_t m,
+                                                  int first_order_correction, float *out) {
+    int rc; bool empty; ss_context *c = pp_interpolator_context(s, &empty, &rc);
+    if (!c) return rc;
+    if ((dim != 1 && dim != 3) || (m && (!points || !out)) || (s->n && !values)) return ss_fail(SS_ERR_INVALID_PARAMETER, "NULL argument or dim not 1 / 3");
+    if (m >= 0x7fffffffull) return ss_fail(SS_ERR_INDEX_TOO_SMALL, "too many interpolation points for one call");
+    if (!m) return SS_OK;
+    try {
+        CK(cudaSetDevice(c->device));
+        cudaStream_t st = c->stream;
+        const uint32_t np = (uint32_t)m;
+        c->post.out.ensure((size_t)np * dim * 4);
+        if (empty) {
+            // no particle at all: every point sees an empty sum, and the reference's correction factor enable * (1 / 0) + (1 - enable) is
+            // NaN whether the correction is enabled or not (sph_interpolation.rs:252-254)
+            LAUNCH(c, k_pp_fill, nblk((uint64_t)np * dim, 256), 256, np * dim, nanf(""), c->post.out.as<float>());
+        } else {
+            c->post.vals.ensure(std::max<size_t>(s->n, 1) * dim * 4); c->post.tmpv.ensure((size_t)np * 12);
+            CK(cudaMemcpyAsync(c->post.vals.p, values, (size_t)s->n * dim * 4, cudaMemcpyDefault, st));
+            CK(cudaMemcpyAsync(c->post.tmpv.p, points, (size_t)np * 12, cudaMemcpyDefault, st));
+            const SsQuery Q = pp_query(c, s);
+            if (dim == 1) LAUNCH(c, k_pp_interpolate<1>, nblk(np, 128), 128, c->post.D, Q, c->post.tmpv.as<float>(), np, c->post.vals.as<float>(), first_order_correction, c->post.out.as<float>());
+            else LAUNCH(c, k_pp_interpolate<3>, nblk(np, 128), 128, c->post.D, Q, c->post.tmpv.as<float>(), np, c->post.vals.as<float>(), first_order_correction, c->post.out.as<float>());
+        }
+        CK(cudaMemcpyAsync(out, c->post.out.p, (size_t)np * dim * 4, cudaMemcpyDefault, st));
+        CK(cudaStreamSynchronize(st));
+        return SS_OK;
+    } PP_CATCH
+}
+
+// SphInterpolator::interpolate_normals (sph_interpolation.rs:82-133) at `m` points: normalised SPH gradient of the indicator function
+// (NaN where no particle is within the support, like the reference's normalisation of a zero vector).
+extern "C" int ss_sph_interpolate_normals_at_f32(ss_surface *s, const float *points, uint64_t m, float *out) {
+    int rc; bool empty; ss_context *c = pp_interpolator_context(s, &empty, &rc);
+    if (!c) return rc;
+    if (m && (!points || !out)) return ss_fail(SS_ERR_INVALID_PARAMETER, "NULL argument");
+    if (m >= 0x7fffffffull) return ss_fail(SS_ERR_INDEX_TOO_SMALL, "too many interpolation points for one call");
+    if (!m) return SS_OK;
+    try {
+        CK(cudaSetDevice(c->device));
+        cudaStream_t st = c->stream;
+        const uint32_t np = (uint32_t)m;
+        c->post.out.ensure((size_t)np * 12);
+        if (empty) LAUNCH(c, k_pp_fill, nblk((uint64_t)np * 3, 256), 256, np * 3, nanf(""), c->post.out.as<float>());
+        else {
+            c->post.tmpv.ensure((size_t)np * 12);
+            CK(cudaMemcpyAsync(c->post.tmpv.p, points, (size_t)np * 12, cudaMemcpyDefault, st));
+            LAUNCH(c, k_pp_sph_normals, nblk(np, 128), 128, c->post.D, pp_query(c, s), c->post.tmpv.as<float>(), np, c->post.out.as<float>());
+        }
+        CK(cudaMemcpyAsync(out, c->post.out.p, (size_t)np * 12, cudaMemcpyDefault, st));
         CK(cudaStreamSynchronize(st));
         return SS_OK;
     } PP_CATCH

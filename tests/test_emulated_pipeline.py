@@ -562,6 +562,12 @@ def test_emulated_large_result_copies_take_the_staged_path(emu, oracle_mod):
         ctx.close()
 
 
+def test_emulated_sph_interpolator_at_arbitrary_points(emu, oracle_mod):
+    """pysplashsurf.SphInterpolator on the CPU executor: same checks as the GPU-marked test (oracle restatements + the wheel's class)."""
+    from test_zzzz_reference_datasets import check_sph_interpolator
+    check_sph_interpolator(emu, oracle_mod)
+
+
 def test_emulated_cli_with_postprocessing(emu, tmp_path):
     """`python -m splashsurf_b200 reconstruct` with the reference CLI's post-processing switches (clean-up, decimation, smoothing, normals,
     mesh checks, quads) -- control flow of the thin harness on the CPU executor."""

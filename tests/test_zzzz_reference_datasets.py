@@ -103,3 +103,57 @@ def test_oracle_neighborhood_hand_cases(oracle_mod):
 @pytest.mark.gpu
 def test_cuda_neighborhood_hand_cases(ss):
     _check_ns(lambda p, **kw: ss.reconstruct_surface(p, global_neighborhood_list=True, **kw), lambda g, n: [g.particle_neighbors[i] for i in range(n)])
+
+
+# ---- SphInterpolator at arbitrary points (sph_interpolation.rs:22-258; pysplashsurf.SphInterpolator): the oracle's restatements (pinned to
+# the wheel, tests/test_oracle_postprocess.py) and, where it is unpacked, the wheel's own class; tolerance 2e-5 (f32 sums in another order)
+def check_sph_interpolator(ss, oracle_mod):
+    from oracle import postprocess as opp
+    from splashsurf_b200 import synthetic as syn
+    p = syn.splash((12, 12, 12), 3, 0.025, 77)
+    rho = oracle_mod.reconstruct(p, particle_radius=0.025, smoothing_length=2.0, cube_size=0.75)["particle_densities"]
+    h, m = np.float32(0.1), float(oracle_mod.sph_rest_mass(0.025))
+    rng = np.random.default_rng(1)
+    near = p[::7] + rng.normal(scale=0.02, size=(len(p[::7]), 3)).astype(np.float32)
+    x = np.concatenate([near, np.float32([[50, 50, 50], [-3, 0, 0]])]).astype(np.float32)        # the last two see no particle
+    sc, ve = rng.normal(size=len(p)).astype(np.float32), rng.normal(size=(len(p), 3)).astype(np.float32)
+    ref = oracle_mod.reference().SphInterpolator(p, rho, m, float(h)) if oracle_mod.reference_available() else None
+    it = ss.SphInterpolator(p, rho, m, float(h))
+    for corr in (False, True):
+        for q in (sc, ve):
+            g = it.interpolate_quantity(q, x, first_order_correction=corr)
+            o = opp.interpolate_quantity(p, rho, m, h, q, x, first_order_correction=corr)
+            assert g.shape == o.shape and g.dtype == np.float32
+            assert np.isnan(g[-2:]).all() and np.isfinite(g[:-2]).all()              # 0 * inf + ... = NaN without neighbours (:252-254)
+            assert np.abs(g[:-2] - o[:-2]).max() <= 2e-5 * max(1.0, float(np.abs(o[:-2]).max()))
+            if ref is not None:
+                r = np.asarray(ref.interpolate_quantity(q, x, first_order_correction=corr))
+                assert np.array_equal(np.isnan(r), np.isnan(g)) and np.abs(g[:-2] - r[:-2]).max() <= 2e-5 * max(1.0, float(np.abs(r[:-2]).max()))
+    g = it.interpolate_normals(x)
+    o = oracle_mod.sph_normals(p, rho, x[:-2], compact_support_radius=h, particle_rest_mass=m)
+    assert np.isnan(g[-2:]).all() and np.abs(np.linalg.norm(g[:-2], axis=1) - 1.0).max() < 1e-5 and np.abs(g[:-2] - o).max() <= 2e-5
+    if ref is not None:
+        assert np.abs(g[:-2] - np.asarray(ref.interpolate_normals(x))[:-2]).max() <= 2e-5
+    # no particles at all; argument checks; sharing a context: the bins are gone after the next reconstruction on it
+    e = ss.SphInterpolator(np.zeros((0, 3), np.float32), np.zeros(0, np.float32), m, float(h))
+    assert np.isnan(e.interpolate_quantity(np.zeros(0, np.float32), x[:3])).all() and np.isnan(e.interpolate_normals(x[:3])).all()
+    assert it.interpolate_normals(np.zeros((0, 3), np.float32)).shape == (0, 3)
+    with pytest.raises(ValueError):
+        it.interpolate_quantity(sc[:-1], x)
+    with pytest.raises(TypeError):
+        it.interpolate_normals(x.astype(np.float64))
+    ctx = ss.Context()
+    shared = ss.SphInterpolator(p, rho, m, float(h), context=ctx)
+    assert np.array_equal(shared.interpolate_normals(x[:5]), g[:5])
+    ss.reconstruct_surface(p[:200], particle_radius=0.025, smoothing_length=2.0, cube_size=1.0, context=ctx)
+    with pytest.raises(ss.SplashsurfError, match="particle bins of this interpolator are gone"):
+        shared.interpolate_normals(x[:5])
+    assert np.array_equal(it.interpolate_normals(x[:5]), g[:5])                        # its own context: still valid
+    for o_ in (shared, it, e):
+        o_.close()
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_cuda_sph_interpolator_at_arbitrary_points(ss, oracle_mod):
+    check_sph_interpolator(ss, oracle_mod)
