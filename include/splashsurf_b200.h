@@ -299,6 +299,15 @@ int ss_sph_interpolate_quantity_at_f32(ss_surface *interpolator, const float *va
 /* interpolate_normals (:82-133): unit SPH normals at the points, out [m * 3] (NaN where no particle lies within the support). */
 int ss_sph_interpolate_normals_at_f32(ss_surface *interpolator, const float *points, uint64_t m, float *out);
 
+/* splashsurf_lib::neighborhood_search::neighborhood_search_spatial_hashing_parallel (neighborhood_search.rs:444-588; Python function of the
+ * same name): for every particle the indices of all OTHER particles with squared distance < search_radius^2, found on the cell lattice of
+ * UniformGrid::from_aabb(domain, search_radius).  The result is a surface without a mesh: read the CSR lists with
+ * ss_surface_num_neighbors / ss_surface_copy_neighbor_lists, free it with ss_surface_free.  The order inside a list is this library's
+ * (cells x-major, ascending index inside a cell); the reference's depends on its hash map.  A particle outside of the domain's lattice is
+ * SS_ERR_INVALID_PARAMETER (reference: panic). */
+int ss_neighborhood_search_f32(ss_context *ctx, const float *xyz, uint64_t n, const float domain_min[3], const float domain_max[3],
+                               float search_radius, ss_surface **out);
+
 /* A surface around a caller-supplied mesh (verts nv x 3 f32, tris nt x 3 u32; host or device pointers), so that the mesh-only
  * entries (laplacian smoothing with explicit / unit weights, area-weighted normals, normal smoothing, connectivity) serve the
  * reference's free functions of postprocessing.rs / mesh.rs on any mesh.  No particles: the [bins] entries are rejected. */

@@ -149,6 +149,7 @@ def _bind(L):
     L.ss_surface_interpolate_quantity_f32.argtypes = [vp, vp, C.c_uint32, C.c_int, vp]
     L.ss_surface_compute_smoothing_weights_f32.argtypes = [vp, C.c_float, vp, vp]
     L.ss_surface_laplacian_smoothing_f32.argtypes = [vp, C.c_uint32, C.c_float, vp]
+    L.ss_neighborhood_search_f32.argtypes = [vp, vp, C.c_uint64, vp, vp, C.c_float, C.POINTER(vp)]
     L.ss_sph_interpolator_create_f32.argtypes = [vp, vp, C.c_uint64, vp, C.c_float, C.c_float, C.POINTER(vp)]
     L.ss_sph_interpolate_quantity_at_f32.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint64, C.c_int, vp]
     L.ss_sph_interpolate_normals_at_f32.argtypes = [vp, vp, C.c_uint64, vp]
@@ -657,6 +658,32 @@ class Context:
         t = _Timings()
         _check(self._L, self._L.ss_surface_timings(s, C.byref(t)))
         return {k: getattr(t, k) for k, _ in _Timings._fields_}
+
+
+def neighborhood_search_spatial_hashing_parallel(particle_positions, domain: "Aabb3d", search_radius: float, *, context: Optional["Context"] = None) -> "NeighborhoodLists":
+    """``pysplashsurf.neighborhood_search_spatial_hashing_parallel`` (neighborhood_search.rs:444-588) on the GPU: for every particle the
+    indices of all other particles closer than ``search_radius`` (strictly), as NeighborhoodLists.  ``domain`` is the AABB whose lattice
+    hashes the particles; a particle outside of it is an error (the reference panics).  The order inside a list is not specified by the
+    reference (hash-map order); here it is cell by cell, ascending index inside a cell."""
+    p = np.asarray(particle_positions)
+    if p.dtype != np.float32:
+        raise TypeError("unsupported scalar type: the device path searches float32 particles only")
+    if p.ndim != 2 or p.shape[1] != 3:
+        raise ValueError("particle_positions must have shape (N, 3)")
+    p = np.ascontiguousarray(p)
+    ctx = default_context() if context is None else context
+    L = ctx._L
+    lo = (C.c_float * 3)(*[float(np.float32(v)) for v in domain.min])
+    hi = (C.c_float * 3)(*[float(np.float32(v)) for v in domain.max])
+    s = C.c_void_p()
+    _check(L, L.ss_neighborhood_search_f32(ctx._h, p.ctypes.data if len(p) else None, len(p), lo, hi, C.c_float(float(search_radius)), C.byref(s)))
+    try:
+        off = np.empty(len(p) + 1, dtype=np.uint64)
+        idx = np.empty(L.ss_surface_num_neighbors(s), dtype=np.uint32)
+        _check(L, L.ss_surface_copy_neighbor_lists(s, off.ctypes.data, idx.ctypes.data if len(idx) else None))
+        return NeighborhoodLists(off, idx)
+    finally:
+        L.ss_surface_free(s)
 
 
 class SphInterpolator:

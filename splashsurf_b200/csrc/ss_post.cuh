@@ -469,6 +469,77 @@ extern "C" int ss_sph_interpolate_normals_at_f32(ss_surface *s, const float *poi
     } PP_CATCH
 }
 
+// ------------------------------------------------------------------ stand-alone neighbourhood search ----
+// splashsurf_lib::neighborhood_search::neighborhood_search_spatial_hashing_parallel (neighborhood_search.rs:444-588; the Python function of
+// the same name): per particle the indices of all other particles with squared distance < search_radius^2.  The global path's cell-list
+// stage does the work: cells of `search_radius` on the lattice of UniformGrid::from_aabb(domain, search_radius) (:172-173), 27 cells per
+// particle.  The lists come back through ss_surface_num_neighbors / ss_surface_copy_neighbor_lists (order inside a list: cell order, then
+// ascending index; the reference's order depends on its hash map).  A particle outside of the domain is an error (reference: panic).
+extern "C" int ss_neighborhood_search_f32(ss_context *c, const float *xyz, uint64_t n, const float domain_min[3], const float domain_max[3],
+                                          float search_radius, ss_surface **out) {
+    if (!c || !out || !domain_min || !domain_max) return ss_fail(SS_ERR_INVALID_PARAMETER, "NULL argument");
+    *out = nullptr;
+    if (n && !xyz) return ss_fail(SS_ERR_INVALID_PARAMETER, "xyz is NULL");
+    if (!(search_radius > 0.0f) || !std::isfinite(search_radius)) return ss_fail(SS_ERR_INVALID_PARAMETER, "search radius must be positive (reference: panic)");
+    HostGrid ns;
+    int rcn = grid_from_aabb(ns, domain_min, domain_max, search_radius);
+    if (rcn) return ss_fail(rcn, "failed to construct grid for neighborhood search: degenerate or inconsistent domain (reference: panic)");
+    const uint64_t cells = (uint64_t)ns.nc[0] * ns.nc[1] * ns.nc[2];
+    if (ns.nc[0] >= (1 << 20) || ns.nc[1] >= (1 << 20) || ns.nc[2] >= (1 << 20) || cells >= (1ull << 28))
+        return ss_fail(SS_ERR_INDEX_TOO_SMALL, "domain too large for the cell list of the neighbourhood search");
+    ss_params_f32 p{};
+    p.particle_radius = search_radius * 0.25f; p.rest_density = 1000.0f; p.compact_support_radius = search_radius; p.cube_size = search_radius;
+    p.iso_surface_threshold = 0.6f; p.enable_multi_threading = 1; p.enable_simd = 1;
+    ss_grid_f32 g{};                                    // only keeps prepare_particles from reducing a bounding box nobody needs
+    for (int d = 0; d < 3; ++d) { g.aabb_min[d] = ns.mn[d]; g.aabb_max[d] = ns.mx[d]; g.points_per_dim[d] = ns.np[d]; g.cells_per_dim[d] = ns.nc[d]; }
+    g.cell_size = search_radius;
+    ss_surface *s = nullptr;
+    try {
+        CK(cudaSetDevice(c->device));
+        s = new ss_surface();
+        s->device = c->device; s->n_in = n;
+        c->launches = 0;
+        Prepared P;
+        int rc = prepare_particles(c, xyz, n, &p, P, nullptr, &g);
+        if (rc) { ss_surface_free(s); return rc; }
+        s->n = P.n; s->grid = ns;
+        s->owner = c; c->post.valid = 0; s->frame = ++c->frame;
+        cudaStream_t st = c->stream;
+        s->rho = c->o_rho; c->o_rho = DevBuf();
+        s->rho.ensure(std::max<uint64_t>(n, 1) * 4);
+        s->nbr_off.ensure((n + 1) * 8);
+        if (n == 0) {
+            CK(cudaMemsetAsync(s->nbr_off.p, 0, 8, st));
+            CK(cudaStreamSynchronize(st));
+            s->has_neighbors = 1; s->n_neighbors = 0;
+            *out = s;
+            return SS_OK;
+        }
+        SsDev D{};
+        D.h = search_radius; D.h2 = fmulr(search_radius, search_radius); D.c = search_radius; D.rest_mass = 1.0f; D.gmode = 1;
+        fill_kernel_consts(D, search_radius);
+        for (int d = 0; d < 3; ++d) { D.g_ns_amin[d] = ns.mn[d]; D.g_ns_nc[d] = (int)ns.nc[d]; D.gmin[d] = ns.mn[d]; }
+        rc = stage_densities(c, D, P.d_xyz, n, 0, 0, cells, /*global_mode=*/true, /*want_nbrs=*/true, s, s->rho.as<float>());
+        if (rc) { ss_surface_free(s); return rc; }
+        int h_err = 0;
+        CK(cudaMemcpyAsync(&h_err, c->err.p, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (h_err) { ss_surface_free(s); return ss_fail(SS_ERR_INVALID_PARAMETER, "particle outside of the domain of the neighbourhood search (reference: panic)"); }
+        s->tm.kernel_launches = c->launches;
+        *out = s;
+        return SS_OK;
+    } catch (const SsCudaError &err) {
+        if (s) ss_surface_free(s);
+        cudaGetLastError();
+        char buf[512];
+        snprintf(buf, sizeof(buf), "%s failed at %s:%d: %s", err.what, err.file, err.line, cudaGetErrorString(err.e));
+        return ss_fail(err.e == cudaErrorMemoryAllocation ? SS_ERR_OUT_OF_MEMORY : SS_ERR_CUDA, buf);
+    } catch (const std::bad_alloc &) {
+        if (s) ss_surface_free(s);
+        return ss_fail(SS_ERR_OUT_OF_MEMORY, "host allocation failed");
+    }
+}
+
 // Smoothing weights of the mesh vertices (reconstruct.rs:1159-1258): distance-weighted neighbour count per particle,
 // SPH-interpolated (with correction) to the vertices, normalised and passed through the smooth-step.  The weights stay on
 // the device for ss_surface_laplacian_smoothing_f32; wnn_out / weights_out ([nv], optional) receive copies

@@ -568,6 +568,12 @@ def test_emulated_sph_interpolator_at_arbitrary_points(emu, oracle_mod):
     check_sph_interpolator(emu, oracle_mod)
 
 
+def test_emulated_neighborhood_search_stand_alone(emu, oracle_mod):
+    """pysplashsurf.neighborhood_search_spatial_hashing_parallel on the CPU executor: same checks as the GPU-marked test."""
+    from test_zzzz_reference_datasets import check_neighborhood_search
+    check_neighborhood_search(emu, oracle_mod)
+
+
 def test_emulated_cli_with_postprocessing(emu, tmp_path):
     """`python -m splashsurf_b200 reconstruct` with the reference CLI's post-processing switches (clean-up, decimation, smoothing, normals,
     mesh checks, quads) -- control flow of the thin harness on the CPU executor."""

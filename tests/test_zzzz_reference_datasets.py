@@ -157,3 +157,44 @@ def check_sph_interpolator(ss, oracle_mod):
 @pytest.mark.gpu
 def test_cuda_sph_interpolator_at_arbitrary_points(ss, oracle_mod):
     check_sph_interpolator(ss, oracle_mod)
+
+
+# ---- stand-alone neighbourhood search (neighborhood_search.rs:444-588; pysplashsurf/tests/test_basic.py:150-182): the reference's hand
+# cases, a random cloud against a k-d tree and against the wheel's function, the lists of the reconstruction itself
+def check_neighborhood_search(ss, oracle_mod):
+    from scipy.spatial import cKDTree
+    from splashsurf_b200 import synthetic as syn
+    for rows, expect in _ns_cases(0.3):
+        p = _ns_particles(rows, 0.3)
+        nl = ss.neighborhood_search_spatial_hashing_parallel(p, ss.Aabb3d(np.float32([-2, -2, -2]), np.float32([3, 3, 3])), float(np.float32(0.3)))
+        assert type(nl) is ss.NeighborhoodLists and [sorted(l) for l in nl.get_neighborhood_lists()] == expect
+    p = syn.splash((14, 14, 14), 3, 0.025, 91)
+    sr = float(np.float32(0.1))
+    rec = ss.reconstruct_surface(p, particle_radius=0.025, smoothing_length=2.0, cube_size=1.0, global_neighborhood_list=True)
+    nl = ss.neighborhood_search_spatial_hashing_parallel(p, rec.grid.aabb, sr)
+    got = [sorted(l) for l in nl.get_neighborhood_lists()]
+    assert len(got) == len(p) and got == [sorted(l) for l in rec.particle_neighbors.get_neighborhood_lists()]     # test_basic.py:150-182
+    d = p.astype(np.float64)
+    pairs = cKDTree(d).query_pairs(sr * 1.001, output_type="ndarray")
+    dx = p[pairs[:, 0]] - p[pairs[:, 1]]                                       # the reference's f32 test: |dx|^2 < r^2
+    keep = (dx[:, 0] * dx[:, 0] + dx[:, 1] * dx[:, 1] + dx[:, 2] * dx[:, 2]).astype(np.float32) < np.float32(sr) * np.float32(sr)
+    brute = [[] for _ in range(len(p))]
+    for a, b in pairs[keep]:
+        brute[a].append(int(b)); brute[b].append(int(a))
+    mism = [i for i in range(len(p)) if sorted(brute[i]) != got[i]]
+    # pairs whose squared distance rounds differently in another summation order sit exactly on the radius: none are expected in this cloud
+    assert not mism, mism[:5]
+    if oracle_mod.reference_available():
+        ps = oracle_mod.reference()
+        ref = ps.neighborhood_search_spatial_hashing_parallel(p, domain=ps.Aabb3d.from_min_max(rec.grid.aabb.min, rec.grid.aabb.max), search_radius=sr)
+        assert [sorted(l) for l in ref.get_neighborhood_lists()] == got
+    assert len(ss.neighborhood_search_spatial_hashing_parallel(np.zeros((0, 3), np.float32), rec.grid.aabb, sr)) == 0
+    with pytest.raises(ss.SplashsurfError, match="outside of the domain"):
+        ss.neighborhood_search_spatial_hashing_parallel(p, ss.Aabb3d(np.float32([0, 0, 0]), np.float32([0.2, 0.2, 0.2])), sr)
+    with pytest.raises(ss.SplashsurfError, match="search radius must be positive"):
+        ss.neighborhood_search_spatial_hashing_parallel(p, rec.grid.aabb, 0.0)
+
+
+@pytest.mark.gpu
+def test_cuda_neighborhood_search_stand_alone(ss, oracle_mod):
+    check_neighborhood_search(ss, oracle_mod)
