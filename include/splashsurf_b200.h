@@ -308,6 +308,15 @@ int ss_sph_interpolate_normals_at_f32(ss_surface *interpolator, const float *poi
 int ss_neighborhood_search_f32(ss_context *ctx, const float *xyz, uint64_t n, const float domain_min[3], const float domain_max[3],
                                float search_radius, ss_surface **out);
 
+/* marching_cubes::triangulate_density_map (marching_cubes.rs:61-127; Python: pysplashsurf.marching_cubes on a dense array) on level-set
+ * tiles the caller provides: `tiles` = ntiles x 65^3 floats (host or device), tile t holding the global points tile_ijk[3t..] * 64 .. + 64
+ * per axis (neighbouring tiles repeat their shared face planes), point (i, j, k) at grid_min + index * cube_size.  Inside / outside and
+ * the vertex interpolation follow the reference's global path (value > threshold is inside; vertices from the point >= threshold towards
+ * its neighbour below).  The mesh is welded across tiles; ss_surface_copy_vertex_edge_keys tells which grid edge a vertex lies on, so a
+ * caller that padded its array to whole tiles can drop the cells of the padding. */
+int ss_marching_cubes_tiles_f32(ss_context *ctx, const float *tiles, uint32_t ntiles, const int32_t *tile_ijk, const float grid_min[3],
+                                float cube_size, float iso_surface_threshold, ss_surface **out);
+
 /* A surface around a caller-supplied mesh (verts nv x 3 f32, tris nt x 3 u32; host or device pointers), so that the mesh-only
  * entries (laplacian smoothing with explicit / unit weights, area-weighted normals, normal smoothing, connectivity) serve the
  * reference's free functions of postprocessing.rs / mesh.rs on any mesh.  No particles: the [bins] entries are rejected. */

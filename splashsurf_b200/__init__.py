@@ -149,6 +149,7 @@ def _bind(L):
     L.ss_surface_interpolate_quantity_f32.argtypes = [vp, vp, C.c_uint32, C.c_int, vp]
     L.ss_surface_compute_smoothing_weights_f32.argtypes = [vp, C.c_float, vp, vp]
     L.ss_surface_laplacian_smoothing_f32.argtypes = [vp, C.c_uint32, C.c_float, vp]
+    L.ss_marching_cubes_tiles_f32.argtypes = [vp, vp, C.c_uint32, vp, vp, C.c_float, C.c_float, C.POINTER(vp)]
     L.ss_neighborhood_search_f32.argtypes = [vp, vp, C.c_uint64, vp, vp, C.c_float, C.POINTER(vp)]
     L.ss_sph_interpolator_create_f32.argtypes = [vp, vp, C.c_uint64, vp, C.c_float, C.c_float, C.POINTER(vp)]
     L.ss_sph_interpolate_quantity_at_f32.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint64, C.c_int, vp]
@@ -658,6 +659,67 @@ class Context:
         t = _Timings()
         _check(self._L, self._L.ss_surface_timings(s, C.byref(t)))
         return {k: getattr(t, k) for k, _ in _Timings._fields_}
+
+
+def marching_cubes(values, *, iso_surface_threshold: float, cube_size: float, translation=None, return_grid: bool = False,
+                   context: Optional["Context"] = None):
+    """``pysplashsurf.marching_cubes`` (pysplashsurf/src/marching_cubes.rs:108-177 -> marching_cubes::triangulate_density_map) on the GPU:
+    triangulates a dense 3-D float32 array of level-set values; point (i, j, k) sits at ``translation + (i, j, k) * cube_size``, values
+    above the threshold are inside (like a density).  Returns a TriMesh3d (and the UniformGrid with ``return_grid``).
+
+    The array is cut into the 65^3-point tiles of the reconstruction's marching-cubes kernels (tiles without a sign change are skipped);
+    where it does not fill whole tiles the border values are repeated, and the triangles of those padded cells -- every one of them has a
+    vertex on a grid edge outside of the array -- are dropped again."""
+    v = np.asarray(values)
+    if v.ndim != 3:
+        raise ValueError("values must be a 3D array")
+    if v.dtype != np.float32:
+        raise TypeError("unsupported scalar type: the device path triangulates float32 values only")
+    if min(v.shape) < 2:
+        raise ValueError("values needs at least two points per dimension (one cell)")
+    thr, cs = np.float32(iso_surface_threshold), np.float32(cube_size)
+    tr = np.zeros(3, np.float32) if translation is None else np.asarray(translation, np.float64).astype(np.float32)
+    ncells = [n - 1 for n in v.shape]
+    grid = UniformGrid(Aabb3d(tr.copy(), (tr + cs * np.asarray(ncells, np.float32)).astype(np.float32)), float(cs), list(v.shape), ncells)
+    nt = [(c + 63) // 64 for c in ncells]
+    padded = np.pad(v, [(0, t * 64 + 1 - n) for t, n in zip(nt, v.shape)], mode="edge")
+    tiles, ijk = [], []
+    for a in range(nt[0]):
+        for b in range(nt[1]):
+            for c_ in range(nt[2]):
+                blk = padded[a * 64:a * 64 + 65, b * 64:b * 64 + 65, c_ * 64:c_ * 64 + 65]
+                if blk.min() > thr or blk.max() < thr:        # no sign change inside this tile (NaNs compare false: kept)
+                    continue
+                tiles.append(blk)
+                ijk.append((a, b, c_))
+    ctx = default_context() if context is None else context
+    L = ctx._L
+    tiles = np.ascontiguousarray(np.stack(tiles)) if tiles else np.zeros((0, 65, 65, 65), np.float32)
+    ijk = np.ascontiguousarray(np.asarray(ijk, dtype=np.int32).reshape(-1, 3))
+    s = C.c_void_p()
+    _check(L, L.ss_marching_cubes_tiles_f32(ctx._h, tiles.ctypes.data if len(tiles) else None, len(tiles), ijk.ctypes.data if len(tiles) else None,
+                                            (C.c_float * 3)(*[float(x) for x in tr]), C.c_float(float(cs)), C.c_float(float(thr)), C.byref(s)))
+    try:
+        nv, ntri = L.ss_surface_num_vertices(s), L.ss_surface_num_triangles(s)
+        verts, tris, keys = np.empty((nv, 3), np.float32), np.empty((ntri, 3), np.uint32), np.empty((nv, 4), np.int64)
+        if nv:
+            _check(L, L.ss_surface_copy_vertices(s, verts.ctypes.data))
+            _check(L, L.ss_surface_copy_vertex_edge_keys(s, keys.ctypes.data))
+        if ntri:
+            _check(L, L.ss_surface_copy_triangles_u32(s, tris.ctypes.data))
+    finally:
+        L.ss_surface_free(s)
+    # cells of the padding: a vertex whose grid edge has an end point beyond the array
+    last = np.asarray(v.shape, np.int64) - 1
+    end = keys[:, :3].copy()
+    end[np.arange(nv), keys[:, 3]] += 1
+    bad_v = (end > last).any(axis=1) if nv else np.zeros(0, bool)
+    if bad_v.any():
+        tris = tris[~bad_v[tris].any(axis=1)]
+        newid = np.cumsum(~bad_v) - 1
+        verts, tris = verts[~bad_v], newid[tris]
+    mesh = TriMesh3d(np.ascontiguousarray(verts), np.ascontiguousarray(tris, dtype=np.uint64))
+    return (mesh, grid) if return_grid else mesh
 
 
 def neighborhood_search_spatial_hashing_parallel(particle_positions, domain: "Aabb3d", search_radius: float, *, context: Optional["Context"] = None) -> "NeighborhoodLists":

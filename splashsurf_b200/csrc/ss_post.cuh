@@ -540,6 +540,86 @@ extern "C" int ss_neighborhood_search_f32(ss_context *c, const float *xyz, uint6
     }
 }
 
+// ------------------------------------------------------------------ marching cubes on caller-supplied level-set tiles ----
+// marching_cubes::triangulate_density_map (marching_cubes.rs:61-127 with narrow_band_extraction.rs / triangulation.rs; the Python function
+// pysplashsurf.marching_cubes on a dense array): the global path's marching-cubes kernels on level-set values the caller provides.
+// The values come as tiles of 65^3 points (64^3 cells; neighbouring tiles share their face planes), tile t covering the global points
+// tile_ijk[t] * 64 .. + 64 per axis -- the layout the level-set stage produces.  Vertices are welded across tiles by their global edge
+// key (ss_surface_copy_vertex_edge_keys).  Cells beyond the caller's array have to be padded by the caller (the Python front end repeats
+// the border values and drops the triangles of the padded cells afterwards).
+extern "C" int ss_marching_cubes_tiles_f32(ss_context *c, const float *tiles, uint32_t ntiles, const int32_t *tile_ijk, const float grid_min[3],
+                                           float cube_size, float iso_surface_threshold, ss_surface **out) {
+    if (!c || !out || !grid_min) return ss_fail(SS_ERR_INVALID_PARAMETER, "NULL argument");
+    *out = nullptr;
+    if (ntiles && (!tiles || !tile_ijk)) return ss_fail(SS_ERR_INVALID_PARAMETER, "tiles / tile_ijk is NULL");
+    if (!(cube_size > 0.0f) || !std::isfinite(cube_size)) return ss_fail(SS_ERR_INVALID_CELL_SIZE, "cube size must be positive");
+    SsDev D{};
+    D.S = 64; D.np = 65; D.np_magic = (uint32_t)(4294967296ull / (uint64_t)D.np) + 1u;
+    D.c = cube_size; D.thr = iso_surface_threshold; D.gmode = 1; D.R = 1; D.simd = 1;
+    D.sub_size = fmulr(cube_size, 64.0f);
+    for (int d = 0; d < 3; ++d) { D.gmin[d] = grid_min[d]; D.nsd[d] = 1; }
+    fill_bins(D, cube_size);
+    const size_t np3 = (size_t)D.np * D.np * D.np;
+    const uint64_t nbricks = (uint64_t)D.nb * D.nb * D.nb;
+    if ((uint64_t)ntiles * nbricks >= 0x7fffffffull) return ss_fail(SS_ERR_INDEX_TOO_SMALL, "too many tiles for one call");
+    std::vector<SsTile> h_tiles(ntiles);
+    for (uint32_t t = 0; t < ntiles; ++t) {
+        SsTile &T = h_tiles[t];
+        for (int d = 0; d < 3; ++d) {
+            const int32_t q = tile_ijk[3 * (size_t)t + d];
+            if (q < 0 || (int64_t)q * 64 + 64 >= (1 << 20)) return ss_fail(SS_ERR_INDEX_TOO_SMALL, "tile index out of range (2^20 grid points per dimension)");
+            T.gbase[d] = q * 64; T.smin[d] = faddr(grid_min[d], fmulr((float)q, D.sub_size));
+        }
+        T.s = t; T.sparse = 1u;
+    }
+    ss_surface *s = nullptr;
+    try {
+        CK(cudaSetDevice(c->device));
+        cudaStream_t st = c->stream;
+        s = new ss_surface();
+        s->device = c->device; s->owner = c; s->S = 64;
+        c->launches = 0; c->post.valid = 0; s->frame = ++c->frame;
+        for (int d = 0; d < 3; ++d) { s->grid.mn[d] = s->grid.mx[d] = grid_min[d]; s->grid.np[d] = s->grid.nc[d] = 0; }
+        s->grid.cell = cube_size;
+        s->verts = c->o_verts; c->o_verts = DevBuf(); s->tris = c->o_tris; c->o_tris = DevBuf(); s->vkeys = c->o_vkeys; c->o_vkeys = DevBuf();
+        s->verts.ensure(1 << 16); s->vkeys.ensure(1 << 16); s->tris.ensure(1 << 16);
+        uint64_t vtotal = 0, ttotal = 0, nv_final = 0;
+        uint32_t bc = 0;
+        if (ntiles) {
+            const uint32_t n_mc = (uint32_t)(ntiles * nbricks);
+            c->tiles.ensure((size_t)ntiles * np3 * 4); c->voff.ensure((size_t)ntiles * np3 * 4); c->vmask.ensure((size_t)ntiles * np3);
+            c->vcnt.ensure((size_t)n_mc * 4 + 4); c->tcnt.ensure((size_t)n_mc * 4 + 4); c->vblk_off.ensure((size_t)n_mc * 4 + 4); c->tblk_off.ensure((size_t)n_mc * 4 + 4);
+            c->tile_tab.ensure((size_t)ntiles * sizeof(SsTile)); c->list_mc.ensure((size_t)n_mc * 4); c->bcount.ensure(4);
+            c->bkeys_a.ensure(1 << 16); c->bids_a.ensure(1 << 16);
+            CK(cudaMemcpyAsync(c->tiles.p, tiles, (size_t)ntiles * np3 * 4, cudaMemcpyDefault, st));
+            CK(cudaMemcpyAsync(c->tile_tab.p, h_tiles.data(), (size_t)ntiles * sizeof(SsTile), cudaMemcpyHostToDevice, st));
+            CK(cudaMemsetAsync(c->vmask.p, 0, (size_t)ntiles * np3, st));
+            CK(cudaMemsetAsync(c->bcount.p, 0, 4, st));
+            LAUNCH(c, k_iota2, nblk(n_mc, 256), 256, n_mc, c->list_mc.as<uint32_t>(), c->vcnt.as<uint32_t>());      // every brick of every tile
+            CK(cudaStreamSynchronize(st));                                                                          // h_tiles is read by the copy above
+            int rc = marching_cubes_batch(c, D, /*global_mode=*/true, n_mc, s, vtotal, ttotal);
+            if (rc) { ss_surface_free(s); return rc; }
+            nv_final = vtotal;
+            rc = weld_boundary_vertices(c, s, vtotal, ttotal, nv_final, bc);
+            if (rc) { ss_surface_free(s); return rc; }
+        }
+        s->nv = nv_final; s->nt = ttotal;
+        CK(cudaStreamSynchronize(st));
+        s->tm.kernel_launches = c->launches;
+        *out = s;
+        return SS_OK;
+    } catch (const SsCudaError &err) {
+        if (s) ss_surface_free(s);
+        cudaGetLastError();
+        char buf[512];
+        snprintf(buf, sizeof(buf), "%s failed at %s:%d: %s", err.what, err.file, err.line, cudaGetErrorString(err.e));
+        return ss_fail(err.e == cudaErrorMemoryAllocation ? SS_ERR_OUT_OF_MEMORY : SS_ERR_CUDA, buf);
+    } catch (const std::bad_alloc &) {
+        if (s) ss_surface_free(s);
+        return ss_fail(SS_ERR_OUT_OF_MEMORY, "host allocation failed");
+    }
+}
+
 // Smoothing weights of the mesh vertices (reconstruct.rs:1159-1258): distance-weighted neighbour count per particle,
 // SPH-interpolated (with correction) to the vertices, normalised and passed through the smooth-step.  The weights stay on
 // the device for ss_surface_laplacian_smoothing_f32; wnn_out / weights_out ([nv], optional) receive copies

@@ -574,6 +574,12 @@ def test_emulated_neighborhood_search_stand_alone(emu, oracle_mod):
     check_neighborhood_search(emu, oracle_mod)
 
 
+def test_emulated_marching_cubes_on_a_dense_array(emu, oracle_mod):
+    """pysplashsurf.marching_cubes on the CPU executor: same checks as the GPU-marked test (one-cell KAT, sphere SDF, the wheel's meshes)."""
+    from test_zzzz_reference_datasets import check_marching_cubes
+    check_marching_cubes(emu, oracle_mod)
+
+
 def test_emulated_cli_with_postprocessing(emu, tmp_path):
     """`python -m splashsurf_b200 reconstruct` with the reference CLI's post-processing switches (clean-up, decimation, smoothing, normals,
     mesh checks, quads) -- control flow of the thin harness on the CPU executor."""

@@ -198,3 +198,70 @@ def check_neighborhood_search(ss, oracle_mod):
 @pytest.mark.gpu
 def test_cuda_neighborhood_search_stand_alone(ss, oracle_mod):
     check_neighborhood_search(ss, oracle_mod)
+
+
+# ---- marching cubes on a dense array (pysplashsurf.marching_cubes = marching_cubes::triangulate_density_map): the reference's one-cell
+# known-answer test (marching_cubes.rs:325-396), its sphere-SDF test (pysplashsurf/tests/test_sdf.py) and random fields of awkward shapes
+# (borders with values on both sides of the threshold, arrays that do not fill whole tiles) against the wheel's function
+def _canonical_mesh(v, t):
+    o = np.lexsort(v.T[::-1])
+    rank = np.empty(len(v), np.int64)
+    rank[o] = np.arange(len(v))
+    t = rank[np.asarray(t).astype(np.int64)]
+    if len(t):
+        t = np.stack([np.roll(row, -s) for row, s in zip(t, np.argmin(t, axis=1))])
+        t = t[np.lexsort(t.T[::-1])]
+    return v[o], t
+
+
+def check_marching_cubes(ss, oracle_mod):
+    # one cell (marching_cubes.rs:325-396): threshold 0.25, six vertices on the local edges 0, 3, 5, 6, 9, 11
+    vals = np.zeros((2, 2, 2), np.float32)
+    for (i, j, k), val in (((0, 0, 0), 0.0), ((1, 0, 0), 0.75), ((1, 1, 0), 1.0), ((0, 1, 0), 0.5), ((0, 0, 1), 0.0), ((1, 0, 1), 0.0), ((1, 1, 1), 1.0),
+                           ((0, 1, 1), 0.0)):
+        vals[i, j, k] = val
+    mesh, grid = ss.marching_cubes(vals, iso_surface_threshold=0.25, cube_size=1.0, return_grid=True)
+    assert np.array_equal(grid.aabb.max, np.float32([1, 1, 1])) and grid.ncells_per_dim == [1, 1, 1] and grid.npoints_per_dim == [2, 2, 2]
+    expect = np.float32([[1 / 3, 0, 0], [0, 0.5, 0], [1, 0.25, 1], [0.25, 1, 1], [1, 0, 2 / 3], [0, 1, 0.5]])
+    assert mesh.vertices.shape == (6, 3) and mesh.triangles.dtype == np.uint64
+    assert np.abs(_canonical_mesh(mesh.vertices, mesh.triangles)[0] - expect[np.lexsort(expect.T[::-1])]).max() < 1e-6
+    assert len(mesh.triangles) == 4                                    # a hexagon: corners 1, 2, 3, 6 are inside
+    empty = ss.marching_cubes(np.zeros((3, 4, 5), np.float32), iso_surface_threshold=0.25, cube_size=1.0)
+    assert empty.vertices.shape == (0, 3) and empty.triangles.shape == (0, 3)
+    # sphere SDF (pysplashsurf/tests/test_sdf.py): values grow towards the outside, so the surface is seen "inside out" -- still one closed sphere
+    n, radius = 100, 1.0
+    dx = radius * 2.2 / (n - 1)
+    tr = -0.5 * radius * 2.2
+    c = np.arange(n, dtype=np.float32) * np.float32(dx) + np.float32(tr)
+    x, y, z = np.meshgrid(c, c, c, indexing="ij")
+    sdf = (np.sqrt(x**2 + y**2 + z**2) - radius).astype(np.float32)
+    mesh, grid = ss.marching_cubes(sdf, iso_surface_threshold=0.0, cube_size=dx, translation=[tr] * 3, return_grid=True)
+    norms = np.linalg.norm(mesh.vertices, axis=1)
+    assert len(mesh.vertices) > 0 and norms.min() > radius - 1e-4 and norms.max() < radius + 1e-4
+    assert ss.check_mesh_consistency(mesh, grid) is None
+    cases = [(sdf, 0.0, dx, [tr] * 3)]
+    rng = np.random.default_rng(3)
+    from scipy.ndimage import gaussian_filter
+    for shape in ((5, 9, 3), (66, 65, 70), (130, 20, 67)):
+        cases.append((gaussian_filter(rng.normal(size=shape), 1.5).astype(np.float32), 0.01, 0.3, [0.5, -2.0, 7.0]))
+    for f, thr, cs, t in cases:
+        m = ss.marching_cubes(f, iso_surface_threshold=thr, cube_size=cs, translation=t)
+        # every vertex lies on a grid edge inside the array; every triangle is a valid one
+        q = (m.vertices.astype(np.float64) - np.asarray(t)) / cs
+        assert q.min() > -1e-4 and (q.max(axis=0) < np.asarray(f.shape) - 1 + 1e-4).all() and int(m.triangles.max()) < len(m.vertices)
+        if oracle_mod.reference_available():
+            r = oracle_mod.reference().marching_cubes(f, iso_surface_threshold=thr, cube_size=cs, translation=t)
+            a, b = _canonical_mesh(m.vertices, m.triangles), _canonical_mesh(np.asarray(r.vertices), np.asarray(r.triangles))
+            assert a[0].shape == b[0].shape and a[1].shape == b[1].shape
+            assert np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32)) and np.array_equal(a[1], b[1])      # bit for bit
+    with pytest.raises(ValueError):
+        ss.marching_cubes(np.zeros((4, 4), np.float32), iso_surface_threshold=0.0, cube_size=1.0)
+    with pytest.raises(TypeError):
+        ss.marching_cubes(np.zeros((4, 4, 4)), iso_surface_threshold=0.0, cube_size=1.0)
+    with pytest.raises(ss.SplashsurfError):
+        ss.marching_cubes(np.zeros((4, 4, 4), np.float32), iso_surface_threshold=0.0, cube_size=0.0)
+
+
+@pytest.mark.gpu
+def test_cuda_marching_cubes_on_a_dense_array(ss, oracle_mod):
+    check_marching_cubes(ss, oracle_mod)
