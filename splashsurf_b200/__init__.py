@@ -661,6 +661,46 @@ class Context:
         return {k: getattr(t, k) for k, _ in _Timings._fields_}
 
 
+class MeshAttribute:
+    """``pysplashsurf.MeshAttribute``: a named per-vertex / per-cell array (name, data, dtype).  The mesh containers of this package keep
+    their attributes in plain dicts (name -> array), like ``MeshWithData.point_attributes`` of the reference returns them."""
+
+    def __init__(self, name: str, data):
+        self._name, self._data = str(name), np.asarray(data)
+
+    @property
+    def name(self) -> str:
+        return self._name
+
+    @property
+    def data(self) -> np.ndarray:
+        return self._data
+
+    @property
+    def dtype(self):
+        return self._data.dtype
+
+
+def run_splashsurf(args) -> None:
+    """``pysplashsurf.run_splashsurf``: the command line of this package (`python -m splashsurf_b200`: `reconstruct`, `convert`) with an
+    argv-style list whose first element is the program name.  Raises RuntimeError when the command fails, like the reference binding."""
+    from .__main__ import main
+    try:
+        rc = main(list(args)[1:])
+    except SystemExit as e:                     # argparse: unknown switch / missing argument
+        rc = e.code if isinstance(e.code, int) else 1
+    except (ValueError, OSError, SplashsurfError) as e:
+        raise RuntimeError(str(e)) from e
+    if rc:
+        raise RuntimeError(f"splashsurf_b200 {' '.join(str(a) for a in list(args)[1:2])} failed (exit code {rc})")
+
+
+def run_pysplashsurf() -> None:
+    """Console entry point of the reference package (pysplashsurf/__init__.py:6-7)."""
+    import sys
+    run_splashsurf(sys.argv)
+
+
 def marching_cubes(values, *, iso_surface_threshold: float, cube_size: float, translation=None, return_grid: bool = False,
                    context: Optional["Context"] = None):
     """``pysplashsurf.marching_cubes`` (pysplashsurf/src/marching_cubes.rs:108-177 -> marching_cubes::triangulate_density_map) on the GPU:

@@ -77,3 +77,23 @@ def test_ctypes_signatures_match_header_arity(ss):
             assert len(fn.argtypes) == n, (name, len(fn.argtypes), n)
             checked += 1
     assert checked >= 25
+
+
+def test_python_mirror_covers_the_public_names_of_pysplashsurf(ss, oracle_mod, tmp_path):
+    """Every public class / function of the reference's Python module exists under the same name here (its sub-modules aside)."""
+    if not oracle_mod.reference_available():
+        pytest.skip("oracle/_ref not unpacked")
+    import types
+    ps = oracle_mod.reference()
+    names = [n for n in dir(ps) if not n.startswith("_") and not isinstance(getattr(ps, n), types.ModuleType)]
+    assert len(names) >= 20 and [n for n in names if not hasattr(ss, n)] == []
+    # run_splashsurf drives this package's command line (no device needed for `convert`)
+    import numpy as np
+    src, dst = str(tmp_path / "a.xyz"), str(tmp_path / "a.json")
+    np.arange(12, dtype=np.float32).tofile(src)
+    ss.run_splashsurf(["splashsurf", "convert", "--particles", src, "-o", dst])
+    assert open(dst).read() == "[[0.0,1.0,2.0],[3.0,4.0,5.0],[6.0,7.0,8.0],[9.0,10.0,11.0]]"
+    with pytest.raises(RuntimeError):
+        ss.run_splashsurf(["splashsurf", "convert", "--particles", src, "-o", dst])          # exists, no --overwrite
+    a = ss.MeshAttribute("w", np.ones(3, np.float32))
+    assert (a.name, a.dtype, a.data.shape) == ("w", np.float32, (3,))
