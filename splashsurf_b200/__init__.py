@@ -735,6 +735,43 @@ def marching_cubes(values, *, iso_surface_threshold: float, cube_size: float, tr
     ctx = default_context() if context is None else context
     L = ctx._L
     tiles = np.ascontiguousarray(np.stack(tiles)) if tiles else np.zeros((0, 65, 65, 65), np.float32)
+    if len(tiles) and np.any(tiles == thr):
+        # A value exactly ON the threshold is "inside" for the vertex pass (>= threshold) but for the case index only where it has a
+        # neighbour below it (narrow_band_extraction.rs:79-126, :179-184).  Where the two disagree along an edge the table asks for a vertex
+        # that was never created -- the reference stops with "Missing iso surface vertex at edge ..."; so does this front end (the check
+        # evaluates the kernels' rules, ss_above / ss_crossing, on the tiles it is about to send).
+        geq, below = tiles >= thr, tiles < thr
+        nb = np.zeros_like(geq)
+        for ax in (1, 2, 3):
+            lo, hi = [slice(None)] * 4, [slice(None)] * 4
+            lo[ax], hi[ax] = slice(0, -1), slice(1, None)
+            nb[tuple(lo)] |= below[tuple(hi)]
+            nb[tuple(hi)] |= below[tuple(lo)]
+        above = (tiles > thr) | ((tiles == thr) & nb)
+        for ax in (1, 2, 3):
+            lo, hi = [slice(None)] * 4, [slice(None)] * 4
+            lo[ax], hi[ax] = slice(0, -1), slice(1, None)
+            if np.any((above[tuple(lo)] != above[tuple(hi)]) & (geq[tuple(lo)] == geq[tuple(hi)])):
+                raise SplashsurfError(SS_ERR_INVALID_PARAMETER, "Missing iso surface vertex at an edge: a value equal to the iso-surface threshold "
+                                      "lies next to a value above it without a value below it on its other side (the reference reports "
+                                      "\"Missing iso surface vertex at edge ... This is a bug.\" for such an array)")
+        # The reference marks such a value "above" per CELL -- only in the cells that touch one of its edges towards a value below
+        # (:108-126) -- the kernels per POINT.  Where the two differ the reference either builds another mesh or stops with the error
+        # above: refuse instead of returning a mesh the reference would not return.
+        eq = tiles == thr
+        cells = (slice(None), slice(0, -1), slice(0, -1), slice(0, -1))
+        for ca in (0, 1):
+            for cb in (0, 1):
+                for cc in (0, 1):
+                    def corner(arr, a=ca, b=cb, c_=cc):
+                        return arr[:, a:a + 64, b:b + 64, c_:c_ + 64]
+                    in_cell_below = corner(below, 1 - ca, cb, cc) | corner(below, ca, 1 - cb, cc) | corner(below, ca, cb, 1 - cc)
+                    ref_above = corner(tiles > thr) | (corner(eq) & in_cell_below)
+                    if np.any(ref_above != corner(above)):
+                        raise SplashsurfError(SS_ERR_UNSUPPORTED, "a value equal to the iso-surface threshold sits where the reference decides inside / "
+                                              "outside per cell (narrow_band_extraction.rs:108-126): this degenerate configuration is not triangulated "
+                                              "here -- move the threshold (or the values) by one ulp")
+        del cells
     ijk = np.ascontiguousarray(np.asarray(ijk, dtype=np.int32).reshape(-1, 3))
     s = C.c_void_p()
     _check(L, L.ss_marching_cubes_tiles_f32(ctx._h, tiles.ctypes.data if len(tiles) else None, len(tiles), ijk.ctypes.data if len(tiles) else None,

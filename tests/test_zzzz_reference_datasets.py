@@ -254,6 +254,34 @@ def check_marching_cubes(ss, oracle_mod):
             a, b = _canonical_mesh(m.vertices, m.triangles), _canonical_mesh(np.asarray(r.vertices), np.asarray(r.triangles))
             assert a[0].shape == b[0].shape and a[1].shape == b[1].shape
             assert np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32)) and np.array_equal(a[1], b[1])      # bit for bit
+    # values exactly ON the threshold: inside for the vertex pass, for the case index only next to a value below (narrow_band_extraction.rs:
+    # 79-126, :179-184).  Consistent arrays give the reference's mesh; where the table would ask for a vertex nobody created the reference
+    # stops with "Missing iso surface vertex" and so does this front end (it never returns a mesh the reference would not)
+    f = np.zeros((3, 3, 3), np.float32)
+    f[1, 1, 1], f[0, 1, 1] = 1.0, 0.5
+    m = ss.marching_cubes(f, iso_surface_threshold=0.5, cube_size=1.0)
+    assert (len(m.vertices), len(m.triangles)) == (9, 12)
+    f[:] = 1.0
+    f[1, 1, 1] = 0.5                                                   # on the threshold, every neighbour above it
+    with pytest.raises(ss.SplashsurfError, match="Missing iso surface vertex"):
+        ss.marching_cubes(f, iso_surface_threshold=0.5, cube_size=1.0)
+    agree = refused = 0
+    for seed in range(40):
+        rs = np.random.default_rng(seed)
+        g = rs.normal(size=(6, 5, 7)).astype(np.float32)
+        g.reshape(-1)[rs.integers(0, g.size, size=3)] = 1.0            # three values exactly on the threshold
+        try:
+            m = ss.marching_cubes(g, iso_surface_threshold=1.0, cube_size=0.5)
+        except ss.SplashsurfError:
+            refused += 1
+            continue
+        assert int(m.triangles.max(initial=0)) < max(len(m.vertices), 1)
+        if oracle_mod.reference_available():
+            r = oracle_mod.reference().marching_cubes(g, iso_surface_threshold=1.0, cube_size=0.5)
+            a, b = _canonical_mesh(m.vertices, m.triangles), _canonical_mesh(np.asarray(r.vertices), np.asarray(r.triangles))
+            assert np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32)) and np.array_equal(a[1], b[1])
+            agree += 1
+    assert refused > 0 and (agree > 0 or not oracle_mod.reference_available())
     with pytest.raises(ValueError):
         ss.marching_cubes(np.zeros((4, 4), np.float32), iso_surface_threshold=0.0, cube_size=1.0)
     with pytest.raises(TypeError):
