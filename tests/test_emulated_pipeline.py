@@ -580,6 +580,12 @@ def test_emulated_marching_cubes_on_a_dense_array(emu, oracle_mod):
     check_marching_cubes(emu, oracle_mod)
 
 
+def test_emulated_cli_sequence_equals_library_calls(emu, tmp_path):
+    """The GPU-marked command-line test on the CPU executor."""
+    from test_zzzz_reference_datasets import check_cli_sequence
+    check_cli_sequence(emu, tmp_path)
+
+
 def test_emulated_cli_with_postprocessing(emu, tmp_path):
     """`python -m splashsurf_b200 reconstruct` with the reference CLI's post-processing switches (clean-up, decimation, smoothing, normals,
     mesh checks, quads) -- control flow of the thin harness on the CPU executor."""

@@ -293,3 +293,29 @@ def check_marching_cubes(ss, oracle_mod):
 @pytest.mark.gpu
 def test_cuda_marching_cubes_on_a_dense_array(ss, oracle_mod):
     check_marching_cubes(ss, oracle_mod)
+
+
+# ---- the command line on the device: a frame sequence on one context (pooled buffers reused from frame to frame), files equal to what the
+# library calls give frame by frame
+def check_cli_sequence(ss, tmp_path):
+    from splashsurf_b200 import io, synthetic as syn, __main__ as cli
+    frames = tmp_path / "frames"
+    frames.mkdir()
+    clouds = {i: syn.splash((7 + i, 7, 7), 2, 0.025, 800 + i) for i in (1, 2, 3)}            # growing clouds: the pooled buffers have to grow
+    for i, p in clouds.items():
+        io.write_particles(str(frames / f"f_{i}.bgeo"), p)
+    out = tmp_path / "out"
+    assert cli.main(["reconstruct", str(frames / "f_{}.bgeo"), "-r=0.025", "-l=2.0", "-c=0.75", "--normals=on", "--sph-normals=on", "--output-dir", str(out),
+                     "-o", "m_{}.ply", "-q"]) == 0
+    assert sorted(os.listdir(out)) == ["m_1.ply", "m_2.ply", "m_3.ply"]
+    for i, p in clouds.items():
+        v, t, _, attrs = io.read_ply_mesh(str(out / f"m_{i}.ply"))
+        mesh, _ = ss.reconstruction_pipeline(p, particle_radius=0.025, smoothing_length=2.0, cube_size=0.75, compute_normals=True, sph_normals=True,
+                                             subdomain_grid_auto_disable=False)
+        assert np.array_equal(v, mesh.mesh.vertices) and np.array_equal(t.astype(np.uint64), mesh.mesh.triangles.astype(np.uint64))
+        assert np.array_equal(attrs["normals"], mesh.point_attributes["normals"])
+
+
+@pytest.mark.gpu
+def test_cuda_cli_frame_sequence(ss, tmp_path):
+    check_cli_sequence(ss, tmp_path)
