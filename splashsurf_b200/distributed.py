@@ -730,9 +730,7 @@ class DistributedReconstructor:
             return ss.MeshWithData(r.mesh, {"normals": r.normals} if self.sph_normals and r.normals is not None else {}, {})
         if self._aabb is not None:                    # lib.rs:369-406: particles outside the half-open box take no part
             p = np.ascontiguousarray(p[np.all(p >= self._aabb[0], axis=1) & np.all(p < self._aabb[1], axis=1)])
-        x = torch.from_numpy(p)
-        if self.runner.device.type == "cuda":
-            x = x.pin_memory()
+        x = torch.from_numpy(p)                       # pageable: the runner's upload stages it (a page-locked tensor is taken as it is)
         out = self.runner.step(x, copy_out=True)
         if self.rank != 0:
             return None
