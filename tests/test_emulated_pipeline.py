@@ -586,6 +586,12 @@ def test_emulated_cli_sequence_equals_library_calls(emu, tmp_path):
     check_cli_sequence(emu, tmp_path)
 
 
+def test_emulated_reference_python_tests(emu, tmp_path, oracle_mod):
+    """pysplashsurf/tests/*.py against `import splashsurf_b200 as pysplashsurf` on the CPU executor (tests/test_zzzz_pysplashsurf_tests.py)."""
+    from test_zzzz_pysplashsurf_tests import run_all
+    run_all(emu, tmp_path, oracle_mod)
+
+
 def test_emulated_cli_with_postprocessing(emu, tmp_path):
     """`python -m splashsurf_b200 reconstruct` with the reference CLI's post-processing switches (clean-up, decimation, smoothing, normals,
     mesh checks, quads) -- control flow of the thin harness on the CPU executor."""

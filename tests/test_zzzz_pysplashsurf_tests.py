@@ -1,0 +1,235 @@
+"""The reference's own Python tests (pysplashsurf/tests/test_basic.py, test_calling.py, test_sdf.py, test_bgeo.py) re-run against
+`import splashsurf_b200 as pysplashsurf`: same calls, same assertions, on the same particle files (tests/golden/pysplashsurf_tests.npz,
+tools/make_golden_pytests.py).  What differs from the originals: meshio / trimesh are replaced by this package's readers and a nearest-
+vertex distance; the f64 halves of the originals assert the documented TypeError (the device path is float32); the "binary vs Python"
+tests compare this package's command line with its pipeline call and -- where the wheel is unpacked -- with the REFERENCE command line.
+GPU-marked; tests/test_emulated_pipeline.py runs the same functions on the CPU executor."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+DATA = np.load(os.path.join(GOLDEN, "pysplashsurf_tests.npz"))
+
+
+def _fluid_vtk(path):
+    """ParticleData_Fluid_5.vtk rebuilt from the fixture: float POINTS + `id` scalars + `velocity` vectors (legacy binary)."""
+    p, vel, ids = DATA["fluid_5"], DATA["fluid_5_velocity"], DATA["fluid_5_id"]
+    n = len(p)
+    with open(path, "wb") as f:
+        f.write(b"# vtk DataFile Version 4.2\nSPH Fluid\nBINARY\nDATASET UNSTRUCTURED_GRID\n")
+        f.write(b"POINTS %d float\n" % n + p.astype(">f4").tobytes() + b"\n")
+        f.write(b"CELLS %d %d\n" % (n, 2 * n) + np.stack([np.ones(n), np.arange(n)], 1).astype(">i4").tobytes() + b"\n")
+        f.write(b"CELL_TYPES %d\n" % n + np.ones(n, ">i4").tobytes() + b"\n")
+        f.write(b"POINT_DATA %d\n" % n)
+        f.write(b"SCALARS id unsigned_int 1\nLOOKUP_TABLE id_table\n" + ids.astype(">u4").tobytes() + b"\n")
+        f.write(b"VECTORS velocity float\n" + vel.astype(">f4").tobytes() + b"\n")
+    return path
+
+
+# ------------------------------------------------------------------------------------------------- test_basic.py
+def check_aabb_class(pysplashsurf):                                               # test_basic.py:13-41
+    aabb = pysplashsurf.Aabb3d.from_min_max(min=[0.0, 0.0, 0.0], max=[1.0, 2.0, 3.0])
+    assert (aabb.min == np.array([0.0, 0.0, 0.0])).all() and (aabb.max == np.array([1.0, 2.0, 3.0])).all()
+    aabb = pysplashsurf.Aabb3d.from_min_max(min=np.array([0.0, 0.0, 0.0]), max=np.array([1.0, 2.0, 3.0]))
+    assert (aabb.min == np.array([0.0, 0.0, 0.0])).all() and (aabb.max == np.array([1.0, 2.0, 3.0])).all()
+    aabb = pysplashsurf.Aabb3d.from_points(np.array([[0.0, 0.0, 0.0], [1.0, 1.0, 1.0], [2.0, 0.5, 4.2]]))
+    assert (aabb.min == np.array([0.0, 0.0, 0.0])).all() and np.allclose(aabb.max, np.array([2.0, 1.0, 4.2]))
+    assert aabb.contains_point([1.0, 0.9, 4.1]) and aabb.contains_point([0.0, 0.0, 0.0])
+    assert not aabb.contains_point([2.0, 1.0, 4.2]) and not aabb.contains_point([1.0, -1.0, 5.0])
+
+
+def check_pipeline(pysplashsurf):                                                 # test_basic.py:44-105
+    dtype = np.float32
+    particles = DATA["random_1000"].astype(dtype)
+    mesh_with_data, reconstruction = pysplashsurf.reconstruction_pipeline(
+        particles, particle_radius=0.025, rest_density=1000.0, smoothing_length=2.0, cube_size=1.0, iso_surface_threshold=0.6,
+        mesh_smoothing_iters=5, output_mesh_smoothing_weights=True)
+    assert type(mesh_with_data) is pysplashsurf.MeshWithData and type(reconstruction) is pysplashsurf.SurfaceReconstruction
+    assert type(mesh_with_data.mesh) is pysplashsurf.TriMesh3d
+    mesh = mesh_with_data.mesh
+    assert mesh_with_data.dtype == mesh.dtype == dtype
+    assert type(mesh_with_data.mesh_type) is pysplashsurf.MeshType and mesh_with_data.mesh_type == pysplashsurf.MeshType.Tri3d
+    assert mesh.vertices.dtype == dtype and mesh.triangles.dtype in [np.uint32, np.uint64]
+    assert mesh_with_data.nvertices == len(mesh.vertices) and mesh_with_data.ncells == len(mesh.triangles)
+    assert mesh_with_data.nvertices in range(21000, 25000) and mesh_with_data.ncells in range(45000, 49000)
+    assert mesh.vertices.shape == (mesh_with_data.nvertices, 3) and mesh.triangles.shape == (mesh_with_data.ncells, 3)
+    assert len(mesh_with_data.point_attributes) == 2 and len(mesh_with_data.cell_attributes) == 0
+    sw, wnn = mesh_with_data.point_attributes["sw"], mesh_with_data.point_attributes["wnn"]
+    assert sw.dtype == wnn.dtype == dtype and sw.shape == wnn.shape == (mesh_with_data.nvertices,)
+    assert sw.min() >= 0.0 and sw.max() <= 1.0 and wnn.min() >= 0.0
+    with pytest.raises(TypeError):                                                # test_pipeline_f64: float32 only here
+        pysplashsurf.reconstruction_pipeline(particles.astype(np.float64), particle_radius=0.025, smoothing_length=2.0, cube_size=1.0)
+
+
+def check_reconstruct(pysplashsurf):                                              # test_basic.py:108-147 (relative lengths)
+    particles = DATA["random_1000"]
+    reconstruction = pysplashsurf.reconstruct_surface(particles, particle_radius=0.025, rest_density=1000.0, smoothing_length=2.0, cube_size=1.0,
+                                                      iso_surface_threshold=0.6, global_neighborhood_list=True)
+    assert type(reconstruction) is pysplashsurf.SurfaceReconstruction and type(reconstruction.mesh) is pysplashsurf.TriMesh3d
+    assert type(reconstruction.grid) is pysplashsurf.UniformGrid and type(reconstruction.particle_neighbors) is pysplashsurf.NeighborhoodLists
+    mesh = reconstruction.mesh
+    assert mesh.vertices.dtype == np.float32 and len(mesh.vertices) in range(21000, 25000) and len(mesh.triangles) in range(45000, 49000)
+    assert reconstruction.particle_densities.dtype == np.float32 and len(reconstruction.particle_densities) == len(particles)
+    assert len(reconstruction.particle_neighbors) == len(particles)
+    with pytest.raises(TypeError):
+        pysplashsurf.reconstruct_surface(particles.astype(np.float64), particle_radius=0.025, smoothing_length=2.0, cube_size=1.0)
+
+
+def check_neighborhood_search(pysplashsurf):                                      # test_basic.py:150-182
+    particles = DATA["random_1000"]
+    reconstruction = pysplashsurf.reconstruct_surface(particles, particle_radius=0.025, rest_density=1000.0, smoothing_length=2.0, cube_size=1.0,
+                                                      iso_surface_threshold=0.6, global_neighborhood_list=True)
+    neighbors_reconstruct = reconstruction.particle_neighbors.get_neighborhood_lists()
+    assert type(neighbors_reconstruct) is list and len(neighbors_reconstruct) == len(particles)
+    neighbor_lists = pysplashsurf.neighborhood_search_spatial_hashing_parallel(particles, domain=reconstruction.grid.aabb, search_radius=4.0 * 0.025)
+    assert type(neighbor_lists) is pysplashsurf.NeighborhoodLists
+    neighbors = neighbor_lists.get_neighborhood_lists()
+    assert type(neighbors) is list and len(neighbors) == len(particles) == len(neighbors_reconstruct)
+    assert [sorted(a) for a in neighbors] == [sorted(b) for b in neighbors_reconstruct]      # the original's TODO: the two searches agree
+
+
+def check_interpolator(pysplashsurf):                                             # test_basic.py:283-345
+    dtype = np.float32
+    particles = DATA["random_1000"]
+    mesh_with_data, reconstruction = pysplashsurf.reconstruction_pipeline(
+        particles, particle_radius=0.025, rest_density=1000.0, smoothing_length=2.0, cube_size=1.0, iso_surface_threshold=0.6,
+        mesh_smoothing_iters=5, output_mesh_smoothing_weights=True)
+    compact_support, rest_mass = 4.0 * 0.025, 1000.0 * 0.025**3
+    interpolator = pysplashsurf.SphInterpolator(particles, reconstruction.particle_densities, rest_mass, compact_support)
+    assert type(interpolator) is pysplashsurf.SphInterpolator
+    mesh = mesh_with_data.mesh
+    mesh_densities = interpolator.interpolate_quantity(reconstruction.particle_densities, mesh.vertices)
+    assert type(mesh_densities) is np.ndarray and mesh_densities.dtype == dtype and mesh_densities.shape == (len(mesh.vertices),)
+    assert mesh_densities.min() >= 0.0
+    mesh_particles = interpolator.interpolate_quantity(particles, mesh.vertices)
+    assert type(mesh_particles) is np.ndarray and mesh_particles.dtype == dtype and mesh_particles.shape == (len(mesh.vertices), 3)
+    mesh_sph_normals = interpolator.interpolate_normals(mesh.vertices)
+    assert type(mesh_sph_normals) is np.ndarray and mesh_sph_normals.dtype == dtype and mesh_sph_normals.shape == (len(mesh.vertices), 3)
+    mesh_with_data.add_point_attribute("density", mesh_densities)
+    mesh_with_data.add_point_attribute("position", mesh_particles)
+    mesh_with_data.add_point_attribute("normal", mesh_sph_normals)
+    for name, arr in (("density", mesh_densities), ("position", mesh_particles), ("normal", mesh_sph_normals)):
+        assert name in mesh_with_data.point_attributes and np.array_equal(mesh_with_data.point_attributes[name], arr, equal_nan=True)
+
+
+# ------------------------------------------------------------------------------------------------- test_calling.py
+def check_marching_cubes_calls(pysplashsurf):                                     # test_calling.py:18-41
+    particles = DATA["fluid_5"]
+    reconstruction = pysplashsurf.reconstruct_surface(particles, particle_radius=0.025, rest_density=1000.0, smoothing_length=2.0, cube_size=0.5,
+                                                      iso_surface_threshold=0.6)
+    verts_before = len(reconstruction.mesh.vertices)
+    mesh_with_data = pysplashsurf.MeshWithData(reconstruction.mesh)
+    pysplashsurf.marching_cubes_cleanup(mesh_with_data, reconstruction.grid)
+    assert len(mesh_with_data.mesh.vertices) < verts_before
+
+
+def _pipeline_to_file(pysplashsurf, particles, attrs, output_file, **kw):         # test_calling.py:52-140
+    mesh_with_data, _ = pysplashsurf.reconstruction_pipeline(particles, attributes_to_interpolate=attrs, particle_radius=0.025, rest_density=1000.0,
+                                                            smoothing_length=2.0, cube_size=0.5, iso_surface_threshold=0.6, **kw)
+    mesh_with_data.write_to_file(output_file)
+
+
+def _binary(args, reference: bool):
+    if reference:
+        code = "import sys; sys.path.insert(0, %r); import oracle; oracle.reference().run_splashsurf(['splashsurf'] + sys.argv[1:])" % ROOT
+        subprocess.check_call([sys.executable, "-c", code, *args, "-q"])
+    else:
+        from splashsurf_b200 import __main__ as cli
+        assert cli.main(list(args) + ["-q"]) == 0
+
+
+def _mean_nearest(a, b):
+    from scipy.spatial import cKDTree
+    return (cKDTree(b).query(a)[0].sum() + cKDTree(a).query(b)[0].sum()) / (len(a) + len(b))
+
+
+def check_no_post_processing(pysplashsurf, tmp_path, oracle_mod):                 # test_calling.py:143-186
+    from splashsurf_b200 import io
+    src = _fluid_vtk(str(tmp_path / "ParticleData_Fluid_5.vtk"))
+    args = ["reconstruct", src, "-r=0.025", "-l=2.0", "-c=0.5", "-t=0.6", "--subdomain-grid=on", "--mesh-cleanup=off", "--mesh-smoothing-weights=off",
+            "--mesh-smoothing-iters=0", "--normals=off", "--normals-smoothing-iters=0"]
+    _pipeline_to_file(pysplashsurf, DATA["fluid_5"], {}, str(tmp_path / "test.vtk"), mesh_smoothing_weights=False, mesh_smoothing_iters=0,
+                      normals_smoothing_iters=0, mesh_cleanup=False, compute_normals=False, subdomain_grid=True)
+    python_verts = io.read_vtk_mesh(str(tmp_path / "test.vtk"))[0]
+    for reference in ([False, True] if oracle_mod.reference_available() else [False]):
+        out = str(tmp_path / f"test_bin{int(reference)}.vtk")
+        _binary(args + ["-o", out], reference)
+        binary_verts = io.read_vtk_mesh(out)[0]
+        assert len(binary_verts) == len(python_verts)
+        assert np.allclose(np.sort(binary_verts, axis=0), np.sort(python_verts, axis=0))
+
+
+def check_with_post_processing(pysplashsurf, tmp_path, oracle_mod):               # test_calling.py:189-278
+    from splashsurf_b200 import io
+    src = _fluid_vtk(str(tmp_path / "ParticleData_Fluid_5.vtk"))
+    args = ["reconstruct", src, "-r=0.025", "-l=2.0", "-c=0.5", "-t=0.6", "--subdomain-grid=on", "--interpolate_attribute", "velocity",
+            "--decimate-barnacles=on", "--mesh-cleanup=on", "--mesh-smoothing-weights=on", "--mesh-smoothing-iters=25", "--normals=on",
+            "--normals-smoothing-iters=10", "--output-smoothing-weights=on", "--generate-quads=off"]
+    _pipeline_to_file(pysplashsurf, DATA["fluid_5"], {"velocity": DATA["fluid_5_velocity"]}, str(tmp_path / "test.vtk"), mesh_smoothing_weights=True,
+                      mesh_smoothing_weights_normalization=13.0, mesh_smoothing_iters=25, normals_smoothing_iters=10, generate_quads=False,
+                      mesh_cleanup=True, compute_normals=True, subdomain_grid=True, decimate_barnacles=True, output_mesh_smoothing_weights=True,
+                      output_raw_normals=True)
+    pv, _, _, pattr, _ = io.read_vtk_mesh(str(tmp_path / "test.vtk"))
+    for reference in ([False, True] if oracle_mod.reference_available() else [False]):
+        out = str(tmp_path / f"test_bin{int(reference)}.vtk")
+        _binary(args + ["-o", out], reference)
+        bv, _, _, battr, _ = io.read_vtk_mesh(out)
+        if not reference:
+            assert len(bv) == len(pv)                                             # the original's checks, this package's two front ends
+            assert np.allclose(np.sort(battr["velocity"], axis=0), np.sort(pattr["velocity"], axis=0))
+            assert np.allclose(np.sort(bv, axis=0), np.sort(pv, axis=0))
+        else:
+            # against the REFERENCE binary: the decimation is sequential and depends on the order of the raw mesh (DESIGN row f.4), so single
+            # collapses can differ: same surface (mean nearest-vertex distance), vertex count within 1 %
+            assert abs(len(bv) - len(pv)) <= 0.01 * len(bv)
+            assert _mean_nearest(bv, pv) < 2e-4
+        assert _mean_nearest(bv, pv) < (1e-5 if not reference else 2e-4)          # the original's trimesh similarity bound
+
+
+# ------------------------------------------------------------------------------------------------- test_sdf.py / test_bgeo.py
+def check_sphere_sdf(pysplashsurf):                                               # test_sdf.py:5-33
+    dtype = np.float32
+    radius, num_verts = 1.0, 100
+    grid_size = radius * 2.2
+    dx = grid_size / (num_verts - 1)
+    translation = -0.5 * grid_size
+    coords = np.arange(num_verts, dtype=dtype) * dx + translation
+    x, y, z = np.meshgrid(coords, coords, coords, indexing="ij")
+    sdf = (np.sqrt(x**2 + y**2 + z**2) - radius).astype(dtype)
+    mesh, grid = pysplashsurf.marching_cubes(sdf, iso_surface_threshold=0.0, cube_size=dx, translation=[translation] * 3, return_grid=True)
+    assert len(mesh.vertices) > 0
+    norms = np.linalg.norm(mesh.vertices, axis=1)
+    assert norms.min() > radius - 1e-4 and norms.max() < radius + 1e-4
+    assert pysplashsurf.check_mesh_consistency(mesh, grid) is None
+    with pytest.raises(TypeError):                                                # test_sphere_sdf_mc_f64
+        pysplashsurf.marching_cubes(sdf.astype(np.float64), iso_surface_threshold=0.0, cube_size=dx)
+
+
+def check_bgeo(tmp_path):                                                         # test_bgeo.py (meshio's bgeo plugin -> this package's reader)
+    from splashsurf_b200 import particle_formats as pf
+    path = str(tmp_path / "ParticleData_Fluid_50.bgeo")
+    pf.write_bgeo(path, DATA["fluid_50_bgeo"])
+    assert len(pf.particles_from_file(path)) == 4732
+
+
+def run_all(pysplashsurf, tmp_path, oracle_mod):
+    check_aabb_class(pysplashsurf)
+    check_pipeline(pysplashsurf)
+    check_reconstruct(pysplashsurf)
+    check_neighborhood_search(pysplashsurf)
+    check_interpolator(pysplashsurf)
+    check_marching_cubes_calls(pysplashsurf)
+    check_no_post_processing(pysplashsurf, tmp_path, oracle_mod)
+    check_with_post_processing(pysplashsurf, tmp_path, oracle_mod)
+    check_sphere_sdf(pysplashsurf)
+    check_bgeo(tmp_path)
+
+
+@pytest.mark.gpu
+def test_cuda_reference_python_tests(ss, tmp_path, oracle_mod):
+    run_all(ss, tmp_path, oracle_mod)
