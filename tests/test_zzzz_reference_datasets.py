@@ -164,10 +164,26 @@ def test_cuda_sph_interpolator_at_arbitrary_points(ss, oracle_mod):
 def check_neighborhood_search(ss, oracle_mod):
     from scipy.spatial import cKDTree
     from splashsurf_b200 import synthetic as syn
-    for rows, expect in _ns_cases(0.3):
+    def grown(points, r):                                             # Aabb3d::from_points + grow_uniformly (test_neighborhood_search.rs:104-106)
+        return ss.Aabb3d((points.min(axis=0) - np.float32(r)).astype(np.float32), (points.max(axis=0) + np.float32(r)).astype(np.float32))
+
+    def naive(points, r):                                             # neighborhood_search_naive: |dx|^2 < r^2 in f32
+        pairs = cKDTree(points.astype(np.float64)).query_pairs(float(r) * 1.001, output_type="ndarray")
+        dx = points[pairs[:, 0]] - points[pairs[:, 1]]
+        keep = (dx[:, 0] * dx[:, 0] + dx[:, 1] * dx[:, 1] + dx[:, 2] * dx[:, 2]).astype(np.float32) < np.float32(r) * np.float32(r)
+        out = [[] for _ in range(len(points))]
+        for a, b in pairs[keep]:
+            out[a].append(int(b)); out[b].append(int(a))
+        return [sorted(l) for l in out]
+    for rows, expect in _ns_cases(0.3):                               # test_neighborhood_search_spatial_hashing_parallel_simple (:152-176)
         p = _ns_particles(rows, 0.3)
-        nl = ss.neighborhood_search_spatial_hashing_parallel(p, ss.Aabb3d(np.float32([-2, -2, -2]), np.float32([3, 3, 3])), float(np.float32(0.3)))
+        nl = ss.neighborhood_search_spatial_hashing_parallel(p, grown(p, 0.3), float(np.float32(0.3)))
         assert type(nl) is ss.NeighborhoodLists and [sorted(l) for l in nl.get_neighborhood_lists()] == expect
+    # test_compare_free_particles_125 / _1000 (:184-300): the naive search against the spatial hashing on the reference's data sets
+    for name, r in (("free_particles_125_particles.vtk", 1.0), ("free_particles_1000_particles.vtk", 1.0), ("bunny_frame_14_7705_particles.vtk", 0.1)):
+        q = Z["particles:" + name]
+        nl = ss.neighborhood_search_spatial_hashing_parallel(q, grown(q, r), r)
+        assert [sorted(l) for l in nl.get_neighborhood_lists()] == naive(q, r), name
     p = syn.splash((14, 14, 14), 3, 0.025, 91)
     sr = float(np.float32(0.1))
     rec = ss.reconstruct_surface(p, particle_radius=0.025, smoothing_length=2.0, cube_size=1.0, global_neighborhood_list=True)
@@ -319,3 +335,25 @@ def check_cli_sequence(ss, tmp_path):
 @pytest.mark.gpu
 def test_cuda_cli_frame_sequence(ss, tmp_path):
     check_cli_sequence(ss, tmp_path)
+
+
+# ---- tests/integration_tests/test_simple.rs:68-126: one particle whose only surface-crossing edges run from a point above the threshold to a
+# point outside of the compact support -- 6 vertices, 8 triangles, closed and manifold, with the global and the subdomain-grid strategy
+def check_test_simple(reconstruct, ss):
+    p = np.array([[0.01, 0.0, 0.0]], np.float32)
+    for grid in (False, True):
+        r = reconstruct(p, particle_radius=1.0, smoothing_length=0.5, cube_size=1.0, iso_surface_threshold=0.1, multi_threading=False, simd=False,
+                        subdomain_grid=grid, subdomain_grid_auto_disable=False)
+        v, t = (r["vertices"], r["triangles"]) if isinstance(r, dict) else (r.mesh.vertices, r.mesh.triangles)
+        assert (len(v), len(t)) == (6, 8), (grid, len(v), len(t))
+        assert ss.check_mesh_consistency(ss.TriMesh3d(v, t), None, check_closed=True, check_manifold=True) is None
+
+
+def test_oracle_test_simple(oracle_mod):
+    import splashsurf_b200 as ss
+    check_test_simple(oracle_mod.reconstruct, ss)
+
+
+@pytest.mark.gpu
+def test_cuda_test_simple(ss):
+    check_test_simple(ss.reconstruct_surface, ss)
