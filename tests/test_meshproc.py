@@ -263,3 +263,35 @@ def test_mesh_containers_mirror_the_reference_bindings(ss, oracle_mod, tmp_path)
         for pt in ([1, 1, 1], [0, 0, 0], [0.5, 2, 1], [0.999, 1.999, 2.999], [-1e-9, 0, 0]):
             assert ra.contains_point(pt) == a.contains_point(pt)
         assert str(ps.MeshType.Tri3d) == str(ss.MeshType.Tri3d) and str(ps.MeshType.MixedTriQuad3d) == str(ss.MeshType.MixedTriQuad3d)
+
+
+def test_mesh_rs_manifold_known_answers(ss):
+    """The reference's unit tests of its mesh checks (mesh.rs:1120-1221: test_tri_mesh_edge_info, test_tri_mesh_non_manifold_vertex_info,
+    test_tri_mesh_manifold_info) on the helpers behind check_mesh_consistency, and aabb.rs:277-291 (half-open contains_point)."""
+    v5 = np.float32([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0], [0, 0, 1]])
+    nm_edge = ss.TriMesh3d(v5, np.uint64([[0, 1, 2], [1, 3, 2], [1, 2, 4]]))
+    nm_edge2 = ss.TriMesh3d(v5, np.uint64([[0, 1, 2], [1, 3, 2], [1, 2, 4], [4, 2, 1]]))
+    nm_vert = ss.TriMesh3d(np.float32([[1, 0, 0], [0, 1, 0], [1, 1, 0], [2, 1, 1], [1, 2, 1]]), np.uint64([[0, 2, 1], [2, 3, 4]]))
+    one = ss.TriMesh3d(np.random.default_rng(0).random((3, 3)).astype(np.float32), np.uint64([[0, 1, 2]]))
+    uniq, cnt, _ = ss._edge_table(nm_edge.triangles)                           # test_tri_mesh_edge_info
+    for e, c in zip(uniq.tolist(), cnt.tolist()):
+        assert c == (3 if sorted(e) == [1, 2] else 1)
+    assert int((cnt == 1).sum()) == 6 and int((cnt > 2).sum()) == 1
+    assert ss.find_non_manifold_vertices(nm_vert).tolist() == [2]              # test_tri_mesh_non_manifold_vertex_info
+
+    def info(mesh):
+        _, c, _ = ss._edge_table(mesh.triangles)
+        nb, ne, nv = int((c == 1).sum()), int((c > 2).sum()), len(ss.find_non_manifold_vertices(mesh))
+        return nb == 0, ne == 0 and nv == 0, ne, nv                            # closed, manifold, #non-manifold edges, #non-manifold vertices
+    assert info(one) == (False, True, 0, 0)                                    # test_tri_mesh_manifold_info
+    assert info(nm_edge) == (False, False, 1, 0)
+    assert info(nm_edge2) == (False, False, 1, 0)
+    assert info(nm_vert) == (False, False, 0, 1)
+    for mesh, closed_msg, manifold_msg in ((nm_edge, "not closed", "non-manifold edges"), (nm_vert, "not closed", "non-manifold vertices")):
+        text = ss.check_mesh_consistency(mesh, None, check_closed=True, check_manifold=True)
+        assert text is not None and closed_msg in text and manifold_msg in text
+        assert ss.check_mesh_consistency(mesh, None, check_closed=False, check_manifold=False) is None
+    box = ss.Aabb3d.from_min_max([0.0, 0.0, 0.0], [1.0, 1.0, 1.0])             # aabb.rs:277-291
+    for q, inside in (([.5, .5, .5], True), ([0, .5, .5], True), ([.5, 0, .5], True), ([.5, .5, 0], True), ([0, 0, 0], True), ([1, 0, 0], False),
+                      ([0, 1, 0], False), ([0, 0, 1], False), ([1, 1, 1], False)):
+        assert box.contains_point(q) == inside
