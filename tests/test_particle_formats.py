@@ -420,3 +420,39 @@ def test_reference_fixture_files_when_present(tmp_path):
         seen += 1
     assert seen >= 15
     assert len(pf.particles_from_file(os.path.join(d, "cube_8_particles.vtk"))) == 8 and len(pf.particles_from_file(os.path.join(d, "fluid_250_particles.vtu"))) == 250
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/data"), reason="reference checkout only exists in the build container")
+def test_reference_io_unit_tests(tmp_path):
+    """The unit tests inside the reference's io modules, on its own data files: bgeo_format.rs:864-967, vtk_format.rs:406-450, ply_format.rs:
+    274-310, obj_format.rs:168-192."""
+    d = "/root/reference/data"
+    # test_bgeo_read_dam_break / _attributes
+    path = os.path.join(d, "dam_break_frame_9_6859_particles.bgeo")
+    p, attrs = pf.read_bgeo(path)
+    assert len(p) == 6859 and len(attrs) == 3
+    lo, hi = p.min(axis=0), p.max(axis=0)
+    assert np.all(lo >= np.float32([-2.0, 0.03, -0.8])) and np.all(hi < np.float32([-0.3, 0.7, 0.72]))
+    a = pf.particle_attributes_from_file(path, ["id", "density", "velocity"])
+    assert a["id"].dtype == np.uint64 and a["density"].dtype == np.float32 and a["velocity"].shape == (6859, 3)
+    assert a["id"][:3].tolist() == [30, 11, 12]
+    assert a["density"][:3].tolist() == [np.float32(1000.1286), np.float32(1001.53424), np.float32(1001.6626)]
+    assert a["velocity"][0].tolist() == [np.float32(0.3670507), np.float32(-0.41762838), np.float32(0.42659923)]
+    # test_bgeo_write_dam_break: uncompressed write, read back
+    out = str(tmp_path / "w.bgeo")
+    pf.write_bgeo(out, p, enable_compression=False)
+    q = pf.read_bgeo(out)[0]
+    assert len(q) == 6859 and np.array_equal(q.view(np.uint32), p.view(np.uint32))
+    # vtk_format.rs:425-450
+    for name, n in (("cube_8_particles.vtu", 8), ("cube_8_particles.vtk", 8), ("double_dam_break_frame_01_4732_particles.vtk", 4732),
+                    ("fluid_encoded_250_particles.vtu", 250), ("fluid_250_particles.vtu", 250)):
+        assert len(pf.particles_from_file(os.path.join(d, name))) == n, name
+    # ply_format.rs:274-310
+    v, t, a = pf.read_ply_surface_mesh(os.path.join(d, "cube.ply"))
+    assert (len(v), len(t), list(a)) == (24, 12, [])
+    v, t, a = pf.read_ply_surface_mesh(os.path.join(d, "cube_normals.ply"))
+    assert (len(v), len(t)) == (24, 12) and a["normals"].shape == (24, 3)
+    # obj_format.rs:168-192
+    for name in ("icosphere.obj", "icosphere_normals.obj"):
+        v, t = io.read_obj(os.path.join(d, name))
+        assert (len(v), len(t)) == (42, 80) and int(t.max()) == 41
