@@ -97,3 +97,28 @@ def test_python_mirror_covers_the_public_names_of_pysplashsurf(ss, oracle_mod, t
         ss.run_splashsurf(["splashsurf", "convert", "--particles", src, "-o", dst])          # exists, no --overwrite
     a = ss.MeshAttribute("w", np.ones(3, np.float32))
     assert (a.name, a.dtype, a.data.shape) == ("w", np.float32, (3,))
+
+
+def test_cell_local_numbering_tables_of_the_kernels():
+    """uniform_grid.rs:806-930 (CELL_LOCAL_POINT_COORDS, CELL_LOCAL_EDGES and their consistency tests): the corner order behind the case index
+    and the (origin corner, axis) of the twelve local edges as the marching-cubes kernels hold them (csrc/ss_kernels.cuh, csrc/ss_mc.cuh)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "splashsurf_b200", "csrc", "ss_kernels.cuh")).read()
+    corners = [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)]      # CELL_LOCAL_POINT_COORDS
+    edges = [(0, 0), (1, 1), (3, 0), (0, 1), (4, 0), (5, 1), (7, 0), (4, 1), (0, 2), (1, 2), (2, 2), (3, 2)]  # CELL_LOCAL_EDGES (corner, axis)
+    m = re.search(r"c_edge_org\[12\]\[3\]\s*=\s*\{(.*?)\};", src, re.S)
+    org = [tuple(int(x) for x in g.split(",")) for g in re.findall(r"\{([^{}]*)\}", m.group(1))]
+    m = re.search(r"c_edge_axis\[12\]\s*=\s*\{(.*?)\};", src, re.S)
+    axis = [int(x) for x in m.group(1).split(",")]
+    assert org == [corners[c] for c, _ in edges] and axis == [a for _, a in edges]
+    # the case index sets bit v for corner v in exactly this order (ss_case_index)
+    body = src[src.index("__device__ __forceinline__ int ss_case_index"):]
+    body = body[:body.index("return idx;")]
+    seen = [tuple(int(x) for x in g) for g in re.findall(r"// corner \d \((\d),(\d),(\d)\)", body)]
+    assert seen == corners
+    # consistency tests of the reference: the flattened coordinate finds the corner, every edge starts at the corner with the lower coordinate
+    local_points = [0, 1, 3, 2, 4, 5, 7, 6]                                                                   # CELL_LOCAL_POINTS
+    for v, (x, y, z) in enumerate(corners):
+        assert local_points[x + 2 * y + 4 * z] == v
+    for c, a in edges:
+        assert corners[c][a] == 0
