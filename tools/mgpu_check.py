@@ -41,6 +41,27 @@ def main():
         runner.close()
         ctx.close()
         dist.barrier()
+        # the user-facing call (DistributedReconstructor): same mesh as the single-device call of rank 0, with a particle AABB and SPH normals
+        box = dict(aabb_min=(p_all.min(axis=0) - 0.05).tolist(), aabb_max=(np.quantile(p_all, 0.8, axis=0)).tolist())
+        rec = ssd.DistributedReconstructor(sph_normals=True, **kw, **box)
+        n = len(p_all)
+        mwd = rec(p_all[(n * rank) // world:(n * (rank + 1)) // world])
+        if rank == 0:
+            one = ss.reconstruct_surface(p_all, sph_normals=True, context=rec.ctx, **kw, **box)
+
+            def canon(v, t, nrm):
+                o = np.lexsort(v.T[::-1]); r = np.empty(len(v), np.int64); r[o] = np.arange(len(v))
+                t = r[np.asarray(t).astype(np.int64)]
+                t = np.stack([np.roll(row, -s) for row, s in zip(t, np.argmin(t, axis=1))]) if len(t) else t
+                return v[o], t[np.lexsort(t.T[::-1])] if len(t) else t, nrm[o]
+            has_n = "normals" in mwd.point_attributes          # (the CPU executor's host path gathers no normals)
+            a = canon(mwd.mesh.vertices, mwd.mesh.triangles, mwd.point_attributes["normals"] if has_n else one.normals * 0)
+            b = canon(one.mesh.vertices, one.mesh.triangles, one.normals if has_n else one.normals * 0)
+            good = np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32)) and np.array_equal(a[1], b[1]) and np.abs(a[2] - b[2]).max() <= 2e-5
+            print(f"[{name}] DistributedReconstructor world={world}: {len(a[0])} vertices, {len(a[1])} triangles, equal to the single-device call: {good}", flush=True)
+            ok &= bool(good)
+        rec.close()
+        dist.barrier()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
