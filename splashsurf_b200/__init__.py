@@ -759,7 +759,6 @@ def marching_cubes(values, *, iso_surface_threshold: float, cube_size: float, tr
         # (:108-126) -- the kernels per POINT.  Where the two differ the reference either builds another mesh or stops with the error
         # above: refuse instead of returning a mesh the reference would not return.
         eq = tiles == thr
-        cells = (slice(None), slice(0, -1), slice(0, -1), slice(0, -1))
         for ca in (0, 1):
             for cb in (0, 1):
                 for cc in (0, 1):
@@ -771,7 +770,6 @@ def marching_cubes(values, *, iso_surface_threshold: float, cube_size: float, tr
                         raise SplashsurfError(SS_ERR_UNSUPPORTED, "a value equal to the iso-surface threshold sits where the reference decides inside / "
                                               "outside per cell (narrow_band_extraction.rs:108-126): this degenerate configuration is not triangulated "
                                               "here -- move the threshold (or the values) by one ulp")
-        del cells
     ijk = np.ascontiguousarray(np.asarray(ijk, dtype=np.int32).reshape(-1, 3))
     s = C.c_void_p()
     _check(L, L.ss_marching_cubes_tiles_f32(ctx._h, tiles.ctypes.data if len(tiles) else None, len(tiles), ijk.ctypes.data if len(tiles) else None,

@@ -239,9 +239,7 @@ def parse_ply(path: str):
     for name, count, props in elements:
         cols = {}
         if all(p[2] is None for p in props):
-            dt = np.dtype({"names": [p[0] for p in props], "formats": [bo + p[1] for p in props],
-                           "offsets": np.cumsum([0] + [np.dtype(p[1]).itemsize for p in props[:-1]]).tolist() if props else []}) if len({p[0] for p in props}) == len(props) \
-                else np.dtype([(f"f{j}", bo + p[1]) for j, p in enumerate(props)])
+            dt = np.dtype([(f"f{j}", bo + p[1]) for j, p in enumerate(props)])          # packed records, fields by position
             if len(b) < o + count * dt.itemsize:
                 raise ValueError(f"Failed to parse PLY file: element '{name}' is truncated")
             rec = np.frombuffer(b, dtype=dt, count=count, offset=o)
