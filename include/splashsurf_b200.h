@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SS_ABI_VERSION 2
+#define SS_ABI_VERSION 3   /* 3: + ss_sph_interpolator_* / ss_neighborhood_search_f32 / ss_marching_cubes_tiles_f32 (additive) */
 
 /* Error codes.  1..7 mirror ReconstructionError / GridConstructionError
  * (splashsurf_lib/src/lib.rs:289-314, uniform_grid.rs:147-169); the reference's panics on a non-positive

@@ -171,7 +171,7 @@ def _bind(L):
                                     C.POINTER(_MeshAttribute), C.c_uint32, C.c_uint32]
     L.ss_format_f32.argtypes = [C.c_float, C.c_char_p, u64]
     L.ss_meshio_set_chunk_items.argtypes = [u64]
-    if L.ss_abi_version() != 2:
+    if L.ss_abi_version() != 3:
         raise ImportError("libsplashsurf_b200.so ABI version mismatch")
     return L
 

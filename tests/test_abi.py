@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol(ss):
     assert "ss_reconstruct_surface_f32" in names and "ss_levelset_tile_f32" in names and len(names) >= 25
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/splashsurf_b200.h but not exported"
-    assert L.ss_abi_version() == 2
+    assert L.ss_abi_version() == 3
 
 
 def test_params_struct_layout_matches_header(ss):
