@@ -225,7 +225,7 @@ class Runner:
         if protocol not in ("stats", "two_call", "callback"):
             raise ValueError("protocol must be 'stats', 'two_call' or 'callback'")
         self.protocol = protocol
-        self._out_v = self._out_t = None
+        self._out_v = self._out_t = self._out_n = None
         self._seg = None; self._seg_path = None; self._seg_gen = 0; self._seg_registered = False; self._layout = None
         self.want_keys = False           # also publish the MC edge keys of the assembled vertices (parity tools)
         self.ctx_normals = False         # set by the caller when ss_context_set_compute_sph_normals is on: normals join the assembled mesh
@@ -245,7 +245,9 @@ class Runner:
     def gathered_normals(self):
         """Host copy of the SPH normals of the last assembled mesh (None when they were not computed / not gathered)."""
         lay = getattr(self, "_layout", None)
-        if lay is None or not lay[3] or self.device.type != "cuda":
+        if lay is None:                                      # single-GPU / small-domain path
+            return getattr(self, "_out_n", None)
+        if not lay[3] or self.device.type != "cuda":
             return None
         nvg, ntg, want_keys, _ = lay
         nbase = ((nvg * 12 + ntg * 12 + 7) // 8 * 8) + (nvg * 8 if want_keys else 0)
@@ -266,15 +268,15 @@ class Runner:
         return np.ascontiguousarray(particles[lo:hi])
 
     # -- single GPU
-    def _step_single(self, xyz_ptr: int, n: int, copy_out: bool, params=None) -> dict:
+    def _step_single(self, xyz_ptr: int, n: int, copy_out: bool, params=None, force_copy: bool = False) -> dict:
         L = self.ctx._L
         s = self.ctx.reconstruct_raw(xyz_ptr, n, self.params if params is None else params)
         try:
-            return self._collect(s, copy_out, n_local=n)
+            return self._collect(s, copy_out, n_local=n, force_copy=force_copy)
         finally:
             self.ctx.free_surface(s)
 
-    def _collect(self, s, copy_out: bool, n_local: int, extra_ms: float = 0.0) -> dict:
+    def _collect(self, s, copy_out: bool, n_local: int, extra_ms: float = 0.0, force_copy: bool = False) -> dict:
         L = self.ctx._L
         tm = self.ctx.timings(s)
         nv, nt = L.ss_surface_num_vertices(s), L.ss_surface_num_triangles(s)
@@ -287,7 +289,8 @@ class Runner:
             L.ss_surface_copy_subdomain_owned(s, owned.ctypes.data)
         out["memberships"] = float(cnt[owned.astype(bool)].sum())
         out["nsub_owned"] = int(owned.sum())
-        if copy_out and self.world == 1:
+        if copy_out and (self.world == 1 or force_copy):          # (force_copy: the small-domain path of a multi-rank run, rank 0 holds the mesh)
+            self._layout = None
             if self._out_v is None or self._out_v.numel() < nv * 3:
                 self._out_v = _pinned(torch.empty(max(nv * 3, 1), dtype=torch.float32), self.device)
             if self._out_t is None or self._out_t.numel() < nt * 3:
@@ -297,6 +300,12 @@ class Runner:
             if rc:
                 raise RuntimeError("mesh copy-out failed")
             out["d2h_bytes"] = nv * 12 + nt * 12
+            self._out_n = None
+            if force_copy and self.ctx_normals and L.ss_surface_device_normals(s):      # (the bench's single-GPU e2e reading stays as measured)
+                self._out_n = np.empty((nv, 3), dtype=np.float32)
+                if nv and L.ss_surface_copy_normals(s, C.c_void_p(self._out_n.ctypes.data)):
+                    raise RuntimeError("normal copy-out failed")
+                out["d2h_bytes"] += nv * 12
         return out
 
     # -- public step: `x` is this rank's (n, 3) float32 tensor (cuda, or pinned host for the end-to-end path)
@@ -508,7 +517,8 @@ class Runner:
         dist.all_gather(bufs, buf, group=self.group)
         allp = torch.cat([bufs[r][:sizes[r]] for r in range(world)]).contiguous()
         _sync(dev)
-        out = self._step_single(allp.data_ptr(), allp.shape[0] if rank == 0 else 0, copy_out and rank == 0, params=self.grid_params)
+        out = self._step_single(allp.data_ptr(), allp.shape[0] if rank == 0 else 0, copy_out and rank == 0, params=self.grid_params,
+                                force_copy=True)
         t_ev[2].record(); _sync(dev)
         out["device_ms"] = t_ev[0].elapsed_time(t_ev[2])
         out["recv_particles"] = int(allp.shape[0]) if rank == 0 else 0

@@ -473,6 +473,16 @@ def test_emulated_cli_partitioned_frames_over_gloo(emu, tmp_path):
             t = np.stack([np.roll(row, -s) for row, s in zip(t, k)]) if len(t) else t
             return t[np.lexsort(t.T[::-1])]
         assert np.array_equal(canon(t1, r1), canon(t2, r2))
+    # a domain at most 1.2 subdomains wide with auto-disable on (lib.rs:421-440): rank 0 reconstructs the gathered cloud on the global path
+    # and holds the mesh (+ SPH normals); same file as the single-process command line
+    small = ["reconstruct", str(frames / "dam_1.bgeo"), "-r=0.025", "-l=2.0", "-c=1.5", "--subdomain-grid-auto-disable=off", "--normals=on", "--sph-normals=on",
+             "-q", "-o", "small.ply"]
+    assert cli.main(small + ["--output-dir", str(tmp_path / "one")]) == 0
+    r = subprocess.run(cmd[:cmd.index(str(script)) + 1] + small + ["--partition=on", "--output-dir", str(tmp_path / "two")], env=env, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    a, b = io.read_ply_mesh(str(tmp_path / "one" / "small.ply")), io.read_ply_mesh(str(tmp_path / "two" / "small.ply"))
+    assert len(a[0]) > 100 and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[3]["normals"], b[3]["normals"])
     # post-processing is a single-GPU step: refused with a clear message
     r = subprocess.run(cmd + ["--mesh-smoothing-iters=2"], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and "--partition=on reconstructs without mesh post-processing" in r.stderr
