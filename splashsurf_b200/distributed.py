@@ -740,6 +740,10 @@ class DistributedReconstructor:
             return ss.MeshWithData(r.mesh, {"normals": r.normals} if self.sph_normals and r.normals is not None else {}, {})
         if self._aabb is not None:                    # lib.rs:369-406: particles outside the half-open box take no part
             p = np.ascontiguousarray(p[np.all(p >= self._aabb[0], axis=1) & np.all(p < self._aabb[1], axis=1)])
+        total = torch.tensor([len(p)], dtype=torch.int64, device=self.runner.device)
+        dist.all_reduce(total, group=self.runner.group)
+        if int(total.item()) == 0:                    # no particle anywhere: an empty mesh, like the single-device call returns
+            return ss.MeshWithData(ss.TriMesh3d(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint64)), {}, {}) if self.rank == 0 else None
         x = torch.from_numpy(p)                       # pageable: the runner's upload stages it (a page-locked tensor is taken as it is)
         out = self.runner.step(x, copy_out=True)
         if self.rank != 0:

@@ -488,6 +488,48 @@ def test_emulated_cli_partitioned_frames_over_gloo(emu, tmp_path):
     assert r.returncode != 0 and "--partition=on reconstructs without mesh post-processing" in r.stderr
 
 
+API_EDGE_WORKER = r'''
+import ctypes as C, json, os, sys
+import numpy as np, torch.distributed as dist
+sys.path.insert(0, os.environ["SS_ROOT"])
+import splashsurf_b200 as ss
+ss._LIB = ss._bind(C.CDLL(os.environ["SS_EMUL_SO"]))
+from splashsurf_b200.distributed import DistributedReconstructor
+dist.init_process_group("gloo")
+rank = dist.get_rank()
+rec = DistributedReconstructor(device="cpu", particle_radius=0.025, smoothing_length=2.0, cube_size=0.5, subdomain_grid_auto_disable=False)
+out = {}
+for name, p in (("empty", np.zeros((0, 3), np.float32)),
+                ("one_rank_empty", np.random.default_rng(0).random((300 if rank == 0 else 0, 3)).astype(np.float32) * np.float32(0.4)),
+                ("two_particles", np.float32([[0, 0, 0]] if rank == 0 else [[3, 3, 3]]))):
+    m = rec(p)
+    out[name] = None if m is None else [m.nvertices, m.ncells]
+rec.close()
+json.dump(out, open(os.path.join(os.environ["SS_OUT"], f"edge{rank}.json"), "w"))
+dist.destroy_process_group()
+'''
+
+
+def test_emulated_distributed_reconstructor_edge_cases_over_gloo(emu, tmp_path):
+    """DistributedReconstructor with nothing to do on some or all ranks: an empty cloud gives an empty mesh on rank 0 (like the single-device
+    call), a rank without particles takes part in every collective, two far-apart particles on two ranks give the single-device mesh."""
+    import json
+    import sys
+    script = tmp_path / "worker.py"
+    script.write_text(API_EDGE_WORKER)
+    env = dict(os.environ, SS_ROOT=ROOT, SS_OUT=str(tmp_path), SS_EMUL_SO=build_emulated_library(), SS_EMUL_THREADS="3", OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port",
+           str(free_port()), str(script)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r0, r1 = json.load(open(tmp_path / "edge0.json")), json.load(open(tmp_path / "edge1.json"))
+    assert r1 == {"empty": None, "one_rank_empty": None, "two_particles": None}
+    kw = dict(particle_radius=0.025, smoothing_length=2.0, cube_size=0.5, subdomain_grid_auto_disable=False)
+    one = emu.reconstruct_surface(np.random.default_rng(0).random((300, 3)).astype(np.float32) * np.float32(0.4), **kw)
+    two = emu.reconstruct_surface(np.float32([[0, 0, 0], [3, 3, 3]]), **kw)
+    assert r0 == {"empty": [0, 0], "one_rank_empty": [one.mesh.nvertices, one.mesh.ncells], "two_particles": [two.mesh.nvertices, two.mesh.ncells]}
+
+
 FAIL_WORKER = r'''
 import ctypes as C, json, os, sys
 import numpy as np, torch, torch.distributed as dist, datetime
