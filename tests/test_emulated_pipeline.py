@@ -639,8 +639,8 @@ def test_emulated_cli_sequence_equals_library_calls(emu, tmp_path):
 
 
 def test_emulated_reference_python_tests(emu, tmp_path, oracle_mod):
-    """pysplashsurf/tests/*.py against `import splashsurf_b200 as pysplashsurf` on the CPU executor (tests/test_zzzz_pysplashsurf_tests.py)."""
-    from test_zzzz_pysplashsurf_tests import run_all
+    """pysplashsurf/tests/*.py against `import splashsurf_b200 as pysplashsurf` on the CPU executor (tests/test_zzzzz_pysplashsurf_tests.py)."""
+    from test_zzzzz_pysplashsurf_tests import run_all
     run_all(emu, tmp_path, oracle_mod)
 
 

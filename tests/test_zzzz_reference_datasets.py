@@ -154,11 +154,6 @@ def check_sph_interpolator(ss, oracle_mod):
     ctx.close()
 
 
-@pytest.mark.gpu
-def test_cuda_sph_interpolator_at_arbitrary_points(ss, oracle_mod):
-    check_sph_interpolator(ss, oracle_mod)
-
-
 # ---- stand-alone neighbourhood search (neighborhood_search.rs:444-588; pysplashsurf/tests/test_basic.py:150-182): the reference's hand
 # cases, a random cloud against a k-d tree and against the wheel's function, the lists of the reconstruction itself
 def check_neighborhood_search(ss, oracle_mod):
@@ -209,11 +204,6 @@ def check_neighborhood_search(ss, oracle_mod):
         ss.neighborhood_search_spatial_hashing_parallel(p, ss.Aabb3d(np.float32([0, 0, 0]), np.float32([0.2, 0.2, 0.2])), sr)
     with pytest.raises(ss.SplashsurfError, match="search radius must be positive"):
         ss.neighborhood_search_spatial_hashing_parallel(p, rec.grid.aabb, 0.0)
-
-
-@pytest.mark.gpu
-def test_cuda_neighborhood_search_stand_alone(ss, oracle_mod):
-    check_neighborhood_search(ss, oracle_mod)
 
 
 # ---- marching cubes on a dense array (pysplashsurf.marching_cubes = marching_cubes::triangulate_density_map): the reference's one-cell
@@ -306,11 +296,6 @@ def check_marching_cubes(ss, oracle_mod):
         ss.marching_cubes(np.zeros((4, 4, 4), np.float32), iso_surface_threshold=0.0, cube_size=0.0)
 
 
-@pytest.mark.gpu
-def test_cuda_marching_cubes_on_a_dense_array(ss, oracle_mod):
-    check_marching_cubes(ss, oracle_mod)
-
-
 # ---- the command line on the device: a frame sequence on one context (pooled buffers reused from frame to frame), files equal to what the
 # library calls give frame by frame
 def check_cli_sequence(ss, tmp_path):
@@ -330,11 +315,6 @@ def check_cli_sequence(ss, tmp_path):
                                              subdomain_grid_auto_disable=False)
         assert np.array_equal(v, mesh.mesh.vertices) and np.array_equal(t.astype(np.uint64), mesh.mesh.triangles.astype(np.uint64))
         assert np.array_equal(attrs["normals"], mesh.point_attributes["normals"])
-
-
-@pytest.mark.gpu
-def test_cuda_cli_frame_sequence(ss, tmp_path):
-    check_cli_sequence(ss, tmp_path)
 
 
 # ---- tests/integration_tests/test_simple.rs:68-126: one particle whose only surface-crossing edges run from a point above the threshold to a
@@ -357,3 +337,24 @@ def test_oracle_test_simple(oracle_mod):
 @pytest.mark.gpu
 def test_cuda_test_simple(ss):
     check_test_simple(ss.reconstruct_surface, ss)
+
+
+# ---- GPU-marked wrappers of the entries added after the last GPU session: last in the file (the suite runs with -x)
+@pytest.mark.gpu
+def test_cuda_sph_interpolator_at_arbitrary_points(ss, oracle_mod):
+    check_sph_interpolator(ss, oracle_mod)
+
+
+@pytest.mark.gpu
+def test_cuda_neighborhood_search_stand_alone(ss, oracle_mod):
+    check_neighborhood_search(ss, oracle_mod)
+
+
+@pytest.mark.gpu
+def test_cuda_marching_cubes_on_a_dense_array(ss, oracle_mod):
+    check_marching_cubes(ss, oracle_mod)
+
+
+@pytest.mark.gpu
+def test_cuda_cli_frame_sequence(ss, tmp_path):
+    check_cli_sequence(ss, tmp_path)

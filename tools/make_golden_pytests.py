@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """tests/golden/pysplashsurf_tests.npz: the particle files of the reference's own Python tests (pysplashsurf/tests/ParticleData_Random_1000.vtk,
 ParticleData_Fluid_5.vtk with its `velocity` / `id` point data, ParticleData_Fluid_50.bgeo) read with this package's readers, so that
-tests/test_zzzz_pysplashsurf_tests.py -- those tests, re-run against `import splashsurf_b200 as pysplashsurf` -- also runs on the GPU box."""
+tests/test_zzzzz_pysplashsurf_tests.py -- those tests, re-run against `import splashsurf_b200 as pysplashsurf` -- also runs on the GPU box."""
 import os
 import sys
 
