@@ -318,5 +318,15 @@ def reconstruct(a) -> int:
     return 0
 
 
+def _entry() -> int:
+    """Process entry point: errors become one line on stderr and exit code 1 (the reference binary logs `Error occurred: ...`)."""
+    from . import SplashsurfError
+    try:
+        return main()
+    except (ValueError, OSError, SplashsurfError, NotImplementedError) as e:
+        print(f"Error occurred: {e}", file=sys.stderr)
+        return 1
+
+
 if __name__ == "__main__":
-    sys.exit(main())
+    sys.exit(_entry())
