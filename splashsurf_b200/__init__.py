@@ -6,6 +6,8 @@ same RELATIVE ``smoothing_length`` / ``cube_size`` convention (both are multipli
 reconstruction.rs:172-176), same result attributes (``mesh.vertices`` (V,3) float32, ``mesh.triangles``
 (T,3) uint64, ``particle_densities``, ``grid``, ``subdomain_grid``, ``particle_inside_aabb``).
 
+The module mirrors every public name of ``pysplashsurf`` (``import splashsurf_b200 as pysplashsurf``; INTEGRATION.md lists what differs).
+
 All compute happens in ``libsplashsurf_b200.so`` (hand-written sm_100a CUDA behind the C ABI declared in
 ``include/splashsurf_b200.h``).  There is no CPU fallback: a missing library or a missing GPU raises.
 """
@@ -21,8 +23,12 @@ import numpy as np
 
 from . import build as _build
 
-__all__ = ["reconstruct_surface", "reconstruction_pipeline", "MeshWithData", "density_grid_loop", "Context", "SurfaceReconstruction", "TriMesh3d", "UniformGrid", "Aabb3d",
-           "SplashsurfError", "library_path", "load_library"]
+# every public name of the reference's Python module (tests/test_abi.py) + the extras of this package
+__all__ = ["reconstruct_surface", "reconstruction_pipeline", "marching_cubes", "marching_cubes_cleanup", "barnacle_decimation", "convert_tris_to_quads",
+           "laplacian_smoothing_parallel", "laplacian_smoothing_normals_parallel", "check_mesh_consistency", "neighborhood_search_spatial_hashing_parallel",
+           "SphInterpolator", "run_splashsurf", "run_pysplashsurf", "TriMesh3d", "MixedTriQuadMesh3d", "MeshWithData", "MeshAttribute", "MeshType",
+           "SurfaceReconstruction", "UniformGrid", "Aabb3d", "NeighborhoodLists", "VertexVertexConnectivity",
+           "density_grid_loop", "write_mesh", "Context", "default_context", "make_params", "SplashsurfError", "library_path", "load_library"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
