@@ -462,17 +462,9 @@ def test_emulated_cli_partitioned_frames_over_gloo(emu, tmp_path):
         v1, t1 = io.read_vtk_mesh(str(tmp_path / "one" / f))[:2]
         v2, t2 = io.read_vtk_mesh(str(tmp_path / "two" / f))[:2]
         assert len(v1) == len(v2) > 1000 and len(t1) == len(t2)
-        o1, o2 = np.lexsort(v1.T[::-1]), np.lexsort(v2.T[::-1])
-        assert np.array_equal(v1[o1].view(np.uint32), v2[o2].view(np.uint32))                   # the same vertices, bit for bit
-        r1, r2 = np.empty(len(v1), np.int64), np.empty(len(v2), np.int64)
-        r1[o1], r2[o2] = np.arange(len(v1)), np.arange(len(v2))
-
-        def canon(t, rk):
-            t = rk[t.astype(np.int64)]
-            k = np.argmin(t, axis=1)
-            t = np.stack([np.roll(row, -s) for row, s in zip(t, k)]) if len(t) else t
-            return t[np.lexsort(t.T[::-1])]
-        assert np.array_equal(canon(t1, r1), canon(t2, r2))
+        from test_zzzz_reference_datasets import _canonical_mesh
+        a, b = _canonical_mesh(v1, t1), _canonical_mesh(v2, t2)
+        assert np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32)) and np.array_equal(a[1], b[1])     # the same vertices bit for bit, the same triangles
     # a domain at most 1.2 subdomains wide with auto-disable on (lib.rs:421-440): rank 0 reconstructs the gathered cloud on the global path
     # and holds the mesh (+ SPH normals); same file as the single-process command line
     small = ["reconstruct", str(frames / "dam_1.bgeo"), "-r=0.025", "-l=2.0", "-c=1.5", "--subdomain-grid-auto-disable=off", "--normals=on", "--sph-normals=on",

@@ -210,9 +210,14 @@ def check_neighborhood_search(ss, oracle_mod):
 # known-answer test (marching_cubes.rs:325-396), its sphere-SDF test (pysplashsurf/tests/test_sdf.py) and random fields of awkward shapes
 # (borders with values on both sides of the threshold, arrays that do not fill whole tiles) against the wheel's function
 def _canonical_mesh(v, t):
+    """Vertices sorted by position; triangles in terms of the sorted positions (coincident vertices -- an interpolation weight that rounds to
+    0 puts two vertices of neighbouring edges on the same grid point -- share one number, so their order cannot matter), rotated to their
+    smallest number and sorted."""
     o = np.lexsort(v.T[::-1])
     rank = np.empty(len(v), np.int64)
-    rank[o] = np.arange(len(v))
+    vs = v[o].view(np.uint32).reshape(-1, 3) if len(v) else np.zeros((0, 3), np.uint32)
+    group = np.cumsum(np.r_[True, (vs[1:] != vs[:-1]).any(axis=1)]) - 1 if len(v) else np.zeros(0, np.int64)
+    rank[o] = group
     t = rank[np.asarray(t).astype(np.int64)]
     if len(t):
         t = np.stack([np.roll(row, -s) for row, s in zip(t, np.argmin(t, axis=1))])

@@ -50,7 +50,9 @@ def main():
             one = ss.reconstruct_surface(p_all, sph_normals=True, context=rec.ctx, **kw, **box)
 
             def canon(v, t, nrm):
-                o = np.lexsort(v.T[::-1]); r = np.empty(len(v), np.int64); r[o] = np.arange(len(v))
+                o = np.lexsort(v.T[::-1]); r = np.empty(len(v), np.int64)
+                vs = v[o].view(np.uint32).reshape(-1, 3)
+                r[o] = np.cumsum(np.r_[True, (vs[1:] != vs[:-1]).any(axis=1)]) - 1        # coincident vertices share a number
                 t = r[np.asarray(t).astype(np.int64)]
                 t = np.stack([np.roll(row, -s) for row, s in zip(t, np.argmin(t, axis=1))]) if len(t) else t
                 return v[o], t[np.lexsort(t.T[::-1])] if len(t) else t, nrm[o]
